@@ -1,0 +1,75 @@
+"""Pins the CPU oracle to the reference's own golden files.
+
+The goldens print 7 significant digits; the reference's test compares with abs tol 1e-10
+(tests/common.h:30-89).  The oracle solves tighter than the reference (1e-7), so agreement is
+limited by the reference's own solver tolerance: compare to 2e-6 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import oracle as O
+
+
+def _run(scheme, steps, curl_sign=-1):
+    o = O.Oracle((10, 10, 10), d=(0.5, 0.5, 0.5), dt=1.5, curl_sign=curl_sign)
+    sid = o.add_species(q=-1.0, m=1.0, n=1.0, Np=100)
+    assert o.set_particles_maxwell(sid, T=0.1, tov=True) == 100000
+    o.solver_set(0, 1e-12, 1e-50, 500, 30)
+    o.solver_set(1, 1e-12, 1e-50, 500, 30)
+    rows = [(0.0, 0.0, o.scalar("energy"))]
+    extra = []
+    for _ in range(steps):
+        o.step(scheme)
+        wE, wB = o.field_energies()
+        rows.append((wE, wB, o.scalar("energy")))
+        extra.append(o.scalar("lambda_dK"))
+    return o, np.array(rows), np.array(extra)
+
+
+def test_initial_kinetic_energy_matches_golden():
+    o = O.Oracle((10, 10, 10))
+    sid = o.add_species()
+    o.set_particles_maxwell(sid, 0.1, True)
+    _, gold = O.read_table(os.path.join(GOLDEN, "ecsim_ex1", "energy.txt"))
+    assert f"{o.scalar('energy'):.6e}" == f"{gold[0, 3]:.6e}" == "2.923693e-01"
+
+
+def test_ecsim_energy_rows_match_golden():
+    steps = 12
+    _, rows, _ = _run(O.ECSIM, steps)
+    _, gold = O.read_table(os.path.join(GOLDEN, "ecsim_ex1", "energy.txt"))
+    np.testing.assert_allclose(rows, gold[: steps + 1, 1:4], rtol=2e-6, atol=1e-10)
+    # row 1 is independent of the curl sign and must match to every printed digit
+    assert [f"{v:.6e}" for v in rows[1]] == ["4.682143e-04", "1.136926e-04", "2.917873e-01"]
+    # energy conservation at solver tolerance (golden ~2e-13 with the reference's 1e-7 solve)
+    tot = rows.sum(axis=1)
+    assert np.max(np.abs(np.diff(tot))) < 1e-12
+
+
+def test_ecsim_as_read_sign_differs_from_golden_after_step1():
+    # documents the sign question: sources-as-read (+1) match row 1 only
+    _, rows, _ = _run(O.ECSIM, 2, curl_sign=+1)
+    _, gold = O.read_table(os.path.join(GOLDEN, "ecsim_ex1", "energy.txt"))
+    np.testing.assert_allclose(rows[1], gold[1, 1:4], rtol=2e-6)
+    assert abs(rows[2, 0] - gold[2, 1]) > 1e-8
+
+
+def test_ecsimcorr_rows_match_golden():
+    steps = 8
+    _, rows, cwd = _run(O.ECSIMCORR, steps)
+    _, gold = O.read_table(os.path.join(GOLDEN, "ecsimcorr_ex1", "energy.txt"))
+    np.testing.assert_allclose(rows, gold[: steps + 1, 1:4], rtol=2e-6, atol=1e-10)
+    _, gc = O.read_table(os.path.join(GOLDEN, "ecsimcorr_ex1", "energy_conservation.txt"))
+    np.testing.assert_allclose(cwd, gc[1 : steps + 1, 4], rtol=5e-6)
+
+
+@pytest.mark.slow
+def test_ecsim_field_dump_t50():
+    o, _, _ = _run(O.ECSIM, 50)
+    for name in ("E", "B"):
+        g = np.fromfile(os.path.join(GOLDEN, "ecsim_ex1", f"{name}_050.f32"), dtype=np.float32).astype(np.float64)
+        f = o.get_field(name)
+        assert np.linalg.norm(f - g) / np.linalg.norm(g) < 5e-6
