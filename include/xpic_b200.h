@@ -1,0 +1,159 @@
+/* xpic_b200.h -- C ABI of the B200-native ECSIM / ECSIMCorr step.
+ *
+ * xpic (vakurshakov/xpic) has no FFI boundary of its own: a scheme is a C++ subclass compiled
+ * into libxpic.so.  This header is the seam a maintainer binds instead (INTEGRATION.md shows
+ * the shim): every entry point names the reference member it replaces (file:line relative to
+ * the reference tree).  Plain pointers and sizes only; all functions return 0 on success and a
+ * non-zero code otherwise (the PetscErrorCode convention, src/interfaces/simulation.h:59,71-72),
+ * with a message available from xb_last_error().  One context per rank / GPU; a context is not
+ * thread-safe; no exception crosses the ABI.  All arithmetic is fp64, indices int32/int64.
+ *
+ * There is no CPU fallback: xb_create fails when no CUDA device is usable.
+ */
+#ifndef XPIC_B200_H
+#define XPIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xb_ctx xb_ctx;
+
+/* Geometry of the periodic box and of this rank's z-slab.
+ * Replaces World::initialize (src/utils/world.cpp:11-48) + the globals of src/constants.h:10-28.
+ * The slab decomposition mirrors DMDA with -da_processors_z nranks (utils/configuration.cpp:111-130):
+ * rank r owns planes [z0, z0+nzl) of every field, natural [z][y][x][c] order inside. */
+typedef struct xb_grid {
+  int32_t n[3];      /* global cells Nx, Ny, Nz (geom_nx.., src/constants.h:21-24) */
+  double d[3];       /* dx, dy, dz */
+  double dt;         /* time step */
+  int32_t curl_sign; /* +1 = sources as read; -1 reproduces the golden files of tests/ecsim, tests/ecsimcorr */
+  int32_t device;    /* CUDA device ordinal */
+  int32_t rank;      /* z-slab index */
+  int32_t nranks;    /* number of z-slabs (1 = single GPU) */
+  int32_t track_ids; /* 1: carry a 64-bit particle id (parity / diagnostics), 0: do not */
+} xb_grid;
+
+enum { XB_ECSIM = 0, XB_ECSIMCORR = 1 }; /* "Simulation" key, src/interfaces/simulation.cpp:169-178 */
+
+/* Named vectors: Simulation::E,B,B0 (src/interfaces/simulation.h:33-45, get_named_vector :135-143),
+ * ecsim Ep,currI (src/impls/ecsim/simulation.h:27-28), ecsimcorr Ec,currJe
+ * (src/impls/ecsimcorr/simulation.h:16-17), per-sort Particles::currI / currJe
+ * (src/impls/ecsim/particles.h:22, src/impls/ecsimcorr/particles.h:22). */
+enum { XB_E = 0, XB_B = 1, XB_B0 = 2, XB_EP = 3, XB_EC = 4, XB_CURRI = 5, XB_CURRJE = 6, XB_CURRI_SORT = 7, XB_CURRJE_SORT = 8 };
+
+/* Stages of timestep_implementation (src/impls/ecsim/simulation.cpp:145-155,
+ * src/impls/ecsimcorr/simulation.cpp:21-32); same names as the PETSc log stages :495-508. */
+enum {
+  XB_STAGE_CLEAR_SOURCES = 0,
+  XB_STAGE_FIRST_PUSH = 1,   /* push + re-binning + moments (current, mass matrices) */
+  XB_STAGE_ADVANCE_FIELDS = 2, /* "Advance field" / "Predict field" */
+  XB_STAGE_SECOND_PUSH = 3,
+  XB_STAGE_CORRECT_FIELDS = 4, /* ecsimcorr only */
+  XB_STAGE_FINAL_UPDATE = 5,
+  XB_STAGE_COUNT = 6
+};
+
+enum { XB_SOLVER_PREDICT = 0, XB_SOLVER_CORRECT = 1 }; /* ecsim `ksp` / ecsimcorr `predict`,`correct` */
+
+/* xb_scalar selectors: ecsimcorr::Particles members read by ecsimcorr::Energy
+ * (src/impls/ecsimcorr/simulation.cpp:169-197) and Energy::calculate_kinetic (diagnostics/energy.cpp:61-107) */
+enum { XB_KINETIC = 0, XB_PRED_W = 1, XB_CORR_W = 2, XB_PRED_DK = 3, XB_CORR_DK = 4, XB_LAMBDA_DK = 5, XB_ENERGY_MEMBER = 6, XB_J_DIFF_NORM = 7 };
+
+/* Operator selectors for xb_spmv*: bit 0 = particle mass matrix L (matL), bit 1 = constant
+ * M = 2I + dt^2/2 curl curl (matM, src/impls/ecsim/simulation.cpp:544-552); 3 = A = L + M. */
+enum { XB_OP_L = 1, XB_OP_M = 2, XB_OP_A = 3 };
+
+const char* xb_last_error(void);
+int xb_version(void);
+
+/* Number of fixed-offset coefficients per cell of the stencil-layout operator (369). */
+int xb_operator_ncoef(void);
+/* Describe coefficient k: row component c1, column component c2 and column offset (dx,dy,dz). */
+int xb_operator_coef_info(int k, int* c1, int* c2, int* dx, int* dy, int* dz);
+
+/* ncclUniqueId for a multi-rank run (128 bytes), produced on rank 0 and passed to every
+ * rank's xb_create (replaces MPI_Init / PETSC_COMM_WORLD, src/main.cpp:12). */
+int xb_comm_unique_id(void* out128);
+
+/* World::initialize + Simulation::initialize_implementation (src/impls/ecsim/simulation.cpp:122-143):
+ * device vectors, Yee curls, solver defaults (rtol = atol = 1e-7, maxit 100, src/impls/ecsim/simulation.h:15-18). */
+int xb_create(const xb_grid* grid, const void* comm_unique_id, xb_ctx** out);
+/* Simulation::finalize (src/impls/ecsim/simulation.cpp:569-590) */
+int xb_destroy(xb_ctx* ctx);
+
+/* interfaces::Simulation::init_particles, one call per "Particles" JSON entry
+ * (src/interfaces/simulation.tpp:7-79).  capacity = max particles this rank may ever hold. */
+int xb_species_add(xb_ctx* ctx, double q, double m, double n, int32_t Np, int64_t capacity, int32_t* sid);
+
+/* interfaces::Particles::add_particle (src/interfaces/particles.cpp:47-57): host AoS Points
+ * {r[3], p[3]} (48 B each); points outside this rank's slab are skipped; *added = number kept.
+ * ids may be NULL (then ids continue from the species' running counter). */
+int xb_particles_append(xb_ctx* ctx, int32_t sid, const double* aos6, const uint64_t* ids, int64_t count, int64_t* added);
+int xb_particles_count(xb_ctx* ctx, int32_t sid, int64_t* count);
+/* Host mirror of interfaces::Particles::storage (src/interfaces/particles.h:32), cell-major order. */
+int xb_particles_download(xb_ctx* ctx, int32_t sid, double* aos6, uint64_t* ids, int64_t capacity, int64_t* count);
+
+/* Owned z-slab of a named vector, natural [z][y][x][c] order, 3*Nx*Ny*nzl doubles
+ * (VecGetArray / VecView of a DMDA global vector, e.g. diagnostics/field_view.cpp:98-118). */
+int xb_field_upload(xb_ctx* ctx, int32_t which, int32_t sid, const double* host);
+int xb_field_download(xb_ctx* ctx, int32_t which, int32_t sid, double* host);
+
+/* KSPSetTolerances / -ksp_rtol etc. (src/impls/ecsim/simulation.cpp:558-567, ecsimcorr :114-136).
+ * precond: 0 none, k>0 Chebyshev polynomial of degree k in the constant operator M. */
+int xb_solver_set(xb_ctx* ctx, int32_t which, double rtol, double atol, int32_t maxit, int32_t restart, int32_t precond);
+/* KSPGetIterationNumber / KSPGetResidualNorm / KSPGetConvergedReason (reason > 0 converged). */
+int xb_solver_info(xb_ctx* ctx, int32_t which, int32_t* iterations, double* rnorm, int32_t* reason);
+
+/* Simulation::timestep_implementation (ecsim/simulation.cpp:145, ecsimcorr/simulation.cpp:21).
+ * Returns non-zero when a solve does not converge (KSPSetErrorIfNotConverged, :562). */
+int xb_step(xb_ctx* ctx, int32_t scheme);
+/* One stage of the step, for per-stage timing / parity. */
+int xb_stage(xb_ctx* ctx, int32_t scheme, int32_t stage);
+/* The same step behind the reference-facing boundary with HOST buffers: uploads E, B, B0 (what
+ * StepPresets commands may have edited), steps, downloads E, B and the kinetic energy of every
+ * sort (what Energy::diagnose reads each step, src/interfaces/simulation.cpp:91-92).
+ * kinetic may be NULL.  Particles stay resident (xb_particles_download refreshes the mirror). */
+int xb_step_host(xb_ctx* ctx, int32_t scheme, double* E, double* B, const double* B0, double* kinetic);
+
+/* k consecutive steps bracketed by CUDA events on the launching stream; *ms = device-timeline
+ * milliseconds for all k steps (Simulation::calculate's loop, src/interfaces/simulation.cpp:75-96). */
+int xb_run_steps(xb_ctx* ctx, int32_t scheme, int32_t k, double* ms);
+int xb_run_steps_host(xb_ctx* ctx, int32_t scheme, int32_t k, double* E, double* B, const double* B0, double* kinetic, double* ms);
+
+int xb_scalar(xb_ctx* ctx, int32_t sid, int32_t which, double* out);
+
+/* Seconds / launches accumulated per stage since the last reset (SyncClock, utils/sync_clock.cpp:75-93). */
+int xb_timing(xb_ctx* ctx, int32_t stage, double* seconds, int64_t* calls);
+int xb_timing_reset(xb_ctx* ctx);
+/* Number of this library's kernel launches since creation. */
+int xb_launch_count(xb_ctx* ctx, int64_t* launches);
+/* Per-launch CUDA-event timing of the operator kernel (the MatMult event of PETSc's -log_view):
+ * enable != 0 starts collecting; the query returns the launches seen and their summed ms. */
+int xb_spmv_profile(xb_ctx* ctx, int32_t enable);
+int xb_spmv_profile_read(xb_ctx* ctx, int64_t* launches, double* total_ms);
+
+/* --- hooks for the operator sweep (BASELINE config 4) and per-kernel parity tests ----------- */
+/* y = Op x with host vectors (owned slab, natural order).  MatMult, e.g. ecsimcorr/simulation.cpp:78 */
+int xb_spmv(xb_ctx* ctx, int32_t op, const double* x, double* y);
+/* Times `reps` device-resident SpMVs on pseudo-random x; returns average ms per SpMV. */
+int xb_spmv_bench(xb_ctx* ctx, int32_t op, int32_t reps, double* ms_per_spmv);
+/* Stencil-layout coefficients of L: coef[k*ncells + cell], k < xb_operator_ncoef(), owned cells. */
+int xb_operator_download(xb_ctx* ctx, double* coef);
+int xb_operator_upload(xb_ctx* ctx, const double* coef);
+/* Moments only at the present particle positions: fill_ecsim_current (ecsim/simulation.cpp:336-368). */
+int xb_deposit(xb_ctx* ctx);
+/* Solve (L? + M) x = b for host vectors with the given solver slot (KSPSolve). */
+int xb_solve(xb_ctx* ctx, int32_t which, int32_t op, const double* b, double* x);
+/* out = curl(f): positive != 0 -> Rotor::create_positive, else create_negative (utils/operators.cpp:175-213). */
+int xb_curl(xb_ctx* ctx, int32_t positive, const double* f, double* out);
+/* Time one kernel family in isolation on the resident state: what = 0 first_push+sort, 1 deposit,
+ * 2 second_push, 3 solve(predict).  Returns average ms. */
+int xb_kernel_bench(xb_ctx* ctx, int32_t what, int32_t reps, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XPIC_B200_H */

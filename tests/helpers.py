@@ -1,0 +1,59 @@
+"""Shared set-up for the parity tests: the same initial particles and fields in the CPU oracle
+and in the CUDA path (through the C ABI)."""
+import numpy as np
+
+from oracle import oracle as O
+
+
+def make_pair(n=(10, 10, 10), Np=100, T=0.1, scheme=0, curl_sign=+1, rtol=1e-12, precond=0, seed_fields=None, d=(0.5, 0.5, 0.5), dt=1.5,
+              species=((-1.0, 1.0, 1.0),)):
+    """Returns (oracle, gpu simulation) holding identical state.  Particles come from the
+    reference's default-seeded mt19937 stream (oracle.set_particles_maxwell)."""
+    import xpic_b200 as X
+
+    o = O.Oracle(n, d=d, dt=dt, curl_sign=curl_sign)
+    s = X.Simulation(n, d=d, dt=dt, scheme=scheme, curl_sign=curl_sign, track_ids=True)
+    for (q, m, dens) in species:
+        sid = o.add_species(q=q, m=m, n=dens, Np=Np)
+        o.set_particles_maxwell(sid, T=T, tov=True)
+        gs = s.add_species(q=q, m=m, n=dens, Np=Np)
+        assert gs == sid
+        pts, ids = o.get_particles(sid)
+        assert s.add_particles(sid, pts, ids) == len(ids)
+    for which in (0, 1):
+        o.solver_set(which, rtol, 1e-50, 1000, 30)
+        s.solver_set(which, rtol, 1e-50, 1000, 30, precond)
+    if seed_fields is not None:
+        rng = np.random.default_rng(seed_fields)
+        for name, amp in (("E", 0.02), ("B", 0.05)):
+            f = amp * rng.standard_normal(o.n3)
+            o.set_field(name, f)
+            s.set_field(name, f)
+    return o, s
+
+
+def by_id(pts, ids):
+    order = np.argsort(ids, kind="stable")
+    return pts[order], ids[order]
+
+
+def rel_err(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def csr_to_stencil(o, table):
+    """Oracle CSR of L -> coef[k][node] in the product's fixed-offset layout."""
+    import scipy.sparse as sp
+
+    rp, col, val = o.csr(0)
+    A = sp.csr_matrix((val, col, rp), shape=(o.n3, o.n3))
+    nx, ny, nz = o.n
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    node = ((z * ny + y) * nx + x).reshape(-1)
+    coef = np.zeros((len(table), node.size))
+    for k, (c1, c2, dx, dy, dz) in enumerate(table):
+        rows = node * 3 + c1
+        cn = ((((z + dz) % nz) * ny + ((y + dy) % ny)) * nx + ((x + dx) % nx)).reshape(-1)
+        cols = cn * 3 + c2
+        coef[k] = np.asarray(A[rows, cols]).reshape(-1)
+    return coef

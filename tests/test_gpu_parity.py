@@ -1,0 +1,174 @@
+"""GPU parity tests: every kernel family and the whole ECSIM / ECSIMCorr step, through the C ABI,
+against the CPU oracle on the same seeded inputs.  Tolerances: fp64 round-off for single kernels,
+the north-star bound 1e-8 relative for state after 10 steps (BASELINE.json)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from helpers import by_id, csr_to_stencil, make_pair, rel_err
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def X():
+    import xpic_b200
+
+    return xpic_b200
+
+
+def test_library_loaded_and_device_present(X):
+    import torch
+
+    assert torch.cuda.is_available()
+    assert os.path.exists(X.library_path())
+    s = X.Simulation((8, 8, 8))
+    assert s.launch_count() == 0
+    s.close()
+
+
+def test_curl_matches_oracle(X):
+    o, s = make_pair(n=(10, 8, 6), Np=1)
+    f = np.random.default_rng(1).standard_normal(o.n3)
+    for positive in (True, False):
+        assert rel_err(s.curl(f, positive), o.curl(f, positive)) < 1e-14
+
+
+def test_spmv_constant_operator_matches_oracle(X):
+    o, s = make_pair(n=(10, 8, 6), Np=1)
+    x = np.random.default_rng(2).standard_normal(o.n3)
+    assert rel_err(s.spmv(x, op=2), o.spmv(x, L=False, M=True)) < 1e-13
+
+
+@pytest.mark.parametrize("n", [(10, 10, 10), (33, 6, 5)])
+def test_spmv_with_oracle_operator(X, n):
+    o, s = make_pair(n=n, Np=8, seed_fields=3)
+    o.deposit()
+    s.operator_upload(csr_to_stencil(o, X.coef_table()))
+    x = np.random.default_rng(4).standard_normal(o.n3)
+    assert rel_err(s.spmv(x, op=1), o.spmv(x, L=True, M=False)) < 1e-13
+    assert rel_err(s.spmv(x, op=3), o.spmv(x, L=True, M=True)) < 1e-13
+
+
+@pytest.mark.parametrize("n,Np", [((10, 10, 10), 100), ((12, 9, 7), 13)])
+def test_deposit_matches_oracle(X, n, Np):
+    o, s = make_pair(n=n, Np=Np, seed_fields=5)
+    o.deposit()
+    s.deposit()
+    ref = csr_to_stencil(o, X.coef_table())
+    got = s.operator_download()
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-13
+    assert rel_err(s.get_field("currI"), o.get_field("currI")) < 1e-12
+    # the slots are complete: L x agrees too (nothing of the oracle's pattern was dropped)
+    x = np.random.default_rng(6).standard_normal(o.n3)
+    assert rel_err(s.spmv(x, op=1), o.spmv(x, L=True, M=False)) < 1e-12
+
+
+def test_deposit_two_species(X):
+    o, s = make_pair(n=(8, 8, 8), Np=20, seed_fields=7, species=((-1.0, 1.0, 1.0), (+1.0, 100.0, 1.0)))
+    o.deposit()
+    s.deposit()
+    ref = csr_to_stencil(o, X.coef_table())
+    assert np.max(np.abs(s.operator_download() - ref)) / np.max(np.abs(ref)) < 1e-13
+    assert rel_err(s.get_field("currI"), o.get_field("currI")) < 1e-12
+
+
+def test_solve_matches_oracle(X):
+    o, s = make_pair(n=(10, 10, 10), Np=20, seed_fields=8)
+    o.deposit()
+    s.deposit()
+    b = np.random.default_rng(9).standard_normal(o.n3)
+    x = s.solve(b, which=0, op=3)
+    it, rn, reason = s.solver_info(0)
+    assert reason > 0
+    assert rel_err(o.spmv(x), b) < 1e-10
+    # Chebyshev-preconditioned solve gives the same answer in fewer iterations
+    s.solver_set(0, 1e-12, 1e-50, 1000, 30, 6)
+    x2 = s.solve(b, which=0, op=3)
+    it2, _, reason2 = s.solver_info(0)
+    assert reason2 > 0 and it2 < it
+    assert rel_err(x2, x) < 1e-9
+
+
+def _compare_state(o, s, tol):
+    for name in ("E", "B"):
+        assert rel_err(s.get_field(name), o.get_field(name)) < tol, name
+    po, io = by_id(*o.get_particles(0))
+    pg, ig = by_id(*s.get_particles(0))
+    assert np.array_equal(io, ig)
+    assert rel_err(pg[:, :3], po[:, :3]) < tol
+    assert rel_err(pg[:, 3:], po[:, 3:]) < tol
+
+
+def test_ecsim_10_steps_state_parity(X):
+    o, s = make_pair(n=(10, 10, 10), Np=100, scheme=X.ECSIM)
+    for _ in range(10):
+        o.step(O.ECSIM)
+        s.step()
+    _compare_state(o, s, 1e-8)
+
+
+def test_ecsimcorr_10_steps_state_parity(X):
+    o, s = make_pair(n=(10, 10, 10), Np=100, scheme=X.ECSIMCORR)
+    for _ in range(10):
+        o.step(O.ECSIMCORR)
+        s.step()
+    _compare_state(o, s, 1e-8)
+    for name in ("pred_w", "corr_w", "lambda_dK"):
+        assert abs(s.scalar(name) - o.scalar(name)) < 1e-10, name
+
+
+def test_ecsim_golden_energy_rows(X):
+    """The CUDA path against the reference's own golden file (curl_sign = -1)."""
+    _, s = make_pair(n=(10, 10, 10), Np=100, scheme=X.ECSIM, curl_sign=-1)
+    _, gold = O.read_table(os.path.join(GOLDEN, "ecsim_ex1", "energy.txt"))
+    rows = [(0.0, 0.0, s.scalar("kinetic"))]
+    for _ in range(12):
+        s.step()
+        wE, wB = s.field_energies()
+        rows.append((wE, wB, s.scalar("kinetic")))
+    rows = np.array(rows)
+    np.testing.assert_allclose(rows, gold[:13, 1:4], rtol=2e-6, atol=1e-10)
+    assert np.max(np.abs(np.diff(rows.sum(axis=1)))) < 1e-12  # dE + dB + dK at solver tolerance
+
+
+def test_ecsimcorr_golden_energy_rows(X):
+    _, s = make_pair(n=(10, 10, 10), Np=100, scheme=X.ECSIMCORR, curl_sign=-1)
+    _, gold = O.read_table(os.path.join(GOLDEN, "ecsimcorr_ex1", "energy.txt"))
+    _, gc = O.read_table(os.path.join(GOLDEN, "ecsimcorr_ex1", "energy_conservation.txt"))
+    rows = [(0.0, 0.0, s.scalar("kinetic"))]
+    cwd = []
+    for _ in range(8):
+        s.step()
+        wE, wB = s.field_energies()
+        rows.append((wE, wB, s.scalar("kinetic")))
+        cwd.append(s.scalar("lambda_dK"))
+    np.testing.assert_allclose(np.array(rows), gold[:9, 1:4], rtol=2e-6, atol=1e-10)
+    np.testing.assert_allclose(np.array(cwd), gc[1:9, 4], rtol=5e-6)
+
+
+def test_energy_conservation_32cubed(X):
+    """Size-independent property at BASELINE config 1 size (32^3 x 100 ppc): |dE + dB + dK| at
+    solver tolerance, with the default (reference) tolerances and the production preconditioner."""
+    n = (32, 32, 32)
+    s = X.Simulation(n, scheme=X.ECSIM, track_ids=False)
+    sid = s.add_species(Np=100)
+    rng = np.random.default_rng(11)
+    N = 100 * 32**3
+    pts = np.empty((N, 6))
+    pts[:, :3] = rng.random((N, 3)) * 16.0
+    pts[:, 3:] = rng.standard_normal((N, 3)) * np.sqrt(0.1 / 511.0)
+    assert s.add_particles(sid, pts) == N
+    s.solver_set(0, 1e-7, 1e-7, 100, 30, 6)
+    tot = []
+    for _ in range(4):
+        wE, wB = s.field_energies()
+        tot.append(wE + wB + s.scalar("kinetic"))
+        s.step()
+    wE, wB = s.field_energies()
+    tot.append(wE + wB + s.scalar("kinetic"))
+    assert np.max(np.abs(np.diff(tot))) < 1e-9 * tot[0] + 1e-9
+    assert s.launch_count() > 0

@@ -1,0 +1,323 @@
+"""ctypes binding of include/xpic_b200.h.
+
+`Simulation` mirrors the members of the reference's ecsim::Simulation / ecsimcorr::Simulation
+that other subsystems touch (src/interfaces/simulation.h:21-72, src/impls/ecsim/simulation.h:27-40):
+named vectors E, B, B0, Ep, Ec, currI, currJe, one particle sort per add_species(), step() ==
+timestep_implementation().  Errors are raised as XpicB200Error carrying xb_last_error().
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_LIB = os.path.join(_HERE, "_build", "libxpic_b200.so")
+
+ECSIM, ECSIMCORR = 0, 1
+FIELDS = {"E": 0, "B": 1, "B0": 2, "Ep": 3, "Ec": 4, "currI": 5, "currJe": 6, "currI_sort": 7, "currJe_sort": 8}
+SCALARS = {"kinetic": 0, "pred_w": 1, "corr_w": 2, "pred_dK": 3, "corr_dK": 4, "lambda_dK": 5, "energy_member": 6, "j_diff_norm": 7}
+STAGES = ["clear_sources", "first_push", "advance_fields", "second_push", "correct_fields", "final_update"]
+OP_L, OP_M, OP_A = 1, 2, 3
+
+
+class XpicB200Error(RuntimeError):
+    pass
+
+
+class _Grid(C.Structure):
+    _fields_ = [("n", C.c_int32 * 3), ("d", C.c_double * 3), ("dt", C.c_double), ("curl_sign", C.c_int32), ("device", C.c_int32),
+                ("rank", C.c_int32), ("nranks", C.c_int32), ("track_ids", C.c_int32)]
+
+
+def library_path():
+    return _LIB
+
+
+def build_library(force=False, jobs=8):
+    """Compile xpic_b200/csrc for sm_100a (nvcc cross-compiles without a GPU)."""
+    args = ["make", "-C", _CSRC, "-s", "-j", str(jobs)]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args)
+    return _LIB
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/xpic_b200.h declares
+_dp = C.POINTER(C.c_double)
+_u64p = C.POINTER(C.c_uint64)
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+SYMBOLS = {
+    "xb_last_error": (C.c_char_p, []),
+    "xb_version": (C.c_int, []),
+    "xb_operator_ncoef": (C.c_int, []),
+    "xb_operator_coef_info": (C.c_int, [C.c_int] + [C.POINTER(C.c_int)] * 5),
+    "xb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "xb_create": (C.c_int, [C.POINTER(_Grid), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "xb_destroy": (C.c_int, [C.c_void_p]),
+    "xb_species_add": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int64, _i32p]),
+    "xb_particles_append": (C.c_int, [C.c_void_p, C.c_int32, _dp, _u64p, C.c_int64, _i64p]),
+    "xb_particles_count": (C.c_int, [C.c_void_p, C.c_int32, _i64p]),
+    "xb_particles_download": (C.c_int, [C.c_void_p, C.c_int32, _dp, _u64p, C.c_int64, _i64p]),
+    "xb_field_upload": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "xb_field_download": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "xb_solver_set": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32]),
+    "xb_solver_info": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _dp, _i32p]),
+    "xb_step": (C.c_int, [C.c_void_p, C.c_int32]),
+    "xb_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "xb_step_host": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp, _dp, _dp]),
+    "xb_run_steps": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "xb_run_steps_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp]),
+    "xb_spmv_profile": (C.c_int, [C.c_void_p, C.c_int32]),
+    "xb_spmv_profile_read": (C.c_int, [C.c_void_p, _i64p, _dp]),
+    "xb_scalar": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "xb_timing": (C.c_int, [C.c_void_p, C.c_int32, _dp, _i64p]),
+    "xb_timing_reset": (C.c_int, [C.c_void_p]),
+    "xb_launch_count": (C.c_int, [C.c_void_p, _i64p]),
+    "xb_spmv": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp]),
+    "xb_spmv_bench": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "xb_operator_download": (C.c_int, [C.c_void_p, _dp]),
+    "xb_operator_upload": (C.c_int, [C.c_void_p, _dp]),
+    "xb_deposit": (C.c_int, [C.c_void_p]),
+    "xb_solve": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp]),
+    "xb_curl": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp]),
+    "xb_kernel_bench": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+}
+
+
+def load_library():
+    """dlopen the in-tree library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            raise XpicB200Error(f"{_LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(there is no CPU fallback)")
+        L = C.CDLL(_LIB, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise XpicB200Error(load_library().xb_last_error().decode("utf-8", "replace"))
+
+
+def _as_dp(a):
+    return a.ctypes.data_as(_dp)
+
+
+def comm_unique_id():
+    buf = (C.c_uint8 * 128)()
+    _check(load_library().xb_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def coef_table():
+    """(369, 5) int array: c1, c2, dx, dy, dz of every coefficient slot."""
+    L = load_library()
+    n = L.xb_operator_ncoef()
+    out = np.zeros((n, 5), dtype=np.int64)
+    v = [C.c_int() for _ in range(5)]
+    for k in range(n):
+        _check(L.xb_operator_coef_info(k, *[C.byref(x) for x in v]))
+        out[k] = [x.value for x in v]
+    return out
+
+
+class Simulation:
+    def __init__(self, n, d=(0.5, 0.5, 0.5), dt=1.5, scheme=ECSIM, curl_sign=+1, device=0, rank=0, nranks=1, comm_id=None,
+                 track_ids=True):
+        self._L = load_library()
+        self.n = tuple(int(v) for v in n)
+        self.d = tuple(float(v) for v in d)
+        self.dt = float(dt)
+        self.scheme = scheme
+        self.rank, self.nranks = rank, nranks
+        base, rem = divmod(self.n[2], nranks)
+        self.nzl = base + (1 if rank < rem else 0)
+        self.z0 = rank * base + min(rank, rem)
+        self.ncl = self.n[0] * self.n[1] * self.nzl
+        self.nown = 3 * self.ncl
+        g = _Grid()
+        g.n[:] = self.n
+        g.d[:] = self.d
+        g.dt = self.dt
+        g.curl_sign = curl_sign
+        g.device = device
+        g.rank = rank
+        g.nranks = nranks
+        g.track_ids = 1 if track_ids else 0
+        self.track_ids = bool(track_ids)
+        h = C.c_void_p()
+        uid = C.create_string_buffer(comm_id, 128) if comm_id is not None else None
+        _check(self._L.xb_create(C.byref(g), uid, C.byref(h)))
+        self._h = h
+        self.nsorts = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.xb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    # -- particles (interfaces::Particles) -----------------------------------------------------
+    def add_species(self, q=-1.0, m=1.0, n=1.0, Np=100, capacity=None):
+        if capacity is None:
+            capacity = int(self.ncl * Np * 1.5) + 4096
+        sid = C.c_int32()
+        _check(self._L.xb_species_add(self._h, q, m, n, Np, capacity, C.byref(sid)))
+        self.nsorts += 1
+        return sid.value
+
+    def add_particles(self, sid, aos6, ids=None):
+        a = np.ascontiguousarray(aos6, dtype=np.float64).reshape(-1, 6)
+        added = C.c_int64()
+        idp = None
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.uint64)
+            idp = ids.ctypes.data_as(_u64p)
+        _check(self._L.xb_particles_append(self._h, sid, _as_dp(a), idp, a.shape[0], C.byref(added)))
+        return added.value
+
+    def particle_count(self, sid=0):
+        n = C.c_int64()
+        _check(self._L.xb_particles_count(self._h, sid, C.byref(n)))
+        return n.value
+
+    def get_particles(self, sid=0):
+        n = self.particle_count(sid)
+        a = np.empty((n, 6), dtype=np.float64)
+        ids = np.empty(n, dtype=np.uint64) if self.track_ids else None
+        cnt = C.c_int64()
+        _check(self._L.xb_particles_download(self._h, sid, _as_dp(a), ids.ctypes.data_as(_u64p) if ids is not None else None, n, C.byref(cnt)))
+        return a, ids
+
+    # -- named vectors -------------------------------------------------------------------------
+    def get_field(self, name, sid=0):
+        out = np.empty(self.nown, dtype=np.float64)
+        _check(self._L.xb_field_download(self._h, FIELDS[name], sid, _as_dp(out)))
+        return out
+
+    def set_field(self, name, arr, sid=0):
+        a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        assert a.size == self.nown
+        _check(self._L.xb_field_upload(self._h, FIELDS[name], sid, _as_dp(a)))
+
+    # -- solver --------------------------------------------------------------------------------
+    def solver_set(self, which=0, rtol=1e-7, atol=1e-7, maxit=100, restart=30, precond=0):
+        _check(self._L.xb_solver_set(self._h, which, rtol, atol, maxit, restart, precond))
+
+    def solver_info(self, which=0):
+        it, rn, re = C.c_int32(), C.c_double(), C.c_int32()
+        _check(self._L.xb_solver_info(self._h, which, C.byref(it), C.byref(rn), C.byref(re)))
+        return it.value, rn.value, re.value
+
+    # -- stepping ------------------------------------------------------------------------------
+    def step(self, scheme=None):
+        _check(self._L.xb_step(self._h, self.scheme if scheme is None else scheme))
+
+    def stage(self, stage, scheme=None):
+        idx = STAGES.index(stage) if isinstance(stage, str) else stage
+        _check(self._L.xb_stage(self._h, self.scheme if scheme is None else scheme, idx))
+
+    def step_host(self, E, B, B0=None, kinetic=None, scheme=None):
+        """E, B (in/out), B0 (in): host arrays (pinned torch tensors' numpy views work)."""
+        _check(self._L.xb_step_host(self._h, self.scheme if scheme is None else scheme, _as_dp(E), _as_dp(B),
+                                    _as_dp(B0) if B0 is not None else None, _as_dp(kinetic) if kinetic is not None else None))
+
+    def run_steps(self, k, scheme=None):
+        """k steps, state resident; returns device-timeline ms (CUDA events on the launching stream)."""
+        ms = C.c_double()
+        _check(self._L.xb_run_steps(self._h, self.scheme if scheme is None else scheme, k, C.byref(ms)))
+        return ms.value
+
+    def run_steps_host(self, k, E, B, B0=None, kinetic=None, scheme=None):
+        ms = C.c_double()
+        _check(self._L.xb_run_steps_host(self._h, self.scheme if scheme is None else scheme, k, _as_dp(E), _as_dp(B),
+                                         _as_dp(B0) if B0 is not None else None, _as_dp(kinetic) if kinetic is not None else None, C.byref(ms)))
+        return ms.value
+
+    def spmv_profile(self, enable=True):
+        _check(self._L.xb_spmv_profile(self._h, int(enable)))
+
+    def spmv_profile_read(self):
+        n, ms = C.c_int64(), C.c_double()
+        _check(self._L.xb_spmv_profile_read(self._h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def scalar(self, name, sid=0):
+        out = C.c_double()
+        _check(self._L.xb_scalar(self._h, sid, SCALARS[name], C.byref(out)))
+        return out.value
+
+    def field_energies(self):
+        E, B = self.get_field("E"), self.get_field("B")
+        return 0.5 * float(E @ E), 0.5 * float(B @ B)
+
+    def timing(self):
+        out = {}
+        for i, name in enumerate(STAGES):
+            s, n = C.c_double(), C.c_int64()
+            _check(self._L.xb_timing(self._h, i, C.byref(s), C.byref(n)))
+            out[name] = (s.value, n.value)
+        return out
+
+    def timing_reset(self):
+        _check(self._L.xb_timing_reset(self._h))
+
+    def launch_count(self):
+        n = C.c_int64()
+        _check(self._L.xb_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # -- hooks ---------------------------------------------------------------------------------
+    def spmv(self, x, op=OP_A):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.nown, dtype=np.float64)
+        _check(self._L.xb_spmv(self._h, op, _as_dp(x), _as_dp(y)))
+        return y
+
+    def spmv_bench(self, op=OP_A, reps=100):
+        ms = C.c_double()
+        _check(self._L.xb_spmv_bench(self._h, op, reps, C.byref(ms)))
+        return ms.value
+
+    def operator_download(self):
+        out = np.empty((self._L.xb_operator_ncoef(), self.ncl), dtype=np.float64)
+        _check(self._L.xb_operator_download(self._h, _as_dp(out)))
+        return out
+
+    def operator_upload(self, coef):
+        a = np.ascontiguousarray(coef, dtype=np.float64)
+        assert a.shape == (self._L.xb_operator_ncoef(), self.ncl)
+        _check(self._L.xb_operator_upload(self._h, _as_dp(a)))
+
+    def deposit(self):
+        _check(self._L.xb_deposit(self._h))
+
+    def solve(self, b, which=0, op=OP_A):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty(self.nown, dtype=np.float64)
+        _check(self._L.xb_solve(self._h, which, op, _as_dp(b), _as_dp(x)))
+        return x
+
+    def curl(self, f, positive=True):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        y = np.empty(self.nown, dtype=np.float64)
+        _check(self._L.xb_curl(self._h, int(positive), _as_dp(f), _as_dp(y)))
+        return y
+
+    def kernel_bench(self, what, reps=5):
+        ms = C.c_double()
+        _check(self._L.xb_kernel_bench(self._h, what, reps, C.byref(ms)))
+        return ms.value

@@ -1,0 +1,664 @@
+// api.cu -- the extern "C" surface declared in include/xpic_b200.h and the step orchestration
+// (ecsim::Simulation::timestep_implementation, src/impls/ecsim/simulation.cpp:145-155, and
+// ecsimcorr::Simulation::timestep_implementation, src/impls/ecsimcorr/simulation.cpp:21-32).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "comm.cuh"
+#include "common.cuh"
+#include "stencil.cuh"
+
+namespace xb {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+int migrate_and_sort(xb_ctx* c, Species& s, double dt_move);  // migrate.cu
+
+static int sort_species(xb_ctx* c, Species& s, double dt_move)
+{
+  if (c->g.nranks > 1) return migrate_and_sort(c, s, dt_move);
+  return particles_sort(c, s, dt_move);
+}
+
+struct StageTimer {
+  xb_ctx* c;
+  int stage;
+  StageTimer(xb_ctx* c_, int st) : c(c_), stage(st) { cudaEventRecord(c->ev0, c->stream); }
+  int finish()
+  {
+    XB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    XB_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    XB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->clock.seconds[stage] += 1e-3 * ms;
+    c->clock.calls[stage] += 1;
+    return 0;
+  }
+};
+
+static int ensure_sorted(xb_ctx* c)
+{
+  for (auto& s : c->sorts)
+    if (!s.sorted) XB_CHECK(sort_species(c, s, 0.0));
+  return 0;
+}
+
+static int zero_owned_and_ghosts(xb_ctx* c, double* v) { return vec_zero(c, v); }
+
+// ---- stages ---------------------------------------------------------------------------------
+static int stage_clear(xb_ctx* c, int scheme)
+{
+  XB_CHECK(zero_owned_and_ghosts(c, c->currI));
+  for (auto& s : c->sorts) XB_CHECK(zero_owned_and_ghosts(c, s.currI));
+  if (scheme == XB_ECSIMCORR) {
+    XB_CHECK(zero_owned_and_ghosts(c, c->currJe));
+    for (auto& s : c->sorts) {
+      XB_CHECK(zero_owned_and_ghosts(c, s.currJe));
+      XB_CHECK(kinetic_energy(c, s, nullptr, &s.energy));  // ecsimcorr/simulation.cpp:44-45
+    }
+  }
+  return 0;
+}
+
+static int stage_first_push(xb_ctx* c, int scheme)
+{
+  for (auto& s : c->sorts) {
+    if (scheme == XB_ECSIM) {
+      XB_CHECK(sort_species(c, s, c->g.dt));  // r += v dt, wrap, re-bin (ecsim/particles.cpp:21-31)
+    }
+    else {
+      XB_CHECK(push_first_corr(c, s));
+      XB_CHECK(sort_species(c, s, 0.0));
+    }
+  }
+  XB_CHECK(deposit_moments(c));
+  return 0;
+}
+
+static int solve_checked(xb_ctx* c, int which, int op, const double* curr, double* out)
+{
+  XB_CHECK(build_rhs(c, curr, c->rhs));
+  XB_CHECK(gmres(c, which, op, c->rhs, out));
+  if (c->solver[which].reason < 0)
+    XB_FAIL(std::string("KSPSolve(") + (which == 0 ? "predict" : "correct") + ") did not converge: reason " +
+            std::to_string(c->solver[which].reason) + ", iterations " + std::to_string(c->solver[which].iterations));
+  return 0;
+}
+
+static int stage_second_push(xb_ctx* c, int scheme)
+{
+  XB_CHECK(halo_fill(c, c->Ep, 1));
+  XB_CHECK(halo_fill(c, c->B, 1));
+  for (auto& s : c->sorts) {
+    if (scheme == XB_ECSIM) {
+      XB_CHECK(push_second(c, s, c->Ep, c->B));
+      // positions did not change: the reference's second update_cells is a no-op here
+    }
+    else {
+      XB_CHECK(push_second_corr(c, s, c->Ep, c->B));
+      XB_CHECK(halo_reduce(c, s.currJe, GZ, GZ));
+      const double one = 1.0;
+      const double* vs[1] = {s.currJe};
+      XB_CHECK(axpy_multi(c, 1, vs, &one, c->currJe));  // ecsimcorr/particles.cpp:89
+      XB_CHECK(sort_species(c, s, 0.0));
+    }
+  }
+  return 0;
+}
+
+static int stage_final(xb_ctx* c, int scheme)
+{
+  if (scheme == XB_ECSIMCORR) {
+    for (auto& s : c->sorts) {  // ecsimcorr/particles.cpp:93-126
+      const double* vs[1] = {s.currJe};
+      XB_CHECK(dots(c, 1, vs, c->Ec, &s.corr_w));
+      const double K0 = s.energy;
+      double K = 0.0;
+      XB_CHECK(kinetic_energy(c, s, nullptr, &K));
+      const double lambda2 = 1.0 + c->g.dt * (s.corr_w - s.pred_w) / K;
+      const double lambda = std::sqrt(lambda2);
+      XB_CHECK(scale_velocities(c, s, lambda));
+      s.lambda_dK = (lambda2 - 1.0) * K;
+      s.pred_dK = K - K0;
+      s.corr_dK = lambda2 * K - K0;
+      s.energy = lambda2 * K;
+    }
+    {  // ||currJe - (currI + L Ec)||, logged by the reference (ecsimcorr/simulation.cpp:74-82)
+      XB_CHECK(spmv(c, XB_OP_L, c->Ec, c->tmp));
+      const double one = 1.0, mone = -1.0;
+      const double* a1[1] = {c->tmp};
+      XB_CHECK(axpy_multi(c, 1, a1, &one, c->currI));
+      XB_CHECK(vec_copy_owned(c, c->currJe, c->tmp));
+      const double* a2[1] = {c->currI};
+      XB_CHECK(axpy_multi(c, 1, a2, &mone, c->tmp));
+      const double* a3[1] = {c->tmp};
+      double n2 = 0.0;
+      XB_CHECK(dots(c, 1, a3, c->tmp, &n2));
+      c->j_diff_norm = std::sqrt(n2);
+    }
+    std::swap(c->Ep, c->Ec);  // VecSwap(Ep, Ec), :84
+  }
+  XB_CHECK(final_update(c, c->Ep));
+  return 0;
+}
+
+static int run_stage(xb_ctx* c, int scheme, int stage)
+{
+  StageTimer t(c, stage);
+  switch (stage) {
+    case XB_STAGE_CLEAR_SOURCES: XB_CHECK(stage_clear(c, scheme)); break;
+    case XB_STAGE_FIRST_PUSH: XB_CHECK(stage_first_push(c, scheme)); break;
+    case XB_STAGE_ADVANCE_FIELDS: XB_CHECK(solve_checked(c, XB_SOLVER_PREDICT, XB_OP_A, c->currI, c->Ep)); break;
+    case XB_STAGE_SECOND_PUSH: XB_CHECK(stage_second_push(c, scheme)); break;
+    case XB_STAGE_CORRECT_FIELDS:
+      if (scheme == XB_ECSIMCORR) XB_CHECK(solve_checked(c, XB_SOLVER_CORRECT, XB_OP_M, c->currJe, c->Ec));
+      break;
+    case XB_STAGE_FINAL_UPDATE: XB_CHECK(stage_final(c, scheme)); break;
+    default: XB_FAIL("unknown stage");
+  }
+  return t.finish();
+}
+
+static double* named_vector(xb_ctx* c, int which, int sid)
+{
+  switch (which) {
+    case XB_E: return c->E;
+    case XB_B: return c->B;
+    case XB_B0: return c->B0;
+    case XB_EP: return c->Ep;
+    case XB_EC: return c->Ec;
+    case XB_CURRI: return c->currI;
+    case XB_CURRJE: return c->currJe;
+    case XB_CURRI_SORT: return sid >= 0 && sid < (int)c->sorts.size() ? c->sorts[sid].currI : nullptr;
+    case XB_CURRJE_SORT: return sid >= 0 && sid < (int)c->sorts.size() ? c->sorts[sid].currJe : nullptr;
+  }
+  return nullptr;
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+#define XB_API_BEGIN(ctx)                                   \
+  if (!(ctx)) {                                             \
+    xb::set_error("null context");                          \
+    return 1;                                               \
+  }                                                         \
+  if (cudaSetDevice((ctx)->device) != cudaSuccess) {        \
+    xb::set_error("cudaSetDevice failed");                  \
+    return 1;                                               \
+  }
+
+extern "C" {
+
+const char* xb_last_error(void) { return g_error.c_str(); }
+int xb_version(void) { return 100; }
+int xb_operator_ncoef(void) { return NCOEF; }
+
+int xb_operator_coef_info(int k, int* c1, int* c2, int* dx, int* dy, int* dz)
+{
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      const int base = pair_base(a, b), n = pair_size(a, b);
+      if (k >= base && k < base + n) {
+        const DRange rx = drange(a, b, 0), ry = drange(a, b, 1), rz = drange(a, b, 2);
+        const int r = k - base;
+        *c1 = a;
+        *c2 = b;
+        *dx = rx.lo + r % rx.n;
+        *dy = ry.lo + (r / rx.n) % ry.n;
+        *dz = rz.lo + r / (rx.n * ry.n);
+        return 0;
+      }
+    }
+  XB_FAIL("coefficient index out of range");
+}
+
+int xb_comm_unique_id(void* out128) { return comm_unique_id(out128); }
+
+int xb_create(const xb_grid* gr, const void* uid, xb_ctx** out)
+{
+  if (!gr || !out) XB_FAIL("xb_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    XB_FAIL("xb_create: no CUDA device available (this library has no CPU fallback)");
+  if (gr->device < 0 || gr->device >= ndev) XB_FAIL("xb_create: bad device ordinal");
+  if (gr->nranks < 1 || gr->rank < 0 || gr->rank >= gr->nranks) XB_FAIL("xb_create: bad rank / nranks");
+  for (int a = 0; a < 3; ++a)
+    if (gr->n[a] < 1 || !(gr->d[a] > 0.0)) XB_FAIL("xb_create: bad geometry");
+  XB_CUDA(cudaSetDevice(gr->device));
+  xb_ctx* c = new xb_ctx();
+  c->device = gr->device;
+  c->track_ids = gr->track_ids != 0;
+  Grid& g = c->g;
+  g.nx = gr->n[0]; g.ny = gr->n[1]; g.nz = gr->n[2];
+  g.dx = gr->d[0]; g.dy = gr->d[1]; g.dz = gr->d[2];
+  g.dt = gr->dt;
+  g.Lx = g.nx * g.dx; g.Ly = g.ny * g.dy; g.Lz = g.nz * g.dz;  // utils/world.cpp:97-100
+  g.curl_sign = gr->curl_sign < 0 ? -1 : +1;
+  g.rank = gr->rank; g.nranks = gr->nranks;
+  const int base = g.nz / g.nranks, rem = g.nz % g.nranks;
+  g.nzl = base + (g.rank < rem ? 1 : 0);
+  g.z0 = g.rank * base + std::min(g.rank, rem);
+  if (g.nzl < 1) XB_FAIL("xb_create: more ranks than z planes");
+  if (g.nranks > 1 && g.nzl < GZ) XB_FAIL("xb_create: slab thinner than the ghost width");
+  g.plane = (int64_t)g.nx * g.ny;
+  g.ncl = g.plane * g.nzl;
+  g.nown = 3 * g.ncl;
+  g.ntot = 3 * g.plane * (g.nzl + 2 * GZ);
+  g.own0 = 3 * g.plane * GZ;
+  if ((g.nzl + 2) * g.plane * 8 >= (int64_t)0x7fffffff) XB_FAIL("xb_create: slab too large for 32-bit bin keys");
+
+  XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  XB_CUDA(cudaEventCreate(&c->ev0));
+  XB_CUDA(cudaEventCreate(&c->ev1));
+  XB_CUDA(cudaEventCreate(&c->ev2));
+  XB_CUDA(cudaEventCreate(&c->ev3));
+  for (double** v : {&c->E, &c->B, &c->B0, &c->Ep, &c->Ec, &c->currI, &c->currJe, &c->rhs, &c->tmp, &c->tmp2}) {
+    XB_CUDA(cudaMalloc(v, sizeof(double) * g.ntot));
+    XB_CUDA(cudaMemset(*v, 0, sizeof(double) * g.ntot));
+  }
+  XB_CUDA(cudaMalloc(&c->coef, sizeof(double) * NCOEF * g.ncl));
+  XB_CUDA(cudaMemset(c->coef, 0, sizeof(double) * NCOEF * g.ncl));
+  c->stage_cells = g.nranks == 1 ? g.ncl : (g.nzl + 2) * g.plane;
+  const int64_t groups = (c->stage_cells + CELL_GROUP - 1) / CELL_GROUP;
+  XB_CUDA(cudaMalloc(&c->stage, sizeof(double) * groups * CELL_GROUP * BLOCK_ALL));
+  XB_CUDA(cudaMemset(c->stage, 0, sizeof(double) * groups * CELL_GROUP * BLOCK_ALL));
+  c->nbins = (int64_t)(g.nzl + 2) * g.plane * 8;
+  XB_CUDA(cudaMalloc(&c->hist, sizeof(int32_t) * c->nbins));
+  XB_CUDA(cudaMalloc(&c->cursor, sizeof(int32_t) * c->nbins));
+  XB_CUDA(cudaMalloc(&c->scan_tmp, sizeof(int32_t) * (c->nbins / 4096 + 2)));
+  XB_CUDA(cudaMalloc(&c->red_partial, sizeof(double) * RED_BLOCKS * RED_MAXV));
+  XB_CUDA(cudaMalloc(&c->red_out, sizeof(double) * RED_MAXV));
+  XB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * RED_MAXV));
+  if (g.nranks > 1) {
+    if (comm_init(c, uid)) {
+      xb_destroy(c);
+      return 1;
+    }
+  }
+  *out = c;
+  return 0;
+}
+
+int xb_destroy(xb_ctx* c)
+{
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  comm_free(c);
+  for (auto& s : c->sorts) species_free(s);
+  for (double* v : {c->E, c->B, c->B0, c->Ep, c->Ec, c->currI, c->currJe, c->rhs, c->tmp, c->tmp2, c->coef, c->stage, c->Z, c->cheb_r, c->cheb_d,
+                    c->cheb_Md, c->ksp_u, c->red_partial, c->red_out})
+    cudaFree(v);
+  for (double* v : c->V) cudaFree(v);
+  cudaFree(c->hist);
+  cudaFree(c->cursor);
+  cudaFree(c->scan_tmp);
+  if (c->red_host) cudaFreeHost(c->red_host);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev2) cudaEventDestroy(c->ev2);
+  if (c->ev3) cudaEventDestroy(c->ev3);
+  for (auto e : c->spmv_events) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int xb_species_add(xb_ctx* c, double q, double m, double n, int32_t Np, int64_t capacity, int32_t* sid)
+{
+  XB_API_BEGIN(c);
+  if (capacity < 1 || capacity >= (int64_t)0x7fffffff) XB_FAIL("xb_species_add: capacity must be in [1, 2^31)");
+  if (Np < 1 || !(m > 0.0)) XB_FAIL("xb_species_add: bad parameters");
+  c->sorts.emplace_back();
+  Species& s = c->sorts.back();
+  s.q = q; s.m = m; s.n = n; s.Np = Np;
+  if (species_alloc(c, s, capacity)) return 1;
+  if (sid) *sid = (int32_t)c->sorts.size() - 1;
+  return 0;
+}
+
+int xb_particles_append(xb_ctx* c, int32_t sid, const double* aos6, const uint64_t* ids, int64_t count, int64_t* added)
+{
+  XB_API_BEGIN(c);
+  if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
+  Species& s = c->sorts[sid];
+  const Grid& g = c->g;
+  std::vector<double> soa[6];
+  std::vector<uint64_t> kid;
+  for (auto& v : soa) v.reserve(count);
+  for (int64_t p = 0; p < count; ++p) {
+    const double* pt = aos6 + 6 * p;
+    // interfaces/particles.cpp:49-56: FLOOR_STEP(r, d) - start must lie inside the local box
+    const int vx = (int)std::floor(pt[0] / g.dx), vy = (int)std::floor(pt[1] / g.dy), vz = (int)std::floor(pt[2] / g.dz) - g.z0;
+    const uint64_t this_id = ids ? ids[p] : s.next_id + (uint64_t)p;
+    if (vx < 0 || vx >= g.nx || vy < 0 || vy >= g.ny || vz < 0 || vz >= g.nzl) continue;
+    for (int k = 0; k < 6; ++k) soa[k].push_back(pt[k]);
+    kid.push_back(this_id);
+  }
+  if (!ids) s.next_id += (uint64_t)count;
+  const int64_t nadd = (int64_t)kid.size();
+  if (s.count + nadd > s.capacity) XB_FAIL("xb_particles_append: species capacity exceeded");
+  for (int k = 0; k < 6; ++k)
+    XB_CUDA(cudaMemcpy(s.p[s.cur][k] + s.count, soa[k].data(), sizeof(double) * nadd, cudaMemcpyHostToDevice));
+  if (c->track_ids) XB_CUDA(cudaMemcpy(s.id[s.cur] + s.count, kid.data(), sizeof(uint64_t) * nadd, cudaMemcpyHostToDevice));
+  s.count += nadd;
+  s.sorted = false;
+  if (added) *added = nadd;
+  return 0;
+}
+
+int xb_particles_count(xb_ctx* c, int32_t sid, int64_t* count)
+{
+  XB_API_BEGIN(c);
+  if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
+  *count = c->sorts[sid].count;
+  return 0;
+}
+
+int xb_particles_download(xb_ctx* c, int32_t sid, double* aos6, uint64_t* ids, int64_t capacity, int64_t* count)
+{
+  XB_API_BEGIN(c);
+  if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
+  Species& s = c->sorts[sid];
+  XB_CHECK(ensure_sorted(c));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  if (capacity < s.count) XB_FAIL("xb_particles_download: buffer too small");
+  std::vector<double> tmp(s.count);
+  for (int k = 0; k < 6; ++k) {
+    XB_CUDA(cudaMemcpy(tmp.data(), s.p[s.cur][k], sizeof(double) * s.count, cudaMemcpyDeviceToHost));
+    for (int64_t p = 0; p < s.count; ++p) aos6[6 * p + k] = tmp[p];
+  }
+  if (ids) {
+    if (!c->track_ids) XB_FAIL("xb_particles_download: ids requested but the context was created with track_ids = 0");
+    XB_CUDA(cudaMemcpy(ids, s.id[s.cur], sizeof(uint64_t) * s.count, cudaMemcpyDeviceToHost));
+  }
+  if (count) *count = s.count;
+  return 0;
+}
+
+int xb_field_upload(xb_ctx* c, int32_t which, int32_t sid, const double* host)
+{
+  XB_API_BEGIN(c);
+  double* v = named_vector(c, which, sid);
+  if (!v) XB_FAIL("xb_field_upload: unknown vector");
+  XB_CHECK(upload_owned(c, host, v));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int xb_field_download(xb_ctx* c, int32_t which, int32_t sid, double* host)
+{
+  XB_API_BEGIN(c);
+  double* v = named_vector(c, which, sid);
+  if (!v) XB_FAIL("xb_field_download: unknown vector");
+  XB_CHECK(download_owned(c, v, host));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int xb_solver_set(xb_ctx* c, int32_t which, double rtol, double atol, int32_t maxit, int32_t restart, int32_t precond)
+{
+  XB_API_BEGIN(c);
+  if (which < 0 || which > 1) XB_FAIL("bad solver slot");
+  if (restart < 1 || restart > RED_MAXV - 1) XB_FAIL("restart must be in [1, 31]");
+  Solver& s = c->solver[which];
+  s.rtol = rtol; s.atol = atol; s.maxit = maxit; s.restart = restart; s.precond = precond;
+  return 0;
+}
+
+int xb_solver_info(xb_ctx* c, int32_t which, int32_t* iterations, double* rnorm, int32_t* reason)
+{
+  XB_API_BEGIN(c);
+  if (which < 0 || which > 1) XB_FAIL("bad solver slot");
+  const Solver& s = c->solver[which];
+  if (iterations) *iterations = s.iterations;
+  if (rnorm) *rnorm = s.rnorm;
+  if (reason) *reason = s.reason;
+  return 0;
+}
+
+int xb_stage(xb_ctx* c, int32_t scheme, int32_t stage)
+{
+  XB_API_BEGIN(c);
+  if (scheme != XB_ECSIM && scheme != XB_ECSIMCORR) XB_FAIL("unknown scheme");
+  if (stage == XB_STAGE_CLEAR_SOURCES) XB_CHECK(ensure_sorted(c));
+  return run_stage(c, scheme, stage);
+}
+
+int xb_step(xb_ctx* c, int32_t scheme)
+{
+  XB_API_BEGIN(c);
+  if (scheme != XB_ECSIM && scheme != XB_ECSIMCORR) XB_FAIL("unknown scheme");
+  XB_CHECK(ensure_sorted(c));
+  for (int st = 0; st < XB_STAGE_COUNT; ++st) XB_CHECK(run_stage(c, scheme, st));
+  return 0;
+}
+
+int xb_step_host(xb_ctx* c, int32_t scheme, double* E, double* B, const double* B0, double* kinetic)
+{
+  XB_API_BEGIN(c);
+  XB_CHECK(upload_owned(c, E, c->E));
+  XB_CHECK(upload_owned(c, B, c->B));
+  if (B0) XB_CHECK(upload_owned(c, B0, c->B0));
+  XB_CHECK(xb_step(c, scheme));
+  XB_CHECK(download_owned(c, c->E, E));
+  XB_CHECK(download_owned(c, c->B, B));
+  if (kinetic)
+    for (size_t i = 0; i < c->sorts.size(); ++i) XB_CHECK(kinetic_energy(c, c->sorts[i], nullptr, &kinetic[i]));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int xb_run_steps(xb_ctx* c, int32_t scheme, int32_t k, double* ms)
+{
+  XB_API_BEGIN(c);
+  XB_CHECK(ensure_sorted(c));
+  XB_CUDA(cudaEventRecord(c->ev2, c->stream));
+  for (int i = 0; i < k; ++i) XB_CHECK(xb_step(c, scheme));
+  XB_CUDA(cudaEventRecord(c->ev3, c->stream));
+  XB_CUDA(cudaEventSynchronize(c->ev3));
+  float t = 0.f;
+  XB_CUDA(cudaEventElapsedTime(&t, c->ev2, c->ev3));
+  if (ms) *ms = t;
+  return 0;
+}
+
+int xb_run_steps_host(xb_ctx* c, int32_t scheme, int32_t k, double* E, double* B, const double* B0, double* kinetic, double* ms)
+{
+  XB_API_BEGIN(c);
+  XB_CHECK(ensure_sorted(c));
+  XB_CUDA(cudaEventRecord(c->ev2, c->stream));
+  for (int i = 0; i < k; ++i) XB_CHECK(xb_step_host(c, scheme, E, B, B0, kinetic));
+  XB_CUDA(cudaEventRecord(c->ev3, c->stream));
+  XB_CUDA(cudaEventSynchronize(c->ev3));
+  float t = 0.f;
+  XB_CUDA(cudaEventElapsedTime(&t, c->ev2, c->ev3));
+  if (ms) *ms = t;
+  return 0;
+}
+
+int xb_spmv_profile(xb_ctx* c, int32_t enable)
+{
+  XB_API_BEGIN(c);
+  c->spmv_profile = enable != 0;
+  c->spmv_events_used = 0;
+  return 0;
+}
+
+int xb_spmv_profile_read(xb_ctx* c, int64_t* launches, double* total_ms)
+{
+  XB_API_BEGIN(c);
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < c->spmv_events_used; i += 2) {
+    float t = 0.f;
+    XB_CUDA(cudaEventElapsedTime(&t, c->spmv_events[i], c->spmv_events[i + 1]));
+    tot += t;
+  }
+  if (launches) *launches = (int64_t)(c->spmv_events_used / 2);
+  if (total_ms) *total_ms = tot;
+  return 0;
+}
+
+int xb_scalar(xb_ctx* c, int32_t sid, int32_t which, double* out)
+{
+  XB_API_BEGIN(c);
+  if (which == XB_J_DIFF_NORM) {
+    *out = c->j_diff_norm;
+    return 0;
+  }
+  if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
+  Species& s = c->sorts[sid];
+  switch (which) {
+    case XB_KINETIC: return kinetic_energy(c, s, nullptr, out);
+    case XB_PRED_W: *out = s.pred_w; return 0;
+    case XB_CORR_W: *out = s.corr_w; return 0;
+    case XB_PRED_DK: *out = s.pred_dK; return 0;
+    case XB_CORR_DK: *out = s.corr_dK; return 0;
+    case XB_LAMBDA_DK: *out = s.lambda_dK; return 0;
+    case XB_ENERGY_MEMBER: *out = s.energy; return 0;
+  }
+  XB_FAIL("unknown scalar");
+}
+
+int xb_timing(xb_ctx* c, int32_t stage, double* seconds, int64_t* calls)
+{
+  XB_API_BEGIN(c);
+  if (stage < 0 || stage >= XB_STAGE_COUNT) XB_FAIL("bad stage");
+  if (seconds) *seconds = c->clock.seconds[stage];
+  if (calls) *calls = c->clock.calls[stage];
+  return 0;
+}
+
+int xb_timing_reset(xb_ctx* c)
+{
+  XB_API_BEGIN(c);
+  c->clock = StageClock();
+  return 0;
+}
+
+int xb_launch_count(xb_ctx* c, int64_t* launches)
+{
+  XB_API_BEGIN(c);
+  *launches = c->launches;
+  return 0;
+}
+
+int xb_spmv(xb_ctx* c, int32_t op, const double* x, double* y)
+{
+  XB_API_BEGIN(c);
+  XB_CHECK(upload_owned(c, x, c->tmp2));
+  XB_CHECK(spmv(c, op, c->tmp2, c->tmp));
+  XB_CHECK(download_owned(c, c->tmp, y));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int xb_spmv_bench(xb_ctx* c, int32_t op, int32_t reps, double* ms_per_spmv)
+{
+  XB_API_BEGIN(c);
+  // deterministic pseudo-random x: reuse whatever is in E plus a ramp is not needed -- fill tmp2 on host
+  std::vector<double> h(c->g.nown);
+  uint64_t st = 0x9E3779B97F4A7C15ull;
+  for (auto& v : h) {
+    st = st * 6364136223846793005ull + 1442695040888963407ull;
+    v = (double)(st >> 11) / 9007199254740992.0 - 0.5;
+  }
+  XB_CHECK(upload_owned(c, h.data(), c->tmp2));
+  for (int i = 0; i < 3; ++i) XB_CHECK(spmv(c, op, c->tmp2, c->tmp));
+  XB_CUDA(cudaEventRecord(c->ev0, c->stream));
+  for (int i = 0; i < reps; ++i) XB_CHECK(spmv(c, op, c->tmp2, c->tmp));
+  XB_CUDA(cudaEventRecord(c->ev1, c->stream));
+  XB_CUDA(cudaEventSynchronize(c->ev1));
+  float ms = 0.f;
+  XB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  *ms_per_spmv = ms / reps;
+  return 0;
+}
+
+int xb_operator_download(xb_ctx* c, double* coef)
+{
+  XB_API_BEGIN(c);
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  XB_CUDA(cudaMemcpy(coef, c->coef, sizeof(double) * NCOEF * c->g.ncl, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int xb_operator_upload(xb_ctx* c, const double* coef)
+{
+  XB_API_BEGIN(c);
+  XB_CUDA(cudaMemcpy(c->coef, coef, sizeof(double) * NCOEF * c->g.ncl, cudaMemcpyHostToDevice));
+  c->coef_valid = true;
+  return 0;
+}
+
+int xb_deposit(xb_ctx* c)
+{
+  XB_API_BEGIN(c);
+  XB_CHECK(ensure_sorted(c));
+  XB_CHECK(stage_clear(c, XB_ECSIM));
+  XB_CHECK(deposit_moments(c));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int xb_solve(xb_ctx* c, int32_t which, int32_t op, const double* b, double* x)
+{
+  XB_API_BEGIN(c);
+  if (which < 0 || which > 1) XB_FAIL("bad solver slot");
+  XB_CHECK(upload_owned(c, b, c->rhs));
+  XB_CHECK(gmres(c, which, op, c->rhs, c->tmp2));
+  XB_CHECK(download_owned(c, c->tmp2, x));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int xb_curl(xb_ctx* c, int32_t positive, const double* f, double* out)
+{
+  XB_API_BEGIN(c);
+  XB_CHECK(upload_owned(c, f, c->tmp2));
+  XB_CHECK(halo_fill(c, c->tmp2, 1));
+  XB_CHECK(curl_apply(c, positive != 0, c->tmp2, c->tmp, 1.0, false));
+  XB_CHECK(download_owned(c, c->tmp, out));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int xb_kernel_bench(xb_ctx* c, int32_t what, int32_t reps, double* ms)
+{
+  XB_API_BEGIN(c);
+  XB_CHECK(ensure_sorted(c));
+  auto run = [&](int) -> int {
+    switch (what) {
+      case 0:
+        for (auto& s : c->sorts) XB_CHECK(sort_species(c, s, 0.0));
+        return 0;
+      case 1: return deposit_moments(c);
+      case 2:
+        XB_CHECK(halo_fill(c, c->Ep, 1));
+        XB_CHECK(halo_fill(c, c->B, 1));
+        for (auto& s : c->sorts) XB_CHECK(push_second(c, s, c->Ep, c->B));
+        return 0;
+      case 3: XB_CHECK(build_rhs(c, c->currI, c->rhs)); return gmres(c, XB_SOLVER_PREDICT, XB_OP_A, c->rhs, c->tmp2);
+    }
+    xb::set_error("xb_kernel_bench: unknown selector");
+    return 1;
+  };
+  XB_CHECK(run(0));
+  XB_CUDA(cudaEventRecord(c->ev0, c->stream));
+  for (int i = 0; i < reps; ++i) XB_CHECK(run(i));
+  XB_CUDA(cudaEventRecord(c->ev1, c->stream));
+  XB_CUDA(cudaEventSynchronize(c->ev1));
+  float t = 0.f;
+  XB_CUDA(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+  *ms = t / reps;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+// common.cuh -- context, layout conventions and small device helpers shared by every kernel file.
+//
+// Layout conventions (DESIGN.md "Data layout in HBM"):
+//   * grid vectors: [zl + GZ][y][x][c] fp64, zl in [-GZ, nzl + GZ); x/y are never decomposed and
+//     wrap by index arithmetic inside the kernels; the GZ ghost planes per side mirror DMDA's
+//     local vectors (stencil width 4 in the reference, utils/world.h:25; 3 is what the kernels need).
+//   * operator L: coef[k][node], k < NCOEF = 369 fixed (c1, c2, offset) slots per owned node.
+//   * particles: SoA x,y,z,vx,vy,vz (+ optional id), sorted by bin = (cell << 3 | octant), cells over
+//     nzl + 2 planes (plane 0 and nzl + 1 collect particles that left the slab).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/xpic_b200.h"
+
+namespace xb {
+
+constexpr int GZ = 3;  // ghost planes per side of every grid vector
+
+void set_error(const std::string& msg);
+
+#define XB_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) {                                                                            \
+      xb::set_error(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + \
+                    std::to_string(__LINE__));                                                          \
+      return 1;                                                                                         \
+    }                                                                                                   \
+  } while (0)
+
+#define XB_CHECK(expr)    \
+  do {                    \
+    int rc_ = (expr);     \
+    if (rc_) return rc_;  \
+  } while (0)
+
+#define XB_FAIL(msg)      \
+  do {                    \
+    xb::set_error(msg);   \
+    return 1;             \
+  } while (0)
+
+struct Grid {
+  int nx, ny, nz;  // global cells
+  int z0, nzl;     // owned planes [z0, z0 + nzl)
+  int rank, nranks;
+  double dx, dy, dz, dt;
+  double Lx, Ly, Lz;
+  int curl_sign;
+  int64_t plane;  // nx * ny
+  int64_t ncl;    // owned cells = plane * nzl
+  int64_t nown;   // 3 * ncl
+  int64_t ntot;   // 3 * plane * (nzl + 2 GZ)
+  int64_t own0;   // offset of the first owned element = 3 * plane * GZ
+
+  __host__ __device__ inline int64_t vidx(int x, int y, int zl, int c) const
+  {
+    return ((((int64_t)(zl + GZ)) * ny + y) * nx + x) * 3 + c;
+  }
+};
+
+struct Solver {
+  double rtol = 1e-7, atol = 1e-7;  // src/impls/ecsim/simulation.h:15-16
+  int maxit = 100, restart = 30;    // :18, PETSc GMRES default restart
+  int precond = 0;
+  int iterations = 0, reason = 0;
+  double rnorm = 0.0;
+};
+
+struct Species {
+  double q, m, n;
+  int Np;
+  int64_t count = 0, capacity = 0;
+  int cur = 0;                    // which of the two SoA buffers is live
+  double* p[2][6] = {{nullptr}};  // x,y,z,vx,vy,vz
+  uint64_t* id[2] = {nullptr, nullptr};
+  int32_t* key = nullptr;        // bin of every particle (capacity)
+  int32_t* bin_start = nullptr;  // nbins + 1, valid after sort
+  double* currI = nullptr;       // per-sort currents (ghosted grid vectors)
+  double* currJe = nullptr;
+  uint64_t next_id = 0;
+  bool sorted = false;
+  // ecsimcorr::Particles scalars (src/impls/ecsimcorr/particles.h:33-38)
+  double energy = 0, pred_w = 0, corr_w = 0, pred_dK = 0, corr_dK = 0, lambda_dK = 0;
+};
+
+struct Comm;  // comm.cu (NCCL over NVLink, loaded lazily)
+
+struct StageClock {
+  double seconds[XB_STAGE_COUNT] = {0};
+  int64_t calls[XB_STAGE_COUNT] = {0};
+};
+
+}  // namespace xb
+
+struct xb_ctx {
+  xb::Grid g;
+  int device = 0;
+  bool track_ids = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  bool spmv_profile = false;
+  std::vector<cudaEvent_t> spmv_events;  // pairs (start, stop), recorded around every operator launch
+  size_t spmv_events_used = 0;
+  // named grid vectors (ghosted)
+  double *E = nullptr, *B = nullptr, *B0 = nullptr, *Ep = nullptr, *Ec = nullptr, *currI = nullptr, *currJe = nullptr;
+  double *rhs = nullptr, *tmp = nullptr, *tmp2 = nullptr;
+  // operator L, stencil layout
+  double* coef = nullptr;
+  bool coef_valid = false;
+  // deposit staging (cell blocks)
+  double* stage = nullptr;
+  int64_t stage_cells = 0;
+  // Krylov workspace
+  std::vector<double*> V;  // restart + 1 basis vectors (ghosted)
+  double* Z = nullptr;     // preconditioned direction (ghosted)
+  double *cheb_r = nullptr, *cheb_d = nullptr, *cheb_Md = nullptr;  // Chebyshev work vectors (ghosted)
+  double* ksp_u = nullptr;  // sum y_i V_i before right preconditioning
+  double* red_partial = nullptr;  // [RED_BLOCKS][RED_MAXV]
+  double* red_out = nullptr;      // device results
+  double* red_host = nullptr;     // pinned
+  double* hcoef_dev = nullptr;    // small coefficient vectors for multi-axpy
+  // sort workspace
+  int32_t* hist = nullptr;
+  int32_t* cursor = nullptr;
+  int32_t* scan_tmp = nullptr;
+  int64_t nbins = 0;
+  // host staging
+  double* pinned = nullptr;
+  size_t pinned_bytes = 0;
+
+  std::vector<xb::Species> sorts;
+  xb::Solver solver[2];
+  xb::StageClock clock;
+  xb::Comm* comm = nullptr;
+  int64_t launches = 0;
+  double j_diff_norm = 0.0;
+};
+
+namespace xb {
+
+constexpr int RED_BLOCKS = 1184;  // 148 SMs x 8
+constexpr int RED_THREADS = 256;
+constexpr int RED_MAXV = 32;
+
+// ---- fields.cu -------------------------------------------------------------------------------
+int halo_fill(xb_ctx* c, double* v, int width);                 // DMGlobalToLocal(INSERT)
+int halo_reduce(xb_ctx* c, double* v, int width_lo, int width_hi);  // DMLocalToGlobal(ADD)
+int vec_zero(xb_ctx* c, double* v);                              // whole ghosted vector
+int vec_copy_owned(xb_ctx* c, const double* src, double* dst);
+int curl_apply(xb_ctx* c, bool positive, const double* f, double* out, double scale, bool accumulate);
+int build_rhs(xb_ctx* c, const double* curr, double* rhs);       // 2E - dt curr + dt curl^-(B - B0)
+int final_update(xb_ctx* c, const double* Ehalf);                // E = 2 Eh - E ; B -= dt curl^+ Eh
+int dots(xb_ctx* c, int nv, const double* const* vs, const double* w, double* host_out);  // host_out[i] = vs[i].w
+int axpy_multi(xb_ctx* c, int nv, const double* const* vs, const double* coef_host, double* w);  // w += sum coef_i vs_i
+int scale_into(xb_ctx* c, const double* w, double alpha, double* out);                            // out = alpha w
+int axpby(xb_ctx* c, double a, const double* x, double b, double* y);                             // y = a x + b y
+int upload_owned(xb_ctx* c, const double* host, double* dev);
+int download_owned(xb_ctx* c, const double* dev, double* host);
+
+// ---- spmv.cu ---------------------------------------------------------------------------------
+int spmv(xb_ctx* c, int op, double* x_ghosted, double* y);  // fills x's halo (width 2) itself
+
+// ---- krylov.cu -------------------------------------------------------------------------------
+int gmres(xb_ctx* c, int which, int op, const double* b, double* x);
+
+// ---- particles.cu ----------------------------------------------------------------------------
+int species_alloc(xb_ctx* c, Species& s, int64_t capacity);
+void species_free(Species& s);
+int particles_sort(xb_ctx* c, Species& s, double dt_move);   // r += v dt_move, wrap, re-bin
+int push_second(xb_ctx* c, Species& s, const double* Eh, const double* B);
+int kinetic_energy(xb_ctx* c, Species& s, double* sum_v2, double* K);
+int scale_velocities(xb_ctx* c, Species& s, double lambda);
+
+// ---- deposit.cu ------------------------------------------------------------------------------
+int deposit_moments(xb_ctx* c);  // currI (+ per sort) and coef from all sorts
+
+// ---- esirkepov.cu ----------------------------------------------------------------------------
+int push_first_corr(xb_ctx* c, Species& s);
+int push_second_corr(xb_ctx* c, Species& s, const double* Eh, const double* B);
+
+// ---- launch bookkeeping ----------------------------------------------------------------------
+#define XB_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
+  do {                                                                          \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
+    (ctx)->launches++;                                                          \
+    XB_CUDA(cudaGetLastError());                                                \
+  } while (0)
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int wrapi(int i, int n)
+{
+  i %= n;
+  return i < 0 ? i + n : i;
+}
+
+}  // namespace xb

@@ -1,0 +1,309 @@
+// deposit.cu -- ECSIM moments: implicit current I and the 3x3-block particle mass matrices L.
+//
+// Replaces ecsim::Particles::fill_ecsim_current / decompose_ecsim_current
+// (src/impls/ecsim/particles.cpp:33-173), Simulation::fill_matrix_indices (simulation.cpp:370-469)
+// and PETSc's MatSetPreallocationCOO / MatSetValuesCOO duplicate summation (:359,366).
+//
+// Two atomic-free, order-deterministic passes:
+//  1. k_cell_blocks: one warp per cell.  Particles are sorted by (cell, half-cell octant), so all
+//     particles of a bin share one 24-point footprint; every lane owns 18 fixed entries of the
+//     octant's 24 x 24 (component, point) outer-product block in registers and loops over the bin's
+//     particles (per-particle weights / alpha / I_p are computed once by one lane each and
+//     broadcast through shared memory).  After each octant the lane adds its registers into the
+//     cell's private 9 x 12 x 12 block (the reference's coo_v layout, particles.cpp:145-163) kept
+//     in shared memory; finished blocks are written to a staging area in coalesced 64-byte runs
+//     (stage[group of 8 cells][entry][cell % 8]).
+//  2. k_gather_rows / k_gather_current: one thread per (node, component pair); sums, in a fixed
+//     order, the entries of the <= 12 neighbouring cell blocks that land on each of the node's
+//     fixed-offset coefficient slots and writes the coefficient planes coalesced.
+//
+// Roofline: pass 1 is FP64-FMA bound (576 FMA per particle), pass 2 HBM bound
+// (1332 * 8 B read + 369 * 8 B written per cell).
+#include "common.cuh"
+#include "gather.cuh"
+#include "stencil.cuh"
+
+namespace xb {
+
+constexpr int DEP_WARPS = CELL_GROUP;  // one warp per cell, 8 cells per CTA
+constexpr int DEP_CHUNK = 16;          // particles staged per round
+constexpr int REC = 36;                // s[3][8], A*alpha[9], I_p[3]
+constexpr int DEP_SMEM_PER_WARP = BLOCK_ALL + DEP_CHUNK * REC;
+
+// window position of point t = (k, j, i) of component c for a particle of octant (ox, oy, oz)
+// src/impls/ecsim/particles.cpp:145-147
+__device__ __forceinline__ int block_pos(int c, int t, int ox, int oy, int oz)
+{
+  const int i = t & 1, j = (t >> 1) & 1, k = t >> 2;
+  if (c == 0) return (k * 2 + j) * 3 + (ox + i);
+  if (c == 1) return (k * 3 + (oy + j)) * 2 + i;
+  return ((oz + k) * 2 + j) * 2 + i;
+}
+
+struct DepositArgs {
+  const double* p[6];
+  const int32_t* bin_start;
+  int64_t bin_cell0;    // first cell (in bin space) of this launch
+  int64_t ncells;       // cells in this launch
+  int64_t stage_cell0;  // staging cell id of the first cell
+  int zshift;
+  double q, m, mpw;
+};
+
+__global__ void __launch_bounds__(DEP_WARPS * 32) k_cell_blocks(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage)
+{
+  extern __shared__ double smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* block = smem + (size_t)wid * DEP_SMEM_PER_WARP;
+  double* rec = block + BLOCK_ALL;
+  const int64_t cell_local = (int64_t)blockIdx.x * CELL_GROUP + wid;
+
+  for (int e = lane; e < BLOCK_ALL; e += 32) block[e] = 0.0;
+  __syncwarp();
+
+  if (cell_local < a.ncells) {
+    const int64_t bin0 = (a.bin_cell0 + cell_local) << 3;
+    const int g1 = lane >> 2;      // row point t1
+    const int h2 = (lane & 3) * 2;  // column points t2 = h2, h2 + 1
+    const int cI = lane >> 3, tI = lane & 7;  // current entry owned by lanes < 24
+    for (int oct = 0; oct < 8; ++oct) {
+      const int32_t b0 = a.bin_start[bin0 + oct], b1 = a.bin_start[bin0 + oct + 1];
+      if (b0 == b1) continue;
+      double acc[3][3][2];
+#pragma unroll
+      for (int c1 = 0; c1 < 3; ++c1)
+#pragma unroll
+        for (int c2 = 0; c2 < 3; ++c2) acc[c1][c2][0] = acc[c1][c2][1] = 0.0;
+      double accI = 0.0;
+      for (int32_t base = b0; base < b1; base += DEP_CHUNK) {
+        const int cnt = min(DEP_CHUNK, b1 - base);
+        if (lane < cnt) {
+          const int32_t i = base + lane;
+          const double px = a.p[0][i], py = a.p[1][i], pz = a.p[2][i];
+          const double v[3] = {a.p[3][i], a.p[4][i], a.p[5][i]};
+          Weights w;
+          make_weights(g, px, py, pz, a.zshift, w);
+          double Bp[3], b[3];
+          gather_B(g, B, w, Bp);
+          const double f = (0.5 * g.dt) * a.q / a.m;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) b[c] = Bp[c] * f;
+          double vxb[3];
+          cross3(v, b, vxb);
+          const double vb = dot3(v, b), b2 = dot3(b, b);
+          double* r = rec + lane * REC;
+          const double ci = a.q * a.mpw / (1. + b2);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) r[33 + c] = ci * (v[c] + vxb[c] + vb * b[c]);
+          const double Ap = 0.5 * g.dt * g.dt * a.mpw * a.q * a.q / a.m / (1 + b2);
+          r[24 + 0] = Ap * (1.0 + b[0] * b[0]);
+          r[24 + 1] = Ap * (+b[2] + b[0] * b[1]);
+          r[24 + 2] = Ap * (-b[1] + b[0] * b[2]);
+          r[24 + 3] = Ap * (-b[2] + b[1] * b[0]);
+          r[24 + 4] = Ap * (1.0 + b[1] * b[1]);
+          r[24 + 5] = Ap * (+b[0] + b[1] * b[2]);
+          r[24 + 6] = Ap * (+b[1] + b[2] * b[0]);
+          r[24 + 7] = Ap * (-b[0] + b[2] * b[1]);
+          r[24 + 8] = Ap * (1.0 + b[2] * b[2]);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int i1 = t & 1, j1 = (t >> 1) & 1, k1 = t >> 2;
+            r[0 + t] = w.wn[2][k1] * w.wn[1][j1] * w.ws[0][i1];
+            r[8 + t] = w.wn[2][k1] * w.ws[1][j1] * w.wn[0][i1];
+            r[16 + t] = w.ws[2][k1] * w.wn[1][j1] * w.wn[0][i1];
+          }
+        }
+        __syncwarp();
+        for (int p = 0; p < cnt; ++p) {
+          const double* r = rec + p * REC;
+          double s1[3], s2[3][2];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            s1[c] = r[c * 8 + g1];
+            const double2 t2 = *reinterpret_cast<const double2*>(r + c * 8 + h2);
+            s2[c][0] = t2.x;
+            s2[c][1] = t2.y;
+          }
+#pragma unroll
+          for (int c1 = 0; c1 < 3; ++c1)
+#pragma unroll
+            for (int c2 = 0; c2 < 3; ++c2) {
+              const double t = s1[c1] * r[24 + c1 * 3 + c2];
+              acc[c1][c2][0] += t * s2[c2][0];
+              acc[c1][c2][1] += t * s2[c2][1];
+            }
+          if (lane < 24) accI += r[cI * 8 + tI] * r[33 + cI];
+        }
+        __syncwarp();
+      }
+      // fold the octant's registers into the cell block
+      const int ox = oct & 1, oy = (oct >> 1) & 1, oz = oct >> 2;
+#pragma unroll
+      for (int c1 = 0; c1 < 3; ++c1) {
+        const int row = block_pos(c1, g1, ox, oy, oz);
+#pragma unroll
+        for (int c2 = 0; c2 < 3; ++c2) {
+          const int e = (c1 * 3 + c2) * 144 + row * 12;
+          block[e + block_pos(c2, h2, ox, oy, oz)] += acc[c1][c2][0];
+          block[e + block_pos(c2, h2 + 1, ox, oy, oz)] += acc[c1][c2][1];
+        }
+      }
+      if (lane < 24) block[BLOCK_MAT + cI * 12 + block_pos(cI, tI, ox, oy, oz)] += accI;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // coalesced write-out: stage[group][entry][cell % 8]
+  double* out = stage + ((a.stage_cell0 >> 3) + blockIdx.x) * (int64_t)(BLOCK_ALL * CELL_GROUP);
+  for (int idx = threadIdx.x; idx < BLOCK_ALL * CELL_GROUP; idx += DEP_WARPS * 32) {
+    const int e = idx >> 3, w = idx & 7;
+    out[idx] = smem[(size_t)w * DEP_SMEM_PER_WARP + e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: gather cell blocks into the fixed-offset rows
+// ---------------------------------------------------------------------------------------------
+struct GatherArgs {
+  const double* stage;
+  int single_rank;  // 1: staging planes = owned planes, z wraps; 0: staging plane = zl + 1
+};
+
+__device__ __forceinline__ int64_t stage_cell(const Grid& g, const GatherArgs& a, int x, int y, int zl)
+{
+  const int pz = a.single_rank ? wrapi(zl, g.nzl) : zl + 1;
+  return ((int64_t)pz * g.ny + y) * g.nx + x;
+}
+
+__device__ __forceinline__ double stage_read(const double* __restrict__ stage, int64_t cell, int e)
+{
+  return __ldg(stage + (cell >> 3) * (int64_t)(BLOCK_ALL * CELL_GROUP) + (int64_t)e * CELL_GROUP + (cell & 7));
+}
+
+template <int C1, int C2>
+__global__ void __launch_bounds__(128) k_gather_rows(Grid g, GatherArgs a, double* __restrict__ coef, int accumulate)
+{
+  const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (node >= g.ncl) return;
+  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = (int)(node / g.plane);
+  constexpr int NS = pair_size(C1, C2);
+  double acc[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+#pragma unroll
+  for (int k1 = 0; k1 < win_n(C1, 2); ++k1)
+#pragma unroll
+    for (int j1 = 0; j1 < win_n(C1, 1); ++j1)
+#pragma unroll
+      for (int i1 = 0; i1 < win_n(C1, 0); ++i1) {
+        const int o1x = win_lo(C1, 0) + i1, o1y = win_lo(C1, 1) + j1, o1z = win_lo(C1, 2) + k1;
+        // the cell whose window point (i1, j1, k1) is this node
+        const int64_t cell = stage_cell(g, a, wrapi(x - o1x, g.nx), wrapi(y - o1y, g.ny), zl - o1z);
+        const int ebase = (C1 * 3 + C2) * 144 + win_index(C1, i1, j1, k1) * 12;
+#pragma unroll
+        for (int k2 = 0; k2 < win_n(C2, 2); ++k2)
+#pragma unroll
+          for (int j2 = 0; j2 < win_n(C2, 1); ++j2)
+#pragma unroll
+            for (int i2 = 0; i2 < win_n(C2, 0); ++i2) {
+              const int dx = win_lo(C2, 0) + i2 - o1x, dy = win_lo(C2, 1) + j2 - o1y, dz = win_lo(C2, 2) + k2 - o1z;
+              if (in_range(C1, C2, dx, dy, dz))
+                acc[coef_slot(C1, C2, dx, dy, dz) - pair_base(C1, C2)] += stage_read(a.stage, cell, ebase + win_index(C2, i2, j2, k2));
+            }
+      }
+  double* out = coef + (int64_t)pair_base(C1, C2) * g.ncl + node;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    if (accumulate)
+      out[(int64_t)s * g.ncl] += acc[s];
+    else
+      out[(int64_t)s * g.ncl] = acc[s];
+  }
+}
+
+// currI of one sort at the owned nodes; also accumulated into the simulation's total current
+__global__ void k_gather_current(Grid g, GatherArgs a, double* __restrict__ sort_currI, double* __restrict__ sim_currI)
+{
+  const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (node >= g.ncl) return;
+  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = (int)(node / g.plane);
+  double r[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int k = 0; k < win_n(c, 2); ++k)
+#pragma unroll
+      for (int j = 0; j < win_n(c, 1); ++j)
+#pragma unroll
+        for (int i = 0; i < win_n(c, 0); ++i) {
+          const int64_t cell = stage_cell(g, a, wrapi(x - (win_lo(c, 0) + i), g.nx), wrapi(y - (win_lo(c, 1) + j), g.ny), zl - (win_lo(c, 2) + k));
+          r[c] += stage_read(a.stage, cell, BLOCK_MAT + c * 12 + win_index(c, i, j, k));
+        }
+  const int64_t o = g.vidx(x, y, zl, 0);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    sort_currI[o + c] = r[c];
+    sim_currI[o + c] += r[c];
+  }
+}
+
+template <int C1, int C2>
+static int launch_gather(xb_ctx* c, const GatherArgs& ga, int accumulate)
+{
+  const int blocks = (int)((c->g.ncl + 127) / 128);
+  XB_LAUNCH(c, (k_gather_rows<C1, C2>), blocks, 128, 0, c->g, ga, c->coef, accumulate);
+  return 0;
+}
+
+int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage);  // migrate.cu (multi-rank only)
+
+int deposit_moments(xb_ctx* c)
+{
+  const Grid& g = c->g;
+  static bool attr_set = false;
+  const size_t smem = sizeof(double) * DEP_SMEM_PER_WARP * DEP_WARPS;
+  if (!attr_set) {
+    XB_CUDA(cudaFuncSetAttribute(k_cell_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  XB_CHECK(halo_fill(c, c->B, GZ));
+  const bool single = g.nranks == 1;
+  bool first = true;
+  for (auto& s : c->sorts) {
+    if (!s.sorted) XB_FAIL("deposit: particles are not sorted");
+    DepositArgs a;
+    double** p = s.p[s.cur];
+    for (int k = 0; k < 6; ++k) a.p[k] = p[k];
+    a.bin_start = s.bin_start;
+    a.bin_cell0 = g.plane;  // bin plane 1 = first owned plane
+    a.ncells = g.ncl;
+    a.stage_cell0 = single ? 0 : g.plane;
+    a.zshift = 0;
+    a.q = s.q;
+    a.m = s.m;
+    a.mpw = s.n / (double)s.Np;
+    if ((a.stage_cell0 & 7) != 0) XB_FAIL("deposit: plane size must be a multiple of 8 cells in multi-rank runs");
+    const int groups = (int)((a.ncells + CELL_GROUP - 1) / CELL_GROUP);
+    XB_LAUNCH(c, k_cell_blocks, groups, DEP_WARPS * 32, smem, g, a, c->B, c->stage);
+    if (!single) XB_CHECK(deposit_ghost_cells(c, s, c->stage));
+    GatherArgs ga{c->stage, single ? 1 : 0};
+    const int acc = first ? 0 : 1;
+    XB_CHECK((launch_gather<0, 0>(c, ga, acc)));
+    XB_CHECK((launch_gather<0, 1>(c, ga, acc)));
+    XB_CHECK((launch_gather<0, 2>(c, ga, acc)));
+    XB_CHECK((launch_gather<1, 0>(c, ga, acc)));
+    XB_CHECK((launch_gather<1, 1>(c, ga, acc)));
+    XB_CHECK((launch_gather<1, 2>(c, ga, acc)));
+    XB_CHECK((launch_gather<2, 0>(c, ga, acc)));
+    XB_CHECK((launch_gather<2, 1>(c, ga, acc)));
+    XB_CHECK((launch_gather<2, 2>(c, ga, acc)));
+    const int blocks = (int)((g.ncl + 127) / 128);
+    XB_LAUNCH(c, k_gather_current, blocks, 128, 0, g, ga, s.currI, c->currI);
+    first = false;
+  }
+  if (c->sorts.empty()) XB_CUDA(cudaMemsetAsync(c->coef, 0, sizeof(double) * NCOEF * g.ncl, c->stream));
+  c->coef_valid = true;
+  return 0;
+}
+
+}  // namespace xb

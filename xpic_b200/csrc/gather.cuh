@@ -1,0 +1,106 @@
+// gather.cuh -- per-particle CIC weights on the Yee lattice, field gather and the Boris update.
+// Arithmetic follows src/impls/ecsim/simulation.cpp:8-118 (weights :17-43, E :51-57, B :107-113)
+// and src/algorithms/boris_push.cpp:48-57 operation by operation.
+#pragma once
+#include "common.cuh"
+
+namespace xb {
+
+struct Weights {
+  int in[3], is[3];  // nodal / staggered lower index; z entries are LOCAL plane indices
+  double wn[3][2], ws[3][2];
+};
+
+__device__ __forceinline__ void cell_and_octant(double xn, int& i, int& o)
+{
+  i = (int)floor(xn);
+  const int is = (int)floor(xn - 0.5);
+  o = is - i + 1;  // src/impls/ecsim/particles.cpp:92-94
+}
+
+__device__ __forceinline__ void axis_weights(double r, double d, int& in, int& is, double* wn, double* ws)
+{
+  const double xn = r / d;
+  const double xs = xn - 0.5;
+  in = (int)floor(xn);
+  is = (int)floor(xs);
+  wn[1] = xn - in;
+  wn[0] = 1 - wn[1];
+  ws[1] = xs - is;
+  ws[0] = 1 - ws[1];
+}
+
+// zshift: planes added to the z indices (0 for owned particles; -+nz for ghost copies that came
+// across the periodic boundary, so their weights stay bit-identical to the owner's)
+__device__ __forceinline__ void make_weights(const Grid& g, double px, double py, double pz, int zshift, Weights& w)
+{
+  axis_weights(px, g.dx, w.in[0], w.is[0], w.wn[0], w.ws[0]);
+  axis_weights(py, g.dy, w.in[1], w.is[1], w.wn[1], w.ws[1]);
+  axis_weights(pz, g.dz, w.in[2], w.is[2], w.wn[2], w.ws[2]);
+  w.in[2] += zshift - g.z0;
+  w.is[2] += zshift - g.z0;
+}
+
+__device__ __forceinline__ void gather_E(const Grid& g, const double* __restrict__ E, const Weights& w, double* Ep)
+{
+  Ep[0] = Ep[1] = Ep[2] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double sx = w.wn[2][k] * w.wn[1][j] * w.ws[0][i];
+        const double sy = w.wn[2][k] * w.ws[1][j] * w.wn[0][i];
+        const double sz = w.ws[2][k] * w.wn[1][j] * w.wn[0][i];
+        Ep[0] += __ldg(&E[g.vidx(wrapi(w.is[0] + i, g.nx), wrapi(w.in[1] + j, g.ny), w.in[2] + k, 0)]) * sx;
+        Ep[1] += __ldg(&E[g.vidx(wrapi(w.in[0] + i, g.nx), wrapi(w.is[1] + j, g.ny), w.in[2] + k, 1)]) * sy;
+        Ep[2] += __ldg(&E[g.vidx(wrapi(w.in[0] + i, g.nx), wrapi(w.in[1] + j, g.ny), w.is[2] + k, 2)]) * sz;
+      }
+}
+
+__device__ __forceinline__ void gather_B(const Grid& g, const double* __restrict__ B, const Weights& w, double* Bp)
+{
+  Bp[0] = Bp[1] = Bp[2] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double sx = w.ws[2][k] * w.ws[1][j] * w.wn[0][i];
+        const double sy = w.ws[2][k] * w.wn[1][j] * w.ws[0][i];
+        const double sz = w.wn[2][k] * w.ws[1][j] * w.ws[0][i];
+        Bp[0] += __ldg(&B[g.vidx(wrapi(w.in[0] + i, g.nx), wrapi(w.is[1] + j, g.ny), w.is[2] + k, 0)]) * sx;
+        Bp[1] += __ldg(&B[g.vidx(wrapi(w.is[0] + i, g.nx), wrapi(w.in[1] + j, g.ny), w.is[2] + k, 1)]) * sy;
+        Bp[2] += __ldg(&B[g.vidx(wrapi(w.is[0] + i, g.nx), wrapi(w.is[1] + j, g.ny), w.in[2] + k, 2)]) * sz;
+      }
+}
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* o)
+{
+  o[0] = +(a[1] * b[2] - a[2] * b[1]);
+  o[1] = -(a[0] * b[2] - a[2] * b[0]);
+  o[2] = +(a[0] * b[1] - a[1] * b[0]);
+}
+
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+__device__ __forceinline__ void boris_update_vEB(double dt, double qm, const double* Ep, const double* Bp, double* v)
+{
+  const double alpha = dt * qm;
+  double a[3], b[3], w[3], bw[3], bbw[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    a[c] = +alpha * Ep[c];
+    b[c] = -alpha * Bp[c];
+    w[c] = v[c] + 0.5 * a[c];
+  }
+  cross3(b, w, bw);
+  cross3(b, bw, bbw);
+  const double den = 1.0 + 0.25 * dot3(b, b);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v[c] += a[c] + (bw[c] + 0.5 * bbw[c]) / den;
+}
+
+}  // namespace xb

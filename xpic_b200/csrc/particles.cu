@@ -1,0 +1,362 @@
+// particles.cu -- cell-sorted SoA particle store: move + periodic wrap + re-binning (counting
+// sort by (cell, half-cell octant)), field gather + Boris velocity update, kinetic energy.
+//
+// Reference code replaced:
+//   BorisPush::update_r            src/algorithms/boris_push.cpp:19-22   (fused into the key pass)
+//   Particles::update_cells_seq    src/interfaces/particles.cpp:79-116   (wrap + re-bin)
+//   g_bound_periodic               src/interfaces/point.cpp:18-26
+//   interpolate_E_s1 / B_s1        src/impls/ecsim/simulation.cpp:8-118
+//   BorisPush::update_vEB          src/algorithms/boris_push.cpp:48-57
+//   ecsim::Particles::second_push  src/impls/ecsim/particles.cpp:175-192
+//   Energy::calculate_kinetic      src/diagnostics/energy.cpp:61-107
+// All kernels are HBM-bound streams over the SoA arrays (72 B / particle for a push).
+#include "common.cuh"
+#include "gather.cuh"
+
+namespace xb {
+
+static inline int grid_for(int64_t n, int threads = 256)
+{
+  int64_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > 0x7fffffff) b = 0x7fffffff;
+  return (int)b;
+}
+
+int species_alloc(xb_ctx* c, Species& s, int64_t capacity)
+{
+  s.capacity = capacity;
+  for (int b = 0; b < 2; ++b) {
+    for (int k = 0; k < 6; ++k) XB_CUDA(cudaMalloc(&s.p[b][k], sizeof(double) * capacity));
+    if (c->track_ids) XB_CUDA(cudaMalloc(&s.id[b], sizeof(uint64_t) * capacity));
+  }
+  XB_CUDA(cudaMalloc(&s.key, sizeof(int32_t) * capacity));
+  XB_CUDA(cudaMalloc(&s.bin_start, sizeof(int32_t) * (c->nbins + 1)));
+  XB_CUDA(cudaMemset(s.bin_start, 0, sizeof(int32_t) * (c->nbins + 1)));
+  XB_CUDA(cudaMalloc(&s.currI, sizeof(double) * c->g.ntot));
+  XB_CUDA(cudaMalloc(&s.currJe, sizeof(double) * c->g.ntot));
+  XB_CUDA(cudaMemset(s.currI, 0, sizeof(double) * c->g.ntot));
+  XB_CUDA(cudaMemset(s.currJe, 0, sizeof(double) * c->g.ntot));
+  return 0;
+}
+
+void species_free(Species& s)
+{
+  for (int b = 0; b < 2; ++b) {
+    for (int k = 0; k < 6; ++k) cudaFree(s.p[b][k]);
+    cudaFree(s.id[b]);
+  }
+  cudaFree(s.key);
+  cudaFree(s.bin_start);
+  cudaFree(s.currI);
+  cudaFree(s.currJe);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: r += v * dtm, periodic wrap (point.cpp:18-26), bin key, histogram
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double wrap_coord(double s, double L)
+{
+  if (s < 0.0)
+    s = L - (0.0 - s);
+  else if (s > L)
+    s = 0.0 + (s - L);
+  // s == L is the same point as 0 (the reference would index cell N there and drop the particle,
+  // src/interfaces/particles.cpp:101-104; a measure-zero event we fold back instead)
+  if (s >= L) s = 0.0;
+  if (s < 0.0) s = 0.0;
+  return s;
+}
+
+__global__ void k_move_key(Grid g, int64_t n, double* __restrict__ x, double* __restrict__ y, double* __restrict__ z,
+                           const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz, double dtm,
+                           int32_t* __restrict__ key, int32_t* __restrict__ hist)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double px = x[i], py = y[i], pz = z[i];
+  if (dtm != 0.0) {
+    px += vx[i] * dtm;
+    py += vy[i] * dtm;
+    pz += vz[i] * dtm;
+  }
+  px = wrap_coord(px, g.Lx);
+  py = wrap_coord(py, g.Ly);
+  pz = wrap_coord(pz, g.Lz);
+  x[i] = px;
+  y[i] = py;
+  z[i] = pz;
+  int ix, iy, iz, ox, oy, oz;
+  cell_and_octant(px / g.dx, ix, ox);
+  cell_and_octant(py / g.dy, iy, oy);
+  cell_and_octant(pz / g.dz, iz, oz);
+  ix = min(max(ix, 0), g.nx - 1);
+  iy = min(max(iy, 0), g.ny - 1);
+  iz = min(max(iz, 0), g.nz - 1);
+  int pl;
+  const int rel = iz - g.z0;
+  if (rel >= 0 && rel < g.nzl)
+    pl = rel + 1;
+  else {
+    const int up = (iz - (g.z0 + g.nzl) + 2 * g.nz) % g.nz;  // planes above the slab top (periodic)
+    const int dn = (g.z0 - 1 - iz + 2 * g.nz) % g.nz;        // planes below the slab bottom
+    pl = up <= dn ? g.nzl + 1 : 0;
+  }
+  const int32_t k = (int32_t)(((((int64_t)pl * g.ny + iy) * g.nx + ix) << 3) | (oz << 2) | (oy << 1) | ox);
+  key[i] = k;
+  atomicAdd(&hist[k], 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of the histogram (int32), three small kernels
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t n,
+                                                            int32_t* __restrict__ tile_sums)
+{
+  __shared__ int32_t warp_tot[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int32_t v[SCAN_ITEMS];
+  int32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = base + k < n ? in[base + k] : 0;
+    sum += v[k];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int32_t w = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    if (lane < SCAN_THREADS / 32) warp_tot[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  int32_t run = incl - sum + (wid > 0 ? warp_tot[wid - 1] : 0);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == SCAN_THREADS - 1) tile_sums[blockIdx.x] = run;
+}
+
+__global__ void k_scan_sums(int32_t* __restrict__ tile_sums, int ntiles, int32_t* __restrict__ total_out)
+{
+  // one block; sequential over chunks of blockDim
+  __shared__ int32_t carry;
+  __shared__ int32_t wt[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < ntiles; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int32_t v = i < ntiles ? tile_sums[i] : 0;
+    int32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wt[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int32_t w = lane < (blockDim.x >> 5) ? wt[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      wt[lane] = w;
+    }
+    __syncthreads();
+    const int32_t excl = carry + incl - v + (wid > 0 ? wt[wid - 1] : 0);
+    if (i < ntiles) tile_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void k_scan_add(int32_t* __restrict__ out, int64_t n, const int32_t* __restrict__ tile_sums, int32_t* __restrict__ cursor)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t v = out[i] + tile_sums[i / SCAN_TILE];
+  out[i] = v;
+  cursor[i] = v;
+}
+
+// pass 2: scatter into the other SoA buffer
+__global__ void k_scatter(int64_t n, const int32_t* __restrict__ key, int32_t* __restrict__ cursor, const double* __restrict__ s0,
+                          const double* __restrict__ s1, const double* __restrict__ s2, const double* __restrict__ s3,
+                          const double* __restrict__ s4, const double* __restrict__ s5, const uint64_t* __restrict__ sid,
+                          double* __restrict__ d0, double* __restrict__ d1, double* __restrict__ d2, double* __restrict__ d3,
+                          double* __restrict__ d4, double* __restrict__ d5, uint64_t* __restrict__ did)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t pos = atomicAdd(&cursor[key[i]], 1);
+  d0[pos] = s0[i];
+  d1[pos] = s1[i];
+  d2[pos] = s2[i];
+  d3[pos] = s3[i];
+  d4[pos] = s4[i];
+  d5[pos] = s5[i];
+  if (sid) did[pos] = sid[i];
+}
+
+// canonical order inside a bin: ascending particle id (makes every later sum reproducible).
+// one thread per bin, insertion sort (bins hold ~ppc/8 particles).
+__global__ void k_order_bins(int64_t nbins, const int32_t* __restrict__ bin_start, double* __restrict__ p0, double* __restrict__ p1,
+                             double* __restrict__ p2, double* __restrict__ p3, double* __restrict__ p4, double* __restrict__ p5,
+                             uint64_t* __restrict__ id)
+{
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= nbins) return;
+  const int32_t lo = bin_start[b], hi = bin_start[b + 1];
+  for (int32_t i = lo + 1; i < hi; ++i) {
+    const uint64_t kid = id[i];
+    int32_t j = i - 1;
+    if (id[j] <= kid) continue;
+    const double a0 = p0[i], a1 = p1[i], a2 = p2[i], a3 = p3[i], a4 = p4[i], a5 = p5[i];
+    while (j >= lo && id[j] > kid) {
+      id[j + 1] = id[j];
+      p0[j + 1] = p0[j];
+      p1[j + 1] = p1[j];
+      p2[j + 1] = p2[j];
+      p3[j + 1] = p3[j];
+      p4[j + 1] = p4[j];
+      p5[j + 1] = p5[j];
+      --j;
+    }
+    id[j + 1] = kid;
+    p0[j + 1] = a0;
+    p1[j + 1] = a1;
+    p2[j + 1] = a2;
+    p3[j + 1] = a3;
+    p4[j + 1] = a4;
+    p5[j + 1] = a5;
+  }
+}
+
+int particles_sort(xb_ctx* c, Species& s, double dt_move)
+{
+  const Grid& g = c->g;
+  const int64_t n = s.count;
+  XB_CUDA(cudaMemsetAsync(c->hist, 0, sizeof(int32_t) * c->nbins, c->stream));
+  double** p = s.p[s.cur];
+  if (n > 0) XB_LAUNCH(c, k_move_key, grid_for(n), 256, 0, g, n, p[0], p[1], p[2], p[3], p[4], p[5], dt_move, s.key, c->hist);
+  if (g.nranks > 1) XB_FAIL("particles_sort: multi-rank migration goes through migrate.cu");
+  const int ntiles = (int)((c->nbins + SCAN_TILE - 1) / SCAN_TILE);
+  XB_LAUNCH(c, k_scan_tiles, ntiles, SCAN_THREADS, 0, c->hist, s.bin_start, c->nbins, c->scan_tmp);
+  XB_LAUNCH(c, k_scan_sums, 1, 1024, 0, c->scan_tmp, ntiles, s.bin_start + c->nbins);
+  XB_LAUNCH(c, k_scan_add, grid_for(c->nbins), 256, 0, s.bin_start, c->nbins, c->scan_tmp, c->cursor);
+  double** d = s.p[1 - s.cur];
+  if (n > 0)
+    XB_LAUNCH(c, k_scatter, grid_for(n), 256, 0, n, s.key, c->cursor, p[0], p[1], p[2], p[3], p[4], p[5], s.id[s.cur], d[0], d[1], d[2], d[3], d[4],
+              d[5], s.id[1 - s.cur]);
+  s.cur = 1 - s.cur;
+  if (c->track_ids && n > 0) {
+    double** q = s.p[s.cur];
+    XB_LAUNCH(c, k_order_bins, grid_for(c->nbins, 128), 128, 0, c->nbins, s.bin_start, q[0], q[1], q[2], q[3], q[4], q[5], s.id[s.cur]);
+  }
+  s.sorted = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// second push (ecsim): gather E^{n+1/2}, B^n at the particle, Boris update of v
+// ---------------------------------------------------------------------------------------------
+__global__ void k_push_second(Grid g, int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                              double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz, const double* __restrict__ E,
+                              const double* __restrict__ B, double qm)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Weights w;
+  make_weights(g, x[i], y[i], z[i], 0, w);
+  double Ep[3], Bp[3];
+  gather_E(g, E, w, Ep);
+  gather_B(g, B, w, Bp);
+  double v[3] = {vx[i], vy[i], vz[i]};
+  boris_update_vEB(g.dt, qm, Ep, Bp, v);
+  vx[i] = v[0];
+  vy[i] = v[1];
+  vz[i] = v[2];
+}
+
+int push_second(xb_ctx* c, Species& s, const double* Eh, const double* B)
+{
+  if (s.count == 0) return 0;
+  double** p = s.p[s.cur];
+  XB_LAUNCH(c, k_push_second, grid_for(s.count), 256, 0, c->g, s.count, p[0], p[1], p[2], p[3], p[4], p[5], Eh, B, s.q / s.m);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sum v^2 (fixed grid + fixed tree: reproducible for a given particle order)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS) k_sum_v2(int64_t n, const double* __restrict__ vx, const double* __restrict__ vy,
+                                                       const double* __restrict__ vz, double* __restrict__ partial)
+{
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += (vx[i] * vx[i] + vy[i] * vy[i]) + vz[i] * vz[i];
+  __shared__ double sh[RED_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  acc = warp_sum(acc);
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < RED_THREADS / 32; ++q) t += sh[q];
+    partial[(int64_t)blockIdx.x * RED_MAXV] = t;
+  }
+}
+
+int reduce_finish(xb_ctx* c, int nv, double* host_out);  // fields.cu
+
+int kinetic_energy(xb_ctx* c, Species& s, double* sum_v2, double* K)
+{
+  double** p = s.p[s.cur];
+  XB_LAUNCH(c, k_sum_v2, RED_BLOCKS, RED_THREADS, 0, s.count, p[3], p[4], p[5], c->red_partial);
+  double w = 0.0;
+  XB_CHECK(reduce_finish(c, 1, &w));
+  if (sum_v2) *sum_v2 = w;
+  if (K) *K = 0.5 * s.m * (s.n / (double)s.Np) * w;  // diagnostics/energy.cpp:70-88
+  return 0;
+}
+
+__global__ void k_scale3(int64_t n, double* __restrict__ a, double* __restrict__ b, double* __restrict__ cc, double f)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  a[i] *= f;
+  b[i] *= f;
+  cc[i] *= f;
+}
+
+int scale_velocities(xb_ctx* c, Species& s, double lambda)
+{
+  if (s.count == 0) return 0;
+  double** p = s.p[s.cur];
+  XB_LAUNCH(c, k_scale3, grid_for(s.count), 256, 0, s.count, p[3], p[4], p[5], lambda);
+  return 0;
+}
+
+}  // namespace xb
