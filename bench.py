@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- ECSIM particle-steps/s on N B200s (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU arm (oracle port; PETSc reference unbuildable here)
+
+Workload: BASELINE.json configs[1] at N = 1 (ECSIM 3D 128^3 cells x 64 ppc, fp64); for N > 1 the
+per-GPU work is kept (weak scaling): 256 x 256 x (32 N) cells in z-slabs of 32 planes, which at
+N = 8 is BASELINE configs[2]'s 256^3 x 64 ppc box.  A "step" is one timestep_implementation():
+push + re-binning + moment deposition (current, mass matrices) + GMRES solve + Boris update +
+field update.  Inputs are synthetic: Maxwellian electrons (T = 0.1 keV, q = -1, m = 1, n = 1,
+dx = 0.5, dt = 1.5, periodic box, E = B = 0 at t = 0) from a counter-based generator.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ecsim_particle_steps_per_s"
+UNIT = "particle-steps/s"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def workload(n_gpus):
+    grid = os.environ.get("XPIC_BENCH_GRID")
+    ppc = env_int("XPIC_BENCH_PPC", 64)
+    if grid:
+        n = tuple(int(v) for v in grid.split(","))
+    elif n_gpus == 1:
+        n = (128, 128, 128)
+    else:
+        n = (256, 256, 32 * n_gpus)
+    return n, ppc
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline_sample(steps=2, warm=1, n=(24, 24, 24), ppc=64):
+    """The oracle (a single-thread C++ port of the reference's algorithm; the PETSc reference cannot
+    be built in this image) timed on a bounded sample of the workload."""
+    from oracle import oracle as O
+
+    o = O.Oracle(n)
+    sid = o.add_species(Np=ppc)
+    N = o.set_particles_maxwell(sid, 0.1, True)
+    o.solver_set(0, 1e-7, 1e-7, 100, 30)
+    for _ in range(warm):
+        o.step(O.ECSIM)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step(O.ECSIM)
+    dt = time.perf_counter() - t0
+    return N * steps / dt, N, dt / steps, o.solver_info(0)[0]
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n_s, ppc = (24, 24, 24), 64
+    from oracle import oracle as O
+
+    o = O.Oracle(n_s)
+    sid = o.add_species(Np=ppc)
+    N = o.set_particles_maxwell(sid, 0.1, True)
+    o.solver_set(0, 1e-7, 1e-7, 100, 30)
+    for _ in range(args.warmup):
+        o.step(O.ECSIM)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.step(O.ECSIM)
+    dt = time.perf_counter() - t0
+    value = N * args.steps / dt
+    n, ppc_w = workload(args.gpus)
+    sample = f"each step = one ECSIM step of a {n_s[0]}^3-cell x {ppc} ppc sample of the workload ({N} particles), 1 thread"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"ECSIM 3D {n[0]}x{n[1]}x{n[2]} cells x {ppc_w} ppc fp64 (timed on the sample below)", "krylov_iterations_per_step": o.solver_info(0)[0]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "xpic needs MPI + PETSc, neither is in this image (no network): the arm times oracle/ (C++ restatement, GMRES(30) unpreconditioned)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scheme", default="ecsim", choices=["ecsim", "ecsimcorr"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import xpic_b200 as X
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback)")
+    if world != args.gpus:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    comm_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        ids = [X.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm_id = ids[0]
+
+    n, ppc = workload(world)
+    scheme = X.ECSIM if args.scheme == "ecsim" else X.ECSIMCORR
+    sim = X.Simulation(n, d=(0.5, 0.5, 0.5), dt=1.5, scheme=scheme, device=local_rank, rank=rank, nranks=world, comm_id=comm_id, track_ids=False)
+    total = n[0] * n[1] * n[2] * ppc
+    sid = sim.add_species(q=-1.0, m=1.0, n=1.0, Np=ppc, capacity=int(sim.ncl * ppc * 1.25) + 65536)
+    mine = sim.set_particles_maxwellian(sid, total, T=0.1, seed=20261018, tov=True)
+    precond = env_int("XPIC_BENCH_PRECOND", 6)
+    sim.solver_set(0, 1e-7, 1e-7, 100, 30, precond)  # the reference's tolerances (ecsim/simulation.h:15-18)
+    sim.solver_set(1, 1e-7, 1e-7, 100, 30, precond)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sumreduce(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    nparticles = int(sumreduce(float(mine)))
+
+    # ---- resident arm: W warm-up steps, then exactly K timed steps ---------------------------------
+    sim.run_steps(args.warmup)
+    its_warm = sim.solver_info(0)[0]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = sim.launch_count()
+    sim.timing_reset()
+    sim.spmv_profile(True)
+    barrier()
+    ms = sim.run_steps(args.steps)
+    barrier()
+    launches = sim.launch_count() - launches0
+    spmv_n, spmv_ms = sim.spmv_profile_read()
+    sim.spmv_profile(False)
+    stage_s = {k: v[0] / max(v[1], 1) for k, v in sim.timing().items()}
+    its = sim.solver_info(0)[0]
+    ms = maxreduce(ms)
+    clocks = sampler.stop() if rank == 0 else None
+    value = nparticles * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end arm: the same K steps through xb_step_host with pinned HOST buffers ------------
+    E = torch.zeros(sim.nown, dtype=torch.float64).pin_memory()
+    B = torch.zeros(sim.nown, dtype=torch.float64).pin_memory()
+    B0 = torch.zeros(sim.nown, dtype=torch.float64).pin_memory()
+    K = torch.zeros(1, dtype=torch.float64).pin_memory()
+    E.numpy()[:] = sim.get_field("E")
+    B.numpy()[:] = sim.get_field("B")
+    barrier()
+    ms_e2e = sim.run_steps_host(args.steps, E.numpy(), B.numpy(), B0.numpy(), K.numpy())
+    barrier()
+    ms_e2e = maxreduce(ms_e2e)
+    e2e_value = nparticles * args.steps / (ms_e2e * 1e-3)
+    h2d = 3 * sim.nown * 8 * world
+    d2h = (2 * sim.nown * 8 + 8) * world
+
+    # ---- roofline of the dominant kernel (the operator SpMV inside GMRES) --------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    spmv_avg_ms = spmv_ms / max(spmv_n, 1)
+    alg_bytes = 3000.0 * sim.ncl  # 369 coefficients * 8 B + 24 B x + 24 B y per cell
+    achieved = alg_bytes / (spmv_avg_ms * 1e-3) / 1e9 if spmv_n else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tuple(tj.get("grid", [])) == tuple(n) and world == 1:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"kernel": "k_spmv<L+M>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "launches_timed": spmv_n, "avg_launch_ms": spmv_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "spmv_share_of_step": (spmv_ms / ms) if ms else None}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, Ns, sps, its_cpu = cpu_baseline_sample()
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"2 ECSIM steps (after 1 warm-up) of a 24^3-cell x 64 ppc sample of the workload, {Ns} particles, {sps:.2f} s/step, {its_cpu} GMRES its; "
+                             "oracle/ C++ port, 1 thread (PETSc reference not buildable here)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.scheme.upper()} 3D {n[0]}x{n[1]}x{n[2]} cells x {ppc} ppc fp64, periodic Maxwellian plasma", "particles": nparticles,
+                       "parallelism": f"z-slabs x{world}", "krylov": f"GMRES(30) rtol=atol=1e-7, Chebyshev(M) degree {precond} right preconditioner",
+                       "krylov_iterations_per_step": its, "l2": "inputs (6.2 GB operator, 6.4 GB particles per GPU) exceed the 126 MB L2; no flush needed",
+                       "stage_ms": {k: 1e3 * v for k, v in stage_s.items()}},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "boundary": "xb_step_host: E, B, B0 uploaded from pinned host buffers, E, B and kinetic energy downloaded every step; particles resident"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

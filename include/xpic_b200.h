@@ -92,6 +92,11 @@ int xb_species_add(xb_ctx* ctx, double q, double m, double n, int32_t Np, int64_
  * {r[3], p[3]} (48 B each); points outside this rank's slab are skipped; *added = number kept.
  * ids may be NULL (then ids continue from the species' running counter). */
 int xb_particles_append(xb_ctx* ctx, int32_t sid, const double* aos6, const uint64_t* ids, int64_t count, int64_t* added);
+/* SetParticles{CoordinateInBox, MaxwellianMomentum} (src/commands/set_particles.cpp:19-43,
+ * src/utils/particles_load.cpp:11-18,52-76) for the large synthetic configurations: `total` particles
+ * of the GLOBAL box drawn from a counter-based generator (not the serial mt19937 stream; parity-size
+ * runs upload the reference's own stream with xb_particles_append); this rank keeps those of its slab. */
+int xb_particles_maxwellian(xb_ctx* ctx, int32_t sid, int64_t total, const double T[3], uint64_t seed, int32_t tov, int64_t* added);
 int xb_particles_count(xb_ctx* ctx, int32_t sid, int64_t* count);
 /* Host mirror of interfaces::Particles::storage (src/interfaces/particles.h:32), cell-major order. */
 int xb_particles_download(xb_ctx* ctx, int32_t sid, double* aos6, uint64_t* ids, int64_t capacity, int64_t* count);
@@ -143,6 +148,9 @@ int xb_spmv_bench(xb_ctx* ctx, int32_t op, int32_t reps, double* ms_per_spmv);
 /* Stencil-layout coefficients of L: coef[k*ncells + cell], k < xb_operator_ncoef(), owned cells. */
 int xb_operator_download(xb_ctx* ctx, double* coef);
 int xb_operator_upload(xb_ctx* ctx, const double* coef);
+/* Kernel variant switches for cross-checks: what = 0 selects the cell-block kernel of the moment
+ * deposition (value 0: fp64 tensor-core DMMA, default; 1: scalar FMA). */
+int xb_set_option(xb_ctx* ctx, int32_t what, int32_t value);
 /* Moments only at the present particle positions: fill_ecsim_current (ecsim/simulation.cpp:336-368). */
 int xb_deposit(xb_ctx* ctx);
 /* Solve (L? + M) x = b for host vectors with the given solver slot (KSPSolve). */

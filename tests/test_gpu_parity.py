@@ -67,6 +67,17 @@ def test_deposit_matches_oracle(X, n, Np):
     assert rel_err(s.spmv(x, op=1), o.spmv(x, L=True, M=False)) < 1e-12
 
 
+def test_deposit_scalar_and_tensor_core_kernels_agree(X):
+    o, s = make_pair(n=(9, 8, 7), Np=37, seed_fields=15)
+    o.deposit()
+    ref = csr_to_stencil(o, X.coef_table())
+    for variant in (0, 1):  # 0: DMMA cell blocks, 1: scalar FMA cell blocks
+        s.set_option(0, variant)
+        s.deposit()
+        assert np.max(np.abs(s.operator_download() - ref)) / np.max(np.abs(ref)) < 1e-13, variant
+        assert rel_err(s.get_field("currI"), o.get_field("currI")) < 1e-12, variant
+
+
 def test_deposit_two_species(X):
     o, s = make_pair(n=(8, 8, 8), Np=20, seed_fields=7, species=((-1.0, 1.0, 1.0), (+1.0, 100.0, 1.0)))
     o.deposit()

@@ -61,6 +61,7 @@ SYMBOLS = {
     "xb_destroy": (C.c_int, [C.c_void_p]),
     "xb_species_add": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int64, _i32p]),
     "xb_particles_append": (C.c_int, [C.c_void_p, C.c_int32, _dp, _u64p, C.c_int64, _i64p]),
+    "xb_particles_maxwellian": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, _dp, C.c_uint64, C.c_int32, _i64p]),
     "xb_particles_count": (C.c_int, [C.c_void_p, C.c_int32, _i64p]),
     "xb_particles_download": (C.c_int, [C.c_void_p, C.c_int32, _dp, _u64p, C.c_int64, _i64p]),
     "xb_field_upload": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
@@ -82,6 +83,7 @@ SYMBOLS = {
     "xb_spmv_bench": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "xb_operator_download": (C.c_int, [C.c_void_p, _dp]),
     "xb_operator_upload": (C.c_int, [C.c_void_p, _dp]),
+    "xb_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "xb_deposit": (C.c_int, [C.c_void_p]),
     "xb_solve": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp]),
     "xb_curl": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp]),
@@ -187,6 +189,14 @@ class Simulation:
             ids = np.ascontiguousarray(ids, dtype=np.uint64)
             idp = ids.ctypes.data_as(_u64p)
         _check(self._L.xb_particles_append(self._h, sid, _as_dp(a), idp, a.shape[0], C.byref(added)))
+        return added.value
+
+    def set_particles_maxwellian(self, sid, total, T=0.1, seed=1, tov=True):
+        """SetParticles{CoordinateInBox, MaxwellianMomentum} with a counter-based generator; `total`
+        counts particles of the GLOBAL box, the return value those that landed in this rank's slab."""
+        Tv = np.array([T, T, T] if np.isscalar(T) else T, dtype=np.float64)
+        added = C.c_int64()
+        _check(self._L.xb_particles_maxwellian(self._h, sid, int(total), _as_dp(Tv), int(seed), int(tov), C.byref(added)))
         return added.value
 
     def particle_count(self, sid=0):
@@ -301,6 +311,9 @@ class Simulation:
         a = np.ascontiguousarray(coef, dtype=np.float64)
         assert a.shape == (self._L.xb_operator_ncoef(), self.ncl)
         _check(self._L.xb_operator_upload(self._h, _as_dp(a)))
+
+    def set_option(self, what, value):
+        _check(self._L.xb_set_option(self._h, what, value))
 
     def deposit(self):
         _check(self._L.xb_deposit(self._h))

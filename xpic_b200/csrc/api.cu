@@ -237,6 +237,12 @@ int xb_create(const xb_grid* gr, const void* uid, xb_ctx** out)
   g.nx = gr->n[0]; g.ny = gr->n[1]; g.nz = gr->n[2];
   g.dx = gr->d[0]; g.dy = gr->d[1]; g.dz = gr->d[2];
   g.dt = gr->dt;
+  g.inv_dx = 1.0 / g.dx; g.inv_dy = 1.0 / g.dy; g.inv_dz = 1.0 / g.dz;
+  g.exact_inv = 0;
+  for (int a = 0; a < 3; ++a) {
+    int e = 0;
+    if (std::frexp(gr->d[a], &e) == 0.5) g.exact_inv |= 1 << a;
+  }
   g.Lx = g.nx * g.dx; g.Ly = g.ny * g.dy; g.Lz = g.nz * g.dz;  // utils/world.cpp:97-100
   g.curl_sign = gr->curl_sign < 0 ? -1 : +1;
   g.rank = gr->rank; g.nranks = gr->nranks;
@@ -251,6 +257,7 @@ int xb_create(const xb_grid* gr, const void* uid, xb_ctx** out)
   g.ntot = 3 * g.plane * (g.nzl + 2 * GZ);
   g.own0 = 3 * g.plane * GZ;
   if ((g.nzl + 2) * g.plane * 8 >= (int64_t)0x7fffffff) XB_FAIL("xb_create: slab too large for 32-bit bin keys");
+  if (g.ntot >= (int64_t)0x7fffffff) XB_FAIL("xb_create: slab too large for 32-bit field offsets");
 
   XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   XB_CUDA(cudaEventCreate(&c->ev0));
@@ -261,8 +268,9 @@ int xb_create(const xb_grid* gr, const void* uid, xb_ctx** out)
     XB_CUDA(cudaMalloc(v, sizeof(double) * g.ntot));
     XB_CUDA(cudaMemset(*v, 0, sizeof(double) * g.ntot));
   }
-  XB_CUDA(cudaMalloc(&c->coef, sizeof(double) * NCOEF * g.ncl));
-  XB_CUDA(cudaMemset(c->coef, 0, sizeof(double) * NCOEF * g.ncl));
+  c->coef_elems = make_tilemap(g.nx, g.ny, g.nzl).ntiles() * (int64_t)(NCOEF * TILE_NODES);
+  XB_CUDA(cudaMalloc(&c->coef, sizeof(double) * c->coef_elems));
+  XB_CUDA(cudaMemset(c->coef, 0, sizeof(double) * c->coef_elems));
   c->stage_cells = g.nranks == 1 ? g.ncl : (g.nzl + 2) * g.plane;
   const int64_t groups = (c->stage_cells + CELL_GROUP - 1) / CELL_GROUP;
   XB_CUDA(cudaMalloc(&c->stage, sizeof(double) * groups * CELL_GROUP * BLOCK_ALL));
@@ -280,6 +288,11 @@ int xb_create(const xb_grid* gr, const void* uid, xb_ctx** out)
       return 1;
     }
   }
+  if (krylov_prepare(c)) {
+    xb_destroy(c);
+    return 1;
+  }
+  XB_CUDA(cudaStreamSynchronize(c->stream));
   *out = c;
   return 0;
 }
@@ -353,6 +366,13 @@ int xb_particles_append(xb_ctx* c, int32_t sid, const double* aos6, const uint64
   return 0;
 }
 
+int xb_particles_maxwellian(xb_ctx* c, int32_t sid, int64_t total, const double T[3], uint64_t seed, int32_t tov, int64_t* added)
+{
+  XB_API_BEGIN(c);
+  if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
+  return particles_generate(c, c->sorts[sid], total, T, seed, tov, added);
+}
+
 int xb_particles_count(xb_ctx* c, int32_t sid, int64_t* count)
 {
   XB_API_BEGIN(c);
@@ -409,7 +429,7 @@ int xb_solver_set(xb_ctx* c, int32_t which, double rtol, double atol, int32_t ma
   if (restart < 1 || restart > RED_MAXV - 1) XB_FAIL("restart must be in [1, 31]");
   Solver& s = c->solver[which];
   s.rtol = rtol; s.atol = atol; s.maxit = maxit; s.restart = restart; s.precond = precond;
-  return 0;
+  return krylov_prepare(c);
 }
 
 int xb_solver_info(xb_ctx* c, int32_t which, int32_t* iterations, double* rnorm, int32_t* reason)
@@ -585,17 +605,38 @@ int xb_spmv_bench(xb_ctx* c, int32_t op, int32_t reps, double* ms_per_spmv)
 int xb_operator_download(xb_ctx* c, double* coef)
 {
   XB_API_BEGIN(c);
-  XB_CUDA(cudaStreamSynchronize(c->stream));
-  XB_CUDA(cudaMemcpy(coef, c->coef, sizeof(double) * NCOEF * c->g.ncl, cudaMemcpyDeviceToHost));
+  double* plain = nullptr;
+  XB_CUDA(cudaMalloc(&plain, sizeof(double) * NCOEF * c->g.ncl));
+  int rc = coef_convert(c, plain, false);
+  if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = 1;
+  if (!rc && cudaMemcpy(coef, plain, sizeof(double) * NCOEF * c->g.ncl, cudaMemcpyDeviceToHost) != cudaSuccess) rc = 1;
+  cudaFree(plain);
+  if (rc) XB_FAIL("xb_operator_download failed");
   return 0;
 }
 
 int xb_operator_upload(xb_ctx* c, const double* coef)
 {
   XB_API_BEGIN(c);
-  XB_CUDA(cudaMemcpy(c->coef, coef, sizeof(double) * NCOEF * c->g.ncl, cudaMemcpyHostToDevice));
+  double* plain = nullptr;
+  XB_CUDA(cudaMalloc(&plain, sizeof(double) * NCOEF * c->g.ncl));
+  int rc = cudaMemcpy(plain, coef, sizeof(double) * NCOEF * c->g.ncl, cudaMemcpyHostToDevice) != cudaSuccess;
+  if (!rc) rc = coef_convert(c, plain, true);
+  if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = 1;
+  cudaFree(plain);
+  if (rc) XB_FAIL("xb_operator_upload failed");
   c->coef_valid = true;
   return 0;
+}
+
+int xb_set_option(xb_ctx* c, int32_t what, int32_t value)
+{
+  XB_API_BEGIN(c);
+  if (what == 0) {
+    c->deposit_variant = value;
+    return 0;
+  }
+  XB_FAIL("xb_set_option: unknown option");
 }
 
 int xb_deposit(xb_ctx* c)

@@ -50,6 +50,8 @@ struct Grid {
   int z0, nzl;     // owned planes [z0, z0 + nzl)
   int rank, nranks;
   double dx, dy, dz, dt;
+  double inv_dx, inv_dy, inv_dz;
+  int exact_inv;  // bit a set: d[a] is a power of two, r * inv_d == r / d exactly
   double Lx, Ly, Lz;
   int curl_sign;
   int64_t plane;  // nx * ny
@@ -111,8 +113,10 @@ struct xb_ctx {
   double *E = nullptr, *B = nullptr, *B0 = nullptr, *Ep = nullptr, *Ec = nullptr, *currI = nullptr, *currJe = nullptr;
   double *rhs = nullptr, *tmp = nullptr, *tmp2 = nullptr;
   // operator L, stencil layout
-  double* coef = nullptr;
+  double* coef = nullptr;   // blocked [tile][k][t], see stencil.cuh
+  int64_t coef_elems = 0;
   bool coef_valid = false;
+  int deposit_variant = 0;  // 0: DMMA cell blocks (default), 1: scalar-FMA cell blocks (kept as a cross-check)
   // deposit staging (cell blocks)
   double* stage = nullptr;
   int64_t stage_cells = 0;
@@ -168,6 +172,7 @@ int spmv(xb_ctx* c, int op, double* x_ghosted, double* y);  // fills x's halo (w
 
 // ---- krylov.cu -------------------------------------------------------------------------------
 int gmres(xb_ctx* c, int which, int op, const double* b, double* x);
+int krylov_prepare(xb_ctx* c);  // allocate the Krylov workspace up front (not inside the first timed solve)
 
 // ---- particles.cu ----------------------------------------------------------------------------
 int species_alloc(xb_ctx* c, Species& s, int64_t capacity);
@@ -176,9 +181,11 @@ int particles_sort(xb_ctx* c, Species& s, double dt_move);   // r += v dt_move, 
 int push_second(xb_ctx* c, Species& s, const double* Eh, const double* B);
 int kinetic_energy(xb_ctx* c, Species& s, double* sum_v2, double* K);
 int scale_velocities(xb_ctx* c, Species& s, double lambda);
+int particles_generate(xb_ctx* c, Species& s, int64_t total, const double* T, uint64_t seed, int tov, int64_t* added);
 
 // ---- deposit.cu ------------------------------------------------------------------------------
 int deposit_moments(xb_ctx* c);  // currI (+ per sort) and coef from all sorts
+int coef_convert(xb_ctx* c, double* plain_dev, bool to_blocked);
 
 // ---- esirkepov.cu ----------------------------------------------------------------------------
 int push_first_corr(xb_ctx* c, Species& s);

@@ -83,8 +83,10 @@ __global__ void __launch_bounds__(DEP_WARPS * 32) k_cell_blocks(Grid g, DepositA
           const double v[3] = {a.p[3][i], a.p[4][i], a.p[5][i]};
           Weights w;
           make_weights(g, px, py, pz, a.zshift, w);
+          NodeOffsets off;
+          make_offsets(g, w, off);
           double Bp[3], b[3];
-          gather_B(g, B, w, Bp);
+          gather_B(g, B, w, off, Bp);
           const double f = (0.5 * g.dt) * a.q / a.m;
 #pragma unroll
           for (int c = 0; c < 3; ++c) b[c] = Bp[c] * f;
@@ -162,6 +164,181 @@ __global__ void __launch_bounds__(DEP_WARPS * 32) k_cell_blocks(Grid g, DepositA
 }
 
 // ---------------------------------------------------------------------------------------------
+// pass 1, tensor-core form.  For one octant the 24 x 24 block is a sum of rank-1 updates
+//   D[(c1,t1)][(c2,t2)] += s_c1(t1) * (A_p alpha_c1c2) * s_c2(t2)       over the bin's particles,
+// i.e. nine 8 x k x 8 products with k = particles.  mma.sync.m8n8k4.f64 (DMMA, the only fp64
+// tensor path on sm_100a) takes four particles per instruction: lane (g = lane / 4, q = lane % 4)
+// supplies A[t1 = g][k = q] = s_c1(g) of particle q and B[k = q][t2 = g] = (A alpha)_c1c2 * s_c2(g)
+// of the same particle, and receives D[g][2q], D[g][2q + 1] -- exactly the 18 entries per lane of
+// the scalar kernel above, so the fold into the cell block is shared.  The current I uses three
+// more DMMAs with B = I_p in column 0.  Per four particles a lane issues 12 shared loads,
+// 9 multiplies and 12 DMMAs instead of ~180 scalar instructions.
+// ---------------------------------------------------------------------------------------------
+constexpr int MMA_CHUNK = 32;
+constexpr int MREC = 37;  // odd stride: the 16 lanes that write records hit 16 different banks
+constexpr int MMA_SMEM_PER_CELL = BLOCK_ALL + MMA_CHUNK * MREC;
+constexpr int MMA_WARPS = 2 * CELL_GROUP;  // two warps per cell
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void pair_barrier(int slot)
+{
+  asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");
+}
+
+__device__ __forceinline__ void preprocess_particle(const Grid& g, const DepositArgs& a, const double* __restrict__ B, int32_t i, double* __restrict__ r)
+{
+  const double px = a.p[0][i], py = a.p[1][i], pz = a.p[2][i];
+  const double v[3] = {a.p[3][i], a.p[4][i], a.p[5][i]};
+  Weights w;
+  make_weights(g, px, py, pz, a.zshift, w);
+  NodeOffsets off;
+  make_offsets(g, w, off);
+  double Bp[3], b[3];
+  gather_B(g, B, w, off, Bp);
+  const double f = (0.5 * g.dt) * a.q / a.m;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) b[c] = Bp[c] * f;
+  double vxb[3];
+  cross3(v, b, vxb);
+  const double vb = dot3(v, b), b2 = dot3(b, b);
+  const double ci = a.q * a.mpw / (1. + b2);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) r[33 + c] = ci * (v[c] + vxb[c] + vb * b[c]);
+  const double Ap = 0.5 * g.dt * g.dt * a.mpw * a.q * a.q / a.m / (1 + b2);
+  r[24 + 0] = Ap * (1.0 + b[0] * b[0]);
+  r[24 + 1] = Ap * (+b[2] + b[0] * b[1]);
+  r[24 + 2] = Ap * (-b[1] + b[0] * b[2]);
+  r[24 + 3] = Ap * (-b[2] + b[1] * b[0]);
+  r[24 + 4] = Ap * (1.0 + b[1] * b[1]);
+  r[24 + 5] = Ap * (+b[0] + b[1] * b[2]);
+  r[24 + 6] = Ap * (+b[1] + b[2] * b[0]);
+  r[24 + 7] = Ap * (-b[0] + b[2] * b[1]);
+  r[24 + 8] = Ap * (1.0 + b[2] * b[2]);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int i1 = t & 1, j1 = (t >> 1) & 1, k1 = t >> 2;
+    r[0 + t] = w.wn[2][k1] * w.wn[1][j1] * w.ws[0][i1];
+    r[8 + t] = w.wn[2][k1] * w.ws[1][j1] * w.wn[0][i1];
+    r[16 + t] = w.ws[2][k1] * w.wn[1][j1] * w.wn[0][i1];
+  }
+}
+
+// The 12 DMMAs of a particle group are split between the two warps of a cell so that their
+// accumulators (and therefore their folds into the cell block) are disjoint:
+//   half 0: (0,0) (0,1) (0,2) I_0 (1,0) (1,1)      half 1: (1,2) I_1 (2,0) (2,1) (2,2) I_2
+// slot j of a half: row component R(j), column component C(j) (3 = current)
+__device__ __forceinline__ constexpr int op_row(int half, int j) { return half == 0 ? (j < 4 ? 0 : 1) : (j < 2 ? 1 : 2); }
+__device__ __forceinline__ constexpr int op_col(int half, int j)
+{
+  return half == 0 ? (j < 3 ? j : (j == 3 ? 3 : j - 4)) : (j == 0 ? 2 : (j == 1 ? 3 : (j < 5 ? j - 2 : 3)));
+}
+
+template <int HALF>
+__device__ __forceinline__ void cell_half(const Grid& g, const DepositArgs& a, const double* __restrict__ B, double* __restrict__ block,
+                                          double* __restrict__ rec, int slot, int lane, int64_t bin0)
+{
+  const int gq = lane >> 2, q = lane & 3;
+  const int32_t bs = lane < 9 ? a.bin_start[bin0 + lane] : 0;  // bin boundaries of the 8 octants
+  const int32_t p0 = __shfl_sync(0xffffffffu, bs, 0), p1 = __shfl_sync(0xffffffffu, bs, 8);
+  int oct = 0;
+  int32_t oend = __shfl_sync(0xffffffffu, bs, 1);
+  bool dirty = false;
+  double acc[6][2];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) acc[j][0] = acc[j][1] = 0.0;
+
+  auto fold = [&]() {
+    const int ox = oct & 1, oy = (oct >> 1) & 1, oz = oct >> 2;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int c1 = op_row(HALF, j), c2 = op_col(HALF, j);
+      const int row = block_pos(c1, gq, ox, oy, oz);
+      if (c2 < 3) {
+        const int e = (c1 * 3 + c2) * 144 + row * 12;
+        block[e + block_pos(c2, 2 * q, ox, oy, oz)] += acc[j][0];
+        block[e + block_pos(c2, 2 * q + 1, ox, oy, oz)] += acc[j][1];
+      }
+      else if (q == 0) {
+        block[BLOCK_MAT + c1 * 12 + row] += acc[j][0];
+      }
+      acc[j][0] = acc[j][1] = 0.0;
+    }
+    __syncwarp();
+  };
+
+  for (int32_t base = p0; base < p1; base += MMA_CHUNK) {
+    const int n = min(MMA_CHUNK, p1 - base);
+    {  // each warp prepares 16 of the chunk's 32 records
+      const int pi = HALF * 16 + lane;
+      if (lane < 16 && pi < n) preprocess_particle(g, a, B, base + pi, rec + pi * MREC);
+    }
+    pair_barrier(slot);
+    int32_t pos = base;
+    const int32_t cend = base + n;
+    while (pos < cend) {
+      while (oend <= pos) {  // the octant's particles are exhausted (warp-uniform)
+        if (dirty) fold();
+        dirty = false;
+        ++oct;
+        oend = __shfl_sync(0xffffffffu, bs, oct + 1);
+      }
+      const int32_t seg_end = min(oend, cend);
+      for (int32_t gs = pos; gs < seg_end; gs += 4) {
+        const bool valid = gs + q < seg_end;
+        const double* r = rec + (min(gs + q, seg_end - 1) - base) * MREC;  // clamp: operands stay finite
+        double s[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s[c] = r[c * 8 + gq];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int c1 = op_row(HALF, j), c2 = op_col(HALF, j);
+          const double av = valid ? s[c1] : 0.0;
+          const double bv = c2 < 3 ? r[24 + c1 * 3 + c2] * s[c2] : (gq == 0 ? r[33 + c1] : 0.0);
+          dmma(acc[j][0], acc[j][1], av, bv);
+        }
+      }
+      dirty = true;
+      pos = seg_end;
+    }
+    pair_barrier(slot);  // both warps are done with the records before the next chunk overwrites them
+  }
+  if (dirty) fold();
+}
+
+__global__ void __launch_bounds__(MMA_WARPS * 32) k_cell_blocks_mma(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage)
+{
+  extern __shared__ double smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = wid >> 1, half = wid & 1;
+  double* block = smem + (size_t)slot * MMA_SMEM_PER_CELL;
+  double* rec = block + BLOCK_ALL;
+  const int64_t cell_local = (int64_t)blockIdx.x * CELL_GROUP + slot;
+
+  for (int e = half * 32 + lane; e < BLOCK_ALL; e += 64) block[e] = 0.0;
+  pair_barrier(slot);
+
+  if (cell_local < a.ncells) {
+    const int64_t bin0 = (a.bin_cell0 + cell_local) << 3;
+    if (half == 0)
+      cell_half<0>(g, a, B, block, rec, slot, lane, bin0);
+    else
+      cell_half<1>(g, a, B, block, rec, slot, lane, bin0);
+  }
+  __syncthreads();
+  double* out = stage + ((a.stage_cell0 >> 3) + blockIdx.x) * (int64_t)(BLOCK_ALL * CELL_GROUP);
+  for (int idx = threadIdx.x; idx < BLOCK_ALL * CELL_GROUP; idx += MMA_WARPS * 32) {
+    const int e = idx >> 3, w = idx & 7;
+    out[idx] = smem[(size_t)w * MMA_SMEM_PER_CELL + e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // pass 2: gather cell blocks into the fixed-offset rows
 // ---------------------------------------------------------------------------------------------
 struct GatherArgs {
@@ -211,13 +388,14 @@ __global__ void __launch_bounds__(128) k_gather_rows(Grid g, GatherArgs a, doubl
                 acc[coef_slot(C1, C2, dx, dy, dz) - pair_base(C1, C2)] += stage_read(a.stage, cell, ebase + win_index(C2, i2, j2, k2));
             }
       }
-  double* out = coef + (int64_t)pair_base(C1, C2) * g.ncl + node;
+  const TileMap tm = make_tilemap(g.nx, g.ny, g.nzl);
+  double* out = coef + tm.node_offset(x, y, zl) + (int64_t)pair_base(C1, C2) * TILE_NODES;
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     if (accumulate)
-      out[(int64_t)s * g.ncl] += acc[s];
+      out[s * TILE_NODES] += acc[s];
     else
-      out[(int64_t)s * g.ncl] = acc[s];
+      out[s * TILE_NODES] = acc[s];
   }
 }
 
@@ -247,6 +425,29 @@ __global__ void k_gather_current(Grid g, GatherArgs a, double* __restrict__ sort
   }
 }
 
+// plain [k][node] (the C ABI's layout) <-> blocked [tile][k][t]
+__global__ void k_coef_convert(Grid g, double* __restrict__ blocked, double* __restrict__ plain, int to_blocked)
+{
+  const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (node >= g.ncl) return;
+  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = (int)(node / g.plane);
+  const TileMap tm = make_tilemap(g.nx, g.ny, g.nzl);
+  double* b = blocked + tm.node_offset(x, y, zl);
+  for (int k = 0; k < NCOEF; ++k) {
+    if (to_blocked)
+      b[k * TILE_NODES] = plain[(int64_t)k * g.ncl + node];
+    else
+      plain[(int64_t)k * g.ncl + node] = b[k * TILE_NODES];
+  }
+}
+
+int coef_convert(xb_ctx* c, double* plain_dev, bool to_blocked)
+{
+  const int blocks = (int)((c->g.ncl + 127) / 128);
+  XB_LAUNCH(c, k_coef_convert, blocks, 128, 0, c->g, c->coef, plain_dev, to_blocked ? 1 : 0);
+  return 0;
+}
+
 template <int C1, int C2>
 static int launch_gather(xb_ctx* c, const GatherArgs& ga, int accumulate)
 {
@@ -261,9 +462,11 @@ int deposit_moments(xb_ctx* c)
 {
   const Grid& g = c->g;
   static bool attr_set = false;
-  const size_t smem = sizeof(double) * DEP_SMEM_PER_WARP * DEP_WARPS;
+  const bool use_mma = c->deposit_variant != 1;
+  const size_t smem = sizeof(double) * (use_mma ? MMA_SMEM_PER_CELL : DEP_SMEM_PER_WARP) * CELL_GROUP;
   if (!attr_set) {
-    XB_CUDA(cudaFuncSetAttribute(k_cell_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XB_CUDA(cudaFuncSetAttribute(k_cell_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * DEP_SMEM_PER_WARP * DEP_WARPS)));
+    XB_CUDA(cudaFuncSetAttribute(k_cell_blocks_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * MMA_SMEM_PER_CELL * CELL_GROUP)));
     attr_set = true;
   }
   XB_CHECK(halo_fill(c, c->B, GZ));
@@ -284,7 +487,10 @@ int deposit_moments(xb_ctx* c)
     a.mpw = s.n / (double)s.Np;
     if ((a.stage_cell0 & 7) != 0) XB_FAIL("deposit: plane size must be a multiple of 8 cells in multi-rank runs");
     const int groups = (int)((a.ncells + CELL_GROUP - 1) / CELL_GROUP);
-    XB_LAUNCH(c, k_cell_blocks, groups, DEP_WARPS * 32, smem, g, a, c->B, c->stage);
+    if (use_mma)
+      XB_LAUNCH(c, k_cell_blocks_mma, groups, MMA_WARPS * 32, smem, g, a, c->B, c->stage);
+    else
+      XB_LAUNCH(c, k_cell_blocks, groups, DEP_WARPS * 32, smem, g, a, c->B, c->stage);
     if (!single) XB_CHECK(deposit_ghost_cells(c, s, c->stage));
     GatherArgs ga{c->stage, single ? 1 : 0};
     const int acc = first ? 0 : 1;
@@ -301,7 +507,7 @@ int deposit_moments(xb_ctx* c)
     XB_LAUNCH(c, k_gather_current, blocks, 128, 0, g, ga, s.currI, c->currI);
     first = false;
   }
-  if (c->sorts.empty()) XB_CUDA(cudaMemsetAsync(c->coef, 0, sizeof(double) * NCOEF * g.ncl, c->stream));
+  if (c->sorts.empty()) XB_CUDA(cudaMemsetAsync(c->coef, 0, sizeof(double) * c->coef_elems, c->stream));
   c->coef_valid = true;
   return 0;
 }

@@ -107,9 +107,11 @@ __global__ void __launch_bounds__(RED_THREADS) k_push_second_corr(Grid g, int64_
     const double vo[3] = {vx[i], vy[i], vz[i]};
     Weights w;
     make_weights(g, ro[0], ro[1], ro[2], 0, w);
+    NodeOffsets off;
+    make_offsets(g, w, off);
     double Ep[3], Bp[3];
-    gather_E(g, E, w, Ep);
-    gather_B(g, B, w, Bp);
+    gather_E(g, E, w, off, Ep);
+    gather_B(g, B, w, off, Bp);
     double v[3] = {vo[0], vo[1], vo[2]};
     boris_update_vEB(g.dt, qm, Ep, Bp, v);
     const double h = 0.5 * g.dt;

@@ -18,9 +18,15 @@ __device__ __forceinline__ void cell_and_octant(double xn, int& i, int& o)
   o = is - i + 1;  // src/impls/ecsim/particles.cpp:92-94
 }
 
-__device__ __forceinline__ void axis_weights(double r, double d, int& in, int& is, double* wn, double* ws)
+// r / d as the reference computes it; when d is a power of two the product with 1/d is the same
+// number bit for bit and avoids the fp64 division sequence
+__device__ __forceinline__ double to_cells(double r, double d, double inv_d, int exact)
 {
-  const double xn = r / d;
+  return exact ? r * inv_d : r / d;
+}
+
+__device__ __forceinline__ void axis_weights(double xn, int& in, int& is, double* wn, double* ws)
+{
   const double xs = xn - 0.5;
   in = (int)floor(xn);
   is = (int)floor(xs);
@@ -34,14 +40,37 @@ __device__ __forceinline__ void axis_weights(double r, double d, int& in, int& i
 // across the periodic boundary, so their weights stay bit-identical to the owner's)
 __device__ __forceinline__ void make_weights(const Grid& g, double px, double py, double pz, int zshift, Weights& w)
 {
-  axis_weights(px, g.dx, w.in[0], w.is[0], w.wn[0], w.ws[0]);
-  axis_weights(py, g.dy, w.in[1], w.is[1], w.wn[1], w.ws[1]);
-  axis_weights(pz, g.dz, w.in[2], w.is[2], w.wn[2], w.ws[2]);
+  axis_weights(to_cells(px, g.dx, g.inv_dx, g.exact_inv & 1), w.in[0], w.is[0], w.wn[0], w.ws[0]);
+  axis_weights(to_cells(py, g.dy, g.inv_dy, g.exact_inv & 2), w.in[1], w.is[1], w.wn[1], w.ws[1]);
+  axis_weights(to_cells(pz, g.dz, g.inv_dz, g.exact_inv & 4), w.in[2], w.is[2], w.wn[2], w.ws[2]);
   w.in[2] += zshift - g.z0;
   w.is[2] += zshift - g.z0;
 }
 
-__device__ __forceinline__ void gather_E(const Grid& g, const double* __restrict__ E, const Weights& w, double* Ep)
+// element offsets (component 0) of the 2 + 2 node columns a particle touches per axis:
+// [0] = nodal lower/upper, [1] = staggered lower/upper; x and y wrap periodically (indices lie in
+// [-1, n]), z is a local plane index into the ghosted array
+struct NodeOffsets {
+  int x[2][2], y[2][2], z[2][2];
+};
+
+__device__ __forceinline__ int wrap1(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
+
+__device__ __forceinline__ void make_offsets(const Grid& g, const Weights& w, NodeOffsets& o)
+{
+  const int sy = 3 * g.nx, sz = 3 * (int)g.plane;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    o.x[0][i] = 3 * wrap1(w.in[0] + i, g.nx);
+    o.x[1][i] = 3 * wrap1(w.is[0] + i, g.nx);
+    o.y[0][i] = sy * wrap1(w.in[1] + i, g.ny);
+    o.y[1][i] = sy * wrap1(w.is[1] + i, g.ny);
+    o.z[0][i] = sz * (w.in[2] + i + GZ);
+    o.z[1][i] = sz * (w.is[2] + i + GZ);
+  }
+}
+
+__device__ __forceinline__ void gather_E(const Grid& g, const double* __restrict__ E, const Weights& w, const NodeOffsets& o, double* Ep)
 {
   Ep[0] = Ep[1] = Ep[2] = 0.0;
 #pragma unroll
@@ -53,13 +82,13 @@ __device__ __forceinline__ void gather_E(const Grid& g, const double* __restrict
         const double sx = w.wn[2][k] * w.wn[1][j] * w.ws[0][i];
         const double sy = w.wn[2][k] * w.ws[1][j] * w.wn[0][i];
         const double sz = w.ws[2][k] * w.wn[1][j] * w.wn[0][i];
-        Ep[0] += __ldg(&E[g.vidx(wrapi(w.is[0] + i, g.nx), wrapi(w.in[1] + j, g.ny), w.in[2] + k, 0)]) * sx;
-        Ep[1] += __ldg(&E[g.vidx(wrapi(w.in[0] + i, g.nx), wrapi(w.is[1] + j, g.ny), w.in[2] + k, 1)]) * sy;
-        Ep[2] += __ldg(&E[g.vidx(wrapi(w.in[0] + i, g.nx), wrapi(w.in[1] + j, g.ny), w.is[2] + k, 2)]) * sz;
+        Ep[0] += __ldg(&E[o.z[0][k] + o.y[0][j] + o.x[1][i] + 0]) * sx;
+        Ep[1] += __ldg(&E[o.z[0][k] + o.y[1][j] + o.x[0][i] + 1]) * sy;
+        Ep[2] += __ldg(&E[o.z[1][k] + o.y[0][j] + o.x[0][i] + 2]) * sz;
       }
 }
 
-__device__ __forceinline__ void gather_B(const Grid& g, const double* __restrict__ B, const Weights& w, double* Bp)
+__device__ __forceinline__ void gather_B(const Grid& g, const double* __restrict__ B, const Weights& w, const NodeOffsets& o, double* Bp)
 {
   Bp[0] = Bp[1] = Bp[2] = 0.0;
 #pragma unroll
@@ -71,9 +100,9 @@ __device__ __forceinline__ void gather_B(const Grid& g, const double* __restrict
         const double sx = w.ws[2][k] * w.ws[1][j] * w.wn[0][i];
         const double sy = w.ws[2][k] * w.wn[1][j] * w.ws[0][i];
         const double sz = w.wn[2][k] * w.ws[1][j] * w.ws[0][i];
-        Bp[0] += __ldg(&B[g.vidx(wrapi(w.in[0] + i, g.nx), wrapi(w.is[1] + j, g.ny), w.is[2] + k, 0)]) * sx;
-        Bp[1] += __ldg(&B[g.vidx(wrapi(w.is[0] + i, g.nx), wrapi(w.in[1] + j, g.ny), w.is[2] + k, 1)]) * sy;
-        Bp[2] += __ldg(&B[g.vidx(wrapi(w.is[0] + i, g.nx), wrapi(w.is[1] + j, g.ny), w.in[2] + k, 2)]) * sz;
+        Bp[0] += __ldg(&B[o.z[1][k] + o.y[1][j] + o.x[0][i] + 0]) * sx;
+        Bp[1] += __ldg(&B[o.z[1][k] + o.y[0][j] + o.x[1][i] + 1]) * sy;
+        Bp[2] += __ldg(&B[o.z[0][k] + o.y[1][j] + o.x[1][i] + 2]) * sz;
       }
 }
 

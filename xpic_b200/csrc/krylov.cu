@@ -8,22 +8,51 @@
 // fixed Chebyshev polynomial in the constant operator M (spectrum known in closed form), true
 // residual stop test  ||r|| <= max(rtol ||b||, atol)  (KSPConvergedDefault's form).
 #include <cmath>
+#include <utility>
 
 #include "common.cuh"
+#include "operators.cuh"
 
 namespace xb {
 
 int spmv(xb_ctx* c, int op, double* x, double* y);
 
-__global__ void k_cheb_update(double* __restrict__ z, double* __restrict__ r, double* __restrict__ d, const double* __restrict__ Md,
-                              double a, double b, int64_t n)
+// One Chebyshev step fused with the matrix-free M:  z += d ; r -= M d ; d_out = a d + b r.
+// d_in carries valid ghosts (width 1); 144 B of HBM traffic per node, the 13-point stencil reads hit L1/L2.
+__global__ void __launch_bounds__(256) k_cheb_step(Grid g, const double* __restrict__ d_in, double* __restrict__ d_out, double* __restrict__ r,
+                                                  double* __restrict__ z, double a, double b)
+{
+  const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (node >= g.ncl) return;
+  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = (int)(node / g.plane);
+  const int xm = x == 0 ? g.nx - 1 : x - 1, xp = x == g.nx - 1 ? 0 : x + 1;
+  const int ym = y == 0 ? g.ny - 1 : y - 1, yp = y == g.ny - 1 ? 0 : y + 1;
+  auto f = [&](int comp, int ox, int oy, int oz) {
+    const int xx = ox < 0 ? xm : (ox > 0 ? xp : x), yy = oy < 0 ? ym : (oy > 0 ? yp : y);
+    return __ldg(&d_in[g.vidx(xx, yy, zl + oz, comp)]);
+  };
+  const double inv_d[3] = {1.0 / g.dx, 1.0 / g.dy, 1.0 / g.dz};
+  const double h = 0.5 * g.dt * g.dt;
+  const int64_t o = g.vidx(x, y, zl, 0);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double dc = f(c, 0, 0, 0);
+    const double Md = 2.0 * dc + h * curlcurl(c, inv_d, f);
+    const double rn = r[o + c] - Md;
+    z[o + c] += dc;
+    r[o + c] = rn;
+    d_out[o + c] = a * dc + b * rn;
+  }
+}
+
+__global__ void k_cheb_init(const double* __restrict__ u, double* __restrict__ z, double* __restrict__ r, double* __restrict__ d, double inv_theta,
+                            int64_t n)
 {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double di = d[i];
-    const double ri = r[i] - Md[i];
-    z[i] += di;
-    r[i] = ri;
-    d[i] = a * di + b * ri;
+    const double ui = u[i];
+    z[i] = 0.0;
+    r[i] = ui;
+    d[i] = inv_theta * ui;
   }
 }
 
@@ -52,26 +81,33 @@ static int cheb_apply(xb_ctx* c, int deg, const double* u, double* z, double* wo
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
   const double sigma = theta / delta;
   double rho_old = 1.0 / sigma;
-  XB_CUDA(cudaMemsetAsync(z + g.own0, 0, sizeof(double) * g.nown, c->stream));
-  XB_CHECK(vec_copy_owned(c, u, work_r));
-  XB_CHECK(scale_into(c, u, 1.0 / theta, work_d));
+  const int64_t n = g.nown;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  XB_LAUNCH(c, k_cheb_init, blocks, 256, 0, u + g.own0, z + g.own0, work_r + g.own0, work_d + g.own0, 1.0 / theta, n);
+  double* d_cur = work_d;
+  double* d_nxt = work_Md;
   for (int k = 0; k < deg; ++k) {
     const double rho = 1.0 / (2.0 * sigma - rho_old);
     if (k + 1 < deg) {
-      XB_CHECK(spmv(c, XB_OP_M, work_d, work_Md));
-      int64_t n = g.nown;
-      int blocks = (int)((n + 255) / 256);
-      if (blocks > 148 * 16) blocks = 148 * 16;
-      XB_LAUNCH(c, k_cheb_update, blocks, 256, 0, z + g.own0, work_r + g.own0, work_d + g.own0, work_Md + g.own0, rho * rho_old, 2.0 * rho / delta, n);
+      XB_CHECK(halo_fill(c, d_cur, 1));
+      XB_LAUNCH(c, k_cheb_step, (int)((g.ncl + 255) / 256), 256, 0, g, d_cur, d_nxt, work_r, z, rho * rho_old, 2.0 * rho / delta);
+      std::swap(d_cur, d_nxt);
     }
     else {
       const double one = 1.0;
-      const double* vs[1] = {work_d};
+      const double* vs[1] = {d_cur};
       XB_CHECK(axpy_multi(c, 1, vs, &one, z));  // last step: z += d, no further residual needed
     }
     rho_old = rho;
   }
   return 0;
+}
+
+int krylov_prepare(xb_ctx* c)
+{
+  int m = c->solver[0].restart > c->solver[1].restart ? c->solver[0].restart : c->solver[1].restart;
+  return ensure_workspace(c, m);
 }
 
 int gmres(xb_ctx* c, int which, int op, const double* b, double* x)

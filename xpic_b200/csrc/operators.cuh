@@ -1,0 +1,27 @@
+// operators.cuh -- the constant part of the implicit Maxwell operator, matrix-free.
+// M = 2 I + dt^2/2 curl^- curl^+   (matM, src/impls/ecsim/simulation.cpp:544-552)
+#pragma once
+
+namespace xb {
+
+// (curl^- curl^+ f)_c at a node; f(comp, ox, oy, oz) reads component comp at the node + offset.
+// (CC f)_c = - d_a^- d_a^+ f_c - d_b^- d_b^+ f_c + d_a^- d_c^+ f_a + d_b^- d_c^+ f_b,  {a, b} = axes != c
+template <class F>
+__device__ __forceinline__ double curlcurl(int c, const double* inv_d, F&& f)
+{
+  double r = 0.0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (a == c) continue;
+    int ea[3] = {0, 0, 0}, ec[3] = {0, 0, 0};
+    ea[a] = 1;
+    ec[c] = 1;
+    const double lap = (f(c, ea[0], ea[1], ea[2]) - 2.0 * f(c, 0, 0, 0) + f(c, -ea[0], -ea[1], -ea[2])) * (inv_d[a] * inv_d[a]);
+    const double mix = ((f(a, ec[0], ec[1], ec[2]) - f(a, 0, 0, 0)) - (f(a, ec[0] - ea[0], ec[1] - ea[1], ec[2] - ea[2]) - f(a, -ea[0], -ea[1], -ea[2]))) *
+                       (inv_d[a] * inv_d[c]);
+    r += mix - lap;
+  }
+  return r;
+}
+
+}  // namespace xb

@@ -87,9 +87,9 @@ __global__ void k_move_key(Grid g, int64_t n, double* __restrict__ x, double* __
   y[i] = py;
   z[i] = pz;
   int ix, iy, iz, ox, oy, oz;
-  cell_and_octant(px / g.dx, ix, ox);
-  cell_and_octant(py / g.dy, iy, oy);
-  cell_and_octant(pz / g.dz, iz, oz);
+  cell_and_octant(to_cells(px, g.dx, g.inv_dx, g.exact_inv & 1), ix, ox);
+  cell_and_octant(to_cells(py, g.dy, g.inv_dy, g.exact_inv & 2), iy, oy);
+  cell_and_octant(to_cells(pz, g.dz, g.inv_dz, g.exact_inv & 4), iz, oz);
   ix = min(max(ix, 0), g.nx - 1);
   iy = min(max(iy, 0), g.ny - 1);
   iz = min(max(iz, 0), g.nz - 1);
@@ -201,7 +201,9 @@ __global__ void k_scan_add(int32_t* __restrict__ out, int64_t n, const int32_t* 
   cursor[i] = v;
 }
 
-// pass 2: scatter into the other SoA buffer
+// pass 2: scatter into the other SoA buffer.  The input is nearly sorted, so the lanes of a warp
+// mostly share a handful of bins: lanes with equal keys elect a leader that reserves the whole
+// run with one atomic (returning atomics are what limits this kernel, not the copies).
 __global__ void k_scatter(int64_t n, const int32_t* __restrict__ key, int32_t* __restrict__ cursor, const double* __restrict__ s0,
                           const double* __restrict__ s1, const double* __restrict__ s2, const double* __restrict__ s3,
                           const double* __restrict__ s4, const double* __restrict__ s5, const uint64_t* __restrict__ sid,
@@ -209,8 +211,17 @@ __global__ void k_scatter(int64_t n, const int32_t* __restrict__ key, int32_t* _
                           double* __restrict__ d4, double* __restrict__ d5, uint64_t* __restrict__ did)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int32_t pos = atomicAdd(&cursor[key[i]], 1);
+  const bool live = i < n;
+  const unsigned active = __ballot_sync(0xffffffffu, live);
+  if (!live) return;
+  const int32_t k = key[i];
+  const unsigned peers = __match_any_sync(active, k);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  int32_t base = 0;
+  if (lane == leader) base = atomicAdd(&cursor[k], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  const int32_t pos = base + __popc(peers & ((1u << lane) - 1u));
   d0[pos] = s0[i];
   d1[pos] = s1[i];
   d2[pos] = s2[i];
@@ -280,6 +291,79 @@ int particles_sort(xb_ctx* c, Species& s, double dt_move)
 }
 
 // ---------------------------------------------------------------------------------------------
+// synthetic initial condition for the large configurations: CoordinateInBox + MaxwellianMomentum
+// (src/utils/particles_load.cpp:11-18,52-76) driven by a counter-based generator instead of the
+// serial mt19937 stream.  Every rank walks the same global stream and keeps the
+// particles of its slab, so the initial state does not depend on the decomposition
+// (src/interfaces/particles.cpp:47-57 semantics).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ double u01(uint64_t seed, uint64_t i, int k)
+{
+  const uint64_t h = splitmix64(seed ^ splitmix64(i * 16 + (uint64_t)k));
+  return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0);  // (0, 1)
+}
+
+__global__ void k_generate_maxwellian(Grid g, uint64_t total, uint64_t seed, double sx, double sy, double sz, double m, int tov,
+                                      double* __restrict__ x, double* __restrict__ y, double* __restrict__ z, double* __restrict__ vx,
+                                      double* __restrict__ vy, double* __restrict__ vz, uint64_t* __restrict__ id, uint64_t id0,
+                                      unsigned long long* __restrict__ cursor, int64_t base, int64_t capacity)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double pz = u01(seed, i, 2) * g.Lz;
+    const int cz = (int)floor(pz / g.dz) - g.z0;
+    if (cz < 0 || cz >= g.nzl) continue;
+    const double px = u01(seed, i, 0) * g.Lx, py = u01(seed, i, 1) * g.Ly;
+    double p[3];
+    const double sg[3] = {sx, sy, sz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      p[c] = sinpi(2.0 * u01(seed, i, 3 + 2 * c)) * sqrt(-2.0 * sg[c] * log(u01(seed, i, 4 + 2 * c)));
+    if (tov) {
+      const double den = sqrt(m * m + (p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
+      p[0] /= den;
+      p[1] /= den;
+      p[2] /= den;
+    }
+    const int64_t pos = base + (int64_t)atomicAdd(cursor, 1ull);
+    if (pos >= capacity) continue;  // counted, reported as an error by the host
+    x[pos] = px;
+    y[pos] = py;
+    z[pos] = pz;
+    vx[pos] = p[0];
+    vy[pos] = p[1];
+    vz[pos] = p[2];
+    if (id) id[pos] = id0 + i;
+  }
+}
+
+int particles_generate(xb_ctx* c, Species& s, int64_t total, const double* T, uint64_t seed, int tov, int64_t* added)
+{
+  unsigned long long* cur = reinterpret_cast<unsigned long long*>(c->red_out);
+  XB_CUDA(cudaMemsetAsync(cur, 0, sizeof(unsigned long long), c->stream));
+  double** p = s.p[s.cur];
+  const double f = s.m / 511.0;  // temperature_momentum: sqrt(-2 (T m / mec2) ln u)
+  XB_LAUNCH(c, k_generate_maxwellian, 148 * 32, 256, 0, c->g, (uint64_t)total, seed, T[0] * f, T[1] * f, T[2] * f, s.m, tov, p[0], p[1], p[2], p[3],
+            p[4], p[5], s.id[s.cur], s.next_id, cur, s.count, s.capacity);
+  unsigned long long n = 0;
+  XB_CUDA(cudaMemcpyAsync(&n, cur, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  if (s.count + (int64_t)n > s.capacity) XB_FAIL("particles_generate: species capacity exceeded");
+  s.count += (int64_t)n;
+  s.next_id += (uint64_t)total;
+  s.sorted = false;
+  if (added) *added = (int64_t)n;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // second push (ecsim): gather E^{n+1/2}, B^n at the particle, Boris update of v
 // ---------------------------------------------------------------------------------------------
 __global__ void k_push_second(Grid g, int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
@@ -290,9 +374,11 @@ __global__ void k_push_second(Grid g, int64_t n, const double* __restrict__ x, c
   if (i >= n) return;
   Weights w;
   make_weights(g, x[i], y[i], z[i], 0, w);
+  NodeOffsets off;
+  make_offsets(g, w, off);
   double Ep[3], Bp[3];
-  gather_E(g, E, w, Ep);
-  gather_B(g, B, w, Bp);
+  gather_E(g, E, w, off, Ep);
+  gather_B(g, B, w, off, Bp);
   double v[3] = {vx[i], vy[i], vz[i]};
   boris_update_vEB(g.dt, qm, Ep, Bp, v);
   vx[i] = v[0];

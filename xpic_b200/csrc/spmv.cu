@@ -7,36 +7,49 @@
 //
 // Roofline: HBM.  Algorithmic bytes per cell = 369 * 8 + 24 (x) + 24 (y) = 3000.
 #include "common.cuh"
+#include "operators.cuh"
 #include "stencil.cuh"
 
 namespace xb {
 
-constexpr int TX = 32, TY = 4, TZ = 2;
 constexpr int HALO = 2;
 constexpr int SX = TX + 2 * HALO, SY = TY + 2 * HALO, SZ = TZ + 2 * HALO;
 
-// (curl^- curl^+ f)_c at the tile point, f(comp, ox, oy, oz) reads the shared tile.
-// (CC f)_c = - d_a^- d_a^+ f_c - d_b^- d_b^+ f_c + d_a^- d_c^+ f_a + d_b^- d_c^+ f_b,  {a, b} = axes != c
-template <class F>
-__device__ __forceinline__ double curlcurl(int c, const double* inv_d, F&& f)
+// sum over the fixed offsets of one component pair; every index is a compile-time constant, so the
+// loads carry immediate offsets into the shared tile (xt points at this thread's own node)
+template <int C1, int C2>
+__device__ __forceinline__ double pair_sum(const double* __restrict__ cp, const double* __restrict__ xt)
 {
-  double r = 0.0;
+  constexpr DRange rx = drange(C1, C2, 0), ry = drange(C1, C2, 1), rz = drange(C1, C2, 2);
+  constexpr int SLICE = rx.n * ry.n;  // 9, 12 or 16 coefficients per z-slice
+  const double* c0 = cp + pair_base(C1, C2) * TILE_NODES;
+  const double* x0 = xt + ((C2 * SZ + rz.lo) * SY + ry.lo) * SX + rx.lo;
+  double a0 = 0.0, a1 = 0.0;  // two chains
+  // the z loop stays a real loop: one slice of loads is in flight per thread, the compiler cannot
+  // hoist all 369 loads (it spills when it does) and the code stays inside the instruction cache
+#pragma unroll 1
+  for (int dz = 0; dz < rz.n; ++dz) {
+    double cv[SLICE];
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    if (a == c) continue;
-    int ea[3] = {0, 0, 0}, ec[3] = {0, 0, 0};
-    ea[a] = 1;
-    ec[c] = 1;
-    const double lap = (f(c, ea[0], ea[1], ea[2]) - 2.0 * f(c, 0, 0, 0) + f(c, -ea[0], -ea[1], -ea[2])) * (inv_d[a] * inv_d[a]);
-    const double mix = ((f(a, ec[0], ec[1], ec[2]) - f(a, 0, 0, 0)) - (f(a, ec[0] - ea[0], ec[1] - ea[1], ec[2] - ea[2]) - f(a, -ea[0], -ea[1], -ea[2]))) *
-                       (inv_d[a] * inv_d[c]);
-    r += mix - lap;
+    for (int i = 0; i < SLICE; ++i) cv[i] = __ldg(c0 + i * TILE_NODES);
+#pragma unroll
+    for (int dy = 0; dy < ry.n; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < rx.n; ++dx) {
+        const double xv = x0[dy * SX + dx];
+        if ((dx + dy) & 1)
+          a1 += cv[dy * rx.n + dx] * xv;
+        else
+          a0 += cv[dy * rx.n + dx] * xv;
+      }
+    c0 += SLICE * TILE_NODES;
+    x0 += SY * SX;
   }
-  return r;
+  return a0 + a1;
 }
 
 template <int OP>
-__global__ void __launch_bounds__(TX * TY * TZ) k_spmv(Grid g, const double* __restrict__ coef, const double* __restrict__ x, double* __restrict__ y,
+__global__ void __launch_bounds__(TX * TY * TZ, 3) k_spmv(Grid g, const double* __restrict__ coef, const double* __restrict__ x, double* __restrict__ y,
                                                       int tiles_x, int tiles_y)
 {
   __shared__ double xs[3][SZ][SY][SX];
@@ -58,29 +71,14 @@ __global__ void __launch_bounds__(TX * TY * TZ) k_spmv(Grid g, const double* __r
   const int tx = threadIdx.x % TX, ty = (threadIdx.x / TX) % TY, tz = threadIdx.x / (TX * TY);
   const int gx = x0 + tx, gy = y0 + ty, zl = z0 + tz;
   if (gx >= g.nx || gy >= g.ny || zl >= g.nzl) return;
-  const int64_t node = ((int64_t)zl * g.ny + gy) * g.nx + gx;
 
   double acc[3] = {0.0, 0.0, 0.0};
   if (OP & XB_OP_L) {
-    const double* cp = coef + node;
-    const int64_t ncl = g.ncl;
-#pragma unroll
-    for (int c1 = 0; c1 < 3; ++c1)
-#pragma unroll
-      for (int c2 = 0; c2 < 3; ++c2) {
-        constexpr int dummy = 0;
-        (void)dummy;
-        const DRange rx = drange(c1, c2, 0), ry = drange(c1, c2, 1), rz = drange(c1, c2, 2);
-#pragma unroll
-        for (int dz = 0; dz < rz.n; ++dz)
-#pragma unroll
-          for (int dy = 0; dy < ry.n; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < rx.n; ++dx) {
-              const int k = pair_base(c1, c2) + (dz * ry.n + dy) * rx.n + dx;
-              acc[c1] += __ldg(cp + (int64_t)k * ncl) * xs[c2][tz + HALO + rz.lo + dz][ty + HALO + ry.lo + dy][tx + HALO + rx.lo + dx];
-            }
-      }
+    const double* cp = coef + (int64_t)blockIdx.x * (NCOEF * TILE_NODES) + threadIdx.x;
+    const double* xt = &xs[0][tz + HALO][ty + HALO][tx + HALO];
+    acc[0] = pair_sum<0, 0>(cp, xt) + pair_sum<0, 1>(cp, xt) + pair_sum<0, 2>(cp, xt);
+    acc[1] = pair_sum<1, 0>(cp, xt) + pair_sum<1, 1>(cp, xt) + pair_sum<1, 2>(cp, xt);
+    acc[2] = pair_sum<2, 0>(cp, xt) + pair_sum<2, 1>(cp, xt) + pair_sum<2, 2>(cp, xt);
   }
   if (OP & XB_OP_M) {
     const double inv_d[3] = {1.0 / g.dx, 1.0 / g.dy, 1.0 / g.dz};

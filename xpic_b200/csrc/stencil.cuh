@@ -64,6 +64,30 @@ __host__ __device__ constexpr int win_index(int c, int i, int j, int k)
   return (k * win_n(c, 1) + j) * win_n(c, 0) + i;
 }
 
+// ---- blocked storage of the coefficients ------------------------------------------------------
+// coef[tile][k][t]: a tile is TX x TY x TZ nodes (the SpMV CTA), t = (tz * TY + ty) * TX + tx.
+// One tile's 369 x 256 coefficients are 756 KB contiguous: every load of a thread is one base
+// register + an immediate offset, and a CTA touches one 2 MB page instead of 369.
+constexpr int TX = 32, TY = 4, TZ = 2;
+constexpr int TILE_NODES = TX * TY * TZ;
+
+struct TileMap {
+  int tiles_x, tiles_y, tiles_z;
+  __host__ __device__ inline long long ntiles() const { return (long long)tiles_x * tiles_y * tiles_z; }
+  // offset of slot 0 of node (x, y, zl); slot k lives TILE_NODES * k doubles further
+  __host__ __device__ inline long long node_offset(int x, int y, int zl) const
+  {
+    const long long tile = ((long long)(zl / TZ) * tiles_y + (y / TY)) * tiles_x + (x / TX);
+    const int t = ((zl % TZ) * TY + (y % TY)) * TX + (x % TX);
+    return tile * (long long)(NCOEF * TILE_NODES) + t;
+  }
+};
+
+__host__ __device__ inline TileMap make_tilemap(int nx, int ny, int nzl)
+{
+  return TileMap{(nx + TX - 1) / TX, (ny + TY - 1) / TY, (nzl + TZ - 1) / TZ};
+}
+
 constexpr int BLOCK_MAT = 9 * 144;  // 1296 mass-matrix entries of one cell (ecsim/simulation.cpp:488)
 constexpr int BLOCK_CUR = 36;       // 3 x 12 current partials of one cell
 constexpr int BLOCK_ALL = BLOCK_MAT + BLOCK_CUR;
