@@ -25,7 +25,7 @@
 
 namespace xb {
 
-constexpr int DEP_WARPS = CELL_GROUP;  // one warp per cell, 8 cells per CTA
+constexpr int DEP_WARPS = CELL_GROUP;  // one warp per cell
 constexpr int DEP_CHUNK = 16;          // particles staged per round
 constexpr int REC = 36;                // s[3][8], A*alpha[9], I_p[3]
 constexpr int DEP_SMEM_PER_WARP = BLOCK_ALL + DEP_CHUNK * REC;
@@ -156,9 +156,9 @@ __global__ void __launch_bounds__(DEP_WARPS * 32) k_cell_blocks(Grid g, DepositA
   }
   __syncthreads();
   // coalesced write-out: stage[group][entry][cell % 8]
-  double* out = stage + ((a.stage_cell0 >> 3) + blockIdx.x) * (int64_t)(BLOCK_ALL * CELL_GROUP);
+  double* out = stage + ((a.stage_cell0 / CELL_GROUP) + blockIdx.x) * (int64_t)(BLOCK_ALL * CELL_GROUP);
   for (int idx = threadIdx.x; idx < BLOCK_ALL * CELL_GROUP; idx += DEP_WARPS * 32) {
-    const int e = idx >> 3, w = idx & 7;
+    const int e = idx / CELL_GROUP, w = idx % CELL_GROUP;
     out[idx] = smem[(size_t)w * DEP_SMEM_PER_WARP + e];
   }
 }
@@ -178,6 +178,7 @@ constexpr int MMA_CHUNK = 32;
 constexpr int MREC = 37;  // odd stride: the 16 lanes that write records hit 16 different banks
 constexpr int MMA_SMEM_PER_CELL = BLOCK_ALL + MMA_CHUNK * MREC;
 constexpr int MMA_WARPS = 2 * CELL_GROUP;  // two warps per cell
+static_assert(CELL_GROUP == 4, "pair_barrier enumerates four cell slots");
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 {
@@ -186,15 +187,36 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 
 __device__ __forceinline__ void pair_barrier(int slot)
 {
-  asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");
+  // immediate barrier ids: the compiler then reserves 1 + CELL_GROUP barriers, not all 16
+  switch (slot) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
 }
 
-__device__ __forceinline__ void preprocess_particle(const Grid& g, const DepositArgs& a, const double* __restrict__ B, int32_t i, double* __restrict__ r)
+// Per-particle record, prepared once per particle and read by the MMA lanes:
+//   r[0..23]  = s_c(t): E-like CIC weights of the 8 corners, 3 components   (written by warp half 0)
+//   r[24..32] = A_p * alpha[c1][c2],  r[33..35] = I_p                      (written by warp half 1)
+__device__ __forceinline__ void prepare_shapes(const Grid& g, const DepositArgs& a, int32_t i, double* __restrict__ r)
 {
-  const double px = a.p[0][i], py = a.p[1][i], pz = a.p[2][i];
+  Weights w;
+  make_weights(g, a.p[0][i], a.p[1][i], a.p[2][i], a.zshift, w);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int i1 = t & 1, j1 = (t >> 1) & 1, k1 = t >> 2;
+    r[0 + t] = w.wn[2][k1] * w.wn[1][j1] * w.ws[0][i1];
+    r[8 + t] = w.wn[2][k1] * w.ws[1][j1] * w.wn[0][i1];
+    r[16 + t] = w.ws[2][k1] * w.wn[1][j1] * w.wn[0][i1];
+  }
+}
+
+__device__ __forceinline__ void prepare_fields(const Grid& g, const DepositArgs& a, const double* __restrict__ B, int32_t i, double* __restrict__ r)
+{
   const double v[3] = {a.p[3][i], a.p[4][i], a.p[5][i]};
   Weights w;
-  make_weights(g, px, py, pz, a.zshift, w);
+  make_weights(g, a.p[0][i], a.p[1][i], a.p[2][i], a.zshift, w);
   NodeOffsets off;
   make_offsets(g, w, off);
   double Bp[3], b[3];
@@ -218,23 +240,61 @@ __device__ __forceinline__ void preprocess_particle(const Grid& g, const Deposit
   r[24 + 6] = Ap * (+b[1] + b[2] * b[0]);
   r[24 + 7] = Ap * (-b[0] + b[2] * b[1]);
   r[24 + 8] = Ap * (1.0 + b[2] * b[2]);
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const int i1 = t & 1, j1 = (t >> 1) & 1, k1 = t >> 2;
-    r[0 + t] = w.wn[2][k1] * w.wn[1][j1] * w.ws[0][i1];
-    r[8 + t] = w.wn[2][k1] * w.ws[1][j1] * w.wn[0][i1];
-    r[16 + t] = w.ws[2][k1] * w.wn[1][j1] * w.wn[0][i1];
-  }
 }
 
 // The 12 DMMAs of a particle group are split between the two warps of a cell so that their
 // accumulators (and therefore their folds into the cell block) are disjoint:
 //   half 0: (0,0) (0,1) (0,2) I_0 (1,0) (1,1)      half 1: (1,2) I_1 (2,0) (2,1) (2,2) I_2
-// slot j of a half: row component R(j), column component C(j) (3 = current)
-__device__ __forceinline__ constexpr int op_row(int half, int j) { return half == 0 ? (j < 4 ? 0 : 1) : (j < 2 ? 1 : 2); }
-__device__ __forceinline__ constexpr int op_col(int half, int j)
+// slot j of a half: row component op_row, column component op_col (3 = current).
+//
+// Where a slot's 8 x 8 tile lands inside the cell's 12 x 12 block depends only on the stagger bit
+// of its row component and of its column component (src/impls/ecsim/particles.cpp:145-147), so a
+// slot has 2 (c1 == c2, current) or 4 (c1 != c2) distinct placements ("variants") over the eight
+// octants.  Each lane keeps one accumulator pair per (slot, variant) -- 18 pairs per half -- and
+// the octants of a cell accumulate straight into them: the block in shared memory is touched once
+// per cell instead of once per octant.
+__host__ __device__ constexpr int op_row(int half, int j) { return half == 0 ? (j < 4 ? 0 : 1) : (j < 2 ? 1 : 2); }
+__host__ __device__ constexpr int op_col(int half, int j)
 {
   return half == 0 ? (j < 3 ? j : (j == 3 ? 3 : j - 4)) : (j == 0 ? 2 : (j == 1 ? 3 : (j < 5 ? j - 2 : 3)));
+}
+__host__ __device__ constexpr int op_nvar(int half, int j) { return (op_col(half, j) == 3 || op_col(half, j) == op_row(half, j)) ? 2 : 4; }
+__host__ __device__ constexpr int op_base(int half, int j)
+{
+  int b = 0;
+  for (int i = 0; i < j; ++i) b += op_nvar(half, i);
+  return b;
+}
+__host__ __device__ constexpr int op_variant(int half, int j, int oct)
+{
+  const int c1 = op_row(half, j), c2 = op_col(half, j);
+  const int o1 = (oct >> c1) & 1;
+  return (c2 == 3 || c2 == c1) ? o1 : o1 * 2 + ((oct >> c2) & 1);
+}
+constexpr int NACC = 18;
+static_assert(op_base(0, 5) + op_nvar(0, 5) == NACC && op_base(1, 5) + op_nvar(1, 5) == NACC, "18 accumulator pairs per half");
+
+// all groups of one octant segment: cnt particles whose records start at r0
+template <int HALF, int OCT>
+__device__ __forceinline__ void octant_segment(const double* __restrict__ r0, int cnt, int gq, int q, double (&acc)[NACC][2])
+{
+  for (int gs = 0; gs < cnt; gs += 4) {
+    const bool valid = gs + q < cnt;
+    const double* r = r0 + min(gs + q, cnt - 1) * MREC;  // clamp: operands of padded lanes stay finite
+    double s[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s[c] = r[c * 8 + gq];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int c1 = op_row(HALF, j), c2 = op_col(HALF, j);
+      const double av = valid ? s[c1] : 0.0;
+      const double bv = c2 < 3 ? r[24 + c1 * 3 + c2] * s[c2] : (gq == 0 ? r[33 + c1] : 0.0);
+      const int v = op_base(HALF, j) + op_variant(HALF, j, OCT);
+      dmma(acc[v][0], acc[v][1], av, bv);
+    }
+  }
 }
 
 template <int HALF>
@@ -246,72 +306,70 @@ __device__ __forceinline__ void cell_half(const Grid& g, const DepositArgs& a, c
   const int32_t p0 = __shfl_sync(0xffffffffu, bs, 0), p1 = __shfl_sync(0xffffffffu, bs, 8);
   int oct = 0;
   int32_t oend = __shfl_sync(0xffffffffu, bs, 1);
-  bool dirty = false;
-  double acc[6][2];
+  double acc[NACC][2];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) acc[j][0] = acc[j][1] = 0.0;
-
-  auto fold = [&]() {
-    const int ox = oct & 1, oy = (oct >> 1) & 1, oz = oct >> 2;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      constexpr int dummy = 0;
-      (void)dummy;
-      const int c1 = op_row(HALF, j), c2 = op_col(HALF, j);
-      const int row = block_pos(c1, gq, ox, oy, oz);
-      if (c2 < 3) {
-        const int e = (c1 * 3 + c2) * 144 + row * 12;
-        block[e + block_pos(c2, 2 * q, ox, oy, oz)] += acc[j][0];
-        block[e + block_pos(c2, 2 * q + 1, ox, oy, oz)] += acc[j][1];
-      }
-      else if (q == 0) {
-        block[BLOCK_MAT + c1 * 12 + row] += acc[j][0];
-      }
-      acc[j][0] = acc[j][1] = 0.0;
-    }
-    __syncwarp();
-  };
+  for (int v = 0; v < NACC; ++v) acc[v][0] = acc[v][1] = 0.0;
 
   for (int32_t base = p0; base < p1; base += MMA_CHUNK) {
     const int n = min(MMA_CHUNK, p1 - base);
-    {  // each warp prepares 16 of the chunk's 32 records
-      const int pi = HALF * 16 + lane;
-      if (lane < 16 && pi < n) preprocess_particle(g, a, B, base + pi, rec + pi * MREC);
+    if (lane < n) {  // half 0 prepares the shape part of the 32 records, half 1 the field part
+      if (HALF == 0)
+        prepare_shapes(g, a, base + lane, rec + lane * MREC);
+      else
+        prepare_fields(g, a, B, base + lane, rec + lane * MREC);
     }
     pair_barrier(slot);
     int32_t pos = base;
     const int32_t cend = base + n;
     while (pos < cend) {
       while (oend <= pos) {  // the octant's particles are exhausted (warp-uniform)
-        if (dirty) fold();
-        dirty = false;
         ++oct;
         oend = __shfl_sync(0xffffffffu, bs, oct + 1);
       }
       const int32_t seg_end = min(oend, cend);
-      for (int32_t gs = pos; gs < seg_end; gs += 4) {
-        const bool valid = gs + q < seg_end;
-        const double* r = rec + (min(gs + q, seg_end - 1) - base) * MREC;  // clamp: operands stay finite
-        double s[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) s[c] = r[c * 8 + gq];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const int c1 = op_row(HALF, j), c2 = op_col(HALF, j);
-          const double av = valid ? s[c1] : 0.0;
-          const double bv = c2 < 3 ? r[24 + c1 * 3 + c2] * s[c2] : (gq == 0 ? r[33 + c1] : 0.0);
-          dmma(acc[j][0], acc[j][1], av, bv);
-        }
+      const double* r0 = rec + (pos - base) * MREC;
+      const int cnt = seg_end - pos;
+      switch (oct) {
+        case 0: octant_segment<HALF, 0>(r0, cnt, gq, q, acc); break;
+        case 1: octant_segment<HALF, 1>(r0, cnt, gq, q, acc); break;
+        case 2: octant_segment<HALF, 2>(r0, cnt, gq, q, acc); break;
+        case 3: octant_segment<HALF, 3>(r0, cnt, gq, q, acc); break;
+        case 4: octant_segment<HALF, 4>(r0, cnt, gq, q, acc); break;
+        case 5: octant_segment<HALF, 5>(r0, cnt, gq, q, acc); break;
+        case 6: octant_segment<HALF, 6>(r0, cnt, gq, q, acc); break;
+        default: octant_segment<HALF, 7>(r0, cnt, gq, q, acc); break;
       }
-      dirty = true;
       pos = seg_end;
     }
     pair_barrier(slot);  // both warps are done with the records before the next chunk overwrites them
   }
-  if (dirty) fold();
+
+  // one fold per cell: variants of a slot may land on the same entry, so they go in separate passes
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int c1 = op_row(HALF, j), c2 = op_col(HALF, j);
+#pragma unroll
+    for (int v = 0; v < op_nvar(HALF, j); ++v) {
+      const int o1 = op_nvar(HALF, j) == 2 ? v : (v >> 1), o2 = op_nvar(HALF, j) == 2 ? v : (v & 1);
+      // block_pos only looks at the stagger bit of its own component
+      const int row = block_pos(c1, gq, o1, o1, o1);
+      const int k = op_base(HALF, j) + v;
+      if (c2 < 3) {
+        const int e = (c1 * 3 + c2) * 144 + row * 12;
+        block[e + block_pos(c2, 2 * q, o2, o2, o2)] += acc[k][0];
+        block[e + block_pos(c2, 2 * q + 1, o2, o2, o2)] += acc[k][1];
+      }
+      else if (q == 0) {
+        block[BLOCK_MAT + c1 * 12 + row] += acc[k][0];
+      }
+      __syncwarp();
+    }
+  }
 }
 
-__global__ void __launch_bounds__(MMA_WARPS * 32) k_cell_blocks_mma(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage)
+__global__ void __launch_bounds__(MMA_WARPS * 32, 2) k_cell_blocks_mma(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage)
 {
   extern __shared__ double smem[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -320,6 +378,30 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) k_cell_blocks_mma(Grid g, Depo
   double* rec = block + BLOCK_ALL;
   const int64_t cell_local = (int64_t)blockIdx.x * CELL_GROUP + slot;
 
+  {
+    // The four cells of the CTA own one contiguous particle range: pull its six SoA segments into
+    // L1 now (one prefetch per 128-byte line), so the record preparation below does not expose a
+    // DRAM round trip per chunk; also nudge the range of a CTA that will run later into L2.
+    const int64_t c0 = (int64_t)blockIdx.x * CELL_GROUP;
+    const int64_t c1 = min(c0 + CELL_GROUP, a.ncells);
+    const int32_t q0 = a.bin_start[(a.bin_cell0 + c0) << 3], q1 = a.bin_start[(a.bin_cell0 + c1) << 3];
+    const int nlines = (int)((((int64_t)q1 * 8 + 127) >> 7) - (((int64_t)q0 * 8) >> 7));
+    for (int t = threadIdx.x; t < 6 * nlines; t += MMA_WARPS * 32) {
+      const int arr = t / nlines, ln = t % nlines;
+      const char* p = reinterpret_cast<const char*>(a.p[arr]) + ((((int64_t)q0 * 8) >> 7) << 7) + (int64_t)ln * 128;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    }
+    const int64_t far = c0 + (int64_t)CELL_GROUP * 2 * 148 * 2;  // a CTA roughly two waves ahead
+    if (far + CELL_GROUP <= a.ncells) {
+      const int32_t f0 = a.bin_start[(a.bin_cell0 + far) << 3], f1 = a.bin_start[(a.bin_cell0 + far + CELL_GROUP) << 3];
+      const int flines = (int)((((int64_t)f1 * 8 + 127) >> 7) - (((int64_t)f0 * 8) >> 7));
+      for (int t = threadIdx.x; t < 6 * flines; t += MMA_WARPS * 32) {
+        const int arr = t / flines, ln = t % flines;
+        const char* p = reinterpret_cast<const char*>(a.p[arr]) + ((((int64_t)f0 * 8) >> 7) << 7) + (int64_t)ln * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      }
+    }
+  }
   for (int e = half * 32 + lane; e < BLOCK_ALL; e += 64) block[e] = 0.0;
   pair_barrier(slot);
 
@@ -331,9 +413,9 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) k_cell_blocks_mma(Grid g, Depo
       cell_half<1>(g, a, B, block, rec, slot, lane, bin0);
   }
   __syncthreads();
-  double* out = stage + ((a.stage_cell0 >> 3) + blockIdx.x) * (int64_t)(BLOCK_ALL * CELL_GROUP);
+  double* out = stage + ((a.stage_cell0 / CELL_GROUP) + blockIdx.x) * (int64_t)(BLOCK_ALL * CELL_GROUP);
   for (int idx = threadIdx.x; idx < BLOCK_ALL * CELL_GROUP; idx += MMA_WARPS * 32) {
-    const int e = idx >> 3, w = idx & 7;
+    const int e = idx / CELL_GROUP, w = idx % CELL_GROUP;
     out[idx] = smem[(size_t)w * MMA_SMEM_PER_CELL + e];
   }
 }
@@ -354,7 +436,7 @@ __device__ __forceinline__ int64_t stage_cell(const Grid& g, const GatherArgs& a
 
 __device__ __forceinline__ double stage_read(const double* __restrict__ stage, int64_t cell, int e)
 {
-  return __ldg(stage + (cell >> 3) * (int64_t)(BLOCK_ALL * CELL_GROUP) + (int64_t)e * CELL_GROUP + (cell & 7));
+  return __ldg(stage + (cell / CELL_GROUP) * (int64_t)(BLOCK_ALL * CELL_GROUP) + (int64_t)e * CELL_GROUP + (cell % CELL_GROUP));
 }
 
 template <int C1, int C2>
@@ -485,7 +567,7 @@ int deposit_moments(xb_ctx* c)
     a.q = s.q;
     a.m = s.m;
     a.mpw = s.n / (double)s.Np;
-    if ((a.stage_cell0 & 7) != 0) XB_FAIL("deposit: plane size must be a multiple of 8 cells in multi-rank runs");
+    if ((a.stage_cell0 % CELL_GROUP) != 0) XB_FAIL("deposit: plane size must be a multiple of the staging group in multi-rank runs");
     const int groups = (int)((a.ncells + CELL_GROUP - 1) / CELL_GROUP);
     if (use_mma)
       XB_LAUNCH(c, k_cell_blocks_mma, groups, MMA_WARPS * 32, smem, g, a, c->B, c->stage);
