@@ -109,6 +109,24 @@ int comm_exchange(xb_ctx* c, const void* to_down, size_t n_to_down, const void* 
   return 0;
 }
 
+int comm_exchange_list(xb_ctx* c, const ExchangeList& l)
+{
+  Comm* cm = c->comm;
+  XB_NCCL(api.GroupStart());
+  // same ordering rule as comm_exchange: everything for `down` first, then everything for `up`;
+  // receives from `up` first, then from `down` (keeps message order consistent when up == down)
+  for (int i = 0; i < l.n; ++i)
+    if (l.n_to_down[i]) XB_NCCL(api.Send(l.to_down[i], l.n_to_down[i], ncclUint8, cm->down, cm->comm, c->stream));
+  for (int i = 0; i < l.n; ++i)
+    if (l.n_to_up[i]) XB_NCCL(api.Send(l.to_up[i], l.n_to_up[i], ncclUint8, cm->up, cm->comm, c->stream));
+  for (int i = 0; i < l.n; ++i)
+    if (l.n_from_up[i]) XB_NCCL(api.Recv(l.from_up[i], l.n_from_up[i], ncclUint8, cm->up, cm->comm, c->stream));
+  for (int i = 0; i < l.n; ++i)
+    if (l.n_from_down[i]) XB_NCCL(api.Recv(l.from_down[i], l.n_from_down[i], ncclUint8, cm->down, cm->comm, c->stream));
+  XB_NCCL(api.GroupEnd());
+  return 0;
+}
+
 // ghost planes [-w, 0) <- down's top planes ; [nzl, nzl + w) <- up's bottom planes
 int comm_halo_fill(xb_ctx* c, double* v, int w)
 {

@@ -18,6 +18,16 @@ int comm_allreduce_sum(xb_ctx* c, double* dev, int n);
 // received (sizes in bytes, known on both sides).
 int comm_exchange(xb_ctx* c, const void* to_down, size_t n_to_down, const void* to_up, size_t n_to_up, void* from_up,
                   size_t n_from_up, void* from_down, size_t n_from_down);
+// The same for lists of buffers (particle SoA segments), all inside one NCCL group.
+struct ExchangeList {
+  int n = 0;
+  const void* to_down[16];
+  const void* to_up[16];
+  void* from_up[16];
+  void* from_down[16];
+  size_t n_to_down[16], n_to_up[16], n_from_up[16], n_from_down[16];
+};
+int comm_exchange_list(xb_ctx* c, const ExchangeList& l);
 int add_planes(xb_ctx* c, double* dst, const double* src, int64_t n);  // fields.cu
 
 }  // namespace xb

@@ -74,6 +74,17 @@ struct Solver {
   double rnorm = 0.0;
 };
 
+struct MigrateBuffers {  // multi-rank only (migrate.cu)
+  double* send[2][7] = {{nullptr}};   // [0] to the rank below, [1] to the rank above; 6 SoA arrays + ids
+  double* recv[2][7] = {{nullptr}};   // [0] from below, [1] from above
+  double* ghost[2][6] = {{nullptr}};  // copies of the neighbours' boundary-plane particles
+  int32_t* ghost_bins[2] = {nullptr, nullptr};
+  int32_t* recv_key[2] = {nullptr, nullptr};
+  int64_t cap = 0, ghost_cap = 0;
+  unsigned long long* counts_dev = nullptr;
+  unsigned long long* counts_host = nullptr;
+};
+
 struct Species {
   double q, m, n;
   int Np;
@@ -87,6 +98,7 @@ struct Species {
   double* currJe = nullptr;
   uint64_t next_id = 0;
   bool sorted = false;
+  MigrateBuffers* mig = nullptr;
   // ecsimcorr::Particles scalars (src/impls/ecsimcorr/particles.h:33-38)
   double energy = 0, pred_w = 0, corr_w = 0, pred_dK = 0, corr_dK = 0, lambda_dK = 0;
 };
@@ -177,6 +189,7 @@ int krylov_prepare(xb_ctx* c);  // allocate the Krylov workspace up front (not i
 // ---- particles.cu ----------------------------------------------------------------------------
 int species_alloc(xb_ctx* c, Species& s, int64_t capacity);
 void species_free(Species& s);
+void migrate_free(Species& s);  // migrate.cu
 int particles_sort(xb_ctx* c, Species& s, double dt_move);   // r += v dt_move, wrap, re-bin
 int push_second(xb_ctx* c, Species& s, const double* Eh, const double* B);
 int kinetic_energy(xb_ctx* c, Species& s, double* sum_v2, double* K);

@@ -540,39 +540,47 @@ static int launch_gather(xb_ctx* c, const GatherArgs& ga, int accumulate)
 
 int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage);  // migrate.cu (multi-rank only)
 
-int deposit_moments(xb_ctx* c)
+// cell blocks of `ncells` consecutive cells (bin space) into the staging area
+int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* bin_start, int64_t bin_cell0, int64_t ncells, int64_t stage_cell0,
+                  int zshift)
 {
-  const Grid& g = c->g;
   static bool attr_set = false;
   const bool use_mma = c->deposit_variant != 1;
   const size_t smem = sizeof(double) * (use_mma ? MMA_SMEM_PER_CELL : DEP_SMEM_PER_WARP) * CELL_GROUP;
   if (!attr_set) {
-    XB_CUDA(cudaFuncSetAttribute(k_cell_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * DEP_SMEM_PER_WARP * DEP_WARPS)));
+    XB_CUDA(cudaFuncSetAttribute(k_cell_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * DEP_SMEM_PER_WARP * CELL_GROUP)));
     XB_CUDA(cudaFuncSetAttribute(k_cell_blocks_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * MMA_SMEM_PER_CELL * CELL_GROUP)));
     attr_set = true;
   }
+  DepositArgs a;
+  for (int k = 0; k < 6; ++k) a.p[k] = p[k];
+  a.bin_start = bin_start;
+  a.bin_cell0 = bin_cell0;
+  a.ncells = ncells;
+  a.stage_cell0 = stage_cell0;
+  a.zshift = zshift;
+  a.q = s.q;
+  a.m = s.m;
+  a.mpw = s.n / (double)s.Np;
+  if ((a.stage_cell0 % CELL_GROUP) != 0) XB_FAIL("deposit: plane size must be a multiple of the staging group in multi-rank runs");
+  const int groups = (int)((a.ncells + CELL_GROUP - 1) / CELL_GROUP);
+  if (use_mma)
+    XB_LAUNCH(c, k_cell_blocks_mma, groups, MMA_WARPS * 32, smem, c->g, a, c->B, c->stage);
+  else
+    XB_LAUNCH(c, k_cell_blocks, groups, DEP_WARPS * 32, smem, c->g, a, c->B, c->stage);
+  return 0;
+}
+
+int deposit_moments(xb_ctx* c)
+{
+  const Grid& g = c->g;
   XB_CHECK(halo_fill(c, c->B, GZ));
   const bool single = g.nranks == 1;
   bool first = true;
   for (auto& s : c->sorts) {
     if (!s.sorted) XB_FAIL("deposit: particles are not sorted");
-    DepositArgs a;
-    double** p = s.p[s.cur];
-    for (int k = 0; k < 6; ++k) a.p[k] = p[k];
-    a.bin_start = s.bin_start;
-    a.bin_cell0 = g.plane;  // bin plane 1 = first owned plane
-    a.ncells = g.ncl;
-    a.stage_cell0 = single ? 0 : g.plane;
-    a.zshift = 0;
-    a.q = s.q;
-    a.m = s.m;
-    a.mpw = s.n / (double)s.Np;
-    if ((a.stage_cell0 % CELL_GROUP) != 0) XB_FAIL("deposit: plane size must be a multiple of the staging group in multi-rank runs");
-    const int groups = (int)((a.ncells + CELL_GROUP - 1) / CELL_GROUP);
-    if (use_mma)
-      XB_LAUNCH(c, k_cell_blocks_mma, groups, MMA_WARPS * 32, smem, g, a, c->B, c->stage);
-    else
-      XB_LAUNCH(c, k_cell_blocks, groups, DEP_WARPS * 32, smem, g, a, c->B, c->stage);
+    // bin plane 1 = first owned plane; staging plane 0 is the low ghost plane in multi-rank runs
+    XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane, g.ncl, single ? 0 : g.plane, 0));
     if (!single) XB_CHECK(deposit_ghost_cells(c, s, c->stage));
     GatherArgs ga{c->stage, single ? 1 : 0};
     const int acc = first ? 0 : 1;

@@ -106,6 +106,45 @@ __device__ __forceinline__ void gather_B(const Grid& g, const double* __restrict
       }
 }
 
+// ---- binning ------------------------------------------------------------------------------------
+// periodic wrap of one coordinate, src/interfaces/point.cpp:18-26
+__device__ __forceinline__ double wrap_coord(double s, double L)
+{
+  if (s < 0.0)
+    s = L - (0.0 - s);
+  else if (s > L)
+    s = 0.0 + (s - L);
+  // s == L is the same point as 0 (the reference would index cell N there and drop the particle,
+  // src/interfaces/particles.cpp:101-104; a measure-zero event we fold back instead)
+  if (s >= L) s = 0.0;
+  if (s < 0.0) s = 0.0;
+  return s;
+}
+
+// bin plane of a (wrapped) z: 1..nzl inside the slab, 0 / nzl + 1 for the neighbour below / above
+__device__ __forceinline__ int slab_plane(const Grid& g, double pz)
+{
+  int iz = (int)floor(to_cells(pz, g.dz, g.inv_dz, g.exact_inv & 4));
+  iz = min(max(iz, 0), g.nz - 1);
+  const int rel = iz - g.z0;
+  if (rel >= 0 && rel < g.nzl) return rel + 1;
+  const int up = (iz - (g.z0 + g.nzl) + 2 * g.nz) % g.nz;  // planes above the slab top (periodic)
+  const int dn = (g.z0 - 1 - iz + 2 * g.nz) % g.nz;        // planes below the slab bottom
+  return up <= dn ? g.nzl + 1 : 0;
+}
+
+// bin = (cell << 3) | octant, cell over the nzl + 2 bin planes
+__device__ __forceinline__ int32_t particle_key(const Grid& g, double px, double py, double pz, int pl)
+{
+  int ix, iy, iz, ox, oy, oz;
+  cell_and_octant(to_cells(px, g.dx, g.inv_dx, g.exact_inv & 1), ix, ox);
+  cell_and_octant(to_cells(py, g.dy, g.inv_dy, g.exact_inv & 2), iy, oy);
+  cell_and_octant(to_cells(pz, g.dz, g.inv_dz, g.exact_inv & 4), iz, oz);
+  ix = min(max(ix, 0), g.nx - 1);
+  iy = min(max(iy, 0), g.ny - 1);
+  return (int32_t)(((((int64_t)pl * g.ny + iy) * g.nx + ix) << 3) | (oz << 2) | (oy << 1) | ox);
+}
+
 __device__ __forceinline__ void cross3(const double* a, const double* b, double* o)
 {
   o[0] = +(a[1] * b[2] - a[2] * b[1]);

@@ -50,24 +50,12 @@ void species_free(Species& s)
   cudaFree(s.bin_start);
   cudaFree(s.currI);
   cudaFree(s.currJe);
+  migrate_free(s);
 }
 
 // ---------------------------------------------------------------------------------------------
 // pass 1: r += v * dtm, periodic wrap (point.cpp:18-26), bin key, histogram
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double wrap_coord(double s, double L)
-{
-  if (s < 0.0)
-    s = L - (0.0 - s);
-  else if (s > L)
-    s = 0.0 + (s - L);
-  // s == L is the same point as 0 (the reference would index cell N there and drop the particle,
-  // src/interfaces/particles.cpp:101-104; a measure-zero event we fold back instead)
-  if (s >= L) s = 0.0;
-  if (s < 0.0) s = 0.0;
-  return s;
-}
-
 __global__ void k_move_key(Grid g, int64_t n, double* __restrict__ x, double* __restrict__ y, double* __restrict__ z,
                            const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz, double dtm,
                            int32_t* __restrict__ key, int32_t* __restrict__ hist)
@@ -86,23 +74,7 @@ __global__ void k_move_key(Grid g, int64_t n, double* __restrict__ x, double* __
   x[i] = px;
   y[i] = py;
   z[i] = pz;
-  int ix, iy, iz, ox, oy, oz;
-  cell_and_octant(to_cells(px, g.dx, g.inv_dx, g.exact_inv & 1), ix, ox);
-  cell_and_octant(to_cells(py, g.dy, g.inv_dy, g.exact_inv & 2), iy, oy);
-  cell_and_octant(to_cells(pz, g.dz, g.inv_dz, g.exact_inv & 4), iz, oz);
-  ix = min(max(ix, 0), g.nx - 1);
-  iy = min(max(iy, 0), g.ny - 1);
-  iz = min(max(iz, 0), g.nz - 1);
-  int pl;
-  const int rel = iz - g.z0;
-  if (rel >= 0 && rel < g.nzl)
-    pl = rel + 1;
-  else {
-    const int up = (iz - (g.z0 + g.nzl) + 2 * g.nz) % g.nz;  // planes above the slab top (periodic)
-    const int dn = (g.z0 - 1 - iz + 2 * g.nz) % g.nz;        // planes below the slab bottom
-    pl = up <= dn ? g.nzl + 1 : 0;
-  }
-  const int32_t k = (int32_t)(((((int64_t)pl * g.ny + iy) * g.nx + ix) << 3) | (oz << 2) | (oy << 1) | ox);
+  const int32_t k = particle_key(g, px, py, pz, slab_plane(g, pz));
   key[i] = k;
   atomicAdd(&hist[k], 1);
 }
@@ -211,10 +183,10 @@ __global__ void k_scatter(int64_t n, const int32_t* __restrict__ key, int32_t* _
                           double* __restrict__ d4, double* __restrict__ d5, uint64_t* __restrict__ did)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const bool live = i < n;
+  const int32_t k = i < n ? key[i] : -1;
+  const bool live = k >= 0;  // key -1: the particle left the slab (migrate.cu)
   const unsigned active = __ballot_sync(0xffffffffu, live);
   if (!live) return;
-  const int32_t k = key[i];
   const unsigned peers = __match_any_sync(active, k);
   const int lane = threadIdx.x & 31;
   const int leader = __ffs(peers) - 1;
@@ -265,27 +237,45 @@ __global__ void k_order_bins(int64_t nbins, const int32_t* __restrict__ bin_star
   }
 }
 
-int particles_sort(xb_ctx* c, Species& s, double dt_move)
+// scan the histogram, scatter the local particles (and, in multi-rank runs, the arrivals) into the
+// other SoA buffer, canonicalise the order inside every bin when ids are tracked
+int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBuffers* arr, int64_t n_from_down, int64_t n_from_up)
 {
-  const Grid& g = c->g;
-  const int64_t n = s.count;
-  XB_CUDA(cudaMemsetAsync(c->hist, 0, sizeof(int32_t) * c->nbins, c->stream));
-  double** p = s.p[s.cur];
-  if (n > 0) XB_LAUNCH(c, k_move_key, grid_for(n), 256, 0, g, n, p[0], p[1], p[2], p[3], p[4], p[5], dt_move, s.key, c->hist);
-  if (g.nranks > 1) XB_FAIL("particles_sort: multi-rank migration goes through migrate.cu");
   const int ntiles = (int)((c->nbins + SCAN_TILE - 1) / SCAN_TILE);
   XB_LAUNCH(c, k_scan_tiles, ntiles, SCAN_THREADS, 0, c->hist, s.bin_start, c->nbins, c->scan_tmp);
   XB_LAUNCH(c, k_scan_sums, 1, 1024, 0, c->scan_tmp, ntiles, s.bin_start + c->nbins);
   XB_LAUNCH(c, k_scan_add, grid_for(c->nbins), 256, 0, s.bin_start, c->nbins, c->scan_tmp, c->cursor);
+  double** p = s.p[s.cur];
   double** d = s.p[1 - s.cur];
-  if (n > 0)
-    XB_LAUNCH(c, k_scatter, grid_for(n), 256, 0, n, s.key, c->cursor, p[0], p[1], p[2], p[3], p[4], p[5], s.id[s.cur], d[0], d[1], d[2], d[3], d[4],
-              d[5], s.id[1 - s.cur]);
+  uint64_t* did = s.id[1 - s.cur];
+  if (nlocal > 0)
+    XB_LAUNCH(c, k_scatter, grid_for(nlocal), 256, 0, nlocal, s.key, c->cursor, p[0], p[1], p[2], p[3], p[4], p[5], s.id[s.cur], d[0], d[1], d[2], d[3],
+              d[4], d[5], did);
+  if (arr) {
+    const int64_t na[2] = {n_from_down, n_from_up};
+    for (int k = 0; k < 2; ++k)
+      if (na[k] > 0)
+        XB_LAUNCH(c, k_scatter, grid_for(na[k]), 256, 0, na[k], arr->recv_key[k], c->cursor, arr->recv[k][0], arr->recv[k][1], arr->recv[k][2],
+                  arr->recv[k][3], arr->recv[k][4], arr->recv[k][5], c->track_ids ? reinterpret_cast<const uint64_t*>(arr->recv[k][6]) : nullptr, d[0],
+                  d[1], d[2], d[3], d[4], d[5], did);
+  }
   s.cur = 1 - s.cur;
-  if (c->track_ids && n > 0) {
+  if (c->track_ids) {
     double** q = s.p[s.cur];
     XB_LAUNCH(c, k_order_bins, grid_for(c->nbins, 128), 128, 0, c->nbins, s.bin_start, q[0], q[1], q[2], q[3], q[4], q[5], s.id[s.cur]);
   }
+  return 0;
+}
+
+int particles_sort(xb_ctx* c, Species& s, double dt_move)
+{
+  const Grid& g = c->g;
+  const int64_t n = s.count;
+  if (g.nranks > 1) XB_FAIL("particles_sort: multi-rank runs sort through migrate_and_sort");
+  XB_CUDA(cudaMemsetAsync(c->hist, 0, sizeof(int32_t) * c->nbins, c->stream));
+  double** p = s.p[s.cur];
+  if (n > 0) XB_LAUNCH(c, k_move_key, grid_for(n), 256, 0, g, n, p[0], p[1], p[2], p[3], p[4], p[5], dt_move, s.key, c->hist);
+  XB_CHECK(sort_scan_and_scatter(c, s, n, nullptr, 0, 0));
   s.sorted = true;
   return 0;
 }
