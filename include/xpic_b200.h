@@ -129,6 +129,9 @@ int xb_run_steps(xb_ctx* ctx, int32_t scheme, int32_t k, double* ms);
 int xb_run_steps_host(xb_ctx* ctx, int32_t scheme, int32_t k, double* E, double* B, const double* B0, double* kinetic, double* ms);
 
 int xb_scalar(xb_ctx* ctx, int32_t sid, int32_t which, double* out);
+/* Energy::calculate_kinetic's sums over all ranks (src/diagnostics/energy.cpp:61-107):
+ * out = { sum vx, sum vy, sum vz, sum v^2, number of particles }. */
+int xb_particle_moments(xb_ctx* ctx, int32_t sid, double out[5]);
 
 /* Seconds / launches accumulated per stage since the last reset (SyncClock, utils/sync_clock.cpp:75-93). */
 int xb_timing(xb_ctx* ctx, int32_t stage, double* seconds, int64_t* calls);

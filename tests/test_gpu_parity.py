@@ -183,3 +183,34 @@ def test_energy_conservation_32cubed(X):
     tot.append(wE + wB + s.scalar("kinetic"))
     assert np.max(np.abs(np.diff(tot))) < 1e-9 * tot[0] + 1e-9
     assert s.launch_count() > 0
+
+
+def test_host_program_reproduces_golden_tables(X, tmp_path):
+    """The C++ host mirror (config.json in, temporal/*.txt out) against the reference's golden
+    tables: same file format (tests/common.h:30-89 compares column by column), same numbers."""
+    import json
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "xpic_b200", "_build", "xpic_b200.out")
+    if not os.path.exists(exe):
+        pytest.skip("host program not built")
+    for name, opts in (("ecsim_ex1", ["-ksp_rtol", "1e-11", "-ksp_atol", "1e-50"]),
+                       ("ecsimcorr_ex1", ["-predict_ksp_rtol", "1e-11", "-predict_ksp_atol", "1e-50", "-correct_ksp_rtol", "1e-11", "-correct_ksp_atol", "1e-50"])):
+        cfg = json.load(open(os.path.join(ROOT, "configs", name + ".json")))
+        cfg["OutputDirectory"] = str(tmp_path / name)
+        path = tmp_path / (name + ".json")
+        path.write_text(json.dumps(cfg))
+        subprocess.run([exe, str(path), "-curl_sign", "-1", "-ksp_max_it", "500"] + opts, check=True, capture_output=True, timeout=300)
+        for table in ("energy.txt", "energy_conservation.txt"):
+            tg, gold = O.read_table(os.path.join(GOLDEN, name, table))
+            to, out = O.read_table(str(tmp_path / name / "temporal" / table))
+            assert to == tg  # identical headers (titles are truncated to the column width)
+            rows = out.shape[0]
+            assert rows == 11
+            if table == "energy.txt":
+                np.testing.assert_allclose(out[:, 1:4], gold[:rows, 1:4], rtol=2e-6, atol=1e-10)
+            else:
+                np.testing.assert_allclose(out[:, 1:4], gold[:rows, 1:4], rtol=1e-4, atol=2e-9)
+                assert np.max(np.abs(out[:, -2 if name == "ecsimcorr_ex1" else -1])) < 1e-11

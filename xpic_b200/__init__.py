@@ -6,9 +6,9 @@ build helper.  There is no CPU fallback: importing works anywhere, creating a Si
 needs the built library and a CUDA device.
 """
 from .binding import (ECSIM, ECSIMCORR, FIELDS, SCALARS, STAGES, Simulation, XpicB200Error, build_library, coef_table,
-                      comm_unique_id, library_path, load_library)
+                      comm_unique_id, library_path, load_library, owner_rank, slab_range)
 
 __all__ = [
     "ECSIM", "ECSIMCORR", "FIELDS", "SCALARS", "STAGES", "Simulation", "XpicB200Error", "build_library", "coef_table",
-    "comm_unique_id", "library_path", "load_library",
+    "comm_unique_id", "library_path", "load_library", "owner_rank", "slab_range",
 ]

@@ -31,6 +31,21 @@ class _Grid(C.Structure):
                 ("rank", C.c_int32), ("nranks", C.c_int32), ("track_ids", C.c_int32)]
 
 
+def slab_range(nz, rank, nranks):
+    """Planes [z0, z0 + nzl) of z-slab `rank` (DMDA's default split: the first nz % nranks slabs are
+    one plane thicker).  Must agree with xb_create (csrc/api.cu)."""
+    base, rem = divmod(int(nz), int(nranks))
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+
+
+def owner_rank(z_cell, nz, nranks):
+    """Rank owning global cell plane z_cell (interfaces::Particles::add_particle keeps a particle on the
+    rank whose box contains floor(z / dz), src/interfaces/particles.cpp:47-57)."""
+    base, rem = divmod(int(nz), int(nranks))
+    split = rem * (base + 1)
+    return z_cell // (base + 1) if z_cell < split else rem + (z_cell - split) // base
+
+
 def library_path():
     return _LIB
 
@@ -76,6 +91,7 @@ SYMBOLS = {
     "xb_spmv_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "xb_spmv_profile_read": (C.c_int, [C.c_void_p, _i64p, _dp]),
     "xb_scalar": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "xb_particle_moments": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "xb_timing": (C.c_int, [C.c_void_p, C.c_int32, _dp, _i64p]),
     "xb_timing_reset": (C.c_int, [C.c_void_p]),
     "xb_launch_count": (C.c_int, [C.c_void_p, _i64p]),
@@ -143,9 +159,7 @@ class Simulation:
         self.dt = float(dt)
         self.scheme = scheme
         self.rank, self.nranks = rank, nranks
-        base, rem = divmod(self.n[2], nranks)
-        self.nzl = base + (1 if rank < rem else 0)
-        self.z0 = rank * base + min(rank, rem)
+        self.z0, self.nzl = slab_range(self.n[2], rank, nranks)
         self.ncl = self.n[0] * self.n[1] * self.nzl
         self.nown = 3 * self.ncl
         g = _Grid()
@@ -269,6 +283,11 @@ class Simulation:
         out = C.c_double()
         _check(self._L.xb_scalar(self._h, sid, SCALARS[name], C.byref(out)))
         return out.value
+
+    def particle_moments(self, sid=0):
+        out = np.zeros(5)
+        _check(self._L.xb_particle_moments(self._h, sid, _as_dp(out)))
+        return out
 
     def field_energies(self):
         E, B = self.get_field("E"), self.get_field("B")

@@ -547,6 +547,13 @@ int xb_scalar(xb_ctx* c, int32_t sid, int32_t which, double* out)
   XB_FAIL("unknown scalar");
 }
 
+int xb_particle_moments(xb_ctx* c, int32_t sid, double out[5])
+{
+  XB_API_BEGIN(c);
+  if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
+  return particle_moments(c, c->sorts[sid], out);
+}
+
 int xb_timing(xb_ctx* c, int32_t stage, double* seconds, int64_t* calls)
 {
   XB_API_BEGIN(c);

@@ -194,6 +194,7 @@ int particles_sort(xb_ctx* c, Species& s, double dt_move);   // r += v dt_move, 
 int push_second(xb_ctx* c, Species& s, const double* Eh, const double* B);
 int kinetic_energy(xb_ctx* c, Species& s, double* sum_v2, double* K);
 int scale_velocities(xb_ctx* c, Species& s, double lambda);
+int particle_moments(xb_ctx* c, Species& s, double* out5);
 int particles_generate(xb_ctx* c, Species& s, int64_t total, const double* T, uint64_t seed, int tov, int64_t* added);
 
 // ---- deposit.cu ------------------------------------------------------------------------------

@@ -10,6 +10,7 @@
 //   ecsim::Particles::second_push  src/impls/ecsim/particles.cpp:175-192
 //   Energy::calculate_kinetic      src/diagnostics/energy.cpp:61-107
 // All kernels are HBM-bound streams over the SoA arrays (72 B / particle for a push).
+#include "comm.cuh"
 #include "common.cuh"
 #include "gather.cuh"
 
@@ -415,6 +416,50 @@ int kinetic_energy(xb_ctx* c, Species& s, double* sum_v2, double* K)
   XB_CHECK(reduce_finish(c, 1, &w));
   if (sum_v2) *sum_v2 = w;
   if (K) *K = 0.5 * s.m * (s.n / (double)s.Np) * w;  // diagnostics/energy.cpp:70-88
+  return 0;
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_moments(int64_t n, const double* __restrict__ vx, const double* __restrict__ vy,
+                                                        const double* __restrict__ vz, double* __restrict__ partial)
+{
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = vx[i], y = vy[i], z = vz[i];
+    a[0] += x;
+    a[1] += y;
+    a[2] += z;
+    a[3] += (x * x + y * y) + z * z;
+  }
+  __shared__ double sh[RED_THREADS / 32][4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double t = warp_sum(a[k]);
+    if (lane == 0) sh[wid][k] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int q = 0; q < RED_THREADS / 32; ++q) t += sh[q][threadIdx.x];
+    partial[(int64_t)blockIdx.x * RED_MAXV + threadIdx.x] = t;
+  }
+}
+
+int particle_moments(xb_ctx* c, Species& s, double* out5)
+{
+  double** p = s.p[s.cur];
+  XB_LAUNCH(c, k_moments, RED_BLOCKS, RED_THREADS, 0, s.count, p[3], p[4], p[5], c->red_partial);
+  XB_CHECK(reduce_finish(c, 4, out5));
+  double n = (double)s.count;
+  if (c->g.nranks > 1) {
+    c->red_host[0] = n;
+    XB_CUDA(cudaMemcpyAsync(c->red_out, c->red_host, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    XB_CHECK(comm_allreduce_sum(c, c->red_out, 1));
+    XB_CUDA(cudaMemcpyAsync(c->red_host, c->red_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    XB_CUDA(cudaStreamSynchronize(c->stream));
+    n = c->red_host[0];
+  }
+  out5[4] = n;
   return 0;
 }
 

@@ -1,0 +1,392 @@
+// xpic_host.cpp -- see xpic_host.h.
+#include "xpic_host.h"
+
+#include <cmath>
+#include <filesystem>
+#include <format>
+#include <iostream>
+#include <stdexcept>
+
+#include <nlohmann/json.hpp>
+
+namespace b200 {
+
+using json = nlohmann::ordered_json;
+constexpr double mec2 = 511.0;  // src/constants.h:30
+
+#define B200_CALL(expr)                                                              \
+  do {                                                                               \
+    if ((expr) != 0) {                                                               \
+      std::cerr << "xpic_b200: " << #expr << " failed: " << xb_last_error() << "\n"; \
+      return 1;                                                                      \
+    }                                                                                \
+  } while (0)
+
+// ---- Builder::parse_value (src/interfaces/builder.cpp:54-81) -----------------------------------
+static double parse_value(const json& value, const Geometry& g)
+{
+  if (!value.is_string()) return value.get<double>();
+  const std::string str = value.get<std::string>();
+  if (str == "geom_x" || str == "geom_nx") return g.geom_x;
+  if (str == "geom_y" || str == "geom_ny") return g.geom_y;
+  if (str == "geom_z" || str == "geom_nz") return g.geom_z;
+  auto ends = [&](const char* suffix) { return str.ends_with(suffix); };
+  if (ends(" [dx]")) return std::stod(str.substr(0, str.size() - 5)) * g.dx;
+  if (ends(" [dy]")) return std::stod(str.substr(0, str.size() - 5)) * g.dy;
+  if (ends(" [dz]")) return std::stod(str.substr(0, str.size() - 5)) * g.dz;
+  if (ends(" [dt]")) return std::stod(str.substr(0, str.size() - 5)) * g.dt;
+  if (ends(" [c/w_pe]") || ends(" [1/w_pe]")) return std::stod(str.substr(0, str.size() - 9));
+  throw std::runtime_error("Unknown string format to convert: " + str);
+}
+
+static int round_step(double s, double ds) { return static_cast<int>(std::round(s / ds)); }
+
+// ---- Table -------------------------------------------------------------------------------------
+Table::Table(const std::string& filename)
+{
+  std::filesystem::create_directories(std::filesystem::path(filename).parent_path());
+  file_.open(filename);
+}
+
+void Table::add(int w, std::string title, const std::string& formatted)
+{
+  titles_.push_back(std::format("{:<{}.{}s}", title, w, w));
+  values_.push_back(std::format("{:^{}.{}s}", formatted, w, w));
+}
+
+void Table::row(bool with_titles)
+{
+  auto write = [&](const std::vector<std::string>& c) {
+    for (size_t i = 0; i + 1 < c.size(); ++i) file_ << c[i] << "  ";
+    std::string last = c.back();
+    while (!last.empty() && last.back() == ' ') last.pop_back();
+    file_ << last << "\n";
+  };
+  if (!values_.empty()) {
+    if (with_titles) write(titles_);
+    write(values_);
+  }
+  titles_.clear();
+  values_.clear();
+}
+
+// ---- Particles ---------------------------------------------------------------------------------
+Particles::Particles(Simulation& simulation, const SortParameters& parameters, int32_t sid)
+  : parameters(parameters), simulation_(simulation), sid_(sid)
+{
+}
+
+int Particles::add_particle(const Point& point, bool* is_added)
+{
+  const Geometry& g = simulation_.geom;
+  const int vx = (int)std::floor(point.r[0] / g.dx), vy = (int)std::floor(point.r[1] / g.dy), vz = (int)std::floor(point.r[2] / g.dz);
+  if (vx < 0 || vx >= g.geom_nx || vy < 0 || vy >= g.geom_ny || vz < 0 || vz >= g.geom_nz) return 0;
+  pending_.push_back(point);
+  if (is_added) *is_added = true;
+  return 0;
+}
+
+int Particles::flush()
+{
+  if (pending_.empty()) return 0;
+  int64_t added = 0;
+  B200_CALL(xb_particles_append(simulation_.ctx, sid_, &pending_[0].r[0], nullptr, (int64_t)pending_.size(), &added));
+  pending_.clear();
+  return 0;
+}
+
+int64_t Particles::size()
+{
+  int64_t n = 0;
+  xb_particles_count(simulation_.ctx, sid_, &n);
+  return n;
+}
+
+int Particles::download(std::vector<Point>& out)
+{
+  out.resize((size_t)size());
+  int64_t n = 0;
+  B200_CALL(xb_particles_download(simulation_.ctx, sid_, out.empty() ? nullptr : &out[0].r[0], nullptr, (int64_t)out.size(), &n));
+  return 0;
+}
+
+double Particles::scalar(int which)
+{
+  double v = 0.0;
+  xb_scalar(simulation_.ctx, sid_, which, &v);
+  return v;
+}
+
+// ---- Simulation --------------------------------------------------------------------------------
+Simulation::~Simulation() { finalize(); }
+
+void Simulation::set_option(const std::string& key, const std::string& value)
+{
+  auto tol = [&](const std::string& prefix, int which) {
+    if (key == "-" + prefix + "ksp_rtol") { rtol_[which] = std::stod(value); return true; }
+    if (key == "-" + prefix + "ksp_atol") { atol_[which] = std::stod(value); return true; }
+    if (key == "-" + prefix + "ksp_max_it") { maxit_[which] = std::stoi(value); return true; }
+    return false;
+  };
+  if (tol("", 0) || tol("predict_", 0) || tol("correct_", 1)) return;
+  if (key == "-curl_sign") curl_sign_ = std::stoi(value);
+  else if (key == "-device") device_ = std::stoi(value);
+  else if (key == "-precond") precond_ = std::stoi(value);
+  else throw std::runtime_error("Unknown option " + key);
+}
+
+int Simulation::configure(const std::string& config_path)
+{
+  std::ifstream f(config_path);
+  if (!f) throw std::runtime_error("Cannot open configuration file " + config_path);
+  const json cfg = json::parse(f);
+  cfg.at("Simulation").get_to(scheme_name);
+  if (scheme_name == "ecsim") scheme = XB_ECSIM;
+  else if (scheme_name == "ecsimcorr") scheme = XB_ECSIMCORR;
+  else throw std::runtime_error("Unknown simulation is used: " + scheme_name + " (this build covers ecsim, ecsimcorr)");
+  if (cfg.contains("OutputDirectory")) cfg.at("OutputDirectory").get_to(out_dir);
+
+  const json& ge = cfg.at("Geometry");  // utils/world.cpp:14-34
+  geom.dx = ge.at("dx").get<double>();
+  geom.dy = ge.at("dy").get<double>();
+  geom.dz = ge.at("dz").get<double>();
+  geom.dt = ge.at("dt").get<double>();
+  geom.geom_x = parse_value(ge.at("x"), geom);
+  geom.geom_y = parse_value(ge.at("y"), geom);
+  geom.geom_z = parse_value(ge.at("z"), geom);
+  geom.geom_t = parse_value(ge.at("t"), geom);
+  geom.geom_nx = round_step(geom.geom_x, geom.dx);
+  geom.geom_ny = round_step(geom.geom_y, geom.dy);
+  geom.geom_nz = round_step(geom.geom_z, geom.dz);
+  geom.geom_nt = round_step(geom.geom_t, geom.dt);
+  geom.diagnose_period = std::max(1, round_step(parse_value(ge.at("diagnose_period"), geom), geom.dt));
+  for (const char* key : {"da_boundary_x", "da_boundary_y", "da_boundary_z"})
+    if (ge.contains(key) && ge.at(key).get<std::string>() != "DM_BOUNDARY_PERIODIC")
+      throw std::runtime_error(std::string(key) + ": only DM_BOUNDARY_PERIODIC is covered by this build");
+
+  if (cfg.contains("Particles"))  // src/interfaces/simulation.tpp:12-45
+    for (const json& info : cfg.at("Particles")) {
+      if (!info.contains("sort_name")) continue;
+      SortParameters p;
+      info.at("sort_name").get_to(p.sort_name);
+      info.at("Np").get_to(p.Np);
+      info.at("n").get_to(p.n);
+      info.at("q").get_to(p.q);
+      info.at("m").get_to(p.m);
+      if (info.contains("T")) p.Tx = p.Ty = p.Tz = info.at("T").get<double>();
+      else {
+        info.at("Tx").get_to(p.Tx);
+        info.at("Ty").get_to(p.Ty);
+        info.at("Tz").get_to(p.Tz);
+      }
+      sorts_.push_back(p);
+    }
+  if (cfg.contains("Presets"))  // commands/builders/command_builder.cpp:42-59
+    for (const json& info : cfg.at("Presets")) {
+      const std::string command = info.at("command").get<std::string>();
+      if (command != "SetParticles") throw std::runtime_error("Preset " + command + " is not covered by this build");
+      Preset pr;
+      info.at("particles").get_to(pr.particles);
+      pr.coordinate = info.at("coordinate").at("name").get<std::string>();
+      pr.momentum = info.at("momentum").at("name").get<std::string>();
+      if (info.at("momentum").contains("tov")) info.at("momentum").at("tov").get_to(pr.tov);
+      if (pr.coordinate != "CoordinateInBox" || info.at("coordinate").contains("min") || info.at("coordinate").contains("max"))
+        throw std::runtime_error("SetParticles: only the whole-box CoordinateInBox generator is covered by this build");
+      if (pr.momentum != "MaxwellianMomentum") throw std::runtime_error("SetParticles: only MaxwellianMomentum is covered by this build");
+      presets_.push_back(pr);
+    }
+  return 0;
+}
+
+Particles& Simulation::get_named_particles(const std::string& name)
+{
+  for (auto& s : particles_)
+    if (s->parameters.sort_name == name) return *s;
+  throw std::runtime_error("No particles with name " + name);  // src/interfaces/simulation.cpp:145-155
+}
+
+int Simulation::get_named_vector(const std::string& name, std::vector<double>& out)
+{
+  static const std::vector<std::pair<std::string, int>> names = {{"E", XB_E}, {"B", XB_B}, {"B0", XB_B0}, {"Ep", XB_EP}, {"Ec", XB_EC},
+                                                                 {"currI", XB_CURRI}, {"currJe", XB_CURRJE}};
+  for (auto& [n, id] : names)
+    if (n == name) {
+      out.resize((size_t)3 * geom.geom_nx * geom.geom_ny * geom.geom_nz);
+      B200_CALL(xb_field_download(ctx, id, 0, out.data()));
+      return 0;
+    }
+  throw std::runtime_error("Unknown vector name " + name);
+}
+
+int Simulation::initialize()
+{
+  xb_grid g{};
+  g.n[0] = geom.geom_nx; g.n[1] = geom.geom_ny; g.n[2] = geom.geom_nz;
+  g.d[0] = geom.dx; g.d[1] = geom.dy; g.d[2] = geom.dz;
+  g.dt = geom.dt;
+  g.curl_sign = curl_sign_;
+  g.device = device_;
+  g.rank = 0;
+  g.nranks = 1;
+  g.track_ids = 0;
+  B200_CALL(xb_create(&g, nullptr, &ctx));
+  for (int w = 0; w < 2; ++w) B200_CALL(xb_solver_set(ctx, w, rtol_[w], atol_[w], maxit_[w], 30, precond_));
+
+  const int64_t ncells = (int64_t)geom.geom_nx * geom.geom_ny * geom.geom_nz;
+  for (const auto& p : sorts_) {
+    int32_t sid = 0;
+    B200_CALL(xb_species_add(ctx, p.q, p.m, p.n, p.Np, (int64_t)(1.5 * ncells * p.Np) + 4096, &sid));
+    particles_.push_back(std::make_shared<Particles>(*this, p, sid));
+  }
+
+  // presets: SetParticles::execute (src/commands/set_particles.cpp:19-43) with the generators of
+  // src/utils/particles_load.cpp:11-18,52-76 and the count of particles_builder.cpp:17,26
+  auto r01 = [&]() { return uni_(gen_); };
+  for (const auto& pr : presets_) {
+    Particles& sort = get_named_particles(pr.particles);
+    const SortParameters& sp = sort.parameters;
+    const double frac = sp.Np / (geom.dx * geom.dy * geom.dz);
+    const int64_t count = (int64_t)((geom.geom_x * geom.geom_y * geom.geom_z) * frac);
+    auto tm = [&](double T) { return std::sqrt(-2.0 * (T * sp.m / mec2) * std::log(r01())); };
+    for (int64_t i = 0; i < count; ++i) {
+      Point pt;
+      pt.r[0] = 0.0 + r01() * (geom.geom_x - 0.0);
+      pt.r[1] = 0.0 + r01() * (geom.geom_y - 0.0);
+      pt.r[2] = 0.0 + r01() * (geom.geom_z - 0.0);
+      const double T[3] = {sp.Tx, sp.Ty, sp.Tz}, p0[3] = {sp.px, sp.py, sp.pz};
+      for (int c = 0; c < 3; ++c) {
+        const double sn = std::sin(2.0 * M_PI * r01());  // the sine factor is drawn first
+        pt.p[c] = p0[c] + sn * tm(T[c]);
+      }
+      if (pr.tov) {
+        const double den = std::sqrt(sp.m * sp.m + (pt.p[0] * pt.p[0] + pt.p[1] * pt.p[1] + pt.p[2] * pt.p[2]));
+        for (double& v : pt.p) v /= den;
+      }
+      sort.add_particle(pt);
+    }
+    if (sort.flush()) return 1;
+  }
+
+  energy_ = std::make_unique<Table>(out_dir + "/temporal/energy.txt");
+  energy_cons_ = std::make_unique<Table>(out_dir + "/temporal/energy_conservation.txt");
+  K_.assign(particles_.size(), 0.0);
+  K0_ = stdK_ = K_;
+  return diagnose_energy(start);
+}
+
+int Simulation::timestep_implementation(int /* t */)
+{
+  B200_CALL(xb_step(ctx, scheme));
+  return 0;
+}
+
+int Simulation::calculate()
+{
+  for (int t = start + 1; t <= geom.geom_nt; ++t) {
+    std::cout << std::format("Timestep = {:.4f} [1/w_pe] = {} [dt]", t * geom.dt, t) << "\n";
+    if (timestep_implementation(t)) return 1;
+    int its = 0, reason = 0;
+    double rn = 0;
+    xb_solver_info(ctx, XB_SOLVER_PREDICT, &its, &rn, &reason);
+    std::cout << std::format("  KSPSolve() has finished: reason {}, iterations {}, residual norm {:.3e}", reason, its, rn) << "\n";
+    if (diagnose_energy(t)) return 1;
+  }
+  std::cout << "Summary of Stages:\n";  // utils/sync_clock.cpp:85-91
+  const char* names[XB_STAGE_COUNT] = {"Clear sources", "First push", "Advance field", "Second push", "Correct fields", "Final update"};
+  for (int s = 0; s < XB_STAGE_COUNT; ++s) {
+    double sec = 0;
+    int64_t calls = 0;
+    xb_timing(ctx, s, &sec, &calls);
+    std::cout << std::format("  {:<16s} {:10.4e} [sec] over {} calls", names[s], sec, calls) << "\n";
+  }
+  return 0;
+}
+
+int Simulation::finalize()
+{
+  if (energy_) energy_->flush();
+  if (energy_cons_) energy_cons_->flush();
+  if (ctx) {
+    xb_destroy(ctx);
+    ctx = nullptr;
+  }
+  return 0;
+}
+
+// Energy::diagnose (src/diagnostics/energy.cpp:20-180) + ecsimcorr::Energy (ecsimcorr/simulation.cpp:169-197)
+int Simulation::diagnose_energy(int t)
+{
+  auto field = [&](const char* name, double& w, double& sd) {
+    std::vector<double> f;
+    if (get_named_vector(name, f)) return 1;
+    double n2 = 0, mean[3] = {0, 0, 0};
+    for (size_t i = 0; i < f.size(); ++i) {
+      n2 += f[i] * f[i];
+      mean[i % 3] += f[i];
+    }
+    w = 0.5 * n2;  // energy.cpp:46-50 (the norm is squared again there)
+    const double g3 = (double)geom.geom_nx * geom.geom_ny * geom.geom_nz;
+    sd = std::sqrt((w - 0.5 * (mean[0] * mean[0] + mean[1] * mean[1] + mean[2] * mean[2]) / g3) / g3);
+    return 0;
+  };
+  auto kinetic = [&]() {
+    for (size_t i = 0; i < particles_.size(); ++i) {
+      double mo[5];
+      B200_CALL(xb_particle_moments(ctx, (int32_t)i, mo));
+      const SortParameters& sp = particles_[i]->parameters;
+      const double fr = 0.5 * sp.m * (sp.n / (double)sp.Np);
+      K_[i] = fr * mo[3];
+      const double s = mo[3] - (mo[0] * mo[0] + mo[1] * mo[1] + mo[2] * mo[2]) / mo[4];
+      stdK_[i] = mo[4] > 0 ? fr * std::sqrt(std::abs(s) / mo[4]) : 0.0;
+    }
+    return 0;
+  };
+  if (t == 0) {
+    if (field("E", E_, stdE_) || field("B", B_, stdB_) || kinetic()) return 1;
+  }
+  E0_ = E_;
+  B0_ = B_;
+  K0_ = K_;
+  if (field("E", E_, stdE_) || field("B", B_, stdB_) || kinetic()) return 1;
+
+  auto num = [](double v) { return std::format("{: .6e}", v); };
+  energy_->add(6, "Time", std::format("{:d}", t));
+  energy_->add(13, "wE", num(E_));
+  energy_->add(13, "wB", num(B_));
+  for (size_t i = 0; i < particles_.size(); ++i) energy_->add(13, "wK_" + particles_[i]->parameters.sort_name, num(K_[i]));
+  energy_->add(13, "sE", num(stdE_));
+  energy_->add(13, "sB", num(stdB_));
+  for (size_t i = 0; i < particles_.size(); ++i) energy_->add(13, "sK_" + particles_[i]->parameters.sort_name, num(stdK_[i]));
+  energy_->row(t == 0);
+
+  const double dE = E_ - E0_, dB = B_ - B0_;
+  double dK = 0.0;
+  energy_cons_->add(6, "Time", std::format("{:d}", t));
+  energy_cons_->add(13, "dE", num(dE));
+  energy_cons_->add(13, "dB", num(dB));
+  for (size_t i = 0; i < particles_.size(); ++i) {
+    const std::string& name = particles_[i]->parameters.sort_name;
+    energy_cons_->add(13, "dK_" + name, num(K_[i] - K0_[i]));
+    dK += K_[i] - K0_[i];
+    if (scheme == XB_ECSIMCORR) {
+      Particles& p = *particles_[i];
+      energy_cons_->add(13, "CWD_" + name, num(p.scalar(XB_LAMBDA_DK)));
+      energy_cons_->add(13, "PWD_" + name, num(p.scalar(XB_PRED_DK) - geom.dt * p.scalar(XB_PRED_W)));
+      energy_cons_->add(13, "LdK_" + name, num(p.scalar(XB_CORR_DK) - geom.dt * p.scalar(XB_CORR_W)));
+    }
+  }
+  energy_cons_->add(13, "dE+dB+dK", num(dE + dB + dK));
+  if (scheme == XB_ECSIMCORR) {
+    double corr_w = 0.0;
+    for (auto& p : particles_) corr_w += p->scalar(XB_CORR_W);
+    energy_cons_->add(13, "WD", num(dK - geom.dt * corr_w));
+  }
+  energy_cons_->row(t == 0);
+  if (t % geom.diagnose_period == 0) {
+    energy_->flush();
+    energy_cons_->flush();
+  }
+  return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,123 @@
+// xpic_host.h -- C++ host side above the C ABI, mirroring the interface of the reference's
+// ecsim::Simulation / ecsimcorr::Simulation and interfaces::Particles for this path:
+// same member names, same life cycle (initialize / calculate / finalize), same config.json
+// schema, same temporal/*.txt output (src/interfaces/simulation.h:21-72,
+// src/interfaces/particles.h:11-78, src/diagnostics/energy.cpp, table_diagnostic.h:17-37).
+// Errors: every method returns 0 on success (PetscErrorCode convention); configuration errors
+// throw std::runtime_error like the reference's builders (src/main.cpp:19-35).
+#pragma once
+#include <cstdint>
+#include <fstream>
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/xpic_b200.h"
+
+namespace b200 {
+
+struct Point {  // src/interfaces/point.h:7-35
+  double r[3];
+  double p[3];
+};
+
+struct SortParameters {  // src/interfaces/sort_parameters.h:7-19
+  std::string sort_name;
+  int Np = 0;
+  double n = 0, q = 0, m = 0;
+  double px = 0, py = 0, pz = 0;
+  double Tx = 0, Ty = 0, Tz = 0;
+};
+
+struct Geometry {  // globals of src/constants.h:10-28, set by World::set_geometry (utils/world.cpp:64-85)
+  double dx = 0, dy = 0, dz = 0, dt = 0;
+  double geom_x = 0, geom_y = 0, geom_z = 0, geom_t = 0;
+  int geom_nx = 0, geom_ny = 0, geom_nz = 0, geom_nt = 0;
+  int diagnose_period = 1;
+};
+
+class Simulation;
+
+class Particles {  // interfaces::Particles + ecsim/ecsimcorr::Particles
+public:
+  Particles(Simulation& simulation, const SortParameters& parameters, int32_t sid);
+  const SortParameters parameters;
+
+  /// src/interfaces/particles.cpp:47-57; points are staged on the host and sent by flush()
+  int add_particle(const Point& point, bool* is_added = nullptr);
+  int flush();
+  /// host mirror of `storage` (cell-major order), refreshed on demand
+  int download(std::vector<Point>& out);
+  int64_t size();
+
+  // ecsimcorr::Particles scalars (src/impls/ecsimcorr/particles.h:33-38)
+  double scalar(int which);
+
+private:
+  Simulation& simulation_;
+  int32_t sid_;
+  std::vector<Point> pending_;
+};
+
+/// table_diagnostic.h:17-37 / .cpp:43-59: fixed-width text tables
+class Table {
+public:
+  explicit Table(const std::string& filename);
+  void add(int w, std::string title, const std::string& formatted);
+  void row(bool with_titles);
+  void flush() { file_.flush(); }
+
+private:
+  std::ofstream file_;
+  std::vector<std::string> titles_, values_;
+};
+
+class Simulation {
+public:
+  Simulation() = default;
+  ~Simulation();
+
+  /// reads the reference's config.json schema
+  int configure(const std::string& config_path);
+  /// options the reference takes from PETSc's database: -ksp_rtol/-ksp_atol/-ksp_max_it (ecsim),
+  /// -predict_ksp_*, -correct_ksp_* (ecsimcorr), plus -curl_sign, -device, -precond
+  void set_option(const std::string& key, const std::string& value);
+
+  int initialize();   // interfaces::Simulation::initialize (src/interfaces/simulation.cpp:16-73)
+  int calculate();    // :75-96
+  int finalize();     // :98-112
+  int timestep_implementation(int t);
+
+  /// host mirrors of the named vectors, natural [z][y][x][c] order ("E", "B", "B0", "Ep", "Ec", "currI", "currJe")
+  int get_named_vector(const std::string& name, std::vector<double>& out);
+  Particles& get_named_particles(const std::string& name);  // throws std::runtime_error if unknown
+
+  Geometry geom;
+  std::string scheme_name = "ecsim";
+  std::string out_dir = "results";
+  std::vector<std::shared_ptr<Particles>> particles_;
+  int start = 0;
+  xb_ctx* ctx = nullptr;
+  int32_t scheme = XB_ECSIM;
+
+private:
+  int diagnose_energy(int t);
+  struct Preset {
+    std::string particles, coordinate, momentum;
+    bool tov = false;
+  };
+  std::vector<SortParameters> sorts_;
+  std::vector<Preset> presets_;
+  std::unique_ptr<Table> energy_, energy_cons_;
+  double E_ = 0, B_ = 0, E0_ = 0, B0_ = 0;
+  std::vector<double> K_, K0_, stdK_;
+  double stdE_ = 0, stdB_ = 0;
+  std::mt19937 gen_;  // src/utils/random_generator.h:20-27, default seed
+  std::uniform_real_distribution<double> uni_{0.0, 1.0};
+  double rtol_[2] = {1e-7, 1e-7}, atol_[2] = {1e-7, 1e-7};
+  int maxit_[2] = {100, 100};
+  int curl_sign_ = +1, device_ = 0, precond_ = 6;
+};
+
+}  // namespace b200
