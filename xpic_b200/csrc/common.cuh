@@ -78,6 +78,7 @@ struct MigrateBuffers {  // multi-rank only (migrate.cu)
   double* send[2][7] = {{nullptr}};   // [0] to the rank below, [1] to the rank above; 6 SoA arrays + ids
   double* recv[2][7] = {{nullptr}};   // [0] from below, [1] from above
   double* ghost[2][6] = {{nullptr}};  // copies of the neighbours' boundary-plane particles
+  double* ghost_rec[2] = {nullptr, nullptr};  // their field records, SoA [12][ghost_cap]
   int32_t* ghost_bins[2] = {nullptr, nullptr};
   int32_t* recv_key[2] = {nullptr, nullptr};
   int64_t cap = 0, ghost_cap = 0;
@@ -93,6 +94,7 @@ struct Species {
   double* p[2][6] = {{nullptr}};  // x,y,z,vx,vy,vz
   uint64_t* id[2] = {nullptr, nullptr};
   int32_t* key = nullptr;        // bin of every particle (capacity)
+  double* rec = nullptr;         // field record of every particle, SoA [12][capacity] (deposit.cu)
   int32_t* bin_start = nullptr;  // nbins + 1, valid after sort
   double* currI = nullptr;       // per-sort currents (ghosted grid vectors)
   double* currJe = nullptr;

@@ -48,6 +48,8 @@ struct DepositArgs {
   int64_t stage_cell0;  // staging cell id of the first cell
   int zshift;
   double q, m, mpw;
+  double* rec;         // per-particle field record, SoA [12][rec_stride]: A_p alpha (9), I_p (3)
+  int64_t rec_stride;
 };
 
 __global__ void __launch_bounds__(DEP_WARPS * 32) k_cell_blocks(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage)
@@ -175,8 +177,11 @@ __global__ void __launch_bounds__(DEP_WARPS * 32) k_cell_blocks(Grid g, DepositA
 // 9 multiplies and 12 DMMAs instead of ~180 scalar instructions.
 // ---------------------------------------------------------------------------------------------
 constexpr int MMA_CHUNK = 32;
-constexpr int MREC = 37;  // odd stride: the 16 lanes that write records hit 16 different banks
-constexpr int MMA_SMEM_PER_CELL = BLOCK_ALL + MMA_CHUNK * MREC;
+constexpr int SREC = 25;  // shape record: 24 weights, odd stride (conflict-free stores and loads)
+constexpr int FREC = 13;  // field record: 9 A_p alpha + 3 I_p, odd stride
+// per cell: the 12 x 12 x 9 block + currents, 32 shape records, and two buffers of asynchronously
+// staged inputs of the next chunk (x, y, z and the 12 field values of each particle)
+constexpr int MMA_SMEM_PER_CELL = BLOCK_ALL + MMA_CHUNK * SREC + 2 * MMA_CHUNK * FREC + 2 * 3 * MMA_CHUNK;
 constexpr int MMA_WARPS = 2 * CELL_GROUP;  // two warps per cell
 static_assert(CELL_GROUP == 4, "pair_barrier enumerates four cell slots");
 
@@ -199,21 +204,40 @@ __device__ __forceinline__ void pair_barrier(int slot)
 // Per-particle record, prepared once per particle and read by the MMA lanes:
 //   r[0..23]  = s_c(t): E-like CIC weights of the 8 corners, 3 components   (written by warp half 0)
 //   r[24..32] = A_p * alpha[c1][c2],  r[33..35] = I_p                      (written by warp half 1)
-__device__ __forceinline__ void prepare_shapes(const Grid& g, const DepositArgs& a, int32_t i, double* __restrict__ r)
+// Shape part of the record: E-like CIC weights of the 8 corners (src/impls/ecsim/particles.cpp:76-105,
+// 129-131).  Warp half 0 writes components X and Y, half 1 component Z.
+template <int HALF>
+__device__ __forceinline__ void prepare_shapes(const Grid& g, int zshift, double px, double py, double pz, double* __restrict__ r)
 {
   Weights w;
-  make_weights(g, a.p[0][i], a.p[1][i], a.p[2][i], a.zshift, w);
+  make_weights(g, px, py, pz, zshift, w);
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
     const int i1 = t & 1, j1 = (t >> 1) & 1, k1 = t >> 2;
-    r[0 + t] = w.wn[2][k1] * w.wn[1][j1] * w.ws[0][i1];
-    r[8 + t] = w.wn[2][k1] * w.ws[1][j1] * w.wn[0][i1];
-    r[16 + t] = w.ws[2][k1] * w.wn[1][j1] * w.wn[0][i1];
+    if (HALF == 0) {
+      r[0 + t] = w.wn[2][k1] * w.wn[1][j1] * w.ws[0][i1];
+      r[8 + t] = w.wn[2][k1] * w.ws[1][j1] * w.wn[0][i1];
+    }
+    else {
+      r[16 + t] = w.ws[2][k1] * w.wn[1][j1] * w.wn[0][i1];
+    }
   }
 }
 
-__device__ __forceinline__ void prepare_fields(const Grid& g, const DepositArgs& a, const double* __restrict__ B, int32_t i, double* __restrict__ r)
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
 {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Field part of the record, one thread per particle at full occupancy (it needs ~100 registers and
+// two dependent global loads, which is what starved the tensor-core kernel when it was inlined):
+// gather B^n, beta, A_p alpha[3][3] and I_p (src/impls/ecsim/particles.cpp:107-115).
+__global__ void __launch_bounds__(256) k_particle_fields(Grid g, DepositArgs a, int64_t n, const double* __restrict__ B)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
   const double v[3] = {a.p[3][i], a.p[4][i], a.p[5][i]};
   Weights w;
   make_weights(g, a.p[0][i], a.p[1][i], a.p[2][i], a.zshift, w);
@@ -227,22 +251,21 @@ __device__ __forceinline__ void prepare_fields(const Grid& g, const DepositArgs&
   double vxb[3];
   cross3(v, b, vxb);
   const double vb = dot3(v, b), b2 = dot3(b, b);
-  // one division for both 1 / (1 + b^2) factors (the reference divides twice,
-  // src/impls/ecsim/particles.cpp:108-109; the results differ in the last bit at most)
-  const double inv = 1.0 / (1. + b2);
-  const double ci = a.q * a.mpw * inv;
+  double* r = a.rec + i;
+  const int64_t st = a.rec_stride;
+  const double ci = a.q * a.mpw / (1. + b2);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) r[33 + c] = ci * (v[c] + vxb[c] + vb * b[c]);
-  const double Ap = (0.5 * g.dt * g.dt * a.mpw * a.q * a.q / a.m) * inv;
-  r[24 + 0] = Ap * (1.0 + b[0] * b[0]);
-  r[24 + 1] = Ap * (+b[2] + b[0] * b[1]);
-  r[24 + 2] = Ap * (-b[1] + b[0] * b[2]);
-  r[24 + 3] = Ap * (-b[2] + b[1] * b[0]);
-  r[24 + 4] = Ap * (1.0 + b[1] * b[1]);
-  r[24 + 5] = Ap * (+b[0] + b[1] * b[2]);
-  r[24 + 6] = Ap * (+b[1] + b[2] * b[0]);
-  r[24 + 7] = Ap * (-b[0] + b[2] * b[1]);
-  r[24 + 8] = Ap * (1.0 + b[2] * b[2]);
+  for (int c = 0; c < 3; ++c) r[(9 + c) * st] = ci * (v[c] + vxb[c] + vb * b[c]);
+  const double Ap = 0.5 * g.dt * g.dt * a.mpw * a.q * a.q / a.m / (1 + b2);
+  r[0 * st] = Ap * (1.0 + b[0] * b[0]);
+  r[1 * st] = Ap * (+b[2] + b[0] * b[1]);
+  r[2 * st] = Ap * (-b[1] + b[0] * b[2]);
+  r[3 * st] = Ap * (-b[2] + b[1] * b[0]);
+  r[4 * st] = Ap * (1.0 + b[1] * b[1]);
+  r[5 * st] = Ap * (+b[0] + b[1] * b[2]);
+  r[6 * st] = Ap * (+b[1] + b[2] * b[0]);
+  r[7 * st] = Ap * (-b[0] + b[2] * b[1]);
+  r[8 * st] = Ap * (1.0 + b[2] * b[2]);
 }
 
 // The 12 DMMAs of a particle group are split between the two warps of a cell so that their
@@ -277,23 +300,26 @@ __host__ __device__ constexpr int op_variant(int half, int j, int oct)
 constexpr int NACC = 18;
 static_assert(op_base(0, 5) + op_nvar(0, 5) == NACC && op_base(1, 5) + op_nvar(1, 5) == NACC, "18 accumulator pairs per half");
 
-// all groups of one octant segment: cnt particles whose records start at r0
+// all groups of one octant segment: cnt particles whose records start at rs0 (shapes) / rf0 (fields)
 template <int HALF, int OCT>
-__device__ __forceinline__ void octant_segment(const double* __restrict__ r0, int cnt, int gq, int q, double (&acc)[NACC][2])
+__device__ __forceinline__ void octant_segment(const double* __restrict__ rs0, const double* __restrict__ rf0, int cnt, int gq, int q,
+                                               double (&acc)[NACC][2])
 {
   for (int gs = 0; gs < cnt; gs += 4) {
     const bool valid = gs + q < cnt;
-    const double* r = r0 + min(gs + q, cnt - 1) * MREC;  // clamp: operands of padded lanes stay finite
+    const int pi = min(gs + q, cnt - 1);  // clamp: operands of padded lanes stay finite
+    const double* rs = rs0 + pi * SREC;
+    const double* rf = rf0 + pi * FREC;
     double s[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) s[c] = r[c * 8 + gq];
+    for (int c = 0; c < 3; ++c) s[c] = rs[c * 8 + gq];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       constexpr int dummy = 0;
       (void)dummy;
       const int c1 = op_row(HALF, j), c2 = op_col(HALF, j);
       const double av = valid ? s[c1] : 0.0;
-      const double bv = c2 < 3 ? r[24 + c1 * 3 + c2] * s[c2] : (gq == 0 ? r[33 + c1] : 0.0);
+      const double bv = c2 < 3 ? rf[c1 * 3 + c2] * s[c2] : (gq == 0 ? rf[9 + c1] : 0.0);
       const int v = op_base(HALF, j) + op_variant(HALF, j, OCT);
       dmma(acc[v][0], acc[v][1], av, bv);
     }
@@ -301,9 +327,12 @@ __device__ __forceinline__ void octant_segment(const double* __restrict__ r0, in
 }
 
 template <int HALF>
-__device__ __forceinline__ void cell_half(const Grid& g, const DepositArgs& a, const double* __restrict__ B, double* __restrict__ block,
-                                          double* __restrict__ rec, int slot, int lane, int64_t bin0)
+__device__ __forceinline__ void cell_half(const Grid& g, const DepositArgs& a, double* __restrict__ block, double* __restrict__ cellmem, int slot,
+                                          int lane, int64_t bin0)
 {
+  double* srec = cellmem;                              // [32][SREC]
+  double* frec = srec + MMA_CHUNK * SREC;              // [2][32][FREC]
+  double* xyz = frec + 2 * MMA_CHUNK * FREC;           // [2][3][32]
   const int gq = lane >> 2, q = lane & 3;
   const int32_t bs = lane < 9 ? a.bin_start[bin0 + lane] : 0;  // bin boundaries of the 8 octants
   const int32_t p0 = __shfl_sync(0xffffffffu, bs, 0), p1 = __shfl_sync(0xffffffffu, bs, 8);
@@ -313,15 +342,34 @@ __device__ __forceinline__ void cell_half(const Grid& g, const DepositArgs& a, c
 #pragma unroll
   for (int v = 0; v < NACC; ++v) acc[v][0] = acc[v][1] = 0.0;
 
-  for (int32_t base = p0; base < p1; base += MMA_CHUNK) {
+  // asynchronous staging of a chunk's inputs: half 0 fetches x, y, z, half 1 the 12 field values
+  auto stage_chunk = [&](int32_t base, int buf) {
     const int n = min(MMA_CHUNK, p1 - base);
-    if (lane < n) {  // half 0 prepares the shape part of the 32 records, half 1 the field part
-      if (HALF == 0)
-        prepare_shapes(g, a, base + lane, rec + lane * MREC);
-      else
-        prepare_fields(g, a, B, base + lane, rec + lane * MREC);
+    if (lane < n) {
+      const int32_t i = base + lane;
+      if (HALF == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cp_async8(xyz + (buf * 3 + c) * MMA_CHUNK + lane, a.p[c] + i);
+      }
+      else {
+        double* dst = frec + (buf * MMA_CHUNK + lane) * FREC;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) cp_async8(dst + j, a.rec + i + j * a.rec_stride);
+      }
     }
-    pair_barrier(slot);
+  };
+  if (p0 < p1) stage_chunk(p0, 0);
+  int buf = 0;
+  for (int32_t base = p0; base < p1; base += MMA_CHUNK, buf ^= 1) {
+    const int n = min(MMA_CHUNK, p1 - base);
+    cp_async_wait_all();
+    pair_barrier(slot);  // both halves' copies of this chunk have landed; srec is free again
+    if (lane < n) {
+      const double* xs = xyz + buf * 3 * MMA_CHUNK;
+      prepare_shapes<HALF>(g, a.zshift, xs[lane], xs[MMA_CHUNK + lane], xs[2 * MMA_CHUNK + lane], srec + lane * SREC);
+    }
+    if (base + MMA_CHUNK < p1) stage_chunk(base + MMA_CHUNK, buf ^ 1);  // overlaps with the MMA phase below
+    pair_barrier(slot);  // shape records of both halves are complete
     int32_t pos = base;
     const int32_t cend = base + n;
     while (pos < cend) {
@@ -330,21 +378,21 @@ __device__ __forceinline__ void cell_half(const Grid& g, const DepositArgs& a, c
         oend = __shfl_sync(0xffffffffu, bs, oct + 1);
       }
       const int32_t seg_end = min(oend, cend);
-      const double* r0 = rec + (pos - base) * MREC;
+      const double* rs0 = srec + (pos - base) * SREC;
+      const double* rf0 = frec + (buf * MMA_CHUNK + (pos - base)) * FREC;
       const int cnt = seg_end - pos;
       switch (oct) {
-        case 0: octant_segment<HALF, 0>(r0, cnt, gq, q, acc); break;
-        case 1: octant_segment<HALF, 1>(r0, cnt, gq, q, acc); break;
-        case 2: octant_segment<HALF, 2>(r0, cnt, gq, q, acc); break;
-        case 3: octant_segment<HALF, 3>(r0, cnt, gq, q, acc); break;
-        case 4: octant_segment<HALF, 4>(r0, cnt, gq, q, acc); break;
-        case 5: octant_segment<HALF, 5>(r0, cnt, gq, q, acc); break;
-        case 6: octant_segment<HALF, 6>(r0, cnt, gq, q, acc); break;
-        default: octant_segment<HALF, 7>(r0, cnt, gq, q, acc); break;
+        case 0: octant_segment<HALF, 0>(rs0, rf0, cnt, gq, q, acc); break;
+        case 1: octant_segment<HALF, 1>(rs0, rf0, cnt, gq, q, acc); break;
+        case 2: octant_segment<HALF, 2>(rs0, rf0, cnt, gq, q, acc); break;
+        case 3: octant_segment<HALF, 3>(rs0, rf0, cnt, gq, q, acc); break;
+        case 4: octant_segment<HALF, 4>(rs0, rf0, cnt, gq, q, acc); break;
+        case 5: octant_segment<HALF, 5>(rs0, rf0, cnt, gq, q, acc); break;
+        case 6: octant_segment<HALF, 6>(rs0, rf0, cnt, gq, q, acc); break;
+        default: octant_segment<HALF, 7>(rs0, rf0, cnt, gq, q, acc); break;
       }
       pos = seg_end;
     }
-    pair_barrier(slot);  // both warps are done with the records before the next chunk overwrites them
   }
 
   // one fold per cell: variants of a slot may land on the same entry, so they go in separate passes
@@ -378,42 +426,18 @@ __global__ void __launch_bounds__(MMA_WARPS * 32, 2) k_cell_blocks_mma(Grid g, D
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = wid >> 1, half = wid & 1;
   double* block = smem + (size_t)slot * MMA_SMEM_PER_CELL;
-  double* rec = block + BLOCK_ALL;
+  double* cellmem = block + BLOCK_ALL;
   const int64_t cell_local = (int64_t)blockIdx.x * CELL_GROUP + slot;
 
-  {
-    // The four cells of the CTA own one contiguous particle range: pull its six SoA segments into
-    // L1 now (one prefetch per 128-byte line), so the record preparation below does not expose a
-    // DRAM round trip per chunk; also nudge the range of a CTA that will run later into L2.
-    const int64_t c0 = (int64_t)blockIdx.x * CELL_GROUP;
-    const int64_t c1 = min(c0 + CELL_GROUP, a.ncells);
-    const int32_t q0 = a.bin_start[(a.bin_cell0 + c0) << 3], q1 = a.bin_start[(a.bin_cell0 + c1) << 3];
-    const int nlines = (int)((((int64_t)q1 * 8 + 127) >> 7) - (((int64_t)q0 * 8) >> 7));
-    for (int t = threadIdx.x; t < 6 * nlines; t += MMA_WARPS * 32) {
-      const int arr = t / nlines, ln = t % nlines;
-      const char* p = reinterpret_cast<const char*>(a.p[arr]) + ((((int64_t)q0 * 8) >> 7) << 7) + (int64_t)ln * 128;
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-    }
-    const int64_t far = c0 + (int64_t)CELL_GROUP * 2 * 148 * 2;  // a CTA roughly two waves ahead
-    if (far + CELL_GROUP <= a.ncells) {
-      const int32_t f0 = a.bin_start[(a.bin_cell0 + far) << 3], f1 = a.bin_start[(a.bin_cell0 + far + CELL_GROUP) << 3];
-      const int flines = (int)((((int64_t)f1 * 8 + 127) >> 7) - (((int64_t)f0 * 8) >> 7));
-      for (int t = threadIdx.x; t < 6 * flines; t += MMA_WARPS * 32) {
-        const int arr = t / flines, ln = t % flines;
-        const char* p = reinterpret_cast<const char*>(a.p[arr]) + ((((int64_t)f0 * 8) >> 7) << 7) + (int64_t)ln * 128;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-      }
-    }
-  }
   for (int e = half * 32 + lane; e < BLOCK_ALL; e += 64) block[e] = 0.0;
   pair_barrier(slot);
 
   if (cell_local < a.ncells) {
     const int64_t bin0 = (a.bin_cell0 + cell_local) << 3;
     if (half == 0)
-      cell_half<0>(g, a, B, block, rec, slot, lane, bin0);
+      cell_half<0>(g, a, block, cellmem, slot, lane, bin0);
     else
-      cell_half<1>(g, a, B, block, rec, slot, lane, bin0);
+      cell_half<1>(g, a, block, cellmem, slot, lane, bin0);
   }
   __syncthreads();
   // coalesced write-out of the CTA's four blocks: stage[group][entry][cell % 4] (per-pair strided
@@ -547,7 +571,7 @@ int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage);  // migrate.cu (m
 
 // cell blocks of `ncells` consecutive cells (bin space) into the staging area
 int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* bin_start, int64_t bin_cell0, int64_t ncells, int64_t stage_cell0,
-                  int zshift)
+                  int zshift, double* rec, int64_t rec_stride, int64_t nparticles)
 {
   static bool attr_set = false;
   const bool use_mma = c->deposit_variant != 1;
@@ -567,10 +591,14 @@ int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* 
   a.q = s.q;
   a.m = s.m;
   a.mpw = s.n / (double)s.Np;
+  a.rec = rec;
+  a.rec_stride = rec_stride;
   if ((a.stage_cell0 % CELL_GROUP) != 0) XB_FAIL("deposit: plane size must be a multiple of the staging group in multi-rank runs");
   const int groups = (int)((a.ncells + CELL_GROUP - 1) / CELL_GROUP);
-  if (use_mma)
+  if (use_mma) {
+    if (nparticles > 0) XB_LAUNCH(c, k_particle_fields, (int)((nparticles + 255) / 256), 256, 0, c->g, a, nparticles, c->B);
     XB_LAUNCH(c, k_cell_blocks_mma, groups, MMA_WARPS * 32, smem, c->g, a, c->B, c->stage);
+  }
   else
     XB_LAUNCH(c, k_cell_blocks, groups, DEP_WARPS * 32, smem, c->g, a, c->B, c->stage);
   return 0;
@@ -585,7 +613,7 @@ int deposit_moments(xb_ctx* c)
   for (auto& s : c->sorts) {
     if (!s.sorted) XB_FAIL("deposit: particles are not sorted");
     // bin plane 1 = first owned plane; staging plane 0 is the low ghost plane in multi-rank runs
-    XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane, g.ncl, single ? 0 : g.plane, 0));
+    XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane, g.ncl, single ? 0 : g.plane, 0, s.rec, s.capacity, s.count));
     if (!single) XB_CHECK(deposit_ghost_cells(c, s, c->stage));
     GatherArgs ga{c->stage, single ? 1 : 0};
     const int acc = first ? 0 : 1;
