@@ -18,3 +18,6 @@ sim.solver_set(0, 1e-7, 1e-7, 100, 30, p)
 sim.solver_set(1, 1e-7, 1e-7, 100, 30, p)
 ms = sim.run_steps(steps)
 print("steps", steps, "ms/step", ms / steps, "its", sim.solver_info(0)[0], {k: round(1e3 * v[0] / max(v[1], 1), 3) for k, v in sim.timing().items()})
+if os.environ.get("XPIC_KERNEL_BENCH"):
+    for what, name in ((0, "sort (no move)"), (1, "deposit (fields + cell blocks + gather)"), (2, "second push"), (3, "solve")):
+        print(f"kernel_bench {name}: {sim.kernel_bench(what, 5):.3f} ms")

@@ -231,41 +231,52 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Field part of the record, one thread per particle at full occupancy (it needs ~100 registers and
-// two dependent global loads, which is what starved the tensor-core kernel when it was inlined):
+// Field part of the record in its own kernel at full occupancy (inlined in the tensor-core kernel it
+// needs ~100 registers and two dependent global loads, which starved that kernel); one CTA per 4 cells,
+// B staged in a shared-memory tile:
 // gather B^n, beta, A_p alpha[3][3] and I_p (src/impls/ecsim/particles.cpp:107-115).
-__global__ void __launch_bounds__(256) k_particle_fields(Grid g, DepositArgs a, int64_t n, const double* __restrict__ B)
+constexpr int PF_THREADS = 128;
+
+__global__ void __launch_bounds__(PF_THREADS) k_particle_fields(Grid g, DepositArgs a, const double* __restrict__ B, int groups_x, int zl_off)
 {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double v[3] = {a.p[3][i], a.p[4][i], a.p[5][i]};
-  Weights w;
-  make_weights(g, a.p[0][i], a.p[1][i], a.p[2][i], a.zshift, w);
-  NodeOffsets off;
-  make_offsets(g, w, off);
-  double Bp[3], b[3];
-  gather_B(g, B, w, off, Bp);
+  __shared__ double Bt[FIELD_TILE];
+  const int gx = blockIdx.x % groups_x, row = blockIdx.x / groups_x;  // row = plane index * ny + cy within this launch
+  const int cy = row % g.ny, pl = row / g.ny;
+  const int zl = pl + zl_off;
+  const int cx0 = gx * TILE_CELLS, ncell = min(TILE_CELLS, g.nx - cx0);
+  load_field_tile(g, B, cx0, cy, zl, Bt, threadIdx.x, PF_THREADS);
+  const int64_t cell0 = a.bin_cell0 + ((int64_t)pl * g.ny + cy) * g.nx + cx0;
+  const int32_t p0 = a.bin_start[cell0 << 3], p1 = a.bin_start[(cell0 + ncell) << 3];
+  __syncthreads();
   const double f = (0.5 * g.dt) * a.q / a.m;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) b[c] = Bp[c] * f;
-  double vxb[3];
-  cross3(v, b, vxb);
-  const double vb = dot3(v, b), b2 = dot3(b, b);
-  double* r = a.rec + i;
   const int64_t st = a.rec_stride;
-  const double ci = a.q * a.mpw / (1. + b2);
+  for (int32_t i = p0 + threadIdx.x; i < p1; i += PF_THREADS) {
+    const double v[3] = {a.p[3][i], a.p[4][i], a.p[5][i]};
+    Weights w;
+    make_weights(g, a.p[0][i], a.p[1][i], a.p[2][i], a.zshift, w);
+    const TileIndex t = tile_index(w, cx0, cy, zl);
+    double Bp[3], b[3];
+    gather_B_tile(Bt, w, t, Bp);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) r[(9 + c) * st] = ci * (v[c] + vxb[c] + vb * b[c]);
-  const double Ap = 0.5 * g.dt * g.dt * a.mpw * a.q * a.q / a.m / (1 + b2);
-  r[0 * st] = Ap * (1.0 + b[0] * b[0]);
-  r[1 * st] = Ap * (+b[2] + b[0] * b[1]);
-  r[2 * st] = Ap * (-b[1] + b[0] * b[2]);
-  r[3 * st] = Ap * (-b[2] + b[1] * b[0]);
-  r[4 * st] = Ap * (1.0 + b[1] * b[1]);
-  r[5 * st] = Ap * (+b[0] + b[1] * b[2]);
-  r[6 * st] = Ap * (+b[1] + b[2] * b[0]);
-  r[7 * st] = Ap * (-b[0] + b[2] * b[1]);
-  r[8 * st] = Ap * (1.0 + b[2] * b[2]);
+    for (int c = 0; c < 3; ++c) b[c] = Bp[c] * f;
+    double vxb[3];
+    cross3(v, b, vxb);
+    const double vb = dot3(v, b), b2 = dot3(b, b);
+    double* r = a.rec + i;
+    const double ci = a.q * a.mpw / (1. + b2);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[(9 + c) * st] = ci * (v[c] + vxb[c] + vb * b[c]);
+    const double Ap = 0.5 * g.dt * g.dt * a.mpw * a.q * a.q / a.m / (1 + b2);
+    r[0 * st] = Ap * (1.0 + b[0] * b[0]);
+    r[1 * st] = Ap * (+b[2] + b[0] * b[1]);
+    r[2 * st] = Ap * (-b[1] + b[0] * b[2]);
+    r[3 * st] = Ap * (-b[2] + b[1] * b[0]);
+    r[4 * st] = Ap * (1.0 + b[1] * b[1]);
+    r[5 * st] = Ap * (+b[0] + b[1] * b[2]);
+    r[6 * st] = Ap * (+b[1] + b[2] * b[0]);
+    r[7 * st] = Ap * (-b[0] + b[2] * b[1]);
+    r[8 * st] = Ap * (1.0 + b[2] * b[2]);
+  }
 }
 
 // The 12 DMMAs of a particle group are split between the two warps of a cell so that their
@@ -596,7 +607,14 @@ int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* 
   if ((a.stage_cell0 % CELL_GROUP) != 0) XB_FAIL("deposit: plane size must be a multiple of the staging group in multi-rank runs");
   const int groups = (int)((a.ncells + CELL_GROUP - 1) / CELL_GROUP);
   if (use_mma) {
-    if (nparticles > 0) XB_LAUNCH(c, k_particle_fields, (int)((nparticles + 255) / 256), 256, 0, c->g, a, nparticles, c->B);
+    if (nparticles > 0) {
+      // the cells of one launch are whole planes: owned planes (bin plane 1.. -> zl 0..) or one ghost plane
+      const Grid& g = c->g;
+      const int groups_x = (g.nx + TILE_CELLS - 1) / TILE_CELLS;
+      const int64_t planes = ncells / g.plane;
+      const int zl_off = bin_cell0 == g.plane ? 0 : (stage_cell0 == 0 ? -1 : g.nzl);
+      XB_LAUNCH(c, k_particle_fields, (int)(groups_x * g.ny * planes), PF_THREADS, 0, g, a, c->B, groups_x, zl_off);
+    }
     XB_LAUNCH(c, k_cell_blocks_mma, groups, MMA_WARPS * 32, smem, c->g, a, c->B, c->stage);
   }
   else

@@ -106,6 +106,76 @@ __device__ __forceinline__ void gather_B(const Grid& g, const double* __restrict
       }
 }
 
+// ---- gathers from a shared-memory field tile --------------------------------------------------
+// A CTA that owns TILE_CELLS x-consecutive cells stages the nodes its particles can touch:
+// x in [cx0 - 1, cx0 + TILE_CELLS], y in [cy - 1, cy + 1], z in [cz - 1, cz + 1], 3 components.
+constexpr int TILE_CELLS = 4;
+constexpr int TILE_NX = TILE_CELLS + 2;
+constexpr int FIELD_TILE = 3 * 3 * 3 * TILE_NX;  // [c][z][y][x]
+
+__device__ __forceinline__ void load_field_tile(const Grid& g, const double* __restrict__ F, int cx0, int cy, int zl, double* __restrict__ T, int tid,
+                                                int nthreads)
+{
+  for (int e = tid; e < FIELD_TILE; e += nthreads) {
+    const int x = e % TILE_NX, y = (e / TILE_NX) % 3, z = (e / (TILE_NX * 3)) % 3, c = e / (TILE_NX * 9);
+    T[e] = __ldg(&F[g.vidx(wrap1(cx0 - 1 + x, g.nx), wrap1(cy - 1 + y, g.ny), zl - 1 + z, c)]);
+  }
+}
+
+struct TileIndex {
+  int xn, xs, yn, ys, zn, zs;  // offsets of the particle's lower nodal / staggered node inside the tile
+};
+
+__device__ __forceinline__ TileIndex tile_index(const Weights& w, int cx0, int cy, int zl)
+{
+  TileIndex t;
+  t.xn = w.in[0] - (cx0 - 1);
+  t.xs = w.is[0] - (cx0 - 1);
+  t.yn = (w.in[1] - (cy - 1)) * TILE_NX;
+  t.ys = (w.is[1] - (cy - 1)) * TILE_NX;
+  t.zn = (w.in[2] - (zl - 1)) * (3 * TILE_NX);
+  t.zs = (w.is[2] - (zl - 1)) * (3 * TILE_NX);
+  return t;
+}
+
+__device__ __forceinline__ void gather_E_tile(const double* __restrict__ T, const Weights& w, const TileIndex& t, double* Ep)
+{
+  Ep[0] = Ep[1] = Ep[2] = 0.0;
+  constexpr int C = 9 * TILE_NX, Y = TILE_NX, Z = 3 * TILE_NX;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double sx = w.wn[2][k] * w.wn[1][j] * w.ws[0][i];
+        const double sy = w.wn[2][k] * w.ws[1][j] * w.wn[0][i];
+        const double sz = w.ws[2][k] * w.wn[1][j] * w.wn[0][i];
+        Ep[0] += T[0 * C + t.zn + k * Z + t.yn + j * Y + t.xs + i] * sx;
+        Ep[1] += T[1 * C + t.zn + k * Z + t.ys + j * Y + t.xn + i] * sy;
+        Ep[2] += T[2 * C + t.zs + k * Z + t.yn + j * Y + t.xn + i] * sz;
+      }
+}
+
+__device__ __forceinline__ void gather_B_tile(const double* __restrict__ T, const Weights& w, const TileIndex& t, double* Bp)
+{
+  Bp[0] = Bp[1] = Bp[2] = 0.0;
+  constexpr int C = 9 * TILE_NX, Y = TILE_NX, Z = 3 * TILE_NX;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double sx = w.ws[2][k] * w.ws[1][j] * w.wn[0][i];
+        const double sy = w.ws[2][k] * w.wn[1][j] * w.ws[0][i];
+        const double sz = w.wn[2][k] * w.ws[1][j] * w.ws[0][i];
+        Bp[0] += T[0 * C + t.zs + k * Z + t.ys + j * Y + t.xn + i] * sx;
+        Bp[1] += T[1 * C + t.zs + k * Z + t.yn + j * Y + t.xs + i] * sy;
+        Bp[2] += T[2 * C + t.zn + k * Z + t.ys + j * Y + t.xs + i] * sz;
+      }
+}
+
 // ---- binning ------------------------------------------------------------------------------------
 // periodic wrap of one coordinate, src/interfaces/point.cpp:18-26
 __device__ __forceinline__ double wrap_coord(double s, double L)

@@ -359,31 +359,49 @@ int particles_generate(xb_ctx* c, Species& s, int64_t total, const double* T, ui
 // ---------------------------------------------------------------------------------------------
 // second push (ecsim): gather E^{n+1/2}, B^n at the particle, Boris update of v
 // ---------------------------------------------------------------------------------------------
-__global__ void k_push_second(Grid g, int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                              double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz, const double* __restrict__ E,
-                              const double* __restrict__ B, double qm)
+// One CTA per group of 4 x-consecutive cells: the 54 nodes x 3 components of E and of B its particles
+// can touch are staged in shared memory once, so the 48 gathers per particle are shared-memory
+// reads and HBM sees only the particle stream (72 B / particle).
+constexpr int PUSH_THREADS = 128;
+
+__global__ void __launch_bounds__(PUSH_THREADS) k_push_second(Grid g, const int32_t* __restrict__ bin_start, const double* __restrict__ x,
+                                                              const double* __restrict__ y, const double* __restrict__ z, double* __restrict__ vx,
+                                                              double* __restrict__ vy, double* __restrict__ vz, const double* __restrict__ E,
+                                                              const double* __restrict__ B, double qm, int groups_x)
 {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Weights w;
-  make_weights(g, x[i], y[i], z[i], 0, w);
-  NodeOffsets off;
-  make_offsets(g, w, off);
-  double Ep[3], Bp[3];
-  gather_E(g, E, w, off, Ep);
-  gather_B(g, B, w, off, Bp);
-  double v[3] = {vx[i], vy[i], vz[i]};
-  boris_update_vEB(g.dt, qm, Ep, Bp, v);
-  vx[i] = v[0];
-  vy[i] = v[1];
-  vz[i] = v[2];
+  __shared__ double Et[FIELD_TILE], Bt[FIELD_TILE];
+  const int gx = blockIdx.x % groups_x, row = blockIdx.x / groups_x;  // row = zl * ny + cy
+  const int cy = row % g.ny, zl = row / g.ny;
+  const int cx0 = gx * TILE_CELLS, ncell = min(TILE_CELLS, g.nx - cx0);
+  load_field_tile(g, E, cx0, cy, zl, Et, threadIdx.x, PUSH_THREADS);
+  load_field_tile(g, B, cx0, cy, zl, Bt, threadIdx.x, PUSH_THREADS);
+  const int64_t cell0 = ((int64_t)(zl + 1) * g.ny + cy) * g.nx + cx0;  // bin plane = zl + 1
+  const int32_t p0 = bin_start[cell0 << 3], p1 = bin_start[(cell0 + ncell) << 3];
+  __syncthreads();
+  for (int32_t i = p0 + threadIdx.x; i < p1; i += PUSH_THREADS) {
+    Weights w;
+    make_weights(g, x[i], y[i], z[i], 0, w);
+    const TileIndex t = tile_index(w, cx0, cy, zl);
+    double Ep[3], Bp[3];
+    gather_E_tile(Et, w, t, Ep);
+    gather_B_tile(Bt, w, t, Bp);
+    double v[3] = {vx[i], vy[i], vz[i]};
+    boris_update_vEB(g.dt, qm, Ep, Bp, v);
+    vx[i] = v[0];
+    vy[i] = v[1];
+    vz[i] = v[2];
+  }
 }
 
 int push_second(xb_ctx* c, Species& s, const double* Eh, const double* B)
 {
   if (s.count == 0) return 0;
+  if (!s.sorted) XB_FAIL("push_second: particles are not sorted");
+  const Grid& g = c->g;
   double** p = s.p[s.cur];
-  XB_LAUNCH(c, k_push_second, grid_for(s.count), 256, 0, c->g, s.count, p[0], p[1], p[2], p[3], p[4], p[5], Eh, B, s.q / s.m);
+  const int groups_x = (g.nx + TILE_CELLS - 1) / TILE_CELLS;
+  const int64_t blocks = (int64_t)groups_x * g.ny * g.nzl;
+  XB_LAUNCH(c, k_push_second, (int)blocks, PUSH_THREADS, 0, g, s.bin_start, p[0], p[1], p[2], p[3], p[4], p[5], Eh, B, s.q / s.m, groups_x);
   return 0;
 }
 
