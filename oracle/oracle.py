@@ -33,6 +33,8 @@ def lib():
         build()
         L = C.CDLL(_LIB)
         dp = C.POINTER(C.c_double)
+        L.xo_set_threads.argtypes = [C.c_int]
+        L.xo_max_threads.restype = C.c_int
         L.xo_create.restype = C.c_void_p
         L.xo_create.argtypes = [C.c_int] * 3 + [C.c_double] * 4 + [C.c_int]
         L.xo_destroy.argtypes = [C.c_void_p]
@@ -62,6 +64,15 @@ def lib():
         L.xo_esirkepov.argtypes = [C.c_void_p, dp, dp, C.c_double, dp]
         _lib = L
     return _lib
+
+
+def set_threads(n):
+    """OpenMP threads used by the particle / matrix / Krylov loops (default 1: deterministic)."""
+    lib().xo_set_threads(int(n))
+
+
+def max_threads():
+    return lib().xo_max_threads()
 
 
 def _dp(a):

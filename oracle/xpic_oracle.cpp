@@ -13,7 +13,10 @@
 // un-pinned third party: GMRES(30)+ILU(0) defaults) is NOT restated -- "parity unpinned"
 // for residual histories; the converged solution is what the goldens pin.
 //
-// Single-threaded, plain C++17, no dependencies.  Every routine cites the reference
+// Plain C++17, no dependencies.  Single-threaded by default (deterministic, what the tests use);
+// xo_set_threads(n) enables OpenMP over cells / rows for the CPU-baseline timings, with the same
+// loop structure the reference parallelises (omp parallel for over cells + atomics on shared arrays,
+// src/impls/ecsim/particles.cpp:41-47,137-142).  Every routine cites the reference
 // file:line (relative to /root/reference) whose arithmetic it follows.
 #include <algorithm>
 #include <cmath>
@@ -23,6 +26,10 @@
 #include <list>
 #include <random>
 #include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace {
 
@@ -103,8 +110,11 @@ inline double& csr_at(Csr& A, int64_t row, int32_t col)
   return A.val[it - A.col.begin()];
 }
 
+int g_threads = 1;
+
 void csr_mult(const Csr& A, const double* x, double* y, int64_t nrows)
 {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
   for (int64_t r = 0; r < nrows; ++r) {
     double s = 0.0;
     for (int64_t k = A.rowptr[r]; k < A.rowptr[r + 1]; ++k) s += A.val[k] * x[A.col[k]];
@@ -402,8 +412,11 @@ void decompose_ecsim_current(const Sim& s, const Species& sp, const Point& pt, s
         s1[0] = w.wn[2][k1] * w.wn[1][j1] * w.ws[0][i1];
         s1[1] = w.wn[2][k1] * w.ws[1][j1] * w.wn[0][i1];
         s1[2] = w.ws[2][k1] * w.wn[1][j1] * w.wn[0][i1];
+#pragma omp atomic update
         currI[s.vidx(w.is[0] + i1, w.in[1] + j1, w.in[2] + k1, 0)] += s1[0] * I_p[0];
+#pragma omp atomic update
         currI[s.vidx(w.in[0] + i1, w.is[1] + j1, w.in[2] + k1, 1)] += s1[1] * I_p[1];
+#pragma omp atomic update
         currI[s.vidx(w.in[0] + i1, w.in[1] + j1, w.is[2] + k1, 2)] += s1[2] * I_p[2];
 
         i[0] = (k1 * 2 + j1) * 3 + (ox + i1);
@@ -445,7 +458,9 @@ void add_block_to_csr(Sim& s, int x, int y, int z, const double* coo_v)
                   const int32_t col = (int32_t)s.vidx(x + i2 + lo2[0], y + j2 + lo2[1], z + k2 + lo2[2], c2);
                   const int j = (k2 * sz2[1] + j2) * sz2[0] + i2;
                   const int ind = (c1 * 3 + c2) * 144 + (i * 12 + j);
-                  csr_at(s.matL, row, col) += coo_v[ind];
+                  double& dst = csr_at(s.matL, row, col);
+#pragma omp atomic update
+                  dst += coo_v[ind];
                 }
           }
         }
@@ -456,18 +471,21 @@ void add_block_to_csr(Sim& s, int x, int y, int z, const double* coo_v)
 void fill_ecsim_current(Sim& s)
 {
   std::fill(s.matL.val.begin(), s.matL.val.end(), 0.0);
-  std::vector<double> coo_v(1296);
   for (auto& sp : s.sorts) {
     // per-sort currI was zeroed in clear_sources
-    for (int z = 0; z < s.N[2]; ++z)
-      for (int y = 0; y < s.N[1]; ++y)
-        for (int x = 0; x < s.N[0]; ++x) {
-          const auto& cell = sp.storage[s.cell(x, y, z)];
-          if (cell.empty()) continue;
-          std::fill(coo_v.begin(), coo_v.end(), 0.0);
-          for (const auto& pt : cell) decompose_ecsim_current(s, sp, pt, sp.currI, coo_v.data());
-          add_block_to_csr(s, x, y, z, coo_v.data());
-        }
+#pragma omp parallel num_threads(g_threads)
+    {
+      std::vector<double> coo_v(1296);
+#pragma omp for schedule(dynamic, 16)
+      for (int64_t gcell = 0; gcell < s.nc; ++gcell) {
+        const int x = (int)(gcell % s.N[0]), y = (int)((gcell / s.N[0]) % s.N[1]), z = (int)(gcell / ((int64_t)s.N[0] * s.N[1]));
+        const auto& cell = sp.storage[gcell];
+        if (cell.empty()) continue;
+        std::fill(coo_v.begin(), coo_v.end(), 0.0);
+        for (const auto& pt : cell) decompose_ecsim_current(s, sp, pt, sp.currI, coo_v.data());
+        add_block_to_csr(s, x, y, z, coo_v.data());
+      }
+    }
     for (int64_t i = 0; i < s.n3; ++i) s.currI[i] += sp.currI[i];
   }
 }
@@ -537,6 +555,7 @@ void gmres(Op&& apply, int64_t n, const double* b, double* x, Solver& sv)
   std::vector<double> H((m + 1) * m), cs(m), sn(m), g(m + 1), w(n), r(n), y(m);
   auto nrm = [&](const double* a) {
     double s = 0;
+#pragma omp parallel for num_threads(g_threads) reduction(+ : s) schedule(static)
     for (int64_t i = 0; i < n; ++i) s += a[i] * a[i];
     return std::sqrt(s);
   };
@@ -558,9 +577,13 @@ void gmres(Op&& apply, int64_t n, const double* b, double* x, Solver& sv)
       apply(V[k].data(), w.data());
       for (int i = 0; i <= k; ++i) {
         double h = 0;
-        for (int64_t l = 0; l < n; ++l) h += w[l] * V[i][l];
+        const double* vi = V[i].data();
+        double* wp = w.data();
+#pragma omp parallel for num_threads(g_threads) reduction(+ : h) schedule(static)
+        for (int64_t l = 0; l < n; ++l) h += wp[l] * vi[l];
         H[i * m + k] = h;
-        for (int64_t l = 0; l < n; ++l) w[l] -= h * V[i][l];
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+        for (int64_t l = 0; l < n; ++l) wp[l] -= h * vi[l];
       }
       const double hn = nrm(w.data());
       H[(k + 1) * m + k] = hn;
@@ -648,17 +671,19 @@ void step_ecsim(Sim& s)  // ecsim/simulation.cpp:145-155
 {
   clear_sources(s);
   for (auto& sp : s.sorts) {  // first_push :174-189, particles.cpp:21-31
-    for (auto& cell : sp.storage)
-      for (auto& pt : cell)
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic, 16)
+    for (int64_t gc = 0; gc < s.nc; ++gc)
+      for (auto& pt : sp.storage[gc])
         for (int c = 0; c < 3; ++c) pt.r[c] += pt.p[c] * s.dt;
-    update_cells_seq(s, sp);
+    update_cells_seq(s, sp);  // serial in the reference as well (interfaces/particles.cpp:79-116)
   }
   fill_ecsim_current(s);
   advance_fields(s, s.predict, true, s.currI, s.Ep);
   for (auto& sp : s.sorts) {  // second_push :212-239, particles.cpp:175-192
     const double qm = sp.q / sp.m;
-    for (auto& cell : sp.storage)
-      for (auto& pt : cell) {
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic, 16)
+    for (int64_t gc = 0; gc < s.nc; ++gc)
+      for (auto& pt : sp.storage[gc]) {
         W w;
         weights(s, pt.r, w);
         double Ep[3], Bp[3];
@@ -763,6 +788,17 @@ std::vector<double>* field_by_id(Sim& s, int which, int sid)
 // C interface (ctypes)
 // =============================================================================================
 extern "C" {
+
+// OpenMP threads for the baseline timings (1 = deterministic serial execution, the default)
+void xo_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+int xo_max_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_num_procs();
+#else
+  return 1;
+#endif
+}
 
 void* xo_create(int nx, int ny, int nz, double dx, double dy, double dz, double dt, int curl_sign)
 {
