@@ -165,6 +165,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # libraries (NCCL's version banner, torch warnings) write to fd 1; the contract is ONE JSON line on
+    # stdout, so everything else goes to stderr and the line is written to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -296,7 +302,8 @@ def main():
                     "boundary": "xb_step_host: E, B, B0 uploaded from pinned host buffers, E, B and kinetic energy downloaded every step; particles resident"},
             "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     sim.close()
     if world > 1:
         dist.destroy_process_group()
