@@ -132,6 +132,25 @@ def test_ecsimcorr_10_steps_state_parity(X):
         assert abs(s.scalar(name) - o.scalar(name)) < 1e-10, name
 
 
+def test_ecsimcorr_esirkepov_variants_agree(X):
+    """Atomic-free tensor-core Esirkepov deposit vs the per-particle reduction kernel vs the oracle."""
+    res = {}
+    for variant in (0, 1):
+        o, s = make_pair(n=(9, 7, 6), Np=30, scheme=X.ECSIMCORR, seed_fields=21)
+        s.set_option(1, variant)
+        for _ in range(3):
+            s.step()
+        res[variant] = (s.get_field("currJe"), s.get_field("E"), s.scalar("pred_w"))
+        if variant == 0:
+            for _ in range(3):
+                o.step(O.ECSIMCORR)
+            assert rel_err(res[0][0], o.get_field("currJe")) < 1e-10
+            assert rel_err(res[0][1], o.get_field("E")) < 1e-10
+            assert abs(res[0][2] - o.scalar("pred_w")) < 1e-12
+    assert rel_err(res[0][0], res[1][0]) < 1e-11
+    assert rel_err(res[0][1], res[1][1]) < 1e-11
+
+
 def test_ecsim_golden_energy_rows(X):
     """The CUDA path against the reference's own golden file (curl_sign = -1)."""
     _, s = make_pair(n=(10, 10, 10), Np=100, scheme=X.ECSIM, curl_sign=-1)

@@ -70,7 +70,10 @@ static int stage_first_push(xb_ctx* c, int scheme)
       XB_CHECK(sort_species(c, s, c->g.dt));  // r += v dt, wrap, re-bin (ecsim/particles.cpp:21-31)
     }
     else {
-      XB_CHECK(push_first_corr(c, s));
+      if (c->esirkepov_variant == 1)
+        XB_CHECK(push_first_corr(c, s));
+      else
+        XB_CHECK(push_first_corr_mma(c, s));
       XB_CHECK(sort_species(c, s, 0.0));
     }
   }
@@ -98,7 +101,10 @@ static int stage_second_push(xb_ctx* c, int scheme)
       // positions did not change: the reference's second update_cells is a no-op here
     }
     else {
-      XB_CHECK(push_second_corr(c, s, c->Ep, c->B));
+      if (c->esirkepov_variant == 1)
+        XB_CHECK(push_second_corr(c, s, c->Ep, c->B));
+      else
+        XB_CHECK(push_second_corr_mma(c, s, c->Ep, c->B));
       XB_CHECK(halo_reduce(c, s.currJe, GZ, GZ));
       const double one = 1.0;
       const double* vs[1] = {s.currJe};
@@ -641,6 +647,10 @@ int xb_set_option(xb_ctx* c, int32_t what, int32_t value)
   XB_API_BEGIN(c);
   if (what == 0) {
     c->deposit_variant = value;
+    return 0;
+  }
+  if (what == 1) {
+    c->esirkepov_variant = value;
     return 0;
   }
   XB_FAIL("xb_set_option: unknown option");

@@ -131,6 +131,7 @@ struct xb_ctx {
   int64_t coef_elems = 0;
   bool coef_valid = false;
   int deposit_variant = 0;  // 0: DMMA cell blocks (default), 1: scalar-FMA cell blocks (kept as a cross-check)
+  int esirkepov_variant = 0;  // 0: DMMA cell blocks + gather (default), 1: per-particle global reductions (cross-check)
   // deposit staging (cell blocks)
   double* stage = nullptr;
   int64_t stage_cells = 0;
@@ -206,6 +207,10 @@ int coef_convert(xb_ctx* c, double* plain_dev, bool to_blocked);
 // ---- esirkepov.cu ----------------------------------------------------------------------------
 int push_first_corr(xb_ctx* c, Species& s);
 int push_second_corr(xb_ctx* c, Species& s, const double* Eh, const double* B);
+
+// ---- esirkepov_mma.cu (atomic-free tensor-core form, the default) ----------------------------
+int push_first_corr_mma(xb_ctx* c, Species& s);
+int push_second_corr_mma(xb_ctx* c, Species& s, const double* Eh, const double* B);
 
 // ---- launch bookkeeping ----------------------------------------------------------------------
 #define XB_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
