@@ -195,6 +195,7 @@ void species_free(Species& s);
 void migrate_free(Species& s);  // migrate.cu
 int particles_sort(xb_ctx* c, Species& s, double dt_move);   // r += v dt_move, wrap, re-bin
 int push_second(xb_ctx* c, Species& s, const double* Eh, const double* B);
+int push_second_work(xb_ctx* c, Species& s, const double* Eh, const double* B, double* pred_w);
 int kinetic_energy(xb_ctx* c, Species& s, double* sum_v2, double* K);
 int scale_velocities(xb_ctx* c, Species& s, double lambda);
 int particle_moments(xb_ctx* c, Species& s, double* out5);

@@ -4,7 +4,7 @@
 // src/impls/ecsimcorr/particles.cpp:27-91; EsirkepovDecomposition::process,
 // src/algorithms/esirkepov_decomposition.cpp:20-103) with the structure of the moment deposition:
 //
-//  pass 1  k_esirkepov_cells<MODE>: one CTA per 4 x-consecutive cells, three warps per cell (one per
+//  pass 1  k_esirkepov_cells: one CTA per 4 x-consecutive cells, three warps per cell (one per
 //          current component).  With the 2nd-order spline the current of one particle is
 //              Jx(i,j,k) = Px(i) * [ S'y(j) Az(k) + Sy(j) Bz(k) ],   A = 2 S' + S,  B = 2 S + S'
 //          (Px = running sum of -q dx (S'x - Sx), esirkepov_decomposition.cpp:57-71; cyclic for y, z),
@@ -13,8 +13,8 @@
 //          reference's own window get an exact zero).  Four particles go through one
 //          mma.sync.m8n8k4.f64: rows = the prefix axis (6 of 8 used), columns = the fast transverse
 //          axis (6 of 8), one DMMA per value of the slow transverse axis: 18 DMMAs per 4 particles.
-//          MODE 1 (second push) first gathers E^{n+1/2}, B from shared-memory field tiles, does the
-//          Boris update and accumulates the predicted work (particles.cpp:59-79).
+//          The kernel also does the half move r += v dt/2 (the second push's Boris update and
+//          predicted work run before it in k_push_second<true>, particles.cu).
 //          Finished 648-entry cell blocks leave in coalesced runs to the staging area.
 //  pass 2  k_esirkepov_gather: one thread per (node, component) sums, in a fixed order, the 216 cell
 //          blocks whose window contains the node, into the ghosted current (+=).
@@ -35,7 +35,7 @@ constexpr int EAX = 31;
 constexpr int EREC = 3 * EAX;         // 93 doubles per particle
 constexpr int ECELLS = CELL_GROUP;    // 4 cells per CTA
 constexpr int EWARPS = 3 * ECELLS;
-constexpr int ESMEM_PER_CELL = ECHUNK * EREC + ECHUNK * 8;  // records + E/B scratch (6 used)
+constexpr int ESMEM_PER_CELL = ECHUNK * EREC;
 static_assert(ECHUNK * EREC >= EBLOCK, "the cell block aliases the record buffer");
 
 __device__ __forceinline__ double spline2e(double s)
@@ -65,10 +65,8 @@ struct EsirkepovArgs {
   double* p[6];
   const int32_t* bin_start;
   double q_alpha;  // q n / Np / (6 dt), src/impls/ecsimcorr/particles.cpp:130
-  double qm, qn_Np;
   double* stage;
-  double* partial;  // one predicted-work partial per CTA (MODE 1)
-  int* flag;        // set when a particle moves a full cell or more in one half move
+  int* flag;       // set when a particle moves a full cell or more in one half move
 };
 
 // axis data of one particle: fills r[0..30) = S'[6], S[6], A[6], B[6], P[6]
@@ -88,120 +86,83 @@ __device__ __forceinline__ void axis_record(double po, double pn, int c0, double
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(EWARPS * 32, 2) k_esirkepov_cells(Grid g, EsirkepovArgs a, const double* __restrict__ E, const double* __restrict__ B,
-                                                                     int groups_x)
+// One warp = one current component (AXIS) of one cell.
+//   Jx: rows x (Px), tiles over y (S'y, Sy), columns z (Az, Bz)
+//   Jy: rows y (Py), tiles over x (S'x, Sx), columns z (Az, Bz)
+//   Jz: rows z (Pz), tiles over x (Ax, Bx),  columns y (S'y, Sy)
+template <int AXIS>
+__device__ __forceinline__ void cell_axis(const Grid& g, const EsirkepovArgs& a, double* __restrict__ rec, int slot, int lane, int c_axis, int32_t p0,
+                                          int32_t p1, double (&acc)[EW][2])
+{
+  constexpr int SLOW = AXIS == 0 ? 1 : 0, FAST = AXIS == 2 ? 1 : 2;
+  constexpr int SLOW_OFF = AXIS == 2 ? 12 : 0;  // (A, B) of x for Jz, (S', S) otherwise
+  constexpr int FAST_OFF = AXIS == 2 ? 0 : 12;  // (S', S) of y for Jz, (A, B) of z otherwise
+  const double d_axis = AXIS == 0 ? g.dx : (AXIS == 1 ? g.dy : g.dz);
+  const double inv_axis = AXIS == 0 ? g.inv_dx : (AXIS == 1 ? g.inv_dy : g.inv_dz);
+  const int exact = g.exact_inv & (1 << AXIS);
+  const int gq = lane >> 2, q = lane & 3;
+  const int gc = gq < EW ? gq : 0;
+  const double h = 0.5 * g.dt;
+  double* __restrict__ pos = a.p[AXIS];
+  const double* __restrict__ vel = a.p[3 + AXIS];
+  for (int32_t base = p0; base < p1; base += ECHUNK) {
+    const int n = min(ECHUNK, p1 - base);
+    const int32_t i = base + lane;
+    double rn = 0.0;
+    if (lane < n) {
+      const double ro = pos[i];
+      rn = ro + vel[i] * h;
+      const double po = to_cells(ro, d_axis, inv_axis, exact), pn = to_cells(rn, d_axis, inv_axis, exact);
+      if (fabs(pn - po) >= 1.0) atomicOr(a.flag, 1);
+      axis_record(po, pn, c_axis, a.q_alpha * d_axis, rec + lane * EREC + AXIS * EAX);
+      pos[i] = rn;  // only this warp reads or writes this axis' coordinate
+    }
+    cell_barrier(slot);  // all three axis records of the chunk are complete
+    for (int gs = 0; gs < n; gs += 4) {
+      const bool valid = gs + q < n;
+      const double* r = rec + min(gs + q, n - 1) * EREC;
+      // A operand: prefix sums along the own axis at node gq (rows 6, 7 are padding)
+      const double av = (valid && gq < EW) ? r[AXIS * EAX + 24 + gq] : 0.0;
+      double f0 = r[FAST * EAX + FAST_OFF + gc], f1 = r[FAST * EAX + FAST_OFF + 6 + gc];  // column factors at node gq
+      if (gq >= EW) f0 = f1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < EW; ++t) {
+        const double s0 = r[SLOW * EAX + SLOW_OFF + t], s1 = r[SLOW * EAX + SLOW_OFF + 6 + t];  // same for all lanes of a particle
+        dmma_e(acc[t][0], acc[t][1], av, s0 * f0 + s1 * f1);
+      }
+    }
+    cell_barrier(slot);  // the records may be overwritten by the next chunk
+  }
+}
+
+__global__ void __launch_bounds__(EWARPS * 32, 2) k_esirkepov_cells(Grid g, EsirkepovArgs a, int groups_x)
 {
   extern __shared__ double smem[];
-  double* Et = smem;                      // field tiles (MODE 1)
-  double* Bt = Et + FIELD_TILE;
-  double* cells = Bt + FIELD_TILE;
+  double* cells = smem;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = wid / 3, axis = wid % 3;
   double* rec = cells + (size_t)slot * ESMEM_PER_CELL;
-  double* eb = rec + ECHUNK * EREC;       // [32][8]: Ep[3], Bp[3]
 
   const int gx = blockIdx.x % groups_x, row = blockIdx.x / groups_x;
   const int cy = row % g.ny, zl = row / g.ny;
   const int cx0 = gx * TILE_CELLS, ncell = min(TILE_CELLS, g.nx - cx0);
-  if (MODE == 1) {
-    load_field_tile(g, E, cx0, cy, zl, Et, threadIdx.x, EWARPS * 32);
-    load_field_tile(g, B, cx0, cy, zl, Bt, threadIdx.x, EWARPS * 32);
-    __syncthreads();
-  }
   const bool live = slot < ncell;
   const int cx = cx0 + slot;
-  const int ccell[3] = {cx, cy, zl + g.z0};  // global cell indices: positions are global coordinates
-  const double dd[3] = {g.dx, g.dy, g.dz}, inv[3] = {g.inv_dx, g.inv_dy, g.inv_dz};
   const int gq = lane >> 2, q = lane & 3;
   double acc[EW][2];
 #pragma unroll
   for (int t = 0; t < EW; ++t) acc[t][0] = acc[t][1] = 0.0;
-  double work = 0.0;
 
   if (live) {
     const int64_t cell0 = ((int64_t)(zl + 1) * g.ny + cy) * g.nx + cx;
     const int32_t p0 = a.bin_start[cell0 << 3], p1 = a.bin_start[(cell0 + 1) << 3];
-    const double h = 0.5 * g.dt;
-    // which axes feed this warp's component: prefix axis = own, transverse slow / fast
-    //   Jx: tiles over y (S'y, Sy), columns z (Az, Bz)      Jy: tiles over x (S'x, Sx), columns z (Az, Bz)
-    //   Jz: tiles over x (Ax, Bx),  columns y (S'y, Sy)
-    const int slow = axis == 0 ? 1 : 0, fast = axis == 2 ? 1 : 2;
-    for (int32_t base = p0; base < p1; base += ECHUNK) {
-      const int n = min(ECHUNK, p1 - base);
-      const int32_t i = base + lane;
-      double ro = 0.0, vo = 0.0;
-      if (lane < n) {
-        ro = a.p[axis][i];
-        vo = a.p[3 + axis][i];
-      }
-      double vn = vo;
-      if (MODE == 1) {
-        // phase A: this warp gathers component `axis` of E and B for the chunk's particles
-        if (lane < n) {
-          Weights w;
-          make_weights(g, a.p[0][i], a.p[1][i], a.p[2][i], 0, w);
-          const TileIndex t = tile_index(w, cx0, cy, zl);
-          double Ep[3], Bp[3];
-          gather_E_tile(Et, w, t, Ep);  // the compiler drops the two unused components
-          gather_B_tile(Bt, w, t, Bp);
-          eb[lane * 8 + axis] = Ep[axis];
-          eb[lane * 8 + 3 + axis] = Bp[axis];
-        }
-        cell_barrier(slot);
-        if (lane < n) {
-          const double Ep[3] = {eb[lane * 8 + 0], eb[lane * 8 + 1], eb[lane * 8 + 2]};
-          const double Bp[3] = {eb[lane * 8 + 3], eb[lane * 8 + 4], eb[lane * 8 + 5]};
-          double v[3] = {a.p[3][i], a.p[4][i], a.p[5][i]};
-          boris_update_vEB(g.dt, a.qm, Ep, Bp, v);
-          vn = v[axis];
-          work += a.qn_Np * 0.5 * (vo + vn) * Ep[axis];  // one term of (v_old + v_new) . E_p
-        }
-      }
-      if (lane < n) {
-        const double rn = ro + vn * h;
-        const double po = to_cells(ro, dd[axis], inv[axis], g.exact_inv & (1 << axis));
-        const double pn = to_cells(rn, dd[axis], inv[axis], g.exact_inv & (1 << axis));
-        if (fabs(pn - po) >= 1.0) atomicOr(a.flag, 1);
-        axis_record(po, pn, ccell[axis], a.q_alpha * dd[axis], rec + lane * EREC + axis * EAX);
-      }
-      cell_barrier(slot);  // all three axis records of the chunk are complete (and eb was consumed)
-      if (lane < n) {      // positions / velocities are written only after every warp has read the old ones
-        a.p[axis][i] = ro + vn * h;
-        if (MODE == 1) a.p[3 + axis][i] = vn;
-      }
-      for (int gs = 0; gs < n; gs += 4) {
-        const bool valid = gs + q < n;
-        const double* r = rec + min(gs + q, n - 1) * EREC;
-        // A operand: prefix sums along the own axis at node gq (rows 6, 7 are padding)
-        const double av = (valid && gq < EW) ? r[axis * EAX + 24 + gq] : 0.0;
-        const int gc = gq < EW ? gq : 0;
-        double f0, f1;  // fast-axis factors at column node gq
-        if (axis == 2) {
-          f0 = r[fast * EAX + 0 + gc];   // S'y
-          f1 = r[fast * EAX + 6 + gc];   // Sy
-        }
-        else {
-          f0 = r[fast * EAX + 12 + gc];  // Az
-          f1 = r[fast * EAX + 18 + gc];  // Bz
-        }
-        if (gq >= EW) f0 = f1 = 0.0;
-#pragma unroll
-        for (int t = 0; t < EW; ++t) {
-          double s0, s1;  // slow-axis factors at node t (same for all lanes of a particle)
-          if (axis == 2) {
-            s0 = r[slow * EAX + 12 + t];  // Ax
-            s1 = r[slow * EAX + 18 + t];  // Bx
-          }
-          else {
-            s0 = r[slow * EAX + 0 + t];   // S'(slow)
-            s1 = r[slow * EAX + 6 + t];   // S(slow)
-          }
-          dmma_e(acc[t][0], acc[t][1], av, s0 * f0 + s1 * f1);
-        }
-      }
-      cell_barrier(slot);  // the records may be overwritten by the next chunk
-    }
+    // global cell indices: positions are global coordinates
+    if (axis == 0)
+      cell_axis<0>(g, a, rec, slot, lane, cx, p0, p1, acc);
+    else if (axis == 1)
+      cell_axis<1>(g, a, rec, slot, lane, cy, p0, p1, acc);
+    else
+      cell_axis<2>(g, a, rec, slot, lane, zl + g.z0, p0, p1, acc);
   }
   // accumulators -> the cell's [comp][k][j][i] block (aliases the record buffer)
   cell_barrier(slot);
@@ -219,22 +180,12 @@ __global__ void __launch_bounds__(EWARPS * 32, 2) k_esirkepov_cells(Grid g, Esir
         rec[axis * (EW * EW * EW) + (kk * EW + jj) * EW + ii] = live ? acc[t][e] : 0.0;
       }
   }
-  if (MODE == 1) {
-    work = warp_sum(work);
-    if (lane == 0) eb[axis] = work;  // eb is free again
-  }
   __syncthreads();
   const int64_t group = ((int64_t)zl * g.ny + cy) * groups_x + gx;
   double* out = a.stage + group * (int64_t)(EBLOCK * ECELLS);
   for (int idx = threadIdx.x; idx < EBLOCK * ECELLS; idx += EWARPS * 32) {
     const int e = idx / ECELLS, w = idx % ECELLS;
     out[idx] = cells[(size_t)w * ESMEM_PER_CELL + e];
-  }
-  if (MODE == 1 && threadIdx.x == 0) {
-    double t = 0.0;
-    for (int s = 0; s < ECELLS; ++s)
-      for (int ax = 0; ax < 3; ++ax) t += cells[(size_t)s * ESMEM_PER_CELL + ECHUNK * EREC + ax];
-    a.partial[group] = t;
   }
 }
 
@@ -281,44 +232,33 @@ __global__ void __launch_bounds__(RED_THREADS) k_sum_partials(const double* __re
   }
 }
 
-static int run_cells(xb_ctx* c, Species& s, int mode, const double* Eh, const double* B)
+// half move r += v dt/2 of every particle + Esirkepov current of that move into s.currJe (ghosted, +=)
+static int run_cells(xb_ctx* c, Species& s)
 {
   const Grid& g = c->g;
   if (!s.sorted) XB_FAIL("esirkepov: particles are not sorted");
   if (g.nx < EW || g.ny < EW) XB_FAIL("esirkepov (tensor-core form): the box must be at least 6 cells wide in x and y");
   static bool attr = false;
-  const size_t smem = sizeof(double) * (2 * FIELD_TILE + (size_t)ECELLS * ESMEM_PER_CELL);
+  const size_t smem = sizeof(double) * ((size_t)ECELLS * ESMEM_PER_CELL);
   if (!attr) {
-    XB_CUDA(cudaFuncSetAttribute(k_esirkepov_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    XB_CUDA(cudaFuncSetAttribute(k_esirkepov_cells<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XB_CUDA(cudaFuncSetAttribute(k_esirkepov_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   const int groups_x = (g.nx + TILE_CELLS - 1) / TILE_CELLS;
   const int64_t groups = (int64_t)groups_x * g.ny * g.nzl;
   if (groups * EBLOCK * ECELLS > ((c->stage_cells + CELL_GROUP - 1) / CELL_GROUP) * (int64_t)CELL_GROUP * BLOCK_ALL)
     XB_FAIL("esirkepov: staging area too small");
-  if (groups > g.ntot) XB_FAIL("esirkepov: partial buffer too small");
   EsirkepovArgs a;
   double** p = s.p[s.cur];
   for (int k = 0; k < 6; ++k) a.p[k] = p[k];
   a.bin_start = s.bin_start;
-  a.qn_Np = s.q * s.n / s.Np;
-  a.q_alpha = a.qn_Np / (6.0 * g.dt);
-  a.qm = s.q / s.m;
+  a.q_alpha = s.q * s.n / s.Np / (6.0 * g.dt);
   a.stage = c->stage;
-  a.partial = c->tmp;  // one double per CTA; c->tmp is free during the pushes
   a.flag = reinterpret_cast<int*>(c->red_out + RED_MAXV - 1);
   XB_CUDA(cudaMemsetAsync(a.flag, 0, sizeof(int), c->stream));
-  if (mode == 0)
-    XB_LAUNCH(c, k_esirkepov_cells<0>, (int)groups, EWARPS * 32, smem, g, a, Eh, B, groups_x);
-  else
-    XB_LAUNCH(c, k_esirkepov_cells<1>, (int)groups, EWARPS * 32, smem, g, a, Eh, B, groups_x);
+  XB_LAUNCH(c, k_esirkepov_cells, (int)groups, EWARPS * 32, smem, g, a, groups_x);
   const int64_t total = (int64_t)g.plane * (g.nzl + 2 * GZ) * 3;
   XB_LAUNCH(c, k_esirkepov_gather, (int)((total + 127) / 128), 128, 0, g, c->stage, s.currJe, groups_x);
-  if (mode == 1) {
-    XB_LAUNCH(c, k_sum_partials, RED_BLOCKS, RED_THREADS, 0, c->tmp, groups, c->red_partial);
-    XB_CHECK(reduce_finish(c, 1, &s.pred_w));
-  }
   int flag = 0;
   XB_CUDA(cudaMemcpyAsync(&flag, a.flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   XB_CUDA(cudaStreamSynchronize(c->stream));
@@ -327,7 +267,14 @@ static int run_cells(xb_ctx* c, Species& s, int mode, const double* Eh, const do
   return 0;
 }
 
-int push_first_corr_mma(xb_ctx* c, Species& s) { return run_cells(c, s, 0, nullptr, nullptr); }
-int push_second_corr_mma(xb_ctx* c, Species& s, const double* Eh, const double* B) { return run_cells(c, s, 1, Eh, B); }
+int push_first_corr_mma(xb_ctx* c, Species& s) { return run_cells(c, s); }
+// second push = Boris update + predicted work at full occupancy (particles.cu), then the same half
+// move + deposit kernel as the first push (gather + Boris inside the tensor-core kernel, three
+// redundant updates at 24 warps/SM, measured 19 ms slower at 128^3 x 64)
+int push_second_corr_mma(xb_ctx* c, Species& s, const double* Eh, const double* B)
+{
+  XB_CHECK(push_second_work(c, s, Eh, B, &s.pred_w));
+  return run_cells(c, s);
+}
 
 }  // namespace xb

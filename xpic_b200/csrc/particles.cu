@@ -364,10 +364,14 @@ int particles_generate(xb_ctx* c, Species& s, int64_t total, const double* T, ui
 // reads and HBM sees only the particle stream (72 B / particle).
 constexpr int PUSH_THREADS = 128;
 
+// WORK: also accumulate the predicted field work  q n/Np * (v_old + v_new)/2 . E_p  of ecsimcorr
+// (src/impls/ecsimcorr/particles.cpp:77-78), one partial per CTA (summed by a fixed tree afterwards)
+template <bool WORK>
 __global__ void __launch_bounds__(PUSH_THREADS) k_push_second(Grid g, const int32_t* __restrict__ bin_start, const double* __restrict__ x,
                                                               const double* __restrict__ y, const double* __restrict__ z, double* __restrict__ vx,
                                                               double* __restrict__ vy, double* __restrict__ vz, const double* __restrict__ E,
-                                                              const double* __restrict__ B, double qm, int groups_x)
+                                                              const double* __restrict__ B, double qm, int groups_x, double qn_Np,
+                                                              double* __restrict__ partial)
 {
   __shared__ double Et[FIELD_TILE], Bt[FIELD_TILE];
   const int gx = blockIdx.x % groups_x, row = blockIdx.x / groups_x;  // row = zl * ny + cy
@@ -378,6 +382,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_second(Grid g, const int3
   const int64_t cell0 = ((int64_t)(zl + 1) * g.ny + cy) * g.nx + cx0;  // bin plane = zl + 1
   const int32_t p0 = bin_start[cell0 << 3], p1 = bin_start[(cell0 + ncell) << 3];
   __syncthreads();
+  double work = 0.0;
   for (int32_t i = p0 + threadIdx.x; i < p1; i += PUSH_THREADS) {
     Weights w;
     make_weights(g, x[i], y[i], z[i], 0, w);
@@ -385,12 +390,62 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_second(Grid g, const int3
     double Ep[3], Bp[3];
     gather_E_tile(Et, w, t, Ep);
     gather_B_tile(Bt, w, t, Bp);
-    double v[3] = {vx[i], vy[i], vz[i]};
+    const double vo[3] = {vx[i], vy[i], vz[i]};
+    double v[3] = {vo[0], vo[1], vo[2]};
     boris_update_vEB(g.dt, qm, Ep, Bp, v);
     vx[i] = v[0];
     vy[i] = v[1];
     vz[i] = v[2];
+    if (WORK) {
+      const double vs[3] = {vo[0] + v[0], vo[1] + v[1], vo[2] + v[2]};
+      work += qn_Np * 0.5 * dot3(vs, Ep);
+    }
   }
+  if (WORK) {
+    __shared__ double sh[PUSH_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    work = warp_sum(work);
+    if (lane == 0) sh[wid] = work;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int q = 0; q < PUSH_THREADS / 32; ++q) t += sh[q];
+      partial[blockIdx.x] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_sum_array(const double* __restrict__ v, int64_t n, double* __restrict__ partial)
+{
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += v[i];
+  __shared__ double sh[RED_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  acc = warp_sum(acc);
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < RED_THREADS / 32; ++q) t += sh[q];
+    partial[(int64_t)blockIdx.x * RED_MAXV] = t;
+  }
+}
+
+int reduce_finish(xb_ctx* c, int nv, double* host_out);  // fields.cu
+
+// second push of ecsimcorr without the half move: Boris update + predicted work (all ranks' sum)
+int push_second_work(xb_ctx* c, Species& s, const double* Eh, const double* B, double* pred_w)
+{
+  const Grid& g = c->g;
+  if (!s.sorted) XB_FAIL("push_second: particles are not sorted");
+  double** p = s.p[s.cur];
+  const int groups_x = (g.nx + TILE_CELLS - 1) / TILE_CELLS;
+  const int64_t blocks = (int64_t)groups_x * g.ny * g.nzl;
+  if (blocks > g.ntot) XB_FAIL("push_second: partial buffer too small");
+  XB_LAUNCH(c, k_push_second<true>, (int)blocks, PUSH_THREADS, 0, g, s.bin_start, p[0], p[1], p[2], p[3], p[4], p[5], Eh, B, s.q / s.m, groups_x,
+            s.q * s.n / s.Np, c->tmp);
+  XB_LAUNCH(c, k_sum_array, RED_BLOCKS, RED_THREADS, 0, c->tmp, blocks, c->red_partial);
+  return reduce_finish(c, 1, pred_w);
 }
 
 int push_second(xb_ctx* c, Species& s, const double* Eh, const double* B)
@@ -401,7 +456,8 @@ int push_second(xb_ctx* c, Species& s, const double* Eh, const double* B)
   double** p = s.p[s.cur];
   const int groups_x = (g.nx + TILE_CELLS - 1) / TILE_CELLS;
   const int64_t blocks = (int64_t)groups_x * g.ny * g.nzl;
-  XB_LAUNCH(c, k_push_second, (int)blocks, PUSH_THREADS, 0, g, s.bin_start, p[0], p[1], p[2], p[3], p[4], p[5], Eh, B, s.q / s.m, groups_x);
+  XB_LAUNCH(c, k_push_second<false>, (int)blocks, PUSH_THREADS, 0, g, s.bin_start, p[0], p[1], p[2], p[3], p[4], p[5], Eh, B, s.q / s.m, groups_x, 0.0,
+            nullptr);
   return 0;
 }
 
