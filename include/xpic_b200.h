@@ -153,7 +153,11 @@ int xb_operator_download(xb_ctx* ctx, double* coef);
 int xb_operator_upload(xb_ctx* ctx, const double* coef);
 /* Kernel variant switches for cross-checks: what = 0 selects the cell-block kernel of the moment
  * deposition (value 0: fp64 tensor-core DMMA, default; 1: scalar FMA); what = 1 the Esirkepov deposit
- * of ecsimcorr (0: atomic-free DMMA cell blocks, default; 1: per-particle global fp64 reductions). */
+ * of ecsimcorr (0: atomic-free DMMA cell blocks, default; 1: per-particle global fp64 reductions);
+ * what = 2: canonical particle order inside every bin after a sort when ids are not tracked
+ * (1: runs are bit-reproducible, costs one more pass over the particles; 0, default: keep the order
+ * in which the scatter's integer atomics resolved -- results then differ run to run at round-off level;
+ * with track_ids = 1 the order is always canonical, by id). */
 int xb_set_option(xb_ctx* ctx, int32_t what, int32_t value);
 /* Moments only at the present particle positions: fill_ecsim_current (ecsim/simulation.cpp:336-368). */
 int xb_deposit(xb_ctx* ctx);

@@ -653,6 +653,10 @@ int xb_set_option(xb_ctx* c, int32_t what, int32_t value)
     c->esirkepov_variant = value;
     return 0;
   }
+  if (what == 2) {
+    c->deterministic = value != 0;
+    return 0;
+  }
   XB_FAIL("xb_set_option: unknown option");
 }
 

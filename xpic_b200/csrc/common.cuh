@@ -118,6 +118,7 @@ struct xb_ctx {
   xb::Grid g;
   int device = 0;
   bool track_ids = false;
+  bool deterministic = false;  // canonical particle order inside every bin even without ids (costs one more pass)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   bool spmv_profile = false;

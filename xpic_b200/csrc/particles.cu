@@ -206,8 +206,11 @@ __global__ void k_scatter(int64_t n, const int32_t* __restrict__ key, int32_t* _
   if (sid) did[pos] = sid[i];
 }
 
-// canonical order inside a bin: ascending particle id (makes every later sum reproducible).
-// one thread per bin, insertion sort (bins hold ~ppc/8 particles).
+// canonical order inside a bin (makes every later sum reproducible run to run although the scatter
+// reserves slots with atomics): ascending particle id when ids are tracked, else ascending x
+// coordinate (ties would need bit-identical x inside one half cell).  One thread per bin, insertion
+// sort (bins hold ~ppc/8 particles).
+template <bool BY_ID>
 __global__ void k_order_bins(int64_t nbins, const int32_t* __restrict__ bin_start, double* __restrict__ p0, double* __restrict__ p1,
                              double* __restrict__ p2, double* __restrict__ p3, double* __restrict__ p4, double* __restrict__ p5,
                              uint64_t* __restrict__ id)
@@ -216,12 +219,13 @@ __global__ void k_order_bins(int64_t nbins, const int32_t* __restrict__ bin_star
   if (b >= nbins) return;
   const int32_t lo = bin_start[b], hi = bin_start[b + 1];
   for (int32_t i = lo + 1; i < hi; ++i) {
-    const uint64_t kid = id[i];
+    const uint64_t kid = BY_ID ? id[i] : 0;
+    const double a0 = p0[i];
     int32_t j = i - 1;
-    if (id[j] <= kid) continue;
-    const double a0 = p0[i], a1 = p1[i], a2 = p2[i], a3 = p3[i], a4 = p4[i], a5 = p5[i];
-    while (j >= lo && id[j] > kid) {
-      id[j + 1] = id[j];
+    if (BY_ID ? (id[j] <= kid) : (p0[j] <= a0)) continue;
+    const double a1 = p1[i], a2 = p2[i], a3 = p3[i], a4 = p4[i], a5 = p5[i];
+    while (j >= lo && (BY_ID ? (id[j] > kid) : (p0[j] > a0))) {
+      if (BY_ID) id[j + 1] = id[j];
       p0[j + 1] = p0[j];
       p1[j + 1] = p1[j];
       p2[j + 1] = p2[j];
@@ -230,7 +234,7 @@ __global__ void k_order_bins(int64_t nbins, const int32_t* __restrict__ bin_star
       p5[j + 1] = p5[j];
       --j;
     }
-    id[j + 1] = kid;
+    if (BY_ID) id[j + 1] = kid;
     p0[j + 1] = a0;
     p1[j + 1] = a1;
     p2[j + 1] = a2;
@@ -263,9 +267,12 @@ int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBu
                   d[1], d[2], d[3], d[4], d[5], did);
   }
   s.cur = 1 - s.cur;
-  if (c->track_ids) {
+  {
     double** q = s.p[s.cur];
-    XB_LAUNCH(c, k_order_bins, grid_for(c->nbins, 128), 128, 0, c->nbins, s.bin_start, q[0], q[1], q[2], q[3], q[4], q[5], s.id[s.cur]);
+    if (c->track_ids)
+      XB_LAUNCH(c, k_order_bins<true>, grid_for(c->nbins, 128), 128, 0, c->nbins, s.bin_start, q[0], q[1], q[2], q[3], q[4], q[5], s.id[s.cur]);
+    else if (c->deterministic)
+      XB_LAUNCH(c, k_order_bins<false>, grid_for(c->nbins, 128), 128, 0, c->nbins, s.bin_start, q[0], q[1], q[2], q[3], q[4], q[5], nullptr);
   }
   return 0;
 }
