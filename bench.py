@@ -283,6 +283,28 @@ def main():
                 "launches_timed": spmv_n, "avg_launch_ms": spmv_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "spmv_share_of_step": (spmv_ms / ms) if ms else None}
 
+    # ---- the other kernel families, timed in isolation on the resident state (CUDA events) --------
+    kernels = None
+    if world == 1 and args.scheme == "ecsim":
+        fp64_peak = float(os.environ.get("XPIC_FP64_TFLOPS", "37.0"))  # B200 vendor figure (vector = tensor fp64)
+        t_sort, t_dep, t_push, t_solve = (sim.kernel_bench(w, 3) for w in (0, 1, 2, 3))
+        npart = float(nparticles)
+        kernels = [
+            {"name": "re-binning (key pass + scatter, no move)", "ms": t_sort, "bound": "hbm", "achieved": 152.0 * npart / t_sort / 1e6, "unit": "GB/s",
+             "algorithmic": "152 B/particle: read r,v + key, write r,v"},
+            {"name": "moments (field records + DMMA cell blocks + row gather)", "ms": t_dep, "bound": "fp64", "achieved": 1200.0 * npart / t_dep / 1e9,
+             "unit": "TFLOP/s", "algorithmic": "1200 flop/particle (576 + 24 FMA); HBM: 48 + 192 B/particle, 2 x 10.6 KB + 3 KB per cell"},
+            {"name": "second push (tile-staged gather + Boris)", "ms": t_push, "bound": "hbm", "achieved": 72.0 * npart / t_push / 1e6, "unit": "GB/s",
+             "algorithmic": "72 B/particle: read r,v, write v"},
+            {"name": "field solve (GMRES + Chebyshev(M))", "ms": t_solve, "bound": "hbm", "achieved": None, "unit": "GB/s",
+             "algorithmic": f"{its} x (3000 B/cell SpMV + 5 x 144 B/cell Chebyshev + Gram-Schmidt)"},
+        ]
+        for k in kernels:
+            if k["achieved"] is not None:
+                k["frac"] = k["achieved"] / (peak if k["bound"] == "hbm" else fp64_peak * 1e0)
+        kernels[1]["peak"] = fp64_peak
+        kernels[1]["peak_source"] = "vendor fp64 figure for B200 (not measured); DMMA issue floor measured at 16 cycles / m8n8k4 / SM sub-partition"
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -297,7 +319,7 @@ def main():
                        "parallelism": f"z-slabs x{world}", "krylov": f"GMRES(30) rtol=atol=1e-7, Chebyshev(M) degree {precond} right preconditioner",
                        "krylov_iterations_per_step": its, "l2": "inputs (6.2 GB operator, 6.4 GB particles per GPU) exceed the 126 MB L2; no flush needed",
                        "stage_ms": {k: 1e3 * v for k, v in stage_s.items()}},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "boundary": "xb_step_host: E, B, B0 uploaded from pinned host buffers, E, B and kinetic energy downloaded every step; particles resident"},
             "gpu_launches": launches, "clocks": clocks,
