@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_particle_fields(Grid g, DepositA
   const int cy = row % g.ny, pl = row / g.ny;
   const int zl = pl + zl_off;
   const int cx0 = gx * TILE_CELLS, ncell = min(TILE_CELLS, g.nx - cx0);
-  load_field_tile(g, B, cx0, cy, zl, Bt, threadIdx.x, PF_THREADS);
+  load_field_tile<TILE_CELLS>(g, B, cx0, cy, zl, Bt, threadIdx.x, PF_THREADS);
   const int64_t cell0 = a.bin_cell0 + ((int64_t)pl * g.ny + cy) * g.nx + cx0;
   const int32_t p0 = a.bin_start[cell0 << 3], p1 = a.bin_start[(cell0 + ncell) << 3];
   __syncthreads();
@@ -254,9 +254,9 @@ __global__ void __launch_bounds__(PF_THREADS) k_particle_fields(Grid g, DepositA
     const double v[3] = {a.p[3][i], a.p[4][i], a.p[5][i]};
     Weights w;
     make_weights(g, a.p[0][i], a.p[1][i], a.p[2][i], a.zshift, w);
-    const TileIndex t = tile_index(w, cx0, cy, zl);
+    const TileIndex t = tile_index<TILE_CELLS>(w, cx0, cy, zl);
     double Bp[3], b[3];
-    gather_B_tile(Bt, w, t, Bp);
+    gather_B_tile<TILE_CELLS>(Bt, w, t, Bp);
 #pragma unroll
     for (int c = 0; c < 3; ++c) b[c] = Bp[c] * f;
     double vxb[3];

@@ -107,18 +107,25 @@ __device__ __forceinline__ void gather_B(const Grid& g, const double* __restrict
 }
 
 // ---- gathers from a shared-memory field tile --------------------------------------------------
-// A CTA that owns TILE_CELLS x-consecutive cells stages the nodes its particles can touch:
-// x in [cx0 - 1, cx0 + TILE_CELLS], y in [cy - 1, cy + 1], z in [cz - 1, cz + 1], 3 components.
-constexpr int TILE_CELLS = 4;
-constexpr int TILE_NX = TILE_CELLS + 2;
-constexpr int FIELD_TILE = 3 * 3 * 3 * TILE_NX;  // [c][z][y][x]
+// A CTA that owns NC x-consecutive cells stages the nodes its particles can touch:
+// x in [cx0 - 1, cx0 + NC], y in [cy - 1, cy + 1], z in [cz - 1, cz + 1], 3 components.
+constexpr int TILE_CELLS = 4;  // cells per CTA of the deposit-side kernels (= staging group)
 
+template <int NC>
+struct FieldTile {
+  static constexpr int NX = NC + 2;
+  static constexpr int SIZE = 3 * 3 * 3 * NX;  // [c][z][y][x]
+};
+constexpr int FIELD_TILE = FieldTile<TILE_CELLS>::SIZE;
+
+template <int NC>
 __device__ __forceinline__ void load_field_tile(const Grid& g, const double* __restrict__ F, int cx0, int cy, int zl, double* __restrict__ T, int tid,
                                                 int nthreads)
 {
-  for (int e = tid; e < FIELD_TILE; e += nthreads) {
-    const int x = e % TILE_NX, y = (e / TILE_NX) % 3, z = (e / (TILE_NX * 3)) % 3, c = e / (TILE_NX * 9);
-    T[e] = __ldg(&F[g.vidx(wrap1(cx0 - 1 + x, g.nx), wrap1(cy - 1 + y, g.ny), zl - 1 + z, c)]);
+  constexpr int NX = FieldTile<NC>::NX;
+  for (int e = tid; e < FieldTile<NC>::SIZE; e += nthreads) {
+    const int x = e % NX, y = (e / NX) % 3, z = (e / (NX * 3)) % 3, c = e / (NX * 9);
+    T[e] = __ldg(&F[g.vidx(wrapi(cx0 - 1 + x, g.nx), wrap1(cy - 1 + y, g.ny), zl - 1 + z, c)]);
   }
 }
 
@@ -126,22 +133,25 @@ struct TileIndex {
   int xn, xs, yn, ys, zn, zs;  // offsets of the particle's lower nodal / staggered node inside the tile
 };
 
+template <int NC>
 __device__ __forceinline__ TileIndex tile_index(const Weights& w, int cx0, int cy, int zl)
 {
+  constexpr int NX = FieldTile<NC>::NX;
   TileIndex t;
   t.xn = w.in[0] - (cx0 - 1);
   t.xs = w.is[0] - (cx0 - 1);
-  t.yn = (w.in[1] - (cy - 1)) * TILE_NX;
-  t.ys = (w.is[1] - (cy - 1)) * TILE_NX;
-  t.zn = (w.in[2] - (zl - 1)) * (3 * TILE_NX);
-  t.zs = (w.is[2] - (zl - 1)) * (3 * TILE_NX);
+  t.yn = (w.in[1] - (cy - 1)) * NX;
+  t.ys = (w.is[1] - (cy - 1)) * NX;
+  t.zn = (w.in[2] - (zl - 1)) * (3 * NX);
+  t.zs = (w.is[2] - (zl - 1)) * (3 * NX);
   return t;
 }
 
+template <int NC>
 __device__ __forceinline__ void gather_E_tile(const double* __restrict__ T, const Weights& w, const TileIndex& t, double* Ep)
 {
   Ep[0] = Ep[1] = Ep[2] = 0.0;
-  constexpr int C = 9 * TILE_NX, Y = TILE_NX, Z = 3 * TILE_NX;
+  constexpr int NX = FieldTile<NC>::NX, C = 9 * NX, Y = NX, Z = 3 * NX;
 #pragma unroll
   for (int k = 0; k < 2; ++k)
 #pragma unroll
@@ -157,10 +167,11 @@ __device__ __forceinline__ void gather_E_tile(const double* __restrict__ T, cons
       }
 }
 
+template <int NC>
 __device__ __forceinline__ void gather_B_tile(const double* __restrict__ T, const Weights& w, const TileIndex& t, double* Bp)
 {
   Bp[0] = Bp[1] = Bp[2] = 0.0;
-  constexpr int C = 9 * TILE_NX, Y = TILE_NX, Z = 3 * TILE_NX;
+  constexpr int NX = FieldTile<NC>::NX, C = 9 * NX, Y = NX, Z = 3 * NX;
 #pragma unroll
   for (int k = 0; k < 2; ++k)
 #pragma unroll

@@ -366,10 +366,11 @@ int particles_generate(xb_ctx* c, Species& s, int64_t total, const double* T, ui
 // ---------------------------------------------------------------------------------------------
 // second push (ecsim): gather E^{n+1/2}, B^n at the particle, Boris update of v
 // ---------------------------------------------------------------------------------------------
-// One CTA per group of 4 x-consecutive cells: the 54 nodes x 3 components of E and of B its particles
-// can touch are staged in shared memory once, so the 48 gathers per particle are shared-memory
-// reads and HBM sees only the particle stream (72 B / particle).
-constexpr int PUSH_THREADS = 128;
+// One CTA per group of 16 x-consecutive cells: the 18 x 3 x 3 nodes x 3 components of E and of B
+// its particles can touch are staged in shared memory once, so the 48 gathers per particle are
+// shared-memory reads and HBM sees only the particle stream (72 B / particle).
+constexpr int PUSH_THREADS = 256;
+constexpr int PUSH_CELLS = 16;
 
 // WORK: also accumulate the predicted field work  q n/Np * (v_old + v_new)/2 . E_p  of ecsimcorr
 // (src/impls/ecsimcorr/particles.cpp:77-78), one partial per CTA (summed by a fixed tree afterwards)
@@ -380,12 +381,12 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_second(Grid g, const int3
                                                               const double* __restrict__ B, double qm, int groups_x, double qn_Np,
                                                               double* __restrict__ partial)
 {
-  __shared__ double Et[FIELD_TILE], Bt[FIELD_TILE];
+  __shared__ double Et[FieldTile<PUSH_CELLS>::SIZE], Bt[FieldTile<PUSH_CELLS>::SIZE];
   const int gx = blockIdx.x % groups_x, row = blockIdx.x / groups_x;  // row = zl * ny + cy
   const int cy = row % g.ny, zl = row / g.ny;
-  const int cx0 = gx * TILE_CELLS, ncell = min(TILE_CELLS, g.nx - cx0);
-  load_field_tile(g, E, cx0, cy, zl, Et, threadIdx.x, PUSH_THREADS);
-  load_field_tile(g, B, cx0, cy, zl, Bt, threadIdx.x, PUSH_THREADS);
+  const int cx0 = gx * PUSH_CELLS, ncell = min(PUSH_CELLS, g.nx - cx0);
+  load_field_tile<PUSH_CELLS>(g, E, cx0, cy, zl, Et, threadIdx.x, PUSH_THREADS);
+  load_field_tile<PUSH_CELLS>(g, B, cx0, cy, zl, Bt, threadIdx.x, PUSH_THREADS);
   const int64_t cell0 = ((int64_t)(zl + 1) * g.ny + cy) * g.nx + cx0;  // bin plane = zl + 1
   const int32_t p0 = bin_start[cell0 << 3], p1 = bin_start[(cell0 + ncell) << 3];
   __syncthreads();
@@ -393,10 +394,10 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_second(Grid g, const int3
   for (int32_t i = p0 + threadIdx.x; i < p1; i += PUSH_THREADS) {
     Weights w;
     make_weights(g, x[i], y[i], z[i], 0, w);
-    const TileIndex t = tile_index(w, cx0, cy, zl);
+    const TileIndex t = tile_index<PUSH_CELLS>(w, cx0, cy, zl);
     double Ep[3], Bp[3];
-    gather_E_tile(Et, w, t, Ep);
-    gather_B_tile(Bt, w, t, Bp);
+    gather_E_tile<PUSH_CELLS>(Et, w, t, Ep);
+    gather_B_tile<PUSH_CELLS>(Bt, w, t, Bp);
     const double vo[3] = {vx[i], vy[i], vz[i]};
     double v[3] = {vo[0], vo[1], vo[2]};
     boris_update_vEB(g.dt, qm, Ep, Bp, v);
@@ -446,7 +447,7 @@ int push_second_work(xb_ctx* c, Species& s, const double* Eh, const double* B, d
   const Grid& g = c->g;
   if (!s.sorted) XB_FAIL("push_second: particles are not sorted");
   double** p = s.p[s.cur];
-  const int groups_x = (g.nx + TILE_CELLS - 1) / TILE_CELLS;
+  const int groups_x = (g.nx + PUSH_CELLS - 1) / PUSH_CELLS;
   const int64_t blocks = (int64_t)groups_x * g.ny * g.nzl;
   if (blocks > g.ntot) XB_FAIL("push_second: partial buffer too small");
   XB_LAUNCH(c, k_push_second<true>, (int)blocks, PUSH_THREADS, 0, g, s.bin_start, p[0], p[1], p[2], p[3], p[4], p[5], Eh, B, s.q / s.m, groups_x,
@@ -461,7 +462,7 @@ int push_second(xb_ctx* c, Species& s, const double* Eh, const double* B)
   if (!s.sorted) XB_FAIL("push_second: particles are not sorted");
   const Grid& g = c->g;
   double** p = s.p[s.cur];
-  const int groups_x = (g.nx + TILE_CELLS - 1) / TILE_CELLS;
+  const int groups_x = (g.nx + PUSH_CELLS - 1) / PUSH_CELLS;
   const int64_t blocks = (int64_t)groups_x * g.ny * g.nzl;
   XB_LAUNCH(c, k_push_second<false>, (int)blocks, PUSH_THREADS, 0, g, s.bin_start, p[0], p[1], p[2], p[3], p[4], p[5], Eh, B, s.q / s.m, groups_x, 0.0,
             nullptr);
