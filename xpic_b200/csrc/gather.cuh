@@ -202,6 +202,13 @@ __device__ __forceinline__ double wrap_coord(double s, double L)
   return s;
 }
 
+// r + v * dtm followed by the periodic wrap; unfused multiply and add with explicit rounding so that the
+// key pass and the scatter pass, which both evaluate it, get the same bits
+__device__ __forceinline__ double moved_coord(double r, double v, double dtm, double L)
+{
+  return wrap_coord(dtm != 0.0 ? __dadd_rn(r, __dmul_rn(v, dtm)) : r, L);
+}
+
 // bin plane of a (wrapped) z: 1..nzl inside the slab, 0 / nzl + 1 for the neighbour below / above
 __device__ __forceinline__ int slab_plane(const Grid& g, double pz)
 {

@@ -23,7 +23,8 @@
 
 namespace xb {
 
-int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBuffers* arrivals, int64_t n_from_down, int64_t n_from_up);  // particles.cu
+int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBuffers* arrivals, int64_t n_from_down, int64_t n_from_up,
+                          double dt_move);  // particles.cu
 int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* bin_start, int64_t bin_cell0, int64_t ncells, int64_t stage_cell0,
                   int zshift, double* rec, int64_t rec_stride, int64_t nparticles);  // deposit.cu
 
@@ -83,15 +84,9 @@ __global__ void k_move_key_slab(Grid g, int64_t n, double* __restrict__ x, doubl
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double px = x[i], py = y[i], pz = z[i];
-  if (dtm != 0.0) {
-    px += vx[i] * dtm;
-    py += vy[i] * dtm;
-    pz += vz[i] * dtm;
-  }
-  px = wrap_coord(px, g.Lx);
-  py = wrap_coord(py, g.Ly);
-  pz = wrap_coord(pz, g.Lz);
+  const double px = moved_coord(x[i], dtm != 0.0 ? vx[i] : 0.0, dtm, g.Lx);
+  const double py = moved_coord(y[i], dtm != 0.0 ? vy[i] : 0.0, dtm, g.Ly);
+  const double pz = moved_coord(z[i], dtm != 0.0 ? vz[i] : 0.0, dtm, g.Lz);
   x[i] = px;
   y[i] = py;
   z[i] = pz;
@@ -176,7 +171,7 @@ int migrate_and_sort(xb_ctx* c, Species& s, double dt_move)
     XB_LAUNCH(c, k_key_arrivals, (int)((from_down + 255) / 256), 256, 0, g, from_down, m.recv[0][0], m.recv[0][1], m.recv[0][2], m.recv_key[0], c->hist, bad);
   if (from_up > 0)
     XB_LAUNCH(c, k_key_arrivals, (int)((from_up + 255) / 256), 256, 0, g, from_up, m.recv[1][0], m.recv[1][1], m.recv[1][2], m.recv_key[1], c->hist, bad);
-  XB_CHECK(sort_scan_and_scatter(c, s, n, &m, from_down, from_up));
+  XB_CHECK(sort_scan_and_scatter(c, s, n, &m, from_down, from_up, 0.0));  // k_move_key_slab already stored the moved positions
   s.count = n - to_down - to_up + from_down + from_up;
   int nbad = 0;
   XB_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

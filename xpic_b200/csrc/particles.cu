@@ -59,24 +59,17 @@ void species_free(Species& s)
 // ---------------------------------------------------------------------------------------------
 // pass 1: r += v * dtm, periodic wrap (point.cpp:18-26), bin key, histogram
 // ---------------------------------------------------------------------------------------------
-__global__ void k_move_key(Grid g, int64_t n, double* __restrict__ x, double* __restrict__ y, double* __restrict__ z,
+// single-rank key pass: the moved position is NOT stored -- the scatter pass recomputes it with the
+// same moved_coord() while it copies the particle (saves 24 B / particle of HBM writes)
+__global__ void k_move_key(Grid g, int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                            const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz, double dtm,
                            int32_t* __restrict__ key, int32_t* __restrict__ hist)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double px = x[i], py = y[i], pz = z[i];
-  if (dtm != 0.0) {
-    px += vx[i] * dtm;
-    py += vy[i] * dtm;
-    pz += vz[i] * dtm;
-  }
-  px = wrap_coord(px, g.Lx);
-  py = wrap_coord(py, g.Ly);
-  pz = wrap_coord(pz, g.Lz);
-  x[i] = px;
-  y[i] = py;
-  z[i] = pz;
+  const double px = moved_coord(x[i], dtm != 0.0 ? vx[i] : 0.0, dtm, g.Lx);
+  const double py = moved_coord(y[i], dtm != 0.0 ? vy[i] : 0.0, dtm, g.Ly);
+  const double pz = moved_coord(z[i], dtm != 0.0 ? vz[i] : 0.0, dtm, g.Lz);
   const int32_t k = particle_key(g, px, py, pz, slab_plane(g, pz));
   key[i] = k;
   atomicAdd(&hist[k], 1);
@@ -183,7 +176,7 @@ __global__ void k_scatter(int64_t n, const int32_t* __restrict__ key, int32_t* _
                           const double* __restrict__ s1, const double* __restrict__ s2, const double* __restrict__ s3,
                           const double* __restrict__ s4, const double* __restrict__ s5, const uint64_t* __restrict__ sid,
                           double* __restrict__ d0, double* __restrict__ d1, double* __restrict__ d2, double* __restrict__ d3,
-                          double* __restrict__ d4, double* __restrict__ d5, uint64_t* __restrict__ did)
+                          double* __restrict__ d4, double* __restrict__ d5, uint64_t* __restrict__ did, double dtm, double Lx, double Ly, double Lz)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int32_t k = i < n ? key[i] : -1;
@@ -197,12 +190,13 @@ __global__ void k_scatter(int64_t n, const int32_t* __restrict__ key, int32_t* _
   if (lane == leader) base = atomicAdd(&cursor[k], __popc(peers));
   base = __shfl_sync(peers, base, leader);
   const int32_t pos = base + __popc(peers & ((1u << lane) - 1u));
-  d0[pos] = s0[i];
-  d1[pos] = s1[i];
-  d2[pos] = s2[i];
-  d3[pos] = s3[i];
-  d4[pos] = s4[i];
-  d5[pos] = s5[i];
+  const double vx = s3[i], vy = s4[i], vz = s5[i];
+  d0[pos] = moved_coord(s0[i], vx, dtm, Lx);  // the same bits the key pass binned (dtm = 0: plain copy + wrap)
+  d1[pos] = moved_coord(s1[i], vy, dtm, Ly);
+  d2[pos] = moved_coord(s2[i], vz, dtm, Lz);
+  d3[pos] = vx;
+  d4[pos] = vy;
+  d5[pos] = vz;
   if (sid) did[pos] = sid[i];
 }
 
@@ -246,8 +240,9 @@ __global__ void k_order_bins(int64_t nbins, const int32_t* __restrict__ bin_star
 
 // scan the histogram, scatter the local particles (and, in multi-rank runs, the arrivals) into the
 // other SoA buffer, canonicalise the order inside every bin when ids are tracked
-int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBuffers* arr, int64_t n_from_down, int64_t n_from_up)
+int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBuffers* arr, int64_t n_from_down, int64_t n_from_up, double dt_move)
 {
+  const Grid& g = c->g;
   const int ntiles = (int)((c->nbins + SCAN_TILE - 1) / SCAN_TILE);
   XB_LAUNCH(c, k_scan_tiles, ntiles, SCAN_THREADS, 0, c->hist, s.bin_start, c->nbins, c->scan_tmp);
   XB_LAUNCH(c, k_scan_sums, 1, 1024, 0, c->scan_tmp, ntiles, s.bin_start + c->nbins);
@@ -257,14 +252,14 @@ int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBu
   uint64_t* did = s.id[1 - s.cur];
   if (nlocal > 0)
     XB_LAUNCH(c, k_scatter, grid_for(nlocal), 256, 0, nlocal, s.key, c->cursor, p[0], p[1], p[2], p[3], p[4], p[5], s.id[s.cur], d[0], d[1], d[2], d[3],
-              d[4], d[5], did);
+              d[4], d[5], did, dt_move, g.Lx, g.Ly, g.Lz);
   if (arr) {
     const int64_t na[2] = {n_from_down, n_from_up};
     for (int k = 0; k < 2; ++k)
       if (na[k] > 0)
         XB_LAUNCH(c, k_scatter, grid_for(na[k]), 256, 0, na[k], arr->recv_key[k], c->cursor, arr->recv[k][0], arr->recv[k][1], arr->recv[k][2],
                   arr->recv[k][3], arr->recv[k][4], arr->recv[k][5], c->track_ids ? reinterpret_cast<const uint64_t*>(arr->recv[k][6]) : nullptr, d[0],
-                  d[1], d[2], d[3], d[4], d[5], did);
+                  d[1], d[2], d[3], d[4], d[5], did, 0.0, g.Lx, g.Ly, g.Lz);
   }
   s.cur = 1 - s.cur;
   {
@@ -285,7 +280,7 @@ int particles_sort(xb_ctx* c, Species& s, double dt_move)
   XB_CUDA(cudaMemsetAsync(c->hist, 0, sizeof(int32_t) * c->nbins, c->stream));
   double** p = s.p[s.cur];
   if (n > 0) XB_LAUNCH(c, k_move_key, grid_for(n), 256, 0, g, n, p[0], p[1], p[2], p[3], p[4], p[5], dt_move, s.key, c->hist);
-  XB_CHECK(sort_scan_and_scatter(c, s, n, nullptr, 0, 0));
+  XB_CHECK(sort_scan_and_scatter(c, s, n, nullptr, 0, 0, dt_move));
   s.sorted = true;
   return 0;
 }
