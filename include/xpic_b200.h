@@ -1,4 +1,4 @@
-/* xpic_b200.h -- C ABI of the B200-native ECSIM / ECSIMCorr step.
+/* xpic_b200.h -- C ABI of the B200-native ECSIM / ECSIMCorr / EC-CAPFIM step.
  *
  * xpic (vakurshakov/xpic) has no FFI boundary of its own: a scheme is a C++ subclass compiled
  * into libxpic.so.  This header is the seam a maintainer binds instead (INTEGRATION.md shows
@@ -36,13 +36,16 @@ typedef struct xb_grid {
   int32_t track_ids; /* 1: carry a 64-bit particle id (parity / diagnostics), 0: do not */
 } xb_grid;
 
-enum { XB_ECSIM = 0, XB_ECSIMCORR = 1 }; /* "Simulation" key, src/interfaces/simulation.cpp:169-178 */
+enum { XB_ECSIM = 0, XB_ECSIMCORR = 1, XB_ECCAPFIM = 2 }; /* "Simulation" key, src/interfaces/simulation.cpp:169-178 */
 
 /* Named vectors: Simulation::E,B,B0 (src/interfaces/simulation.h:33-45, get_named_vector :135-143),
  * ecsim Ep,currI (src/impls/ecsim/simulation.h:27-28), ecsimcorr Ec,currJe
  * (src/impls/ecsimcorr/simulation.h:16-17), per-sort Particles::currI / currJe
  * (src/impls/ecsim/particles.h:22, src/impls/ecsimcorr/particles.h:22). */
-enum { XB_E = 0, XB_B = 1, XB_B0 = 2, XB_EP = 3, XB_EC = 4, XB_CURRI = 5, XB_CURRJE = 6, XB_CURRI_SORT = 7, XB_CURRJE_SORT = 8 };
+enum { XB_E = 0, XB_B = 1, XB_B0 = 2, XB_EP = 3, XB_EC = 4, XB_CURRI = 5, XB_CURRJE = 6, XB_CURRI_SORT = 7, XB_CURRJE_SORT = 8,
+       /* eccapfim: Simulation::J, Particles::J and E_hk of the last residual evaluation
+        * (src/interfaces/simulation.h:36, src/interfaces/particles.h:41, src/impls/eccapfim/simulation.h:74) */
+       XB_J = 9, XB_J_SORT = 10, XB_EHK = 11 };
 
 /* Stages of timestep_implementation (src/impls/ecsim/simulation.cpp:145-155,
  * src/impls/ecsimcorr/simulation.cpp:21-32); same names as the PETSc log stages :495-508. */
@@ -159,6 +162,27 @@ int xb_operator_upload(xb_ctx* ctx, const double* coef);
  * in which the scatter's integer atomics resolved -- results then differ run to run at round-off level;
  * with track_ids = 1 the order is always canonical, by id). */
 int xb_set_option(xb_ctx* ctx, int32_t what, int32_t value);
+/* --- eccapfim (BASELINE config 5): xb_step / xb_stage with scheme XB_ECCAPFIM run
+ * eccapfim::Simulation::timestep_implementation (src/impls/eccapfim/simulation.cpp:36-44); stages
+ * XB_STAGE_CLEAR_SOURCES = init_iteration (:46-70), XB_STAGE_ADVANCE_FIELDS = calc_iteration (SNESSolve,
+ * :72-104; non-zero return when it does not converge, :102), XB_STAGE_FINAL_UPDATE = after_iteration (:106-129).
+ * SNESSetTolerances (simulation.cpp:384, defaults simulation.h:14-19) + the per-particle Crank-Nicolson
+ * tolerance and iteration cap (particles.cpp:99-101: 0.5 * atol, 30).  depth = Anderson history,
+ * cheb_degree = degree of the Chebyshev residual preconditioner (0 = plain fixed-point residual). */
+int xb_nonlinear_set(xb_ctx* ctx, double atol, double rtol, double stol, int32_t maxit, int32_t depth, int32_t cheb_degree, double particle_tol,
+                     int32_t particle_maxit);
+/* SNESGetIterationNumber / SNESGetNumberFunctionEvals / SNESGetConvergedReason and the averages the
+ * ConvergenceHistory diagnostic prints (src/impls/eccapfim/convergence_history.cpp:11-44). */
+int xb_nonlinear_info(xb_ctx* ctx, int32_t* iterations, int32_t* fevals, int32_t* reason, double* fnorm, double* avg_cn, double* avg_cells);
+/* SNESGetConvergenceHistory: |F| after every iteration of the last solve (length entries, <= capacity copied). */
+int xb_nonlinear_history(xb_ctx* ctx, double* out, int32_t capacity, int32_t* length);
+/* CUDA-event timing of the particle pass of every residual evaluation (the "form_current" event,
+ * simulation.cpp:180-192): returns the totals so far, then enable >= 0 resets and switches collecting. */
+int xb_nonlinear_profile(xb_ctx* ctx, int32_t enable, int64_t* evaluations, double* total_ms);
+/* F(x) of form_iteration (simulation.cpp:132-155) for host x at the present E^n, B^n and particles;
+ * XB_J / XB_J_SORT then hold the currents of that evaluation. */
+int xb_eccapfim_function(xb_ctx* ctx, const double* x, double* f);
+
 /* Moments only at the present particle positions: fill_ecsim_current (ecsim/simulation.cpp:336-368). */
 int xb_deposit(xb_ctx* ctx);
 /* Solve (L? + M) x = b for host vectors with the given solver slot (KSPSolve). */

@@ -12,8 +12,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "libxpic_oracle.so")
 
-ECSIM, ECSIMCORR = 0, 1
-FIELDS = {"E": 0, "B": 1, "B0": 2, "Ep": 3, "Ec": 4, "currI": 5, "currJe": 6, "currI_sort": 7, "currJe_sort": 8}
+ECSIM, ECSIMCORR, ECCAPFIM = 0, 1, 2
+FIELDS = {"E": 0, "B": 1, "B0": 2, "Ep": 3, "Ec": 4, "currI": 5, "currJe": 6, "currI_sort": 7, "currJe_sort": 8, "J": 9, "J_sort": 10, "Ehk": 11}
 SCALARS = {"energy": 0, "pred_w": 1, "corr_w": 2, "pred_dK": 3, "corr_dK": 4, "lambda_dK": 5, "energy_member": 6, "j_diff_norm": 7}
 
 
@@ -62,6 +62,14 @@ def lib():
         L.xo_interpolate.argtypes = [C.c_void_p, dp, dp, dp]
         L.xo_boris_update_vEB.argtypes = [C.c_double, C.c_double, dp, dp, dp]
         L.xo_esirkepov.argtypes = [C.c_void_p, dp, dp, C.c_double, dp]
+        L.xo_snes_set.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double]
+        L.xo_snes_set_particle_tol.argtypes = [C.c_void_p, C.c_double]
+        L.xo_snes_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), dp, dp]
+        L.xo_snes_history.restype = C.c_int
+        L.xo_snes_history.argtypes = [C.c_void_p, dp, C.c_int]
+        L.xo_eccapfim_function.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.xo_cell_traversal.restype = C.c_int
+        L.xo_cell_traversal.argtypes = [C.c_void_p, dp, dp, dp, C.c_int]
         _lib = L
     return _lib
 
@@ -135,6 +143,38 @@ class Oracle:
         it, rn, re = C.c_int(), C.c_double(), C.c_int()
         lib().xo_solver_info(self._h, which, C.byref(it), C.byref(rn), C.byref(re))
         return it.value, rn.value, re.value
+
+    def snes_set(self, atol=1e-7, rtol=1e-7, stol=1e-7, maxit=1000, precond=0, shift=0.0):
+        """eccapfim nonlinear solver (reference defaults: eccapfim/simulation.h:14-19).  precond=1 solves
+        P F = 0 with P = ((1 + shift) I + dt^2/4 curl curl)^-1 -- not in the reference."""
+        lib().xo_snes_set(self._h, atol, rtol, stol, maxit, int(precond), float(shift))
+
+    def snes_set_particle_tol(self, tol=0.5e-7):
+        lib().xo_snes_set_particle_tol(self._h, float(tol))
+
+    def snes_info(self):
+        it, fe, re = C.c_int(), C.c_int(), C.c_int()
+        ai, ac = C.c_double(), C.c_double()
+        lib().xo_snes_info(self._h, C.byref(it), C.byref(fe), C.byref(re), C.byref(ai), C.byref(ac))
+        return {"iterations": it.value, "fevals": fe.value, "reason": re.value, "avg_cn": ai.value, "avg_cells": ac.value}
+
+    def snes_history(self):
+        buf = np.empty(2048)
+        n = lib().xo_snes_history(self._h, _dp(buf), buf.size)
+        return buf[: min(n, buf.size)].copy()
+
+    def eccapfim_function(self, x, prepare=True):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.empty(self.n3)
+        lib().xo_eccapfim_function(self._h, _dp(x), _dp(f), int(prepare))
+        return f
+
+    def cell_traversal(self, end, start):
+        e = np.ascontiguousarray(end, dtype=np.float64)
+        s0 = np.ascontiguousarray(start, dtype=np.float64)
+        out = np.empty((64, 3))
+        n = lib().xo_cell_traversal(self._h, _dp(e), _dp(s0), _dp(out), 64)
+        return out[:n].copy()
 
     def scalar(self, name, sid=0):
         return lib().xo_scalar(self._h, sid, SCALARS[name])

@@ -19,10 +19,13 @@
 // src/impls/ecsim/particles.cpp:41-47,137-142).  Every routine cites the reference
 // file:line (relative to /root/reference) whose arithmetic it follows.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <limits>
 #include <list>
 #include <random>
 #include <vector>
@@ -61,6 +64,27 @@ struct Species {
   std::vector<double> currI, currJe;      // per-sort global currents
   double energy = 0, pred_w = 0, corr_w = 0, pred_dK = 0, corr_dK = 0, lambda_dK = 0;
   uint64_t next_id = 0;
+  // eccapfim (src/impls/eccapfim/particles.h:31-37)
+  std::vector<std::vector<Point>> previous_storage;
+  std::vector<double> J;
+  int64_t size = 0;
+  double avgit = 0, avgcell = 0;
+};
+
+// SNES NGMRES state: tolerances src/impls/eccapfim/simulation.h:14-19, the rest PETSc's
+// SNESNGMRES defaults (third party, un-vendored: src/snes/impls/ngmres/{snesngmres,ngmresfunc}.c)
+struct Ngmres {
+  double atol = 1e-7, rtol = 1e-7, stol = 1e-7;
+  int maxit = 1000;
+  int msize = 30, restart_it = 2;
+  double gammaA = 2.0, gammaC = 2.0, epsilonB = 0.1, deltaB = 0.9;
+  // NOT in the reference: solve P F(x) = 0 with the fixed linear operator
+  // P = ((1 + shift) I + 1/4 dt^2 curl curl)^-1 (tests use it to reach tight tolerances quickly)
+  int precond = 0;
+  double shift = 0.0;
+  double cn_tol = 0.5 * 1e-7;  // per-particle Picard tolerance (particles.cpp:100-101); tests may tighten it
+  int iterations = 0, fevals = 0, reason = 0;
+  std::vector<double> hist;
 };
 
 struct Sim {
@@ -76,6 +100,8 @@ struct Sim {
   std::mt19937 gen;  // src/utils/random_generator.h:20-27 (default seed 5489)
   std::uniform_real_distribution<double> uni{0.0, 1.0};
   double last_j_diff_norm = 0.0;
+  std::vector<double> Ehk, J;  // eccapfim: E^{n+1/2,k} and the total current of the last evaluation
+  Ngmres snes;
 
   inline int wrap(int i, int a) const
   {
@@ -766,6 +792,553 @@ void step_ecsimcorr(Sim& s)  // ecsimcorr/simulation.cpp:21-32
   final_update_fields(s);
 }
 
+// =============================================================================================
+// eccapfim: fully implicit, energy- and charge-conserving scheme (BASELINE config 5)
+//   src/impls/eccapfim/simulation.cpp:36-241, particles.cpp:30-181, cell_traversal.cpp:3-77,
+//   src/algorithms/implicit_esirkepov.cpp:11-117, src/utils/shape.cpp:3-107
+// Golden: tests/eccapfim/expected/eccapfim_ex1 (copy under tests/golden/eccapfim_ex1); its
+// convergence_history.txt records PETSc's NGMRES residual history, so the nonlinear solver below
+// restates SNESSolve_NGMRES (PETSc is un-vendored and un-pinned; defaults of release 3.22) and is
+// checked against that history.
+// ---------------------------------------------------------------------------------------------
+using V3 = std::array<double, 3>;
+
+// src/impls/eccapfim/cell_traversal.cpp:3-77 (Amanatides & Woo on the half-shifted lattice)
+void cell_traversal(const Sim& s, const V3& end, const V3& start, std::vector<V3>& points)
+{
+  points.clear();
+  int curr[3], last[3];
+  for (int a = 0; a < 3; ++a) {
+    curr[a] = (int)std::round(start[a] / s.d[a]);
+    last[a] = (int)std::round(end[a] / s.d[a]);
+  }
+  if (curr[0] == last[0] && curr[1] == last[1] && curr[2] == last[2]) {
+    points.push_back(start);
+    points.push_back(end);
+    return;
+  }
+  static const double maxv = std::numeric_limits<double>::max();
+  double dir[3], next[3], t3[3], dt3[3];
+  int sg[3];
+  for (int a = 0; a < 3; ++a) {
+    dir[a] = end[a] - start[a];
+    sg[a] = dir[a] > 0 ? 1 : -1;
+    next[a] = (curr[a] + sg[a] * 0.5) * s.d[a];
+    t3[a] = (dir[a] != 0) ? (next[a] - start[a]) / dir[a] : maxv;
+    dt3[a] = (dir[a] != 0) ? s.d[a] / dir[a] * sg[a] : 0.0;
+  }
+  points.push_back(start);
+  int guard = 0;
+  while (!(curr[0] == last[0] && curr[1] == last[1] && curr[2] == last[2]) && ++guard < 256) {
+    int a;
+    if (t3[0] < t3[1])
+      a = (t3[0] < t3[2]) ? 0 : 2;
+    else
+      a = (t3[1] < t3[2]) ? 1 : 2;
+    const double t = t3[a];
+    curr[a] += sg[a];
+    t3[a] += dt3[a];
+    points.push_back({start[0] + dir[0] * t, start[1] + dir[1] * t, start[2] + dir[2] * t});
+  }
+  points.push_back(end);
+}
+
+// ImplicitEsirkepov::Shape (src/algorithms/implicit_esirkepov.h:18-53, .cpp:11-60)
+struct CapShape {
+  int start[3];
+  double cache[54];
+};
+
+inline double sfunc_1(double x) { return 1.0 - std::abs(x); }
+inline double sfunc_21(double x) { x = std::abs(x); return (0.75 - x * x); }
+inline double sfunc_22(double x) { x = std::abs(x); return 0.5 * ((1.5 - x) * (1.5 - x)); }
+inline double sfunc_2(int j, double x) { return j == 1 ? sfunc_21(x) : sfunc_22(x); }
+
+void cap_shape_setup(const Sim& s, const V3& rn, const V3& r0, CapShape& sh)
+{
+  double prn[3], pr0[3], prh[3], gc[3], gv[3];
+  for (int a = 0; a < 3; ++a) {
+    prn[a] = rn[a] / s.d[a];
+    pr0[a] = r0[a] / s.d[a];
+    prh[a] = 0.5 * (prn[a] + pr0[a]);
+    gc[a] = std::round(prh[a]);
+    sh.start[a] = (int)gc[a] - 1;
+    gv[a] = gc[a] + 0.5;
+  }
+  static constexpr double sixth = 1.0 / 6.0;
+  int m = 0;
+  for (int cx = 0; cx < 3; ++cx) {
+    const int cy = (cx + 1) % 3, cz = (cx + 2) % 3;
+    for (int i = 0; i < 2; ++i) {
+      const double shx = sixth * sfunc_1(gv[cx] + (i - 1) - prh[cx]);
+      for (int j = 0; j < 3; ++j) {
+        const double sny = sfunc_2(j, gc[cy] + (j - 1) - prn[cy]);
+        const double s0y = sfunc_2(j, gc[cy] + (j - 1) - pr0[cy]);
+        for (int k = 0; k < 3; ++k) {
+          const double snz = sfunc_2(k, gc[cz] + (k - 1) - prn[cz]);
+          const double s0z = sfunc_2(k, gc[cz] + (k - 1) - pr0[cz]);
+          sh.cache[m++] = shx * (sny * (2 * snz + s0z) + s0y * (2 * s0z + snz));
+        }
+      }
+    }
+  }
+}
+
+// Shape::setup(r) with the global 2nd-order form factor (src/utils/shape.cpp:34-45,81-107,
+// src/constants.h:4) + SimpleInterpolation::process for B (simple_interpolation.cpp:8-38,
+// Shape::magnetic shape.h:66-73)
+void interpolate_B_s2(const Sim& s, const std::vector<double>& Bg, const V3& r, double* Bp)
+{
+  constexpr double radius = 1.5;
+  int start[3], size[3];
+  double pr[3];
+  for (int a = 0; a < 3; ++a) {
+    pr[a] = r[a] / s.d[a];
+    start[a] = (int)std::round(pr[a] - radius);
+    size[a] = (int)std::floor(pr[a] + radius) + 1 - start[a];
+  }
+  const int n = size[0] * size[1] * size[2];
+  for (int i = 0; i < n; ++i) {
+    const int ix = i % size[0], iy = (i / size[0]) % size[1], iz = (i / size[0]) / size[1];
+    double gx = (double)(start[0] + ix), gy = (double)(start[1] + iy), gz = (double)(start[2] + iz);
+    const double nox = spline2(pr[0] - gx), noy = spline2(pr[1] - gy), noz = spline2(pr[2] - gz);
+    gx += 0.5; gy += 0.5; gz += 0.5;
+    const double shx = spline2(pr[0] - gx), shy = spline2(pr[1] - gy), shz = spline2(pr[2] - gz);
+    const int64_t o = s.vidx(start[0] + ix, start[1] + iy, start[2] + iz, 0);
+    Bp[0] += Bg[o + 0] * (shz * shy * nox);
+    Bp[1] += Bg[o + 1] * (shz * noy * shx);
+    Bp[2] += Bg[o + 2] * (noz * shy * shx);
+  }
+}
+
+// ImplicitEsirkepov::interpolate (implicit_esirkepov.cpp:63-91): adds into Ep, Bp
+void cap_interpolate(const Sim& s, const std::vector<double>& Eg, const std::vector<double>& Bg, double* Ep, double* Bp, const V3& rn, const V3& r0)
+{
+  const V3 rh = {0.5 * (rn[0] + r0[0]), 0.5 * (rn[1] + r0[1]), 0.5 * (rn[2] + r0[2])};
+  interpolate_B_s2(s, Bg, rh, Bp);
+  CapShape sh;
+  cap_shape_setup(s, rn, r0, sh);
+  int i[3], m = 0;
+  for (int cx = 0; cx < 3; ++cx) {
+    const int cy = (cx + 1) % 3, cz = (cx + 2) % 3;
+    for (i[cx] = 0; i[cx] < 2; i[cx]++)
+      for (i[cy] = 0; i[cy] < 3; i[cy]++)
+        for (i[cz] = 0; i[cz] < 3; i[cz]++)
+          Ep[cx] += Eg[s.vidx(sh.start[0] + i[0], sh.start[1] + i[1], sh.start[2] + i[2], cx)] * sh.cache[m++];
+  }
+}
+
+// ImplicitEsirkepov::decompose (implicit_esirkepov.cpp:93-117)
+void cap_decompose(const Sim& s, std::vector<double>& Jg, double alpha, const double* v, const V3& rn, const V3& r0)
+{
+  CapShape sh;
+  cap_shape_setup(s, rn, r0, sh);
+  int i[3], m = 0;
+  for (int cx = 0; cx < 3; ++cx) {
+    const int cy = (cx + 1) % 3, cz = (cx + 2) % 3;
+    for (i[cx] = 0; i[cx] < 2; i[cx]++)
+      for (i[cy] = 0; i[cy] < 3; i[cy]++)
+        for (i[cz] = 0; i[cz] < 3; i[cz]++) {
+          double& dst = Jg[s.vidx(sh.start[0] + i[0], sh.start[1] + i[1], sh.start[2] + i[2], cx)];
+          const double add = alpha * v[cx] * sh.cache[m++];
+#pragma omp atomic update
+          dst += add;
+        }
+  }
+}
+
+inline double len3(const V3& a, const V3& b) { return std::hypot(a[0] - b[0], a[1] - b[1], a[2] - b[2]); }  // vector3.h:160-164
+
+// eccapfim::Particles::form_iteration for one particle (particles.cpp:73-176).  `curr` enters as
+// the start-of-step state and leaves as (x^{n+1,k}, v^{n+1,k}); returns Picard iterations and
+// traversed segments through it / ncell.
+void cap_push_particle(const Sim& s, const Species& sp, const std::vector<double>& Eg, const std::vector<double>& Bg, std::vector<double>& Jg, Point& curr,
+                       double& it_sum, double& cell_sum, std::vector<V3>& coords)
+{
+  const double q = sp.q, m = sp.m, mpw = sp.n / sp.Np, dt = s.dt;
+  const double maxv = std::numeric_limits<double>::max();
+  // :39-45 single box: start = 0, end = N
+  const double lo[3] = {(0 - 0.5) * s.d[0], (0 - 0.5) * s.d[1], (0 - 0.5) * s.d[2]};
+  const double hi[3] = {(s.N[0] + 0.5) * s.d[0], (s.N[1] + 0.5) * s.d[1], (s.N[2] + 0.5) * s.d[2]};
+  auto process_bound = [&](double vh, double x, double xb, double xe) {  // :49-56
+    if (vh > 0 && std::abs(xe - x) > 1e-7) return (xe - x) / vh;
+    else if (vh < 0 && std::abs(xb - x) > 1e-7) return (xb - x) / vh;
+    else return maxv;
+  };
+  Point tmp = curr;
+  Point& pn = curr;
+  Point& p0 = tmp;
+  double tau = 0, dtau = 0;
+  for (; tau < dt; tau += dtau) {
+    double vh[3];
+    for (int c = 0; c < 3; ++c) vh[c] = 0.5 * (pn.p[c] + p0.p[c]);
+    const double dtx = process_bound(vh[0], p0.r[0], lo[0], hi[0]);
+    const double dty = process_bound(vh[1], p0.r[1], lo[1], hi[1]);
+    const double dtz = process_bound(vh[2], p0.r[2], lo[2], hi[2]);
+    dtau = std::min({dt - tau, dtx, dty, dtz});
+    const double a0 = q * mpw;
+    const double alpha = 0.5 * dtau * (q / m);
+    const int cn_maxit = 30;
+    const double cn_atol = s.snes.cn_tol, cn_rtol = s.snes.cn_tol;  // 0.5 * eccapfim::atol (:100-101)
+    int it = 0;
+    double Ep[3], Bp[3];
+    auto set_fields = [&] {  // :109-127
+      Ep[0] = Ep[1] = Ep[2] = Bp[0] = Bp[1] = Bp[2] = 0.0;
+      const V3 rn = {pn.r[0], pn.r[1], pn.r[2]}, r0 = {p0.r[0], p0.r[1], p0.r[2]};
+      const double d = len3(rn, r0);
+      cell_traversal(s, rn, r0, coords);
+      for (size_t k = 1; k < coords.size(); ++k) {
+        const double ds = len3(coords[k], coords[k - 1]);
+        const double bs = (d > 0 ? ds / d : 1.0);
+        double Es[3] = {0, 0, 0}, Bs[3] = {0, 0, 0};
+        cap_interpolate(s, Eg, Bg, Es, Bs, coords[k], coords[k - 1]);
+        for (int c = 0; c < 3; ++c) {
+          Ep[c] += Es[c] * bs;
+          Bp[c] += Bs[c] * bs;
+        }
+      }
+    };
+    auto get_residue = [&] {  // :129-131
+      double vxb[3];
+      cross(vh, Bp, vxb);
+      const double f = dtau * q / m;
+      return std::hypot((pn.p[0] - p0.p[0]) - f * (Ep[0] + vxb[0]), (pn.p[1] - p0.p[1]) - f * (Ep[1] + vxb[1]), (pn.p[2] - p0.p[2]) - f * (Ep[2] + vxb[2]));
+    };
+    set_fields();
+    double rn_, r0_;
+    rn_ = r0_ = get_residue();
+    for (; rn_ > cn_atol + cn_rtol * r0_ && it < cn_maxit; it++) {  // :136-148
+      double a[3], b[3], w[3], wxb[3];
+      for (int c = 0; c < 3; ++c) {
+        a[c] = alpha * Ep[c];
+        b[c] = alpha * Bp[c];
+        w[c] = p0.p[c] + a[c];
+      }
+      cross(w, b, wxb);
+      const double wb = dot(w, b), den = 1.0 + dot(b, b);
+      for (int c = 0; c < 3; ++c) vh[c] = ((w[c] + wxb[c]) + b[c] * wb) / den;
+      for (int c = 0; c < 3; ++c) {
+        pn.r[c] = p0.r[c] + dtau * vh[c];
+        pn.p[c] = 2.0 * vh[c] - p0.p[c];
+      }
+      set_fields();
+      rn_ = get_residue();
+    }
+    it_sum += (double)it;
+    cell_sum += (double)(coords.size() - 1);
+    {  // :153-163
+      const V3 rn = {pn.r[0], pn.r[1], pn.r[2]}, r0 = {p0.r[0], p0.r[1], p0.r[2]};
+      const double d = len3(rn, r0);
+      cell_traversal(s, rn, r0, coords);
+      for (size_t k = 1; k < coords.size(); ++k) {
+        const double ds = len3(coords[k], coords[k - 1]);
+        const double bs = (d > 0 ? ds / d : 1.0);
+        cap_decompose(s, Jg, a0 * bs * (dtau / dt), vh, coords[k], coords[k - 1]);
+      }
+    }
+    bool reset = false;  // :58-68,165-171
+    for (int a = 0; a < 3; ++a) {
+      double& x = pn.r[a];
+      if (x < 0.0) { x = s.L[a] - (0.0 - x); reset = true; }
+      else if (x > s.L[a]) { x = 0.0 + (x - s.L[a]); reset = true; }
+    }
+    if (reset) p0 = pn;
+  }
+}
+
+// eccapfim::Simulation::form_iteration: clear_sources, form_current, form_function
+// (simulation.cpp:132-241): vf = F(vx)
+void cap_form_function(Sim& s, const double* vx, double* vf)
+{
+  std::copy(vx, vx + s.n3, s.Ehk.begin());
+  std::fill(s.J.begin(), s.J.end(), 0.0);
+  for (auto& sp : s.sorts) {
+    std::fill(sp.J.begin(), sp.J.end(), 0.0);
+    double it_sum = 0, cell_sum = 0;
+#pragma omp parallel num_threads(g_threads) reduction(+ : it_sum, cell_sum)
+    {
+      std::vector<V3> coords;
+#pragma omp for schedule(dynamic, 16)
+      for (int64_t g = 0; g < s.nc; ++g) {
+        int i = 0;
+        for (auto& curr : sp.storage[g]) {
+          curr = sp.previous_storage[g][i++];
+          cap_push_particle(s, sp, s.Ehk, s.B, sp.J, curr, it_sum, cell_sum, coords);
+        }
+      }
+    }
+    sp.avgit = sp.size ? it_sum / sp.size : 0.0;
+    sp.avgcell = sp.size ? cell_sum / sp.size : 0.0;
+    for (int64_t i = 0; i < s.n3; ++i) s.J[i] += sp.J[i];
+  }
+  // form_function :228-236 with matM = +1/4 dt^2 C-C+, rotB = -1/2 dt C- (:349-351)
+  std::vector<double> t1(s.n3), t2(s.n3), cb(s.n3);
+  curl(s, true, s.Ehk.data(), t1.data());
+  curl(s, false, t1.data(), t2.data());
+  curl(s, false, s.B.data(), cb.data());
+  const double dt = s.dt;
+  for (int64_t i = 0; i < s.n3; ++i) {
+    double f = s.Ehk[i];
+    f += (0.25 * dt * dt) * t2[i];
+    f += -1 * s.E[i];
+    f += (0.5 * dt) * s.J[i];
+    f += (-0.5 * dt) * cb[i];
+    vf[i] = f;
+  }
+  ++s.snes.fevals;
+}
+
+// P r, P = ((1 + shift) I + 1/4 dt^2 C-C+)^-1 by conjugate gradients (oracle-only helper)
+void cap_precondition(Sim& s, const double* r, double* z)
+{
+  const int64_t n = s.n3;
+  const double sh = 1.0 + s.snes.shift, c = 0.25 * s.dt * s.dt;
+  std::vector<double> res(r, r + n), p(r, r + n), t1(n), Ap(n);
+  std::fill(z, z + n, 0.0);
+  double rr = 0;
+  for (int64_t i = 0; i < n; ++i) rr += res[i] * res[i];
+  const double stop = rr * 1e-30;
+  for (int it = 0; it < 2000 && rr > stop && rr > 0; ++it) {
+    curl(s, true, p.data(), t1.data());
+    curl(s, false, t1.data(), Ap.data());
+    double pAp = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      Ap[i] = sh * p[i] + c * Ap[i];
+      pAp += p[i] * Ap[i];
+    }
+    const double al = rr / pAp;
+    double rn = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      z[i] += al * p[i];
+      res[i] -= al * Ap[i];
+      rn += res[i] * res[i];
+    }
+    const double be = rn / rr;
+    rr = rn;
+    for (int64_t i = 0; i < n; ++i) p[i] = res[i] + be * p[i];
+  }
+}
+
+// minimum-norm least squares  min |H a - b|  through a one-sided Jacobi SVD, singular values below
+// eps * s_max dropped (LAPACK gelss with rcond = -1, as SNESNGMRESFormCombinedSolution_Private calls it)
+void lstsq_svd(int l, std::vector<double> H /* l x l, H[i*l+j] */, std::vector<double>& b)
+{
+  std::vector<double> V(l * l, 0.0);
+  for (int i = 0; i < l; ++i) V[i * l + i] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0;
+    for (int p = 0; p < l - 1; ++p)
+      for (int q = p + 1; q < l; ++q) {
+        double al = 0, be = 0, ga = 0;
+        for (int i = 0; i < l; ++i) {
+          al += H[i * l + p] * H[i * l + p];
+          be += H[i * l + q] * H[i * l + q];
+          ga += H[i * l + p] * H[i * l + q];
+        }
+        if (ga == 0.0 || std::abs(ga) <= 1e-17 * std::sqrt(al * be)) continue;
+        off = std::max(off, std::abs(ga) / std::sqrt(al * be));
+        const double zeta = (be - al) / (2.0 * ga);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::abs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
+        for (int i = 0; i < l; ++i) {
+          const double hp = H[i * l + p], hq = H[i * l + q];
+          H[i * l + p] = cs * hp - sn * hq;
+          H[i * l + q] = sn * hp + cs * hq;
+          const double vp = V[i * l + p], vq = V[i * l + q];
+          V[i * l + p] = cs * vp - sn * vq;
+          V[i * l + q] = sn * vp + cs * vq;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  std::vector<double> sig(l), y(l, 0.0);
+  double smax = 0;
+  for (int j = 0; j < l; ++j) {
+    double nn = 0;
+    for (int i = 0; i < l; ++i) nn += H[i * l + j] * H[i * l + j];
+    sig[j] = std::sqrt(nn);
+    smax = std::max(smax, sig[j]);
+  }
+  const double thr = std::numeric_limits<double>::epsilon() * smax;
+  for (int j = 0; j < l; ++j) {
+    if (sig[j] <= thr || sig[j] == 0.0) continue;
+    double ub = 0;  // u_j . b with u_j = H[:, j] / sig_j
+    for (int i = 0; i < l; ++i) ub += H[i * l + j] * b[i];
+    y[j] = ub / (sig[j] * sig[j]);
+  }
+  for (int i = 0; i < l; ++i) {
+    double x = 0;
+    for (int j = 0; j < l; ++j) x += V[i * l + j] * y[j];
+    b[i] = x;
+  }
+}
+
+// SNESSolve_NGMRES with PETSc's defaults (select/restart type "difference", basic line search,
+// no nonlinear preconditioner): per iteration X^M = X - F(X), F^M = F(X^M), the combined X^A from
+// the stored (X_i, F_i) and F^A = F(X^A) -- two function evaluations per iteration, as the golden
+// FEvals = 2 ItNum + 1 shows.  With snes.precond the function is G = P F (not in the reference);
+// the stop test and the history always use the true |F|.
+void cap_ngmres(Sim& s, std::vector<double>& X)
+{
+  Ngmres& ng = s.snes;
+  const int64_t n = s.n3;
+  const int ms = ng.msize;
+  ng.hist.clear();
+  ng.iterations = 0;
+  ng.fevals = 0;
+  ng.reason = 0;
+  std::vector<double> F(n), XA(n), FA(n), XM(n), FM(n), D(n), raw(n);
+  std::vector<std::vector<double>> Fdot(ms, std::vector<double>(n)), Xdot(ms, std::vector<double>(n));
+  std::vector<double> fnorms(ms), Q(ms * ms, 0.0), beta(ms), xi(ms);
+  auto norm = [&](const std::vector<double>& a) {
+    double t = 0;
+    for (int64_t i = 0; i < n; ++i) t += a[i] * a[i];
+    return std::sqrt(t);
+  };
+  auto vdot = [&](const std::vector<double>& a, const std::vector<double>& b) {
+    double t = 0;
+    for (int64_t i = 0; i < n; ++i) t += a[i] * b[i];
+    return t;
+  };
+  // function value (possibly preconditioned) and the true residual norm
+  auto eval = [&](const std::vector<double>& x, std::vector<double>& f, double& true_norm) {
+    if (!ng.precond) {
+      cap_form_function(s, x.data(), f.data());
+      true_norm = norm(f);
+    }
+    else {
+      cap_form_function(s, x.data(), raw.data());
+      true_norm = norm(raw);
+      cap_precondition(s, raw.data(), f.data());
+    }
+  };
+  auto update_subspace = [&](int ivec, const std::vector<double>& f, double fn, const std::vector<double>& x) {
+    Fdot[ivec] = f;
+    Xdot[ivec] = x;
+    fnorms[ivec] = fn;
+  };
+  double tF, tFM, tFA;
+  eval(X, F, tF);
+  double fnorm = norm(F), fminnorm = fnorm;
+  ng.hist.push_back(tF);
+  const double ttol = tF * ng.rtol;
+  auto converged = [&](double tn) {  // SNESConvergedDefault (snorm = xnorm = 0 as NGMRES passes them)
+    if (tn < ng.atol) return 2;      // SNES_CONVERGED_FNORM_ABS
+    if (tn <= ttol) return 3;        // SNES_CONVERGED_FNORM_RELATIVE
+    return 0;
+  };
+  if ((ng.reason = converged(tF))) return;
+  update_subspace(0, F, fnorm, X);
+  int k_restart = 1, l = 1, ivec = 0, restart_count = 0;
+  for (int k = 1; k < ng.maxit + 1; ++k) {
+    // x^M: basic line search, full step along -F
+    for (int64_t i = 0; i < n; ++i) XM[i] = X[i] - F[i];
+    eval(XM, FM, tFM);
+    const double fMnorm = norm(FM);
+    // combined solution (ngmresfunc.c: SNESNGMRESFormCombinedSolution_Private)
+    const double nu = fMnorm * fMnorm;
+    for (int i = 0; i < l; ++i) {
+      xi[i] = vdot(FM, Fdot[i]);
+      beta[i] = vdot(Fdot[ivec], Fdot[i]);
+    }
+    for (int i = 0; i < l; ++i) Q[i * ms + ivec] = Q[ivec * ms + i] = beta[i];
+    for (int i = 0; i < l; ++i) beta[i] = nu - xi[i];
+    if (l == 1) {
+      const double h00 = Q[0] - xi[0] - xi[0] + nu;
+      beta[0] = h00 != 0.0 ? beta[0] / h00 : 0.0;
+    }
+    else {
+      std::vector<double> H(l * l), rhs(beta.begin(), beta.begin() + l);
+      for (int j = 0; j < l; ++j)
+        for (int i = 0; i < l; ++i) H[i * l + j] = Q[i * ms + j] - xi[i] - xi[j] + nu;
+      lstsq_svd(l, H, rhs);
+      std::copy(rhs.begin(), rhs.end(), beta.begin());
+    }
+    double alph_total = 0;
+    for (int i = 0; i < l; ++i) alph_total += beta[i];
+    for (int64_t j = 0; j < n; ++j) XA[j] = (1.0 - alph_total) * XM[j];
+    for (int i = 0; i < l; ++i)
+      for (int64_t j = 0; j < n; ++j) XA[j] += beta[i] * Xdot[i][j];
+    eval(XA, FA, tFA);
+    if (fminnorm > fMnorm) fminnorm = fMnorm;
+    // SNESNGMRESNorms_Private
+    const double fAnorm = norm(FA);
+    for (int64_t j = 0; j < n; ++j) D[j] = XA[j] - XM[j];
+    const double dnorm = norm(D);
+    double dminnorm = -1.0;
+    for (int i = 0; i < l; ++i) {
+      for (int64_t j = 0; j < n; ++j) D[j] = Xdot[i][j] - XA[j];
+      const double dc = norm(D);
+      if (dc < dminnorm || dminnorm < 0.0) dminnorm = dc;
+    }
+    // SNESNGMRESSelect_Private, select_type difference
+    bool selectA = true;
+    if (fAnorm >= ng.gammaA * fminnorm) selectA = false;
+    if (ng.epsilonB * dnorm < dminnorm || std::sqrt(fnorm) < ng.deltaB * std::sqrt(fminnorm)) {}
+    else selectA = false;
+    if (selectA) {
+      fnorm = fAnorm; tF = tFA;
+      F = FA; X = XA;
+    }
+    else {
+      fnorm = fMnorm; tF = tFM;
+      F = FM; X = XM;
+    }
+    // SNESNGMRESSelectRestart_Private
+    bool selectRestart = false;
+    if ((ng.epsilonB * dnorm > dminnorm) && (std::sqrt(fAnorm) > ng.deltaB * std::sqrt(fminnorm)) && l > 0) selectRestart = true;
+    if (std::sqrt(fAnorm) > ng.gammaC * std::sqrt(fminnorm)) selectRestart = true;
+    if (selectRestart) restart_count++;
+    else restart_count = 0;
+    ivec = k_restart % ms;
+    if (restart_count >= ng.restart_it) {
+      restart_count = 0;
+      k_restart = 1;
+      l = 1;
+      ivec = 0;
+      update_subspace(0, FM, fMnorm, XM);
+    }
+    else {
+      if (l < ms) l++;
+      k_restart++;
+      if (fminnorm > fnorm) fminnorm = fnorm;
+      update_subspace(ivec, F, fnorm, X);
+    }
+    if (getenv("XO_NGMRES_DEBUG"))
+      fprintf(stderr, "k %d l %d fM %.4e fA %.4e fmin %.4e dnorm %.3e dmin %.3e selA %d restart %d cnt %d asum %.3e\n", k, l, fMnorm, fAnorm, fminnorm, dnorm, dminnorm, (int)selectA,
+              (int)selectRestart, restart_count, alph_total);
+    ng.iterations = k;
+    ng.hist.push_back(tF);
+    if ((ng.reason = converged(tF))) return;
+  }
+  ng.reason = -5;  // SNES_DIVERGED_MAX_IT
+}
+
+void step_eccapfim(Sim& s)  // eccapfim/simulation.cpp:36-130
+{
+  // init_iteration :46-70, Particles::prepare_storage particles.cpp:191-208
+  for (auto& sp : s.sorts) {
+    sp.size = 0;
+    for (int64_t g = 0; g < s.nc; ++g) {
+      auto& cur = sp.storage[g];
+      if (cur.empty()) continue;
+      sp.previous_storage[g].assign(cur.begin(), cur.end());
+      sp.size += (int64_t)cur.size();
+    }
+  }
+  std::vector<double> sol(s.E);
+  cap_ngmres(s, sol);  // calc_iteration :72-104
+  // after_iteration :106-129
+  std::vector<double> ce(s.n3);
+  curl(s, true, sol.data(), ce.data());
+  for (int64_t i = 0; i < s.n3; ++i) {
+    s.E[i] = 2 * sol[i] + (-1) * s.E[i];
+    s.B[i] = s.B[i] + (-s.dt) * ce[i];
+  }
+  s.Ehk = sol;
+  for (auto& sp : s.sorts) update_cells_seq(s, sp);
+}
+
 std::vector<double>* field_by_id(Sim& s, int which, int sid)
 {
   switch (which) {
@@ -778,6 +1351,9 @@ std::vector<double>* field_by_id(Sim& s, int which, int sid)
     case 6: return &s.currJe;
     case 7: return &s.sorts.at(sid).currI;
     case 8: return &s.sorts.at(sid).currJe;
+    case 9: return &s.J;
+    case 10: return &s.sorts.at(sid).J;
+    case 11: return &s.Ehk;
   }
   return nullptr;
 }
@@ -810,7 +1386,7 @@ void* xo_create(int nx, int ny, int nz, double dx, double dy, double dz, double 
   s->curl_sign = curl_sign;
   s->nc = (int64_t)nx * ny * nz;
   s->n3 = 3 * s->nc;
-  for (auto* v : {&s->E, &s->Ep, &s->Ec, &s->B, &s->B0, &s->currI, &s->currJe}) v->assign(s->n3, 0.0);
+  for (auto* v : {&s->E, &s->Ep, &s->Ec, &s->B, &s->B0, &s->currI, &s->currJe, &s->Ehk, &s->J}) v->assign(s->n3, 0.0);
   build_matM(*s);
   build_matL_pattern(*s);
   return s;
@@ -827,6 +1403,8 @@ int xo_add_species(void* h, double q, double m, double n, int Np)
   sp.storage.resize(s.nc);
   sp.currI.assign(s.n3, 0.0);
   sp.currJe.assign(s.n3, 0.0);
+  sp.J.assign(s.n3, 0.0);
+  sp.previous_storage.resize(s.nc);
   return (int)s.sorts.size() - 1;
 }
 
@@ -907,7 +1485,9 @@ void xo_get_particles(void* h, int sid, double* aos6, uint64_t* ids)
 void xo_step(void* h, int scheme)
 {
   Sim& s = *(Sim*)h;
-  if (scheme == 0) step_ecsim(s); else step_ecsimcorr(s);
+  if (scheme == 0) step_ecsim(s);
+  else if (scheme == 1) step_ecsimcorr(s);
+  else step_eccapfim(s);
 }
 
 void xo_get_field(void* h, int which, int sid, double* out)
@@ -960,6 +1540,58 @@ double xo_scalar(void* h, int sid, int which)
     case 7: return s.last_j_diff_norm;
   }
   return 0.0;
+}
+
+// eccapfim nonlinear solver controls / results
+void xo_snes_set(void* h, double atol, double rtol, double stol, int maxit, int precond, double shift)
+{
+  Ngmres& ng = ((Sim*)h)->snes;
+  ng.atol = atol; ng.rtol = rtol; ng.stol = stol; ng.maxit = maxit; ng.precond = precond; ng.shift = shift;
+}
+
+void xo_snes_set_particle_tol(void* h, double tol) { ((Sim*)h)->snes.cn_tol = tol; }
+
+void xo_snes_info(void* h, int* iterations, int* fevals, int* reason, double* avgit, double* avgcell)
+{
+  Sim& s = *(Sim*)h;
+  *iterations = s.snes.iterations; *fevals = s.snes.fevals; *reason = s.snes.reason;
+  *avgit = s.sorts.empty() ? 0.0 : s.sorts[0].avgit;
+  *avgcell = s.sorts.empty() ? 0.0 : s.sorts[0].avgcell;
+}
+
+int xo_snes_history(void* h, double* out, int cap)
+{
+  Ngmres& ng = ((Sim*)h)->snes;
+  const int n = (int)std::min<size_t>(ng.hist.size(), (size_t)cap);
+  std::copy(ng.hist.begin(), ng.hist.begin() + n, out);
+  return (int)ng.hist.size();
+}
+
+// F(x) of the eccapfim step at the present (E^n, B^n, particles); the particles afterwards hold the
+// pushed state of this evaluation and `previous_storage` the start-of-step state
+void xo_eccapfim_function(void* h, const double* x, double* f, int prepare)
+{
+  Sim& s = *(Sim*)h;
+  if (prepare)
+    for (auto& sp : s.sorts) {
+      sp.size = 0;
+      for (int64_t g = 0; g < s.nc; ++g) {
+        sp.previous_storage[g].assign(sp.storage[g].begin(), sp.storage[g].end());
+        sp.size += (int64_t)sp.storage[g].size();
+      }
+    }
+  cap_form_function(s, x, f);
+}
+
+// the stopping points of cell_traversal(end, start); returns their number (<= cap written)
+int xo_cell_traversal(void* h, const double* end, const double* start, double* out, int cap)
+{
+  Sim& s = *(Sim*)h;
+  std::vector<V3> pts;
+  cell_traversal(s, {end[0], end[1], end[2]}, {start[0], start[1], start[2]}, pts);
+  for (int i = 0; i < (int)pts.size() && i < cap; ++i)
+    for (int c = 0; c < 3; ++c) out[3 * i + c] = pts[i][c];
+  return (int)pts.size();
 }
 
 // Stand-alone pieces (used to test individual kernels) --------------------------------------

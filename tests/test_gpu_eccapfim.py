@@ -1,0 +1,155 @@
+"""GPU parity tests of the eccapfim step (BASELINE config 5) through the C ABI against the CPU oracle.
+
+The residual evaluation F(x) -- a full re-push of every particle with the Picard-iterated
+Crank-Nicolson mover, path splitting and implicit-Esirkepov gather / scatter -- is compared kernel
+for kernel; whole steps are compared with both nonlinear solvers converged far below the bound
+(the oracle runs its NGMRES restatement, the product Anderson acceleration: two different solvers
+must land on the same solution).  Tolerances: 1e-8 relative for state after 10 steps (north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from helpers import by_id, rel_err
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TIGHT = 1e-14  # per-particle Picard tolerance for parity runs (reference: 0.5e-7)
+
+
+def make_cap_pair(n=(10, 10, 10), Np=30, T=0.1, curl_sign=+1, seed_fields=None, particles=None, d=(0.5, 0.5, 0.5), dt=1.5, particle_tol=TIGHT, atol=1e-13):
+    import xpic_b200 as X
+
+    O.set_threads(min(8, O.max_threads()))
+    o = O.Oracle(n, d=d, dt=dt, curl_sign=curl_sign)
+    s = X.Simulation(n, d=d, dt=dt, scheme=X.ECCAPFIM, curl_sign=curl_sign, track_ids=True)
+    sid = o.add_species(q=-1.0, m=1.0, n=1.0, Np=Np)
+    if particles is None:
+        o.set_particles_maxwell(sid, T=T, tov=True)
+    else:
+        o.set_particles(sid, particles)
+    gs = s.add_species(q=-1.0, m=1.0, n=1.0, Np=Np)
+    pts, ids = o.get_particles(sid)
+    assert s.add_particles(gs, pts, ids) == len(ids)
+    o.snes_set(atol=atol, rtol=1e-30, maxit=400, precond=1, shift=0.5)
+    o.snes_set_particle_tol(particle_tol)
+    s.nonlinear_set(atol=atol, rtol=1e-30, maxit=400, particle_tol=particle_tol, particle_maxit=30)
+    if seed_fields is not None:
+        rng = np.random.default_rng(seed_fields)
+        for name, amp in (("E", 0.02), ("B", 0.05)):
+            f = amp * rng.standard_normal(o.n3)
+            o.set_field(name, f)
+            s.set_field(name, f)
+    return o, s
+
+
+def compare_function(o, s, x, tol=1e-11):
+    fo = o.eccapfim_function(x)
+    fg = s.eccapfim_function(x)
+    assert rel_err(s.get_field("J"), o.get_field("J")) < tol
+    assert rel_err(fg, fo) < tol
+    return fo, fg
+
+
+def test_residual_evaluation_matches_oracle():
+    o, s = make_cap_pair(n=(10, 9, 8), Np=20, seed_fields=11)
+    x = o.get_field("E") + 0.01 * np.random.default_rng(12).standard_normal(o.n3)
+    compare_function(o, s, x)
+    io, ig = o.snes_info(), s.nonlinear_info()
+    # the statistics the ConvergenceHistory diagnostic prints (integers summed, then averaged)
+    assert abs(io["avg_cells"] - ig["avg_cells"]) < 1e-12
+    assert abs(io["avg_cn"] - ig["avg_cn"]) < 2e-3  # an iteration count may flip where the residual sits on the threshold
+
+
+def test_residual_evaluation_fast_particles_cross_cells_tiles_and_the_box():
+    # velocities up to 0.45 c: up to 1.35 cells per step -> several path pieces, particles that leave the
+    # shared-memory tile (global fallback), periodic wraps and the sub-step split at the box edge + 1/2 cell
+    rng = np.random.default_rng(21)
+    n, d = (8, 7, 6), (0.5, 0.5, 0.5)
+    L = np.array(n) * 0.5
+    npart = 4000
+    pts = np.empty((npart, 6))
+    pts[:, :3] = rng.random((npart, 3)) * L
+    pts[:, 3:] = (rng.random((npart, 3)) - 0.5) * 0.9
+    # a handful right at the faces of the box, moving out
+    pts[:50, 0] = L[0] - 1e-3
+    pts[:50, 3] = 0.4
+    pts[50:100, 2] = 1e-3
+    pts[50:100, 5] = -0.4
+    o, s = make_cap_pair(n=n, Np=10, seed_fields=22, particles=pts)
+    x = o.get_field("E")
+    compare_function(o, s, x, tol=1e-10)
+    assert o.snes_info()["avg_cells"] > 1.5
+    assert abs(o.snes_info()["avg_cells"] - s.nonlinear_info()["avg_cells"]) < 1e-12
+
+
+def test_step_matches_oracle_10_steps():
+    o, s = make_cap_pair(n=(10, 10, 10), Np=30)
+    for t in range(10):
+        o.step(O.ECCAPFIM)
+        s.step()
+        assert s.nonlinear_info()["reason"] > 0
+    for name in ("E", "B"):
+        assert rel_err(s.get_field(name), o.get_field(name)) < 1e-8, name
+    po, io = by_id(*o.get_particles())
+    pg, ig = by_id(*s.get_particles())
+    assert np.array_equal(io, ig)
+    assert rel_err(pg, po) < 1e-8
+
+
+def test_energy_is_conserved_to_solver_tolerance():
+    o, s = make_cap_pair(n=(12, 10, 8), Np=40)
+    tot = [sum(s.field_energies()) + s.scalar("kinetic")]
+    for t in range(5):
+        s.step()
+        tot.append(sum(s.field_energies()) + s.scalar("kinetic"))
+    assert np.max(np.abs(np.diff(tot))) < 1e-12  # golden (reference tolerances): ~1e-10..1e-9
+
+
+def test_golden_energy_rows_with_reference_tolerances():
+    # tests/eccapfim/eccapfim_ex1.cpp set-up, SNES atol = rtol = 1e-7 as in the reference; the particles are
+    # converged (HEAD's 0.5e-7 Picard tolerance drifts the energy by ~1.5e-7 per step, the golden does not)
+    import xpic_b200 as X
+
+    o = O.Oracle((10, 10, 10))
+    sid = o.add_species(Np=100)
+    o.set_particles_maxwell(sid, 0.1, True)
+    s = X.Simulation((10, 10, 10), scheme=X.ECCAPFIM, track_ids=True)
+    gs = s.add_species(Np=100)
+    pts, ids = o.get_particles(sid)
+    s.add_particles(gs, pts, ids)
+    s.nonlinear_set(particle_tol=1e-13)
+    _, gold = O.read_table(os.path.join(GOLDEN, "eccapfim_ex1", "energy.txt"))
+    rows = [(0.0, 0.0, s.scalar("kinetic"))]
+    evals = []
+    for t in range(10):
+        s.step()
+        rows.append((*s.field_energies(), s.scalar("kinetic")))
+        info = s.nonlinear_info()
+        evals.append(info["fevals"])
+        assert info["reason"] > 0 and info["fnorm"] < 1e-7
+    rows = np.array(rows)
+    np.testing.assert_allclose(rows[:, 2], gold[:11, 3], rtol=2e-6)   # wK
+    np.testing.assert_allclose(rows[:, 0], gold[:11, 1], rtol=5e-5, atol=1e-12)   # wE
+    np.testing.assert_allclose(rows[:, 1], gold[:11, 2], rtol=1e-3, atol=1e-12)   # wB (curl amplifies the solver tolerance)
+    # the reference's NGMRES needs ~105 residual evaluations per step (golden FEvals column)
+    assert max(evals) <= 30
+    for name in ("E", "B"):
+        g = np.fromfile(os.path.join(GOLDEN, "eccapfim_ex1", f"{name}_010.f32"), dtype=np.float32).astype(np.float64)
+        assert rel_err(s.get_field(name), g) < (2e-3 if name == "E" else 1e-2)  # ten reference solves stopped at |F| ~ 1e-7
+
+
+def test_empty_and_single_particle():
+    import xpic_b200 as X
+
+    s = X.Simulation((6, 5, 4), scheme=X.ECCAPFIM)
+    s.add_species(Np=1)
+    s.step()  # no particles: F(E^n = 0) = 0 converges immediately
+    assert s.nonlinear_info()["iterations"] == 0
+    o, s2 = make_cap_pair(n=(6, 5, 4), Np=1, particles=np.array([[1.3, 0.7, 1.1, 0.05, -0.02, 0.01]]), seed_fields=31)
+    o.step(O.ECCAPFIM)
+    s2.step()
+    assert rel_err(s2.get_field("E"), o.get_field("E")) < 1e-9
+    assert rel_err(s2.get_particles()[0], o.get_particles()[0]) < 1e-10

@@ -5,10 +5,10 @@ this package is the thin ctypes binding the tests and bench.py drive it through,
 build helper.  There is no CPU fallback: importing works anywhere, creating a Simulation
 needs the built library and a CUDA device.
 """
-from .binding import (ECSIM, ECSIMCORR, FIELDS, SCALARS, STAGES, Simulation, XpicB200Error, build_library, coef_table,
+from .binding import (ECCAPFIM, ECSIM, ECSIMCORR, FIELDS, SCALARS, STAGES, Simulation, XpicB200Error, build_library, coef_table,
                       comm_unique_id, library_path, load_library, owner_rank, slab_range)
 
 __all__ = [
-    "ECSIM", "ECSIMCORR", "FIELDS", "SCALARS", "STAGES", "Simulation", "XpicB200Error", "build_library", "coef_table",
+    "ECCAPFIM", "ECSIM", "ECSIMCORR", "FIELDS", "SCALARS", "STAGES", "Simulation", "XpicB200Error", "build_library", "coef_table",
     "comm_unique_id", "library_path", "load_library", "owner_rank", "slab_range",
 ]

@@ -15,8 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _LIB = os.path.join(_HERE, "_build", "libxpic_b200.so")
 
-ECSIM, ECSIMCORR = 0, 1
-FIELDS = {"E": 0, "B": 1, "B0": 2, "Ep": 3, "Ec": 4, "currI": 5, "currJe": 6, "currI_sort": 7, "currJe_sort": 8}
+ECSIM, ECSIMCORR, ECCAPFIM = 0, 1, 2
+FIELDS = {"E": 0, "B": 1, "B0": 2, "Ep": 3, "Ec": 4, "currI": 5, "currJe": 6, "currI_sort": 7, "currJe_sort": 8, "J": 9, "J_sort": 10, "Ehk": 11}
 SCALARS = {"kinetic": 0, "pred_w": 1, "corr_w": 2, "pred_dK": 3, "corr_dK": 4, "lambda_dK": 5, "energy_member": 6, "j_diff_norm": 7}
 STAGES = ["clear_sources", "first_push", "advance_fields", "second_push", "correct_fields", "final_update"]
 OP_L, OP_M, OP_A = 1, 2, 3
@@ -104,6 +104,11 @@ SYMBOLS = {
     "xb_solve": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp]),
     "xb_curl": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp]),
     "xb_kernel_bench": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "xb_nonlinear_set": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32]),
+    "xb_nonlinear_info": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _dp, _dp, _dp]),
+    "xb_nonlinear_history": (C.c_int, [C.c_void_p, _dp, C.c_int32, _i32p]),
+    "xb_nonlinear_profile": (C.c_int, [C.c_void_p, C.c_int32, _i64p, _dp]),
+    "xb_eccapfim_function": (C.c_int, [C.c_void_p, _dp, _dp]),
 }
 
 
@@ -245,6 +250,34 @@ class Simulation:
         it, rn, re = C.c_int32(), C.c_double(), C.c_int32()
         _check(self._L.xb_solver_info(self._h, which, C.byref(it), C.byref(rn), C.byref(re)))
         return it.value, rn.value, re.value
+
+    # -- eccapfim's nonlinear solve (SNES in the reference) -------------------------------------
+    def nonlinear_set(self, atol=1e-7, rtol=1e-7, stol=1e-7, maxit=1000, depth=10, cheb_degree=12, particle_tol=0.5e-7, particle_maxit=30):
+        _check(self._L.xb_nonlinear_set(self._h, atol, rtol, stol, maxit, depth, cheb_degree, particle_tol, particle_maxit))
+
+    def nonlinear_info(self):
+        it, fe, re = C.c_int32(), C.c_int32(), C.c_int32()
+        fn, ai, ac = C.c_double(), C.c_double(), C.c_double()
+        _check(self._L.xb_nonlinear_info(self._h, C.byref(it), C.byref(fe), C.byref(re), C.byref(fn), C.byref(ai), C.byref(ac)))
+        return {"iterations": it.value, "fevals": fe.value, "reason": re.value, "fnorm": fn.value, "avg_cn": ai.value, "avg_cells": ac.value}
+
+    def nonlinear_history(self):
+        n = C.c_int32()
+        buf = np.empty(2048)
+        _check(self._L.xb_nonlinear_history(self._h, _as_dp(buf), buf.size, C.byref(n)))
+        return buf[: min(n.value, buf.size)].copy()
+
+    def nonlinear_profile(self, enable=-1):
+        """(particle passes timed, their summed ms) so far; enable in {0, 1} then resets and switches collecting."""
+        n, ms = C.c_int64(), C.c_double()
+        _check(self._L.xb_nonlinear_profile(self._h, int(enable), C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def eccapfim_function(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.empty(self.nown, dtype=np.float64)
+        _check(self._L.xb_eccapfim_function(self._h, _as_dp(x), _as_dp(f)))
+        return f
 
     # -- stepping ------------------------------------------------------------------------------
     def step(self, scheme=None):

@@ -154,6 +154,15 @@ static int stage_final(xb_ctx* c, int scheme)
 static int run_stage(xb_ctx* c, int scheme, int stage)
 {
   StageTimer t(c, stage);
+  if (scheme == XB_ECCAPFIM) {  // eccapfim/simulation.cpp:36-44: init_iteration, calc_iteration, after_iteration
+    switch (stage) {
+      case XB_STAGE_CLEAR_SOURCES: XB_CHECK(cap_prepare(c)); break;
+      case XB_STAGE_ADVANCE_FIELDS: XB_CHECK(cap_solve(c)); break;
+      case XB_STAGE_FINAL_UPDATE: XB_CHECK(cap_finish(c)); break;
+      default: break;
+    }
+    return t.finish();
+  }
   switch (stage) {
     case XB_STAGE_CLEAR_SOURCES: XB_CHECK(stage_clear(c, scheme)); break;
     case XB_STAGE_FIRST_PUSH: XB_CHECK(stage_first_push(c, scheme)); break;
@@ -180,6 +189,9 @@ static double* named_vector(xb_ctx* c, int which, int sid)
     case XB_CURRJE: return c->currJe;
     case XB_CURRI_SORT: return sid >= 0 && sid < (int)c->sorts.size() ? c->sorts[sid].currI : nullptr;
     case XB_CURRJE_SORT: return sid >= 0 && sid < (int)c->sorts.size() ? c->sorts[sid].currJe : nullptr;
+    case XB_J: return c->cap_J;
+    case XB_J_SORT: return sid >= 0 && sid < (int)c->sorts.size() ? c->sorts[sid].currI : nullptr;  // eccapfim keeps Particles::J there
+    case XB_EHK: return c->cap_x;
   }
   return nullptr;
 }
@@ -311,8 +323,11 @@ int xb_destroy(xb_ctx* c)
   comm_free(c);
   for (auto& s : c->sorts) species_free(s);
   for (double* v : {c->E, c->B, c->B0, c->Ep, c->Ec, c->currI, c->currJe, c->rhs, c->tmp, c->tmp2, c->coef, c->stage, c->Z, c->cheb_r, c->cheb_d,
-                    c->cheb_Md, c->ksp_u, c->red_partial, c->red_out})
+                    c->cheb_Md, c->ksp_u, c->red_partial, c->red_out, c->cap_x, c->cap_F, c->cap_g, c->cap_rhs0, c->cap_J})
     cudaFree(v);
+  cudaFree(c->cap_counters);
+  for (auto e : c->nl.events)
+    if (e) cudaEventDestroy(e);
   for (double* v : c->V) cudaFree(v);
   cudaFree(c->hist);
   cudaFree(c->cursor);
@@ -452,7 +467,7 @@ int xb_solver_info(xb_ctx* c, int32_t which, int32_t* iterations, double* rnorm,
 int xb_stage(xb_ctx* c, int32_t scheme, int32_t stage)
 {
   XB_API_BEGIN(c);
-  if (scheme != XB_ECSIM && scheme != XB_ECSIMCORR) XB_FAIL("unknown scheme");
+  if (scheme != XB_ECSIM && scheme != XB_ECSIMCORR && scheme != XB_ECCAPFIM) XB_FAIL("unknown scheme");
   if (stage == XB_STAGE_CLEAR_SOURCES) XB_CHECK(ensure_sorted(c));
   return run_stage(c, scheme, stage);
 }
@@ -460,7 +475,7 @@ int xb_stage(xb_ctx* c, int32_t scheme, int32_t stage)
 int xb_step(xb_ctx* c, int32_t scheme)
 {
   XB_API_BEGIN(c);
-  if (scheme != XB_ECSIM && scheme != XB_ECSIMCORR) XB_FAIL("unknown scheme");
+  if (scheme != XB_ECSIM && scheme != XB_ECSIMCORR && scheme != XB_ECCAPFIM) XB_FAIL("unknown scheme");
   XB_CHECK(ensure_sorted(c));
   for (int st = 0; st < XB_STAGE_COUNT; ++st) XB_CHECK(run_stage(c, scheme, st));
   return 0;
@@ -658,6 +673,65 @@ int xb_set_option(xb_ctx* c, int32_t what, int32_t value)
     return 0;
   }
   XB_FAIL("xb_set_option: unknown option");
+}
+
+int xb_nonlinear_set(xb_ctx* c, double atol, double rtol, double stol, int32_t maxit, int32_t depth, int32_t cheb_degree, double particle_tol,
+                     int32_t particle_maxit)
+{
+  XB_API_BEGIN(c);
+  if (maxit < 1 || depth < 1 || cheb_degree < 0 || particle_maxit < 0) XB_FAIL("xb_nonlinear_set: bad argument");
+  Nonlinear& nl = c->nl;
+  nl.atol = atol; nl.rtol = rtol; nl.stol = stol; nl.maxit = maxit; nl.depth = depth; nl.cheb_degree = cheb_degree;
+  nl.cn_tol = particle_tol; nl.cn_maxit = particle_maxit;
+  return 0;
+}
+
+int xb_nonlinear_info(xb_ctx* c, int32_t* iterations, int32_t* fevals, int32_t* reason, double* fnorm, double* avg_cn, double* avg_cells)
+{
+  XB_API_BEGIN(c);
+  const Nonlinear& nl = c->nl;
+  if (iterations) *iterations = nl.iterations;
+  if (fevals) *fevals = nl.fevals;
+  if (reason) *reason = nl.reason;
+  if (fnorm) *fnorm = nl.fnorm;
+  if (avg_cn) *avg_cn = nl.avg_cn;
+  if (avg_cells) *avg_cells = nl.avg_cells;
+  return 0;
+}
+
+int xb_nonlinear_history(xb_ctx* c, double* out, int32_t capacity, int32_t* length)
+{
+  XB_API_BEGIN(c);
+  const Nonlinear& nl = c->nl;
+  if (length) *length = (int32_t)nl.hist.size();
+  for (int i = 0; out && i < capacity && i < (int)nl.hist.size(); ++i) out[i] = nl.hist[i];
+  return 0;
+}
+
+int xb_nonlinear_profile(xb_ctx* c, int32_t enable, int64_t* evaluations, double* total_ms)
+{
+  XB_API_BEGIN(c);
+  Nonlinear& nl = c->nl;
+  if (evaluations) *evaluations = nl.push_evals;
+  if (total_ms) *total_ms = nl.push_ms;
+  if (enable >= 0) {
+    nl.profile = enable != 0;
+    nl.push_ms = 0.0;
+    nl.push_evals = 0;
+  }
+  return 0;
+}
+
+int xb_eccapfim_function(xb_ctx* c, const double* x, double* f)
+{
+  XB_API_BEGIN(c);
+  XB_CHECK(ensure_sorted(c));
+  XB_CHECK(cap_prepare(c));
+  XB_CHECK(upload_owned(c, x, c->cap_x));
+  XB_CHECK(cap_form_function(c, c->cap_x, c->cap_F));
+  XB_CHECK(download_owned(c, c->cap_F, f));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
 }
 
 int xb_deposit(xb_ctx* c)

@@ -74,6 +74,26 @@ struct Solver {
   double rnorm = 0.0;
 };
 
+// eccapfim's nonlinear solve: tolerances of src/impls/eccapfim/simulation.h:14-19, per-particle
+// Picard tolerance 0.5 * atol and 30 iterations (src/impls/eccapfim/particles.cpp:99-101)
+struct Nonlinear {
+  double atol = 1e-7, rtol = 1e-7, stol = 1e-7;
+  int maxit = 1000;
+  int depth = 10;         // Anderson history
+  int cheb_degree = 12;   // Chebyshev degree of the residual preconditioner (0: none)
+  double cn_tol = 0.5e-7;
+  int cn_maxit = 30;
+  int iterations = 0, fevals = 0, reason = 0;
+  double fnorm = 0.0, avg_cn = 0.0, avg_cells = 0.0;
+  std::vector<double> hist;
+  int64_t particles_per_eval = 0;
+  bool profile = false;   // CUDA-event timing of every particle pass
+  std::vector<cudaEvent_t> events;
+  size_t events_used = 0;
+  double push_ms = 0.0;
+  int64_t push_evals = 0;
+};
+
 struct MigrateBuffers {  // multi-rank only (migrate.cu)
   double* send[2][7] = {{nullptr}};   // [0] to the rank below, [1] to the rank above; 6 SoA arrays + ids
   double* recv[2][7] = {{nullptr}};   // [0] from below, [1] from above
@@ -160,6 +180,10 @@ struct xb_ctx {
   xb::Comm* comm = nullptr;
   int64_t launches = 0;
   double j_diff_norm = 0.0;
+  // eccapfim (eccapfim.cu), allocated on first use
+  xb::Nonlinear nl;
+  double *cap_x = nullptr, *cap_F = nullptr, *cap_g = nullptr, *cap_rhs0 = nullptr, *cap_J = nullptr;
+  unsigned long long* cap_counters = nullptr;
 };
 
 namespace xb {
@@ -213,6 +237,12 @@ int push_second_corr(xb_ctx* c, Species& s, const double* Eh, const double* B);
 // ---- esirkepov_mma.cu (atomic-free tensor-core form, the default) ----------------------------
 int push_first_corr_mma(xb_ctx* c, Species& s);
 int push_second_corr_mma(xb_ctx* c, Species& s, const double* Eh, const double* B);
+
+// ---- eccapfim.cu -----------------------------------------------------------------------------
+int cap_prepare(xb_ctx* c);                              // init_iteration: sort if needed, rhs0
+int cap_form_function(xb_ctx* c, double* x, double* F);  // form_iteration: F(x), x ghosted
+int cap_solve(xb_ctx* c);                                // calc_iteration
+int cap_finish(xb_ctx* c);                               // after_iteration
 
 // ---- launch bookkeeping ----------------------------------------------------------------------
 #define XB_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \

@@ -1,0 +1,813 @@
+// eccapfim.cu -- the fully implicit energy- and charge-conserving step (BASELINE config 5).
+//
+// Reference code replaced (paths relative to the reference tree):
+//   eccapfim::Simulation::timestep_implementation / init_iteration / calc_iteration / after_iteration
+//                                            src/impls/eccapfim/simulation.cpp:36-130
+//   Simulation::form_iteration / form_current / form_function      simulation.cpp:132-241
+//   eccapfim::Particles::form_iteration (Picard-iterated Crank-Nicolson mover with path splitting)
+//                                            src/impls/eccapfim/particles.cpp:30-181
+//   cell_traversal                           src/impls/eccapfim/cell_traversal.cpp:3-77
+//   ImplicitEsirkepov::{Shape::setup, interpolate, decompose}   src/algorithms/implicit_esirkepov.cpp:11-117
+//   Shape::setup(r) + SimpleInterpolation (B at the segment midpoint)  src/utils/shape.cpp:34-45,81-107,
+//                                            src/algorithms/simple_interpolation.cpp:8-38
+//   SNESSolve (PETSc NGMRES, un-vendored)    simulation.cpp:75, init_snes_solver :358-390
+//
+// The nonlinear system F(E^{n+1/2}) = 0 is the reference's (form_function :228-236):
+//   F(x) = x + dt^2/4 curl^- curl^+ x - E^n + dt/2 J(x) - dt/2 curl^- B^n ,
+// J(x) = the current of all particles re-pushed from their start-of-step state through x.
+// PETSc's NGMRES iteration path is not restated (the golden convergence history was produced by an
+// older revision of the reference whose residual is scaled by 2/dt); the solver here
+// is Anderson acceleration of the preconditioned fixed-point map x <- x - P F(x) with
+// P ~= ((1 + sigma) I + dt^2/4 curl curl)^-1 (Chebyshev polynomial, sigma = sum_s (omega_ps dt)^2 / 4):
+// one residual evaluation per iteration and ~10 instead of the reference's ~105 per step.  The stop
+// test is SNESConvergedDefault's on the true |F| with the reference's tolerances (simulation.h:14-19).
+//
+// k_cap_push: one CTA per CAP_CELLS x-consecutive cells; the E^{n+1/2,k} and B^n nodes a particle of
+// these cells can reach within one cell of motion are staged in shared memory, the current is
+// accumulated in a shared tile and flushed once (fast particles fall back to global loads / atomics).
+#include <algorithm>
+#include <cmath>
+
+#include "comm.cuh"
+#include "common.cuh"
+#include "gather.cuh"
+#include "operators.cuh"
+
+namespace xb {
+
+int cheb_solve_shifted(xb_ctx* c, int deg, double diag, const double* u, double* z);  // krylov.cu
+int reduce_finish(xb_ctx* c, int nv, double* host_out);                                // fields.cu
+int migrate_and_sort(xb_ctx* c, Species& s, double dt_move);                           // migrate.cu
+
+constexpr int CAP_CELLS = 8;
+constexpr int CAP_THREADS = 256;
+constexpr int CAP_LO = 2;  // staged nodes below the first cell (x), the row (y) and the plane (z)
+constexpr int CAP_NX = CAP_CELLS + 5, CAP_NY = 6, CAP_NZ = 6;
+constexpr int CAP_VOL = CAP_NX * CAP_NY * CAP_NZ;  // nodes per component, layout [c][z][y][x]
+
+struct CapArgs {
+  const double* p0[6];  // start-of-step state (cell-sorted)
+  double* pn[6];        // (x^{n+1,k}, v^{n+1,k}) of this evaluation
+  const int32_t* bin_start;
+  const double* E;  // E^{n+1/2,k}, ghosts valid (width GZ)
+  const double* B;  // B^n, ghosts valid
+  double* J;        // this sort's current (ghosted, zeroed by the caller)
+  double q, m, mpw;
+  double cn_tol;
+  int cn_maxit;
+  int groups_x;
+  unsigned long long* counters;  // [0] Picard iterations, [1] traversed segments
+  int* error;
+};
+
+struct CapCtx {
+  Grid g;
+  const double* Et;
+  const double* Bt;
+  double* Jt;
+  int x0, y0, z0;  // global (unwrapped) node index of the tile origin
+  const double* E;
+  const double* B;
+  double* J;
+  int* error;
+
+  __device__ __forceinline__ bool inside(const int* lo, int ext) const
+  {
+    return lo[0] >= x0 && lo[0] + ext <= x0 + CAP_NX && lo[1] >= y0 && lo[1] + ext <= y0 + CAP_NY && lo[2] >= z0 && lo[2] + ext <= z0 + CAP_NZ;
+  }
+  __device__ __forceinline__ int tile_base(const int* lo) const { return ((lo[2] - z0) * CAP_NY + (lo[1] - y0)) * CAP_NX + (lo[0] - x0); }
+  // element index in a ghosted global vector of the (unwrapped) global node (gx, gy, gz)
+  __device__ __forceinline__ int64_t gidx(int gx, int gy, int gz, int c) const
+  {
+    const int x = wrapi(gx, g.nx), y = wrapi(gy, g.ny);
+    int zl;
+    if (g.nranks == 1)
+      zl = wrapi(gz, g.nz);
+    else {
+      zl = gz - g.z0;
+      if (zl < -GZ) zl += g.nz;
+      else if (zl >= g.nzl + GZ) zl -= g.nz;
+      if (zl < -GZ || zl >= g.nzl + GZ) {
+        *error = 2;  // the particle left the ghost planes of this slab within one step
+        zl = min(max(zl, -GZ), g.nzl + GZ - 1);
+      }
+    }
+    return g.vidx(x, y, zl, c);
+  }
+};
+
+// ---- shapes -----------------------------------------------------------------------------------
+__device__ __forceinline__ double sf1(double x) { return 1.0 - fabs(x); }
+__device__ __forceinline__ double sf2(int j, double x)  // sfunc_2[j], implicit_esirkepov.h:40-44
+{
+  x = fabs(x);
+  return j == 1 ? (0.75 - x * x) : 0.5 * ((1.5 - x) * (1.5 - x));
+}
+__device__ __forceinline__ double spline2(double x)  // interfaces/sort_parameters.cpp:21-30
+{
+  x = fabs(x);
+  if (x <= 0.5) return (0.75 - x * x);
+  if (x < 1.5) return 0.5 * (1.5 - x) * (1.5 - x);
+  return 0.0;
+}
+
+__device__ __forceinline__ void cells3(const Grid& g, const double* r, double* p)
+{
+  p[0] = to_cells(r[0], g.dx, g.inv_dx, g.exact_inv & 1);
+  p[1] = to_cells(r[1], g.dy, g.inv_dy, g.exact_inv & 2);
+  p[2] = to_cells(r[2], g.dz, g.inv_dz, g.exact_inv & 4);
+}
+
+// ImplicitEsirkepov::Shape::setup (implicit_esirkepov.cpp:11-60): the 54 weights factorise into
+// per-axis tables; start = round(midpoint) - 1
+struct CapW {
+  int start[3];
+  double sh1[3][2];          // 1/6 * S1 at the two points along the component's own axis
+  double sn[3][3], s0[3][3];  // S2 at the segment end (n) and start (0)
+};
+
+__device__ __forceinline__ void cap_weights(const Grid& g, const double* rn, const double* r0, CapW& w)
+{
+  double prn[3], pr0[3];
+  cells3(g, rn, prn);
+  cells3(g, r0, pr0);
+  constexpr double sixth = 1.0 / 6.0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double prh = 0.5 * (prn[a] + pr0[a]);
+    const double gc = round(prh);
+    w.start[a] = (int)gc - 1;
+    const double gv = gc + 0.5;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) w.sh1[a][i] = sixth * sf1(gv + (i - 1) - prh);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      w.sn[a][j] = sf2(j, gc + (j - 1) - prn[a]);
+      w.s0[a][j] = sf2(j, gc + (j - 1) - pr0[a]);
+    }
+  }
+}
+
+// E gather (FAST: from the tile) -- implicit_esirkepov.cpp:71-90; DEPOSIT: the same loop adds
+// alpha * v[c] * weight into J (:97-116)
+template <bool FAST, bool DEPOSIT>
+__device__ __forceinline__ void cap_apply(const CapCtx& k, const CapW& w, double* Ep, double alpha, const double* v)
+{
+  const int base = FAST ? k.tile_base(w.start) : 0;
+#pragma unroll
+  for (int cx = 0; cx < 3; ++cx) {
+    const int cy = (cx + 1) % 3, cz = (cx + 2) % 3;
+    double T[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk) T[j][kk] = w.sn[cy][j] * (2 * w.sn[cz][kk] + w.s0[cz][kk]) + w.s0[cy][j] * (2 * w.s0[cz][kk] + w.sn[cz][kk]);
+    double acc = 0.0;
+    const double av = DEPOSIT ? alpha * v[cx] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          int d[3];
+          d[cx] = i;
+          d[cy] = j;
+          d[cz] = kk;
+          const double wt = w.sh1[cx][i] * T[j][kk];
+          if (FAST) {
+            const int e = cx * CAP_VOL + base + (d[2] * CAP_NY + d[1]) * CAP_NX + d[0];
+            if (DEPOSIT)
+              atomicAdd(&k.Jt[e], av * wt);
+            else
+              acc += k.Et[e] * wt;
+          }
+          else {
+            const int64_t e = k.gidx(w.start[0] + d[0], w.start[1] + d[1], w.start[2] + d[2], cx);
+            if (DEPOSIT)
+              atomicAdd(&k.J[e], av * wt);
+            else
+              acc += __ldg(&k.E[e]) * wt;
+          }
+        }
+    if (!DEPOSIT) Ep[cx] += acc;
+  }
+}
+
+// B at the point r with the 2nd-order form factor: Shape::setup(r) (utils/shape.cpp:34-45) +
+// Shape::magnetic (shape.h:66-73).  Each 1-D weight vector has three non-zero entries inside the
+// reference's 3- or 4-point window: nodal from round(p) - 1, staggered from floor(p) - 1.
+template <bool FAST>
+__device__ __forceinline__ void cap_gather_B(const CapCtx& k, const double* p, const int* lo_n, const int* lo_s, double* Bp)
+{
+  double wn[3][3], ws[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      wn[a][j] = spline2(p[a] - (double)(lo_n[a] + j));
+      ws[a][j] = spline2(p[a] - ((double)(lo_s[a] + j) + 0.5));
+    }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    // component c is nodal along c and staggered along the other two axes
+    int lo[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) lo[a] = a == c ? lo_n[a] : lo_s[a];
+    const int base = FAST ? k.tile_base(lo) : 0;
+    double acc = 0.0;
+#pragma unroll
+    for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+      for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+        for (int ix = 0; ix < 3; ++ix) {
+          const double wz = c == 2 ? wn[2][kz] : ws[2][kz];
+          const double wy = c == 1 ? wn[1][jy] : ws[1][jy];
+          const double wx = c == 0 ? wn[0][ix] : ws[0][ix];
+          const double b = FAST ? k.Bt[c * CAP_VOL + base + (kz * CAP_NY + jy) * CAP_NX + ix] : __ldg(&k.B[k.gidx(lo[0] + ix, lo[1] + jy, lo[2] + kz, c)]);
+          acc += b * (wz * wy * wx);
+        }
+    Bp[c] += acc;
+  }
+}
+
+// ImplicitEsirkepov::interpolate (implicit_esirkepov.cpp:63-91) for one segment: adds into Es, Bs
+__device__ __forceinline__ void cap_interpolate(const CapCtx& k, const double* rsn, const double* rs0, double* Es, double* Bs)
+{
+  const double rh[3] = {0.5 * (rsn[0] + rs0[0]), 0.5 * (rsn[1] + rs0[1]), 0.5 * (rsn[2] + rs0[2])};
+  double p[3];
+  cells3(k.g, rh, p);
+  int lo_n[3], lo_s[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    lo_n[a] = (int)round(p[a]) - 1;
+    lo_s[a] = (int)floor(p[a]) - 1;
+  }
+  if (k.inside(lo_s, 4))
+    cap_gather_B<true>(k, p, lo_n, lo_s, Bs);
+  else
+    cap_gather_B<false>(k, p, lo_n, lo_s, Bs);
+  CapW w;
+  cap_weights(k.g, rsn, rs0, w);
+  if (k.inside(w.start, 3))
+    cap_apply<true, false>(k, w, Es, 0.0, nullptr);
+  else
+    cap_apply<false, false>(k, w, Es, 0.0, nullptr);
+}
+
+// cell_traversal (cell_traversal.cpp:3-77): calls f(segment start, segment end) for every straight
+// piece between crossings of the half-shifted cell faces; returns the number of pieces
+template <class F>
+__device__ __forceinline__ int for_each_segment(const Grid& g, const double* end, const double* start, F&& f)
+{
+  double ps[3], pe[3];
+  cells3(g, start, ps);
+  cells3(g, end, pe);
+  int curr[3], last[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    curr[a] = (int)round(ps[a]);
+    last[a] = (int)round(pe[a]);
+  }
+  if (curr[0] == last[0] && curr[1] == last[1] && curr[2] == last[2]) {
+    f(start, end);
+    return 1;
+  }
+  const double d3[3] = {g.dx, g.dy, g.dz};
+  const double maxv = 1.7976931348623157e308;
+  double dir[3], t3[3], dt3[3];
+  int sg[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    dir[a] = end[a] - start[a];
+    sg[a] = dir[a] > 0 ? 1 : -1;
+    const double next = (curr[a] + sg[a] * 0.5) * d3[a];
+    t3[a] = (dir[a] != 0) ? (next - start[a]) / dir[a] : maxv;
+    dt3[a] = (dir[a] != 0) ? d3[a] / dir[a] * sg[a] : 0.0;
+  }
+  double prev[3] = {start[0], start[1], start[2]};
+  int n = 0;
+  while (!(curr[0] == last[0] && curr[1] == last[1] && curr[2] == last[2]) && n < 255) {
+    int a;
+    if (t3[0] < t3[1])
+      a = (t3[0] < t3[2]) ? 0 : 2;
+    else
+      a = (t3[1] < t3[2]) ? 1 : 2;
+    double t;
+    // (no dynamic indexing of the small arrays)
+    if (a == 0) { t = t3[0]; curr[0] += sg[0]; t3[0] += dt3[0]; }
+    else if (a == 1) { t = t3[1]; curr[1] += sg[1]; t3[1] += dt3[1]; }
+    else { t = t3[2]; curr[2] += sg[2]; t3[2] += dt3[2]; }
+    const double pt[3] = {start[0] + dir[0] * t, start[1] + dir[1] * t, start[2] + dir[2] * t};
+    f(prev, pt);
+    prev[0] = pt[0];
+    prev[1] = pt[1];
+    prev[2] = pt[2];
+    ++n;
+  }
+  f(prev, end);
+  return n + 1;
+}
+
+// eccapfim::Particles::form_iteration for one particle (particles.cpp:73-176)
+__device__ __forceinline__ void cap_push_particle(const CapCtx& k, const CapArgs& a, double* r, double* v, int& it_out, int& seg_out)
+{
+  const Grid& g = k.g;
+  const double dt = g.dt, q = a.q, m = a.m;
+  const double maxv = 1.7976931348623157e308;
+  // :39-45 with the whole periodic box as the domain (start = 0, end = N on every axis)
+  const double lo[3] = {(0 - 0.5) * g.dx, (0 - 0.5) * g.dy, (0 - 0.5) * g.dz};
+  const double hi[3] = {(g.nx + 0.5) * g.dx, (g.ny + 0.5) * g.dy, (g.nz + 0.5) * g.dz};
+  const double L[3] = {g.Lx, g.Ly, g.Lz};
+  double r0[3] = {r[0], r[1], r[2]}, v0[3] = {v[0], v[1], v[2]};  // p0 (tmp); r, v are pn (curr)
+  double tau = 0.0, dtau = 0.0;
+  it_out = 0;
+  seg_out = 0;
+  for (; tau < dt; tau += dtau) {
+    double vh[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) vh[c] = 0.5 * (v[c] + v0[c]);
+    dtau = dt - tau;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {  // process_bound :49-56
+      double tb = maxv;
+      if (vh[c] > 0 && fabs(hi[c] - r0[c]) > 1e-7)
+        tb = (hi[c] - r0[c]) / vh[c];
+      else if (vh[c] < 0 && fabs(lo[c] - r0[c]) > 1e-7)
+        tb = (lo[c] - r0[c]) / vh[c];
+      dtau = fmin(dtau, tb);
+    }
+    const double a0 = q * a.mpw;
+    const double alpha = 0.5 * dtau * (q / m);
+    double Ep[3], Bp[3];
+    int nseg = 0;
+    auto set_fields = [&]() {  // :109-127
+      Ep[0] = Ep[1] = Ep[2] = Bp[0] = Bp[1] = Bp[2] = 0.0;
+      const double d = norm3d(r[0] - r0[0], r[1] - r0[1], r[2] - r0[2]);
+      nseg = for_each_segment(g, r, r0, [&](const double* rs0, const double* rsn) {
+        const double ds = norm3d(rsn[0] - rs0[0], rsn[1] - rs0[1], rsn[2] - rs0[2]);
+        const double bs = (d > 0 ? ds / d : 1.0);
+        double Es[3] = {0.0, 0.0, 0.0}, Bs[3] = {0.0, 0.0, 0.0};
+        cap_interpolate(k, rsn, rs0, Es, Bs);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          Ep[c] += Es[c] * bs;
+          Bp[c] += Bs[c] * bs;
+        }
+      });
+    };
+    auto residue = [&]() {  // :129-131
+      double vxb[3];
+      cross3(vh, Bp, vxb);
+      const double f = dtau * q / m;
+      return norm3d((v[0] - v0[0]) - f * (Ep[0] + vxb[0]), (v[1] - v0[1]) - f * (Ep[1] + vxb[1]), (v[2] - v0[2]) - f * (Ep[2] + vxb[2]));
+    };
+    set_fields();
+    double rn = residue();
+    const double rr0 = rn;
+    int it = 0;
+    for (; rn > a.cn_tol + a.cn_tol * rr0 && it < a.cn_maxit; ++it) {  // :136-148
+      double aa[3], b[3], w[3], wxb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        aa[c] = alpha * Ep[c];
+        b[c] = alpha * Bp[c];
+        w[c] = v0[c] + aa[c];
+      }
+      cross3(w, b, wxb);
+      const double wb = dot3(w, b), den = 1.0 + dot3(b, b);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) vh[c] = ((w[c] + wxb[c]) + b[c] * wb) / den;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        r[c] = r0[c] + dtau * vh[c];
+        v[c] = 2.0 * vh[c] - v0[c];
+      }
+      set_fields();
+      rn = residue();
+    }
+    it_out += it;
+    seg_out += nseg;
+    {  // current of this sub-step, :153-163
+      const double d = norm3d(r[0] - r0[0], r[1] - r0[1], r[2] - r0[2]);
+      for_each_segment(g, r, r0, [&](const double* rs0, const double* rsn) {
+        const double ds = norm3d(rsn[0] - rs0[0], rsn[1] - rs0[1], rsn[2] - rs0[2]);
+        const double bs = (d > 0 ? ds / d : 1.0);
+        CapW w;
+        cap_weights(g, rsn, rs0, w);
+        const double al = a0 * bs * (dtau / dt);
+        if (k.inside(w.start, 3))
+          cap_apply<true, true>(k, w, nullptr, al, vh);
+        else
+          cap_apply<false, true>(k, w, nullptr, al, vh);
+      });
+    }
+    bool reset = false;  // bound_periodic :58-68, :165-171
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (r[c] < 0.0) {
+        r[c] = L[c] - (0.0 - r[c]);
+        reset = true;
+      }
+      else if (r[c] > L[c]) {
+        r[c] = 0.0 + (r[c] - L[c]);
+        reset = true;
+      }
+    }
+    if (reset) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        r0[c] = r[c];
+        v0[c] = v[c];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CAP_THREADS) k_cap_push(Grid g, CapArgs a)
+{
+  __shared__ double Et[3 * CAP_VOL], Bt[3 * CAP_VOL], Jt[3 * CAP_VOL];
+  __shared__ unsigned long long cnt[2];
+  const int gx = blockIdx.x % a.groups_x, row = blockIdx.x / a.groups_x;  // row = zl * ny + cy
+  const int cy = row % g.ny, zl = row / g.ny;
+  const int cx0 = gx * CAP_CELLS, ncell = min(CAP_CELLS, g.nx - cx0);
+  if (threadIdx.x < 2) cnt[threadIdx.x] = 0ull;
+  for (int e = threadIdx.x; e < 3 * CAP_VOL; e += CAP_THREADS) {
+    const int x = e % CAP_NX, y = (e / CAP_NX) % CAP_NY, z = (e / (CAP_NX * CAP_NY)) % CAP_NZ, c = e / CAP_VOL;
+    const int64_t o = g.vidx(wrapi(cx0 - CAP_LO + x, g.nx), wrapi(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c);
+    Et[e] = __ldg(&a.E[o]);
+    Bt[e] = __ldg(&a.B[o]);
+    Jt[e] = 0.0;
+  }
+  const int64_t cell0 = ((int64_t)(zl + 1) * g.ny + cy) * g.nx + cx0;  // bin plane = zl + 1
+  const int32_t p0 = a.bin_start[cell0 << 3], p1 = a.bin_start[(cell0 + ncell) << 3];
+  __syncthreads();
+  CapCtx k{g, Et, Bt, Jt, cx0 - CAP_LO, cy - CAP_LO, g.z0 + zl - CAP_LO, a.E, a.B, a.J, a.error};
+  unsigned its = 0, segs = 0;
+  for (int32_t i = p0 + threadIdx.x; i < p1; i += CAP_THREADS) {
+    double r[3] = {a.p0[0][i], a.p0[1][i], a.p0[2][i]};
+    double v[3] = {a.p0[3][i], a.p0[4][i], a.p0[5][i]};
+    int it, ns;
+    cap_push_particle(k, a, r, v, it, ns);
+    a.pn[0][i] = r[0];
+    a.pn[1][i] = r[1];
+    a.pn[2][i] = r[2];
+    a.pn[3][i] = v[0];
+    a.pn[4][i] = v[1];
+    a.pn[5][i] = v[2];
+    its += it;
+    segs += ns;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    its += __shfl_down_sync(0xffffffffu, its, o);
+    segs += __shfl_down_sync(0xffffffffu, segs, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (its | segs)) {
+    atomicAdd(&cnt[0], (unsigned long long)its);
+    atomicAdd(&cnt[1], (unsigned long long)segs);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && cnt[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], cnt[threadIdx.x]);
+  // flush the current tile: one reduction per touched node instead of 54 per particle segment
+  for (int e = threadIdx.x; e < 3 * CAP_VOL; e += CAP_THREADS) {
+    const double val = Jt[e];
+    if (val == 0.0) continue;
+    const int x = e % CAP_NX, y = (e / CAP_NX) % CAP_NY, z = (e / (CAP_NX * CAP_NY)) % CAP_NZ, c = e / CAP_VOL;
+    atomicAdd(&a.J[g.vidx(wrapi(cx0 - CAP_LO + x, g.nx), wrapi(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c)], val);
+  }
+}
+
+// F = x + dt^2/4 curl^- curl^+ x - rhs0 + dt/2 J        (form_function, simulation.cpp:228-236;
+// rhs0 = E^n + dt/2 curl^- B^n is constant during the step)
+__global__ void __launch_bounds__(256) k_cap_function(Grid g, const double* __restrict__ xk, const double* __restrict__ rhs0, const double* __restrict__ J,
+                                                     double* __restrict__ F)
+{
+  const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (node >= g.ncl) return;
+  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = (int)(node / g.plane);
+  const int xm = x == 0 ? g.nx - 1 : x - 1, xp = x == g.nx - 1 ? 0 : x + 1;
+  const int ym = y == 0 ? g.ny - 1 : y - 1, yp = y == g.ny - 1 ? 0 : y + 1;
+  auto f = [&](int comp, int ox, int oy, int oz) {
+    const int xx = ox < 0 ? xm : (ox > 0 ? xp : x), yy = oy < 0 ? ym : (oy > 0 ? yp : y);
+    return __ldg(&xk[g.vidx(xx, yy, zl + oz, comp)]);
+  };
+  const double inv_d[3] = {1.0 / g.dx, 1.0 / g.dy, 1.0 / g.dz};
+  const double h = 0.25 * g.dt * g.dt;
+  const int64_t o = g.vidx(x, y, zl, 0);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) F[o + c] = ((f(c, 0, 0, 0) + h * curlcurl(c, inv_d, f)) - rhs0[o + c]) + (0.5 * g.dt) * J[o + c];
+}
+
+static inline int grid_for(int64_t n, int threads = 256)
+{
+  int64_t b = (n + threads - 1) / threads;
+  return (int)(b < 1 ? 1 : b);
+}
+
+static int cap_alloc(xb_ctx* c)
+{
+  if (c->cap_x) return 0;
+  for (double** v : {&c->cap_x, &c->cap_F, &c->cap_g, &c->cap_rhs0, &c->cap_J}) {
+    XB_CUDA(cudaMalloc(v, sizeof(double) * c->g.ntot));
+    XB_CUDA(cudaMemsetAsync(*v, 0, sizeof(double) * c->g.ntot, c->stream));
+  }
+  XB_CUDA(cudaMalloc(&c->cap_counters, 4 * sizeof(unsigned long long)));
+  return 0;
+}
+
+// form_iteration (simulation.cpp:132-155): J(x) from all sorts, then F(x).  x must be a ghosted vector.
+int cap_form_function(xb_ctx* c, double* x, double* F)
+{
+  const Grid& g = c->g;
+  Nonlinear& nl = c->nl;
+  XB_CHECK(cap_alloc(c));
+  XB_CHECK(halo_fill(c, x, GZ));
+  XB_CHECK(vec_zero(c, c->cap_J));
+  XB_CUDA(cudaMemsetAsync(c->cap_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (nl.profile) {
+    if (nl.events.size() < nl.events_used + 2) {
+      nl.events.resize(nl.events_used + 2, nullptr);
+      XB_CUDA(cudaEventCreate(&nl.events[nl.events_used]));
+      XB_CUDA(cudaEventCreate(&nl.events[nl.events_used + 1]));
+    }
+    e0 = nl.events[nl.events_used];
+    e1 = nl.events[nl.events_used + 1];
+    nl.events_used += 2;
+    XB_CUDA(cudaEventRecord(e0, c->stream));
+  }
+  int64_t total = 0;
+  for (auto& s : c->sorts) {
+    if (!s.sorted) XB_FAIL("eccapfim: particles are not sorted");
+    XB_CHECK(vec_zero(c, s.currI));  // Particles::J of this evaluation (clear_sources, particles.cpp:183-189)
+    total += s.count;
+    if (s.count == 0) continue;
+    CapArgs a;
+    for (int k = 0; k < 6; ++k) {
+      a.p0[k] = s.p[s.cur][k];
+      a.pn[k] = s.p[1 - s.cur][k];
+    }
+    a.bin_start = s.bin_start;
+    a.E = x;
+    a.B = c->B;
+    a.J = s.currI;
+    a.q = s.q;
+    a.m = s.m;
+    a.mpw = s.n / (double)s.Np;
+    a.cn_tol = nl.cn_tol;
+    a.cn_maxit = nl.cn_maxit;
+    a.groups_x = (g.nx + CAP_CELLS - 1) / CAP_CELLS;
+    a.counters = c->cap_counters;
+    a.error = reinterpret_cast<int*>(c->cap_counters + 2);
+    const int64_t blocks = (int64_t)a.groups_x * g.ny * g.nzl;
+    XB_LAUNCH(c, k_cap_push, (int)blocks, CAP_THREADS, 0, g, a);
+    XB_CHECK(halo_reduce(c, s.currI, GZ, GZ));  // DMLocalToGlobal(ADD), particles.cpp:179
+    const double one = 1.0;
+    const double* vs[1] = {s.currI};
+    XB_CHECK(axpy_multi(c, 1, vs, &one, c->cap_J));  // VecAXPY(J, 1, sort->J), simulation.cpp:188
+  }
+  if (nl.profile) XB_CUDA(cudaEventRecord(e1, c->stream));
+  XB_LAUNCH(c, k_cap_function, grid_for(g.ncl), 256, 0, g, x, c->cap_rhs0, c->cap_J, F);
+  ++nl.fevals;
+  nl.particles_per_eval = total;
+  return 0;
+}
+
+static int cap_read_counters(xb_ctx* c)
+{
+  Nonlinear& nl = c->nl;
+  unsigned long long h[4];
+  XB_CUDA(cudaMemcpyAsync(h, c->cap_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  const int err = (int)(h[2] & 0xffffffffu);
+  if (err) XB_FAIL("eccapfim: a particle moved beyond the ghost planes of its slab within one step");
+  double sums[2] = {(double)h[0], (double)h[1]};
+  double n = (double)nl.particles_per_eval;
+  if (c->g.nranks > 1) {
+    c->red_host[0] = sums[0];
+    c->red_host[1] = sums[1];
+    c->red_host[2] = n;
+    XB_CUDA(cudaMemcpyAsync(c->red_out, c->red_host, 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    XB_CHECK(comm_allreduce_sum(c, c->red_out, 3));
+    XB_CUDA(cudaMemcpyAsync(c->red_host, c->red_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    XB_CUDA(cudaStreamSynchronize(c->stream));
+    sums[0] = c->red_host[0];
+    sums[1] = c->red_host[1];
+    n = c->red_host[2];
+  }
+  nl.avg_cn = n > 0 ? sums[0] / n : 0.0;
+  nl.avg_cells = n > 0 ? sums[1] / n : 0.0;
+  return 0;
+}
+
+// rhs0 = E^n + dt/2 curl^- B^n
+int cap_prepare(xb_ctx* c)
+{
+  XB_CHECK(cap_alloc(c));
+  for (auto& s : c->sorts)
+    if (!s.sorted) {
+      if (c->g.nranks > 1) XB_CHECK(migrate_and_sort(c, s, 0.0));
+      else XB_CHECK(particles_sort(c, s, 0.0));
+    }
+  XB_CHECK(halo_fill(c, c->B, GZ));  // DMGlobalToLocal(B), simulation.cpp:64
+  XB_CHECK(vec_copy_owned(c, c->E, c->cap_rhs0));
+  XB_CHECK(curl_apply(c, false, c->B, c->cap_rhs0, 0.5 * c->g.dt, true));
+  return 0;
+}
+
+// symmetric least squares  G gamma = b  through a Jacobi eigen-decomposition; eigenvalues below
+// cut * max dropped (G is the Gram matrix of the Anderson differences, possibly near-singular)
+static void solve_gram(int m, std::vector<double> G, const std::vector<double>& b, std::vector<double>& gamma, double cut)
+{
+  std::vector<double> V((size_t)m * m, 0.0);
+  for (int i = 0; i < m; ++i) V[(size_t)i * m + i] = 1.0;
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j) (i == j ? diag : off) += G[(size_t)i * m + j] * G[(size_t)i * m + j];
+    if (off <= 1e-32 * diag) break;
+    for (int p = 0; p < m - 1; ++p)
+      for (int q = p + 1; q < m; ++q) {
+        const double apq = G[(size_t)p * m + q];
+        if (apq == 0.0) continue;
+        const double theta = (G[(size_t)q * m + q] - G[(size_t)p * m + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+        for (int k = 0; k < m; ++k) {  // columns p, q
+          const double gkp = G[(size_t)k * m + p], gkq = G[(size_t)k * m + q];
+          G[(size_t)k * m + p] = cs * gkp - sn * gkq;
+          G[(size_t)k * m + q] = sn * gkp + cs * gkq;
+        }
+        for (int k = 0; k < m; ++k) {  // rows p, q
+          const double gpk = G[(size_t)p * m + k], gqk = G[(size_t)q * m + k];
+          G[(size_t)p * m + k] = cs * gpk - sn * gqk;
+          G[(size_t)q * m + k] = sn * gpk + cs * gqk;
+        }
+        for (int k = 0; k < m; ++k) {
+          const double vkp = V[(size_t)k * m + p], vkq = V[(size_t)k * m + q];
+          V[(size_t)k * m + p] = cs * vkp - sn * vkq;
+          V[(size_t)k * m + q] = sn * vkp + cs * vkq;
+        }
+      }
+  }
+  double lmax = 0.0;
+  for (int i = 0; i < m; ++i) lmax = std::max(lmax, G[(size_t)i * m + i]);
+  gamma.assign(m, 0.0);
+  for (int j = 0; j < m; ++j) {
+    const double lam = G[(size_t)j * m + j];
+    if (!(lam > cut * lmax)) continue;
+    double vb = 0.0;
+    for (int i = 0; i < m; ++i) vb += V[(size_t)i * m + j] * b[i];
+    const double y = vb / lam;
+    for (int i = 0; i < m; ++i) gamma[i] += V[(size_t)i * m + j] * y;
+  }
+}
+
+static double norm_of(xb_ctx* c, const double* v, int* rc)
+{
+  const double* vs[1] = {v};
+  double n2 = 0.0;
+  *rc = dots(c, 1, vs, v, &n2);
+  return std::sqrt(n2);
+}
+
+// g = -P F,  P = ((1 + sigma) I + dt^2/4 curl curl)^-1 = 2 ((2 + 2 sigma) I + dt^2/2 curl curl)^-1
+static int cap_precondition(xb_ctx* c, const double* F, double* gout)
+{
+  Nonlinear& nl = c->nl;
+  if (nl.cheb_degree <= 0) return scale_into(c, F, -1.0, gout);
+  double sigma = 0.0;
+  for (auto& s : c->sorts) sigma += 0.25 * c->g.dt * c->g.dt * s.q * s.q * s.n / s.m;
+  XB_CHECK(cheb_solve_shifted(c, nl.cheb_degree, 2.0 + 2.0 * sigma, F, gout));
+  return scale_into(c, gout, -2.0, gout);
+}
+
+// calc_iteration (simulation.cpp:72-104): solve F(x) = 0 from x = E^n by Anderson acceleration of
+// x <- x + g(x), g = -P F.  Ring of `slots` difference pairs (dX_i = x_{i+1} - x_i, dG_i = g_{i+1} - g_i):
+// up to slots - 1 complete ("live") pairs plus the pending one whose dG is closed by the next evaluation.
+int cap_solve(xb_ctx* c)
+{
+  Nonlinear& nl = c->nl;
+  const int slots = std::max(2, std::min(nl.depth + 1, (int)(c->V.size() / 2)));
+  double** dX = c->V.data();
+  double** dG = c->V.data() + slots;
+  nl.hist.clear();
+  nl.iterations = 0;
+  nl.fevals = 0;
+  nl.reason = 0;
+  nl.events_used = 0;
+  double *x = c->cap_x, *F = c->cap_F, *gk = c->cap_g;
+  XB_CHECK(vec_copy_owned(c, c->E, x));  // initial guess E^{n+1/2,0} = E^n (:58-63)
+  XB_CHECK(cap_form_function(c, x, F));
+  int rc = 0;
+  double fnorm = norm_of(c, F, &rc);
+  XB_CHECK(rc);
+  nl.hist.push_back(fnorm);
+  const double ttol = fnorm * nl.rtol;
+  auto converged = [&](double fn) {  // SNESConvergedDefault with snorm = xnorm = 0
+    if (!(fn == fn)) return -4;      // SNES_DIVERGED_FNORM_NAN
+    if (fn < nl.atol) return 2;      // SNES_CONVERGED_FNORM_ABS
+    if (fn <= ttol) return 3;        // SNES_CONVERGED_FNORM_RELATIVE
+    return 0;
+  };
+  nl.reason = converged(fnorm);
+  std::vector<double> G((size_t)slots * slots, 0.0), row(slots), gamma;
+  int mk = 0, head = 0;  // live pairs; the pending slot
+  bool pending = false;
+  const double one = 1.0;
+  for (int k = 1; !nl.reason && k <= nl.maxit; ++k) {
+    XB_CHECK(cap_precondition(c, F, gk));
+    if (pending) {
+      // close the pending pair: dG[last] held -g_{k-1}
+      const int last = (head + slots - 1) % slots;
+      const double* vs[1] = {gk};
+      XB_CHECK(axpy_multi(c, 1, vs, &one, dG[last]));
+      if (mk < slots - 1) ++mk;
+      std::vector<const double*> ptr(mk);
+      for (int j = 0; j < mk; ++j) ptr[j] = dG[(head + slots - 1 - j) % slots];
+      XB_CHECK(dots(c, mk, ptr.data(), dG[last], row.data()));
+      for (int j = 0; j < mk; ++j) {
+        const int i = (head + slots - 1 - j) % slots;
+        G[(size_t)i * slots + last] = G[(size_t)last * slots + i] = row[j];
+      }
+    }
+    double* step = dX[head];  // becomes x_{k+1} - x_k
+    XB_CHECK(vec_copy_owned(c, gk, step));
+    if (mk > 0) {
+      std::vector<const double*> ptr(mk);
+      std::vector<int> live(mk);
+      for (int j = 0; j < mk; ++j) {
+        live[j] = (head + slots - 1 - j) % slots;
+        ptr[j] = dG[live[j]];
+      }
+      std::vector<double> bs(mk), Gs((size_t)mk * mk);
+      XB_CHECK(dots(c, mk, ptr.data(), gk, bs.data()));
+      for (int i = 0; i < mk; ++i)
+        for (int j = 0; j < mk; ++j) Gs[(size_t)i * mk + j] = G[(size_t)live[i] * slots + live[j]];
+      solve_gram(mk, Gs, bs, gamma, 1e-14);
+      std::vector<const double*> vs;
+      std::vector<double> cf;
+      for (int j = 0; j < mk; ++j) {
+        vs.push_back(dX[live[j]]);
+        cf.push_back(-gamma[j]);
+        vs.push_back(dG[live[j]]);
+        cf.push_back(-gamma[j]);
+      }
+      XB_CHECK(axpy_multi(c, (int)vs.size(), vs.data(), cf.data(), step));
+    }
+    XB_CHECK(scale_into(c, gk, -1.0, dG[head]));
+    pending = true;
+    {
+      const double* vs[1] = {step};
+      XB_CHECK(axpy_multi(c, 1, vs, &one, x));
+    }
+    head = (head + 1) % slots;
+    XB_CHECK(cap_form_function(c, x, F));
+    const double fprev = fnorm;
+    fnorm = norm_of(c, F, &rc);
+    XB_CHECK(rc);
+    nl.iterations = k;
+    nl.hist.push_back(fnorm);
+    nl.reason = converged(fnorm);
+    if (!nl.reason && fnorm > 1e3 * fprev) {  // the accelerated step went astray: restart the history
+      mk = 0;
+      pending = false;
+    }
+  }
+  if (!nl.reason) nl.reason = -5;  // SNES_DIVERGED_MAX_IT
+  nl.fnorm = fnorm;
+  XB_CHECK(cap_read_counters(c));
+  if (nl.profile) {
+    XB_CUDA(cudaStreamSynchronize(c->stream));
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < nl.events_used; i += 2) {
+      float t = 0.f;
+      XB_CUDA(cudaEventElapsedTime(&t, nl.events[i], nl.events[i + 1]));
+      ms += t;
+    }
+    nl.push_ms += ms;
+    nl.push_evals += (int64_t)(nl.events_used / 2);
+  }
+  if (nl.reason < 0) XB_FAIL("SNESSolve has not converged: reason " + std::to_string(nl.reason) + ", |F| = " + std::to_string(fnorm));
+  return 0;
+}
+
+// after_iteration (simulation.cpp:106-129): E, B update; the particles of the last evaluation become
+// the stored state and are re-binned
+int cap_finish(xb_ctx* c)
+{
+  XB_CHECK(final_update(c, c->cap_x));  // E = 2 x - E ; B -= dt curl^+ x
+  for (auto& s : c->sorts) {
+    if (s.count > 0 && c->track_ids)
+      XB_CUDA(cudaMemcpyAsync(s.id[1 - s.cur], s.id[s.cur], sizeof(uint64_t) * s.count, cudaMemcpyDeviceToDevice, c->stream));
+    s.cur = 1 - s.cur;
+    s.sorted = false;
+    if (c->g.nranks > 1) XB_CHECK(migrate_and_sort(c, s, 0.0));
+    else XB_CHECK(particles_sort(c, s, 0.0));
+  }
+  return 0;
+}
+
+}  // namespace xb

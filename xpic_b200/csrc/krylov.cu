@@ -20,7 +20,7 @@ int spmv(xb_ctx* c, int op, double* x, double* y);
 // One Chebyshev step fused with the matrix-free M:  z += d ; r -= M d ; d_out = a d + b r.
 // d_in carries valid ghosts (width 1); 144 B of HBM traffic per node, the 13-point stencil reads hit L1/L2.
 __global__ void __launch_bounds__(256) k_cheb_step(Grid g, const double* __restrict__ d_in, double* __restrict__ d_out, double* __restrict__ r,
-                                                  double* __restrict__ z, double a, double b)
+                                                  double* __restrict__ z, double a, double b, double diag)
 {
   const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (node >= g.ncl) return;
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) k_cheb_step(Grid g, const double* __restr
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const double dc = f(c, 0, 0, 0);
-    const double Md = 2.0 * dc + h * curlcurl(c, inv_d, f);
+    const double Md = diag * dc + h * curlcurl(c, inv_d, f);
     const double rn = r[o + c] - Md;
     z[o + c] += dc;
     r[o + c] = rn;
@@ -72,12 +72,13 @@ static int ensure_workspace(xb_ctx* c, int m)
   return 0;
 }
 
-// z ~= M^{-1} u by `deg` Chebyshev steps on [lmin, lmax] (Saad, Iterative Methods, Alg. 12.1).
-static int cheb_apply(xb_ctx* c, int deg, const double* u, double* z, double* work_r, double* work_d, double* work_Md)
+// z ~= (diag I + dt^2/2 curl curl)^{-1} u by `deg` Chebyshev steps on [lmin, lmax] (Saad, Iterative
+// Methods, Alg. 12.1); diag = 2 gives M^{-1}.
+static int cheb_apply(xb_ctx* c, int deg, const double* u, double* z, double* work_r, double* work_d, double* work_Md, double diag = 2.0)
 {
   const Grid& g = c->g;
-  const double lmin = 2.0;
-  const double lmax = 2.0 + 0.5 * g.dt * g.dt * 4.0 * (1.0 / (g.dx * g.dx) + 1.0 / (g.dy * g.dy) + 1.0 / (g.dz * g.dz));
+  const double lmin = diag;
+  const double lmax = diag + 0.5 * g.dt * g.dt * 4.0 * (1.0 / (g.dx * g.dx) + 1.0 / (g.dy * g.dy) + 1.0 / (g.dz * g.dz));
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
   const double sigma = theta / delta;
   double rho_old = 1.0 / sigma;
@@ -91,7 +92,7 @@ static int cheb_apply(xb_ctx* c, int deg, const double* u, double* z, double* wo
     const double rho = 1.0 / (2.0 * sigma - rho_old);
     if (k + 1 < deg) {
       XB_CHECK(halo_fill(c, d_cur, 1));
-      XB_LAUNCH(c, k_cheb_step, (int)((g.ncl + 255) / 256), 256, 0, g, d_cur, d_nxt, work_r, z, rho * rho_old, 2.0 * rho / delta);
+      XB_LAUNCH(c, k_cheb_step, (int)((g.ncl + 255) / 256), 256, 0, g, d_cur, d_nxt, work_r, z, rho * rho_old, 2.0 * rho / delta, diag);
       std::swap(d_cur, d_nxt);
     }
     else {
@@ -102,6 +103,13 @@ static int cheb_apply(xb_ctx* c, int deg, const double* u, double* z, double* wo
     rho_old = rho;
   }
   return 0;
+}
+
+// z ~= (diag I + dt^2/2 curl curl)^{-1} u  (eccapfim's residual preconditioner, eccapfim.cu)
+int cheb_solve_shifted(xb_ctx* c, int deg, double diag, const double* u, double* z)
+{
+  XB_CHECK(ensure_workspace(c, 0));
+  return cheb_apply(c, deg, u, z, c->cheb_r, c->cheb_d, c->cheb_Md, diag);
 }
 
 int krylov_prepare(xb_ctx* c)
