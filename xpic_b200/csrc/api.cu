@@ -729,6 +729,7 @@ int xb_eccapfim_function(xb_ctx* c, const double* x, double* f)
   XB_CHECK(cap_prepare(c));
   XB_CHECK(upload_owned(c, x, c->cap_x));
   XB_CHECK(cap_form_function(c, c->cap_x, c->cap_F));
+  XB_CHECK(cap_read_counters(c));
   XB_CHECK(download_owned(c, c->cap_F, f));
   XB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

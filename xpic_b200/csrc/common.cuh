@@ -243,6 +243,7 @@ int cap_prepare(xb_ctx* c);                              // init_iteration: sort
 int cap_form_function(xb_ctx* c, double* x, double* F);  // form_iteration: F(x), x ghosted
 int cap_solve(xb_ctx* c);                                // calc_iteration
 int cap_finish(xb_ctx* c);                               // after_iteration
+int cap_read_counters(xb_ctx* c);                        // averages of the last evaluation -> c->nl
 
 // ---- launch bookkeeping ----------------------------------------------------------------------
 #define XB_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \

@@ -575,7 +575,7 @@ int cap_form_function(xb_ctx* c, double* x, double* F)
   return 0;
 }
 
-static int cap_read_counters(xb_ctx* c)
+int cap_read_counters(xb_ctx* c)
 {
   Nonlinear& nl = c->nl;
   unsigned long long h[4];
