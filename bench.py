@@ -31,11 +31,13 @@ def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
-def workload(n_gpus):
+def workload(n_gpus, scheme="ecsim"):
     grid = os.environ.get("XPIC_BENCH_GRID")
-    ppc = env_int("XPIC_BENCH_PPC", 64)
+    ppc = env_int("XPIC_BENCH_PPC", 32 if scheme == "eccapfim" else 64)
     if grid:
         n = tuple(int(v) for v in grid.split(","))
+    elif scheme == "eccapfim":
+        n = (192, 192, 24 * n_gpus)  # BASELINE configs[4]: 192^3 x 32 ppc on 8 GPUs, the same slab per GPU for fewer
     elif n_gpus == 1:
         n = (128, 128, 128)
     else:
@@ -152,7 +154,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scheme", default="ecsim", choices=["ecsim", "ecsimcorr"])
+    ap.add_argument("--scheme", default="ecsim", choices=["ecsim", "ecsimcorr", "eccapfim"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -189,8 +191,8 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         comm_id = ids[0]
 
-    n, ppc = workload(world)
-    scheme = X.ECSIM if args.scheme == "ecsim" else X.ECSIMCORR
+    n, ppc = workload(world, args.scheme)
+    scheme = {"ecsim": X.ECSIM, "ecsimcorr": X.ECSIMCORR, "eccapfim": X.ECCAPFIM}[args.scheme]
     sim = X.Simulation(n, d=(0.5, 0.5, 0.5), dt=1.5, scheme=scheme, device=local_rank, rank=rank, nranks=world, comm_id=comm_id, track_ids=False)
     total = n[0] * n[1] * n[2] * ppc
     sid = sim.add_species(q=-1.0, m=1.0, n=1.0, Np=ppc, capacity=int(sim.ncl * ppc * 1.25) + 65536)
@@ -230,9 +232,15 @@ def main():
     launches0 = sim.launch_count()
     sim.timing_reset()
     sim.spmv_profile(True)
+    if args.scheme == "eccapfim":
+        sim.nonlinear_profile(1)
     barrier()
     ms = sim.run_steps(args.steps)
     barrier()
+    cap = None
+    if args.scheme == "eccapfim":
+        passes, pass_ms = sim.nonlinear_profile(0)
+        cap = dict(sim.nonlinear_info(), passes=passes, pass_ms=pass_ms / max(passes, 1))
     launches = sim.launch_count() - launches0
     spmv_n, spmv_ms = sim.spmv_profile_read()
     sim.spmv_profile(False)
@@ -282,6 +290,18 @@ def main():
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "launches_timed": spmv_n, "avg_launch_ms": spmv_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "spmv_share_of_step": (spmv_ms / ms) if ms else None}
+    if cap is not None:
+        # eccapfim: the dominant kernel is the particle pass of every residual evaluation (k_cap_push);
+        # its algorithmic HBM bytes are 96 B per particle (read r, v of the start state, write the pushed
+        # state) -- the kernel is bound by fp64 / shared-memory work, the HBM fraction says how far from a stream it is
+        npart_rank = float(nparticles) / world
+        pass_bytes = 96.0 * npart_rank
+        ach = pass_bytes / (cap["pass_ms"] * 1e-3) / 1e9 if cap["pass_ms"] else None
+        roofline = {"kernel": "k_cap_push (+ current halo add)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    "launches_timed": cap["passes"], "avg_launch_ms": cap["pass_ms"], "algorithmic_bytes_per_launch": pass_bytes,
+                    "share_of_step": cap["passes"] * cap["pass_ms"] / ms if ms else None,
+                    "particle_pushes_per_s": npart_rank * world * cap["passes"] / (ms * 1e-3) if ms else None}
 
     # ---- the other kernel families, timed in isolation on the resident state (CUDA events) --------
     kernels = None
@@ -313,12 +333,16 @@ def main():
                    "sample": f"4 ECSIM steps (after 1 warm-up) of a 32^3-cell x 64 ppc sample of the workload, {Ns} particles, {sps:.2f} s/step, {its_cpu} GMRES its; "
                              f"oracle/ C++ port, {cores} OpenMP threads (PETSc reference not buildable here)"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "metric": METRIC if args.scheme == "ecsim" else f"{args.scheme}_particle_steps_per_s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.scheme.upper()} 3D {n[0]}x{n[1]}x{n[2]} cells x {ppc} ppc fp64, periodic Maxwellian plasma", "particles": nparticles,
                        "parallelism": f"z-slabs x{world}", "krylov": f"GMRES(30) rtol=atol=1e-7, Chebyshev(M) degree {precond} right preconditioner",
                        "krylov_iterations_per_step": its, "l2": "inputs (6.2 GB operator, 6.4 GB particles per GPU) exceed the 126 MB L2; no flush needed",
-                       "stage_ms": {k: 1e3 * v for k, v in stage_s.items()}},
+                       "stage_ms": {k: 1e3 * v for k, v in stage_s.items()},
+                       **({"nonlinear": {"solver": "Anderson(10) on x - P F(x), P = Chebyshev(12) of ((1+sigma) I + dt^2/4 curl curl)^-1; atol = rtol = 1e-7 (reference)",
+                                         "iterations_last_step": cap["iterations"], "residual_evaluations_last_step": cap["fevals"],
+                                         "picard_iterations_per_particle": cap["avg_cn"], "path_pieces_per_particle": cap["avg_cells"],
+                                         "reference_residual_evaluations_per_step": 105}} if cap else {})},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "boundary": "xb_step_host: E, B, B0 uploaded from pinned host buffers, E, B and kinetic energy downloaded every step; particles resident"},

@@ -160,7 +160,9 @@ int xb_operator_upload(xb_ctx* ctx, const double* coef);
  * what = 2: canonical particle order inside every bin after a sort when ids are not tracked
  * (1: runs are bit-reproducible, costs one more pass over the particles; 0, default: keep the order
  * in which the scatter's integer atomics resolved -- results then differ run to run at round-off level;
- * with track_ids = 1 the order is always canonical, by id). */
+ * with track_ids = 1 the order is always canonical, by id);
+ * what = 3 the particle pass of eccapfim's residual evaluation (0: CTA-wide task machine, default;
+ * 1: one thread per particle). */
 int xb_set_option(xb_ctx* ctx, int32_t what, int32_t value);
 /* --- eccapfim (BASELINE config 5): xb_step / xb_stage with scheme XB_ECCAPFIM run
  * eccapfim::Simulation::timestep_implementation (src/impls/eccapfim/simulation.cpp:36-44); stages

@@ -27,7 +27,7 @@ def main():
     n = (12, 8, 8 * world)
     steps = int(os.environ.get("XPIC_CHECK_STEPS", "6"))
     ok = True
-    for scheme, oscheme in ((X.ECSIM, O.ECSIM), (X.ECSIMCORR, O.ECSIMCORR)):
+    for scheme, oscheme in ((X.ECSIM, O.ECSIM), (X.ECSIMCORR, O.ECSIMCORR), (X.ECCAPFIM, O.ECCAPFIM)):
         ids = [X.comm_unique_id() if rank == 0 else None]  # one communicator id per context
         dist.broadcast_object_list(ids, src=0)
         o = O.Oracle(n)  # only used for the reference's mt19937 initial particles
@@ -43,6 +43,7 @@ def main():
         slab.set_field("B", B0[lo:hi])
         for w in (0, 1):
             slab.solver_set(w, 1e-12, 1e-50, 1000, 30, 4)
+        slab.nonlinear_set(atol=1e-13, rtol=1e-30, particle_tol=1e-14)
         for _ in range(steps):
             slab.step()
         cnt = torch.tensor([slab.particle_count(0)], device="cuda")
@@ -58,6 +59,7 @@ def main():
             single.set_field("B", B0)
             for w in (0, 1):
                 single.solver_set(w, 1e-12, 1e-50, 1000, 30, 4)
+            single.nonlinear_set(atol=1e-13, rtol=1e-30, particle_tol=1e-14)
             for _ in range(steps):
                 single.step()
             E = np.concatenate([g[0] for g in gathered])

@@ -9,7 +9,7 @@ import xpic_b200 as X
 grid = tuple(int(v) for v in os.environ.get("XPIC_BENCH_GRID", "128,128,128").split(","))
 ppc = int(os.environ.get("XPIC_BENCH_PPC", "64"))
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-scheme = X.ECSIMCORR if os.environ.get("XPIC_SCHEME", "ecsim") == "ecsimcorr" else X.ECSIM
+scheme = {"ecsim": X.ECSIM, "ecsimcorr": X.ECSIMCORR, "eccapfim": X.ECCAPFIM}[os.environ.get("XPIC_SCHEME", "ecsim")]
 sim = X.Simulation(grid, scheme=scheme, track_ids=False)
 sid = sim.add_species(Np=ppc, capacity=int(sim.ncl * ppc * 1.25) + 65536)
 sim.set_particles_maxwellian(sid, grid[0] * grid[1] * grid[2] * ppc, T=0.1, seed=20261018)
@@ -17,6 +17,8 @@ p = int(os.environ.get("XPIC_BENCH_PRECOND", "6"))
 sim.solver_set(0, 1e-7, 1e-7, 100, 30, p)
 sim.solver_set(1, 1e-7, 1e-7, 100, 30, p)
 ms = sim.run_steps(steps)
+if scheme == X.ECCAPFIM:
+    print("nonlinear", sim.nonlinear_info())
 print("steps", steps, "ms/step", ms / steps, "its", sim.solver_info(0)[0], {k: round(1e3 * v[0] / max(v[1], 1), 3) for k, v in sim.timing().items()})
 if os.environ.get("XPIC_KERNEL_BENCH"):
     for what, name in ((0, "sort (no move)"), (1, "deposit (fields + cell blocks + gather)"), (2, "second push"), (3, "solve")):

@@ -672,6 +672,10 @@ int xb_set_option(xb_ctx* c, int32_t what, int32_t value)
     c->deterministic = value != 0;
     return 0;
   }
+  if (what == 3) {
+    c->cap_variant = value;
+    return 0;
+  }
   XB_FAIL("xb_set_option: unknown option");
 }
 

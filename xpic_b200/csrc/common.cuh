@@ -152,6 +152,7 @@ struct xb_ctx {
   int64_t coef_elems = 0;
   bool coef_valid = false;
   int deposit_variant = 0;  // 0: DMMA cell blocks (default), 1: scalar-FMA cell blocks (kept as a cross-check)
+  int cap_variant = 0;  // eccapfim particle pass: 0 CTA task machine (default), 1 thread per particle (cross-check)
   int esirkepov_variant = 0;  // 0: DMMA cell blocks + gather (default), 1: per-particle global reductions (cross-check)
   // deposit staging (cell blocks)
   double* stage = nullptr;

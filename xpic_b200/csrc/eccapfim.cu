@@ -60,7 +60,9 @@ struct CapArgs {
   int* error;
 };
 
-struct CapCtx {
+template <int NC>
+struct CapCtxT {
+  static constexpr int NX = NC + 5, NY = 6, NZ = 6, VOL = NX * NY * NZ;
   Grid g;
   const double* Et;
   const double* Bt;
@@ -73,9 +75,9 @@ struct CapCtx {
 
   __device__ __forceinline__ bool inside(const int* lo, int ext) const
   {
-    return lo[0] >= x0 && lo[0] + ext <= x0 + CAP_NX && lo[1] >= y0 && lo[1] + ext <= y0 + CAP_NY && lo[2] >= z0 && lo[2] + ext <= z0 + CAP_NZ;
+    return lo[0] >= x0 && lo[0] + ext <= x0 + NX && lo[1] >= y0 && lo[1] + ext <= y0 + NY && lo[2] >= z0 && lo[2] + ext <= z0 + NZ;
   }
-  __device__ __forceinline__ int tile_base(const int* lo) const { return ((lo[2] - z0) * CAP_NY + (lo[1] - y0)) * CAP_NX + (lo[0] - x0); }
+  __device__ __forceinline__ int tile_base(const int* lo) const { return ((lo[2] - z0) * NY + (lo[1] - y0)) * NX + (lo[0] - x0); }
   // element index in a ghosted global vector of the (unwrapped) global node (gx, gy, gz)
   __device__ __forceinline__ int64_t gidx(int gx, int gy, int gz, int c) const
   {
@@ -95,6 +97,7 @@ struct CapCtx {
     return g.vidx(x, y, zl, c);
   }
 };
+using CapCtx = CapCtxT<CAP_CELLS>;
 
 // ---- shapes -----------------------------------------------------------------------------------
 __device__ __forceinline__ double sf1(double x) { return 1.0 - fabs(x); }
@@ -150,8 +153,8 @@ __device__ __forceinline__ void cap_weights(const Grid& g, const double* rn, con
 
 // E gather (FAST: from the tile) -- implicit_esirkepov.cpp:71-90; DEPOSIT: the same loop adds
 // alpha * v[c] * weight into J (:97-116)
-template <bool FAST, bool DEPOSIT>
-__device__ __forceinline__ void cap_apply(const CapCtx& k, const CapW& w, double* Ep, double alpha, const double* v)
+template <bool FAST, bool DEPOSIT, class K>
+__device__ __forceinline__ void cap_apply(const K& k, const CapW& w, double* Ep, double alpha, const double* v)
 {
   const int base = FAST ? k.tile_base(w.start) : 0;
 #pragma unroll
@@ -176,7 +179,7 @@ __device__ __forceinline__ void cap_apply(const CapCtx& k, const CapW& w, double
           d[cz] = kk;
           const double wt = w.sh1[cx][i] * T[j][kk];
           if (FAST) {
-            const int e = cx * CAP_VOL + base + (d[2] * CAP_NY + d[1]) * CAP_NX + d[0];
+            const int e = cx * K::VOL + base + (d[2] * K::NY + d[1]) * K::NX + d[0];
             if (DEPOSIT)
               atomicAdd(&k.Jt[e], av * wt);
             else
@@ -197,8 +200,8 @@ __device__ __forceinline__ void cap_apply(const CapCtx& k, const CapW& w, double
 // B at the point r with the 2nd-order form factor: Shape::setup(r) (utils/shape.cpp:34-45) +
 // Shape::magnetic (shape.h:66-73).  Each 1-D weight vector has three non-zero entries inside the
 // reference's 3- or 4-point window: nodal from round(p) - 1, staggered from floor(p) - 1.
-template <bool FAST>
-__device__ __forceinline__ void cap_gather_B(const CapCtx& k, const double* p, const int* lo_n, const int* lo_s, double* Bp)
+template <bool FAST, class K>
+__device__ __forceinline__ void cap_gather_B(const K& k, const double* p, const int* lo_n, const int* lo_s, double* Bp)
 {
   double wn[3][3], ws[3][3];
 #pragma unroll
@@ -225,15 +228,28 @@ __device__ __forceinline__ void cap_gather_B(const CapCtx& k, const double* p, c
           const double wz = c == 2 ? wn[2][kz] : ws[2][kz];
           const double wy = c == 1 ? wn[1][jy] : ws[1][jy];
           const double wx = c == 0 ? wn[0][ix] : ws[0][ix];
-          const double b = FAST ? k.Bt[c * CAP_VOL + base + (kz * CAP_NY + jy) * CAP_NX + ix] : __ldg(&k.B[k.gidx(lo[0] + ix, lo[1] + jy, lo[2] + kz, c)]);
+          const double b = FAST ? k.Bt[c * K::VOL + base + (kz * K::NY + jy) * K::NX + ix] : __ldg(&k.B[k.gidx(lo[0] + ix, lo[1] + jy, lo[2] + kz, c)]);
           acc += b * (wz * wy * wx);
         }
     Bp[c] += acc;
   }
 }
 
+// out-of-tile paths (fast particles): kept out of line, they are rare and would triple the code size
+template <class K>
+__device__ __noinline__ void cap_gather_B_slow(const K& k, const double* p, const int* lo_n, const int* lo_s, double* Bp)
+{
+  cap_gather_B<false>(k, p, lo_n, lo_s, Bp);
+}
+template <bool DEPOSIT, class K>
+__device__ __noinline__ void cap_apply_slow(const K& k, const CapW& w, double* Ep, double alpha, const double* v)
+{
+  cap_apply<false, DEPOSIT>(k, w, Ep, alpha, v);
+}
+
 // ImplicitEsirkepov::interpolate (implicit_esirkepov.cpp:63-91) for one segment: adds into Es, Bs
-__device__ __forceinline__ void cap_interpolate(const CapCtx& k, const double* rsn, const double* rs0, double* Es, double* Bs)
+template <class K>
+__device__ __forceinline__ void cap_interpolate(const K& k, const double* rsn, const double* rs0, double* Es, double* Bs)
 {
   const double rh[3] = {0.5 * (rsn[0] + rs0[0]), 0.5 * (rsn[1] + rs0[1]), 0.5 * (rsn[2] + rs0[2])};
   double p[3];
@@ -247,13 +263,13 @@ __device__ __forceinline__ void cap_interpolate(const CapCtx& k, const double* r
   if (k.inside(lo_s, 4))
     cap_gather_B<true>(k, p, lo_n, lo_s, Bs);
   else
-    cap_gather_B<false>(k, p, lo_n, lo_s, Bs);
+    cap_gather_B_slow(k, p, lo_n, lo_s, Bs);
   CapW w;
   cap_weights(k.g, rsn, rs0, w);
   if (k.inside(w.start, 3))
     cap_apply<true, false>(k, w, Es, 0.0, nullptr);
   else
-    cap_apply<false, false>(k, w, Es, 0.0, nullptr);
+    cap_apply_slow<false>(k, w, Es, 0.0, nullptr);
 }
 
 // cell_traversal (cell_traversal.cpp:3-77): calls f(segment start, segment end) for every straight
@@ -400,7 +416,7 @@ __device__ __forceinline__ void cap_push_particle(const CapCtx& k, const CapArgs
         if (k.inside(w.start, 3))
           cap_apply<true, true>(k, w, nullptr, al, vh);
         else
-          cap_apply<false, true>(k, w, nullptr, al, vh);
+          cap_apply_slow<true>(k, w, nullptr, al, vh);
       });
     }
     bool reset = false;  // bound_periodic :58-68, :165-171
@@ -475,6 +491,292 @@ __global__ void __launch_bounds__(CAP_THREADS) k_cap_push(Grid g, CapArgs a)
     const double val = Jt[e];
     if (val == 0.0) continue;
     const int x = e % CAP_NX, y = (e / CAP_NX) % CAP_NY, z = (e / (CAP_NX * CAP_NY)) % CAP_NZ, c = e / CAP_VOL;
+    atomicAdd(&a.J[g.vidx(wrapi(cx0 - CAP_LO + x, g.nx), wrapi(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c)], val);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_cap_push_tasks: the same particle pass organised as a CTA-wide task machine.
+//
+// In k_cap_push a warp pays for the longest path (pieces) and the largest Picard count among its 32
+// particles: 97 % of the warps contain a particle that crosses a face, so every field evaluation
+// costs two piece evaluations, and the iteration count is the warp maximum.  Here a thread owns one
+// particle at a time (taken from a CTA work queue) and advances it through a small state machine;
+// every round each owner EMITS its path pieces as tasks into shared memory (gather tasks from the
+// front of the array, deposit tasks from the back), all threads then PROCESS the tasks densely
+// (32 tasks per warp instruction, whatever particle they belong to), and the owners CONSUME the
+// results in piece order -- so the arithmetic per particle and its order are those of k_cap_push,
+// and the work is proportional to the number of pieces actually evaluated.
+// ---------------------------------------------------------------------------------------------
+constexpr int CAP2_CELLS = 16;
+constexpr int CAP2_THREADS = 256;
+constexpr int CAP2_TASKS = 640;
+constexpr int CAP2_HALF = CAP2_TASKS / 2;
+constexpr int CAP2_TSTRIDE = 10;  // doubles per task: rs0[3], rsn[3], bs | al, vh[3]
+constexpr int CAP2_MAXSEG = 24;
+using CapCtx2 = CapCtxT<CAP2_CELLS>;
+constexpr int CAP2_SMEM_DOUBLES = 3 * 3 * CapCtx2::VOL + CAP2_TASKS * CAP2_TSTRIDE;
+
+enum { CS_FETCH = 0, CS_FIELDS = 1, CS_WAIT = 2, CS_DEPOSIT = 3, CS_DEPOSITED = 4, CS_IDLE = 5 };
+
+__global__ void __launch_bounds__(CAP2_THREADS) k_cap_push_tasks(Grid g, CapArgs a)
+{
+  extern __shared__ double smem[];
+  constexpr int VOL3 = 3 * CapCtx2::VOL;
+  double* Et = smem;
+  double* Bt = Et + VOL3;
+  double* Jt = Bt + VOL3;
+  double* tasks = Jt + VOL3;
+  __shared__ int q_next, n_gather, n_deposit;
+  __shared__ unsigned long long cnt[2];
+  const int tid = threadIdx.x;
+  const int gx = blockIdx.x % a.groups_x, row = blockIdx.x / a.groups_x;  // row = zl * ny + cy
+  const int cy = row % g.ny, zl = row / g.ny;
+  const int cx0 = gx * CAP2_CELLS, ncell = min(CAP2_CELLS, g.nx - cx0);
+  const int64_t cell0 = ((int64_t)(zl + 1) * g.ny + cy) * g.nx + cx0;  // bin plane = zl + 1
+  const int32_t p0 = a.bin_start[cell0 << 3], p1 = a.bin_start[(cell0 + ncell) << 3];
+  if (p0 == p1) return;
+  if (tid == 0) {
+    q_next = p0;
+    n_gather = 0;
+    n_deposit = 0;
+    cnt[0] = cnt[1] = 0ull;
+  }
+  for (int e = tid; e < VOL3; e += CAP2_THREADS) {
+    const int x = e % CapCtx2::NX, y = (e / CapCtx2::NX) % CapCtx2::NY, z = (e / (CapCtx2::NX * CapCtx2::NY)) % CapCtx2::NZ, c = e / CapCtx2::VOL;
+    const int64_t o = g.vidx(wrapi(cx0 - CAP_LO + x, g.nx), wrapi(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c);
+    Et[e] = __ldg(&a.E[o]);
+    Bt[e] = __ldg(&a.B[o]);
+    Jt[e] = 0.0;
+  }
+  __syncthreads();
+  CapCtx2 k{g, Et, Bt, Jt, cx0 - CAP_LO, cy - CAP_LO, g.z0 + zl - CAP_LO, a.E, a.B, a.J, a.error};
+
+  const double dt = g.dt, qm = a.q / a.m, a0 = a.q * a.mpw;
+  const double maxv = 1.7976931348623157e308;
+  const double lo[3] = {(0 - 0.5) * g.dx, (0 - 0.5) * g.dy, (0 - 0.5) * g.dz};
+  const double hi[3] = {(g.nx + 0.5) * g.dx, (g.ny + 0.5) * g.dy, (g.nz + 0.5) * g.dz};
+  const double L[3] = {g.Lx, g.Ly, g.Lz};
+
+  // the particle this thread owns
+  int state = CS_FETCH, idx = 0, it = 0, base = 0, nseg = 0;
+  bool first = true;
+  double r0[3], v0[3], r[3], v[3], vh[3];
+  double tau = 0.0, dtau = 0.0, rr0 = 0.0;
+  unsigned its = 0, segs = 0;
+
+  auto start_substep = [&]() {  // particles.cpp:84-101
+#pragma unroll
+    for (int c = 0; c < 3; ++c) vh[c] = 0.5 * (v[c] + v0[c]);
+    dtau = dt - tau;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double tb = maxv;
+      if (vh[c] > 0 && fabs(hi[c] - r0[c]) > 1e-7)
+        tb = (hi[c] - r0[c]) / vh[c];
+      else if (vh[c] < 0 && fabs(lo[c] - r0[c]) > 1e-7)
+        tb = (lo[c] - r0[c]) / vh[c];
+      dtau = fmin(dtau, tb);
+    }
+    it = 0;
+    first = true;
+  };
+  // number of straight pieces of r0 -> r: one more than the faces of the half-shifted lattice crossed
+  auto count_pieces = [&]() {
+    double ps[3], pe[3];
+    cells3(g, r0, ps);
+    cells3(g, r, pe);
+    int n = 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) n += abs((int)round(pe[c]) - (int)round(ps[c]));
+    return n;
+  };
+
+  while (true) {
+    // ---- emit ------------------------------------------------------------------------------------
+    if (state == CS_FETCH) {
+      idx = atomicAdd(&q_next, 1);
+      if (idx < p1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          r0[c] = r[c] = a.p0[c][idx];
+          v0[c] = v[c] = a.p0[3 + c][idx];
+        }
+        tau = 0.0;
+        start_substep();
+        state = CS_FIELDS;
+      }
+      else
+        state = CS_IDLE;
+    }
+    if (state == CS_FIELDS || state == CS_DEPOSIT) {
+      int n = count_pieces();
+      if (n > CAP2_MAXSEG) {
+        *a.error = 3;  // more than CAP2_MAXSEG - 1 cell faces crossed in one step
+        n = CAP2_MAXSEG;
+      }
+      const bool dep = state == CS_DEPOSIT;
+      // reserve (the counters only grow within a round): gather tasks fill the front half of the
+      // array, deposit tasks the back half; a reservation that does not fit waits for the next round
+      // and neutralises the part of its range that lies below the limit
+      auto put = [&](int slot_index, const double* rs0, const double* rsn, double wgt) {
+        const int slot = dep ? CAP2_TASKS - 1 - slot_index : slot_index;
+        double* t = tasks + slot * CAP2_TSTRIDE;
+        t[0] = rs0[0]; t[1] = rs0[1]; t[2] = rs0[2];
+        t[3] = rsn[0]; t[4] = rsn[1]; t[5] = rsn[2];
+        t[6] = wgt;
+        if (dep) {
+          t[7] = vh[0]; t[8] = vh[1]; t[9] = vh[2];
+        }
+      };
+      const int mine = atomicAdd(dep ? &n_deposit : &n_gather, n);
+      if (mine + n <= CAP2_HALF) {
+        base = mine;
+        const double d = norm3d(r[0] - r0[0], r[1] - r0[1], r[2] - r0[2]);
+        int kk = 0;
+        for_each_segment(g, r, r0, [&](const double* rs0, const double* rsn) {
+          if (kk >= n) return;
+          const double ds = norm3d(rsn[0] - rs0[0], rsn[1] - rs0[1], rsn[2] - rs0[2]);
+          const double bs = (d > 0 ? ds / d : 1.0);
+          put(base + kk, rs0, rsn, dep ? a0 * bs * (dtau / dt) : bs);
+          ++kk;
+        });
+        nseg = kk;
+        for (; kk < n; ++kk) put(base + kk, r0, r0, 0.0);
+        state = dep ? CS_DEPOSITED : CS_WAIT;
+      }
+      else {
+        for (int s = mine; s < min(mine + n, CAP2_HALF); ++s) put(s, r0, r0, 0.0);
+      }
+    }
+    __syncthreads();
+    // ---- process ---------------------------------------------------------------------------------
+    {
+      const int ng = min(n_gather, CAP2_HALF), nd = min(n_deposit, CAP2_HALF);
+      for (int t = tid; t < ng; t += CAP2_THREADS) {
+        double* tk = tasks + t * CAP2_TSTRIDE;
+        const double rs0[3] = {tk[0], tk[1], tk[2]}, rsn[3] = {tk[3], tk[4], tk[5]};
+        double Es[3] = {0.0, 0.0, 0.0}, Bs[3] = {0.0, 0.0, 0.0};
+        cap_interpolate(k, rsn, rs0, Es, Bs);
+        tk[0] = Es[0]; tk[1] = Es[1]; tk[2] = Es[2];
+        tk[3] = Bs[0]; tk[4] = Bs[1]; tk[5] = Bs[2];
+      }
+      // deposit tasks are taken by the threads in reverse so that both kinds spread over all warps
+      for (int t = CAP2_THREADS - 1 - tid; t < nd; t += CAP2_THREADS) {
+        const double* tk = tasks + (CAP2_TASKS - 1 - t) * CAP2_TSTRIDE;
+        const double rs0[3] = {tk[0], tk[1], tk[2]}, rsn[3] = {tk[3], tk[4], tk[5]};
+        const double al = tk[6], vv[3] = {tk[7], tk[8], tk[9]};
+        CapW w;
+        cap_weights(g, rsn, rs0, w);
+        if (k.inside(w.start, 3))
+          cap_apply<true, true>(k, w, nullptr, al, vv);
+        else
+          cap_apply_slow<true>(k, w, nullptr, al, vv);
+      }
+    }
+    __syncthreads();
+    // ---- consume ---------------------------------------------------------------------------------
+    if (state == CS_WAIT) {
+      double Ep[3] = {0.0, 0.0, 0.0}, Bp[3] = {0.0, 0.0, 0.0};
+      for (int s = 0; s < nseg; ++s) {
+        const double* tk = tasks + (base + s) * CAP2_TSTRIDE;
+        const double bs = tk[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          Ep[c] += tk[c] * bs;
+          Bp[c] += tk[3 + c] * bs;
+        }
+      }
+      double vxb[3];
+      cross3(vh, Bp, vxb);
+      const double f = dtau * qm;
+      const double rn = norm3d((v[0] - v0[0]) - f * (Ep[0] + vxb[0]), (v[1] - v0[1]) - f * (Ep[1] + vxb[1]), (v[2] - v0[2]) - f * (Ep[2] + vxb[2]));
+      if (first) {
+        rr0 = rn;
+        first = false;
+      }
+      if (rn > a.cn_tol + a.cn_tol * rr0 && it < a.cn_maxit) {  // particles.cpp:136-148
+        const double alpha = 0.5 * dtau * qm;
+        double aa[3], b[3], w[3], wxb[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          aa[c] = alpha * Ep[c];
+          b[c] = alpha * Bp[c];
+          w[c] = v0[c] + aa[c];
+        }
+        cross3(w, b, wxb);
+        const double wb = dot3(w, b), den = 1.0 + dot3(b, b);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vh[c] = ((w[c] + wxb[c]) + b[c] * wb) / den;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          r[c] = r0[c] + dtau * vh[c];
+          v[c] = 2.0 * vh[c] - v0[c];
+        }
+        ++it;
+        state = CS_FIELDS;
+      }
+      else {
+        its += it;
+        segs += nseg;
+        state = CS_DEPOSIT;
+      }
+    }
+    else if (state == CS_DEPOSITED) {
+      bool reset = false;  // bound_periodic, particles.cpp:58-68,165-171
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (r[c] < 0.0) {
+          r[c] = L[c] - (0.0 - r[c]);
+          reset = true;
+        }
+        else if (r[c] > L[c]) {
+          r[c] = 0.0 + (r[c] - L[c]);
+          reset = true;
+        }
+      }
+      if (reset) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          r0[c] = r[c];
+          v0[c] = v[c];
+        }
+      }
+      tau += dtau;
+      if (tau < dt) {
+        start_substep();
+        state = CS_FIELDS;
+      }
+      else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          a.pn[c][idx] = r[c];
+          a.pn[3 + c][idx] = v[c];
+        }
+        state = CS_FETCH;
+      }
+    }
+    if (tid == 0) {
+      n_gather = 0;
+      n_deposit = 0;
+    }
+    if (!__syncthreads_or(state != CS_IDLE)) break;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    its += __shfl_down_sync(0xffffffffu, its, o);
+    segs += __shfl_down_sync(0xffffffffu, segs, o);
+  }
+  if ((tid & 31) == 0 && (its | segs)) {
+    atomicAdd(&cnt[0], (unsigned long long)its);
+    atomicAdd(&cnt[1], (unsigned long long)segs);
+  }
+  __syncthreads();
+  if (tid < 2 && cnt[tid]) atomicAdd(&a.counters[tid], cnt[tid]);
+  for (int e = tid; e < VOL3; e += CAP2_THREADS) {
+    const double val = Jt[e];
+    if (val == 0.0) continue;
+    const int x = e % CapCtx2::NX, y = (e / CapCtx2::NX) % CapCtx2::NY, z = (e / (CapCtx2::NX * CapCtx2::NY)) % CapCtx2::NZ, c = e / CapCtx2::VOL;
     atomicAdd(&a.J[g.vidx(wrapi(cx0 - CAP_LO + x, g.nx), wrapi(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c)], val);
   }
 }
@@ -558,11 +860,24 @@ int cap_form_function(xb_ctx* c, double* x, double* F)
     a.mpw = s.n / (double)s.Np;
     a.cn_tol = nl.cn_tol;
     a.cn_maxit = nl.cn_maxit;
-    a.groups_x = (g.nx + CAP_CELLS - 1) / CAP_CELLS;
     a.counters = c->cap_counters;
     a.error = reinterpret_cast<int*>(c->cap_counters + 2);
-    const int64_t blocks = (int64_t)a.groups_x * g.ny * g.nzl;
-    XB_LAUNCH(c, k_cap_push, (int)blocks, CAP_THREADS, 0, g, a);
+    if (c->cap_variant == 1) {  // thread-per-particle kernel, kept as a cross-check
+      a.groups_x = (g.nx + CAP_CELLS - 1) / CAP_CELLS;
+      const int64_t blocks = (int64_t)a.groups_x * g.ny * g.nzl;
+      XB_LAUNCH(c, k_cap_push, (int)blocks, CAP_THREADS, 0, g, a);
+    }
+    else {
+      static bool attr_set = false;
+      const size_t smem = sizeof(double) * CAP2_SMEM_DOUBLES;
+      if (!attr_set) {
+        XB_CUDA(cudaFuncSetAttribute(k_cap_push_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      a.groups_x = (g.nx + CAP2_CELLS - 1) / CAP2_CELLS;
+      const int64_t blocks = (int64_t)a.groups_x * g.ny * g.nzl;
+      XB_LAUNCH(c, k_cap_push_tasks, (int)blocks, CAP2_THREADS, smem, g, a);
+    }
     XB_CHECK(halo_reduce(c, s.currI, GZ, GZ));  // DMLocalToGlobal(ADD), particles.cpp:179
     const double one = 1.0;
     const double* vs[1] = {s.currI};
