@@ -114,6 +114,10 @@ __device__ __forceinline__ double spline2(double x)  // interfaces/sort_paramete
   return 0.0;
 }
 
+// |(x, y, z)|: the reference's Vector3::length() is std::hypot (utils/vector3.h:160-164); the plain
+// square root differs from it by an ulp at most and avoids hypot's rescaling (lengths here are O(1))
+__device__ __forceinline__ double len3(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
+
 __device__ __forceinline__ void cells3(const Grid& g, const double* r, double* p)
 {
   p[0] = to_cells(r[0], g.dx, g.inv_dx, g.exact_inv & 1);
@@ -328,8 +332,9 @@ __device__ __forceinline__ int for_each_segment(const Grid& g, const double* end
     dir[a] = end[a] - start[a];
     sg[a] = dir[a] > 0 ? 1 : -1;
     const double next = (curr[a] + sg[a] * 0.5) * d3[a];
-    t3[a] = (dir[a] != 0) ? (next - start[a]) / dir[a] : maxv;
-    dt3[a] = (dir[a] != 0) ? d3[a] / dir[a] * sg[a] : 0.0;
+    const double inv = (dir[a] != 0) ? 1.0 / dir[a] : 0.0;  // one division per axis (the reference divides twice)
+    t3[a] = (dir[a] != 0) ? (next - start[a]) * inv : maxv;
+    dt3[a] = (dir[a] != 0) ? d3[a] * inv * sg[a] : 0.0;
   }
   double prev[3] = {start[0], start[1], start[2]};
   int n = 0;
@@ -389,9 +394,9 @@ __device__ __forceinline__ void cap_push_particle(const CapCtx& k, const CapArgs
     int nseg = 0;
     auto set_fields = [&]() {  // :109-127
       Ep[0] = Ep[1] = Ep[2] = Bp[0] = Bp[1] = Bp[2] = 0.0;
-      const double d = norm3d(r[0] - r0[0], r[1] - r0[1], r[2] - r0[2]);
+      const double d = len3(r[0] - r0[0], r[1] - r0[1], r[2] - r0[2]);
       nseg = for_each_segment(g, r, r0, [&](const double* rs0, const double* rsn) {
-        const double ds = norm3d(rsn[0] - rs0[0], rsn[1] - rs0[1], rsn[2] - rs0[2]);
+        const double ds = len3(rsn[0] - rs0[0], rsn[1] - rs0[1], rsn[2] - rs0[2]);
         const double bs = (d > 0 ? ds / d : 1.0);
         double Es[3] = {0.0, 0.0, 0.0}, Bs[3] = {0.0, 0.0, 0.0};
         cap_interpolate(k, rsn, rs0, Es, Bs);
@@ -406,7 +411,7 @@ __device__ __forceinline__ void cap_push_particle(const CapCtx& k, const CapArgs
       double vxb[3];
       cross3(vh, Bp, vxb);
       const double f = dtau * q / m;
-      return norm3d((v[0] - v0[0]) - f * (Ep[0] + vxb[0]), (v[1] - v0[1]) - f * (Ep[1] + vxb[1]), (v[2] - v0[2]) - f * (Ep[2] + vxb[2]));
+      return len3((v[0] - v0[0]) - f * (Ep[0] + vxb[0]), (v[1] - v0[1]) - f * (Ep[1] + vxb[1]), (v[2] - v0[2]) - f * (Ep[2] + vxb[2]));
     };
     set_fields();
     double rn = residue();
@@ -435,9 +440,9 @@ __device__ __forceinline__ void cap_push_particle(const CapCtx& k, const CapArgs
     it_out += it;
     seg_out += nseg;
     {  // current of this sub-step, :153-163
-      const double d = norm3d(r[0] - r0[0], r[1] - r0[1], r[2] - r0[2]);
+      const double d = len3(r[0] - r0[0], r[1] - r0[1], r[2] - r0[2]);
       for_each_segment(g, r, r0, [&](const double* rs0, const double* rsn) {
-        const double ds = norm3d(rsn[0] - rs0[0], rsn[1] - rs0[1], rsn[2] - rs0[2]);
+        const double ds = len3(rsn[0] - rs0[0], rsn[1] - rs0[1], rsn[2] - rs0[2]);
         const double bs = (d > 0 ? ds / d : 1.0);
         CapW w;
         cap_weights(g, rsn, rs0, w);
@@ -631,7 +636,7 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
   };
   // pieces of r0 -> r into queue slots [first_slot, first_slot + n); slots the walk does not fill are neutralised
   auto emit = [&](double* queue, int stride, int first_slot, int n, bool dep) {
-    const double d = norm3d(r[0] - r0[0], r[1] - r0[1], r[2] - r0[2]);
+    const double d = len3(r[0] - r0[0], r[1] - r0[1], r[2] - r0[2]);
     int kk = 0;
     auto put = [&](const double* rs0, const double* rsn, double wgt) {
       double* t = queue + (first_slot + kk) * stride;
@@ -645,7 +650,7 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
     };
     for_each_segment(g, r, r0, [&](const double* rs0, const double* rsn) {
       if (kk >= n) return;
-      const double ds = norm3d(rsn[0] - rs0[0], rsn[1] - rs0[1], rsn[2] - rs0[2]);
+      const double ds = len3(rsn[0] - rs0[0], rsn[1] - rs0[1], rsn[2] - rs0[2]);
       const double bs = (d > 0 ? ds / d : 1.0);
       put(rs0, rsn, dep ? a0 * bs * (dtau / dt) : bs);
     });
@@ -727,7 +732,7 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
       double vxb[3];
       cross3(vh, Bp, vxb);
       const double f = dtau * qm;
-      const double rn = norm3d((v[0] - v0[0]) - f * (Ep[0] + vxb[0]), (v[1] - v0[1]) - f * (Ep[1] + vxb[1]), (v[2] - v0[2]) - f * (Ep[2] + vxb[2]));
+      const double rn = len3((v[0] - v0[0]) - f * (Ep[0] + vxb[0]), (v[1] - v0[1]) - f * (Ep[1] + vxb[1]), (v[2] - v0[2]) - f * (Ep[2] + vxb[2]));
       if (first) {
         rr0 = rn;
         first = false;
@@ -813,7 +818,10 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
     const int nd = min(n_deposit, CAP2_DCAP);
     const int take = busy ? (nd / CAP2_THREADS) * CAP2_THREADS : nd;
     if (take > 0) {
-      for (int t = tid; t < take; t += CAP2_THREADS) deposit_task(dq + t * CAP2_DSTRIDE);
+      // lane l of warp w takes tasks 8 l + w (+ 256 j): the tasks of one warp instruction are 8 apart in the
+      // queue, i.e. mostly particles of different half cells, so their shared-memory additions rarely
+      // collide (consecutive tasks share a 54-node window and would serialise the CAS loops)
+      for (int t = (tid & 31) * (CAP2_THREADS / 32) + (tid >> 5); t < take; t += CAP2_THREADS) deposit_task(dq + t * CAP2_DSTRIDE);
       __syncthreads();
       const int rem = nd - take;  // < CAP2_THREADS <= take: source and destination do not overlap
       for (int e = tid; e < rem * CAP2_DSTRIDE; e += CAP2_THREADS) dq[e] = dq[take * CAP2_DSTRIDE + e];
