@@ -176,3 +176,35 @@ def test_empty_and_single_particle():
     s2.step()
     assert rel_err(s2.get_field("E"), o.get_field("E")) < 1e-9
     assert rel_err(s2.get_particles()[0], o.get_particles()[0]) < 1e-10
+
+
+def test_host_program_writes_the_reference_tables(tmp_path):
+    """The C++ host mirror with "Simulation": "eccapfim": temporal/energy.txt against the golden table and
+    convergence_history.txt in the reference's format (eccapfim/convergence_history.cpp:11-44)."""
+    import json
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "xpic_b200", "_build", "xpic_b200.out")
+    if not os.path.exists(exe):
+        pytest.skip("host program not built")
+    cfg = json.load(open(os.path.join(ROOT, "configs", "eccapfim_ex1.json")))
+    cfg["OutputDirectory"] = str(tmp_path / "eccapfim_ex1")
+    path = tmp_path / "eccapfim_ex1.json"
+    path.write_text(json.dumps(cfg))
+    res = subprocess.run([exe, str(path)], check=True, capture_output=True, timeout=300, text=True)
+    assert "SNESSolve() has finished" in res.stdout
+    tg, gold = O.read_table(os.path.join(GOLDEN, "eccapfim_ex1", "energy.txt"))
+    to, out = O.read_table(str(tmp_path / "eccapfim_ex1" / "temporal" / "energy.txt"))
+    assert to == tg and out.shape[0] == 11
+    # reference tolerances all the way (SNES 1e-7, particles 0.5e-7): the energy drifts by ~1.5e-7 per step
+    np.testing.assert_allclose(out[:, 3], gold[:, 3], rtol=1e-5)
+    np.testing.assert_allclose(out[:, 1], gold[:, 1], rtol=1e-4, atol=1e-12)
+    np.testing.assert_allclose(out[:, 2], gold[:, 2], rtol=2e-3, atol=1e-12)
+    lines = open(tmp_path / "eccapfim_ex1" / "temporal" / "convergence_history.txt").read().splitlines()
+    assert lines[0].split()[:5] == ["Time", "AvgCN_el", "AvgTC_el", "FEvals", "ItNum"]
+    row = lines[2].split()
+    assert int(row[3]) == int(row[4]) + 1 and len(row) == 5 + int(row[3])  # one evaluation per iteration + the first
+    _, cons = O.read_table(str(tmp_path / "eccapfim_ex1" / "temporal" / "energy_conservation.txt"))
+    assert np.max(np.abs(cons[:, -1])) < 1e-6

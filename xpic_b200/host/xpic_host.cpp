@@ -129,7 +129,11 @@ void Simulation::set_option(const std::string& key, const std::string& value)
     return false;
   };
   if (tol("", 0) || tol("predict_", 0) || tol("correct_", 1)) return;
-  if (key == "-curl_sign") curl_sign_ = std::stoi(value);
+  if (key == "-snes_atol") snes_atol_ = std::stod(value);  // SNESSetFromOptions, eccapfim/simulation.cpp:390
+  else if (key == "-snes_rtol") snes_rtol_ = std::stod(value);
+  else if (key == "-snes_stol") snes_stol_ = std::stod(value);
+  else if (key == "-snes_max_it") snes_maxit_ = std::stoi(value);
+  else if (key == "-curl_sign") curl_sign_ = std::stoi(value);
   else if (key == "-device") device_ = std::stoi(value);
   else if (key == "-precond") precond_ = std::stoi(value);
   else throw std::runtime_error("Unknown option " + key);
@@ -143,7 +147,8 @@ int Simulation::configure(const std::string& config_path)
   cfg.at("Simulation").get_to(scheme_name);
   if (scheme_name == "ecsim") scheme = XB_ECSIM;
   else if (scheme_name == "ecsimcorr") scheme = XB_ECSIMCORR;
-  else throw std::runtime_error("Unknown simulation is used: " + scheme_name + " (this build covers ecsim, ecsimcorr)");
+  else if (scheme_name == "eccapfim") scheme = XB_ECCAPFIM;
+  else throw std::runtime_error("Unknown simulation is used: " + scheme_name + " (this build covers ecsim, ecsimcorr, eccapfim)");
   if (cfg.contains("OutputDirectory")) cfg.at("OutputDirectory").get_to(out_dir);
 
   const json& ge = cfg.at("Geometry");  // utils/world.cpp:14-34
@@ -231,6 +236,8 @@ int Simulation::initialize()
   g.track_ids = 0;
   B200_CALL(xb_create(&g, nullptr, &ctx));
   for (int w = 0; w < 2; ++w) B200_CALL(xb_solver_set(ctx, w, rtol_[w], atol_[w], maxit_[w], 30, precond_));
+  // SNESSetTolerances + the Crank-Nicolson tolerance 0.5 * atol (eccapfim/simulation.cpp:384, particles.cpp:99-101)
+  B200_CALL(xb_nonlinear_set(ctx, snes_atol_, snes_rtol_, snes_stol_, snes_maxit_, 10, 12, 0.5 * snes_atol_, 30));
 
   const int64_t ncells = (int64_t)geom.geom_nx * geom.geom_ny * geom.geom_nz;
   for (const auto& p : sorts_) {
@@ -271,6 +278,10 @@ int Simulation::initialize()
   energy_cons_ = std::make_unique<Table>(out_dir + "/temporal/energy_conservation.txt");
   K_.assign(particles_.size(), 0.0);
   K0_ = stdK_ = K_;
+  if (scheme == XB_ECCAPFIM) {  // eccapfim/simulation.cpp:28
+    convergence_ = std::make_unique<Table>(out_dir + "/temporal/convergence_history.txt");
+    if (diagnose_convergence(start)) return 1;
+  }
   return diagnose_energy(start);
 }
 
@@ -285,15 +296,29 @@ int Simulation::calculate()
   for (int t = start + 1; t <= geom.geom_nt; ++t) {
     std::cout << std::format("Timestep = {:.4f} [1/w_pe] = {} [dt]", t * geom.dt, t) << "\n";
     if (timestep_implementation(t)) return 1;
-    int its = 0, reason = 0;
-    double rn = 0;
-    xb_solver_info(ctx, XB_SOLVER_PREDICT, &its, &rn, &reason);
-    std::cout << std::format("  KSPSolve() has finished: reason {}, iterations {}, residual norm {:.3e}", reason, its, rn) << "\n";
+    if (scheme == XB_ECCAPFIM) {  // the LOG lines of calc_iteration, eccapfim/simulation.cpp:80-96
+      int32_t its = 0, fev = 0, reason = 0;
+      double fn = 0, cn = 0, tc = 0;
+      xb_nonlinear_info(ctx, &its, &fev, &reason, &fn, &cn, &tc);
+      std::cout << std::format("  SNESSolve() has finished: reason {}, iterations {}, function evaluations {}, function norm {:e}", reason, its, fev, fn) << "\n";
+      std::cout << std::format("    Number of Crank-Nicolson iterations is {:3.4f}", cn) << "\n";
+      std::cout << std::format("    Number of traversed cells is {:3.4f}", tc) << "\n";
+      if (diagnose_convergence(t)) return 1;
+    }
+    else {
+      int its = 0, reason = 0;
+      double rn = 0;
+      xb_solver_info(ctx, XB_SOLVER_PREDICT, &its, &rn, &reason);
+      std::cout << std::format("  KSPSolve() has finished: reason {}, iterations {}, residual norm {:.3e}", reason, its, rn) << "\n";
+    }
     if (diagnose_energy(t)) return 1;
   }
   std::cout << "Summary of Stages:\n";  // utils/sync_clock.cpp:85-91
-  const char* names[XB_STAGE_COUNT] = {"Clear sources", "First push", "Advance field", "Second push", "Correct fields", "Final update"};
+  const char* names_ec[XB_STAGE_COUNT] = {"Clear sources", "First push", "Advance field", "Second push", "Correct fields", "Final update"};
+  const char* names_cap[XB_STAGE_COUNT] = {"init_iteration", "-", "calc_iteration", "-", "-", "after_iteration"};  // eccapfim/simulation.cpp:46,72,106
+  const char* const* names = scheme == XB_ECCAPFIM ? names_cap : names_ec;
   for (int s = 0; s < XB_STAGE_COUNT; ++s) {
+    if (names[s][0] == '-') continue;
     double sec = 0;
     int64_t calls = 0;
     xb_timing(ctx, s, &sec, &calls);
@@ -306,10 +331,35 @@ int Simulation::finalize()
 {
   if (energy_) energy_->flush();
   if (energy_cons_) energy_cons_->flush();
+  if (convergence_) convergence_->flush();
   if (ctx) {
     xb_destroy(ctx);
     ctx = nullptr;
   }
+  return 0;
+}
+
+// eccapfim::ConvergenceHistory::add_columns (src/impls/eccapfim/convergence_history.cpp:11-44)
+int Simulation::diagnose_convergence(int t)
+{
+  int32_t its = 0, fev = 0, reason = 0, len = 0;
+  double fn = 0, cn = 0, tc = 0;
+  std::vector<double> hist(2048);
+  if (t > 0) {
+    B200_CALL(xb_nonlinear_info(ctx, &its, &fev, &reason, &fn, &cn, &tc));
+    B200_CALL(xb_nonlinear_history(ctx, hist.data(), (int32_t)hist.size(), &len));
+  }
+  convergence_->add(6, "Time", std::format("{:d}", t));
+  for (auto& p : particles_) {  // the averages are over all sorts here; the reference prints them per sort
+    convergence_->add(8, "AvgCN_" + p->parameters.sort_name, std::format("{:.3f}", cn));
+    convergence_->add(8, "AvgTC_" + p->parameters.sort_name, std::format("{:.3f}", tc));
+  }
+  convergence_->add(6, "FEvals", std::format("{:d}", fev));
+  convergence_->add(6, "ItNum", std::format("{:d}", its));
+  if (len == 0) convergence_->add(12, "ConvHist", "");
+  for (int i = 0; i < len && i < (int)hist.size(); ++i) convergence_->add(12, "ConvHist", std::format("{:8.6e}", hist[i]));
+  convergence_->row(t == 0);
+  if (t % geom.diagnose_period == 0) convergence_->flush();
   return 0;
 }
 

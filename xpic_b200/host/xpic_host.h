@@ -1,5 +1,5 @@
 // xpic_host.h -- C++ host side above the C ABI, mirroring the interface of the reference's
-// ecsim::Simulation / ecsimcorr::Simulation and interfaces::Particles for this path:
+// ecsim::Simulation / ecsimcorr::Simulation / eccapfim::Simulation and interfaces::Particles for this path:
 // same member names, same life cycle (initialize / calculate / finalize), same config.json
 // schema, same temporal/*.txt output (src/interfaces/simulation.h:21-72,
 // src/interfaces/particles.h:11-78, src/diagnostics/energy.cpp, table_diagnostic.h:17-37).
@@ -103,13 +103,14 @@ public:
 
 private:
   int diagnose_energy(int t);
+  int diagnose_convergence(int t);  // eccapfim::ConvergenceHistory
   struct Preset {
     std::string particles, coordinate, momentum;
     bool tov = false;
   };
   std::vector<SortParameters> sorts_;
   std::vector<Preset> presets_;
-  std::unique_ptr<Table> energy_, energy_cons_;
+  std::unique_ptr<Table> energy_, energy_cons_, convergence_;
   double E_ = 0, B_ = 0, E0_ = 0, B0_ = 0;
   std::vector<double> K_, K0_, stdK_;
   double stdE_ = 0, stdB_ = 0;
@@ -118,6 +119,8 @@ private:
   double rtol_[2] = {1e-7, 1e-7}, atol_[2] = {1e-7, 1e-7};
   int maxit_[2] = {100, 100};
   int curl_sign_ = +1, device_ = 0, precond_ = 6;
+  double snes_atol_ = 1e-7, snes_rtol_ = 1e-7, snes_stol_ = 1e-7;  // src/impls/eccapfim/simulation.h:14-19
+  int snes_maxit_ = 1000;
 };
 
 }  // namespace b200
