@@ -207,13 +207,18 @@ __device__ __forceinline__ void cap_apply(const K& k, const CapW& w, double* Ep,
 template <bool FAST, class K>
 __device__ __forceinline__ void cap_gather_B(const K& k, const double* p, const int* lo_n, const int* lo_s, double* Bp)
 {
+  // inside these windows the middle point is always within half a cell (the 0.75 - x^2 branch of the spline)
+  // and the outer two between 0.5 and 1.5 (the other branch, which reaches 0 at 1.5): no branches needed,
+  // same values as spline_of_2nd_order
   double wn[3][3], ws[3][3];
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      wn[a][j] = spline2(p[a] - (double)(lo_n[a] + j));
-      ws[a][j] = spline2(p[a] - ((double)(lo_s[a] + j) + 0.5));
+      const double xn = fabs(p[a] - (double)(lo_n[a] + j));
+      const double xs = fabs(p[a] - ((double)(lo_s[a] + j) + 0.5));
+      wn[a][j] = j == 1 ? (0.75 - xn * xn) : 0.5 * (1.5 - xn) * (1.5 - xn);
+      ws[a][j] = j == 1 ? (0.75 - xs * xs) : 0.5 * (1.5 - xs) * (1.5 - xs);
     }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -547,16 +552,20 @@ __global__ void __launch_bounds__(CAP_THREADS) k_cap_push(Grid g, CapArgs a)
 constexpr int CAP2_CELLS = 16;
 constexpr int CAP2_THREADS = 256;
 constexpr int CAP2_OWNERS = 224;   // ~1.1 pieces per particle => ~246 gather tasks per round: one dense pass
-constexpr int CAP2_GCAP = 288;     // gather tasks per round
+constexpr int CAP2_GCAP = 272;     // gather tasks per round (two buffers: consume one while the next fills)
 constexpr int CAP2_GSTRIDE = 7;    // rs0[3], rsn[3], bs  -> Es[3], Bs[3], bs
-constexpr int CAP2_DCAP = 384;     // queued deposit tasks
+constexpr int CAP2_DCAP = 320;     // ring of queued deposit tasks
 constexpr int CAP2_DSTRIDE = 10;   // rs0[3], rsn[3], al, vh[3]
 constexpr int CAP2_MAXSEG = 24;
 using CapCtx2 = CapCtxT<CAP2_CELLS>;
-constexpr int CAP2_SMEM_DOUBLES = 3 * 3 * CapCtx2::VOL + CAP2_GCAP * CAP2_GSTRIDE + CAP2_DCAP * CAP2_DSTRIDE;
+constexpr int CAP2_SMEM_DOUBLES = 3 * 3 * CapCtx2::VOL + 2 * CAP2_GCAP * CAP2_GSTRIDE + CAP2_DCAP * CAP2_DSTRIDE;
 
 enum { CS_FETCH = 0, CS_FIELDS = 1, CS_WAIT = 2, CS_DEPOSIT = 3, CS_IDLE = 4 };
 
+// Reservation of n consecutive slots with one atomicAdd (a CAS loop over 224 owners is quadratic).  The
+// counter only grows within a round; a reservation that crosses `limit` fails, and its owner neutralises
+// the part of its range that lies below the limit (the pass over the queue would otherwise read stale
+// slots there).  The round's uniform bookkeeping clamps the counter back to the limit.
 __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapArgs a)
 {
   extern __shared__ double smem[];
@@ -564,9 +573,9 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
   double* Et = smem;
   double* Bt = Et + VOL3;
   double* Jt = Bt + VOL3;
-  double* gq = Jt + VOL3;                        // gather tasks of this round
-  double* dq = gq + CAP2_GCAP * CAP2_GSTRIDE;    // deposit queue
-  __shared__ int q_next, n_gather, n_deposit;
+  double* gq0 = Jt + VOL3;                           // gather tasks, two buffers
+  double* dq = gq0 + 2 * CAP2_GCAP * CAP2_GSTRIDE;   // deposit ring
+  __shared__ int q_next, n_gather[2], d_tail;
   __shared__ unsigned long long cnt[2];
   const int tid = threadIdx.x;
   const int gx = blockIdx.x % a.groups_x, row = blockIdx.x / a.groups_x;  // row = zl * ny + cy
@@ -577,8 +586,8 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
   if (p0 == p1) return;
   if (tid == 0) {
     q_next = p0;
-    n_gather = 0;
-    n_deposit = 0;
+    n_gather[0] = n_gather[1] = 0;
+    d_tail = 0;
     cnt[0] = cnt[1] = 0ull;
   }
   for (int e = tid; e < VOL3; e += CAP2_THREADS) {
@@ -593,20 +602,27 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
 
   const double dt = g.dt, qm = a.q / a.m, a0 = a.q * a.mpw;
 
-  // the particle this thread owns
+  // the particle this thread owns: start state (r0, v0), mean velocity vh of the present Picard iterate,
+  // from which r = r0 + dtau vh, v = 2 vh - v0 once the particle has been moved (particles.cpp:143-144)
   int state = tid < CAP2_OWNERS ? CS_FETCH : CS_IDLE;
   int idx = 0, it = 0, base = 0, nseg = 0;
-  bool first = true;
-  double r0[3], v0[3], r[3], v[3], vh[3];
+  bool first = true, moved = false;
+  double r0[3], v0[3], vh[3];
   double tau = 0.0, dtau = 0.0, rr0 = 0.0;
   unsigned its = 0, segs = 0;
+  int d_head = 0;  // the same value in every thread (advanced by the uniform drain decision)
+  int cur = 0;     // gather buffer whose results are being consumed; the other one is being filled
 
+  auto position = [&](double* r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[c] = moved ? r0[c] + dtau * vh[c] : r0[c];
+  };
   auto start_substep = [&]() {  // particles.cpp:84-101; the domain is the whole periodic box (:39-45)
     const double maxv = 1.7976931348623157e308;
     const double lo[3] = {(0 - 0.5) * g.dx, (0 - 0.5) * g.dy, (0 - 0.5) * g.dz};
     const double hi[3] = {(g.nx + 0.5) * g.dx, (g.ny + 0.5) * g.dy, (g.nz + 0.5) * g.dz};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) vh[c] = 0.5 * (v[c] + v0[c]);
+    for (int c = 0; c < 3; ++c) vh[c] = v0[c];  // 0.5 (v + v0) with v = v0 at the start of a sub-step
     dtau = dt - tau;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -619,9 +635,10 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
     }
     it = 0;
     first = true;
+    moved = false;
   };
   // number of straight pieces of r0 -> r: one more than the faces of the half-shifted lattice crossed
-  auto count_pieces = [&]() {
+  auto count_pieces = [&](const double* r) {
     double ps[3], pe[3];
     cells3(g, r0, ps);
     cells3(g, r, pe);
@@ -634,12 +651,15 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
     }
     return n;
   };
-  // pieces of r0 -> r into queue slots [first_slot, first_slot + n); slots the walk does not fill are neutralised
-  auto emit = [&](double* queue, int stride, int first_slot, int n, bool dep) {
+  // pieces of r0 -> r into `n` queue slots starting at first_slot (modulo `cap`); slots the walk does not
+  // fill are neutralised; returns the pieces written
+  auto emit = [&](double* queue, int stride, int cap, int first_slot, int n, const double* r, bool dep) {
     const double d = len3(r[0] - r0[0], r[1] - r0[1], r[2] - r0[2]);
     int kk = 0;
     auto put = [&](const double* rs0, const double* rsn, double wgt) {
-      double* t = queue + (first_slot + kk) * stride;
+      int slot = first_slot + kk;
+      if (slot >= cap) slot -= cap;
+      double* t = queue + slot * stride;
       t[0] = rs0[0]; t[1] = rs0[1]; t[2] = rs0[2];
       t[3] = rsn[0]; t[4] = rsn[1]; t[5] = rsn[2];
       t[6] = wgt;
@@ -670,58 +690,13 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
   };
 
   while (true) {
-    // ---- emit: owners without a result pending put the pieces of their present path up for evaluation
-    if (state == CS_FETCH) {
-      idx = atomicAdd(&q_next, 1);
-      if (idx < p1) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          r0[c] = r[c] = a.p0[c][idx];
-          v0[c] = v[c] = a.p0[3 + c][idx];
-        }
-        tau = 0.0;
-        start_substep();
-        state = CS_FIELDS;
-      }
-      else
-        state = CS_IDLE;
-    }
-    if (state == CS_FIELDS) {
-      const int n = count_pieces();
-      const int mine = atomicAdd(&n_gather, n);  // only grows within a round
-      if (mine + n <= CAP2_GCAP) {
-        base = mine;
-        nseg = emit(gq, CAP2_GSTRIDE, base, n, false);
-        state = CS_WAIT;
-      }
-      else {
-        // no room this round: neutralise the part of the range below the limit and try again
-        for (int s = mine; s < min(mine + n, CAP2_GCAP); ++s) {
-          double* t = gq + s * CAP2_GSTRIDE;
-          t[0] = t[3] = r0[0]; t[1] = t[4] = r0[1]; t[2] = t[5] = r0[2];
-          t[6] = 0.0;
-        }
-      }
-    }
-    __syncthreads();
-    // ---- process: one gather task per lane
-    {
-      const int ng = min(n_gather, CAP2_GCAP);
-      for (int t = tid; t < ng; t += CAP2_THREADS) {
-        double* tk = gq + t * CAP2_GSTRIDE;
-        const double rs0[3] = {tk[0], tk[1], tk[2]}, rsn[3] = {tk[3], tk[4], tk[5]};
-        double Es[3] = {0.0, 0.0, 0.0}, Bs[3] = {0.0, 0.0, 0.0};
-        cap_interpolate(k, rsn, rs0, Es, Bs);
-        tk[0] = Es[0]; tk[1] = Es[1]; tk[2] = Es[2];
-        tk[3] = Bs[0]; tk[4] = Bs[1]; tk[5] = Bs[2];
-      }
-    }
-    __syncthreads();
-    // ---- consume: residual of the particle's equation of motion, next Picard iterate or deposit
+    double* gq_cur = gq0 + cur * (CAP2_GCAP * CAP2_GSTRIDE);
+    double* gq_nxt = gq0 + (cur ^ 1) * (CAP2_GCAP * CAP2_GSTRIDE);
+    // ---- owners: consume the results of the last pass, then put up the next request ------------------
     if (state == CS_WAIT) {
       double Ep[3] = {0.0, 0.0, 0.0}, Bp[3] = {0.0, 0.0, 0.0};
       for (int s = 0; s < nseg; ++s) {
-        const double* tk = gq + (base + s) * CAP2_GSTRIDE;
+        const double* tk = gq_cur + (base + s) * CAP2_GSTRIDE;
         const double bs = tk[6];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -732,7 +707,11 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
       double vxb[3];
       cross3(vh, Bp, vxb);
       const double f = dtau * qm;
-      const double rn = len3((v[0] - v0[0]) - f * (Ep[0] + vxb[0]), (v[1] - v0[1]) - f * (Ep[1] + vxb[1]), (v[2] - v0[2]) - f * (Ep[2] + vxb[2]));
+      // v - v0 = 2 (vh - v0) once moved, 0 before
+      double dv[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dv[c] = moved ? (2.0 * vh[c] - v0[c]) - v0[c] : 0.0;
+      const double rn = len3(dv[0] - f * (Ep[0] + vxb[0]), dv[1] - f * (Ep[1] + vxb[1]), dv[2] - f * (Ep[2] + vxb[2]));
       if (first) {
         rr0 = rn;
         first = false;
@@ -750,11 +729,7 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
         const double wb = dot3(w, b), den = 1.0 + dot3(b, b);
 #pragma unroll
         for (int c = 0; c < 3; ++c) vh[c] = ((w[c] + wxb[c]) + b[c] * wb) / den;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          r[c] = r0[c] + dtau * vh[c];
-          v[c] = 2.0 * vh[c] - v0[c];
-        }
+        moved = true;
         ++it;
         state = CS_FIELDS;
       }
@@ -766,10 +741,22 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
     }
     if (state == CS_DEPOSIT) {
       // queue the current of this sub-step (:153-163); nobody waits for it, so finish the sub-step at once
-      const int n = count_pieces();
-      const int mine = atomicAdd(&n_deposit, n);
-      if (mine + n <= CAP2_DCAP) {
-        emit(dq, CAP2_DSTRIDE, mine, n, true);
+      double r[3];
+      position(r);
+      const int n = count_pieces(r);
+      const int mine = atomicAdd(&d_tail, n), dlimit = d_head + CAP2_DCAP;
+      if (mine + n > dlimit) {
+        for (int s = mine; s < min(mine + n, dlimit); ++s) {  // stays in CS_DEPOSIT; a drain follows this round
+          double* t = dq + (s % CAP2_DCAP) * CAP2_DSTRIDE;
+          t[0] = t[3] = r0[0]; t[1] = t[4] = r0[1]; t[2] = t[5] = r0[2];
+          t[6] = t[7] = t[8] = t[9] = 0.0;
+        }
+      }
+      else {
+        emit(dq, CAP2_DSTRIDE, CAP2_DCAP, mine % CAP2_DCAP, n, r, true);
+        double v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = moved ? 2.0 * vh[c] - v0[c] : v0[c];
         bool reset = false;  // bound_periodic, particles.cpp:58-68,165-171
         const double L[3] = {g.Lx, g.Ly, g.Lz};
 #pragma unroll
@@ -783,15 +770,16 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
             reset = true;
           }
         }
-        if (reset) {
+        tau += dtau;
+        if (tau < dt) {
+          // the sub-step ended on the box edge + 1/2 cell, i.e. outside the box: the wrap always resets the
+          // start state (:169-171); anything else would need the unreset (r, v) pair this kernel does not keep
+          if (!reset) *a.error = 4;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             r0[c] = r[c];
             v0[c] = v[c];
           }
-        }
-        tau += dtau;
-        if (tau < dt) {
           start_substep();
           state = CS_FIELDS;
         }
@@ -804,35 +792,70 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
           state = CS_FETCH;
         }
       }
+    }
+    if (state == CS_FETCH) {
+      idx = atomicAdd(&q_next, 1);
+      if (idx < p1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          r0[c] = a.p0[c][idx];
+          v0[c] = a.p0[3 + c][idx];
+        }
+        tau = 0.0;
+        start_substep();
+        state = CS_FIELDS;
+      }
+      else
+        state = CS_IDLE;
+    }
+    if (state == CS_FIELDS) {
+      double r[3];
+      position(r);
+      const int n = count_pieces(r);
+      const int mine = atomicAdd(&n_gather[cur ^ 1], n);
+      if (mine + n <= CAP2_GCAP) {
+        base = mine;
+        nseg = emit(gq_nxt, CAP2_GSTRIDE, CAP2_GCAP, base, n, r, false);
+        state = CS_WAIT;
+      }
       else {
-        // the queue is full: neutralise the reserved slots below the limit; a drain follows this round
-        for (int s = mine; s < min(mine + n, CAP2_DCAP); ++s) {
-          double* t = dq + s * CAP2_DSTRIDE;
+        for (int s = mine; s < min(mine + n, CAP2_GCAP); ++s) {  // stays in CS_FIELDS, tries again next round
+          double* t = gq_nxt + s * CAP2_GSTRIDE;
           t[0] = t[3] = r0[0]; t[1] = t[4] = r0[1]; t[2] = t[5] = r0[2];
-          t[6] = t[7] = t[8] = t[9] = 0.0;
+          t[6] = 0.0;
         }
       }
     }
     const bool busy = __syncthreads_or(state != CS_IDLE) != 0;
-    // ---- drain the deposit queue in full passes (everything once no particle is left)
-    const int nd = min(n_deposit, CAP2_DCAP);
-    const int take = busy ? (nd / CAP2_THREADS) * CAP2_THREADS : nd;
-    if (take > 0) {
+    // ---- all threads: one gather task per lane; deposits in full passes (everything once no particle is left)
+    {
+      const int ng = min(n_gather[cur ^ 1], CAP2_GCAP);
+      for (int t = tid; t < ng; t += CAP2_THREADS) {
+        double* tk = gq_nxt + t * CAP2_GSTRIDE;
+        const double rs0[3] = {tk[0], tk[1], tk[2]}, rsn[3] = {tk[3], tk[4], tk[5]};
+        double Es[3] = {0.0, 0.0, 0.0}, Bs[3] = {0.0, 0.0, 0.0};
+        cap_interpolate(k, rsn, rs0, Es, Bs);
+        tk[0] = Es[0]; tk[1] = Es[1]; tk[2] = Es[2];
+        tk[3] = Bs[0]; tk[4] = Bs[1]; tk[5] = Bs[2];
+      }
+      const int avail = min(d_tail, d_head + CAP2_DCAP) - d_head;  // failed reservations overshoot the limit
+      const int take = busy ? (avail / CAP2_THREADS) * CAP2_THREADS : avail;
       // lane l of warp w takes tasks 8 l + w (+ 256 j): the tasks of one warp instruction are 8 apart in the
       // queue, i.e. mostly particles of different half cells, so their shared-memory additions rarely
       // collide (consecutive tasks share a 54-node window and would serialise the CAS loops)
-      for (int t = (tid & 31) * (CAP2_THREADS / 32) + (tid >> 5); t < take; t += CAP2_THREADS) deposit_task(dq + t * CAP2_DSTRIDE);
-      __syncthreads();
-      const int rem = nd - take;  // < CAP2_THREADS <= take: source and destination do not overlap
-      for (int e = tid; e < rem * CAP2_DSTRIDE; e += CAP2_THREADS) dq[e] = dq[take * CAP2_DSTRIDE + e];
-      if (tid == 0) n_deposit = rem;
+      for (int t = (tid & 31) * (CAP2_THREADS / 32) + (tid >> 5); t < take; t += CAP2_THREADS)
+        deposit_task(dq + ((d_head + t) % CAP2_DCAP) * CAP2_DSTRIDE);
+      if (tid == 0) {
+        n_gather[cur] = 0;  // that buffer was consumed above; it is filled again in the next round
+        if (d_tail > d_head + CAP2_DCAP) d_tail = d_head + CAP2_DCAP;  // idempotent under the min() above
+      }
+      d_head += take;
     }
-    else if (tid == 0 && n_deposit > CAP2_DCAP)
-      n_deposit = CAP2_DCAP;  // failed reservations only
-    if (tid == 0) n_gather = 0;
     if (!busy) break;
+    cur ^= 1;
     __syncthreads();
   }
+  __syncthreads();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     its += __shfl_down_sync(0xffffffffu, its, o);
