@@ -157,10 +157,19 @@ __device__ __forceinline__ void cap_weights(const Grid& g, const double* rn, con
 
 // E gather (FAST: from the tile) -- implicit_esirkepov.cpp:71-90; DEPOSIT: the same loop adds
 // alpha * v[c] * weight into J (:97-116)
+// fp64 addition into the shared-memory current tile.  sm_100a has no native 64-bit shared atomic add: the
+// instruction is a load / add / compare-and-swap spin either way, but naming the state space saves the
+// generic-address test the plain atomicAdd() carries
+__device__ __forceinline__ void shared_add_f64(unsigned addr, double v)
+{
+  asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
 template <bool FAST, bool DEPOSIT, class K>
 __device__ __forceinline__ void cap_apply(const K& k, const CapW& w, double* Ep, double alpha, const double* v)
 {
   const int base = FAST ? k.tile_base(w.start) : 0;
+  const unsigned jaddr = (FAST && DEPOSIT) ? (unsigned)__cvta_generic_to_shared(k.Jt) + 8u * (unsigned)base : 0u;
 #pragma unroll
   for (int cx = 0; cx < 3; ++cx) {
     const int cy = (cx + 1) % 3, cz = (cx + 2) % 3;
@@ -185,7 +194,7 @@ __device__ __forceinline__ void cap_apply(const K& k, const CapW& w, double* Ep,
           if (FAST) {
             const int e = cx * K::VOL + base + (d[2] * K::NY + d[1]) * K::NX + d[0];
             if (DEPOSIT)
-              atomicAdd(&k.Jt[e], av * wt);
+              shared_add_f64(jaddr + 8u * (unsigned)(e - base), av * wt);
             else
               acc += k.Et[e] * wt;
           }
