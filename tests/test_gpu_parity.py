@@ -365,3 +365,42 @@ def test_golden_field_dumps_and_all_rows_100_steps(X, name, scheme):
     # the reference solved to 1e-7 and chaos amplifies the difference slowly: 7 digits early, 5 at the end
     np.testing.assert_allclose(np.array(rows)[:31], gold[:31, 1:4], rtol=3e-6, atol=1e-10)
     np.testing.assert_allclose(np.array(rows), gold[:, 1:4], rtol=2e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("scheme", [0, 1, 2])
+def test_step_host_equals_resident_step(X, scheme):
+    """xb_step_host (host E, B, B0 in; E, B, kinetic energies out; the copies of E and B0 overlap the
+    particle stages) gives the same state as xb_step on resident fields."""
+    sims = []
+    o = O.Oracle((9, 8, 7))
+    sid = o.add_species(Np=12)
+    o.set_particles_maxwell(sid, 0.1, True)
+    pts, ids = o.get_particles(sid)
+    rng = np.random.default_rng(77)
+    E0, B0 = 0.01 * rng.standard_normal(o.n3), 0.03 * rng.standard_normal(o.n3)
+    for _ in range(2):
+        s = X.Simulation((9, 8, 7), scheme=scheme, track_ids=True)
+        s.add_species(Np=12)
+        s.add_particles(0, pts, ids)
+        s.solver_set(0, 1e-12, 1e-50, 500, 30, 4)
+        s.solver_set(1, 1e-12, 1e-50, 500, 30, 4)
+        s.nonlinear_set(atol=1e-13, rtol=1e-30, particle_tol=1e-14)
+        sims.append(s)
+    a, b = sims
+    a.set_field("E", E0)
+    a.set_field("B", B0)
+    E, B, Bz = E0.copy(), B0.copy(), np.zeros(o.n3)
+    K = np.zeros(1)
+    for _ in range(3):
+        a.step()
+        b.step_host(E, B, Bz, K)
+    pa, ia = by_id(*a.get_particles())
+    pb, ib = by_id(*b.get_particles())
+    assert np.array_equal(ia, ib) and np.array_equal(b.get_field("E"), E)
+    if scheme == 2:
+        # eccapfim's current is summed with shared-memory fp64 additions whose order varies run to run
+        assert rel_err(a.get_field("E"), E) < 1e-11 and rel_err(a.get_field("B"), B) < 1e-11
+        assert abs(K[0] / a.scalar("kinetic") - 1) < 1e-12 and rel_err(pa, pb) < 1e-12
+    else:
+        assert np.array_equal(a.get_field("E"), E) and np.array_equal(a.get_field("B"), B)
+        assert K[0] == a.scalar("kinetic") and np.array_equal(pa, pb)

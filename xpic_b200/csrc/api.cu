@@ -278,6 +278,8 @@ int xb_create(const xb_grid* gr, const void* uid, xb_ctx** out)
   if (g.ntot >= (int64_t)0x7fffffff) XB_FAIL("xb_create: slab too large for 32-bit field offsets");
 
   XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  XB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  XB_CUDA(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
   XB_CUDA(cudaEventCreate(&c->ev0));
   XB_CUDA(cudaEventCreate(&c->ev1));
   XB_CUDA(cudaEventCreate(&c->ev2));
@@ -339,6 +341,8 @@ int xb_destroy(xb_ctx* c)
   if (c->ev2) cudaEventDestroy(c->ev2);
   if (c->ev3) cudaEventDestroy(c->ev3);
   for (auto e : c->spmv_events) cudaEventDestroy(e);
+  if (c->copy_done) cudaEventDestroy(c->copy_done);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -484,14 +488,36 @@ int xb_step(xb_ctx* c, int32_t scheme)
 int xb_step_host(xb_ctx* c, int32_t scheme, double* E, double* B, const double* B0, double* kinetic)
 {
   XB_API_BEGIN(c);
-  XB_CHECK(upload_owned(c, E, c->E));
+  if (scheme != XB_ECSIM && scheme != XB_ECSIMCORR && scheme != XB_ECCAPFIM) XB_FAIL("unknown scheme");
+  const Grid& g = c->g;
+  // B^n is needed by the first particle stage (moments); E^n and B0 only by the field solve, so for ecsim /
+  // ecsimcorr their upload travels on a second stream underneath the push, re-binning and moment kernels
+  const bool overlap = scheme != XB_ECCAPFIM;
   XB_CHECK(upload_owned(c, B, c->B));
-  if (B0) XB_CHECK(upload_owned(c, B0, c->B0));
-  XB_CHECK(xb_step(c, scheme));
-  XB_CHECK(download_owned(c, c->E, E));
-  XB_CHECK(download_owned(c, c->B, B));
+  if (overlap) {
+    XB_CUDA(cudaEventRecord(c->copy_done, c->stream));  // the previous step's readers of E, B0 are done
+    XB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_done, 0));
+    XB_CUDA(cudaMemcpyAsync(c->E + g.own0, E, sizeof(double) * g.nown, cudaMemcpyHostToDevice, c->copy_stream));
+    if (B0) XB_CUDA(cudaMemcpyAsync(c->B0 + g.own0, B0, sizeof(double) * g.nown, cudaMemcpyHostToDevice, c->copy_stream));
+    XB_CUDA(cudaEventRecord(c->copy_done, c->copy_stream));
+  }
+  else {
+    XB_CHECK(upload_owned(c, E, c->E));
+    if (B0) XB_CHECK(upload_owned(c, B0, c->B0));
+  }
+  XB_CHECK(ensure_sorted(c));
+  for (int st = 0; st < XB_STAGE_COUNT; ++st) {
+    if (overlap && st == XB_STAGE_ADVANCE_FIELDS) XB_CUDA(cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+    XB_CHECK(run_stage(c, scheme, st));
+  }
+  // E goes home on the second stream while the kinetic energies are reduced and B follows on the first
+  XB_CUDA(cudaEventRecord(c->copy_done, c->stream));
+  XB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_done, 0));
+  XB_CUDA(cudaMemcpyAsync(E, c->E + g.own0, sizeof(double) * g.nown, cudaMemcpyDeviceToHost, c->copy_stream));
   if (kinetic)
     for (size_t i = 0; i < c->sorts.size(); ++i) XB_CHECK(kinetic_energy(c, c->sorts[i], nullptr, &kinetic[i]));
+  XB_CHECK(download_owned(c, c->B, B));
+  XB_CUDA(cudaStreamSynchronize(c->copy_stream));
   XB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }

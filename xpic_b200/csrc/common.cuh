@@ -140,6 +140,8 @@ struct xb_ctx {
   bool track_ids = false;
   bool deterministic = false;  // canonical particle order inside every bin even without ids (costs one more pass)
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host<->device copies of xb_step_host that overlap with the particle stages
+  cudaEvent_t copy_done = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   bool spmv_profile = false;
   std::vector<cudaEvent_t> spmv_events;  // pairs (start, stop), recorded around every operator launch
