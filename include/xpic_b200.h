@@ -185,6 +185,18 @@ int xb_nonlinear_profile(xb_ctx* ctx, int32_t enable, int64_t* evaluations, doub
  * XB_J / XB_J_SORT then hold the currents of that evaluation. */
 int xb_eccapfim_function(xb_ctx* ctx, const double* x, double* f);
 
+/* --- per-step diagnostics on the device (the reference walks Particles::storage on the host) -------
+ * ParticlesChargeDensity::collect (src/diagnostics/charge_conservation.cpp:67-97): the charge density of
+ * sort sid at the nodes, 2nd-order form factor; rho (may be NULL) receives the owned slab, Nx*Ny*nzl doubles.
+ * The collection is remembered as the sort's latest density for xb_charge_conservation. */
+int xb_charge_density(xb_ctx* ctx, int32_t sid, double* rho);
+/* ChargeConservation::add_columns (charge_conservation.cpp:125-171): for every sort the 1- and 2-norm of
+ * (rho_now - rho_previous) / dt + div J_sort (rho_now is collected here, rho_previous by the previous
+ * call or xb_charge_density = ChargeConservation::initialize), then the same for the sum of the sorts with
+ * the total current.  which_current: 0 = currJe (ecsimcorr, ecsimcorr/simulation.cpp:103-110),
+ * 1 = J (eccapfim).  norms receives 2 * (number of sorts + 1) doubles, summed over all ranks. */
+int xb_charge_conservation(xb_ctx* ctx, int32_t which_current, double* norms);
+
 /* Moments only at the present particle positions: fill_ecsim_current (ecsim/simulation.cpp:336-368). */
 int xb_deposit(xb_ctx* ctx);
 /* Solve (L? + M) x = b for host vectors with the given solver slot (KSPSolve). */

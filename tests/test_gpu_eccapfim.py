@@ -208,3 +208,6 @@ def test_host_program_writes_the_reference_tables(tmp_path):
     assert int(row[3]) == int(row[4]) + 1 and len(row) == 5 + int(row[3])  # one evaluation per iteration + the first
     _, cons = O.read_table(str(tmp_path / "eccapfim_ex1" / "temporal" / "energy_conservation.txt"))
     assert np.max(np.abs(cons[:, -1])) < 1e-6
+    tq, charge = O.read_table(str(tmp_path / "eccapfim_ex1" / "temporal" / "charge_conservation.txt"))
+    assert tq == O.read_table(os.path.join(GOLDEN, "eccapfim_ex1", "charge_conservation.txt"))[0]
+    assert charge.shape[0] == 10 and np.max(charge[:, 1:]) < 5e-12  # rows t = 1..10 (no current exists at t = 0)

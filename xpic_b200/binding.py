@@ -109,6 +109,8 @@ SYMBOLS = {
     "xb_nonlinear_history": (C.c_int, [C.c_void_p, _dp, C.c_int32, _i32p]),
     "xb_nonlinear_profile": (C.c_int, [C.c_void_p, C.c_int32, _i64p, _dp]),
     "xb_eccapfim_function": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "xb_charge_density": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
+    "xb_charge_conservation": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
 }
 
 
@@ -278,6 +280,19 @@ class Simulation:
         f = np.empty(self.nown, dtype=np.float64)
         _check(self._L.xb_eccapfim_function(self._h, _as_dp(x), _as_dp(f)))
         return f
+
+    # -- device-side diagnostics ----------------------------------------------------------------
+    def charge_density(self, sid=0):
+        """ParticlesChargeDensity::collect: rho of sort sid on the owned nodes (also remembered for charge_conservation)."""
+        rho = np.empty(self.ncl, dtype=np.float64)
+        _check(self._L.xb_charge_density(self._h, sid, _as_dp(rho)))
+        return rho
+
+    def charge_conservation(self, current="currJe"):
+        """ChargeConservation::add_columns: (nsorts + 1, 2) array of the 1- and 2-norms of d rho / dt + div J."""
+        out = np.zeros(2 * (self.nsorts + 1))
+        _check(self._L.xb_charge_conservation(self._h, {"currJe": 0, "J": 1}[current], _as_dp(out)))
+        return out.reshape(-1, 2)
 
     # -- stepping ------------------------------------------------------------------------------
     def step(self, scheme=None):

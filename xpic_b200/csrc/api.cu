@@ -765,6 +765,30 @@ int xb_eccapfim_function(xb_ctx* c, const double* x, double* f)
   return 0;
 }
 
+int xb_charge_density(xb_ctx* c, int32_t sid, double* rho)
+{
+  XB_API_BEGIN(c);
+  if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
+  Species& s = c->sorts[sid];
+  XB_CHECK(charge_density(c, s));
+  if (rho) {
+    // component 0 of the owned part of the grid vector
+    std::vector<double> tmp((size_t)c->g.nown);
+    XB_CHECK(download_owned(c, s.rho[s.rho_cur], tmp.data()));
+    XB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < c->g.ncl; ++i) rho[i] = tmp[3 * i];
+  }
+  return 0;
+}
+
+int xb_charge_conservation(xb_ctx* c, int32_t which_current, double* norms)
+{
+  XB_API_BEGIN(c);
+  if (which_current != 0 && which_current != 1) XB_FAIL("xb_charge_conservation: which_current must be 0 (currJe) or 1 (J)");
+  if (!norms) XB_FAIL("xb_charge_conservation: null output");
+  return charge_conservation(c, which_current, norms);
+}
+
 int xb_deposit(xb_ctx* c)
 {
   XB_API_BEGIN(c);

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cmath>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -118,6 +119,8 @@ struct Species {
   int32_t* bin_start = nullptr;  // nbins + 1, valid after sort
   double* currI = nullptr;       // per-sort currents (ghosted grid vectors)
   double* currJe = nullptr;
+  double* rho[2] = {nullptr, nullptr};  // charge density of the last two collections (diagnostics.cu), component 0 of a grid vector
+  int rho_cur = 0;
   uint64_t next_id = 0;
   bool sorted = false;
   MigrateBuffers* mig = nullptr;
@@ -247,6 +250,10 @@ int cap_form_function(xb_ctx* c, double* x, double* F);  // form_iteration: F(x)
 int cap_solve(xb_ctx* c);                                // calc_iteration
 int cap_finish(xb_ctx* c);                               // after_iteration
 int cap_read_counters(xb_ctx* c);                        // averages of the last evaluation -> c->nl
+
+// ---- diagnostics.cu --------------------------------------------------------------------------
+int charge_density(xb_ctx* c, Species& s);                               // ParticlesChargeDensity::collect
+int charge_conservation(xb_ctx* c, int which_current, double* norms);   // ChargeConservation::add_columns
 
 // ---- launch bookkeeping ----------------------------------------------------------------------
 #define XB_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \

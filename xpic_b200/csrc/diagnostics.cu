@@ -1,0 +1,145 @@
+// diagnostics.cu -- per-step particle diagnostics on the device: the reference walks
+// `Particles::storage` on the host every step for these, which would force a particle download per step.
+//
+// Reference code replaced:
+//   ParticlesChargeDensity::Shape::setup / collect   src/diagnostics/charge_conservation.cpp:33-97
+//   ChargeConservation::initialize / add_columns     src/diagnostics/charge_conservation.cpp:115-171
+//   Divergence (negative Yee shift)                  src/utils/operators.cpp:275-323
+// The charge density is a scalar field kept in component 0 of a ghosted grid vector, so the halo
+// reduction and the slab layout of the field kernels apply unchanged.
+#include "common.cuh"
+#include "gather.cuh"
+
+namespace xb {
+
+int reduce_finish(xb_ctx* c, int nv, double* host_out);  // fields.cu
+
+__device__ __forceinline__ double spline2_diag(double x)  // interfaces/sort_parameters.cpp:21-30
+{
+  x = fabs(x);
+  if (x <= 0.5) return (0.75 - x * x);
+  if (x < 1.5) return 0.5 * (1.5 - x) * (1.5 - x);
+  return 0.0;
+}
+
+// rho(g) += q * n/Np * S2(x - gx) S2(y - gy) S2(z - gz) over the 3^3 nodes from ceil(p - 1.5)
+__global__ void __launch_bounds__(256) k_charge_density(Grid g, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                                                       const double* __restrict__ z, double qn_Np, double* __restrict__ rho)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double p[3] = {to_cells(x[i], g.dx, g.inv_dx, g.exact_inv & 1), to_cells(y[i], g.dy, g.inv_dy, g.exact_inv & 2),
+                       to_cells(z[i], g.dz, g.inv_dz, g.exact_inv & 4)};
+  int start[3];
+  double w[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    start[a] = (int)ceil(p[a] - 1.5);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) w[a][j] = spline2_diag(p[a] - (double)(start[a] + j));
+  }
+#pragma unroll
+  for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+    for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+      for (int ix = 0; ix < 3; ++ix) {
+        const double v = qn_Np * (w[0][ix] * w[1][jy] * w[2][kz]);  // q * cache[i] * n_Np, cache = sx * sy * sz
+        atomicAdd(&rho[g.vidx(wrapi(start[0] + ix, g.nx), wrapi(start[1] + jy, g.ny), start[2] + kz - g.z0, 0)], v);
+      }
+}
+
+// diff = (rho_new - rho_old) / dt + div^- J ; partial sums of |diff| and diff^2; optionally sum += (rho_new - rho_old) / dt
+__global__ void __launch_bounds__(RED_THREADS) k_continuity(Grid g, const double* __restrict__ rho_new, const double* __restrict__ rho_old,
+                                                           const double* __restrict__ J, double* __restrict__ sum, int mode,
+                                                           double* __restrict__ partial)
+{
+  double n1 = 0.0, n2 = 0.0;
+  const double ix = 1.0 / g.dx, iy = 1.0 / g.dy, iz = 1.0 / g.dz;
+  for (int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; node < g.ncl; node += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = (int)(node / g.plane);
+    const int64_t o = g.vidx(x, y, zl, 0);
+    double diff;
+    if (mode == 0) {  // one sort: d rho / dt, accumulated into the running sum of all sorts
+      diff = (rho_new[o] - rho_old[o]) / g.dt;  // VecAYPX(diff, -1, rho); VecScale(diff, 1 / dt)
+      sum[o] += diff;
+    }
+    else
+      diff = sum[o];  // the total: sum over sorts + div of the total current
+    const double div = (ix * J[o + 0] - ix * J[g.vidx(wrapi(x - 1, g.nx), y, zl, 0)]) + (iy * J[o + 1] - iy * J[g.vidx(x, wrapi(y - 1, g.ny), zl, 1)]) +
+                       (iz * J[o + 2] - iz * J[g.vidx(x, y, zl - 1, 2)]);
+    diff += div;
+    n1 += fabs(diff);
+    n2 += diff * diff;
+  }
+  __shared__ double sh[RED_THREADS / 32][2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  n1 = warp_sum(n1);
+  n2 = warp_sum(n2);
+  if (lane == 0) {
+    sh[wid][0] = n1;
+    sh[wid][1] = n2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int q = 0; q < RED_THREADS / 32; ++q) t += sh[q][threadIdx.x];
+    partial[(int64_t)blockIdx.x * RED_MAXV + threadIdx.x] = t;
+  }
+}
+
+static int ensure_rho(xb_ctx* c, Species& s)
+{
+  for (int b = 0; b < 2; ++b)
+    if (!s.rho[b]) {
+      XB_CUDA(cudaMalloc(&s.rho[b], sizeof(double) * c->g.ntot));
+      XB_CUDA(cudaMemsetAsync(s.rho[b], 0, sizeof(double) * c->g.ntot, c->stream));
+    }
+  return 0;
+}
+
+// ParticlesChargeDensity::collect into s.rho[s.rho_cur]
+int charge_density(xb_ctx* c, Species& s)
+{
+  XB_CHECK(ensure_rho(c, s));
+  double* rho = s.rho[s.rho_cur];
+  XB_CHECK(vec_zero(c, rho));
+  if (s.count > 0) {
+    double** p = s.p[s.cur];
+    const int blocks = (int)((s.count + 255) / 256);
+    XB_LAUNCH(c, k_charge_density, blocks, 256, 0, c->g, s.count, p[0], p[1], p[2], s.q * (s.n / (double)s.Np), rho);
+  }
+  return halo_reduce(c, rho, GZ, GZ);  // DMLocalToGlobal(ADD), charge_conservation.cpp:95
+}
+
+// ChargeConservation::add_columns: norms = {N1dQ_s, N2dQ_s} for every sort, then {N1dQ_tot, N2dQ_tot}
+int charge_conservation(xb_ctx* c, int which_current, double* norms)
+{
+  const Grid& g = c->g;
+  double* total_J = which_current == 0 ? c->currJe : c->cap_J;
+  if (!total_J) XB_FAIL("charge_conservation: the requested current does not exist yet (no eccapfim step was taken)");
+  XB_CHECK(vec_zero(c, c->tmp2));  // running sum over the sorts
+  size_t k = 0;
+  for (auto& s : c->sorts) {
+    XB_CHECK(ensure_rho(c, s));
+    s.rho_cur ^= 1;  // the previous collection becomes rho_old
+    XB_CHECK(charge_density(c, s));
+    double* J = which_current == 0 ? s.currJe : s.currI;  // eccapfim keeps Particles::J in currI
+    XB_CHECK(halo_fill(c, J, 1));
+    XB_LAUNCH(c, k_continuity, RED_BLOCKS, RED_THREADS, 0, g, s.rho[s.rho_cur], s.rho[s.rho_cur ^ 1], J, c->tmp2, 0, c->red_partial);
+    double r[2];
+    XB_CHECK(reduce_finish(c, 2, r));
+    norms[2 * k + 0] = r[0];
+    norms[2 * k + 1] = std::sqrt(r[1]);
+    ++k;
+  }
+  XB_CHECK(halo_fill(c, total_J, 1));
+  XB_LAUNCH(c, k_continuity, RED_BLOCKS, RED_THREADS, 0, g, nullptr, nullptr, total_J, c->tmp2, 1, c->red_partial);
+  double r[2];
+  XB_CHECK(reduce_finish(c, 2, r));
+  norms[2 * k + 0] = r[0];
+  norms[2 * k + 1] = std::sqrt(r[1]);
+  return 0;
+}
+
+}  // namespace xb

@@ -53,6 +53,8 @@ void species_free(Species& s)
   cudaFree(s.bin_start);
   cudaFree(s.currI);
   cudaFree(s.currJe);
+  cudaFree(s.rho[0]);
+  cudaFree(s.rho[1]);
   migrate_free(s);
 }
 

@@ -282,6 +282,11 @@ int Simulation::initialize()
     convergence_ = std::make_unique<Table>(out_dir + "/temporal/convergence_history.txt");
     if (diagnose_convergence(start)) return 1;
   }
+  if (scheme != XB_ECSIM) {  // ChargeConservation: interfaces/simulation.cpp:32-38 (J), ecsimcorr/simulation.cpp:103-110 (currJe)
+    charge_ = std::make_unique<Table>(out_dir + "/temporal/charge_conservation.txt");
+    for (size_t i = 0; i < particles_.size(); ++i) B200_CALL(xb_charge_density(ctx, (int32_t)i, nullptr));  // ChargeConservation::initialize
+    if (scheme == XB_ECSIMCORR && diagnose_charge(start)) return 1;  // eccapfim has no current before its first step
+  }
   return diagnose_energy(start);
 }
 
@@ -311,6 +316,7 @@ int Simulation::calculate()
       xb_solver_info(ctx, XB_SOLVER_PREDICT, &its, &rn, &reason);
       std::cout << std::format("  KSPSolve() has finished: reason {}, iterations {}, residual norm {:.3e}", reason, its, rn) << "\n";
     }
+    if (charge_ && diagnose_charge(t)) return 1;
     if (diagnose_energy(t)) return 1;
   }
   std::cout << "Summary of Stages:\n";  // utils/sync_clock.cpp:85-91
@@ -332,10 +338,30 @@ int Simulation::finalize()
   if (energy_) energy_->flush();
   if (energy_cons_) energy_cons_->flush();
   if (convergence_) convergence_->flush();
+  if (charge_) charge_->flush();
   if (ctx) {
     xb_destroy(ctx);
     ctx = nullptr;
   }
+  return 0;
+}
+
+// ChargeConservation::add_columns (src/diagnostics/charge_conservation.cpp:125-171), evaluated on the device
+int Simulation::diagnose_charge(int t)
+{
+  std::vector<double> norms(2 * (particles_.size() + 1), 0.0);
+  B200_CALL(xb_charge_conservation(ctx, scheme == XB_ECSIMCORR ? 0 : 1, norms.data()));
+  auto num = [](double v) { return std::format("{: .6e}", v); };
+  charge_->add(6, "Time", std::format("{:d}", t));
+  for (size_t i = 0; i < particles_.size(); ++i) {
+    charge_->add(13, "N1dQ_" + particles_[i]->parameters.sort_name, num(norms[2 * i]));
+    charge_->add(13, "N2dQ_" + particles_[i]->parameters.sort_name, num(norms[2 * i + 1]));
+  }
+  charge_->add(13, "N1dQ_tot", num(norms[2 * particles_.size()]));
+  charge_->add(13, "N2dQ_tot", num(norms[2 * particles_.size() + 1]));
+  charge_->row(!charge_header_);
+  charge_header_ = true;
+  if (t % geom.diagnose_period == 0) charge_->flush();
   return 0;
 }
 

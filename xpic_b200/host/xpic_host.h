@@ -104,13 +104,15 @@ public:
 private:
   int diagnose_energy(int t);
   int diagnose_convergence(int t);  // eccapfim::ConvergenceHistory
+  int diagnose_charge(int t);       // ChargeConservation (ecsimcorr, eccapfim)
   struct Preset {
     std::string particles, coordinate, momentum;
     bool tov = false;
   };
   std::vector<SortParameters> sorts_;
   std::vector<Preset> presets_;
-  std::unique_ptr<Table> energy_, energy_cons_, convergence_;
+  std::unique_ptr<Table> energy_, energy_cons_, convergence_, charge_;
+  bool charge_header_ = false;
   double E_ = 0, B_ = 0, E0_ = 0, B0_ = 0;
   std::vector<double> K_, K0_, stdK_;
   double stdE_ = 0, stdB_ = 0;
