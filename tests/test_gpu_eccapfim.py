@@ -210,4 +210,4 @@ def test_host_program_writes_the_reference_tables(tmp_path):
     assert np.max(np.abs(cons[:, -1])) < 1e-6
     tq, charge = O.read_table(str(tmp_path / "eccapfim_ex1" / "temporal" / "charge_conservation.txt"))
     assert tq == O.read_table(os.path.join(GOLDEN, "eccapfim_ex1", "charge_conservation.txt"))[0]
-    assert charge.shape[0] == 10 and np.max(charge[:, 1:]) < 5e-12  # rows t = 1..10 (no current exists at t = 0)
+    assert charge.shape[0] == 11 and np.max(charge[:, 1:]) < 5e-12

@@ -245,6 +245,7 @@ int push_first_corr_mma(xb_ctx* c, Species& s);
 int push_second_corr_mma(xb_ctx* c, Species& s, const double* Eh, const double* B);
 
 // ---- eccapfim.cu -----------------------------------------------------------------------------
+int cap_alloc(xb_ctx* c);                                // the scheme's grid vectors, on first use
 int cap_prepare(xb_ctx* c);                              // init_iteration: sort if needed, rhs0
 int cap_form_function(xb_ctx* c, double* x, double* F);  // form_iteration: F(x), x ghosted
 int cap_solve(xb_ctx* c);                                // calc_iteration

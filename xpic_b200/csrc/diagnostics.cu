@@ -116,8 +116,8 @@ int charge_density(xb_ctx* c, Species& s)
 int charge_conservation(xb_ctx* c, int which_current, double* norms)
 {
   const Grid& g = c->g;
+  if (which_current == 1) XB_CHECK(cap_alloc(c));  // before the first eccapfim step J = 0, as in the reference
   double* total_J = which_current == 0 ? c->currJe : c->cap_J;
-  if (!total_J) XB_FAIL("charge_conservation: the requested current does not exist yet (no eccapfim step was taken)");
   XB_CHECK(vec_zero(c, c->tmp2));  // running sum over the sorts
   size_t k = 0;
   for (auto& s : c->sorts) {

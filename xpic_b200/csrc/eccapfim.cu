@@ -911,7 +911,7 @@ static inline int grid_for(int64_t n, int threads = 256)
   return (int)(b < 1 ? 1 : b);
 }
 
-static int cap_alloc(xb_ctx* c)
+int cap_alloc(xb_ctx* c)
 {
   if (c->cap_x) return 0;
   for (double** v : {&c->cap_x, &c->cap_F, &c->cap_g, &c->cap_rhs0, &c->cap_J}) {

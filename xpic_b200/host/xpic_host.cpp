@@ -285,7 +285,7 @@ int Simulation::initialize()
   if (scheme != XB_ECSIM) {  // ChargeConservation: interfaces/simulation.cpp:32-38 (J), ecsimcorr/simulation.cpp:103-110 (currJe)
     charge_ = std::make_unique<Table>(out_dir + "/temporal/charge_conservation.txt");
     for (size_t i = 0; i < particles_.size(); ++i) B200_CALL(xb_charge_density(ctx, (int32_t)i, nullptr));  // ChargeConservation::initialize
-    if (scheme == XB_ECSIMCORR && diagnose_charge(start)) return 1;  // eccapfim has no current before its first step
+    if (diagnose_charge(start)) return 1;
   }
   return diagnose_energy(start);
 }
