@@ -208,6 +208,13 @@ def test_host_program_writes_the_reference_tables(tmp_path):
     assert int(row[3]) == int(row[4]) + 1 and len(row) == 5 + int(row[3])  # one evaluation per iteration + the first
     _, cons = O.read_table(str(tmp_path / "eccapfim_ex1" / "temporal" / "energy_conservation.txt"))
     assert np.max(np.abs(cons[:, -1])) < 1e-6
+    # FieldView dumps: same names, sizes and (to the reference's solver tolerance) contents as the golden files
+    for field, tol in (("E", 2e-3), ("B", 1e-2)):
+        assert sorted(os.listdir(tmp_path / "eccapfim_ex1" / field)) == ["00", "05", "10"]
+        for t in ("05", "10"):
+            mine = np.fromfile(tmp_path / "eccapfim_ex1" / field / t, dtype=np.float32).astype(np.float64)
+            gold_f = np.fromfile(os.path.join(GOLDEN, "eccapfim_ex1", f"{field}_0{t}.f32"), dtype=np.float32).astype(np.float64)
+            assert mine.size == gold_f.size == 3000 and rel_err(mine, gold_f) < tol
     tq, charge = O.read_table(str(tmp_path / "eccapfim_ex1" / "temporal" / "charge_conservation.txt"))
     assert tq == O.read_table(os.path.join(GOLDEN, "eccapfim_ex1", "charge_conservation.txt"))[0]
     assert charge.shape[0] == 11 and np.max(charge[:, 1:]) < 5e-12

@@ -560,7 +560,10 @@ __global__ void __launch_bounds__(CAP_THREADS) k_cap_push(Grid g, CapArgs a)
 // ---------------------------------------------------------------------------------------------
 constexpr int CAP2_CELLS = 16;
 constexpr int CAP2_THREADS = 256;
-constexpr int CAP2_OWNERS = 224;   // ~1.1 pieces per particle => ~246 gather tasks per round: one dense pass
+#ifndef CAP2_OWNERS_V
+#define CAP2_OWNERS_V 224
+#endif
+constexpr int CAP2_OWNERS = CAP2_OWNERS_V;   // ~1.1 pieces per particle => ~246 gather tasks per round: one dense pass
 constexpr int CAP2_GCAP = 272;     // gather tasks per round (two buffers: consume one while the next fills)
 constexpr int CAP2_GSTRIDE = 7;    // rs0[3], rsn[3], bs  -> Es[3], Bs[3], bs
 constexpr int CAP2_DCAP = 320;     // ring of queued deposit tasks

@@ -186,6 +186,16 @@ int Simulation::configure(const std::string& config_path)
       }
       sorts_.push_back(p);
     }
+  if (cfg.contains("Diagnostics"))  // diagnostics/builders/diagnostic_builder.cpp, field_view_builder.cpp:13-52
+    for (const json& info : cfg.at("Diagnostics")) {
+      const std::string name = info.at("diagnostic").get<std::string>();
+      if (name == "FieldView") {
+        if (info.contains("region")) throw std::runtime_error("FieldView: only the whole-box region is covered by this build");
+        field_views_.push_back(info.at("field").get<std::string>());
+      }
+      else
+        std::cout << "  diagnostic " << name << " is not covered by this build, skipped\n";
+    }
   if (cfg.contains("Presets"))  // commands/builders/command_builder.cpp:42-59
     for (const json& info : cfg.at("Presets")) {
       const std::string command = info.at("command").get<std::string>();
@@ -287,7 +297,29 @@ int Simulation::initialize()
     for (size_t i = 0; i < particles_.size(); ++i) B200_CALL(xb_charge_density(ctx, (int32_t)i, nullptr));  // ChargeConservation::initialize
     if (diagnose_charge(start)) return 1;
   }
+  if (diagnose_fields(start)) return 1;
   return diagnose_energy(start);
+}
+
+// FieldView::diagnose (src/diagnostics/field_view.cpp:98-118): float32 image of the whole vector in
+// natural [z][y][x][c] order (MPIBinaryFile::write_floats, utils/mpi_binary_file.cpp:98-106), named by
+// Diagnostic::format_time (interfaces/diagnostic.cpp:21-25)
+int Simulation::diagnose_fields(int t)
+{
+  if (field_views_.empty() || t % geom.diagnose_period != 0) return 0;
+  const int width = (int)std::to_string(geom.geom_nt).size();
+  std::vector<double> f;
+  std::vector<float> out;
+  for (const std::string& field : field_views_) {
+    if (get_named_vector(field, f)) return 1;
+    out.assign(f.begin(), f.end());
+    const std::string dir = out_dir + "/" + field;
+    std::filesystem::create_directories(dir);
+    std::ofstream file(dir + "/" + std::format("{:0{}d}", t, width), std::ios::binary);
+    file.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)(out.size() * sizeof(float)));
+    if (!file) throw std::runtime_error("FieldView: cannot write into " + dir);
+  }
+  return 0;
 }
 
 int Simulation::timestep_implementation(int /* t */)
@@ -317,6 +349,7 @@ int Simulation::calculate()
       std::cout << std::format("  KSPSolve() has finished: reason {}, iterations {}, residual norm {:.3e}", reason, its, rn) << "\n";
     }
     if (charge_ && diagnose_charge(t)) return 1;
+    if (diagnose_fields(t)) return 1;
     if (diagnose_energy(t)) return 1;
   }
   std::cout << "Summary of Stages:\n";  // utils/sync_clock.cpp:85-91

@@ -105,12 +105,14 @@ private:
   int diagnose_energy(int t);
   int diagnose_convergence(int t);  // eccapfim::ConvergenceHistory
   int diagnose_charge(int t);       // ChargeConservation (ecsimcorr, eccapfim)
+  int diagnose_fields(int t);       // FieldView dumps
   struct Preset {
     std::string particles, coordinate, momentum;
     bool tov = false;
   };
   std::vector<SortParameters> sorts_;
   std::vector<Preset> presets_;
+  std::vector<std::string> field_views_;  // "Diagnostics": [{"diagnostic": "FieldView", "field": ...}]
   std::unique_ptr<Table> energy_, energy_cons_, convergence_, charge_;
   bool charge_header_ = false;
   double E_ = 0, B_ = 0, E0_ = 0, B0_ = 0;
