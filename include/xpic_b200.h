@@ -162,7 +162,11 @@ int xb_operator_upload(xb_ctx* ctx, const double* coef);
  * in which the scatter's integer atomics resolved -- results then differ run to run at round-off level;
  * with track_ids = 1 the order is always canonical, by id);
  * what = 3 the particle pass of eccapfim's residual evaluation (0: CTA-wide task machine, default;
- * 1: one thread per particle). */
+ * 1: one thread per particle);
+ * what = 4: eccapfim's per-particle Picard iteration of residual evaluation k + 1 starts from the velocity
+ * evaluation k of the same step converged to (1, default) or from the start-of-step velocity every time as
+ * the reference does (0, src/impls/eccapfim/particles.cpp:77-78); the converged particle state is the same
+ * to the Picard tolerance, the number of field gathers per evaluation drops from ~3.7 to ~2. */
 int xb_set_option(xb_ctx* ctx, int32_t what, int32_t value);
 /* --- eccapfim (BASELINE config 5): xb_step / xb_stage with scheme XB_ECCAPFIM run
  * eccapfim::Simulation::timestep_implementation (src/impls/eccapfim/simulation.cpp:36-44); stages

@@ -702,6 +702,10 @@ int xb_set_option(xb_ctx* c, int32_t what, int32_t value)
     c->cap_variant = value;
     return 0;
   }
+  if (what == 4) {
+    c->nl.warm_start = value != 0;
+    return 0;
+  }
   XB_FAIL("xb_set_option: unknown option");
 }
 

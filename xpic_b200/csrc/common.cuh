@@ -84,6 +84,8 @@ struct Nonlinear {
   int cheb_degree = 12;   // Chebyshev degree of the residual preconditioner (0: none)
   double cn_tol = 0.5e-7;
   int cn_maxit = 30;
+  bool warm_start = true;  // Picard iterations of evaluation k + 1 start from the velocities of evaluation k
+  bool pn_valid = false;
   int iterations = 0, fevals = 0, reason = 0;
   double fnorm = 0.0, avg_cn = 0.0, avg_cells = 0.0;
   std::vector<double> hist;

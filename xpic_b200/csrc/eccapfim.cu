@@ -58,6 +58,7 @@ struct CapArgs {
   int groups_x;
   unsigned long long* counters;  // [0] Picard iterations, [1] traversed segments
   int* error;
+  int warm;  // pn holds the pushed state of the previous evaluation of this step: start Picard from it
 };
 
 template <int NC>
@@ -815,6 +816,13 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
         }
         tau = 0.0;
         start_substep();
+        if (a.warm && dtau == dt) {
+          // Picard starts from the mean velocity the previous residual evaluation of this step converged to
+          // (the reference restarts from v0 every time, particles.cpp:77-78; the fixed point is the same)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) vh[c] = 0.5 * (a.pn[3 + c][idx] + v0[c]);
+          moved = true;
+        }
         state = CS_FIELDS;
       }
       else
@@ -968,6 +976,7 @@ int cap_form_function(xb_ctx* c, double* x, double* F)
     a.cn_maxit = nl.cn_maxit;
     a.counters = c->cap_counters;
     a.error = reinterpret_cast<int*>(c->cap_counters + 2);
+    a.warm = (nl.warm_start && nl.pn_valid) ? 1 : 0;
     if (c->cap_variant == 1) {  // thread-per-particle kernel, kept as a cross-check
       a.groups_x = (g.nx + CAP_CELLS - 1) / CAP_CELLS;
       const int64_t blocks = (int64_t)a.groups_x * g.ny * g.nzl;
@@ -993,6 +1002,7 @@ int cap_form_function(xb_ctx* c, double* x, double* F)
   XB_LAUNCH(c, k_cap_function, grid_for(g.ncl), 256, 0, g, x, c->cap_rhs0, c->cap_J, F);
   ++nl.fevals;
   nl.particles_per_eval = total;
+  nl.pn_valid = true;
   return 0;
 }
 
@@ -1032,6 +1042,7 @@ int cap_prepare(xb_ctx* c)
       if (c->g.nranks > 1) XB_CHECK(migrate_and_sort(c, s, 0.0));
       else XB_CHECK(particles_sort(c, s, 0.0));
     }
+  c->nl.pn_valid = false;  // the first evaluation of a step starts every particle from (r0, v0)
   XB_CHECK(halo_fill(c, c->B, GZ));  // DMGlobalToLocal(B), simulation.cpp:64
   XB_CHECK(vec_copy_owned(c, c->E, c->cap_rhs0));
   XB_CHECK(curl_apply(c, false, c->B, c->cap_rhs0, 0.5 * c->g.dt, true));
