@@ -173,33 +173,56 @@ __global__ void k_scan_add(int32_t* __restrict__ out, int64_t n, const int32_t* 
 
 // pass 2: scatter into the other SoA buffer.  The input is nearly sorted, so the lanes of a warp
 // mostly share a handful of bins: lanes with equal keys elect a leader that reserves the whole
-// run with one atomic (returning atomics are what limits this kernel, not the copies).
-__global__ void k_scatter(int64_t n, const int32_t* __restrict__ key, int32_t* __restrict__ cursor, const double* __restrict__ s0,
-                          const double* __restrict__ s1, const double* __restrict__ s2, const double* __restrict__ s3,
-                          const double* __restrict__ s4, const double* __restrict__ s5, const uint64_t* __restrict__ sid,
-                          double* __restrict__ d0, double* __restrict__ d1, double* __restrict__ d2, double* __restrict__ d3,
-                          double* __restrict__ d4, double* __restrict__ d5, uint64_t* __restrict__ did, double dtm, double Lx, double Ly, double Lz)
+// run with one atomic.  The kernel is bound by the latency of those returning atomics (ncu: 65 stall
+// cycles per issued instruction on the long scoreboard), so every thread carries SCATTER_ITEMS
+// particles whose reservations are all in flight before the first one is used.
+constexpr int SCATTER_ITEMS = 4;
+constexpr int SCATTER_THREADS = 256;
+
+__global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(int64_t n, const int32_t* __restrict__ key, int32_t* __restrict__ cursor,
+                                                            const double* __restrict__ s0, const double* __restrict__ s1,
+                                                            const double* __restrict__ s2, const double* __restrict__ s3,
+                                                            const double* __restrict__ s4, const double* __restrict__ s5,
+                                                            const uint64_t* __restrict__ sid, double* __restrict__ d0, double* __restrict__ d1,
+                                                            double* __restrict__ d2, double* __restrict__ d3, double* __restrict__ d4,
+                                                            double* __restrict__ d5, uint64_t* __restrict__ did, double dtm, double Lx, double Ly,
+                                                            double Lz)
 {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int32_t k = i < n ? key[i] : -1;
-  const bool live = k >= 0;  // key -1: the particle left the slab (migrate.cu)
-  const unsigned active = __ballot_sync(0xffffffffu, live);
-  if (!live) return;
-  const unsigned peers = __match_any_sync(active, k);
   const int lane = threadIdx.x & 31;
-  const int leader = __ffs(peers) - 1;
-  int32_t base = 0;
-  if (lane == leader) base = atomicAdd(&cursor[k], __popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  const int32_t pos = base + __popc(peers & ((1u << lane) - 1u));
-  const double vx = s3[i], vy = s4[i], vz = s5[i];
-  d0[pos] = moved_coord(s0[i], vx, dtm, Lx);  // the same bits the key pass binned (dtm = 0: plain copy + wrap)
-  d1[pos] = moved_coord(s1[i], vy, dtm, Ly);
-  d2[pos] = moved_coord(s2[i], vz, dtm, Lz);
-  d3[pos] = vx;
-  d4[pos] = vy;
-  d5[pos] = vz;
-  if (sid) did[pos] = sid[i];
+  const int64_t first = (int64_t)blockIdx.x * (SCATTER_THREADS * SCATTER_ITEMS) + threadIdx.x;
+  int32_t k[SCATTER_ITEMS], base[SCATTER_ITEMS];
+  unsigned peers[SCATTER_ITEMS];
+#pragma unroll
+  for (int j = 0; j < SCATTER_ITEMS; ++j) {
+    const int64_t i = first + (int64_t)j * SCATTER_THREADS;
+    k[j] = i < n ? key[i] : -1;  // key -1: the particle left the slab (migrate.cu)
+  }
+#pragma unroll
+  for (int j = 0; j < SCATTER_ITEMS; ++j) {
+    const bool live = k[j] >= 0;
+    const unsigned active = __ballot_sync(0xffffffffu, live);
+    peers[j] = 0u;
+    base[j] = 0;
+    if (live) {
+      peers[j] = __match_any_sync(active, k[j]);
+      if (lane == __ffs(peers[j]) - 1) base[j] = atomicAdd(&cursor[k[j]], __popc(peers[j]));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SCATTER_ITEMS; ++j) {
+    if (k[j] < 0) continue;
+    const int64_t i = first + (int64_t)j * SCATTER_THREADS;
+    const int32_t b = __shfl_sync(peers[j], base[j], __ffs(peers[j]) - 1);
+    const int32_t pos = b + __popc(peers[j] & ((1u << lane) - 1u));
+    const double vx = s3[i], vy = s4[i], vz = s5[i];
+    d0[pos] = moved_coord(s0[i], vx, dtm, Lx);  // the same bits the key pass binned (dtm = 0: plain copy + wrap)
+    d1[pos] = moved_coord(s1[i], vy, dtm, Ly);
+    d2[pos] = moved_coord(s2[i], vz, dtm, Lz);
+    d3[pos] = vx;
+    d4[pos] = vy;
+    d5[pos] = vz;
+    if (sid) did[pos] = sid[i];
+  }
 }
 
 // canonical order inside a bin (makes every later sum reproducible run to run although the scatter
@@ -253,13 +276,13 @@ int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBu
   double** d = s.p[1 - s.cur];
   uint64_t* did = s.id[1 - s.cur];
   if (nlocal > 0)
-    XB_LAUNCH(c, k_scatter, grid_for(nlocal), 256, 0, nlocal, s.key, c->cursor, p[0], p[1], p[2], p[3], p[4], p[5], s.id[s.cur], d[0], d[1], d[2], d[3],
+    XB_LAUNCH(c, k_scatter, grid_for(nlocal, SCATTER_THREADS * SCATTER_ITEMS), SCATTER_THREADS, 0, nlocal, s.key, c->cursor, p[0], p[1], p[2], p[3], p[4], p[5], s.id[s.cur], d[0], d[1], d[2], d[3],
               d[4], d[5], did, dt_move, g.Lx, g.Ly, g.Lz);
   if (arr) {
     const int64_t na[2] = {n_from_down, n_from_up};
     for (int k = 0; k < 2; ++k)
       if (na[k] > 0)
-        XB_LAUNCH(c, k_scatter, grid_for(na[k]), 256, 0, na[k], arr->recv_key[k], c->cursor, arr->recv[k][0], arr->recv[k][1], arr->recv[k][2],
+        XB_LAUNCH(c, k_scatter, grid_for(na[k], SCATTER_THREADS * SCATTER_ITEMS), SCATTER_THREADS, 0, na[k], arr->recv_key[k], c->cursor, arr->recv[k][0], arr->recv[k][1], arr->recv[k][2],
                   arr->recv[k][3], arr->recv[k][4], arr->recv[k][5], c->track_ids ? reinterpret_cast<const uint64_t*>(arr->recv[k][6]) : nullptr, d[0],
                   d[1], d[2], d[3], d[4], d[5], did, 0.0, g.Lx, g.Ly, g.Lz);
   }
