@@ -235,16 +235,17 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // needs ~100 registers and two dependent global loads, which starved that kernel); one CTA per 4 cells,
 // B staged in a shared-memory tile:
 // gather B^n, beta, A_p alpha[3][3] and I_p (src/impls/ecsim/particles.cpp:107-115).
-constexpr int PF_THREADS = 128;
+constexpr int PF_THREADS = 256;
+constexpr int PF_CELLS = 16;  // x-consecutive cells per CTA (one B tile of 18 x 3 x 3 nodes)
 
 __global__ void __launch_bounds__(PF_THREADS) k_particle_fields(Grid g, DepositArgs a, const double* __restrict__ B, int groups_x, int zl_off)
 {
-  __shared__ double Bt[FIELD_TILE];
+  __shared__ double Bt[FieldTile<PF_CELLS>::SIZE];
   const int gx = blockIdx.x % groups_x, row = blockIdx.x / groups_x;  // row = plane index * ny + cy within this launch
   const int cy = row % g.ny, pl = row / g.ny;
   const int zl = pl + zl_off;
-  const int cx0 = gx * TILE_CELLS, ncell = min(TILE_CELLS, g.nx - cx0);
-  load_field_tile<TILE_CELLS>(g, B, cx0, cy, zl, Bt, threadIdx.x, PF_THREADS);
+  const int cx0 = gx * PF_CELLS, ncell = min(PF_CELLS, g.nx - cx0);
+  load_field_tile<PF_CELLS>(g, B, cx0, cy, zl, Bt, threadIdx.x, PF_THREADS);
   const int64_t cell0 = a.bin_cell0 + ((int64_t)pl * g.ny + cy) * g.nx + cx0;
   const int32_t p0 = a.bin_start[cell0 << 3], p1 = a.bin_start[(cell0 + ncell) << 3];
   __syncthreads();
@@ -254,9 +255,9 @@ __global__ void __launch_bounds__(PF_THREADS) k_particle_fields(Grid g, DepositA
     const double v[3] = {a.p[3][i], a.p[4][i], a.p[5][i]};
     Weights w;
     make_weights(g, a.p[0][i], a.p[1][i], a.p[2][i], a.zshift, w);
-    const TileIndex t = tile_index<TILE_CELLS>(w, cx0, cy, zl);
+    const TileIndex t = tile_index<PF_CELLS>(w, cx0, cy, zl);
     double Bp[3], b[3];
-    gather_B_tile<TILE_CELLS>(Bt, w, t, Bp);
+    gather_B_tile<PF_CELLS>(Bt, w, t, Bp);
 #pragma unroll
     for (int c = 0; c < 3; ++c) b[c] = Bp[c] * f;
     double vxb[3];
@@ -610,7 +611,7 @@ int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* 
     if (nparticles > 0) {
       // the cells of one launch are whole planes: owned planes (bin plane 1.. -> zl 0..) or one ghost plane
       const Grid& g = c->g;
-      const int groups_x = (g.nx + TILE_CELLS - 1) / TILE_CELLS;
+      const int groups_x = (g.nx + PF_CELLS - 1) / PF_CELLS;
       const int64_t planes = ncells / g.plane;
       const int zl_off = bin_cell0 == g.plane ? 0 : (stage_cell0 == 0 ? -1 : g.nzl);
       XB_LAUNCH(c, k_particle_fields, (int)(groups_x * g.ny * planes), PF_THREADS, 0, g, a, c->B, groups_x, zl_off);
