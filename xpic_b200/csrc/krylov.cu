@@ -17,10 +17,13 @@ namespace xb {
 
 int spmv(xb_ctx* c, int op, double* x, double* y);
 
-// One Chebyshev step fused with the matrix-free M:  z += d ; r -= M d ; d_out = a d + b r.
-// d_in carries valid ghosts (width 1); 144 B of HBM traffic per node, the 13-point stencil reads hit L1/L2.
-__global__ void __launch_bounds__(256) k_cheb_step(Grid g, const double* __restrict__ d_in, double* __restrict__ d_out, double* __restrict__ r,
-                                                  double* __restrict__ z, double a, double b, double diag)
+// One Chebyshev step as a three-term recurrence in the iterate itself, fused with the matrix-free operator
+// D = diag I + dt^2/2 curl curl:   z2 = z1 + a (z1 - z0) + b (u - D z1).
+// z1 carries valid ghosts (width 1).  96 B of HBM traffic per node (z1, z0, u in, z2 out; the 13-point
+// stencil reads hit L1/L2) against 144 B for the textbook form that carries the residual and the
+// direction along (z += d; r -= D d; d = a d + b r).  z0 == nullptr stands for z0 = 0 (first step).
+__global__ void __launch_bounds__(256) k_cheb_step(Grid g, const double* __restrict__ z1, const double* __restrict__ z0, const double* __restrict__ u,
+                                                  double* __restrict__ z2, double a, double b, double diag)
 {
   const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (node >= g.ncl) return;
@@ -29,30 +32,17 @@ __global__ void __launch_bounds__(256) k_cheb_step(Grid g, const double* __restr
   const int ym = y == 0 ? g.ny - 1 : y - 1, yp = y == g.ny - 1 ? 0 : y + 1;
   auto f = [&](int comp, int ox, int oy, int oz) {
     const int xx = ox < 0 ? xm : (ox > 0 ? xp : x), yy = oy < 0 ? ym : (oy > 0 ? yp : y);
-    return __ldg(&d_in[g.vidx(xx, yy, zl + oz, comp)]);
+    return __ldg(&z1[g.vidx(xx, yy, zl + oz, comp)]);
   };
   const double inv_d[3] = {1.0 / g.dx, 1.0 / g.dy, 1.0 / g.dz};
   const double h = 0.5 * g.dt * g.dt;
   const int64_t o = g.vidx(x, y, zl, 0);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const double dc = f(c, 0, 0, 0);
-    const double Md = diag * dc + h * curlcurl(c, inv_d, f);
-    const double rn = r[o + c] - Md;
-    z[o + c] += dc;
-    r[o + c] = rn;
-    d_out[o + c] = a * dc + b * rn;
-  }
-}
-
-__global__ void k_cheb_init(const double* __restrict__ u, double* __restrict__ z, double* __restrict__ r, double* __restrict__ d, double inv_theta,
-                            int64_t n)
-{
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double ui = u[i];
-    z[i] = 0.0;
-    r[i] = ui;
-    d[i] = inv_theta * ui;
+    const double zc = f(c, 0, 0, 0);
+    const double Dz = diag * zc + h * curlcurl(c, inv_d, f);
+    const double zo = z0 ? z0[o + c] : 0.0;
+    z2[o + c] = zc + a * (zc - zo) + b * (u[o + c] - Dz);
   }
 }
 
@@ -73,33 +63,27 @@ static int ensure_workspace(xb_ctx* c, int m)
 }
 
 // z ~= (diag I + dt^2/2 curl curl)^{-1} u by `deg` Chebyshev steps on [lmin, lmax] (Saad, Iterative
-// Methods, Alg. 12.1); diag = 2 gives M^{-1}.
-static int cheb_apply(xb_ctx* c, int deg, const double* u, double* z, double* work_r, double* work_d, double* work_Md, double diag = 2.0)
+// Methods, Alg. 12.1, written for the iterates: z_1 = u / theta,
+// z_{k+2} = z_{k+1} + rho_{k+1} rho_k (z_{k+1} - z_k) + (2 rho_{k+1} / delta) (u - D z_{k+1})); diag = 2 gives M^{-1}.
+// The iterates rotate through {z, work_a, work_b} so that the last one lands in z.
+static int cheb_apply(xb_ctx* c, int deg, const double* u, double* z, double* /*work_r*/, double* work_a, double* work_b, double diag = 2.0)
 {
   const Grid& g = c->g;
   const double lmin = diag;
   const double lmax = diag + 0.5 * g.dt * g.dt * 4.0 * (1.0 / (g.dx * g.dx) + 1.0 / (g.dy * g.dy) + 1.0 / (g.dz * g.dz));
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
   const double sigma = theta / delta;
+  double* buf[3] = {z, work_a, work_b};
+  if (deg < 1) deg = 1;
+  const int off = (3 - deg % 3) % 3;  // z_k lives in buf[(k + off) % 3]; z_deg in buf[0] = z
+  XB_CHECK(scale_into(c, u, 1.0 / theta, buf[(1 + off) % 3]));  // z_1
   double rho_old = 1.0 / sigma;
-  const int64_t n = g.nown;
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  XB_LAUNCH(c, k_cheb_init, blocks, 256, 0, u + g.own0, z + g.own0, work_r + g.own0, work_d + g.own0, 1.0 / theta, n);
-  double* d_cur = work_d;
-  double* d_nxt = work_Md;
-  for (int k = 0; k < deg; ++k) {
+  for (int k = 1; k < deg; ++k) {  // z_{k+1} from z_k, z_{k-1}
     const double rho = 1.0 / (2.0 * sigma - rho_old);
-    if (k + 1 < deg) {
-      XB_CHECK(halo_fill(c, d_cur, 1));
-      XB_LAUNCH(c, k_cheb_step, (int)((g.ncl + 255) / 256), 256, 0, g, d_cur, d_nxt, work_r, z, rho * rho_old, 2.0 * rho / delta, diag);
-      std::swap(d_cur, d_nxt);
-    }
-    else {
-      const double one = 1.0;
-      const double* vs[1] = {d_cur};
-      XB_CHECK(axpy_multi(c, 1, vs, &one, z));  // last step: z += d, no further residual needed
-    }
+    double* zk = buf[(k + off) % 3];
+    const double* zkm = k > 1 ? buf[(k - 1 + off) % 3] : nullptr;
+    XB_CHECK(halo_fill(c, zk, 1));
+    XB_LAUNCH(c, k_cheb_step, (int)((g.ncl + 255) / 256), 256, 0, g, zk, zkm, u, buf[(k + 1 + off) % 3], rho * rho_old, 2.0 * rho / delta, diag);
     rho_old = rho;
   }
   return 0;
