@@ -16,7 +16,17 @@ sim.set_particles_maxwellian(sid, grid[0] * grid[1] * grid[2] * ppc, T=0.1, seed
 p = int(os.environ.get("XPIC_BENCH_PRECOND", "6"))
 sim.solver_set(0, 1e-7, 1e-7, 100, 30, p)
 sim.solver_set(1, 1e-7, 1e-7, 100, 30, p)
-ms = sim.run_steps(steps)
+if os.environ.get("XPIC_PROFILE_RANGE"):
+    # ncu --profile-from-start off: only whole steady-state steps are captured (two warm-up steps first)
+    import ctypes
+
+    rt = ctypes.CDLL("libcudart.so")
+    sim.run_steps(2)
+    rt.cudaProfilerStart()
+    ms = sim.run_steps(steps)
+    rt.cudaProfilerStop()
+else:
+    ms = sim.run_steps(steps)
 if scheme == X.ECCAPFIM:
     print("nonlinear", sim.nonlinear_info())
 print("steps", steps, "ms/step", ms / steps, "its", sim.solver_info(0)[0], {k: round(1e3 * v[0] / max(v[1], 1), 3) for k, v in sim.timing().items()})
