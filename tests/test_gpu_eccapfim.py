@@ -19,20 +19,23 @@ pytestmark = pytest.mark.gpu
 TIGHT = 1e-14  # per-particle Picard tolerance for parity runs (reference: 0.5e-7)
 
 
-def make_cap_pair(n=(10, 10, 10), Np=30, T=0.1, curl_sign=+1, seed_fields=None, particles=None, d=(0.5, 0.5, 0.5), dt=1.5, particle_tol=TIGHT, atol=1e-13):
+def make_cap_pair(n=(10, 10, 10), Np=30, T=0.1, curl_sign=+1, seed_fields=None, particles=None, d=(0.5, 0.5, 0.5), dt=1.5, particle_tol=TIGHT, atol=1e-13,
+                  species=((-1.0, 1.0, 1.0),)):
     import xpic_b200 as X
 
     O.set_threads(min(8, O.max_threads()))
     o = O.Oracle(n, d=d, dt=dt, curl_sign=curl_sign)
     s = X.Simulation(n, d=d, dt=dt, scheme=X.ECCAPFIM, curl_sign=curl_sign, track_ids=True)
-    sid = o.add_species(q=-1.0, m=1.0, n=1.0, Np=Np)
-    if particles is None:
-        o.set_particles_maxwell(sid, T=T, tov=True)
-    else:
-        o.set_particles(sid, particles)
-    gs = s.add_species(q=-1.0, m=1.0, n=1.0, Np=Np)
-    pts, ids = o.get_particles(sid)
-    assert s.add_particles(gs, pts, ids) == len(ids)
+    for (q, m, dens) in species:
+        sid = o.add_species(q=q, m=m, n=dens, Np=Np)
+        if particles is None:
+            o.set_particles_maxwell(sid, T=T, tov=True)
+        else:
+            o.set_particles(sid, particles)
+        gs = s.add_species(q=q, m=m, n=dens, Np=Np)
+        assert gs == sid
+        pts, ids = o.get_particles(sid)
+        assert s.add_particles(gs, pts, ids) == len(ids)
     o.snes_set(atol=atol, rtol=1e-30, maxit=400, precond=1, shift=0.5)
     o.snes_set_particle_tol(particle_tol)
     s.nonlinear_set(atol=atol, rtol=1e-30, maxit=400, particle_tol=particle_tol, particle_maxit=30)
@@ -120,6 +123,33 @@ def test_step_matches_oracle_10_steps():
     pg, ig = by_id(*s.get_particles())
     assert np.array_equal(io, ig)
     assert rel_err(pg, po) < 1e-8
+
+
+def test_two_species_step_matches_oracle():
+    # electrons and (heavy, oppositely charged) ions: per-sort currents, their sum in the residual, the
+    # preconditioner's plasma shift summed over the sorts
+    o, s = make_cap_pair(n=(9, 8, 7), Np=12, species=((-1.0, 1.0, 1.0), (+1.0, 100.0, 1.0)), seed_fields=51)
+    x = o.get_field("E")
+    fo = o.eccapfim_function(x)
+    fg = s.eccapfim_function(x)
+    assert rel_err(fg, fo) < 1e-11
+    for sid in (0, 1):
+        assert rel_err(s.get_field("J_sort", sid), o.get_field("J_sort", sid)) < 1e-11
+    o2, s2 = make_cap_pair(n=(9, 8, 7), Np=12, species=((-1.0, 1.0, 1.0), (+1.0, 100.0, 1.0)), seed_fields=51)
+    for _ in range(3):
+        o2.step(O.ECCAPFIM)
+        s2.step()
+    for name in ("E", "B"):
+        assert rel_err(s2.get_field(name), o2.get_field(name)) < 1e-9, name
+    for sid in (0, 1):
+        po, io = by_id(*o2.get_particles(sid))
+        pg, ig = by_id(*s2.get_particles(sid))
+        assert np.array_equal(io, ig) and rel_err(pg, po) < 1e-9
+    for sid in (0, 1):
+        s2.charge_density(sid)  # ChargeConservation::initialize
+    s2.step()
+    norms = s2.charge_conservation("J")  # two sorts + the total
+    assert norms.shape == (3, 2) and np.all(norms[:, 0] < 5e-12)
 
 
 def test_energy_is_conserved_to_solver_tolerance():
