@@ -73,3 +73,30 @@ def test_ecsim_field_dump_t50():
         g = np.fromfile(os.path.join(GOLDEN, "ecsim_ex1", f"{name}_050.f32"), dtype=np.float32).astype(np.float64)
         f = o.get_field(name)
         assert np.linalg.norm(f - g) / np.linalg.norm(g) < 5e-6
+
+
+@pytest.mark.parametrize("scheme", ["EB1A", "EB1B", "EBLF"])
+def test_boris_update_vEB_trajectories_match_golden(scheme):
+    """BorisPush::update_vEB + update_r (src/algorithms/boris_push.cpp:19-22,48-57), the velocity update of
+    the second push, against the reference's golden single-particle trajectories: electron drift in crossed
+    fields, 5000 steps of omega_c dt = 49 (tests/boris_push/boris_push_ex4.cpp:11-60, process_EB1A / EB1B /
+    EBLF of tests/boris_push/boris_push.h:160-183)."""
+    dt, nt, qm = 0.1975, 5000, -1.0
+    E0, B0 = np.array([0.0, 0.0, 1.0]), np.array([250.0, 0.0, 0.0])
+    r, v = np.array([0.0, 0.0, 0.0]), np.array([0.1, 0.0, 0.4])
+    if scheme.endswith("LF"):
+        r = r + v * (-dt / 2.0)
+    rows = []
+    for t in range(nt + 1):
+        if t % 32 == 0:
+            rows.append([t * dt, *r, *v])
+        if scheme == "EB1A":
+            v = O.boris_update_vEB(dt, qm, E0, B0, v)
+            r = r + v * dt
+        else:  # EB1B, EBLF
+            r = r + v * dt
+            v = O.boris_update_vEB(dt, qm, E0, B0, v)
+    _, gold = O.read_table(os.path.join(GOLDEN, "boris_push_ex4", scheme + ".txt"))
+    rows = np.array(rows)
+    assert rows.shape == gold.shape
+    np.testing.assert_allclose(rows, gold, rtol=2e-6, atol=2e-7)
