@@ -68,6 +68,7 @@ def lib():
         L.xo_snes_history.restype = C.c_int
         L.xo_snes_history.argtypes = [C.c_void_p, dp, C.c_int]
         L.xo_eccapfim_function.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.xo_crank_nicolson_uniform.argtypes = [C.c_double, C.c_double, dp, dp, dp, dp]
         L.xo_cell_traversal.restype = C.c_int
         L.xo_cell_traversal.argtypes = [C.c_void_p, dp, dp, dp, C.c_int]
         _lib = L
@@ -226,6 +227,15 @@ def boris_update_vEB(dt, qm, E, B, v):
     v = np.array(v, dtype=np.float64)
     lib().xo_boris_update_vEB(dt, qm, _dp(E), _dp(B), _dp(v))
     return v
+
+
+def crank_nicolson_uniform(dt, qm, E, B, r, v):
+    E = np.ascontiguousarray(E, dtype=np.float64)
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    r = np.array(r, dtype=np.float64)
+    v = np.array(v, dtype=np.float64)
+    lib().xo_crank_nicolson_uniform(dt, qm, _dp(E), _dp(B), _dp(r), _dp(v))
+    return r, v
 
 
 def read_table(path):

@@ -947,6 +947,22 @@ void cap_decompose(const Sim& s, std::vector<double>& Jg, double alpha, const do
   }
 }
 
+// The closed form of one Crank-Nicolson velocity solve for given mean fields: particles.cpp:137-144 ==
+// CrankNicolsonPush::process, src/algorithms/crank_nicolson_push.cpp:53-62
+//   a = alpha E, b = alpha B, w = v0 + a, vh = (w + w x b + b (w . b)) / (1 + b^2),  alpha = dtau q / (2 m)
+inline void cn_mean_velocity(double alpha, const double* v0, const double* Ep, const double* Bp, double* vh)
+{
+  double a[3], b[3], w[3], wxb[3];
+  for (int c = 0; c < 3; ++c) {
+    a[c] = alpha * Ep[c];
+    b[c] = alpha * Bp[c];
+    w[c] = v0[c] + a[c];
+  }
+  cross(w, b, wxb);
+  const double wb = dot(w, b), den = 1.0 + dot(b, b);
+  for (int c = 0; c < 3; ++c) vh[c] = ((w[c] + wxb[c]) + b[c] * wb) / den;
+}
+
 inline double len3(const V3& a, const V3& b) { return std::hypot(a[0] - b[0], a[1] - b[1], a[2] - b[2]); }  // vector3.h:160-164
 
 // eccapfim::Particles::form_iteration for one particle (particles.cpp:73-176).  `curr` enters as
@@ -1008,15 +1024,7 @@ void cap_push_particle(const Sim& s, const Species& sp, const std::vector<double
     double rn_, r0_;
     rn_ = r0_ = get_residue();
     for (; rn_ > cn_atol + cn_rtol * r0_ && it < cn_maxit; it++) {  // :136-148
-      double a[3], b[3], w[3], wxb[3];
-      for (int c = 0; c < 3; ++c) {
-        a[c] = alpha * Ep[c];
-        b[c] = alpha * Bp[c];
-        w[c] = p0.p[c] + a[c];
-      }
-      cross(w, b, wxb);
-      const double wb = dot(w, b), den = 1.0 + dot(b, b);
-      for (int c = 0; c < 3; ++c) vh[c] = ((w[c] + wxb[c]) + b[c] * wb) / den;
+      cn_mean_velocity(alpha, p0.p, Ep, Bp, vh);
       for (int c = 0; c < 3; ++c) {
         pn.r[c] = p0.r[c] + dtau * vh[c];
         pn.p[c] = 2.0 * vh[c] - p0.p[c];
@@ -1581,6 +1589,18 @@ void xo_eccapfim_function(void* h, const double* x, double* f, int prepare)
       }
     }
   cap_form_function(s, x, f);
+}
+
+// one Crank-Nicolson step in fields that do not depend on the path (CrankNicolsonPush::process with a
+// constant set_fields callback converges in its first iteration): r += dt vh, v = 2 vh - v
+void xo_crank_nicolson_uniform(double dt, double qm, const double* Ep, const double* Bp, double* r, double* v)
+{
+  double vh[3];
+  cn_mean_velocity(0.5 * dt * qm, v, Ep, Bp, vh);
+  for (int c = 0; c < 3; ++c) {
+    r[c] = r[c] + dt * vh[c];
+    v[c] = 2.0 * vh[c] - v[c];
+  }
 }
 
 // the stopping points of cell_traversal(end, start); returns their number (<= cap written)

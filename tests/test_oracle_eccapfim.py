@@ -90,3 +90,22 @@ def test_field_dumps_t5():
         g = np.fromfile(os.path.join(GOLDEN, "eccapfim_ex1", f"{name}_005.f32"), dtype=np.float32).astype(np.float64)
         f = o.get_field(name)
         assert np.linalg.norm(f - g) / np.linalg.norm(g) < tol
+
+
+@pytest.mark.parametrize("omega_dt", [0.1, 1.0, 10.0])
+def test_crank_nicolson_velocity_solve_matches_golden_gyration(omega_dt):
+    """The closed-form Crank-Nicolson velocity solve inside eccapfim's particle loop (particles.cpp:137-144,
+    the same formula as CrankNicolsonPush::process) against the reference's golden gyration trajectories
+    (tests/crank_nicolson_push/crank_nicolson_push_ex1.cpp: uniform B = (0, 0, 2), 100 000 steps)."""
+    B0 = np.array([0.0, 0.0, 2.0])
+    dt, nt = omega_dt / 2.0, 100_000
+    r, v = np.array([0.5, 0.0, 0.0]), np.array([0.0, 1.0, 0.0])
+    rows = []
+    for t in range(nt + 1):
+        if t % (nt // 123) == 0:
+            rows.append([t * dt, *r, *v])
+        r, v = O.crank_nicolson_uniform(dt, -1.0, np.zeros(3), B0, r, v)
+    _, gold = O.read_table(os.path.join(GOLDEN, "crank_nicolson_push_ex1", f"omega_dt_{omega_dt:.1f}.txt"))
+    rows = np.array(rows)
+    assert rows.shape == gold.shape
+    np.testing.assert_allclose(rows, gold, rtol=5e-6, atol=5e-7)
