@@ -349,7 +349,8 @@ def main():
                        "stage_ms": {k: 1e3 * v for k, v in stage_s.items()},
                        **({"nonlinear": {"solver": "Anderson(10) on x - P F(x), P = Chebyshev(12) of ((1+sigma) I + dt^2/4 curl curl)^-1; atol = rtol = 1e-7 (reference)",
                                          "iterations_last_step": cap["iterations"], "residual_evaluations_last_step": cap["fevals"],
-                                         "picard_iterations_per_particle": cap["avg_cn"], "path_pieces_per_particle": cap["avg_cells"],
+                                         "picard_iterations_per_particle_last_evaluation": cap["avg_cn"], "path_pieces_per_particle": cap["avg_cells"],
+                                         "picard": "warm-started from the previous residual evaluation of the step (first evaluation cold: ~2.7 iterations per particle)",
                                          "reference_residual_evaluations_per_step": 105}} if cap else {})},
             "roofline": roofline, "roofline_dominant": roofline_dominant, "kernels": kernels, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
