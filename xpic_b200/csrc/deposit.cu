@@ -331,9 +331,13 @@ __device__ __forceinline__ void octant_segment(const double* __restrict__ rs0, c
       (void)dummy;
       const int c1 = op_row(HALF, j), c2 = op_col(HALF, j);
       const double av = valid ? s[c1] : 0.0;
-      const double bv = c2 < 3 ? rf[c1 * 3 + c2] * s[c2] : (gq == 0 ? rf[9 + c1] : 0.0);
       const int v = op_base(HALF, j) + op_variant(HALF, j, OCT);
-      dmma(acc[v][0], acc[v][1], av, bv);
+      if (c2 < 3)
+        dmma(acc[v][0], acc[v][1], av, rf[c1 * 3 + c2] * s[c2]);
+      else
+        // the current: a DMMA would be 1/8 filled (one column); each lane keeps s_c1(g) I_c1 of its own
+        // particle instead, the four particles of a row are summed once per cell (cell_half)
+        acc[v][0] += av * rf[9 + c1];
     }
   }
 }
@@ -407,6 +411,18 @@ __device__ __forceinline__ void cell_half(const Grid& g, const DepositArgs& a, d
     }
   }
 
+  // the current partials of the four lanes of a row (one per particle of a group) -> lane q == 0
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    if (op_col(HALF, j) != 3) continue;
+#pragma unroll
+    for (int v = 0; v < op_nvar(HALF, j); ++v) {
+      double t = acc[op_base(HALF, j) + v][0];
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      acc[op_base(HALF, j) + v][0] = t;
+    }
+  }
   // one fold per cell: variants of a slot may land on the same entry, so they go in separate passes
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
