@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(DEP_WARPS * 32) k_cell_blocks(Grid g, DepositA
 // of the same particle, and receives D[g][2q], D[g][2q + 1] -- exactly the 18 entries per lane of
 // the scalar kernel above, so the fold into the cell block is shared.  The current I uses three
 // more DMMAs with B = I_p in column 0.  Per four particles a lane issues 12 shared loads,
-// 9 multiplies and 12 DMMAs instead of ~180 scalar instructions.
+// 9 multiplies, 9 DMMAs and 3 FMAs (the current) instead of ~180 scalar instructions.
 // ---------------------------------------------------------------------------------------------
 constexpr int MMA_CHUNK = 32;
 constexpr int SREC = 25;  // shape record: 24 weights, odd stride (conflict-free stores and loads)
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_particle_fields(Grid g, DepositA
   }
 }
 
-// The 12 DMMAs of a particle group are split between the two warps of a cell so that their
+// The 9 DMMAs + 3 current FMAs of a particle group are split between the two warps of a cell so that their
 // accumulators (and therefore their folds into the cell block) are disjoint:
 //   half 0: (0,0) (0,1) (0,2) I_0 (1,0) (1,1)      half 1: (1,2) I_1 (2,0) (2,1) (2,2) I_2
 // slot j of a half: row component op_row, column component op_col (3 = current).
