@@ -39,6 +39,14 @@ int cheb_solve_shifted(xb_ctx* c, int deg, double diag, const double* u, double*
 int reduce_finish(xb_ctx* c, int nv, double* host_out);                                // fields.cu
 int migrate_and_sort(xb_ctx* c, Species& s, double dt_move);                           // migrate.cu
 
+// periodic index of a node a few cells outside [0, n): compare / add instead of the runtime modulo of wrapi()
+__device__ __forceinline__ int wrap_near(int i, int n)
+{
+  while (i < 0) i += n;
+  while (i >= n) i -= n;
+  return i;
+}
+
 constexpr int CAP_CELLS = 8;
 constexpr int CAP_THREADS = 256;
 constexpr int CAP_LO = 2;  // staged nodes below the first cell (x), the row (y) and the plane (z)
@@ -500,7 +508,7 @@ __global__ void __launch_bounds__(CAP_THREADS) k_cap_push(Grid g, CapArgs a)
   if (threadIdx.x < 2) cnt[threadIdx.x] = 0ull;
   for (int e = threadIdx.x; e < 3 * CAP_VOL; e += CAP_THREADS) {
     const int x = e % CAP_NX, y = (e / CAP_NX) % CAP_NY, z = (e / (CAP_NX * CAP_NY)) % CAP_NZ, c = e / CAP_VOL;
-    const int64_t o = g.vidx(wrapi(cx0 - CAP_LO + x, g.nx), wrapi(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c);
+    const int64_t o = g.vidx(wrap_near(cx0 - CAP_LO + x, g.nx), wrap_near(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c);
     Et[e] = __ldg(&a.E[o]);
     Bt[e] = __ldg(&a.B[o]);
     Jt[e] = 0.0;
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(CAP_THREADS) k_cap_push(Grid g, CapArgs a)
     const double val = Jt[e];
     if (val == 0.0) continue;
     const int x = e % CAP_NX, y = (e / CAP_NX) % CAP_NY, z = (e / (CAP_NX * CAP_NY)) % CAP_NZ, c = e / CAP_VOL;
-    atomicAdd(&a.J[g.vidx(wrapi(cx0 - CAP_LO + x, g.nx), wrapi(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c)], val);
+    atomicAdd(&a.J[g.vidx(wrap_near(cx0 - CAP_LO + x, g.nx), wrap_near(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c)], val);
   }
 }
 
@@ -605,7 +613,7 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
   }
   for (int e = tid; e < VOL3; e += CAP2_THREADS) {
     const int x = e % CapCtx2::NX, y = (e / CapCtx2::NX) % CapCtx2::NY, z = (e / (CapCtx2::NX * CapCtx2::NY)) % CapCtx2::NZ, c = e / CapCtx2::VOL;
-    const int64_t o = g.vidx(wrapi(cx0 - CAP_LO + x, g.nx), wrapi(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c);
+    const int64_t o = g.vidx(wrap_near(cx0 - CAP_LO + x, g.nx), wrap_near(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c);
     Et[e] = __ldg(&a.E[o]);
     Bt[e] = __ldg(&a.B[o]);
     Jt[e] = 0.0;
@@ -891,7 +899,7 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
     const double val = Jt[e];
     if (val == 0.0) continue;
     const int x = e % CapCtx2::NX, y = (e / CapCtx2::NX) % CapCtx2::NY, z = (e / (CapCtx2::NX * CapCtx2::NY)) % CapCtx2::NZ, c = e / CapCtx2::VOL;
-    atomicAdd(&a.J[g.vidx(wrapi(cx0 - CAP_LO + x, g.nx), wrapi(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c)], val);
+    atomicAdd(&a.J[g.vidx(wrap_near(cx0 - CAP_LO + x, g.nx), wrap_near(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c)], val);
   }
 }
 
