@@ -22,9 +22,12 @@
 // one residual evaluation per iteration and ~10 instead of the reference's ~105 per step.  The stop
 // test is SNESConvergedDefault's on the true |F| with the reference's tolerances (simulation.h:14-19).
 //
-// k_cap_push: one CTA per CAP_CELLS x-consecutive cells; the E^{n+1/2,k} and B^n nodes a particle of
-// these cells can reach within one cell of motion are staged in shared memory, the current is
-// accumulated in a shared tile and flushed once (fast particles fall back to global loads / atomics).
+// Particle pass (k_cap_push_tasks, the default; k_cap_push = one thread per particle, cross-check): one CTA
+// per 16 x-consecutive cells; the E^{n+1/2,k} and B^n nodes a particle of these cells can reach within one
+// cell of motion are staged in shared memory, the current is accumulated in a shared tile and flushed once
+// (fast particles fall back to global loads / reductions).  Owners advance one particle each through
+// emit -> wait -> consume, all threads evaluate the emitted path pieces as dense tasks (see the kernel).
+// The Picard iteration of evaluation k + 1 starts from the velocity evaluation k converged to (option 4).
 #include <algorithm>
 #include <cmath>
 
