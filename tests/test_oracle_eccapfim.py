@@ -109,3 +109,13 @@ def test_crank_nicolson_velocity_solve_matches_golden_gyration(omega_dt):
     rows = np.array(rows)
     assert rows.shape == gold.shape
     np.testing.assert_allclose(rows, gold, rtol=5e-6, atol=5e-7)
+
+
+def test_initial_momentum_matches_golden():
+    """Row 0 of momentum_conservation.txt: P = (m / Np) sum v over the mt19937 initial particles
+    (src/diagnostics/momentum_conservation.cpp:84-111; the node weights of a particle sum to one)."""
+    o = _oracle()
+    pts, _ = o.get_particles()
+    P = (1.0 / 100) * pts[:, 3:].sum(axis=0)
+    _, gold = O.read_table(os.path.join(GOLDEN, "eccapfim_ex1", "momentum_conservation.txt"))
+    assert [f"{v: .6e}" for v in P] == [f"{v: .6e}" for v in gold[0, 1:4]]
