@@ -201,6 +201,12 @@ int xb_charge_density(xb_ctx* ctx, int32_t sid, double* rho);
  * 1 = J (eccapfim).  norms receives 2 * (number of sorts + 1) doubles, summed over all ranks. */
 int xb_charge_conservation(xb_ctx* ctx, int32_t which_current, double* norms);
 
+/* MomentumConservation::calculate (src/diagnostics/momentum_conservation.cpp:71-126) for sort sid with the
+ * present E: out = { Px, Py, Pz, QEx, QEy, QEz }, P = m / Np * sum v, QE = q / Np * sum E(x_p) with the global
+ * 2nd-order form factor, summed over all ranks.  The caller keeps P of the previous call for the
+ * (P1 - P0) / dt - QE residual of add_columns (:29-68). */
+int xb_momentum(xb_ctx* ctx, int32_t sid, double out[6]);
+
 /* Moments only at the present particle positions: fill_ecsim_current (ecsim/simulation.cpp:336-368). */
 int xb_deposit(xb_ctx* ctx);
 /* Solve (L? + M) x = b for host vectors with the given solver slot (KSPSolve). */

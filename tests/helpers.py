@@ -57,3 +57,29 @@ def csr_to_stencil(o, table):
         cols = cn * 3 + c2
         coef[k] = np.asarray(A[rows, cols]).reshape(-1)
     return coef
+
+
+def spline2(s):
+    s = np.abs(s)
+    return np.where(s <= 0.5, 0.75 - s * s, np.where(s < 1.5, 0.5 * (1.5 - s) ** 2, 0.0))
+
+
+def momentum_qe(pts, E, n, d, q_np):
+    """QE of MomentumConservation::calculate (momentum_conservation.cpp:84-117): sum over particles of
+    q / Np * E at the particle with the global 2nd-order Shape (electric(): No No Sh per component)."""
+    nx, ny, nz = n
+    Eg = E.reshape(nz, ny, nx, 3)
+    p = pts[:, :3] / np.array(d)
+    start = np.round(p - 1.5).astype(int)  # np.round is half-to-even; exact ties do not occur for these particles
+    out = np.zeros(3)
+    for k in range(4):
+        for j in range(4):
+            for i in range(4):
+                g = start + np.array([i, j, k])
+                no = [spline2(p[:, a] - g[:, a]) for a in range(3)]
+                sh = [spline2(p[:, a] - (g[:, a] + 0.5)) for a in range(3)]
+                idx = (g[:, 2] % nz, g[:, 1] % ny, g[:, 0] % nx)
+                out[0] += np.sum(Eg[idx + (0,)] * (no[2] * no[1] * sh[0]))
+                out[1] += np.sum(Eg[idx + (1,)] * (no[2] * sh[1] * no[0]))
+                out[2] += np.sum(Eg[idx + (2,)] * (sh[2] * no[1] * no[0]))
+    return q_np * out

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from helpers import by_id, rel_err
+from helpers import by_id, momentum_qe, rel_err
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -245,6 +245,35 @@ def test_host_program_writes_the_reference_tables(tmp_path):
             mine = np.fromfile(tmp_path / "eccapfim_ex1" / field / t, dtype=np.float32).astype(np.float64)
             gold_f = np.fromfile(os.path.join(GOLDEN, "eccapfim_ex1", f"{field}_0{t}.f32"), dtype=np.float32).astype(np.float64)
             assert mine.size == gold_f.size == 3000 and rel_err(mine, gold_f) < tol
+    tm, mom = O.read_table(str(tmp_path / "eccapfim_ex1" / "temporal" / "momentum_conservation.txt"))
+    tg, gm = O.read_table(os.path.join(GOLDEN, "eccapfim_ex1", "momentum_conservation.txt"))
+    assert tm == tg and mom.shape == gm.shape
+    np.testing.assert_allclose(mom[:, 1:7], gm[:, 1:7], rtol=5e-3, atol=3e-5)  # P and QE columns, t = 0..10
     tq, charge = O.read_table(str(tmp_path / "eccapfim_ex1" / "temporal" / "charge_conservation.txt"))
     assert tq == O.read_table(os.path.join(GOLDEN, "eccapfim_ex1", "charge_conservation.txt"))[0]
     assert charge.shape[0] == 11 and np.max(charge[:, 1:]) < 5e-12
+
+
+def test_device_momentum_diagnostic_matches_host_restatement_and_golden():
+    """MomentumConservation on the device (xb_momentum) against the numpy restatement on the downloaded
+    state and against the P / QE columns of the golden momentum_conservation.txt at t = 0..3."""
+    import xpic_b200 as X
+
+    o = O.Oracle((10, 10, 10))
+    sid = o.add_species(Np=100)
+    o.set_particles_maxwell(sid, 0.1, True)
+    s = X.Simulation((10, 10, 10), scheme=X.ECCAPFIM, track_ids=True)
+    s.add_species(Np=100)
+    pts, ids = o.get_particles(sid)
+    s.add_particles(0, pts, ids)
+    s.nonlinear_set(atol=1e-9, rtol=1e-30, particle_tol=1e-13)
+    _, gold = O.read_table(os.path.join(GOLDEN, "eccapfim_ex1", "momentum_conservation.txt"))
+    for t in range(0, 4):
+        if t > 0:
+            s.step()
+        P, QE = s.momentum(0)
+        p_now, _ = s.get_particles(0)
+        np.testing.assert_allclose(P, (1.0 / 100) * p_now[:, 3:].sum(axis=0), rtol=1e-11, atol=1e-15)
+        np.testing.assert_allclose(QE, momentum_qe(p_now, s.get_field("E"), (10, 10, 10), (0.5, 0.5, 0.5), -1.0 / 100), rtol=1e-10, atol=1e-15)
+        np.testing.assert_allclose(P, gold[t, 1:4], rtol=1e-3, atol=1e-5)
+        np.testing.assert_allclose(QE, gold[t, 4:7], rtol=2e-3, atol=1e-5)

@@ -14,6 +14,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
+from helpers import momentum_qe
 from oracle import oracle as O
 
 
@@ -121,32 +122,6 @@ def test_initial_momentum_matches_golden():
     assert [f"{v: .6e}" for v in P] == [f"{v: .6e}" for v in gold[0, 1:4]]
 
 
-def _spline2(s):
-    s = np.abs(s)
-    return np.where(s <= 0.5, 0.75 - s * s, np.where(s < 1.5, 0.5 * (1.5 - s) ** 2, 0.0))
-
-
-def _qe(pts, E, n, d, q_np):
-    """QE of MomentumConservation::calculate (momentum_conservation.cpp:84-117): sum over particles of
-    q / Np * E at the particle with the global 2nd-order Shape (electric(): No No Sh per component)."""
-    nx, ny, nz = n
-    Eg = E.reshape(nz, ny, nx, 3)
-    p = pts[:, :3] / np.array(d)
-    start = np.round(p - 1.5).astype(int)  # np.round is half-to-even; exact ties do not occur for these particles
-    out = np.zeros(3)
-    for k in range(4):
-        for j in range(4):
-            for i in range(4):
-                g = start + np.array([i, j, k])
-                no = [_spline2(p[:, a] - g[:, a]) for a in range(3)]
-                sh = [_spline2(p[:, a] - (g[:, a] + 0.5)) for a in range(3)]
-                idx = (g[:, 2] % nz, g[:, 1] % ny, g[:, 0] % nx)
-                out[0] += np.sum(Eg[idx + (0,)] * (no[2] * no[1] * sh[0]))
-                out[1] += np.sum(Eg[idx + (1,)] * (no[2] * sh[1] * no[0]))
-                out[2] += np.sum(Eg[idx + (2,)] * (sh[2] * no[1] * no[0]))
-    return q_np * out
-
-
 def test_momentum_columns_match_golden():
     """P and QE columns of the golden momentum_conservation.txt at t = 1..3: they see the particle
     velocities and E at the particle positions after each converged step."""
@@ -159,5 +134,5 @@ def test_momentum_columns_match_golden():
         pts, _ = o.get_particles()
         P = (1.0 / 100) * pts[:, 3:].sum(axis=0)
         np.testing.assert_allclose(P, gold[t, 1:4], rtol=1e-3, atol=1e-5)  # the net momentum is a sum of 1e5 velocities, the reference stopped at |F| ~ 1e-7
-        QE = _qe(pts, o.get_field("E"), (10, 10, 10), (0.5, 0.5, 0.5), -1.0 / 100)
+        QE = momentum_qe(pts, o.get_field("E"), (10, 10, 10), (0.5, 0.5, 0.5), -1.0 / 100)
         np.testing.assert_allclose(QE, gold[t, 4:7], rtol=2e-3, atol=1e-5)

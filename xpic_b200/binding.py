@@ -111,6 +111,7 @@ SYMBOLS = {
     "xb_eccapfim_function": (C.c_int, [C.c_void_p, _dp, _dp]),
     "xb_charge_density": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "xb_charge_conservation": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
+    "xb_momentum": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
 }
 
 
@@ -293,6 +294,12 @@ class Simulation:
         out = np.zeros(2 * (self.nsorts + 1))
         _check(self._L.xb_charge_conservation(self._h, {"currJe": 0, "J": 1}[current], _as_dp(out)))
         return out.reshape(-1, 2)
+
+    def momentum(self, sid=0):
+        """MomentumConservation::calculate: (P[3], QE[3]) of sort sid with the present E."""
+        out = np.zeros(6)
+        _check(self._L.xb_momentum(self._h, sid, _as_dp(out)))
+        return out[:3], out[3:]
 
     # -- stepping ------------------------------------------------------------------------------
     def step(self, scheme=None):

@@ -785,6 +785,14 @@ int xb_charge_density(xb_ctx* c, int32_t sid, double* rho)
   return 0;
 }
 
+int xb_momentum(xb_ctx* c, int32_t sid, double out[6])
+{
+  XB_API_BEGIN(c);
+  if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
+  if (!out) XB_FAIL("xb_momentum: null output");
+  return momentum(c, c->sorts[sid], out);
+}
+
 int xb_charge_conservation(xb_ctx* c, int32_t which_current, double* norms)
 {
   XB_API_BEGIN(c);

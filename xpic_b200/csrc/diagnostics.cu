@@ -88,6 +88,81 @@ __global__ void __launch_bounds__(RED_THREADS) k_continuity(Grid g, const double
   }
 }
 
+// MomentumConservation::calculate (src/diagnostics/momentum_conservation.cpp:71-126): per particle the node
+// weights of the global 2nd-order Shape (Shape::setup, utils/shape.cpp:34-45,81-107: window from
+// round(p - 1.5), 3 or 4 nodes per axis; all four are visited here, the extra one carries zero weight):
+//   P  += m / Np * v * sum_i ns(i),         ns = No_z No_y No_x
+//   QE += q / Np * sum_i E(g_i) . Es(i),    Es = Shape::electric (shape.h:56-63): No No Sh per component
+__global__ void __launch_bounds__(RED_THREADS) k_momentum(Grid g, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                                                         const double* __restrict__ z, const double* __restrict__ vx, const double* __restrict__ vy,
+                                                         const double* __restrict__ vz, const double* __restrict__ E, double* __restrict__ partial)
+{
+  double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double p[3] = {to_cells(x[i], g.dx, g.inv_dx, g.exact_inv & 1), to_cells(y[i], g.dy, g.inv_dy, g.exact_inv & 2),
+                         to_cells(z[i], g.dz, g.inv_dz, g.exact_inv & 4)};
+    int start[3];
+    double no[3][4], sh[3][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      start[a] = (int)round(p[a] - 1.5);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double gj = (double)(start[a] + j);
+        no[a][j] = spline2_diag(p[a] - gj);
+        sh[a][j] = spline2_diag(p[a] - (gj + 0.5));
+      }
+    }
+    double ns = 0.0, e[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int kz = 0; kz < 4; ++kz)
+#pragma unroll
+      for (int jy = 0; jy < 4; ++jy)
+#pragma unroll
+        for (int ix = 0; ix < 4; ++ix) {
+          const int64_t o = g.vidx(wrapi(start[0] + ix, g.nx), wrapi(start[1] + jy, g.ny), start[2] + kz - g.z0, 0);
+          ns += no[2][kz] * no[1][jy] * no[0][ix];
+          e[0] += __ldg(&E[o + 0]) * (no[2][kz] * no[1][jy] * sh[0][ix]);
+          e[1] += __ldg(&E[o + 1]) * (no[2][kz] * sh[1][jy] * no[0][ix]);
+          e[2] += __ldg(&E[o + 2]) * (sh[2][kz] * no[1][jy] * no[0][ix]);
+        }
+    acc[0] += vx[i] * ns;
+    acc[1] += vy[i] * ns;
+    acc[2] += vz[i] * ns;
+    acc[3] += e[0];
+    acc[4] += e[1];
+    acc[5] += e[2];
+  }
+  __shared__ double shm[RED_THREADS / 32][6];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double t = warp_sum(acc[k]);
+    if (lane == 0) shm[wid][k] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double t = 0.0;
+    for (int q = 0; q < RED_THREADS / 32; ++q) t += shm[q][threadIdx.x];
+    partial[(int64_t)blockIdx.x * RED_MAXV + threadIdx.x] = t;
+  }
+}
+
+// out = {Px, Py, Pz, QEx, QEy, QEz} of one sort with the present E, summed over all ranks
+int momentum(xb_ctx* c, Species& s, double* out)
+{
+  XB_CHECK(halo_fill(c, c->E, GZ));  // DMGlobalToLocal(E), momentum_conservation.cpp:75-76
+  double** p = s.p[s.cur];
+  XB_LAUNCH(c, k_momentum, RED_BLOCKS, RED_THREADS, 0, c->g, s.count, p[0], p[1], p[2], p[3], p[4], p[5], c->E, c->red_partial);
+  XB_CHECK(reduce_finish(c, 6, out));
+  const double Np = (double)s.Np;
+  for (int k = 0; k < 3; ++k) {
+    out[k] *= s.m / Np;      // :87
+    out[3 + k] *= s.q / Np;  // :88
+  }
+  return 0;
+}
+
 static int ensure_rho(xb_ctx* c, Species& s)
 {
   for (int b = 0; b < 2; ++b)

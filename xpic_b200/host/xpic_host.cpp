@@ -1,6 +1,7 @@
 // xpic_host.cpp -- see xpic_host.h.
 #include "xpic_host.h"
 
+#include <array>
 #include <cmath>
 #include <filesystem>
 #include <format>
@@ -297,6 +298,15 @@ int Simulation::initialize()
     for (size_t i = 0; i < particles_.size(); ++i) B200_CALL(xb_charge_density(ctx, (int32_t)i, nullptr));  // ChargeConservation::initialize
     if (diagnose_charge(start)) return 1;
   }
+  // MomentumConservation (interfaces/simulation.cpp:54-56): initialize() stores P at t = 0
+  momentum_ = std::make_unique<Table>(out_dir + "/temporal/momentum_conservation.txt");
+  P0_.assign(particles_.size(), {0.0, 0.0, 0.0});
+  for (size_t i = 0; i < particles_.size(); ++i) {
+    double o[6];
+    B200_CALL(xb_momentum(ctx, (int32_t)i, o));
+    P0_[i] = {o[0], o[1], o[2]};
+  }
+  if (diagnose_momentum(start)) return 1;
   if (diagnose_fields(start)) return 1;
   return diagnose_energy(start);
 }
@@ -349,6 +359,7 @@ int Simulation::calculate()
       std::cout << std::format("  KSPSolve() has finished: reason {}, iterations {}, residual norm {:.3e}", reason, its, rn) << "\n";
     }
     if (charge_ && diagnose_charge(t)) return 1;
+    if (diagnose_momentum(t)) return 1;
     if (diagnose_fields(t)) return 1;
     if (diagnose_energy(t)) return 1;
   }
@@ -372,10 +383,44 @@ int Simulation::finalize()
   if (energy_cons_) energy_cons_->flush();
   if (convergence_) convergence_->flush();
   if (charge_) charge_->flush();
+  if (momentum_) momentum_->flush();
   if (ctx) {
     xb_destroy(ctx);
     ctx = nullptr;
   }
+  return 0;
+}
+
+// MomentumConservation::add_columns (src/diagnostics/momentum_conservation.cpp:29-68), sums on the device
+int Simulation::diagnose_momentum(int t)
+{
+  auto num = [](double v) { return std::format("{: .6e}", v); };
+  auto len = [](const std::array<double, 3>& a) { return std::hypot(a[0], a[1], a[2]); };
+  momentum_->add(6, "Time", std::format("{:d}", t));
+  std::array<double, 3> sum = {0.0, 0.0, 0.0};
+  for (size_t i = 0; i < particles_.size(); ++i) {
+    double o[6];
+    B200_CALL(xb_momentum(ctx, (int32_t)i, o));
+    const std::string& name = particles_[i]->parameters.sort_name;
+    const std::array<double, 3> p1 = {o[0], o[1], o[2]}, qe = {o[3], o[4], o[5]}, p0 = P0_[i];
+    for (int c = 0; c < 3; ++c) momentum_->add(13, std::string("P") + "xyz"[c] + "_" + name, num(p1[c]));
+    for (int c = 0; c < 3; ++c) momentum_->add(13, std::string("QE") + "xyz"[c] + "_" + name, num(qe[c]));
+    std::array<double, 3> err, dp, sp;
+    for (int c = 0; c < 3; ++c) {
+      err[c] = (p1[c] - p0[c]) / geom.dt - qe[c];
+      sum[c] += err[c];
+      dp[c] = p1[c] - p0[c];
+      sp[c] = p1[c] + p0[c];
+    }
+    double freq = 0.0;
+    if (const double denom = len(sp); std::abs(denom) > 1e-10) freq = (len(dp) / denom) / (0.5 * geom.dt);  // PETSC_SMALL
+    momentum_->add(13, "N2dP_" + name, num(len(err)));
+    momentum_->add(13, "fP_" + name, num(freq));
+    P0_[i] = p1;
+  }
+  momentum_->add(13, "N2dP", num(len(sum)));
+  momentum_->row(t == 0);
+  if (t % geom.diagnose_period == 0) momentum_->flush();
   return 0;
 }
 

@@ -6,6 +6,7 @@
 // Errors: every method returns 0 on success (PetscErrorCode convention); configuration errors
 // throw std::runtime_error like the reference's builders (src/main.cpp:19-35).
 #pragma once
+#include <array>
 #include <cstdint>
 #include <fstream>
 #include <memory>
@@ -106,6 +107,7 @@ private:
   int diagnose_convergence(int t);  // eccapfim::ConvergenceHistory
   int diagnose_charge(int t);       // ChargeConservation (ecsimcorr, eccapfim)
   int diagnose_fields(int t);       // FieldView dumps
+  int diagnose_momentum(int t);     // MomentumConservation
   struct Preset {
     std::string particles, coordinate, momentum;
     bool tov = false;
@@ -113,7 +115,8 @@ private:
   std::vector<SortParameters> sorts_;
   std::vector<Preset> presets_;
   std::vector<std::string> field_views_;  // "Diagnostics": [{"diagnostic": "FieldView", "field": ...}]
-  std::unique_ptr<Table> energy_, energy_cons_, convergence_, charge_;
+  std::unique_ptr<Table> energy_, energy_cons_, convergence_, charge_, momentum_;
+  std::vector<std::array<double, 3>> P0_;  // MomentumConservation::P0
   bool charge_header_ = false;
   double E_ = 0, B_ = 0, E0_ = 0, B0_ = 0;
   std::vector<double> K_, K0_, stdK_;
