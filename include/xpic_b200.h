@@ -201,6 +201,12 @@ int xb_charge_density(xb_ctx* ctx, int32_t sid, double* rho);
  * 1 = J (eccapfim).  norms receives 2 * (number of sorts + 1) doubles, summed over all ranks. */
 int xb_charge_conservation(xb_ctx* ctx, int32_t which_current, double* norms);
 
+/* DistributionMoment::collect (src/diagnostics/distribution_moment.cpp:157-210) for sort sid: cell-centred
+ * moments with the 1st-order form factor, owned slab in natural [z][y][x] order, Nx*Ny*nzl doubles.
+ * moment: XB_MOMENT_DENSITY (get_density, :212-216); the velocity / flux moments are not covered. */
+enum { XB_MOMENT_DENSITY = 0 };
+int xb_distribution_moment(xb_ctx* ctx, int32_t sid, int32_t moment, double* out);
+
 /* MomentumConservation::calculate (src/diagnostics/momentum_conservation.cpp:71-126) for sort sid with the
  * present E: out = { Px, Py, Pz, QEx, QEy, QEz }, P = m / Np * sum v, QE = q / Np * sum E(x_p) with the global
  * 2nd-order form factor, summed over all ranks.  The caller keeps P of the previous call for the

@@ -83,3 +83,25 @@ def momentum_qe(pts, E, n, d, q_np):
                 out[1] += np.sum(Eg[idx + (1,)] * (no[2] * sh[1] * no[0]))
                 out[2] += np.sum(Eg[idx + (2,)] * (sh[2] * no[1] * no[0]))
     return q_np * out
+
+
+def cell_density(pts, n, d, n_np):
+    """DistributionMoment::collect with the "density" moment (src/diagnostics/distribution_moment.cpp:131-210):
+    cell-centred, 1st-order form factor, two nodes per axis from round(p - 1), weight n / Np."""
+    nx, ny, nz = n
+    rho = np.zeros((nz, ny, nx))
+    p = pts[:, :3] / np.array(d)
+    start = np.round(p - 1.0).astype(int)
+
+    def s1(s):
+        s = np.abs(s)
+        return np.where(s <= 1.0, 1.0 - s, 0.0)
+
+    for k in range(2):
+        wz = s1(p[:, 2] - (start[:, 2] + k + 0.5))
+        for j in range(2):
+            wy = s1(p[:, 1] - (start[:, 1] + j + 0.5))
+            for i in range(2):
+                wx = s1(p[:, 0] - (start[:, 0] + i + 0.5))
+                np.add.at(rho, ((start[:, 2] + k) % nz, (start[:, 1] + j) % ny, (start[:, 0] + i) % nx), n_np * wx * wy * wz)
+    return rho

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from helpers import by_id, momentum_qe, rel_err
+from helpers import by_id, cell_density, momentum_qe, rel_err
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -245,6 +245,11 @@ def test_host_program_writes_the_reference_tables(tmp_path):
             mine = np.fromfile(tmp_path / "eccapfim_ex1" / field / t, dtype=np.float32).astype(np.float64)
             gold_f = np.fromfile(os.path.join(GOLDEN, "eccapfim_ex1", f"{field}_0{t}.f32"), dtype=np.float32).astype(np.float64)
             assert mine.size == gold_f.size == 3000 and rel_err(mine, gold_f) < tol
+    # DistributionMoment density dumps (electrons/density/{00,05,10}, float32 [z][y][x])
+    for t in ("00", "05", "10"):
+        mine = np.fromfile(tmp_path / "eccapfim_ex1" / "electrons" / "density" / t, dtype=np.float32).astype(np.float64)
+        gold_d = np.fromfile(os.path.join(GOLDEN, "eccapfim_ex1", f"density_0{t}.f32"), dtype=np.float32).astype(np.float64)
+        assert mine.size == gold_d.size == 1000 and np.max(np.abs(mine - gold_d)) < 2e-4 * np.max(gold_d)
     tm, mom = O.read_table(str(tmp_path / "eccapfim_ex1" / "temporal" / "momentum_conservation.txt"))
     tg, gm = O.read_table(os.path.join(GOLDEN, "eccapfim_ex1", "momentum_conservation.txt"))
     assert tm == tg and mom.shape == gm.shape
@@ -277,3 +282,10 @@ def test_device_momentum_diagnostic_matches_host_restatement_and_golden():
         np.testing.assert_allclose(QE, momentum_qe(p_now, s.get_field("E"), (10, 10, 10), (0.5, 0.5, 0.5), -1.0 / 100), rtol=1e-10, atol=1e-15)
         np.testing.assert_allclose(P, gold[t, 1:4], rtol=1e-3, atol=1e-5)
         np.testing.assert_allclose(QE, gold[t, 4:7], rtol=2e-3, atol=1e-5)
+
+
+def test_device_density_moment_matches_host_restatement():
+    o, s = make_cap_pair(n=(9, 8, 7), Np=17)
+    rho = s.density(0).reshape(7, 8, 9)
+    ref = cell_density(s.get_particles(0)[0], (9, 8, 7), (0.5, 0.5, 0.5), 1.0 / 17)
+    assert np.max(np.abs(rho - ref)) < 1e-13 * np.max(ref)

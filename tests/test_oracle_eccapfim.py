@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from helpers import momentum_qe
+from helpers import cell_density, momentum_qe
 from oracle import oracle as O
 
 
@@ -136,3 +136,14 @@ def test_momentum_columns_match_golden():
         np.testing.assert_allclose(P, gold[t, 1:4], rtol=1e-3, atol=1e-5)  # the net momentum is a sum of 1e5 velocities, the reference stopped at |F| ~ 1e-7
         QE = momentum_qe(pts, o.get_field("E"), (10, 10, 10), (0.5, 0.5, 0.5), -1.0 / 100)
         np.testing.assert_allclose(QE, gold[t, 4:7], rtol=2e-3, atol=1e-5)
+
+
+def test_initial_density_dump_matches_golden():
+    """electrons/density/00 of the golden run: the cell-centred density of the mt19937 initial positions
+    (DistributionMoment, float32 dump) -- pins the coordinate stream the way wK pins the momenta."""
+    o = _oracle()
+    pts, _ = o.get_particles()
+    rho = cell_density(pts, (10, 10, 10), (0.5, 0.5, 0.5), 1.0 / 100)
+    gold = np.fromfile(os.path.join(GOLDEN, "eccapfim_ex1", "density_000.f32"), dtype=np.float32).reshape(10, 10, 10)
+    assert np.array_equal(rho.astype(np.float32), gold) or np.max(np.abs(rho - gold)) < 2e-7 * np.max(gold)
+    assert abs(rho.sum() - 1000.0) < 1e-9  # n = 1 in every one of the 1000 cells on average

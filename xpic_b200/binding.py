@@ -112,6 +112,7 @@ SYMBOLS = {
     "xb_charge_density": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "xb_charge_conservation": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "xb_momentum": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
+    "xb_distribution_moment": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
 }
 
 
@@ -294,6 +295,12 @@ class Simulation:
         out = np.zeros(2 * (self.nsorts + 1))
         _check(self._L.xb_charge_conservation(self._h, {"currJe": 0, "J": 1}[current], _as_dp(out)))
         return out.reshape(-1, 2)
+
+    def density(self, sid=0):
+        """DistributionMoment "density": cell-centred number density of sort sid on the owned cells."""
+        out = np.empty(self.ncl, dtype=np.float64)
+        _check(self._L.xb_distribution_moment(self._h, sid, 0, _as_dp(out)))
+        return out
 
     def momentum(self, sid=0):
         """MomentumConservation::calculate: (P[3], QE[3]) of sort sid with the present E."""

@@ -785,6 +785,19 @@ int xb_charge_density(xb_ctx* c, int32_t sid, double* rho)
   return 0;
 }
 
+int xb_distribution_moment(xb_ctx* c, int32_t sid, int32_t moment, double* out)
+{
+  XB_API_BEGIN(c);
+  if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
+  if (!out) XB_FAIL("xb_distribution_moment: null output");
+  XB_CHECK(distribution_moment(c, c->sorts[sid], moment));
+  std::vector<double> tmp((size_t)c->g.nown);
+  XB_CHECK(download_owned(c, c->tmp2, tmp.data()));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  for (int64_t i = 0; i < c->g.ncl; ++i) out[i] = tmp[3 * i];
+  return 0;
+}
+
 int xb_momentum(xb_ctx* c, int32_t sid, double out[6])
 {
   XB_API_BEGIN(c);

@@ -258,6 +258,7 @@ int cap_read_counters(xb_ctx* c);                        // averages of the last
 int charge_density(xb_ctx* c, Species& s);                               // ParticlesChargeDensity::collect
 int charge_conservation(xb_ctx* c, int which_current, double* norms);   // ChargeConservation::add_columns
 int momentum(xb_ctx* c, Species& s, double* out6);                      // MomentumConservation::calculate
+int distribution_moment(xb_ctx* c, Species& s, int moment);             // DistributionMoment::collect -> c->tmp2, component 0
 
 // ---- launch bookkeeping ----------------------------------------------------------------------
 #define XB_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \

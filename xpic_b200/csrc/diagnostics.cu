@@ -163,6 +163,47 @@ int momentum(xb_ctx* c, Species& s, double* out)
   return 0;
 }
 
+// DistributionMoment::collect with the "density" moment (src/diagnostics/distribution_moment.cpp:125-210):
+// cell-centred quantity, 1st-order form factor on the two cells per axis from round(p - 1), weight n / Np
+__global__ void __launch_bounds__(256) k_cell_density(Grid g, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                                                     const double* __restrict__ z, double n_Np, double* __restrict__ rho)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double p[3] = {to_cells(x[i], g.dx, g.inv_dx, g.exact_inv & 1), to_cells(y[i], g.dy, g.inv_dy, g.exact_inv & 2),
+                       to_cells(z[i], g.dz, g.inv_dz, g.exact_inv & 4)};
+  int start[3];
+  double w[3][2];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    start[a] = (int)round(p[a] - 1.0);  // Shape::make_start(p_r, shr = 1)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double s = fabs(p[a] - ((double)(start[a] + j) + 0.5));
+      w[a][j] = s <= 1.0 ? 1.0 - s : 0.0;  // spline_of_1st_order
+    }
+  }
+#pragma unroll
+  for (int kz = 0; kz < 2; ++kz)
+#pragma unroll
+    for (int jy = 0; jy < 2; ++jy)
+#pragma unroll
+      for (int ix = 0; ix < 2; ++ix)
+        atomicAdd(&rho[g.vidx(wrapi(start[0] + ix, g.nx), wrapi(start[1] + jy, g.ny), start[2] + kz - g.z0, 0)], (w[0][ix] * w[1][jy] * w[2][kz]) * n_Np);
+}
+
+// moment 0 = density into component 0 of c->tmp2 (owned part valid after the halo reduction)
+int distribution_moment(xb_ctx* c, Species& s, int moment)
+{
+  if (moment != 0) XB_FAIL("distribution_moment: only the density moment is covered");
+  XB_CHECK(vec_zero(c, c->tmp2));
+  if (s.count > 0) {
+    double** p = s.p[s.cur];
+    XB_LAUNCH(c, k_cell_density, (int)((s.count + 255) / 256), 256, 0, c->g, s.count, p[0], p[1], p[2], s.n / (double)s.Np, c->tmp2);
+  }
+  return halo_reduce(c, c->tmp2, GZ, GZ);
+}
+
 static int ensure_rho(xb_ctx* c, Species& s)
 {
   for (int b = 0; b < 2; ++b)

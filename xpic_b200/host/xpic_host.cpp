@@ -194,6 +194,12 @@ int Simulation::configure(const std::string& config_path)
         if (info.contains("region")) throw std::runtime_error("FieldView: only the whole-box region is covered by this build");
         field_views_.push_back(info.at("field").get<std::string>());
       }
+      else if (name == "DistributionMoment") {  // diagnostics/builders/distribution_moment_builder.cpp:27-75
+        if (info.contains("region")) throw std::runtime_error("DistributionMoment: only the whole-box region is covered by this build");
+        if (info.at("moment").get<std::string>() != "density")
+          throw std::runtime_error("DistributionMoment: only the density moment is covered by this build");
+        density_views_.push_back(info.at("particles").get<std::string>());
+      }
       else
         std::cout << "  diagnostic " << name << " is not covered by this build, skipped\n";
     }
@@ -316,10 +322,24 @@ int Simulation::initialize()
 // Diagnostic::format_time (interfaces/diagnostic.cpp:21-25)
 int Simulation::diagnose_fields(int t)
 {
-  if (field_views_.empty() || t % geom.diagnose_period != 0) return 0;
+  if (t % geom.diagnose_period != 0) return 0;
   const int width = (int)std::to_string(geom.geom_nt).size();
   std::vector<double> f;
   std::vector<float> out;
+  for (const std::string& sort : density_views_) {  // DistributionMoment::diagnose (distribution_moment.cpp:112-122)
+    int32_t sid = -1;
+    for (size_t i = 0; i < particles_.size(); ++i)
+      if (particles_[i]->parameters.sort_name == sort) sid = (int32_t)i;
+    if (sid < 0) throw std::runtime_error("No particles with name " + sort);
+    f.resize((size_t)geom.geom_nx * geom.geom_ny * geom.geom_nz);
+    B200_CALL(xb_distribution_moment(ctx, sid, XB_MOMENT_DENSITY, f.data()));
+    out.assign(f.begin(), f.end());
+    const std::string dir = out_dir + "/" + sort + "/density";
+    std::filesystem::create_directories(dir);
+    std::ofstream file(dir + "/" + std::format("{:0{}d}", t, width), std::ios::binary);
+    file.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)(out.size() * sizeof(float)));
+    if (!file) throw std::runtime_error("DistributionMoment: cannot write into " + dir);
+  }
   for (const std::string& field : field_views_) {
     if (get_named_vector(field, f)) return 1;
     out.assign(f.begin(), f.end());

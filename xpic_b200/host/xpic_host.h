@@ -114,6 +114,7 @@ private:
   };
   std::vector<SortParameters> sorts_;
   std::vector<Preset> presets_;
+  std::vector<std::string> density_views_;  // "Diagnostics": [{"diagnostic": "DistributionMoment", "particles": ..., "moment": "density"}]
   std::vector<std::string> field_views_;  // "Diagnostics": [{"diagnostic": "FieldView", "field": ...}]
   std::unique_ptr<Table> energy_, energy_cons_, convergence_, charge_, momentum_;
   std::vector<std::array<double, 3>> P0_;  // MomentumConservation::P0
