@@ -354,6 +354,8 @@ def test_golden_field_dumps_and_all_rows_100_steps(X, name, scheme):
     _, s = make_pair(n=(10, 10, 10), Np=100, scheme=scheme, curl_sign=-1, rtol=1e-10)
     _, gold = O.read_table(os.path.join(GOLDEN, name, "energy.txt"))
     rows = [(0.0, 0.0, s.scalar("kinetic"))]
+    g0 = np.fromfile(os.path.join(GOLDEN, name, "density_000.f32"), dtype=np.float32).astype(np.float64)
+    assert np.max(np.abs(s.density(0) - g0)) < 2e-7 * np.max(g0)
     for t in range(1, 101):
         s.step()
         wE, wB = s.field_energies()
@@ -362,6 +364,9 @@ def test_golden_field_dumps_and_all_rows_100_steps(X, name, scheme):
             for f in ("E", "B"):
                 g = np.fromfile(os.path.join(GOLDEN, name, f"{f}_{t:03d}.f32"), dtype=np.float32).astype(np.float64)
                 assert rel_err(s.get_field(f), g) < 2e-5, (f, t)
+            # DistributionMoment density dump (electrons/density/050, 100): the particle positions of the run
+            g = np.fromfile(os.path.join(GOLDEN, name, f"density_{t:03d}.f32"), dtype=np.float32).astype(np.float64)
+            assert np.max(np.abs(s.density(0) - g)) < 1e-4 * np.max(g), t
     # the reference solved to 1e-7 and chaos amplifies the difference slowly: 7 digits early, 5 at the end
     np.testing.assert_allclose(np.array(rows)[:31], gold[:31, 1:4], rtol=3e-6, atol=1e-10)
     np.testing.assert_allclose(np.array(rows), gold[:, 1:4], rtol=2e-4, atol=1e-9)
