@@ -442,3 +442,47 @@ def test_device_charge_conservation_diagnostic(X, scheme, current):
         e.charge_density(0)
         e.step()
         assert e.charge_conservation("currJe")[0, 0] > 1e-3
+
+
+def test_host_backup_and_restart_round_trip(X, tmp_path):
+    """SimulationBackup in the host mirror: PETSc binary Vec images of E, B, B0 (big-endian, class id 1211214),
+    raw big-endian particles; a run restarted from the backup of step 5 continues the tables and ends in the
+    state of the uninterrupted run (src/diagnostics/simulation_backup.cpp:27-183)."""
+    import json
+    import shutil
+    import struct
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "xpic_b200", "_build", "xpic_b200.out")
+    if not os.path.exists(exe):
+        pytest.skip("host program not built")
+    cfg = json.load(open(os.path.join(ROOT, "configs", "ecsimcorr_ex1.json")))
+    cfg["SimulationBackup"] = {"diagnose_period": 7.5}
+    a, b = tmp_path / "a", tmp_path / "b"
+    cfg["OutputDirectory"] = str(a)
+    (tmp_path / "a.json").write_text(json.dumps(cfg))
+    subprocess.run([exe, str(tmp_path / "a.json")], check=True, capture_output=True, timeout=300)
+    assert sorted(os.listdir(a / "simulation_backup")) == ["10", "5"]  # only the last two periods are kept
+    raw = (a / "simulation_backup" / "5" / "E").read_bytes()
+    assert len(raw) == 8 + 3000 * 8 and struct.unpack(">ii", raw[:8]) == (1211214, 3000)
+    assert struct.unpack(">i", (a / "simulation_backup" / "5" / "electrons.numparts").read_bytes()) == (100000,)
+    assert (a / "simulation_backup" / "5" / "electrons").stat().st_size == 100000 * 48
+    # restart from step 5 in a fresh output directory that only holds that backup
+    (b / "simulation_backup").mkdir(parents=True)
+    shutil.copytree(a / "simulation_backup" / "5", b / "simulation_backup" / "5")
+    cfg["OutputDirectory"] = str(b)
+    cfg["SimulationBackup"] = {"diagnose_period": 7.5, "load_from": 5}
+    (tmp_path / "b.json").write_text(json.dumps(cfg))
+    res = subprocess.run([exe, str(tmp_path / "b.json")], check=True, capture_output=True, timeout=300, text=True)
+    assert "successfully loaded" in res.stdout
+    for table in ("energy.txt", "energy_conservation.txt", "charge_conservation.txt", "momentum_conservation.txt"):
+        ta, ra = O.read_table(str(a / "temporal" / table))
+        tb, rb = O.read_table(str(b / "temporal" / table))
+        assert ta == tb and ra.shape == rb.shape, table
+        np.testing.assert_allclose(rb, ra, rtol=1e-6, atol=1e-11, err_msg=table)
+    for f in ("E", "B"):
+        fa = np.fromfile(a / f / "10", dtype=np.float32)
+        fb = np.fromfile(b / f / "10", dtype=np.float32)
+        assert rel_err(fb.astype(np.float64), fa.astype(np.float64)) < 1e-6

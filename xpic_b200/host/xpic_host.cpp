@@ -43,10 +43,10 @@ static double parse_value(const json& value, const Geometry& g)
 static int round_step(double s, double ds) { return static_cast<int>(std::round(s / ds)); }
 
 // ---- Table -------------------------------------------------------------------------------------
-Table::Table(const std::string& filename)
+Table::Table(const std::string& filename, bool append)
 {
   std::filesystem::create_directories(std::filesystem::path(filename).parent_path());
-  file_.open(filename);
+  file_.open(filename, append ? std::ios::out | std::ios::app : std::ios::out);
 }
 
 void Table::add(int w, std::string title, const std::string& formatted)
@@ -187,6 +187,12 @@ int Simulation::configure(const std::string& config_path)
       }
       sorts_.push_back(p);
     }
+  if (cfg.contains("SimulationBackup") && !cfg.at("SimulationBackup").empty()) {
+    // builders/simulation_backup_builder.cpp:38-53 (diagnostic), :63-76 + utils/configuration.cpp:76-86 (restart)
+    const json& info = cfg.at("SimulationBackup");
+    if (info.contains("diagnose_period")) backup_period_ = std::max(1, round_step(parse_value(info.at("diagnose_period"), geom), geom.dt));
+    if (info.contains("load_from") && info.at("load_from").is_number_integer()) load_from_ = info.at("load_from").get<int>();
+  }
   if (cfg.contains("Diagnostics"))  // diagnostics/builders/diagnostic_builder.cpp, field_view_builder.cpp:13-52
     for (const json& info : cfg.at("Diagnostics")) {
       const std::string name = info.at("diagnostic").get<std::string>();
@@ -265,8 +271,14 @@ int Simulation::initialize()
 
   // presets: SetParticles::execute (src/commands/set_particles.cpp:19-43) with the generators of
   // src/utils/particles_load.cpp:11-18,52-76 and the count of particles_builder.cpp:17,26
+  const bool restart = load_from_ >= 0;  // "Other preset commands would be dropped" (simulation_backup_builder.cpp:70)
+  if (restart) {
+    if (load_backup(load_from_)) return 1;
+    start = load_from_;
+  }
   auto r01 = [&]() { return uni_(gen_); };
   for (const auto& pr : presets_) {
+    if (restart) break;
     Particles& sort = get_named_particles(pr.particles);
     const SortParameters& sp = sort.parameters;
     const double frac = sp.Np / (geom.dx * geom.dy * geom.dz);
@@ -291,29 +303,36 @@ int Simulation::initialize()
     if (sort.flush()) return 1;
   }
 
-  energy_ = std::make_unique<Table>(out_dir + "/temporal/energy.txt");
-  energy_cons_ = std::make_unique<Table>(out_dir + "/temporal/energy_conservation.txt");
+  // after a restart the tables of the backup continue (rows up to `start` are already there)
+  energy_ = std::make_unique<Table>(out_dir + "/temporal/energy.txt", restart);
+  energy_cons_ = std::make_unique<Table>(out_dir + "/temporal/energy_conservation.txt", restart);
   K_.assign(particles_.size(), 0.0);
   K0_ = stdK_ = K_;
   if (scheme == XB_ECCAPFIM) {  // eccapfim/simulation.cpp:28
-    convergence_ = std::make_unique<Table>(out_dir + "/temporal/convergence_history.txt");
-    if (diagnose_convergence(start)) return 1;
+    convergence_ = std::make_unique<Table>(out_dir + "/temporal/convergence_history.txt", restart);
+    if (!restart && diagnose_convergence(start)) return 1;
   }
   if (scheme != XB_ECSIM) {  // ChargeConservation: interfaces/simulation.cpp:32-38 (J), ecsimcorr/simulation.cpp:103-110 (currJe)
-    charge_ = std::make_unique<Table>(out_dir + "/temporal/charge_conservation.txt");
+    charge_ = std::make_unique<Table>(out_dir + "/temporal/charge_conservation.txt", restart);
+    charge_header_ = restart;
     for (size_t i = 0; i < particles_.size(); ++i) B200_CALL(xb_charge_density(ctx, (int32_t)i, nullptr));  // ChargeConservation::initialize
-    if (diagnose_charge(start)) return 1;
+    if (!restart && diagnose_charge(start)) return 1;
   }
   // MomentumConservation (interfaces/simulation.cpp:54-56): initialize() stores P at t = 0
-  momentum_ = std::make_unique<Table>(out_dir + "/temporal/momentum_conservation.txt");
+  momentum_ = std::make_unique<Table>(out_dir + "/temporal/momentum_conservation.txt", restart);
   P0_.assign(particles_.size(), {0.0, 0.0, 0.0});
   for (size_t i = 0; i < particles_.size(); ++i) {
     double o[6];
     B200_CALL(xb_momentum(ctx, (int32_t)i, o));
     P0_[i] = {o[0], o[1], o[2]};
   }
+  if (restart) {
+    // prime the "previous step" values of the table diagnostics without writing the row of t = start again
+    return prime_energy();
+  }
   if (diagnose_momentum(start)) return 1;
   if (diagnose_fields(start)) return 1;
+  if (backup_period_ > 0 && save_backup(start)) return 1;
   return diagnose_energy(start);
 }
 
@@ -382,6 +401,7 @@ int Simulation::calculate()
     if (diagnose_momentum(t)) return 1;
     if (diagnose_fields(t)) return 1;
     if (diagnose_energy(t)) return 1;
+    if (backup_period_ > 0 && t % backup_period_ == 0 && save_backup(t)) return 1;
   }
   std::cout << "Summary of Stages:\n";  // utils/sync_clock.cpp:85-91
   const char* names_ec[XB_STAGE_COUNT] = {"Clear sources", "First push", "Advance field", "Second push", "Correct fields", "Final update"};
@@ -408,6 +428,118 @@ int Simulation::finalize()
     xb_destroy(ctx);
     ctx = nullptr;
   }
+  return 0;
+}
+
+// ---- SimulationBackup (src/diagnostics/simulation_backup.cpp:27-183) ---------------------------------------
+// Fields: PETSc's binary Vec image (VecView through a binary viewer): int32 VEC_FILE_CLASSID = 1211214,
+// int32 length, then the entries as float64 -- all big-endian, natural [z][y][x][c] order for a DMDA vector --
+// plus the `.info` side file PETSc writes for a blocked vector.  Particles: `<sort>.numparts` = one int32 and
+// `<sort>` = 6 float64 per particle in storage order, header-less (PetscViewerBinarySetSkipHeader), big-endian.
+// PETSc is not available here and the reference ships no backup file: the layout follows PETSc's documented
+// binary format and is checked by a save / restart round trip only (tests/test_gpu_parity.py).
+namespace {
+
+template <class T>
+T byteswap(T v)
+{
+  unsigned char* p = reinterpret_cast<unsigned char*>(&v);
+  for (size_t i = 0; i < sizeof(T) / 2; ++i) std::swap(p[i], p[sizeof(T) - 1 - i]);
+  return v;
+}
+
+void write_be_doubles(std::ofstream& f, const double* v, size_t n)
+{
+  std::vector<double> be(v, v + n);
+  for (double& x : be) x = byteswap(x);
+  f.write(reinterpret_cast<const char*>(be.data()), (std::streamsize)(n * sizeof(double)));
+}
+
+void read_be_doubles(std::ifstream& f, double* v, size_t n)
+{
+  f.read(reinterpret_cast<char*>(v), (std::streamsize)(n * sizeof(double)));
+  for (size_t i = 0; i < n; ++i) v[i] = byteswap(v[i]);
+}
+
+constexpr int32_t VEC_FILE_CLASSID = 1211214;
+
+}  // namespace
+
+int Simulation::save_backup(int t)
+{
+  const std::string dir = std::format("{}/simulation_backup/{}", out_dir, t);
+  std::filesystem::create_directories(dir);
+  std::vector<double> f;
+  for (const char* name : {"E", "B", "B0"}) {  // simulation_backup_builder.cpp:17-21
+    if (get_named_vector(name, f)) return 1;
+    std::ofstream file(dir + "/" + name, std::ios::binary);
+    const int32_t header[2] = {byteswap(VEC_FILE_CLASSID), byteswap((int32_t)f.size())};
+    file.write(reinterpret_cast<const char*>(header), sizeof(header));
+    write_be_doubles(file, f.data(), f.size());
+    if (!file) throw std::runtime_error("SimulationBackup: cannot write " + dir + "/" + name);
+    std::ofstream(dir + "/" + name + ".info") << "-vecload_block_size 3\n";
+  }
+  std::vector<Point> pts;
+  for (auto& sort : particles_) {
+    if (sort->download(pts)) return 1;
+    const std::string base = dir + "/" + sort->parameters.sort_name;
+    const int32_t n = byteswap((int32_t)pts.size());
+    std::ofstream(base + ".numparts", std::ios::binary).write(reinterpret_cast<const char*>(&n), sizeof(n));
+    std::ofstream file(base, std::ios::binary);
+    if (!pts.empty()) write_be_doubles(file, &pts[0].r[0], 6 * pts.size());
+    if (!file) throw std::runtime_error("SimulationBackup: cannot write " + base);
+  }
+  // save_temporal_diagnostics (:98-106): the tables as they are now
+  for (Table* tb : {energy_.get(), energy_cons_.get(), convergence_.get(), charge_.get(), momentum_.get()})
+    if (tb) tb->flush();
+  if (std::filesystem::exists(out_dir + "/temporal"))
+    std::filesystem::copy(out_dir + "/temporal", dir + "/temporal",
+                          std::filesystem::copy_options::overwrite_existing | std::filesystem::copy_options::recursive);
+  // only the last two periods are kept (num_periods_being_kept, simulation_backup.h:46)
+  std::filesystem::remove_all(std::format("{}/simulation_backup/{}", out_dir, t - 2 * backup_period_));
+  return 0;
+}
+
+int Simulation::load_backup(int t)
+{
+  const std::string dir = std::format("{}/simulation_backup/{}", out_dir, t);
+  if (!std::filesystem::exists(dir)) throw std::runtime_error("Cannot load the timestep, no backup directory " + dir);
+  const size_t n3 = (size_t)3 * geom.geom_nx * geom.geom_ny * geom.geom_nz;
+  std::vector<double> f(n3);
+  const std::pair<const char*, int> fields[] = {{"E", XB_E}, {"B", XB_B}, {"B0", XB_B0}};
+  for (auto& [name, id] : fields) {
+    std::ifstream file(dir + "/" + name, std::ios::binary);
+    int32_t header[2] = {0, 0};
+    file.read(reinterpret_cast<char*>(header), sizeof(header));
+    if (!file || byteswap(header[0]) != VEC_FILE_CLASSID || (size_t)byteswap(header[1]) != n3)
+      throw std::runtime_error(std::string("SimulationBackup: ") + name + " is not a PETSc binary Vec of this geometry");
+    read_be_doubles(file, f.data(), n3);
+    if (!file) throw std::runtime_error(std::string("SimulationBackup: short read of ") + name);
+    B200_CALL(xb_field_upload(ctx, id, 0, f.data()));
+  }
+  for (auto& sort : particles_) {
+    const std::string base = dir + "/" + sort->parameters.sort_name;
+    int32_t n = 0;
+    std::ifstream(base + ".numparts", std::ios::binary).read(reinterpret_cast<char*>(&n), sizeof(n));
+    n = byteswap(n);
+    std::ifstream file(base, std::ios::binary);
+    std::vector<double> raw((size_t)6 * (size_t)std::max(n, 0));
+    read_be_doubles(file, raw.data(), raw.size());
+    if (!file) throw std::runtime_error("SimulationBackup: short read of " + base);
+    for (int32_t i = 0; i < n; ++i) {
+      Point pt;
+      for (int c = 0; c < 3; ++c) {
+        pt.r[c] = raw[6 * (size_t)i + c];
+        pt.p[c] = raw[6 * (size_t)i + 3 + c];
+      }
+      sort->add_particle(pt);
+    }
+    if (sort->flush()) return 1;
+  }
+  if (std::filesystem::exists(dir + "/temporal"))  // load_temporal_diagnostics (:162-169)
+    std::filesystem::copy(dir + "/temporal", out_dir + "/temporal",
+                          std::filesystem::copy_options::overwrite_existing | std::filesystem::copy_options::recursive);
+  std::cout << std::format("  Simulation is successfully loaded from {:.1f} [1/w_pe], {} [dt]", t * geom.dt, t) << "\n";
   return 0;
 }
 
@@ -487,6 +619,15 @@ int Simulation::diagnose_convergence(int t)
   return 0;
 }
 
+// after a restart: the energies of t = start become the "previous" values, nothing is written
+int Simulation::prime_energy()
+{
+  energy_silent_ = true;
+  const int rc = diagnose_energy(start);
+  energy_silent_ = false;
+  return rc;
+}
+
 // Energy::diagnose (src/diagnostics/energy.cpp:20-180) + ecsimcorr::Energy (ecsimcorr/simulation.cpp:169-197)
 int Simulation::diagnose_energy(int t)
 {
@@ -522,6 +663,7 @@ int Simulation::diagnose_energy(int t)
   B0_ = B_;
   K0_ = K_;
   if (field("E", E_, stdE_) || field("B", B_, stdB_) || kinetic()) return 1;
+  if (energy_silent_) return 0;
 
   auto num = [](double v) { return std::format("{: .6e}", v); };
   energy_->add(6, "Time", std::format("{:d}", t));

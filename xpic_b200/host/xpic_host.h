@@ -64,7 +64,7 @@ private:
 /// table_diagnostic.h:17-37 / .cpp:43-59: fixed-width text tables
 class Table {
 public:
-  explicit Table(const std::string& filename);
+  explicit Table(const std::string& filename, bool append = false);
   void add(int w, std::string title, const std::string& formatted);
   void row(bool with_titles);
   void flush() { file_.flush(); }
@@ -108,6 +108,9 @@ private:
   int diagnose_charge(int t);       // ChargeConservation (ecsimcorr, eccapfim)
   int diagnose_fields(int t);       // FieldView dumps
   int diagnose_momentum(int t);     // MomentumConservation
+  int prime_energy();
+  int save_backup(int t);           // SimulationBackup::save
+  int load_backup(int t);           // SimulationBackup::load
   struct Preset {
     std::string particles, coordinate, momentum;
     bool tov = false;
@@ -119,6 +122,9 @@ private:
   std::unique_ptr<Table> energy_, energy_cons_, convergence_, charge_, momentum_;
   std::vector<std::array<double, 3>> P0_;  // MomentumConservation::P0
   bool charge_header_ = false;
+  bool energy_silent_ = false;
+  int backup_period_ = 0;  // "SimulationBackup": {"diagnose_period": ...} in steps, 0 = none
+  int load_from_ = -1;     // "SimulationBackup": {"load_from": step}
   double E_ = 0, B_ = 0, E0_ = 0, B0_ = 0;
   std::vector<double> K_, K0_, stdK_;
   double stdE_ = 0, stdB_ = 0;
