@@ -72,7 +72,8 @@ enum { XB_OP_L = 1, XB_OP_M = 2, XB_OP_A = 3 };
 const char* xb_last_error(void);
 int xb_version(void);
 
-/* Number of fixed-offset coefficients per cell of the stencil-layout operator (369). */
+/* Number of fixed-offset coefficients per cell of the stencil-layout operator (369): the non-zeros of matL per
+ * cell that Simulation::fill_matrix_indices generates (src/impls/ecsim/simulation.cpp:370-469), without indices. */
 int xb_operator_ncoef(void);
 /* Describe coefficient k: row component c1, column component c2 and column offset (dx,dy,dz). */
 int xb_operator_coef_info(int k, int* c1, int* c2, int* dx, int* dy, int* dz);
@@ -118,7 +119,8 @@ int xb_solver_info(xb_ctx* ctx, int32_t which, int32_t* iterations, double* rnor
 /* Simulation::timestep_implementation (ecsim/simulation.cpp:145, ecsimcorr/simulation.cpp:21).
  * Returns non-zero when a solve does not converge (KSPSetErrorIfNotConverged, :562). */
 int xb_step(xb_ctx* ctx, int32_t scheme);
-/* One stage of the step, for per-stage timing / parity. */
+/* One stage of the step, for per-stage timing / parity: the stages timestep_implementation logs
+ * (src/impls/ecsim/simulation.cpp:145-155, PetscLogStage names :495-508). */
 int xb_stage(xb_ctx* ctx, int32_t scheme, int32_t stage);
 /* The same step behind the reference-facing boundary with HOST buffers: uploads E, B, B0 (what
  * StepPresets commands may have edited), steps, downloads E, B and the kinetic energy of every
@@ -139,7 +141,7 @@ int xb_particle_moments(xb_ctx* ctx, int32_t sid, double out[5]);
 /* Seconds / launches accumulated per stage since the last reset (SyncClock, utils/sync_clock.cpp:75-93). */
 int xb_timing(xb_ctx* ctx, int32_t stage, double* seconds, int64_t* calls);
 int xb_timing_reset(xb_ctx* ctx);
-/* Number of this library's kernel launches since creation. */
+/* Number of this library's kernel launches since creation (measurement hook; PETSc's -log_view counts events instead). */
 int xb_launch_count(xb_ctx* ctx, int64_t* launches);
 /* Per-launch CUDA-event timing of the operator kernel (the MatMult event of PETSc's -log_view):
  * enable != 0 starts collecting; the query returns the launches seen and their summed ms. */
@@ -149,9 +151,11 @@ int xb_spmv_profile_read(xb_ctx* ctx, int64_t* launches, double* total_ms);
 /* --- hooks for the operator sweep (BASELINE config 4) and per-kernel parity tests ----------- */
 /* y = Op x with host vectors (owned slab, natural order).  MatMult, e.g. ecsimcorr/simulation.cpp:78 */
 int xb_spmv(xb_ctx* ctx, int32_t op, const double* x, double* y);
-/* Times `reps` device-resident SpMVs on pseudo-random x; returns average ms per SpMV. */
+/* Times `reps` device-resident SpMVs on pseudo-random x; returns average ms per SpMV (the MatMult event of
+ * PETSc's -log_view, BASELINE config 4). */
 int xb_spmv_bench(xb_ctx* ctx, int32_t op, int32_t reps, double* ms_per_spmv);
-/* Stencil-layout coefficients of L: coef[k*ncells + cell], k < xb_operator_ncoef(), owned cells. */
+/* Stencil-layout coefficients of L: coef[k*ncells + cell], k < xb_operator_ncoef(), owned cells -- the values
+ * MatSetValuesCOO sums into matL (src/impls/ecsim/simulation.cpp:359,366). */
 int xb_operator_download(xb_ctx* ctx, double* coef);
 int xb_operator_upload(xb_ctx* ctx, const double* coef);
 /* Kernel variant switches for cross-checks: what = 0 selects the cell-block kernel of the moment
@@ -219,7 +223,8 @@ int xb_deposit(xb_ctx* ctx);
 int xb_solve(xb_ctx* ctx, int32_t which, int32_t op, const double* b, double* x);
 /* out = curl(f): positive != 0 -> Rotor::create_positive, else create_negative (utils/operators.cpp:175-213). */
 int xb_curl(xb_ctx* ctx, int32_t positive, const double* f, double* out);
-/* Time one kernel family in isolation on the resident state: what = 0 first_push+sort, 1 deposit,
+/* Time one kernel family in isolation on the resident state (the per-stage SyncClock of the reference,
+ * src/utils/sync_clock.cpp:75-93, at kernel-family granularity): what = 0 first_push+sort, 1 deposit,
  * 2 second_push, 3 solve(predict).  Returns average ms. */
 int xb_kernel_bench(xb_ctx* ctx, int32_t what, int32_t reps, double* ms);
 
