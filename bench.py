@@ -123,6 +123,31 @@ def cpu_baseline_sample(steps=4, warm=1, n=(32, 32, 32), ppc=64, scheme="ecsim")
     return N * steps / dt, N, dt / steps, its, cores
 
 
+def cpu_baseline_subprocess(scheme, steps=4, warm=1):
+    """The CPU arm in its own process (keeps the oracle's shared object out of the GPU arm's address space)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--scheme", scheme, "--steps", str(steps), "--warmup", str(warm)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0"))
+        for ln in reversed(out.stdout.splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"unavailable": "no JSON line from the CPU arm: " + out.stderr[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+
+
+def measure_fp64_peak():
+    """tools/fp64_peak.cu (built into xpic_b200/_build/fp64_peak): DFMA / DMMA issue rates of this GPU, CUDA events."""
+    exe = os.path.join(ROOT, "xpic_b200", "_build", "fp64_peak")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -153,6 +178,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scheme", default="ecsim", choices=["ecsim", "ecsimcorr", "eccapfim"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short ECSIMCorr / EC-CAPFIM measurements (BASELINE configs 3, 5) appended to the ECSIM line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -170,7 +196,6 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -181,54 +206,88 @@ def main():
     if world != args.gpus:
         raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run")
     torch.cuda.set_device(local_rank)
-    comm_id = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        ids = [X.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        comm_id = ids[0]
-
-    n, ppc = workload(world, args.scheme)
-    scheme = {"ecsim": X.ECSIM, "ecsimcorr": X.ECSIMCORR, "eccapfim": X.ECCAPFIM}[args.scheme]
-    sim = X.Simulation(n, d=(0.5, 0.5, 0.5), dt=1.5, scheme=scheme, device=local_rank, rank=rank, nranks=world, comm_id=comm_id, track_ids=False)
-    total = n[0] * n[1] * n[2] * ppc
-    sid = sim.add_species(q=-1.0, m=1.0, n=1.0, Np=ppc, capacity=int(sim.ncl * ppc * 1.25) + 65536)
-    mine = sim.set_particles_maxwellian(sid, total, T=0.1, seed=20261018, tov=True)
-    precond = env_int("XPIC_BENCH_PRECOND", 6)
-    sim.solver_set(0, 1e-7, 1e-7, 100, 30, precond)  # the reference's tolerances (ecsim/simulation.h:15-18)
-    sim.solver_set(1, 1e-7, 1e-7, 100, 30, precond)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def maxreduce(v):
+    def reduce(v, op):
         if world == 1:
             return v
         t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
+
+    def maxreduce(v):
+        return reduce(v, dist.ReduceOp.MAX) if world > 1 else v
 
     def sumreduce(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce(v, dist.ReduceOp.SUM) if world > 1 else v
 
-    nparticles = int(sumreduce(float(mine)))
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_source = "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    precond = env_int("XPIC_BENCH_PRECOND", 6)
+    codes = {"ecsim": X.ECSIM, "ecsimcorr": X.ECSIMCORR, "eccapfim": X.ECCAPFIM}
+
+    def make_sim(scheme_name):
+        comm_id = None
+        if world > 1:
+            ids = [X.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            comm_id = ids[0]
+        n, ppc = workload(world, scheme_name)
+        sim = X.Simulation(n, d=(0.5, 0.5, 0.5), dt=1.5, scheme=codes[scheme_name], device=local_rank, rank=rank, nranks=world, comm_id=comm_id,
+                           track_ids=False)
+        total = n[0] * n[1] * n[2] * ppc
+        sid = sim.add_species(q=-1.0, m=1.0, n=1.0, Np=ppc, capacity=int(sim.ncl * ppc * 1.25) + 65536)
+        mine = sim.set_particles_maxwellian(sid, total, T=0.1, seed=20261018, tov=True)
+        sim.solver_set(0, 1e-7, 1e-7, 100, 30, precond)  # the reference's tolerances (ecsim/simulation.h:15-18)
+        sim.solver_set(1, 1e-7, 1e-7, 100, 30, precond)
+        return sim, n, ppc, int(sumreduce(float(mine)))
+
+    def total_energy(sim):
+        # device reductions, summed over all ranks inside the library (Energy diagnostic, diagnostics/energy.cpp:43-107)
+        return sim.field_energy("E") + sim.field_energy("B") + sim.scalar("kinetic")
+
+    def conservation_checks(sim, nparticles, steps=3):
+        """Untimed: `steps` more steps with the invariants the reference's tests assert (tests/common.h:30-89 compares
+        the energy tables; dE + dB + dK at solver tolerance) evaluated around each of them."""
+        e = [total_energy(sim)]
+        reason_min = None
+        for _ in range(steps):
+            sim.step()
+            e.append(total_energy(sim))
+            r = sim.nonlinear_info()["reason"] if sim.scheme == X.ECCAPFIM else sim.solver_info(0)[2]
+            reason_min = r if reason_min is None else min(reason_min, r)
+        drift = max(abs(b - a) for a, b in zip(e[:-1], e[1:]))
+        count = int(sumreduce(float(sim.particle_count(0))))
+        return {"steps_checked": steps, "energy_total": e[-1], "energy_drift_max": drift, "energy_drift_max_rel": drift / e[0] if e[0] else None,
+                "particles_conserved": count == nparticles, "solver_reason_min": reason_min,
+                "note": "max over the checked steps of |d(wE + wB + wK)| (all ranks); the solver stops at rtol = atol = 1e-7 (reference defaults)"}
+
+    # ================= the headline measurement: args.scheme ========================================================
+    sim, n, ppc, nparticles = make_sim(args.scheme)
+    scheme = codes[args.scheme]
 
     # ---- resident arm: W warm-up steps, then exactly K timed steps ---------------------------------
     sim.run_steps(args.warmup)
-    its_warm = sim.solver_info(0)[0]
+    fp64 = measure_fp64_peak() if rank == 0 else None  # before the timed region, while this rank's GPU is idle
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
     launches0 = sim.launch_count()
     sim.timing_reset()
-    sim.spmv_profile(True)
+    sim.family_profile(True)
     if args.scheme == "eccapfim":
         sim.nonlinear_profile(1)
     barrier()
@@ -239,8 +298,9 @@ def main():
         passes, pass_ms = sim.nonlinear_profile(0)
         cap = dict(sim.nonlinear_info(), passes=passes, pass_ms=pass_ms / max(passes, 1))
     launches = sim.launch_count() - launches0
-    spmv_n, spmv_ms = sim.spmv_profile_read()
-    sim.spmv_profile(False)
+    families = sim.family_profile_read()
+    spmv_n, spmv_ms = families["spmv"]
+    sim.family_profile(False)
     stage_s = {k: v[0] / max(v[1], 1) for k, v in sim.timing().items()}
     its = sim.solver_info(0)[0]
     ms = maxreduce(ms)
@@ -261,15 +321,11 @@ def main():
     e2e_value = nparticles * args.steps / (ms_e2e * 1e-3)
     h2d = 3 * sim.nown * 8 * world
     d2h = (2 * sim.nown * 8 + 8) * world
+    del E, B, B0
 
-    # ---- roofline of the dominant kernel (the operator SpMV inside GMRES) --------------------------
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    checks = conservation_checks(sim, nparticles)
+
+    # ---- roofline of the kernel the metric names (the operator SpMV inside GMRES) -----------------
     spmv_avg_ms = spmv_ms / max(spmv_n, 1)
     alg_bytes = 3000.0 * sim.ncl  # 369 coefficients * 8 B + 24 B x + 24 B y per cell
     achieved = alg_bytes / (spmv_avg_ms * 1e-3) / 1e9 if spmv_n else None
@@ -281,10 +337,10 @@ def main():
                 tj = json.load(f)
             if tuple(tj.get("grid", [])) == tuple(n) and world == 1:
                 traffic = tj.get("dram_bytes_per_launch")
-        except Exception:
+        except Exception:  # noqa: BLE001
             pass
     roofline = {"kernel": "k_spmv<L+M>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "traffic": traffic, "peak_source": peak_source,
                 "launches_timed": spmv_n, "avg_launch_ms": spmv_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "spmv_share_of_step": (spmv_ms / ms) if ms else None}
     if cap is not None:
@@ -295,51 +351,83 @@ def main():
         pass_bytes = 96.0 * npart_rank
         ach = pass_bytes / (cap["pass_ms"] * 1e-3) / 1e9 if cap["pass_ms"] else None
         roofline = {"kernel": "k_cap_push (+ current halo add)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    "traffic": None, "peak_source": peak_source,
                     "launches_timed": cap["passes"], "avg_launch_ms": cap["pass_ms"], "algorithmic_bytes_per_launch": pass_bytes,
                     "share_of_step": cap["passes"] * cap["pass_ms"] / ms if ms else None,
                     "particle_pushes_per_s": npart_rank * world * cap["passes"] / (ms * 1e-3) if ms else None}
 
-    # ---- the other kernel families, timed in isolation on the resident state (CUDA events) --------
+    # ---- the kernel families INSIDE the timed steps (CUDA events around every launch group, rank 0's GPU) ---------
     kernels = None
     roofline_dominant = None
-    if world == 1 and args.scheme == "ecsim":
-        fp64_peak = float(os.environ.get("XPIC_FP64_TFLOPS", "37.0"))  # B200 vendor figure (vector = tensor fp64)
-        t_sort, t_dep, t_push, t_solve = (sim.kernel_bench(w, 3) for w in (0, 1, 2, 3))
-        npart = float(nparticles)
+    if args.scheme == "ecsim":
+        npart_rank = float(nparticles) / world
+        fp64_peak = float(fp64["dmma_tflops"]) if fp64 else float(os.environ.get("XPIC_FP64_TFLOPS", "37.0"))
+        fp64_src = ("tools/fp64_peak.cu run on this GPU before the timed region: mma.sync.m8n8k4.f64 issue rate (DFMA rate %.1f TFLOP/s)" % fp64["dfma_tflops"]
+                    if fp64 else "vendor fp64 figure for B200 (xpic_b200/_build/fp64_peak missing)")
+        per = {k: (v[1] / args.steps, v[0] // args.steps) for k, v in families.items()}  # ms per step, launch groups per step
+        t_sort, t_dep, t_push, t_pre = per["sort"][0], per["moments"][0], per["second_push"][0], per["precond"][0]
         kernels = [
-            {"name": "re-binning (key pass + scatter, no move)", "ms": t_sort, "bound": "hbm", "achieved": 152.0 * npart / t_sort / 1e6, "unit": "GB/s",
-             "algorithmic": "152 B/particle: read r,v + key, write r,v"},
-            {"name": "moments (field records + DMMA cell blocks + row gather)", "ms": t_dep, "bound": "fp64", "achieved": 1200.0 * npart / t_dep / 1e9,
-             "unit": "TFLOP/s", "algorithmic": "1200 flop/particle (576 + 24 FMA); HBM: 48 + 192 B/particle, 2 x 10.6 KB + 3 KB per cell"},
-            {"name": "second push (tile-staged gather + Boris)", "ms": t_push, "bound": "hbm", "achieved": 72.0 * npart / t_push / 1e6, "unit": "GB/s",
+            {"name": "re-binning inside the step (move + key pass, scan, scatter" + (", migration" if world > 1 else "") + ")", "ms": t_sort, "bound": "hbm",
+             "achieved": 152.0 * npart_rank / t_sort / 1e6, "unit": "GB/s", "algorithmic": "152 B/particle: read r,v + key, write r,v"},
+            {"name": "moments (fused field records + DMMA cell blocks, row gather)", "ms": t_dep, "bound": "fp64", "achieved": 1200.0 * npart_rank / t_dep / 1e9,
+             "unit": "TFLOP/s", "algorithmic": "1200 flop/particle (576 + 24 FMA); HBM: 48 B/particle in, 10.6 KB/cell staged out and in, 3 KB/cell rows out"},
+            {"name": "second push (tile-staged gather + Boris)", "ms": t_push, "bound": "hbm", "achieved": 72.0 * npart_rank / t_push / 1e6, "unit": "GB/s",
              "algorithmic": "72 B/particle: read r,v, write v"},
-            {"name": "field solve (GMRES + Chebyshev(M))", "ms": t_solve, "bound": "hbm", "achieved": None, "unit": "GB/s",
-             "algorithmic": f"{its} x (3000 B/cell SpMV + 5 x 144 B/cell Chebyshev + Gram-Schmidt)"},
+            {"name": "operator SpMV (all launches of a step)", "ms": spmv_ms / args.steps, "bound": "hbm", "achieved": achieved, "unit": "GB/s",
+             "algorithmic": f"{spmv_n // args.steps} launches x 3000 B/cell"},
+            {"name": f"Chebyshev(M) preconditioner, degree {precond} (all applications of a step)", "ms": t_pre, "bound": "hbm",
+             "achieved": (per["precond"][1] * ((precond - 1) * 96.0 + 48.0) * sim.ncl / t_pre / 1e6) if t_pre else None, "unit": "GB/s",
+             "algorithmic": f"{per['precond'][1]} applications x ({precond - 1} x 96 + 48) B/cell"},
         ]
         for k in kernels:
             if k["achieved"] is not None:
-                k["frac"] = k["achieved"] / (peak if k["bound"] == "hbm" else fp64_peak * 1e0)
+                k["frac"] = k["achieved"] / (peak if k["bound"] == "hbm" else fp64_peak)
         kernels[1]["peak"] = fp64_peak
-        kernels[1]["peak_source"] = "vendor fp64 figure for B200 (not measured); DMMA issue floor measured at 16 cycles / m8n8k4 / SM sub-partition"
+        kernels[1]["peak_source"] = fp64_src
+        stage_sum = {"first_push": t_sort + t_dep, "advance_fields_spmv_plus_precond": spmv_ms / args.steps + t_pre, "second_push": t_push}
         # by time the moment deposition is the dominant kernel family of the step (the SpMV above is the kernel
         # BASELINE.json's metric names); its roof is the fp64 tensor / FMA rate, not HBM
-        roofline_dominant = {"kernel": "moment deposition: k_particle_fields + k_cell_blocks_mma (fp64 DMMA m8n8k4) + k_gather_rows", "bound": "tensor",
+        roofline_dominant = {"kernel": "moment deposition: k_cell_moments (fp64 DMMA m8n8k4, fused field records) + k_gather_rows", "bound": "tensor",
                              "achieved": kernels[1]["achieved"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": kernels[1]["achieved"] / fp64_peak,
-                             "traffic": None, "peak_source": kernels[1]["peak_source"], "avg_launch_ms": t_dep,
-                             "algorithmic_flops_per_launch": 1200.0 * npart, "share_of_step": t_dep / (ms / args.steps) if ms else None}
+                             "traffic": None, "peak_source": fp64_src, "avg_launch_ms": t_dep,
+                             "algorithmic_flops_per_launch": 1200.0 * npart_rank, "share_of_step": t_dep / (ms / args.steps) if ms else None,
+                             "hbm_view": {"algorithmic_bytes": 48.0 * npart_rank + 2976.0 * sim.ncl, "achieved_GBs": (48.0 * npart_rank + 2976.0 * sim.ncl) / t_dep / 1e6,
+                                          "frac_of_hbm_peak": (48.0 * npart_rank + 2976.0 * sim.ncl) / t_dep / 1e6 / peak},
+                             "family_ms_sum_vs_stage_clock": stage_sum}
+    sim.close()
+    del sim
+    torch.cuda.empty_cache()
+
+    # ================= BASELINE configs 3 and 5, short runs on the same GPUs (driver-visible lines) ==================
+    extra = None
+    if args.scheme == "ecsim" and not args.no_extra and not os.environ.get("XPIC_BENCH_GRID"):
+        extra = {}
+        for name, (w_, k_) in (("ecsimcorr", (3, 5)), ("eccapfim", (3, 3))):
+            try:
+                sx, nx_, ppcx, npx = make_sim(name)
+                sx.run_steps(w_)
+                barrier()
+                msx = maxreduce(sx.run_steps(k_))
+                barrier()
+                info = {"metric": f"{name}_particle_steps_per_s", "value": npx * k_ / (msx * 1e-3), "unit": UNIT, "ms_per_step": msx / k_, "steps": k_, "warmup": w_,
+                        "n_gpus": world, "workload": f"{name.upper()} 3D {nx_[0]}x{nx_[1]}x{nx_[2]} cells x {ppcx} ppc fp64", "particles": npx,
+                        "checks": conservation_checks(sx, npx, steps=2)}
+                if name == "eccapfim":
+                    info["nonlinear"] = sx.nonlinear_info()
+                else:
+                    info["krylov_iterations_per_step"] = [sx.solver_info(0)[0], sx.solver_info(1)[0]]
+                extra[name] = info
+                sx.close()
+                del sx
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                extra[name] = {"error": repr(e)[:300]}
+                barrier()
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            if args.scheme == "eccapfim":
-                v, Ns, sps, its_cpu, cores = cpu_baseline_sample(steps=2, warm=1, n=(24, 24, 24), ppc=ppc, scheme="eccapfim")
-                what = f"2 ECCAPFIM steps (after 1 warm-up) of a 24^3-cell x {ppc} ppc sample of the workload, {Ns} particles, {sps:.2f} s/step, {its_cpu} residual evaluations per step"
-            else:
-                v, Ns, sps, its_cpu, cores = cpu_baseline_sample(scheme=args.scheme)
-                what = f"4 {args.scheme.upper()} steps (after 1 warm-up) of a 32^3-cell x 64 ppc sample of the workload, {Ns} particles, {sps:.2f} s/step, {its_cpu} GMRES its"
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": what + f"; oracle/ C++ port, {cores} OpenMP threads (PETSc reference not buildable here)"}
+            cpu = cpu_baseline_subprocess(args.scheme, steps=2 if args.scheme == "eccapfim" else 4, warm=1)
         line = {
             "metric": METRIC if args.scheme == "ecsim" else f"{args.scheme}_particle_steps_per_s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -352,14 +440,14 @@ def main():
                                          "picard_iterations_per_particle_last_evaluation": cap["avg_cn"], "path_pieces_per_particle": cap["avg_cells"],
                                          "picard": "warm-started from the previous residual evaluation of the step (first evaluation cold: ~2.7 iterations per particle)",
                                          "reference_residual_evaluations_per_step": 105}} if cap else {})},
-            "roofline": roofline, "roofline_dominant": roofline_dominant, "kernels": kernels, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_dominant": roofline_dominant, "kernels": kernels, "fp64_peak": fp64, "checks": checks, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "boundary": "xb_step_host: E, B, B0 uploaded from pinned host buffers, E, B and kinetic energy downloaded every step; particles resident"},
+            "other_configs": extra,
             "gpu_launches": launches, "clocks": clocks,
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    sim.close()
     if world > 1:
         dist.destroy_process_group()
 

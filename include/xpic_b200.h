@@ -147,6 +147,15 @@ int xb_launch_count(xb_ctx* ctx, int64_t* launches);
  * enable != 0 starts collecting; the query returns the launches seen and their summed ms. */
 int xb_spmv_profile(xb_ctx* ctx, int32_t enable);
 int xb_spmv_profile_read(xb_ctx* ctx, int64_t* launches, double* total_ms);
+/* The same for the other kernel families INSIDE the step (PETSc log events at kernel-family granularity):
+ * re-binning (Particles::update_cells, src/interfaces/particles.cpp:79-116, with the move of first_push fused),
+ * moments (fill_ecsim_current, src/impls/ecsim/simulation.cpp:336-368), second push (ecsim/particles.cpp:175-192),
+ * operator SpMV (MatMult), Chebyshev preconditioner steps (PCApply). */
+enum { XB_FAMILY_SORT = 0, XB_FAMILY_MOMENTS = 1, XB_FAMILY_PUSH2 = 2, XB_FAMILY_SPMV = 3, XB_FAMILY_PRECOND = 4, XB_FAMILY_COUNT = 5 };
+int xb_family_profile(xb_ctx* ctx, int32_t enable);
+int xb_family_profile_read(xb_ctx* ctx, int32_t family, int64_t* launches, double* total_ms);
+/* Energy::calculate_energy (src/diagnostics/energy.cpp:43-59): 0.5 * |v|^2 of a named vector, summed over all ranks. */
+int xb_field_energy(xb_ctx* ctx, int32_t which, int32_t sid, double* out);
 
 /* --- hooks for the operator sweep (BASELINE config 4) and per-kernel parity tests ----------- */
 /* y = Op x with host vectors (owned slab, natural order).  MatMult, e.g. ecsimcorr/simulation.cpp:78 */

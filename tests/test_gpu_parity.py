@@ -486,3 +486,127 @@ def test_host_backup_and_restart_round_trip(X, tmp_path):
         fa = np.fromfile(a / f / "10", dtype=np.float32)
         fb = np.fromfile(b / f / "10", dtype=np.float32)
         assert rel_err(fb.astype(np.float64), fa.astype(np.float64)) < 1e-6
+
+
+# ---- round 2: sizes and code paths the small boxes above never reach ---------------
+def _sorted_rows(pts):
+    return pts[np.lexsort(pts.T[::-1])]
+
+
+@pytest.mark.parametrize("variant", [0, 3, 2])
+def test_deposit_variants_at_tiling_size(X, variant):
+    """40 x 20 x 12 cells: wider than the SpMV tile (32), the push tiles (16) and not a multiple of either, so
+    CTAs own full tiles and partial ones, x-neighbour tiles exist.  Every moment kernel against the oracle's CSR."""
+    o, s = make_pair(n=(40, 20, 12), Np=16, seed_fields=31)
+    O.set_threads(O.max_threads())
+    try:
+        o.deposit()
+    finally:
+        O.set_threads(1)
+    s.set_option(0, variant)
+    s.deposit()
+    ref = csr_to_stencil(o, X.coef_table())
+    assert np.max(np.abs(s.operator_download() - ref)) / np.max(np.abs(ref)) < 1e-13
+    assert rel_err(s.get_field("currI"), o.get_field("currI")) < 1e-12
+    x = np.random.default_rng(6).standard_normal(o.n3)
+    assert rel_err(s.spmv(x, op=3), o.spmv(x, L=True, M=True)) < 1e-12
+
+
+def test_ecsim_state_parity_at_tiling_size_and_production_path(X):
+    """3 ECSIM steps at 40 x 20 x 12 x 16 ppc against the oracle (fields and id-matched particles < 1e-8), and the
+    production configuration (track_ids = False, reference tolerances replaced by the same tight ones, Chebyshev
+    preconditioner) against the id-tracked run on the same particles."""
+    n = (40, 20, 12)
+    o, s = make_pair(n=n, Np=16, scheme=X.ECSIM, precond=6)
+    pts0, _ = o.get_particles(0)
+    O.set_threads(O.max_threads())
+    try:
+        for _ in range(3):
+            o.step(O.ECSIM)
+            s.step()
+    finally:
+        O.set_threads(1)
+    _compare_state(o, s, 1e-8)
+    p = X.Simulation(n, scheme=X.ECSIM, track_ids=False)
+    p.add_species(Np=16)
+    assert p.add_particles(0, pts0) == len(pts0)
+    p.solver_set(0, 1e-12, 1e-50, 1000, 30, 6)
+    for _ in range(3):
+        p.step()
+    for name in ("E", "B"):
+        assert rel_err(p.get_field(name), s.get_field(name)) < 1e-10, name
+    a, b = _sorted_rows(p.get_particles(0)[0]), _sorted_rows(s.get_particles(0)[0])
+    assert rel_err(a, b) < 1e-10
+    p.close()
+
+
+@pytest.mark.parametrize("scheme", ["ecsim", "ecsimcorr"])
+def test_state_parity_with_cell_sizes_that_are_not_powers_of_two(X, scheme):
+    """d = (0.3, 0.45, 0.7): r / d is a true division (gather.cuh to_cells), the other arithmetic path of every
+    weight computation; 3 steps, fields and id-matched particles within 1e-8."""
+    gs, os_ = (X.ECSIM, O.ECSIM) if scheme == "ecsim" else (X.ECSIMCORR, O.ECSIMCORR)
+    o, s = make_pair(n=(11, 9, 7), Np=30, scheme=gs, d=(0.3, 0.45, 0.7), dt=0.8)
+    for _ in range(3):
+        o.step(os_)
+        s.step()
+    _compare_state(o, s, 1e-8)
+
+
+def test_deposit_with_cell_sizes_that_are_not_powers_of_two(X):
+    o, s = make_pair(n=(11, 9, 7), Np=30, seed_fields=41, d=(0.3, 0.45, 0.7), dt=0.8)
+    o.deposit()
+    ref = csr_to_stencil(o, X.coef_table())
+    for variant in (0, 2, 1):
+        s.set_option(0, variant)
+        s.deposit()
+        assert np.max(np.abs(s.operator_download() - ref)) / np.max(np.abs(ref)) < 1e-13, variant
+        assert rel_err(s.get_field("currI"), o.get_field("currI")) < 1e-12, variant
+
+
+def test_deposit_many_particles_per_cell_and_empty_cells(X):
+    """Ragged bins: 300 particles per cell in a quarter of the box (several record rounds per cell, octants larger
+    than a round), nothing elsewhere (empty cells, empty octants)."""
+    n = (8, 8, 8)
+    o = O.Oracle(n)
+    s = X.Simulation(n, track_ids=True)
+    sid = o.add_species(Np=300)
+    s.add_species(Np=300)
+    rng = np.random.default_rng(3)
+    N = 300 * 4 * 4 * 8
+    pts = np.empty((N, 6))
+    pts[:, 0] = rng.random(N) * 2.0
+    pts[:, 1] = rng.random(N) * 2.0 + 1.0
+    pts[:, 2] = rng.random(N) * 4.0
+    pts[:, 3:] = rng.standard_normal((N, 3)) * 0.02
+    assert o.set_particles(sid, pts) == N
+    pts, ids = o.get_particles(sid)
+    assert s.add_particles(0, pts, ids) == N
+    f = 0.05 * np.random.default_rng(4).standard_normal(o.n3)
+    o.set_field("B", f)
+    s.set_field("B", f)
+    o.deposit()
+    ref = csr_to_stencil(o, X.coef_table())
+    for variant in (0, 3, 2):
+        s.set_option(0, variant)
+        s.deposit()
+        assert np.max(np.abs(s.operator_download() - ref)) / np.max(np.abs(ref)) < 1e-13, variant
+        assert rel_err(s.get_field("currI"), o.get_field("currI")) < 1e-12, variant
+
+
+def test_decomposition_independence_on_two_gpus(X):
+    """The z-slab run equals the single-GPU run (tests/ecsim/CMakeLists.txt:14-16 demands the same of the reference's
+    1- and 2-rank ctest runs).  Needs two GPUs: skipped on a single-GPU box."""
+    import subprocess
+    import sys
+
+    import torch
+
+    from conftest import ROOT
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    env = dict(os.environ, XPIC_CHECK_STEPS="4")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("-> OK") == 3

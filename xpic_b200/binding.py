@@ -19,6 +19,7 @@ ECSIM, ECSIMCORR, ECCAPFIM = 0, 1, 2
 FIELDS = {"E": 0, "B": 1, "B0": 2, "Ep": 3, "Ec": 4, "currI": 5, "currJe": 6, "currI_sort": 7, "currJe_sort": 8, "J": 9, "J_sort": 10, "Ehk": 11}
 SCALARS = {"kinetic": 0, "pred_w": 1, "corr_w": 2, "pred_dK": 3, "corr_dK": 4, "lambda_dK": 5, "energy_member": 6, "j_diff_norm": 7}
 STAGES = ["clear_sources", "first_push", "advance_fields", "second_push", "correct_fields", "final_update"]
+FAMILIES = ["sort", "moments", "second_push", "spmv", "precond"]
 OP_L, OP_M, OP_A = 1, 2, 3
 
 
@@ -90,6 +91,9 @@ SYMBOLS = {
     "xb_run_steps_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp]),
     "xb_spmv_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "xb_spmv_profile_read": (C.c_int, [C.c_void_p, _i64p, _dp]),
+    "xb_family_profile": (C.c_int, [C.c_void_p, C.c_int32]),
+    "xb_family_profile_read": (C.c_int, [C.c_void_p, C.c_int32, _i64p, _dp]),
+    "xb_field_energy": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "xb_scalar": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "xb_particle_moments": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "xb_timing": (C.c_int, [C.c_void_p, C.c_int32, _dp, _i64p]),
@@ -340,6 +344,24 @@ class Simulation:
         n, ms = C.c_int64(), C.c_double()
         _check(self._L.xb_spmv_profile_read(self._h, C.byref(n), C.byref(ms)))
         return n.value, ms.value
+
+    def family_profile(self, enable=True):
+        """CUDA-event timing of the kernel families inside the step (FAMILIES); enabling resets the counters."""
+        _check(self._L.xb_family_profile(self._h, int(enable)))
+
+    def family_profile_read(self):
+        out = {}
+        for i, name in enumerate(FAMILIES):
+            n, ms = C.c_int64(), C.c_double()
+            _check(self._L.xb_family_profile_read(self._h, i, C.byref(n), C.byref(ms)))
+            out[name] = (n.value, ms.value)
+        return out
+
+    def field_energy(self, name, sid=0):
+        """0.5 |v|^2 over ALL ranks, reduced on the device (Energy::calculate_energy)."""
+        out = C.c_double()
+        _check(self._L.xb_field_energy(self._h, FIELDS[name], sid, C.byref(out)))
+        return out.value
 
     def scalar(self, name, sid=0):
         out = C.c_double()

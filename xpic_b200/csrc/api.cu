@@ -17,10 +17,36 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 int migrate_and_sort(xb_ctx* c, Species& s, double dt_move);  // migrate.cu
 
+int prof_begin(xb_ctx* c, int family)
+{
+  if (!c->family_profile) return 0;
+  auto& ev = c->prof_events[family];
+  if (c->prof_used[family] + 2 > ev.size())
+    for (int i = 0; i < 256; ++i) {
+      cudaEvent_t e;
+      XB_CUDA(cudaEventCreate(&e));
+      ev.push_back(e);
+    }
+  XB_CUDA(cudaEventRecord(ev[c->prof_used[family]], c->stream));
+  return 0;
+}
+
+int prof_end(xb_ctx* c, int family)
+{
+  if (!c->family_profile) return 0;
+  XB_CUDA(cudaEventRecord(c->prof_events[family][c->prof_used[family] + 1], c->stream));
+  c->prof_used[family] += 2;
+  return 0;
+}
+
 static int sort_species(xb_ctx* c, Species& s, double dt_move)
 {
-  if (c->g.nranks > 1) return migrate_and_sort(c, s, dt_move);
-  return particles_sort(c, s, dt_move);
+  XB_CHECK(prof_begin(c, XB_FAMILY_SORT));
+  if (c->g.nranks > 1)
+    XB_CHECK(migrate_and_sort(c, s, dt_move));
+  else
+    XB_CHECK(particles_sort(c, s, dt_move));
+  return prof_end(c, XB_FAMILY_SORT);
 }
 
 struct StageTimer {
@@ -77,8 +103,9 @@ static int stage_first_push(xb_ctx* c, int scheme)
       XB_CHECK(sort_species(c, s, 0.0));
     }
   }
+  XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS));
   XB_CHECK(deposit_moments(c));
-  return 0;
+  return prof_end(c, XB_FAMILY_MOMENTS);
 }
 
 static int solve_checked(xb_ctx* c, int which, int op, const double* curr, double* out)
@@ -97,7 +124,9 @@ static int stage_second_push(xb_ctx* c, int scheme)
   XB_CHECK(halo_fill(c, c->B, 1));
   for (auto& s : c->sorts) {
     if (scheme == XB_ECSIM) {
+      XB_CHECK(prof_begin(c, XB_FAMILY_PUSH2));
       XB_CHECK(push_second(c, s, c->Ep, c->B));
+      XB_CHECK(prof_end(c, XB_FAMILY_PUSH2));
       // positions did not change: the reference's second update_cells is a no-op here
     }
     else {
@@ -237,18 +266,11 @@ int xb_operator_coef_info(int k, int* c1, int* c2, int* dx, int* dy, int* dz)
 
 int xb_comm_unique_id(void* out128) { return comm_unique_id(out128); }
 
-int xb_create(const xb_grid* gr, const void* uid, xb_ctx** out)
+int xb_destroy(xb_ctx* c);
+}
+
+static int create_impl(xb_ctx* c, const xb_grid* gr, const void* uid)
 {
-  if (!gr || !out) XB_FAIL("xb_create: null argument");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    XB_FAIL("xb_create: no CUDA device available (this library has no CPU fallback)");
-  if (gr->device < 0 || gr->device >= ndev) XB_FAIL("xb_create: bad device ordinal");
-  if (gr->nranks < 1 || gr->rank < 0 || gr->rank >= gr->nranks) XB_FAIL("xb_create: bad rank / nranks");
-  for (int a = 0; a < 3; ++a)
-    if (gr->n[a] < 1 || !(gr->d[a] > 0.0)) XB_FAIL("xb_create: bad geometry");
-  XB_CUDA(cudaSetDevice(gr->device));
-  xb_ctx* c = new xb_ctx();
   c->device = gr->device;
   c->track_ids = gr->track_ids != 0;
   Grid& g = c->g;
@@ -302,17 +324,31 @@ int xb_create(const xb_grid* gr, const void* uid, xb_ctx** out)
   XB_CUDA(cudaMalloc(&c->red_partial, sizeof(double) * RED_BLOCKS * RED_MAXV));
   XB_CUDA(cudaMalloc(&c->red_out, sizeof(double) * RED_MAXV));
   XB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * RED_MAXV));
-  if (g.nranks > 1) {
-    if (comm_init(c, uid)) {
-      xb_destroy(c);
-      return 1;
-    }
-  }
-  if (krylov_prepare(c)) {
+  if (g.nranks > 1) XB_CHECK(comm_init(c, uid));
+  XB_CHECK(krylov_prepare(c));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+
+extern "C" {
+
+int xb_create(const xb_grid* gr, const void* uid, xb_ctx** out)
+{
+  if (!gr || !out) XB_FAIL("xb_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    XB_FAIL("xb_create: no CUDA device available (this library has no CPU fallback)");
+  if (gr->device < 0 || gr->device >= ndev) XB_FAIL("xb_create: bad device ordinal");
+  if (gr->nranks < 1 || gr->rank < 0 || gr->rank >= gr->nranks) XB_FAIL("xb_create: bad rank / nranks");
+  for (int a = 0; a < 3; ++a)
+    if (gr->n[a] < 1 || !(gr->d[a] > 0.0)) XB_FAIL("xb_create: bad geometry");
+  XB_CUDA(cudaSetDevice(gr->device));
+  xb_ctx* c = new xb_ctx();
+  if (create_impl(c, gr, uid)) {  // any failure after `new` releases what was allocated so far (the message survives)
     xb_destroy(c);
     return 1;
   }
-  XB_CUDA(cudaStreamSynchronize(c->stream));
   *out = c;
   return 0;
 }
@@ -340,7 +376,8 @@ int xb_destroy(xb_ctx* c)
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
   if (c->ev3) cudaEventDestroy(c->ev3);
-  for (auto e : c->spmv_events) cudaEventDestroy(e);
+  for (auto& v : c->prof_events)
+    for (auto e : v) cudaEventDestroy(e);
   if (c->copy_done) cudaEventDestroy(c->copy_done);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -550,26 +587,43 @@ int xb_run_steps_host(xb_ctx* c, int32_t scheme, int32_t k, double* E, double* B
   return 0;
 }
 
-int xb_spmv_profile(xb_ctx* c, int32_t enable)
+int xb_family_profile(xb_ctx* c, int32_t enable)
 {
   XB_API_BEGIN(c);
-  c->spmv_profile = enable != 0;
-  c->spmv_events_used = 0;
+  c->family_profile = enable != 0;
+  for (auto& u : c->prof_used) u = 0;
   return 0;
 }
 
-int xb_spmv_profile_read(xb_ctx* c, int64_t* launches, double* total_ms)
+int xb_family_profile_read(xb_ctx* c, int32_t family, int64_t* launches, double* total_ms)
 {
   XB_API_BEGIN(c);
+  if (family < 0 || family >= XB_FAMILY_COUNT) XB_FAIL("xb_family_profile_read: unknown family");
   XB_CUDA(cudaStreamSynchronize(c->stream));
   double tot = 0.0;
-  for (size_t i = 0; i + 1 < c->spmv_events_used; i += 2) {
+  const auto& ev = c->prof_events[family];
+  for (size_t i = 0; i + 1 < c->prof_used[family]; i += 2) {
     float t = 0.f;
-    XB_CUDA(cudaEventElapsedTime(&t, c->spmv_events[i], c->spmv_events[i + 1]));
+    XB_CUDA(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
     tot += t;
   }
-  if (launches) *launches = (int64_t)(c->spmv_events_used / 2);
+  if (launches) *launches = (int64_t)(c->prof_used[family] / 2);
   if (total_ms) *total_ms = tot;
+  return 0;
+}
+
+int xb_spmv_profile(xb_ctx* c, int32_t enable) { return xb_family_profile(c, enable); }
+int xb_spmv_profile_read(xb_ctx* c, int64_t* launches, double* total_ms) { return xb_family_profile_read(c, XB_FAMILY_SPMV, launches, total_ms); }
+
+int xb_field_energy(xb_ctx* c, int32_t which, int32_t sid, double* out)
+{
+  XB_API_BEGIN(c);
+  const double* v = named_vector(c, which, sid);
+  if (!v || !out) XB_FAIL("xb_field_energy: unknown vector");
+  const double* vs[1] = {v};
+  double n2 = 0.0;
+  XB_CHECK(dots(c, 1, vs, v, &n2));
+  *out = 0.5 * n2;
   return 0;
 }
 

@@ -117,7 +117,7 @@ struct Species {
   double* p[2][6] = {{nullptr}};  // x,y,z,vx,vy,vz
   uint64_t* id[2] = {nullptr, nullptr};
   int32_t* key = nullptr;        // bin of every particle (capacity)
-  double* rec = nullptr;         // field record of every particle, SoA [12][capacity] (deposit.cu)
+  double* rec = nullptr;         // field record of every particle, SoA [12][capacity]: cross-check pipeline only, allocated on first use (deposit.cu)
   int32_t* bin_start = nullptr;  // nbins + 1, valid after sort
   double* currI = nullptr;       // per-sort currents (ghosted grid vectors)
   double* currJe = nullptr;
@@ -148,9 +148,11 @@ struct xb_ctx {
   cudaStream_t copy_stream = nullptr;  // host<->device copies of xb_step_host that overlap with the particle stages
   cudaEvent_t copy_done = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
-  bool spmv_profile = false;
-  std::vector<cudaEvent_t> spmv_events;  // pairs (start, stop), recorded around every operator launch
-  size_t spmv_events_used = 0;
+  // CUDA-event pairs (start, stop) recorded around every launch group of a kernel family inside the step
+  // (xb_family_profile); family 3 is the operator SpMV (xb_spmv_profile)
+  bool family_profile = false;
+  std::vector<cudaEvent_t> prof_events[XB_FAMILY_COUNT];
+  size_t prof_used[XB_FAMILY_COUNT] = {0};
   // named grid vectors (ghosted)
   double *E = nullptr, *B = nullptr, *B0 = nullptr, *Ep = nullptr, *Ec = nullptr, *currI = nullptr, *currJe = nullptr;
   double *rhs = nullptr, *tmp = nullptr, *tmp2 = nullptr;
@@ -158,7 +160,8 @@ struct xb_ctx {
   double* coef = nullptr;   // blocked [tile][k][t], see stencil.cuh
   int64_t coef_elems = 0;
   bool coef_valid = false;
-  int deposit_variant = 0;  // 0: DMMA cell blocks (default), 1: scalar-FMA cell blocks (kept as a cross-check)
+  int deposit_variant = 0;  // 0: fused DMMA kernel (default), 3: same at 2 CTAs / SM, 2: round-1 DMMA pipeline, 1: scalar FMA (cross-checks)
+  bool fused_attr_set = false, deposit_attr_set = false, esirkepov_attr_set = false, cap_attr_set = false;  // per context = per device
   int cap_variant = 0;  // eccapfim particle pass: 0 CTA task machine (default), 1 thread per particle (cross-check)
   int esirkepov_variant = 0;  // 0: DMMA cell blocks + gather (default), 1: per-particle global reductions (cross-check)
   // deposit staging (cell blocks)
@@ -259,6 +262,10 @@ int charge_density(xb_ctx* c, Species& s);                               // Part
 int charge_conservation(xb_ctx* c, int which_current, double* norms);   // ChargeConservation::add_columns
 int momentum(xb_ctx* c, Species& s, double* out6);                      // MomentumConservation::calculate
 int distribution_moment(xb_ctx* c, Species& s, int moment);             // DistributionMoment::collect -> c->tmp2, component 0
+
+// ---- api.cu: in-step kernel-family timing ------------------------------------------------------
+int prof_begin(xb_ctx* c, int family);
+int prof_end(xb_ctx* c, int family);
 
 // ---- launch bookkeeping ----------------------------------------------------------------------
 #define XB_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \

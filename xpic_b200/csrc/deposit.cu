@@ -20,6 +20,7 @@
 // Roofline: pass 1 is FP64-FMA bound (576 FMA per particle), pass 2 HBM bound
 // (1332 * 8 B read + 369 * 8 B written per cell).
 #include "common.cuh"
+#include "deposit.cuh"
 #include "gather.cuh"
 #include "stencil.cuh"
 
@@ -29,28 +30,6 @@ constexpr int DEP_WARPS = CELL_GROUP;  // one warp per cell
 constexpr int DEP_CHUNK = 16;          // particles staged per round
 constexpr int REC = 36;                // s[3][8], A*alpha[9], I_p[3]
 constexpr int DEP_SMEM_PER_WARP = BLOCK_ALL + DEP_CHUNK * REC;
-
-// window position of point t = (k, j, i) of component c for a particle of octant (ox, oy, oz)
-// src/impls/ecsim/particles.cpp:145-147
-__device__ __forceinline__ int block_pos(int c, int t, int ox, int oy, int oz)
-{
-  const int i = t & 1, j = (t >> 1) & 1, k = t >> 2;
-  if (c == 0) return (k * 2 + j) * 3 + (ox + i);
-  if (c == 1) return (k * 3 + (oy + j)) * 2 + i;
-  return ((oz + k) * 2 + j) * 2 + i;
-}
-
-struct DepositArgs {
-  const double* p[6];
-  const int32_t* bin_start;
-  int64_t bin_cell0;    // first cell (in bin space) of this launch
-  int64_t ncells;       // cells in this launch
-  int64_t stage_cell0;  // staging cell id of the first cell
-  int zshift;
-  double q, m, mpw;
-  double* rec;         // per-particle field record, SoA [12][rec_stride]: A_p alpha (9), I_p (3)
-  int64_t rec_stride;
-};
 
 __global__ void __launch_bounds__(DEP_WARPS * 32) k_cell_blocks(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage)
 {
@@ -599,16 +578,11 @@ int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage);  // migrate.cu (m
 
 // cell blocks of `ncells` consecutive cells (bin space) into the staging area
 int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* bin_start, int64_t bin_cell0, int64_t ncells, int64_t stage_cell0,
-                  int zshift, double* rec, int64_t rec_stride, int64_t nparticles)
+                  int zshift, double** rec, int64_t rec_stride, int64_t nparticles)
 {
-  static bool attr_set = false;
-  const bool use_mma = c->deposit_variant != 1;
-  const size_t smem = sizeof(double) * (use_mma ? MMA_SMEM_PER_CELL : DEP_SMEM_PER_WARP) * CELL_GROUP;
-  if (!attr_set) {
-    XB_CUDA(cudaFuncSetAttribute(k_cell_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * DEP_SMEM_PER_WARP * CELL_GROUP)));
-    XB_CUDA(cudaFuncSetAttribute(k_cell_blocks_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * MMA_SMEM_PER_CELL * CELL_GROUP)));
-    attr_set = true;
-  }
+  // variants (xb_set_option(ctx, 0, v)): 0 fused DMMA kernel, 3 the same at two CTAs per SM (255 registers),
+  // 2 round-1 pipeline (field records in HBM + two-warp DMMA kernel), 1 scalar-FMA cell blocks
+  const int variant = c->deposit_variant;
   DepositArgs a;
   for (int k = 0; k < 6; ++k) a.p[k] = p[k];
   a.bin_start = bin_start;
@@ -619,17 +593,28 @@ int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* 
   a.q = s.q;
   a.m = s.m;
   a.mpw = s.n / (double)s.Np;
-  a.rec = rec;
+  a.rec = nullptr;
   a.rec_stride = rec_stride;
   if ((a.stage_cell0 % CELL_GROUP) != 0) XB_FAIL("deposit: plane size must be a multiple of the staging group in multi-rank runs");
+  // the cells of one launch are whole planes: owned planes (bin plane 1.. -> zl 0..) or one ghost plane
+  const Grid& g = c->g;
+  const int zl_off = bin_cell0 == g.plane ? 0 : (stage_cell0 == 0 ? -1 : g.nzl);
+  if (variant == 0 || variant == 3) return launch_cell_moments(c, a, zl_off, variant == 3 ? 2 : 3);
+
+  const bool use_mma = variant == 2;
+  const size_t smem = sizeof(double) * (use_mma ? MMA_SMEM_PER_CELL : DEP_SMEM_PER_WARP) * CELL_GROUP;
+  if (!c->deposit_attr_set) {
+    XB_CUDA(cudaFuncSetAttribute(k_cell_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * DEP_SMEM_PER_WARP * CELL_GROUP)));
+    XB_CUDA(cudaFuncSetAttribute(k_cell_blocks_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * MMA_SMEM_PER_CELL * CELL_GROUP)));
+    c->deposit_attr_set = true;
+  }
   const int groups = (int)((a.ncells + CELL_GROUP - 1) / CELL_GROUP);
   if (use_mma) {
+    if (!*rec) XB_CUDA(cudaMalloc(rec, sizeof(double) * 12 * rec_stride));  // only the cross-check pipeline stores field records
+    a.rec = *rec;
     if (nparticles > 0) {
-      // the cells of one launch are whole planes: owned planes (bin plane 1.. -> zl 0..) or one ghost plane
-      const Grid& g = c->g;
       const int groups_x = (g.nx + PF_CELLS - 1) / PF_CELLS;
       const int64_t planes = ncells / g.plane;
-      const int zl_off = bin_cell0 == g.plane ? 0 : (stage_cell0 == 0 ? -1 : g.nzl);
       XB_LAUNCH(c, k_particle_fields, (int)(groups_x * g.ny * planes), PF_THREADS, 0, g, a, c->B, groups_x, zl_off);
     }
     XB_LAUNCH(c, k_cell_blocks_mma, groups, MMA_WARPS * 32, smem, c->g, a, c->B, c->stage);
@@ -648,7 +633,7 @@ int deposit_moments(xb_ctx* c)
   for (auto& s : c->sorts) {
     if (!s.sorted) XB_FAIL("deposit: particles are not sorted");
     // bin plane 1 = first owned plane; staging plane 0 is the low ghost plane in multi-rank runs
-    XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane, g.ncl, single ? 0 : g.plane, 0, s.rec, s.capacity, s.count));
+    XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane, g.ncl, single ? 0 : g.plane, 0, &s.rec, s.capacity, s.count));
     if (!single) XB_CHECK(deposit_ghost_cells(c, s, c->stage));
     GatherArgs ga{c->stage, single ? 1 : 0};
     const int acc = first ? 0 : 1;

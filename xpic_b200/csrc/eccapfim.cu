@@ -970,7 +970,9 @@ int cap_form_function(xb_ctx* c, double* x, double* F)
     if (!s.sorted) XB_FAIL("eccapfim: particles are not sorted");
     XB_CHECK(vec_zero(c, s.currI));  // Particles::J of this evaluation (clear_sources, particles.cpp:183-189)
     total += s.count;
-    if (s.count == 0) continue;
+    // a slab that holds no particle of this sort skips only the particle kernel: the halo add below is a
+    // collective with both z neighbours (their currents land in this rank's boundary planes)
+    const bool have_particles = s.count > 0;
     CapArgs a;
     for (int k = 0; k < 6; ++k) {
       a.p0[k] = s.p[s.cur][k];
@@ -988,17 +990,18 @@ int cap_form_function(xb_ctx* c, double* x, double* F)
     a.counters = c->cap_counters;
     a.error = reinterpret_cast<int*>(c->cap_counters + 2);
     a.warm = (nl.warm_start && nl.pn_valid) ? 1 : 0;
-    if (c->cap_variant == 1) {  // thread-per-particle kernel, kept as a cross-check
+    if (!have_particles) {
+    }
+    else if (c->cap_variant == 1) {  // thread-per-particle kernel, kept as a cross-check
       a.groups_x = (g.nx + CAP_CELLS - 1) / CAP_CELLS;
       const int64_t blocks = (int64_t)a.groups_x * g.ny * g.nzl;
       XB_LAUNCH(c, k_cap_push, (int)blocks, CAP_THREADS, 0, g, a);
     }
     else {
-      static bool attr_set = false;
       const size_t smem = sizeof(double) * CAP2_SMEM_DOUBLES;
-      if (!attr_set) {
+      if (!c->cap_attr_set) {
         XB_CUDA(cudaFuncSetAttribute(k_cap_push_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        c->cap_attr_set = true;
       }
       a.groups_x = (g.nx + CAP2_CELLS - 1) / CAP2_CELLS;
       const int64_t blocks = (int64_t)a.groups_x * g.ny * g.nzl;
@@ -1024,7 +1027,10 @@ int cap_read_counters(xb_ctx* c)
   XB_CUDA(cudaMemcpyAsync(h, c->cap_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   XB_CUDA(cudaStreamSynchronize(c->stream));
   const int err = (int)(h[2] & 0xffffffffu);
-  if (err) XB_FAIL("eccapfim: a particle moved beyond the ghost planes of its slab within one step");
+  if (err == 2) XB_FAIL("eccapfim: a particle moved beyond the ghost planes of its slab within one step");
+  if (err == 3) XB_FAIL("eccapfim: a particle crossed more cell faces in one step than the path splitter holds (CAP2_MAXSEG)");
+  if (err == 4) XB_FAIL("eccapfim: a time-split sub-step ended inside the box (only the split at the box edge is supported)");
+  if (err) XB_FAIL("eccapfim: particle pass failed with device error code " + std::to_string(err));
   double sums[2] = {(double)h[0], (double)h[1]};
   double n = (double)nl.particles_per_eval;
   if (c->g.nranks > 1) {

@@ -238,11 +238,10 @@ static int run_cells(xb_ctx* c, Species& s)
   const Grid& g = c->g;
   if (!s.sorted) XB_FAIL("esirkepov: particles are not sorted");
   if (g.nx < EW || g.ny < EW) XB_FAIL("esirkepov (tensor-core form): the box must be at least 6 cells wide in x and y");
-  static bool attr = false;
   const size_t smem = sizeof(double) * ((size_t)ECELLS * ESMEM_PER_CELL);
-  if (!attr) {
+  if (!c->esirkepov_attr_set) {
     XB_CUDA(cudaFuncSetAttribute(k_esirkepov_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    c->esirkepov_attr_set = true;
   }
   const int groups_x = (g.nx + TILE_CELLS - 1) / TILE_CELLS;
   const int64_t groups = (int64_t)groups_x * g.ny * g.nzl;

@@ -221,15 +221,21 @@ __device__ __forceinline__ int slab_plane(const Grid& g, double pz)
   return up <= dn ? g.nzl + 1 : 0;
 }
 
-// bin = (cell << 3) | octant, cell over the nzl + 2 bin planes
+// bin = (cell << 3) | octant, cell over the nzl + 2 bin planes.  The octant bit is taken relative to the
+// CLAMPED cell index, so that (cell, octant) always names floor(xn - 0.5) = cell - 1 + octant: when r / d rounds
+// up to exactly n (r one ulp below L, d not a power of two) the particle sits at the top of cell n - 1, octant 1.
+__device__ __forceinline__ void clamped_cell_and_octant(double xn, int n, int& i, int& o)
+{
+  i = min(max((int)floor(xn), 0), n - 1);
+  o = min(max((int)floor(xn - 0.5) - i + 1, 0), 1);
+}
+
 __device__ __forceinline__ int32_t particle_key(const Grid& g, double px, double py, double pz, int pl)
 {
   int ix, iy, iz, ox, oy, oz;
-  cell_and_octant(to_cells(px, g.dx, g.inv_dx, g.exact_inv & 1), ix, ox);
-  cell_and_octant(to_cells(py, g.dy, g.inv_dy, g.exact_inv & 2), iy, oy);
-  cell_and_octant(to_cells(pz, g.dz, g.inv_dz, g.exact_inv & 4), iz, oz);
-  ix = min(max(ix, 0), g.nx - 1);
-  iy = min(max(iy, 0), g.ny - 1);
+  clamped_cell_and_octant(to_cells(px, g.dx, g.inv_dx, g.exact_inv & 1), g.nx, ix, ox);
+  clamped_cell_and_octant(to_cells(py, g.dy, g.inv_dy, g.exact_inv & 2), g.ny, iy, oy);
+  clamped_cell_and_octant(to_cells(pz, g.dz, g.inv_dz, g.exact_inv & 4), g.nz, iz, oz);
   return (int32_t)(((((int64_t)pl * g.ny + iy) * g.nx + ix) << 3) | (oz << 2) | (oy << 1) | ox);
 }
 

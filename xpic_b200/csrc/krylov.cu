@@ -139,7 +139,9 @@ int gmres(xb_ctx* c, int which, int op, const double* b, double* x)
     for (; k < m && sv.iterations < sv.maxit; ++k) {
       double* w = c->V[k + 1];
       if (deg > 0) {
+        XB_CHECK(prof_begin(c, XB_FAMILY_PRECOND));
         XB_CHECK(cheb_apply(c, deg, c->V[k], c->Z, wr, wd, wm));
+        XB_CHECK(prof_end(c, XB_FAMILY_PRECOND));
         XB_CHECK(spmv(c, op, c->Z, w));
       }
       else {
@@ -168,8 +170,8 @@ int gmres(xb_ctx* c, int which, int op, const double* b, double* x)
         H[(size_t)i * m + k] = t;
       }
       const double a = H[(size_t)k * m + k], bq = H[(size_t)(k + 1) * m + k], rr = std::hypot(a, bq);
-      cs[k] = a / rr;
-      sn[k] = bq / rr;
+      cs[k] = rr > 0.0 ? a / rr : 1.0;  // rr = 0: the Krylov space is exhausted (w = 0 and a zero diagonal)
+      sn[k] = rr > 0.0 ? bq / rr : 0.0;
       H[(size_t)k * m + k] = rr;
       H[(size_t)(k + 1) * m + k] = 0.0;
       gg[k + 1] = -sn[k] * gg[k];

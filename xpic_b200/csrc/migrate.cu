@@ -26,7 +26,7 @@ namespace xb {
 int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBuffers* arrivals, int64_t n_from_down, int64_t n_from_up,
                           double dt_move);  // particles.cu
 int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* bin_start, int64_t bin_cell0, int64_t ncells, int64_t stage_cell0,
-                  int zshift, double* rec, int64_t rec_stride, int64_t nparticles);  // deposit.cu
+                  int zshift, double** rec, int64_t rec_stride, int64_t nparticles);  // deposit.cu
 
 static int ensure_buffers(xb_ctx* c, Species& s)
 {
@@ -43,7 +43,6 @@ static int ensure_buffers(xb_ctx* c, Species& s)
       XB_CUDA(cudaMalloc(&m->recv[d][k], sizeof(double) * m->cap));
     }
     for (int k = 0; k < 6; ++k) XB_CUDA(cudaMalloc(&m->ghost[d][k], sizeof(double) * m->ghost_cap));
-    XB_CUDA(cudaMalloc(&m->ghost_rec[d], sizeof(double) * 12 * m->ghost_cap));
     XB_CUDA(cudaMalloc(&m->ghost_bins[d], sizeof(int32_t) * (g.plane * 8 + 1)));
     XB_CUDA(cudaMalloc(&m->recv_key[d], sizeof(int32_t) * m->cap));
   }
@@ -239,8 +238,8 @@ int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage)
   // low ghost plane: the neighbour below; across the periodic boundary its z is nz planes above mine
   const int zs_lo = g.rank == 0 ? -g.nz : 0;
   const int zs_hi = g.rank == g.nranks - 1 ? +g.nz : 0;
-  XB_CHECK(deposit_cells(c, s, m.ghost[0], m.ghost_bins[0], 0, g.plane, 0, zs_lo, m.ghost_rec[0], m.ghost_cap, glo));
-  XB_CHECK(deposit_cells(c, s, m.ghost[1], m.ghost_bins[1], 0, g.plane, (int64_t)(g.nzl + 1) * g.plane, zs_hi, m.ghost_rec[1], m.ghost_cap, ghi));
+  XB_CHECK(deposit_cells(c, s, m.ghost[0], m.ghost_bins[0], 0, g.plane, 0, zs_lo, &m.ghost_rec[0], m.ghost_cap, glo));
+  XB_CHECK(deposit_cells(c, s, m.ghost[1], m.ghost_bins[1], 0, g.plane, (int64_t)(g.nzl + 1) * g.plane, zs_hi, &m.ghost_rec[1], m.ghost_cap, ghi));
   return 0;
 }
 

@@ -1,0 +1,358 @@
+// moments_fused.cu -- pass 1 of the ECSIM moment deposition in ONE kernel: per-particle field
+// records (B gather, beta, A_p alpha, I_p), the rank-1 updates on the fp64 tensor path and the
+// coalesced write of the finished cell blocks.
+//
+// Replaces ecsim::Particles::decompose_ecsim_current (src/impls/ecsim/particles.cpp:62-173); the
+// arithmetic per particle is the reference's, operation by operation (weights :76-105, beta / I_p /
+// alpha :107-115, s1 * s2 * A_p alpha into the cell's 9 x 12 x 12 block :145-165).
+//
+// Differences to the round-1 pipeline (k_particle_fields + k_cell_blocks_mma, kept in deposit.cu as a
+// cross-check): no per-particle record round trip through HBM (96 B written + 120 B read per particle),
+// one warp per cell instead of two (every operand is loaded once per group of four particles and feeds
+// all nine DMMAs), records of 26 instead of 63 doubles (the 24 corner weights are rebuilt from the 12 axis
+// weights by six multiplies per group), 128-bit shared loads, weights from the known cell of the bin
+// instead of floor(), and half the shared-memory folds: accumulators are kept per (slot, ox, oy) variant
+// in registers (21 pairs); the oz bit is handled by folding the z-dependent slots once when the octant
+// walk passes from oz = 0 to oz = 1 and once at the end of the cell.
+//
+// Roofline: fp64 tensor path (mma.sync.m8n8k4.f64, nine per four particles) and the shared-memory
+// pipe; HBM sees 48 B per particle in and 10.6 KB per cell out.
+#include "common.cuh"
+#include "deposit.cuh"
+#include "gather.cuh"
+#include "stencil.cuh"
+
+namespace xb {
+
+namespace {
+
+constexpr int FM_CELLS = CELL_GROUP;       // cells (= warps) per CTA, one staging group
+constexpr int FM_THREADS = 32 * FM_CELLS;
+constexpr int FM_CHUNK = 32;               // particles per record round: one per lane
+constexpr int FM_REC = 26;                 // doubles per record = 13 chunks of 16 bytes (odd: conflict-free 128-bit stores)
+constexpr int FM_BLOCK = 1344;             // BLOCK_ALL = 1332 padded to 21 x 32 double2
+constexpr int FM_TILE = 88;                // 3 x 3 x 3 nodes x 3 components of B (81), padded
+constexpr int FM_CELL = FM_BLOCK + FM_CHUNK * FM_REC + FM_TILE;  // 2264 doubles = 18 112 B per cell
+static_assert(FM_BLOCK >= BLOCK_ALL && FM_BLOCK % 64 == 0, "block padding");
+static_assert(FM_CELL % 16 == 8, "write-out reads the four blocks of a CTA without bank conflicts");
+static_assert(FM_REC % 2 == 0 && (FM_REC / 2) % 2 == 1, "records are an odd number of 16-byte chunks");
+
+// record layout in 16-byte chunks:
+//   0..2  (wn, ws)[axis][lower]     3  (a00, a01)
+//   4..6  (wn, ws)[axis][upper]     7  (a02, a10)
+//   8 (a11, a12)   9 (a20, a21)   10 (a22, I0)   11 (I1, I2)   12 pad
+// a[c1][c2] = A_p alpha[c1][c2].  The lower / upper chunks of an axis are 64 bytes apart, so the eight
+// chunks a warp touches in one weight load (4 particles x 2) fall into eight different 16-byte bank groups.
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// ---- accumulator bookkeeping (compile time) -----------------------------------------------------
+// slot sl = c1 * 3 + c2.  A slot's 8 x 8 tile moves inside the cell's 12 x 12 block with the octant bit of
+// its row component (along that component's staggered axis) and of its column component.  Variants over
+// (ox, oy) live in registers; oz is sequenced (see the header comment).
+__host__ __device__ constexpr bool dep(int sl, int a) { return sl / 3 == a || sl % 3 == a; }
+__host__ __device__ constexpr int nvar(int sl) { return (dep(sl, 0) ? 2 : 1) * (dep(sl, 1) ? 2 : 1); }
+__host__ __device__ constexpr int vbase(int sl)
+{
+  int b = 0;
+  for (int i = 0; i < sl; ++i) b += nvar(i);
+  return b;
+}
+// register variant of slot sl for a particle of (ox, oy) = (oxy & 1, oxy >> 1)
+__host__ __device__ constexpr int vidx(int sl, int oxy)
+{
+  return vbase(sl) + (dep(sl, 0) ? (oxy & 1) : 0) + (dep(sl, 1) ? (oxy >> 1) * (dep(sl, 0) ? 2 : 1) : 0);
+}
+// octant bit of axis a that register variant v of slot sl stands for (oz: the sequenced bit)
+__host__ __device__ constexpr int vbit(int sl, int v, int a, int oz)
+{
+  if (a == 2) return oz;
+  if (!dep(sl, a)) return 0;
+  if (a == 0) return v & 1;
+  return dep(sl, 0) ? (v >> 1) : (v & 1);
+}
+constexpr int NMAT = vbase(8) + nvar(8);  // 21 accumulator pairs
+static_assert(NMAT == 21, "21 (slot, ox, oy) variants");
+// currents: component c moves with its own octant bit only: X 2 variants, Y 2, Z 1 (sequenced)
+__host__ __device__ constexpr int cbase(int c) { return c == 0 ? 0 : (c == 1 ? 2 : 4); }
+__host__ __device__ constexpr int cidx(int c, int oxy) { return cbase(c) + (c == 0 ? (oxy & 1) : (c == 1 ? (oxy >> 1) : 0)); }
+constexpr int NCUR = 5;
+
+struct Lane {
+  int gq, q;
+  int wofs[3];     // offset (doubles) of this lane's (wn, ws) chunk of axis a inside a record
+  int rowpos[3];   // block_pos(c, gq) with octant bits 0
+  int colpos[3];   // block_pos(c, 2 q) with octant bits 0 (2 q + 1 is the next position: i is the fastest index)
+};
+
+__device__ __forceinline__ const double2& ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// all groups of four particles of one octant segment: cnt particles whose records start at r0
+template <int OXY>
+__device__ __forceinline__ void octant_segment(const double* __restrict__ r0, int cnt, const Lane& L, double (&acc)[NMAT][2], double (&cur)[NCUR])
+{
+  for (int gs = 0; gs < cnt; gs += 4) {
+    const bool valid = gs + L.q < cnt;
+    const double* r = r0 + min(gs + L.q, cnt - 1) * FM_REC;  // clamp: operands of padded lanes stay finite
+    const double2 wx = ld2(r + L.wofs[0]), wy = ld2(r + L.wofs[1]), wz = ld2(r + L.wofs[2]);
+    // E-like CIC weights of corner gq (src/impls/ecsim/particles.cpp:129-131), z * y * x as the reference multiplies
+    double s[3];
+    s[0] = (wz.x * wy.x) * wx.y;
+    s[1] = (wz.x * wy.y) * wx.x;
+    s[2] = (wz.y * wy.x) * wx.x;
+    const double2 f0 = ld2(r + 6), f1 = ld2(r + 14), f2 = ld2(r + 16), f3 = ld2(r + 18), f4 = ld2(r + 20), f5 = ld2(r + 22);
+    const double al[9] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y, f4.x};
+    const double ip[3] = {f4.y, f5.x, f5.y};
+    double a[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a[c] = valid ? s[c] : 0.0;
+#pragma unroll
+    for (int c1 = 0; c1 < 3; ++c1) {
+#pragma unroll
+      for (int c2 = 0; c2 < 3; ++c2) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int v = vidx(c1 * 3 + c2, OXY);
+        dmma(acc[v][0], acc[v][1], a[c1], al[c1 * 3 + c2] * s[c2]);
+      }
+      // the current is a matrix-vector product (a DMMA would be 1/8 filled): every lane keeps s_c1(gq) I_c1 of
+      // its own particle, the four particles of a row are summed once per fold
+      cur[cidx(c1, OXY)] += a[c1] * ip[c1];
+    }
+  }
+}
+
+// fold register variants into the cell block.  ZDEP: the z-dependent slots (row or column component Z) and
+// the Z current, at octant bit OZ, and clear them; else the five z-independent slots and the X, Y currents.
+template <bool ZDEP, int OZ>
+__device__ __forceinline__ void fold(double* __restrict__ block, const Lane& L, double (&acc)[NMAT][2], double (&cur)[NCUR])
+{
+  constexpr int st[3] = {1, 2, 4};  // block_pos moves by this much per octant bit of the component's staggered axis
+  // variants of one slot may land on the same entry: one pass per variant index, all slots inside a pass
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+#pragma unroll
+    for (int sl = 0; sl < 9; ++sl) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      if (dep(sl, 2) != ZDEP || v >= nvar(sl)) continue;
+      const int c1 = sl / 3, c2 = sl % 3;
+      const int o1 = vbit(sl, v, c1, OZ), o2 = vbit(sl, v, c2, OZ);
+      double* e = block + sl * 144 + (L.rowpos[c1] + o1 * st[c1]) * 12 + L.colpos[c2] + o2 * st[c2];
+      const int k = vbase(sl) + v;
+      if (c2 == 0) {  // columns 2 q, 2 q + 1 are adjacent but not 16-byte aligned when ox = 1
+        e[0] += acc[k][0];
+        e[1] += acc[k][1];
+      }
+      else {
+        double2 t = *reinterpret_cast<double2*>(e);
+        t.x += acc[k][0];
+        t.y += acc[k][1];
+        *reinterpret_cast<double2*>(e) = t;
+      }
+      if (ZDEP) acc[k][0] = acc[k][1] = 0.0;
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if ((c == 2) != ZDEP || (c == 2 && v > 0)) continue;
+      const int k = cbase(c) + v;
+      double t = cur[k];
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      const int o = c == 2 ? OZ : v;
+      if (L.q == 0) block[BLOCK_MAT + c * 12 + L.rowpos[c] + o * st[c]] += t;
+      if (ZDEP) cur[k] = 0.0;
+    }
+    __syncwarp();
+  }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(FM_THREADS, MINB) k_cell_moments(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage, int zl_off)
+{
+  extern __shared__ __align__(16) double smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* block = smem + (size_t)wid * FM_CELL;
+  double* recs = block + FM_BLOCK;
+  double* Bt = recs + FM_CHUNK * FM_REC;
+  const int64_t cell_local = (int64_t)blockIdx.x * FM_CELLS + wid;
+
+  {
+    double2* b2 = reinterpret_cast<double2*>(block);
+#pragma unroll
+    for (int k = 0; k < FM_BLOCK / 64; ++k) b2[k * 32 + lane] = make_double2(0.0, 0.0);
+  }
+
+  if (cell_local < a.ncells) {
+    Lane L;
+    L.gq = lane >> 2;
+    L.q = lane & 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      L.wofs[c] = 2 * (c + 4 * ((L.gq >> c) & 1));
+      L.rowpos[c] = block_pos(c, L.gq, 0, 0, 0);
+      L.colpos[c] = block_pos(c, 2 * L.q, 0, 0, 0);
+    }
+    // the cells of one launch are whole planes (deposit_cells): owned planes or one ghost plane
+    const int pl = (int)(cell_local / g.plane), rem = (int)(cell_local % g.plane);
+    const int cy = rem / g.nx, cx = rem % g.nx, zl = pl + zl_off;
+    load_field_tile<1>(g, B, cx, cy, zl, Bt, lane, 32);
+    const int64_t bin0 = (a.bin_cell0 + cell_local) << 3;
+    const int32_t bs = lane < 9 ? a.bin_start[bin0 + lane] : 0;  // bin boundaries of the 8 octants
+    const int32_t p0 = __shfl_sync(0xffffffffu, bs, 0), p1 = __shfl_sync(0xffffffffu, bs, 8);
+    // the lower node of the cell as the reference's floor() gives it for every particle binned here
+    const double cxd = (double)cx, cyd = (double)cy, czd = (double)(zl + g.z0 - a.zshift);
+    const double f = (0.5 * g.dt) * a.q / a.m;
+
+    double acc[NMAT][2], cur[NCUR];
+#pragma unroll
+    for (int v = 0; v < NMAT; ++v) acc[v][0] = acc[v][1] = 0.0;
+#pragma unroll
+    for (int v = 0; v < NCUR; ++v) cur[v] = 0.0;
+
+    double pin[6];
+    auto fetch = [&](int32_t base) {
+      const int32_t i = base + lane;
+      if (i < p1) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) pin[k] = __ldg(a.p[k] + i);
+      }
+    };
+    if (p0 < p1) fetch(p0);
+    __syncwarp();  // the B tile is complete
+
+    int oct = 0;
+    int32_t oend = __shfl_sync(0xffffffffu, bs, 1);
+    bool zdone = false;
+    for (int32_t base = p0; base < p1; base += FM_CHUNK) {
+      const int n = min(FM_CHUNK, p1 - base);
+      // ---- records of this round: lane = particle -----------------------------------------------
+      {
+        int po = 0;  // octant of this lane's particle: number of bin boundaries at or below its index
+#pragma unroll
+        for (int k = 1; k < 8; ++k) po += (base + lane >= __shfl_sync(0xffffffffu, bs, k)) ? 1 : 0;
+        if (lane < n) {
+          Weights w;
+          const double cd[3] = {cxd, cyd, czd};
+          const double xn[3] = {to_cells(pin[0], g.dx, g.inv_dx, g.exact_inv & 1), to_cells(pin[1], g.dy, g.inv_dy, g.exact_inv & 2),
+                                to_cells(pin[2], g.dz, g.inv_dz, g.exact_inv & 4)};
+          const int ci[3] = {cx, cy, zl};
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            const int o = (po >> ax) & 1;
+            // src/impls/ecsim/particles.cpp:76-105 with floor(xn) = cell, floor(xn - 0.5) = cell - 1 + octant bit
+            w.in[ax] = ci[ax];
+            w.is[ax] = ci[ax] - 1 + o;
+            w.wn[ax][1] = xn[ax] - cd[ax];
+            w.wn[ax][0] = 1 - w.wn[ax][1];
+            w.ws[ax][1] = (xn[ax] - 0.5) - (cd[ax] - 1.0 + (double)o);
+            w.ws[ax][0] = 1 - w.ws[ax][1];
+          }
+          const TileIndex t = tile_index<1>(w, cx, cy, zl);
+          double Bp[3], b[3];
+          gather_B_tile<1>(Bt, w, t, Bp);
+          const double v[3] = {pin[3], pin[4], pin[5]};
+#pragma unroll
+          for (int c = 0; c < 3; ++c) b[c] = Bp[c] * f;
+          double vxb[3];
+          cross3(v, b, vxb);
+          const double vb = dot3(v, b), b2 = dot3(b, b);
+          const double cI = a.q * a.mpw / (1. + b2);
+          double ip[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) ip[c] = cI * (v[c] + vxb[c] + vb * b[c]);
+          const double Ap = 0.5 * g.dt * g.dt * a.mpw * a.q * a.q / a.m / (1 + b2);
+          double al[9];
+          al[0] = Ap * (1.0 + b[0] * b[0]);
+          al[1] = Ap * (+b[2] + b[0] * b[1]);
+          al[2] = Ap * (-b[1] + b[0] * b[2]);
+          al[3] = Ap * (-b[2] + b[1] * b[0]);
+          al[4] = Ap * (1.0 + b[1] * b[1]);
+          al[5] = Ap * (+b[0] + b[1] * b[2]);
+          al[6] = Ap * (+b[1] + b[2] * b[0]);
+          al[7] = Ap * (-b[0] + b[2] * b[1]);
+          al[8] = Ap * (1.0 + b[2] * b[2]);
+          double2* r = reinterpret_cast<double2*>(recs + lane * FM_REC);
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            r[ax] = make_double2(w.wn[ax][0], w.ws[ax][0]);
+            r[4 + ax] = make_double2(w.wn[ax][1], w.ws[ax][1]);
+          }
+          r[3] = make_double2(al[0], al[1]);
+          r[7] = make_double2(al[2], al[3]);
+          r[8] = make_double2(al[4], al[5]);
+          r[9] = make_double2(al[6], al[7]);
+          r[10] = make_double2(al[8], ip[0]);
+          r[11] = make_double2(ip[1], ip[2]);
+        }
+      }
+      __syncwarp();
+      if (base + FM_CHUNK < p1) fetch(base + FM_CHUNK);  // the next round's particles travel during the MMA phase
+      // ---- rank-1 updates, octant segment by octant segment -------------------------------------
+      int32_t pos = base;
+      const int32_t cend = base + n;
+      while (pos < cend) {
+        while (oend <= pos) {  // the octant's particles are exhausted (warp-uniform)
+          ++oct;
+          oend = __shfl_sync(0xffffffffu, bs, oct + 1);
+        }
+        if (oct >= 4 && !zdone) {  // first particle with oz = 1: the z-dependent slots change their place
+          fold<true, 0>(block, L, acc, cur);
+          zdone = true;
+        }
+        const int32_t seg_end = min(oend, cend);
+        const double* r0 = recs + (pos - base) * FM_REC;
+        const int cnt = seg_end - pos;
+        switch (oct & 3) {
+          case 0: octant_segment<0>(r0, cnt, L, acc, cur); break;
+          case 1: octant_segment<1>(r0, cnt, L, acc, cur); break;
+          case 2: octant_segment<2>(r0, cnt, L, acc, cur); break;
+          default: octant_segment<3>(r0, cnt, L, acc, cur); break;
+        }
+        pos = seg_end;
+      }
+      __syncwarp();  // the records may be overwritten by the next round
+    }
+    if (p0 < p1) {
+      if (zdone)
+        fold<true, 1>(block, L, acc, cur);
+      else
+        fold<true, 0>(block, L, acc, cur);
+      fold<false, 0>(block, L, acc, cur);
+    }
+  }
+  __syncthreads();
+  // coalesced write-out of the CTA's four blocks: stage[group][entry][cell % 4]
+  double* out = stage + ((a.stage_cell0 / CELL_GROUP) + blockIdx.x) * (int64_t)(BLOCK_ALL * CELL_GROUP);
+  for (int idx = threadIdx.x; idx < BLOCK_ALL * CELL_GROUP; idx += FM_THREADS) {
+    const int e = idx / CELL_GROUP, w = idx % CELL_GROUP;
+    out[idx] = smem[(size_t)w * FM_CELL + e];
+  }
+}
+
+}  // namespace
+
+int launch_cell_moments(xb_ctx* c, const DepositArgs& a, int zl_off, int occupancy)
+{
+  const size_t smem = sizeof(double) * FM_CELL * FM_CELLS;
+  if (!c->fused_attr_set) {
+    XB_CUDA(cudaFuncSetAttribute(k_cell_moments<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XB_CUDA(cudaFuncSetAttribute(k_cell_moments<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c->fused_attr_set = true;
+  }
+  const int groups = (int)((a.ncells + FM_CELLS - 1) / FM_CELLS);
+  if (occupancy == 2)
+    XB_LAUNCH(c, k_cell_moments<2>, groups, FM_THREADS, smem, c->g, a, c->B, c->stage, zl_off);
+  else
+    XB_LAUNCH(c, k_cell_moments<3>, groups, FM_THREADS, smem, c->g, a, c->B, c->stage, zl_off);
+  return 0;
+}
+
+}  // namespace xb

@@ -32,7 +32,6 @@ int species_alloc(xb_ctx* c, Species& s, int64_t capacity)
     if (c->track_ids) XB_CUDA(cudaMalloc(&s.id[b], sizeof(uint64_t) * capacity));
   }
   XB_CUDA(cudaMalloc(&s.key, sizeof(int32_t) * capacity));
-  XB_CUDA(cudaMalloc(&s.rec, sizeof(double) * 12 * capacity));
   XB_CUDA(cudaMalloc(&s.bin_start, sizeof(int32_t) * (c->nbins + 1)));
   XB_CUDA(cudaMemset(s.bin_start, 0, sizeof(int32_t) * (c->nbins + 1)));
   XB_CUDA(cudaMalloc(&s.currI, sizeof(double) * c->g.ntot));

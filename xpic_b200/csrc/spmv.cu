@@ -100,26 +100,15 @@ int spmv(xb_ctx* c, int op, double* x, double* y)
   XB_CHECK(halo_fill(c, x, (op & XB_OP_L) ? 2 : 1));
   const int tiles_x = (g.nx + TX - 1) / TX, tiles_y = (g.ny + TY - 1) / TY, tiles_z = (g.nzl + TZ - 1) / TZ;
   const int grid = tiles_x * tiles_y * tiles_z;
-  const bool prof = c->spmv_profile && (op & XB_OP_L);
-  if (prof) {
-    if (c->spmv_events_used + 2 > c->spmv_events.size())
-      for (int i = 0; i < 512; ++i) {
-        cudaEvent_t e;
-        XB_CUDA(cudaEventCreate(&e));
-        c->spmv_events.push_back(e);
-      }
-    XB_CUDA(cudaEventRecord(c->spmv_events[c->spmv_events_used], c->stream));
-  }
+  const bool prof = (op & XB_OP_L) != 0;
+  if (prof) XB_CHECK(prof_begin(c, XB_FAMILY_SPMV));
   switch (op) {
     case XB_OP_L: XB_LAUNCH(c, k_spmv<XB_OP_L>, grid, TX * TY * TZ, 0, g, c->coef, x, y, tiles_x, tiles_y); break;
     case XB_OP_M: XB_LAUNCH(c, k_spmv<XB_OP_M>, grid, TX * TY * TZ, 0, g, c->coef, x, y, tiles_x, tiles_y); break;
     case XB_OP_A: XB_LAUNCH(c, k_spmv<XB_OP_A>, grid, TX * TY * TZ, 0, g, c->coef, x, y, tiles_x, tiles_y); break;
     default: XB_FAIL("spmv: unknown operator selector");
   }
-  if (prof) {
-    XB_CUDA(cudaEventRecord(c->spmv_events[c->spmv_events_used + 1], c->stream));
-    c->spmv_events_used += 2;
-  }
+  if (prof) XB_CHECK(prof_end(c, XB_FAMILY_SPMV));
   return 0;
 }
 

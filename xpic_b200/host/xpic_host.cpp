@@ -332,8 +332,10 @@ int Simulation::initialize()
   }
   if (diagnose_momentum(start)) return 1;
   if (diagnose_fields(start)) return 1;
+  // the backup is the last diagnostic of the reference's list: its copy of temporal/ already holds row `start`
+  if (diagnose_energy(start)) return 1;
   if (backup_period_ > 0 && save_backup(start)) return 1;
-  return diagnose_energy(start);
+  return 0;
 }
 
 // FieldView::diagnose (src/diagnostics/field_view.cpp:98-118): float32 image of the whole vector in
