@@ -51,39 +51,50 @@ __global__ void __launch_bounds__(256) k_fp64(int iters, double seed, double* ou
   if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
 
-// shared-memory probe: every lane issues `iters` x 8 loads of WIDTH bytes with the address pattern PAT
-//   PAT 0: all lanes distinct, consecutive (the bandwidth floor: WIDTH * 32 / 128 wavefronts)
-//   PAT 1: the weight load of k_cell_moments: lane (gq, q) reads the 16-byte chunk (4 * (gq & 1)) of record q
-//          (records 13 chunks apart): 8 distinct chunks in 8 different bank groups
-//   PAT 2: the alpha load: chunk 3 of record q: 4 distinct chunks
-template <int PAT>
-__global__ void __launch_bounds__(256) k_lds(int iters, double* out, long long* cycles)
+// shared-memory probe: every lane issues `iters` x 8 loads of W bytes (4, 8 or 16) with the address pattern PAT
+//   PAT 0: all lanes distinct, consecutive
+//   PAT 1: the weight load of k_cell_moments: lane (gq, q) reads a chunk of record q that depends on a bit of gq
+//          (records 13 x 16 bytes apart): 8 distinct addresses
+//   PAT 2: the alpha load: one chunk of record q: 4 distinct addresses (8 lanes share each)
+// Result: cycles of the SM's shared-memory pipe per warp-wide load (one CTA of 8 warps per SM keeps it busy).
+template <int W, int PAT>
+__global__ void __launch_bounds__(256) k_lds(int iters, double* out)
 {
   __shared__ __align__(16) double sm[8 * 480];
   for (int i = threadIdx.x; i < 8 * 480; i += blockDim.x) sm[i] = i * 1e-3;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, gq = lane >> 2, q = lane & 3;
-  const double* base = sm + wid * 480;
-  int ofs;
+  const char* base = reinterpret_cast<const char*>(sm + wid * 480);
+  int ofs;  // bytes
   if (PAT == 0)
-    ofs = 2 * lane;
+    ofs = W * lane;
   else if (PAT == 1)
-    ofs = q * 26 + 2 * (4 * (gq & 1));
+    ofs = q * 208 + 64 * (gq & 1);
   else
-    ofs = q * 26 + 6;
-  double2 s = make_double2(0.0, 0.0);
-  const long long t0 = clock64();
+    ofs = q * 208 + 48;
+  // integer accumulators, one per load of the unrolled body: no dependent fp64 chain limits the issue rate
+  unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const double2 v = *reinterpret_cast<const double2*>(base + ofs + ((i + k) & 3) * 104);
-      s.x += v.x;
-      s.y += v.y;
+      const char* p = base + ofs + ((i + k) & 3) * 832;
+      if (W == 16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        acc[k] += v.x ^ v.y ^ v.z ^ v.w;
+      }
+      else if (W == 8) {
+        const uint2 v = *reinterpret_cast<const uint2*>(p);
+        acc[k] += v.x ^ v.y;
+      }
+      else {
+        acc[k] += *reinterpret_cast<const unsigned*>(p);
+      }
     }
   }
-  const long long t1 = clock64();
-  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s.x + s.y;
-  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+  unsigned t = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t ^= acc[k];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = (double)t;
 }
 
 template <class K>
@@ -139,35 +150,45 @@ int main()
   const double mix_dfma_tf = 2.0 * nthreads * iters * 8 / (ms[2] * 1e-3) / 1e12;
   // 16 warps per SM = 4 per sub-partition: cycles one sub-partition spends per instruction
   const double warps_per_smsp = 8.0 * threads / 32 / 4;
-  const double dfma_cyc = cycles[0] / (iters * 8.0 * warps_per_smsp);
-  const double dmma_cyc = cycles[1] / (iters * 8.0 * warps_per_smsp);
-  const double mix_cyc = cycles[2] / (iters * 8.0 * warps_per_smsp);
+  const double hz = khz * 1e3;  // cycles from the event time at the maximum SM clock (the clocks line of bench.py shows the GPU holds it)
+  const double dfma_cyc = ms[0] * 1e-3 * hz / (iters * 8.0 * warps_per_smsp);
+  const double dmma_cyc = ms[1] * 1e-3 * hz / (iters * 8.0 * warps_per_smsp);
+  const double mix_cyc = ms[2] * 1e-3 * hz / (iters * 8.0 * warps_per_smsp);
+  (void)cycles;
 
-  float lms[3];
-  long long lcyc[3];
+  // nine probes: widths 4 / 8 / 16 bytes x patterns 0 / 1 / 2
+  float lms[9];
   const int liters = 4000;
-  for (int pat = 0; pat < 3; ++pat) {
+  for (int t = 0; t < 9; ++t) {
     auto launch = [&]() {
-      if (pat == 0) k_lds<0><<<sms, 256>>>(liters, out, cyc);
-      if (pat == 1) k_lds<1><<<sms, 256>>>(liters, out, cyc);
-      if (pat == 2) k_lds<2><<<sms, 256>>>(liters, out, cyc);
+      switch (t) {
+        case 0: k_lds<4, 0><<<sms, 256>>>(liters, out); break;
+        case 1: k_lds<4, 1><<<sms, 256>>>(liters, out); break;
+        case 2: k_lds<4, 2><<<sms, 256>>>(liters, out); break;
+        case 3: k_lds<8, 0><<<sms, 256>>>(liters, out); break;
+        case 4: k_lds<8, 1><<<sms, 256>>>(liters, out); break;
+        case 5: k_lds<8, 2><<<sms, 256>>>(liters, out); break;
+        case 6: k_lds<16, 0><<<sms, 256>>>(liters, out); break;
+        case 7: k_lds<16, 1><<<sms, 256>>>(liters, out); break;
+        default: k_lds<16, 2><<<sms, 256>>>(liters, out); break;
+      }
     };
-    if (time_kernel(launch, &lms[pat])) return 1;
-    CK(cudaMemcpy(&lcyc[pat], cyc, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (time_kernel(launch, &lms[t])) return 1;
   }
-  // one CTA of 8 warps per SM: cycles the SM's shared-memory pipe spends per warp-wide 128-bit load
-  double lds_cyc[3];
-  for (int pat = 0; pat < 3; ++pat) lds_cyc[pat] = lcyc[pat] / (liters * 8.0 * 8.0);
+  // one CTA of 8 warps per SM: SM cycles (at the maximum clock) per warp-wide load
+  double lds_cyc[9];
+  for (int t = 0; t < 9; ++t) lds_cyc[t] = lms[t] * 1e-3 * khz * 1e3 / (liters * 8.0 * 8.0);
 
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"sm_clock_mhz_max\": %.0f, "
          "\"dfma_tflops\": %.3f, \"dmma_tflops\": %.3f, \"mixed_dmma_tflops\": %.3f, \"mixed_dfma_tflops\": %.3f, "
          "\"cycles_per_dfma_per_smsp\": %.3f, \"cycles_per_dmma_per_smsp\": %.3f, \"cycles_per_dmma_plus_dfma_per_smsp\": %.3f, "
          "\"ms\": [%.4f, %.4f, %.4f], "
-         "\"lds128_cycles_per_warp_load\": {\"all_distinct\": %.3f, \"weights_8_chunks\": %.3f, \"alpha_4_chunks\": %.3f}, "
+         "\"lds_cycles_per_warp_load\": {\"b32\": [%.3f, %.3f, %.3f], \"b64\": [%.3f, %.3f, %.3f], \"b128\": [%.3f, %.3f, %.3f], "
+         "\"patterns\": \"all lanes distinct | 8 distinct addresses | 4 distinct addresses (8 lanes each)\"}, "
          "\"how\": \"%d CTAs x %d threads, %d iterations x 8 independent chains per thread; best of 5 launches, CUDA events; "
-         "cycles from clock64() of one thread\"}\n",
+         "cycles = event time x maximum SM clock\"}\n",
          prop.name, sms, khz / 1e3, dfma_tf, dmma_tf, mix_dmma_tf, mix_dfma_tf, dfma_cyc, dmma_cyc, mix_cyc, ms[0], ms[1], ms[2], lds_cyc[0], lds_cyc[1],
-         lds_cyc[2], blocks, threads, iters);
+         lds_cyc[2], lds_cyc[3], lds_cyc[4], lds_cyc[5], lds_cyc[6], lds_cyc[7], lds_cyc[8], blocks, threads, iters);
   cudaFree(out);
   cudaFree(cyc);
   return 0;

@@ -13,6 +13,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -39,6 +40,7 @@ int load_api()
   XB_SYM(CommInitRank, "ncclCommInitRank");
   XB_SYM(CommDestroy, "ncclCommDestroy");
   XB_SYM(AllReduce, "ncclAllReduce");
+  XB_SYM(AllGather, "ncclAllGather");
   XB_SYM(Send, "ncclSend");
   XB_SYM(Recv, "ncclRecv");
   XB_SYM(GroupStart, "ncclGroupStart");
@@ -96,33 +98,42 @@ void comm_free(xb_ctx* c)
 }
 
 int comm_exchange(xb_ctx* c, const void* to_down, size_t n_to_down, const void* to_up, size_t n_to_up, void* from_up,
-                  size_t n_from_up, void* from_down, size_t n_from_down)
+                  size_t n_from_up, void* from_down, size_t n_from_down, cudaStream_t stream)
 {
   Comm* cm = c->comm;
+  if (!stream) stream = c->stream;
   XB_NCCL(api.GroupStart());
   // order matters when up == down (two ranks): first message = low planes -> peer's high side
-  if (n_to_down) XB_NCCL(api.Send(to_down, n_to_down, ncclUint8, cm->down, cm->comm, c->stream));
-  if (n_to_up) XB_NCCL(api.Send(to_up, n_to_up, ncclUint8, cm->up, cm->comm, c->stream));
-  if (n_from_up) XB_NCCL(api.Recv(from_up, n_from_up, ncclUint8, cm->up, cm->comm, c->stream));
-  if (n_from_down) XB_NCCL(api.Recv(from_down, n_from_down, ncclUint8, cm->down, cm->comm, c->stream));
+  if (n_to_down) XB_NCCL(api.Send(to_down, n_to_down, ncclUint8, cm->down, cm->comm, stream));
+  if (n_to_up) XB_NCCL(api.Send(to_up, n_to_up, ncclUint8, cm->up, cm->comm, stream));
+  if (n_from_up) XB_NCCL(api.Recv(from_up, n_from_up, ncclUint8, cm->up, cm->comm, stream));
+  if (n_from_down) XB_NCCL(api.Recv(from_down, n_from_down, ncclUint8, cm->down, cm->comm, stream));
   XB_NCCL(api.GroupEnd());
   return 0;
 }
 
-int comm_exchange_list(xb_ctx* c, const ExchangeList& l)
+int comm_allgather(xb_ctx* c, void* buf, size_t bytes, cudaStream_t stream)
+{
+  if (!stream) stream = c->stream;
+  XB_NCCL(api.AllGather(static_cast<const char*>(buf) + (size_t)c->g.rank * bytes, buf, bytes, ncclUint8, c->comm->comm, stream));
+  return 0;
+}
+
+int comm_exchange_list(xb_ctx* c, const ExchangeList& l, cudaStream_t stream)
 {
   Comm* cm = c->comm;
+  if (!stream) stream = c->stream;
   XB_NCCL(api.GroupStart());
   // same ordering rule as comm_exchange: everything for `down` first, then everything for `up`;
   // receives from `up` first, then from `down` (keeps message order consistent when up == down)
   for (int i = 0; i < l.n; ++i)
-    if (l.n_to_down[i]) XB_NCCL(api.Send(l.to_down[i], l.n_to_down[i], ncclUint8, cm->down, cm->comm, c->stream));
+    if (l.n_to_down[i]) XB_NCCL(api.Send(l.to_down[i], l.n_to_down[i], ncclUint8, cm->down, cm->comm, stream));
   for (int i = 0; i < l.n; ++i)
-    if (l.n_to_up[i]) XB_NCCL(api.Send(l.to_up[i], l.n_to_up[i], ncclUint8, cm->up, cm->comm, c->stream));
+    if (l.n_to_up[i]) XB_NCCL(api.Send(l.to_up[i], l.n_to_up[i], ncclUint8, cm->up, cm->comm, stream));
   for (int i = 0; i < l.n; ++i)
-    if (l.n_from_up[i]) XB_NCCL(api.Recv(l.from_up[i], l.n_from_up[i], ncclUint8, cm->up, cm->comm, c->stream));
+    if (l.n_from_up[i]) XB_NCCL(api.Recv(l.from_up[i], l.n_from_up[i], ncclUint8, cm->up, cm->comm, stream));
   for (int i = 0; i < l.n; ++i)
-    if (l.n_from_down[i]) XB_NCCL(api.Recv(l.from_down[i], l.n_from_down[i], ncclUint8, cm->down, cm->comm, c->stream));
+    if (l.n_from_down[i]) XB_NCCL(api.Recv(l.from_down[i], l.n_from_down[i], ncclUint8, cm->down, cm->comm, stream));
   XB_NCCL(api.GroupEnd());
   return 0;
 }

@@ -17,7 +17,9 @@ int comm_allreduce_sum(xb_ctx* c, double* dev, int n);
 // Exchange byte buffers with the z neighbours: `to_down`/`to_up` are sent, `from_up`/`from_down`
 // received (sizes in bytes, known on both sides).
 int comm_exchange(xb_ctx* c, const void* to_down, size_t n_to_down, const void* to_up, size_t n_to_up, void* from_up,
-                  size_t n_from_up, void* from_down, size_t n_from_down);
+                  size_t n_from_up, void* from_down, size_t n_from_down, cudaStream_t stream = nullptr);
+// every rank contributes `bytes` bytes at buf + rank * bytes and receives all ranks' contributions (in place)
+int comm_allgather(xb_ctx* c, void* buf, size_t bytes, cudaStream_t stream = nullptr);
 // The same for lists of buffers (particle SoA segments), all inside one NCCL group.
 struct ExchangeList {
   int n = 0;
@@ -27,7 +29,7 @@ struct ExchangeList {
   void* from_down[16];
   size_t n_to_down[16], n_to_up[16], n_from_up[16], n_from_down[16];
 };
-int comm_exchange_list(xb_ctx* c, const ExchangeList& l);
+int comm_exchange_list(xb_ctx* c, const ExchangeList& l, cudaStream_t stream = nullptr);
 int add_planes(xb_ctx* c, double* dst, const double* src, int64_t n);  // fields.cu
 
 }  // namespace xb

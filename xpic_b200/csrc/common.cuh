@@ -101,12 +101,16 @@ struct MigrateBuffers {  // multi-rank only (migrate.cu)
   double* send[2][7] = {{nullptr}};   // [0] to the rank below, [1] to the rank above; 6 SoA arrays + ids
   double* recv[2][7] = {{nullptr}};   // [0] from below, [1] from above
   double* ghost[2][6] = {{nullptr}};  // copies of the neighbours' boundary-plane particles
-  double* ghost_rec[2] = {nullptr, nullptr};  // their field records, SoA [12][ghost_cap]
-  int32_t* ghost_bins[2] = {nullptr, nullptr};
+  double* ghost_rec[2] = {nullptr, nullptr};  // their field records, SoA [12][ghost_cap] (cross-check pipeline only)
+  int32_t* ghost_bins[2] = {nullptr, nullptr};      // their bin tables, rebased to the copy
+  int32_t* ghost_bins_raw[2] = {nullptr, nullptr};  // as received (offsets into the owner's arrays)
   int32_t* recv_key[2] = {nullptr, nullptr};
   int64_t cap = 0, ghost_cap = 0;
-  unsigned long long* counts_dev = nullptr;
-  unsigned long long* counts_host = nullptr;
+  int64_t nghost[2] = {0, 0};
+  unsigned long long* counts_dev = nullptr;  // [0], [1] leavers down / up of this sort; [2] particles lost so far
+  unsigned long long* table_dev = nullptr;   // all-gathered rows of counts and limits, one per rank
+  unsigned long long* table_host = nullptr;  // pinned
+  cudaEvent_t sorted = nullptr, ghosts_here = nullptr;
 };
 
 struct Species {
@@ -142,6 +146,7 @@ struct StageClock {
 struct xb_ctx {
   xb::Grid g;
   int device = 0;
+  int sm_count = 0;
   bool track_ids = false;
   bool deterministic = false;  // canonical particle order inside every bin even without ids (costs one more pass)
   cudaStream_t stream = nullptr;
@@ -213,6 +218,7 @@ int build_rhs(xb_ctx* c, const double* curr, double* rhs);       // 2E - dt curr
 int final_update(xb_ctx* c, const double* Ehalf);                // E = 2 Eh - E ; B -= dt curl^+ Eh
 int dots(xb_ctx* c, int nv, const double* const* vs, const double* w, double* host_out);  // host_out[i] = vs[i].w
 int axpy_multi(xb_ctx* c, int nv, const double* const* vs, const double* coef_host, double* w);  // w += sum coef_i vs_i
+int axpy_multi_scaled(xb_ctx* c, int nv, const double* const* vs, const double* coef_host, double* w, double alpha);  // w = alpha (w + sum coef_i vs_i)
 int scale_into(xb_ctx* c, const double* w, double alpha, double* out);                            // out = alpha w
 int axpby(xb_ctx* c, double a, const double* x, double b, double* y);                             // y = a x + b y
 int upload_owned(xb_ctx* c, const double* host, double* dev);

@@ -574,7 +574,10 @@ static int launch_gather(xb_ctx* c, const GatherArgs& ga, int accumulate)
   return 0;
 }
 
-int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage);  // migrate.cu (multi-rank only)
+// migrate.cu (multi-rank only)
+int ghost_exchange_mark(xb_ctx* c, Species& s);
+int ghost_exchange_begin(xb_ctx* c, Species& s);
+int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage);
 
 // cell blocks of `ncells` consecutive cells (bin space) into the staging area
 int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* bin_start, int64_t bin_cell0, int64_t ncells, int64_t stage_cell0,
@@ -593,6 +596,9 @@ int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* 
   a.q = s.q;
   a.m = s.m;
   a.mpw = s.n / (double)s.Np;
+  a.f_beta = (0.5 * c->g.dt) * a.q / a.m;
+  a.num_A = 0.5 * c->g.dt * c->g.dt * a.mpw * a.q * a.q / a.m;
+  a.num_I = a.q * a.mpw;
   a.rec = nullptr;
   a.rec_stride = rec_stride;
   if ((a.stage_cell0 % CELL_GROUP) != 0) XB_FAIL("deposit: plane size must be a multiple of the staging group in multi-rank runs");
@@ -633,8 +639,13 @@ int deposit_moments(xb_ctx* c)
   for (auto& s : c->sorts) {
     if (!s.sorted) XB_FAIL("deposit: particles are not sorted");
     // bin plane 1 = first owned plane; staging plane 0 is the low ghost plane in multi-rank runs
+    if (!single) XB_CHECK(ghost_exchange_mark(c, s));
     XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane, g.ncl, single ? 0 : g.plane, 0, &s.rec, s.capacity, s.count));
-    if (!single) XB_CHECK(deposit_ghost_cells(c, s, c->stage));
+    if (!single) {
+      // the boundary-plane particles of the z neighbours travel (copy stream) while the owned planes are computed
+      XB_CHECK(ghost_exchange_begin(c, s));
+      XB_CHECK(deposit_ghost_cells(c, s, c->stage));
+    }
     GatherArgs ga{c->stage, single ? 1 : 0};
     const int acc = first ? 0 : 1;
     XB_CHECK((launch_gather<0, 0>(c, ga, acc)));

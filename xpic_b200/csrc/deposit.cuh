@@ -23,6 +23,9 @@ struct DepositArgs {
   int64_t stage_cell0;  // staging cell id of the first cell
   int zshift;
   double q, m, mpw;
+  // particle-independent factors of src/impls/ecsim/particles.cpp:107-115, rounded as the reference rounds them:
+  // beta = B_p * f_beta; A_p = num_A / (1 + beta^2); I_p = num_I / (1 + beta^2) * (...)
+  double f_beta, num_A, num_I;
   double* rec;         // per-particle field record, SoA [12][rec_stride]: A_p alpha (9), I_p (3)
   int64_t rec_stride;
 };

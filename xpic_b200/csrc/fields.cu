@@ -311,19 +311,20 @@ struct Coefs {
   double a[8];
 };
 
+// w = alpha * (w + sum_k a_k v_k)
 template <int NV>
-__global__ void k_axpy_multi(VecPtrs vs, Coefs cf, double* __restrict__ w, int64_t n)
+__global__ void k_axpy_multi(VecPtrs vs, Coefs cf, double* __restrict__ w, int64_t n, double alpha)
 {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     double s = w[i];
 #pragma unroll
     for (int k = 0; k < NV; ++k) s += cf.a[k] * vs.v[k][i];
-    w[i] = s;
+    w[i] = alpha * s;
   }
 }
 
 template <int NV>
-static int launch_axpy(xb_ctx* c, const double* const* vs, const double* cf, double* w)
+static int launch_axpy(xb_ctx* c, const double* const* vs, const double* cf, double* w, double alpha)
 {
   VecPtrs p;
   Coefs a;
@@ -331,27 +332,31 @@ static int launch_axpy(xb_ctx* c, const double* const* vs, const double* cf, dou
     p.v[i] = i < NV ? vs[i] + c->g.own0 : nullptr;
     a.a[i] = i < NV ? cf[i] : 0.0;
   }
-  XB_LAUNCH(c, k_axpy_multi<NV>, grid_for(c->g.nown), 256, 0, p, a, w + c->g.own0, c->g.nown);
+  XB_LAUNCH(c, k_axpy_multi<NV>, grid_for(c->g.nown), 256, 0, p, a, w + c->g.own0, c->g.nown, alpha);
   return 0;
 }
 
-int axpy_multi(xb_ctx* c, int nv, const double* const* vs, const double* cf, double* w)
+// w = alpha * (w + sum coef_i vs_i): the projection and the normalisation of a Gram-Schmidt step in one pass
+int axpy_multi_scaled(xb_ctx* c, int nv, const double* const* vs, const double* cf, double* w, double alpha)
 {
   for (int s = 0; s < nv; s += 8) {
     const int m = nv - s < 8 ? nv - s : 8;
+    const double al = s + 8 >= nv ? alpha : 1.0;  // the scale rides on the last chunk
     switch (m) {
-      case 1: XB_CHECK(launch_axpy<1>(c, vs + s, cf + s, w)); break;
-      case 2: XB_CHECK(launch_axpy<2>(c, vs + s, cf + s, w)); break;
-      case 3: XB_CHECK(launch_axpy<3>(c, vs + s, cf + s, w)); break;
-      case 4: XB_CHECK(launch_axpy<4>(c, vs + s, cf + s, w)); break;
-      case 5: XB_CHECK(launch_axpy<5>(c, vs + s, cf + s, w)); break;
-      case 6: XB_CHECK(launch_axpy<6>(c, vs + s, cf + s, w)); break;
-      case 7: XB_CHECK(launch_axpy<7>(c, vs + s, cf + s, w)); break;
-      default: XB_CHECK(launch_axpy<8>(c, vs + s, cf + s, w)); break;
+      case 1: XB_CHECK(launch_axpy<1>(c, vs + s, cf + s, w, al)); break;
+      case 2: XB_CHECK(launch_axpy<2>(c, vs + s, cf + s, w, al)); break;
+      case 3: XB_CHECK(launch_axpy<3>(c, vs + s, cf + s, w, al)); break;
+      case 4: XB_CHECK(launch_axpy<4>(c, vs + s, cf + s, w, al)); break;
+      case 5: XB_CHECK(launch_axpy<5>(c, vs + s, cf + s, w, al)); break;
+      case 6: XB_CHECK(launch_axpy<6>(c, vs + s, cf + s, w, al)); break;
+      case 7: XB_CHECK(launch_axpy<7>(c, vs + s, cf + s, w, al)); break;
+      default: XB_CHECK(launch_axpy<8>(c, vs + s, cf + s, w, al)); break;
     }
   }
   return 0;
 }
+
+int axpy_multi(xb_ctx* c, int nv, const double* const* vs, const double* cf, double* w) { return axpy_multi_scaled(c, nv, vs, cf, w, 1.0); }
 
 __global__ void k_scale_into(const double* __restrict__ w, double alpha, double* __restrict__ out, int64_t n)
 {

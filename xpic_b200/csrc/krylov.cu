@@ -112,6 +112,7 @@ int gmres(xb_ctx* c, int which, int op, const double* b, double* x)
   const int deg = sv.precond;
 
   std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gg(m + 1), y(m), h(m + 2), h2(m + 2);
+  std::vector<const double*> vlist(m + 2);
   double* r = c->tmp;  // residual workspace (callers pass b = c->rhs)
   double* wr = c->cheb_r;
   double* wd = c->cheb_d;
@@ -147,23 +148,46 @@ int gmres(xb_ctx* c, int which, int op, const double* b, double* x)
       else {
         XB_CHECK(spmv(c, op, c->V[k], w));
       }
-      // classical Gram-Schmidt: all k + 1 projections in one pass
-      XB_CHECK(dots(c, k + 1, c->V.data(), w, h.data()));
-      for (int i = 0; i <= k; ++i) h2[i] = -h[i];
-      XB_CHECK(axpy_multi(c, k + 1, c->V.data(), h2.data(), w));
+      double hn = 0.0;
       if (refine) {
+        // parity-grade solves: classical Gram-Schmidt twice, explicit norm (three reductions per iteration)
+        XB_CHECK(dots(c, k + 1, c->V.data(), w, h.data()));
+        for (int i = 0; i <= k; ++i) h2[i] = -h[i];
+        XB_CHECK(axpy_multi(c, k + 1, c->V.data(), h2.data(), w));
         std::vector<double> hc(k + 1);
         XB_CHECK(dots(c, k + 1, c->V.data(), w, hc.data()));
         for (int i = 0; i <= k; ++i) { h[i] += hc[i]; hc[i] = -hc[i]; }
         XB_CHECK(axpy_multi(c, k + 1, c->V.data(), hc.data(), w));
+        const double* ww[1] = {w};
+        double hn2 = 0.0;
+        XB_CHECK(dots(c, 1, ww, w, &hn2));
+        hn = std::sqrt(hn2);
+        if (hn > 0.0) XB_CHECK(scale_into(c, w, 1.0 / hn, w));
       }
-      const double* ww[1] = {w};
-      double hn2 = 0.0;
-      XB_CHECK(dots(c, 1, ww, w, &hn2));
-      const double hn = std::sqrt(hn2);
+      else {
+        // classical Gram-Schmidt with ONE reduction per iteration: the k + 1 projections and |w|^2 in the same pass
+        // over the basis; |w - sum h_i V_i|^2 = |w|^2 - sum h_i^2 because the V_i are orthonormal, so the projection
+        // and the normalisation are one more pass (w = (w - sum h_i V_i) / hn)
+        for (int i = 0; i <= k; ++i) vlist[i] = c->V[i];
+        vlist[k + 1] = w;
+        XB_CHECK(dots(c, k + 2, vlist.data(), w, h.data()));
+        double hn2 = h[k + 1];
+        for (int i = 0; i <= k; ++i) hn2 -= h[i] * h[i];
+        for (int i = 0; i <= k; ++i) h2[i] = -h[i];
+        if (hn2 > 1e-10 * h[k + 1]) {
+          hn = std::sqrt(hn2);
+          XB_CHECK(axpy_multi_scaled(c, k + 1, c->V.data(), h2.data(), w, 1.0 / hn));
+        }
+        else {  // w lies in the span of the basis to 1e-5: the difference above has lost its digits, take the norm explicitly
+          XB_CHECK(axpy_multi(c, k + 1, c->V.data(), h2.data(), w));
+          const double* ww[1] = {w};
+          XB_CHECK(dots(c, 1, ww, w, &hn2));
+          hn = std::sqrt(hn2);
+          if (hn > 0.0) XB_CHECK(scale_into(c, w, 1.0 / hn, w));
+        }
+      }
       for (int i = 0; i <= k; ++i) H[(size_t)i * m + k] = h[i];
       H[(size_t)(k + 1) * m + k] = hn;
-      if (hn > 0.0) XB_CHECK(scale_into(c, w, 1.0 / hn, w));
       for (int i = 0; i < k; ++i) {
         const double t = cs[i] * H[(size_t)i * m + k] + sn[i] * H[(size_t)(i + 1) * m + k];
         H[(size_t)(i + 1) * m + k] = -sn[i] * H[(size_t)i * m + k] + cs[i] * H[(size_t)(i + 1) * m + k];

@@ -31,10 +31,11 @@ constexpr int FM_THREADS = 32 * FM_CELLS;
 constexpr int FM_CHUNK = 32;               // particles per record round: one per lane
 constexpr int FM_REC = 26;                 // doubles per record = 13 chunks of 16 bytes (odd: conflict-free 128-bit stores)
 constexpr int FM_BLOCK = 1344;             // BLOCK_ALL = 1332 padded to 21 x 32 double2
-constexpr int FM_TILE = 88;                // 3 x 3 x 3 nodes x 3 components of B (81), padded
-constexpr int FM_CELL = FM_BLOCK + FM_CHUNK * FM_REC + FM_TILE;  // 2264 doubles = 18 112 B per cell
+constexpr int FM_TILE = 94;                // 3 x 3 x 3 nodes x 3 components of B (81), padded
+// per cell: block, 32 records + one all-zero record (the operand of padded lanes), B tile: 2296 doubles = 18 368 B
+constexpr int FM_CELL = FM_BLOCK + (FM_CHUNK + 1) * FM_REC + FM_TILE;
 static_assert(FM_BLOCK >= BLOCK_ALL && FM_BLOCK % 64 == 0, "block padding");
-static_assert(FM_CELL % 16 == 8, "write-out reads the four blocks of a CTA without bank conflicts");
+static_assert(FM_CELL % 16 == 8 && FM_CELL % 2 == 0, "write-out reads the four blocks of a CTA without bank conflicts");
 static_assert(FM_REC % 2 == 0 && (FM_REC / 2) % 2 == 1, "records are an odd number of 16-byte chunks");
 
 // record layout in 16-byte chunks:
@@ -92,11 +93,11 @@ __device__ __forceinline__ const double2& ld2(const double* p) { return *reinter
 
 // all groups of four particles of one octant segment: cnt particles whose records start at r0
 template <int OXY>
-__device__ __forceinline__ void octant_segment(const double* __restrict__ r0, int cnt, const Lane& L, double (&acc)[NMAT][2], double (&cur)[NCUR])
+__device__ __forceinline__ void octant_segment(const double* __restrict__ r0, const double* __restrict__ zero_rec, int cnt, const Lane& L,
+                                               double (&acc)[NMAT][2], double (&cur)[NCUR])
 {
   for (int gs = 0; gs < cnt; gs += 4) {
-    const bool valid = gs + L.q < cnt;
-    const double* r = r0 + min(gs + L.q, cnt - 1) * FM_REC;  // clamp: operands of padded lanes stay finite
+    const double* r = gs + L.q < cnt ? r0 + (gs + L.q) * FM_REC : zero_rec;  // padded lanes multiply zeros
     const double2 wx = ld2(r + L.wofs[0]), wy = ld2(r + L.wofs[1]), wz = ld2(r + L.wofs[2]);
     // E-like CIC weights of corner gq (src/impls/ecsim/particles.cpp:129-131), z * y * x as the reference multiplies
     double s[3];
@@ -106,9 +107,7 @@ __device__ __forceinline__ void octant_segment(const double* __restrict__ r0, in
     const double2 f0 = ld2(r + 6), f1 = ld2(r + 14), f2 = ld2(r + 16), f3 = ld2(r + 18), f4 = ld2(r + 20), f5 = ld2(r + 22);
     const double al[9] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y, f4.x};
     const double ip[3] = {f4.y, f5.x, f5.y};
-    double a[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) a[c] = valid ? s[c] : 0.0;
+    const double (&a)[3] = s;
 #pragma unroll
     for (int c1 = 0; c1 < 3; ++c1) {
 #pragma unroll
@@ -174,83 +173,117 @@ __device__ __forceinline__ void fold(double* __restrict__ block, const Lane& L, 
   }
 }
 
+// Persistent CTAs: one warp per cell, four x-consecutive cells (one staging group) per round, rounds strided
+// over the grid.  What a cell needs from HBM before its first instruction (bin table, B tile, first 32
+// particles) is requested while the previous round is folded and written out.
 template <int MINB>
-__global__ void __launch_bounds__(FM_THREADS, MINB) k_cell_moments(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage, int zl_off)
+__global__ void __launch_bounds__(FM_THREADS, MINB) k_cell_moments(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage, int zl_off,
+                                                                   int groups)
 {
   extern __shared__ __align__(16) double smem[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* block = smem + (size_t)wid * FM_CELL;
   double* recs = block + FM_BLOCK;
-  double* Bt = recs + FM_CHUNK * FM_REC;
-  const int64_t cell_local = (int64_t)blockIdx.x * FM_CELLS + wid;
+  double* zero_rec = recs + FM_CHUNK * FM_REC;
+  double* Bt = zero_rec + FM_REC;
 
   {
     double2* b2 = reinterpret_cast<double2*>(block);
 #pragma unroll
     for (int k = 0; k < FM_BLOCK / 64; ++k) b2[k * 32 + lane] = make_double2(0.0, 0.0);
+    if (lane < FM_REC) zero_rec[lane] = 0.0;
   }
-
-  if (cell_local < a.ncells) {
-    Lane L;
-    L.gq = lane >> 2;
-    L.q = lane & 3;
+  Lane L;
+  L.gq = lane >> 2;
+  L.q = lane & 3;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      L.wofs[c] = 2 * (c + 4 * ((L.gq >> c) & 1));
-      L.rowpos[c] = block_pos(c, L.gq, 0, 0, 0);
-      L.colpos[c] = block_pos(c, 2 * L.q, 0, 0, 0);
-    }
-    // the cells of one launch are whole planes (deposit_cells): owned planes or one ghost plane
+  for (int c = 0; c < 3; ++c) {
+    L.wofs[c] = 2 * (c + 4 * ((L.gq >> c) & 1));
+    L.rowpos[c] = block_pos(c, L.gq, 0, 0, 0);
+    L.colpos[c] = block_pos(c, 2 * L.q, 0, 0, 0);
+  }
+  // the three B-tile elements this lane fetches per cell: e = lane + 32 j -> (x, y, z, c) of the 3 x 3 x 3 x 3 tile
+  int te[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int e = lane + 32 * j;
+    te[j] = e < 81 ? ((e % 3) | (((e / 3) % 3) << 2) | (((e / 9) % 3) << 4) | ((e / 27) << 6)) : -1;
+  }
+  const double f = a.f_beta;
+
+  // cell of this warp in round grp (the cells of one launch are whole planes: owned planes or one ghost plane)
+  int cx = 0, cy = 0, zl = 0;
+  int32_t bs = 0;
+  double tl[3] = {0.0, 0.0, 0.0};
+  double pin[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  auto locate = [&](int64_t cell_local) {
     const int pl = (int)(cell_local / g.plane), rem = (int)(cell_local % g.plane);
-    const int cy = rem / g.nx, cx = rem % g.nx, zl = pl + zl_off;
-    load_field_tile<1>(g, B, cx, cy, zl, Bt, lane, 32);
-    const int64_t bin0 = (a.bin_cell0 + cell_local) << 3;
-    const int32_t bs = lane < 9 ? a.bin_start[bin0 + lane] : 0;  // bin boundaries of the 8 octants
-    const int32_t p0 = __shfl_sync(0xffffffffu, bs, 0), p1 = __shfl_sync(0xffffffffu, bs, 8);
-    // the lower node of the cell as the reference's floor() gives it for every particle binned here
-    const double cxd = (double)cx, cyd = (double)cy, czd = (double)(zl + g.z0 - a.zshift);
-    const double f = (0.5 * g.dt) * a.q / a.m;
+    cy = rem / g.nx;
+    cx = rem % g.nx;
+    zl = pl + zl_off;
+  };
+  auto request_cell = [&](int64_t cell_local) {  // bin boundaries of the 8 octants and the B tile
+    bs = lane < 9 ? __ldg(a.bin_start + ((a.bin_cell0 + cell_local) << 3) + lane) : 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (te[j] < 0) continue;
+      const int x = wrap1(cx - 1 + (te[j] & 3), g.nx), y = wrap1(cy - 1 + ((te[j] >> 2) & 3), g.ny), z = zl - 1 + ((te[j] >> 4) & 3);
+      tl[j] = __ldg(&B[g.vidx(x, y, z, te[j] >> 6)]);
+    }
+  };
+  auto request_particles = [&](int32_t base, int32_t p1) {
+    const int32_t i = base + lane;
+    if (i < p1) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) pin[k] = __ldg(a.p[k] + i);
+    }
+  };
 
-    double acc[NMAT][2], cur[NCUR];
+  int64_t cell_local = (int64_t)blockIdx.x * FM_CELLS + wid;
+  if (blockIdx.x < groups && cell_local < a.ncells) {
+    locate(cell_local);
+    request_cell(cell_local);
+    request_particles(__shfl_sync(0xffffffffu, bs, 0), __shfl_sync(0xffffffffu, bs, 8));
+  }
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    cell_local = (int64_t)grp * FM_CELLS + wid;
+    if (cell_local < a.ncells) {
+      const int32_t p0 = __shfl_sync(0xffffffffu, bs, 0), p1 = __shfl_sync(0xffffffffu, bs, 8), b4 = __shfl_sync(0xffffffffu, bs, 4);
+      const int32_t bsc = bs;
 #pragma unroll
-    for (int v = 0; v < NMAT; ++v) acc[v][0] = acc[v][1] = 0.0;
-#pragma unroll
-    for (int v = 0; v < NCUR; ++v) cur[v] = 0.0;
+      for (int j = 0; j < 3; ++j)
+        if (te[j] >= 0) Bt[lane + 32 * j] = tl[j];
+      // the lower node of the cell as the reference's floor() gives it for every particle binned here
+      const double cd[3] = {(double)cx, (double)cy, (double)(zl + g.z0 - a.zshift)};
+      const int ci[3] = {cx, cy, zl};
 
-    double pin[6];
-    auto fetch = [&](int32_t base) {
-      const int32_t i = base + lane;
-      if (i < p1) {
+      double acc[NMAT][2], cur[NCUR];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) pin[k] = __ldg(a.p[k] + i);
-      }
-    };
-    if (p0 < p1) fetch(p0);
-    __syncwarp();  // the B tile is complete
+      for (int v = 0; v < NMAT; ++v) acc[v][0] = acc[v][1] = 0.0;
+#pragma unroll
+      for (int v = 0; v < NCUR; ++v) cur[v] = 0.0;
+      __syncwarp();  // the B tile is complete
 
-    int oct = 0;
-    int32_t oend = __shfl_sync(0xffffffffu, bs, 1);
-    bool zdone = false;
-    for (int32_t base = p0; base < p1; base += FM_CHUNK) {
-      const int n = min(FM_CHUNK, p1 - base);
-      // ---- records of this round: lane = particle -----------------------------------------------
-      {
-        int po = 0;  // octant of this lane's particle: number of bin boundaries at or below its index
-#pragma unroll
-        for (int k = 1; k < 8; ++k) po += (base + lane >= __shfl_sync(0xffffffffu, bs, k)) ? 1 : 0;
+      int oct = 0;
+      int32_t oend = __shfl_sync(0xffffffffu, bsc, 1);
+      bool zdone = false;
+      for (int32_t base = p0; base < p1;) {
+        // a round ends at the oz = 0 / oz = 1 boundary when that keeps it within 32 particles: no octant is split
+        const int n = (base < b4 && b4 - base <= FM_CHUNK) ? b4 - base : min(FM_CHUNK, p1 - base);
+        // ---- records of this round: lane = particle ---------------------------------------------
         if (lane < n) {
           Weights w;
-          const double cd[3] = {cxd, cyd, czd};
           const double xn[3] = {to_cells(pin[0], g.dx, g.inv_dx, g.exact_inv & 1), to_cells(pin[1], g.dy, g.inv_dy, g.exact_inv & 2),
                                 to_cells(pin[2], g.dz, g.inv_dz, g.exact_inv & 4)};
-          const int ci[3] = {cx, cy, zl};
 #pragma unroll
           for (int ax = 0; ax < 3; ++ax) {
-            const int o = (po >> ax) & 1;
-            // src/impls/ecsim/particles.cpp:76-105 with floor(xn) = cell, floor(xn - 0.5) = cell - 1 + octant bit
+            // src/impls/ecsim/particles.cpp:76-105 with floor(xn) = cell and floor(xn - 0.5) = cell - 1 + octant bit;
+            // xn - cell and xn - 0.5 are exact, so the bit is (xn - cell >= 0.5), the one the key pass binned by
+            const double fx = xn[ax] - cd[ax];
+            const int o = fx >= 0.5 ? 1 : 0;
             w.in[ax] = ci[ax];
             w.is[ax] = ci[ax] - 1 + o;
-            w.wn[ax][1] = xn[ax] - cd[ax];
+            w.wn[ax][1] = fx;
             w.wn[ax][0] = 1 - w.wn[ax][1];
             w.ws[ax][1] = (xn[ax] - 0.5) - (cd[ax] - 1.0 + (double)o);
             w.ws[ax][0] = 1 - w.ws[ax][1];
@@ -264,11 +297,11 @@ __global__ void __launch_bounds__(FM_THREADS, MINB) k_cell_moments(Grid g, Depos
           double vxb[3];
           cross3(v, b, vxb);
           const double vb = dot3(v, b), b2 = dot3(b, b);
-          const double cI = a.q * a.mpw / (1. + b2);
+          const double cI = a.num_I / (1. + b2);  // q mpw / (1 + b^2)
           double ip[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) ip[c] = cI * (v[c] + vxb[c] + vb * b[c]);
-          const double Ap = 0.5 * g.dt * g.dt * a.mpw * a.q * a.q / a.m / (1 + b2);
+          const double Ap = a.num_A / (1 + b2);   // dt^2/2 mpw q^2 / m / (1 + b^2)
           double al[9];
           al[0] = Ap * (1.0 + b[0] * b[0]);
           al[1] = Ap * (+b[2] + b[0] * b[1]);
@@ -292,48 +325,67 @@ __global__ void __launch_bounds__(FM_THREADS, MINB) k_cell_moments(Grid g, Depos
           r[10] = make_double2(al[8], ip[0]);
           r[11] = make_double2(ip[1], ip[2]);
         }
-      }
-      __syncwarp();
-      if (base + FM_CHUNK < p1) fetch(base + FM_CHUNK);  // the next round's particles travel during the MMA phase
-      // ---- rank-1 updates, octant segment by octant segment -------------------------------------
-      int32_t pos = base;
-      const int32_t cend = base + n;
-      while (pos < cend) {
-        while (oend <= pos) {  // the octant's particles are exhausted (warp-uniform)
-          ++oct;
-          oend = __shfl_sync(0xffffffffu, bs, oct + 1);
+        __syncwarp();
+        if (base + n < p1) request_particles(base + n, p1);  // the next round's particles travel during the MMA phase
+        // ---- rank-1 updates, octant segment by octant segment -----------------------------------
+        int32_t pos = base;
+        const int32_t cend = base + n;
+        while (pos < cend) {
+          while (oend <= pos) {  // the octant's particles are exhausted (warp-uniform)
+            ++oct;
+            oend = __shfl_sync(0xffffffffu, bsc, oct + 1);
+          }
+          if (oct >= 4 && !zdone) {  // first particle with oz = 1: the z-dependent slots change their place
+            fold<true, 0>(block, L, acc, cur);
+            zdone = true;
+          }
+          const int32_t seg_end = min(oend, cend);
+          const double* r0 = recs + (pos - base) * FM_REC;
+          const int cnt = seg_end - pos;
+          switch (oct & 3) {
+            case 0: octant_segment<0>(r0, zero_rec, cnt, L, acc, cur); break;
+            case 1: octant_segment<1>(r0, zero_rec, cnt, L, acc, cur); break;
+            case 2: octant_segment<2>(r0, zero_rec, cnt, L, acc, cur); break;
+            default: octant_segment<3>(r0, zero_rec, cnt, L, acc, cur); break;
+          }
+          pos = seg_end;
         }
-        if (oct >= 4 && !zdone) {  // first particle with oz = 1: the z-dependent slots change their place
+        __syncwarp();  // the records may be overwritten by the next round
+        base += n;
+      }
+      if (p0 < p1) {
+        if (zdone)
+          fold<true, 1>(block, L, acc, cur);
+        else
           fold<true, 0>(block, L, acc, cur);
-          zdone = true;
-        }
-        const int32_t seg_end = min(oend, cend);
-        const double* r0 = recs + (pos - base) * FM_REC;
-        const int cnt = seg_end - pos;
-        switch (oct & 3) {
-          case 0: octant_segment<0>(r0, cnt, L, acc, cur); break;
-          case 1: octant_segment<1>(r0, cnt, L, acc, cur); break;
-          case 2: octant_segment<2>(r0, cnt, L, acc, cur); break;
-          default: octant_segment<3>(r0, cnt, L, acc, cur); break;
-        }
-        pos = seg_end;
+        fold<false, 0>(block, L, acc, cur);
       }
-      __syncwarp();  // the records may be overwritten by the next round
     }
-    if (p0 < p1) {
-      if (zdone)
-        fold<true, 1>(block, L, acc, cur);
-      else
-        fold<true, 0>(block, L, acc, cur);
-      fold<false, 0>(block, L, acc, cur);
+    // what the next round's cell needs first is requested before this round's blocks leave
+    const int next = grp + gridDim.x;
+    const int64_t next_cell = (int64_t)next * FM_CELLS + wid;
+    const bool have_next = next < groups && next_cell < a.ncells;
+    if (have_next) {
+      locate(next_cell);
+      request_cell(next_cell);
     }
-  }
-  __syncthreads();
-  // coalesced write-out of the CTA's four blocks: stage[group][entry][cell % 4]
-  double* out = stage + ((a.stage_cell0 / CELL_GROUP) + blockIdx.x) * (int64_t)(BLOCK_ALL * CELL_GROUP);
-  for (int idx = threadIdx.x; idx < BLOCK_ALL * CELL_GROUP; idx += FM_THREADS) {
-    const int e = idx / CELL_GROUP, w = idx % CELL_GROUP;
-    out[idx] = smem[(size_t)w * FM_CELL + e];
+    __syncthreads();
+    if (have_next) request_particles(__shfl_sync(0xffffffffu, bs, 0), __shfl_sync(0xffffffffu, bs, 8));
+    // coalesced write-out of the CTA's four blocks, stage[group][entry][cell % 4]: one thread per entry reads it
+    // from the four blocks, stores 32 contiguous bytes and leaves zeros behind for the next round
+    double* out = stage + ((a.stage_cell0 / CELL_GROUP) + grp) * (int64_t)(BLOCK_ALL * CELL_GROUP);
+    for (int e = threadIdx.x; e < BLOCK_ALL; e += FM_THREADS) {
+      double v[FM_CELLS];
+#pragma unroll
+      for (int w = 0; w < FM_CELLS; ++w) {
+        v[w] = smem[(size_t)w * FM_CELL + e];
+        smem[(size_t)w * FM_CELL + e] = 0.0;
+      }
+      double2* o2 = reinterpret_cast<double2*>(out + (size_t)e * CELL_GROUP);
+      o2[0] = make_double2(v[0], v[1]);
+      o2[1] = make_double2(v[2], v[3]);
+    }
+    __syncthreads();
   }
 }
 
@@ -348,10 +400,14 @@ int launch_cell_moments(xb_ctx* c, const DepositArgs& a, int zl_off, int occupan
     c->fused_attr_set = true;
   }
   const int groups = (int)((a.ncells + FM_CELLS - 1) / FM_CELLS);
+  if (c->sm_count == 0) XB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+  const int resident = c->sm_count * (occupancy == 2 ? 2 : 3);  // persistent CTAs: one wave
+  const int grid = groups < resident ? groups : resident;
+  if (grid < 1) return 0;
   if (occupancy == 2)
-    XB_LAUNCH(c, k_cell_moments<2>, groups, FM_THREADS, smem, c->g, a, c->B, c->stage, zl_off);
+    XB_LAUNCH(c, k_cell_moments<2>, grid, FM_THREADS, smem, c->g, a, c->B, c->stage, zl_off, groups);
   else
-    XB_LAUNCH(c, k_cell_moments<3>, groups, FM_THREADS, smem, c->g, a, c->B, c->stage, zl_off);
+    XB_LAUNCH(c, k_cell_moments<3>, grid, FM_THREADS, smem, c->g, a, c->B, c->stage, zl_off, groups);
   return 0;
 }
 
