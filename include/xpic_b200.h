@@ -156,6 +156,9 @@ int xb_family_profile(xb_ctx* ctx, int32_t enable);
 int xb_family_profile_read(xb_ctx* ctx, int32_t family, int64_t* launches, double* total_ms);
 /* Energy::calculate_energy (src/diagnostics/energy.cpp:43-59): 0.5 * |v|^2 of a named vector, summed over all ranks. */
 int xb_field_energy(xb_ctx* ctx, int32_t which, int32_t sid, double* out);
+/* The sums Energy::calculate_energy forms with VecNorm and VecStrideSumAll (energy.cpp:43-59), over all ranks:
+ * out = { sum of component x, y, z, sum of squares }. */
+int xb_field_sums(xb_ctx* ctx, int32_t which, int32_t sid, double out[4]);
 
 /* --- hooks for the operator sweep (BASELINE config 4) and per-kernel parity tests ----------- */
 /* y = Op x with host vectors (owned slab, natural order).  MatMult, e.g. ecsimcorr/simulation.cpp:78 */
@@ -168,7 +171,8 @@ int xb_spmv_bench(xb_ctx* ctx, int32_t op, int32_t reps, double* ms_per_spmv);
 int xb_operator_download(xb_ctx* ctx, double* coef);
 int xb_operator_upload(xb_ctx* ctx, const double* coef);
 /* Kernel variant switches for cross-checks: what = 0 selects the cell-block kernel of the moment
- * deposition (value 0: fp64 tensor-core DMMA, default; 1: scalar FMA); what = 1 the Esirkepov deposit
+ * deposition (value 0: fused warp-specialised fp64 tensor-core kernel, default; 3: fused kernel without role split;
+ * 2: round-1 pipeline with field records in HBM; 1: scalar FMA); what = 1 the Esirkepov deposit
  * of ecsimcorr (0: atomic-free DMMA cell blocks, default; 1: per-particle global fp64 reductions);
  * what = 2: canonical particle order inside every bin after a sort when ids are not tracked
  * (1: runs are bit-reproducible, costs one more pass over the particles; 0, default: keep the order
@@ -179,7 +183,9 @@ int xb_operator_upload(xb_ctx* ctx, const double* coef);
  * what = 4: eccapfim's per-particle Picard iteration of residual evaluation k + 1 starts from the velocity
  * evaluation k of the same step converged to (1, default) or from the start-of-step velocity every time as
  * the reference does (0, src/impls/eccapfim/particles.cpp:77-78); the converged particle state is the same
- * to the Picard tolerance, the number of field gathers per evaluation drops from ~3.7 to ~2. */
+ * to the Picard tolerance, the number of field gathers per evaluation drops from ~3.7 to ~2;
+ * what = 5: nanoseconds a warp of the warp-specialised moment kernel sleeps between two polls of its mbarrier
+ * (measurement knob; 0 = spin). */
 int xb_set_option(xb_ctx* ctx, int32_t what, int32_t value);
 /* --- eccapfim (BASELINE config 5): xb_step / xb_stage with scheme XB_ECCAPFIM run
  * eccapfim::Simulation::timestep_implementation (src/impls/eccapfim/simulation.cpp:36-44); stages

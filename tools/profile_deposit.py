@@ -20,6 +20,12 @@ out = {"grid": grid, "ppc": ppc}
 for v in variants:
     sim.set_option(0, v)
     out[f"deposit_variant_{v}_ms"] = sim.kernel_bench(1, 3)
+if os.environ.get("XPIC_BACKOFF_SWEEP"):
+    sim.set_option(0, 0)
+    for ns in (0, 32, 64, 128, 256, 512):
+        sim.set_option(5, ns)
+        out[f"deposit_ws_backoff_{ns}ns_ms"] = sim.kernel_bench(1, 3)
+    sim.set_option(5, 64)
 sim.set_option(0, variants[0])
 sim.family_profile(True)
 ms = sim.run_steps(3)

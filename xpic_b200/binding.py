@@ -94,6 +94,7 @@ SYMBOLS = {
     "xb_family_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "xb_family_profile_read": (C.c_int, [C.c_void_p, C.c_int32, _i64p, _dp]),
     "xb_field_energy": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "xb_field_sums": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "xb_scalar": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "xb_particle_moments": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "xb_timing": (C.c_int, [C.c_void_p, C.c_int32, _dp, _i64p]),

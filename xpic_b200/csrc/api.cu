@@ -615,6 +615,14 @@ int xb_family_profile_read(xb_ctx* c, int32_t family, int64_t* launches, double*
 int xb_spmv_profile(xb_ctx* c, int32_t enable) { return xb_family_profile(c, enable); }
 int xb_spmv_profile_read(xb_ctx* c, int64_t* launches, double* total_ms) { return xb_family_profile_read(c, XB_FAMILY_SPMV, launches, total_ms); }
 
+int xb_field_sums(xb_ctx* c, int32_t which, int32_t sid, double out[4])
+{
+  XB_API_BEGIN(c);
+  const double* v = named_vector(c, which, sid);
+  if (!v || !out) XB_FAIL("xb_field_sums: unknown vector");
+  return field_sums(c, v, out);
+}
+
 int xb_field_energy(xb_ctx* c, int32_t which, int32_t sid, double* out)
 {
   XB_API_BEGIN(c);
@@ -758,6 +766,10 @@ int xb_set_option(xb_ctx* c, int32_t what, int32_t value)
   }
   if (what == 4) {
     c->nl.warm_start = value != 0;
+    return 0;
+  }
+  if (what == 5) {
+    c->ws_backoff_ns = value < 0 ? 0 : value;
     return 0;
   }
   XB_FAIL("xb_set_option: unknown option");

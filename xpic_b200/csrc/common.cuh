@@ -147,6 +147,7 @@ struct xb_ctx {
   xb::Grid g;
   int device = 0;
   int sm_count = 0;
+  int ws_backoff_ns = 64;  // k_cell_moments_ws: pause of a waiting warp between two polls of its mbarrier (xb_set_option 5)
   bool track_ids = false;
   bool deterministic = false;  // canonical particle order inside every bin even without ids (costs one more pass)
   cudaStream_t stream = nullptr;
@@ -217,6 +218,7 @@ int curl_apply(xb_ctx* c, bool positive, const double* f, double* out, double sc
 int build_rhs(xb_ctx* c, const double* curr, double* rhs);       // 2E - dt curr + dt curl^-(B - B0)
 int final_update(xb_ctx* c, const double* Ehalf);                // E = 2 Eh - E ; B -= dt curl^+ Eh
 int dots(xb_ctx* c, int nv, const double* const* vs, const double* w, double* host_out);  // host_out[i] = vs[i].w
+int field_sums(xb_ctx* c, const double* v, double* out4);  // component sums and sum of squares, all ranks
 int axpy_multi(xb_ctx* c, int nv, const double* const* vs, const double* coef_host, double* w);  // w += sum coef_i vs_i
 int axpy_multi_scaled(xb_ctx* c, int nv, const double* const* vs, const double* coef_host, double* w, double alpha);  // w = alpha (w + sum coef_i vs_i)
 int scale_into(xb_ctx* c, const double* w, double alpha, double* out);                            // out = alpha w

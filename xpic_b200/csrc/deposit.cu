@@ -583,7 +583,7 @@ int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage);
 int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* bin_start, int64_t bin_cell0, int64_t ncells, int64_t stage_cell0,
                   int zshift, double** rec, int64_t rec_stride, int64_t nparticles)
 {
-  // variants (xb_set_option(ctx, 0, v)): 0 fused DMMA kernel, 3 the same at two CTAs per SM (255 registers),
+  // variants (xb_set_option(ctx, 0, v)): 0 fused warp-specialised DMMA kernel, 3 fused kernel without role split,
   // 2 round-1 pipeline (field records in HBM + two-warp DMMA kernel), 1 scalar-FMA cell blocks
   const int variant = c->deposit_variant;
   DepositArgs a;
@@ -605,7 +605,7 @@ int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* 
   // the cells of one launch are whole planes: owned planes (bin plane 1.. -> zl 0..) or one ghost plane
   const Grid& g = c->g;
   const int zl_off = bin_cell0 == g.plane ? 0 : (stage_cell0 == 0 ? -1 : g.nzl);
-  if (variant == 0 || variant == 3) return launch_cell_moments(c, a, zl_off, variant == 3 ? 2 : 3);
+  if (variant == 0 || variant == 3) return launch_cell_moments(c, a, zl_off, variant);
 
   const bool use_mma = variant == 2;
   const size_t smem = sizeof(double) * (use_mma ? MMA_SMEM_PER_CELL : DEP_SMEM_PER_WARP) * CELL_GROUP;

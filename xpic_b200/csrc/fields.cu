@@ -288,6 +288,39 @@ int reduce_finish(xb_ctx* c, int nv, double* host_out)
   return 0;
 }
 
+// sum of every component and of the squares over the owned part (Energy::calculate_energy's VecNorm and
+// VecStrideSumAll, src/diagnostics/energy.cpp:43-59), all ranks
+__global__ void __launch_bounds__(RED_THREADS) k_field_sums(const double* __restrict__ v, int64_t nodes, double* __restrict__ partial)
+{
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nodes; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = v[3 * i], y = v[3 * i + 1], z = v[3 * i + 2];
+    a[0] += x;
+    a[1] += y;
+    a[2] += z;
+    a[3] += (x * x + y * y) + z * z;
+  }
+  __shared__ double sh[RED_THREADS / 32][4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double t = warp_sum(a[k]);
+    if (lane == 0) sh[wid][k] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int q = 0; q < RED_THREADS / 32; ++q) t += sh[q][threadIdx.x];
+    partial[(int64_t)blockIdx.x * RED_MAXV + threadIdx.x] = t;
+  }
+}
+
+int field_sums(xb_ctx* c, const double* v, double* out4)
+{
+  XB_LAUNCH(c, k_field_sums, RED_BLOCKS, RED_THREADS, 0, v + c->g.own0, c->g.ncl, c->red_partial);
+  return reduce_finish(c, 4, out4);
+}
+
 int dots(xb_ctx* c, int nv, const double* const* vs, const double* w, double* host_out)
 {
   if (nv > RED_MAXV) XB_FAIL("dots: too many vectors");

@@ -389,24 +389,289 @@ __global__ void __launch_bounds__(FM_THREADS, MINB) k_cell_moments(Grid g, Depos
   }
 }
 
+// =====================================================================================================
+// Warp-specialised form (the default).  In the kernel above a warp that carries 94 accumulator registers
+// spends three quarters of its time on work that needs none of them (particle loads, B gather, two fp64
+// divisions per particle, record stores: all latency-bound), and those registers cap the SM at 12 warps.
+// Here a CTA is two warpgroups: warps 0-3 are CONSUMERS (rank-1 updates, folds, write-out; 152 registers
+// after setmaxnreg.inc), warps 4-7 are PRODUCERS (bin table, B tile, particle loads, records; 104 registers
+// after setmaxnreg.dec).  Producer 4 + i feeds consumer i through a two-stage ring of 32-particle record
+// buffers in shared memory, one mbarrier pair (full / empty) per stage; it runs up to two rounds ahead,
+// also across cells, so the consumer never sees HBM latency.  Two CTAs per SM: 8 + 8 warps.
+// =====================================================================================================
+constexpr int WS_THREADS = 256;
+constexpr int WS_STAGES = 2;
+constexpr int WS_META = 16;  // ints per stage: [0..8] bin boundaries of the cell (first round only), [9] base, [10] n, [11] 1 = first | 2 = last
+// per cell: block, WS_STAGES x 32 records, zero record, B tile, meta, 2 x WS_STAGES mbarriers (+ pad to 16 k + 8)
+constexpr int WS_CELL = FM_BLOCK + WS_STAGES * FM_CHUNK * FM_REC + FM_REC + FM_TILE + WS_STAGES * WS_META / 2 + 2 * WS_STAGES + 12;
+static_assert(WS_CELL % 16 == 8, "write-out reads the four blocks of a CTA without bank conflicts");
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(unsigned bar, int parity)
+{
+  unsigned ok;
+  asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// a warp that finds its stage not ready backs off before it polls again: the polls of the waiting role share the
+// issue slots and the shared-memory pipe with the working role
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity, unsigned backoff_ns)
+{
+  const unsigned addr = smem_u32(bar);
+  while (!mbar_try(addr, parity))
+    if (backoff_ns) __nanosleep(backoff_ns);
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage, int zl_off,
+                                                                   int groups, unsigned backoff_ns)
+{
+  extern __shared__ __align__(16) double smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = wid & 3;
+  const bool producer = wid >= 4;
+  double* block = smem + (size_t)slot * WS_CELL;
+  double* recs = block + FM_BLOCK;
+  double* zero_rec = recs + WS_STAGES * FM_CHUNK * FM_REC;
+  double* Bt = zero_rec + FM_REC;
+  int* meta = reinterpret_cast<int*>(Bt + FM_TILE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(meta + WS_STAGES * WS_META);
+  uint64_t* empty = full + WS_STAGES;
+
+  if (!producer) {
+    double2* b2 = reinterpret_cast<double2*>(block);
+#pragma unroll
+    for (int k = 0; k < FM_BLOCK / 64; ++k) b2[k * 32 + lane] = make_double2(0.0, 0.0);
+    if (lane < FM_REC) zero_rec[lane] = 0.0;
+    if (lane == 0) {
+#pragma unroll
+      for (int st = 0; st < WS_STAGES; ++st) {
+        mbar_init(full + st, 1);
+        mbar_init(empty + st, 1);
+      }
+    }
+  }
+  __syncthreads();
+
+  if (producer) {
+    // ================================ producer: records =============================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    int te[3];  // the three B-tile elements this lane fetches per cell: e = lane + 32 j -> (x, y, z, c)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int e = lane + 32 * j;
+      te[j] = e < 81 ? ((e % 3) | (((e / 3) % 3) << 2) | (((e / 9) % 3) << 4) | ((e / 27) << 6)) : -1;
+    }
+    const double f = a.f_beta;
+    int seq = 0;
+    for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+      const int64_t cell_local = (int64_t)grp * FM_CELLS + slot;
+      if (cell_local >= a.ncells) continue;
+      // the cells of one launch are whole planes (deposit_cells): owned planes or one ghost plane
+      const int pl = (int)(cell_local / g.plane), rem = (int)(cell_local % g.plane);
+      const int cy = rem / g.nx, cx = rem % g.nx, zl = pl + zl_off;
+      const int32_t bs = lane < 9 ? __ldg(a.bin_start + ((a.bin_cell0 + cell_local) << 3) + lane) : 0;  // bin boundaries of the 8 octants
+      double tl[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (te[j] < 0) continue;
+        const int x = wrap1(cx - 1 + (te[j] & 3), g.nx), y = wrap1(cy - 1 + ((te[j] >> 2) & 3), g.ny), z = zl - 1 + ((te[j] >> 4) & 3);
+        tl[j] = __ldg(&B[g.vidx(x, y, z, te[j] >> 6)]);
+      }
+      const int32_t p0 = __shfl_sync(0xffffffffu, bs, 0), p1 = __shfl_sync(0xffffffffu, bs, 8), b4 = __shfl_sync(0xffffffffu, bs, 4);
+      __syncwarp();  // the gathers of the previous cell are done with the tile
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (te[j] >= 0) Bt[lane + 32 * j] = tl[j];
+      __syncwarp();
+      // the lower node of the cell as the reference's floor() gives it for every particle binned here
+      const double cd[3] = {(double)cx, (double)cy, (double)(zl + g.z0 - a.zshift)};
+      const int ci[3] = {cx, cy, zl};
+      int32_t base = p0;
+      bool first = true;
+      do {
+        // a round ends at the oz = 0 / oz = 1 boundary when that keeps it within 32 particles: no octant is split
+        const int n = (base < b4 && b4 - base <= FM_CHUNK) ? b4 - base : min(FM_CHUNK, p1 - base);
+        double pin[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (lane < n) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) pin[k] = __ldg(a.p[k] + base + lane);
+        }
+        const int st = seq & (WS_STAGES - 1);
+        mbar_wait(empty + st, ((seq / WS_STAGES) & 1) ^ 1, backoff_ns);  // the consumer has released this stage
+        if (lane < n) {
+          Weights w;
+          const double xn[3] = {to_cells(pin[0], g.dx, g.inv_dx, g.exact_inv & 1), to_cells(pin[1], g.dy, g.inv_dy, g.exact_inv & 2),
+                                to_cells(pin[2], g.dz, g.inv_dz, g.exact_inv & 4)};
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            // src/impls/ecsim/particles.cpp:76-105 with floor(xn) = cell and floor(xn - 0.5) = cell - 1 + octant bit;
+            // xn - cell and xn - 0.5 are exact, so the bit is (xn - cell >= 0.5), the one the key pass binned by
+            const double fx = xn[ax] - cd[ax];
+            const int o = fx >= 0.5 ? 1 : 0;
+            w.in[ax] = ci[ax];
+            w.is[ax] = ci[ax] - 1 + o;
+            w.wn[ax][1] = fx;
+            w.wn[ax][0] = 1 - w.wn[ax][1];
+            w.ws[ax][1] = (xn[ax] - 0.5) - (cd[ax] - 1.0 + (double)o);
+            w.ws[ax][0] = 1 - w.ws[ax][1];
+          }
+          const TileIndex t = tile_index<1>(w, cx, cy, zl);
+          double Bp[3], b[3];
+          gather_B_tile<1>(Bt, w, t, Bp);
+          const double v[3] = {pin[3], pin[4], pin[5]};
+#pragma unroll
+          for (int c = 0; c < 3; ++c) b[c] = Bp[c] * f;
+          double vxb[3];
+          cross3(v, b, vxb);
+          const double vb = dot3(v, b), b2 = dot3(b, b);
+          const double cI = a.num_I / (1. + b2);  // q mpw / (1 + b^2)
+          double ip[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) ip[c] = cI * (v[c] + vxb[c] + vb * b[c]);
+          const double Ap = a.num_A / (1 + b2);   // dt^2/2 mpw q^2 / m / (1 + b^2)
+          double2* r = reinterpret_cast<double2*>(recs + (st * FM_CHUNK + lane) * FM_REC);
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            r[ax] = make_double2(w.wn[ax][0], w.ws[ax][0]);
+            r[4 + ax] = make_double2(w.wn[ax][1], w.ws[ax][1]);
+          }
+          r[3] = make_double2(Ap * (1.0 + b[0] * b[0]), Ap * (+b[2] + b[0] * b[1]));
+          r[7] = make_double2(Ap * (-b[1] + b[0] * b[2]), Ap * (-b[2] + b[1] * b[0]));
+          r[8] = make_double2(Ap * (1.0 + b[1] * b[1]), Ap * (+b[0] + b[1] * b[2]));
+          r[9] = make_double2(Ap * (+b[1] + b[2] * b[0]), Ap * (-b[0] + b[2] * b[1]));
+          r[10] = make_double2(Ap * (1.0 + b[2] * b[2]), ip[0]);
+          r[11] = make_double2(ip[1], ip[2]);
+        }
+        int* mt = meta + st * WS_META;
+        if (first && lane < 9) mt[lane] = bs;
+        if (lane == 0) {
+          mt[9] = base;
+          mt[10] = n;
+          mt[11] = (first ? 1 : 0) | (base + n >= p1 ? 2 : 0);
+        }
+        __syncwarp();  // every lane's records are written before lane 0 publishes the stage
+        if (lane == 0) mbar_arrive(full + st);
+        base += n;
+        first = false;
+        ++seq;
+      } while (base < p1);
+    }
+    return;
+  }
+
+  // ================================== consumer: rank-1 updates, folds, write-out =====================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+  Lane L;
+  L.gq = lane >> 2;
+  L.q = lane & 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    L.wofs[c] = 2 * (c + 4 * ((L.gq >> c) & 1));
+    L.rowpos[c] = block_pos(c, L.gq, 0, 0, 0);
+    L.colpos[c] = block_pos(c, 2 * L.q, 0, 0, 0);
+  }
+  int seq = 0;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int64_t cell_local = (int64_t)grp * FM_CELLS + slot;
+    if (cell_local < a.ncells) {
+      double acc[NMAT][2], cur[NCUR];
+#pragma unroll
+      for (int v = 0; v < NMAT; ++v) acc[v][0] = acc[v][1] = 0.0;
+#pragma unroll
+      for (int v = 0; v < NCUR; ++v) cur[v] = 0.0;
+      int oct = 0;
+      int32_t bsc = 0, oend = 0;
+      bool zdone = false, any = false;
+      while (true) {
+        const int st = seq & (WS_STAGES - 1);
+        mbar_wait(full + st, (seq / WS_STAGES) & 1, backoff_ns);  // the producer has published this stage
+        const int* mt = meta + st * WS_META;
+        const int32_t base = mt[9];
+        const int n = mt[10], flags = mt[11];
+        if (flags & 1) {
+          bsc = lane < 9 ? mt[lane] : 0;
+          oend = __shfl_sync(0xffffffffu, bsc, 1);
+        }
+        const double* rbuf = recs + st * FM_CHUNK * FM_REC;
+        int32_t pos = base;
+        const int32_t cend = base + n;
+        any = any || n > 0;
+        while (pos < cend) {
+          while (oend <= pos) {  // the octant's particles are exhausted (warp-uniform)
+            ++oct;
+            oend = __shfl_sync(0xffffffffu, bsc, oct + 1);
+          }
+          if (oct >= 4 && !zdone) {  // first particle with oz = 1: the z-dependent slots change their place
+            fold<true, 0>(block, L, acc, cur);
+            zdone = true;
+          }
+          const int32_t seg_end = min(oend, cend);
+          const double* r0 = rbuf + (pos - base) * FM_REC;
+          const int cnt = seg_end - pos;
+          switch (oct & 3) {
+            case 0: octant_segment<0>(r0, zero_rec, cnt, L, acc, cur); break;
+            case 1: octant_segment<1>(r0, zero_rec, cnt, L, acc, cur); break;
+            case 2: octant_segment<2>(r0, zero_rec, cnt, L, acc, cur); break;
+            default: octant_segment<3>(r0, zero_rec, cnt, L, acc, cur); break;
+          }
+          pos = seg_end;
+        }
+        __syncwarp();  // every lane is done with the stage before lane 0 releases it
+        if (lane == 0) mbar_arrive(empty + st);
+        ++seq;
+        if (flags & 2) break;
+      }
+      if (any) {
+        if (zdone)
+          fold<true, 1>(block, L, acc, cur);
+        else
+          fold<true, 0>(block, L, acc, cur);
+        fold<false, 0>(block, L, acc, cur);
+      }
+    }
+    consumer_barrier();
+    // coalesced write-out of the CTA's four blocks, stage[group][entry][cell % 4]: one consumer thread per entry
+    // reads it from the four blocks, stores 32 contiguous bytes and leaves zeros behind for the next round
+    double* out = stage + ((a.stage_cell0 / CELL_GROUP) + grp) * (int64_t)(BLOCK_ALL * CELL_GROUP);
+    for (int e = threadIdx.x; e < BLOCK_ALL; e += 128) {
+      double v[FM_CELLS];
+#pragma unroll
+      for (int w = 0; w < FM_CELLS; ++w) {
+        v[w] = smem[(size_t)w * WS_CELL + e];
+        smem[(size_t)w * WS_CELL + e] = 0.0;
+      }
+      double2* o2 = reinterpret_cast<double2*>(out + (size_t)e * CELL_GROUP);
+      o2[0] = make_double2(v[0], v[1]);
+      o2[1] = make_double2(v[2], v[3]);
+    }
+    consumer_barrier();
+  }
+}
+
 }  // namespace
 
-int launch_cell_moments(xb_ctx* c, const DepositArgs& a, int zl_off, int occupancy)
+int launch_cell_moments(xb_ctx* c, const DepositArgs& a, int zl_off, int form)
 {
-  const size_t smem = sizeof(double) * FM_CELL * FM_CELLS;
+  const size_t smem = sizeof(double) * FM_CELL * FM_CELLS, smem_ws = sizeof(double) * WS_CELL * FM_CELLS;
   if (!c->fused_attr_set) {
     XB_CUDA(cudaFuncSetAttribute(k_cell_moments<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    XB_CUDA(cudaFuncSetAttribute(k_cell_moments<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XB_CUDA(cudaFuncSetAttribute(k_cell_moments_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
     c->fused_attr_set = true;
   }
   const int groups = (int)((a.ncells + FM_CELLS - 1) / FM_CELLS);
   if (c->sm_count == 0) XB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
-  const int resident = c->sm_count * (occupancy == 2 ? 2 : 3);  // persistent CTAs: one wave
+  const int resident = c->sm_count * (form == 0 ? 2 : 3);  // persistent CTAs: one wave
   const int grid = groups < resident ? groups : resident;
   if (grid < 1) return 0;
-  if (occupancy == 2)
-    XB_LAUNCH(c, k_cell_moments<2>, grid, FM_THREADS, smem, c->g, a, c->B, c->stage, zl_off, groups);
-  else
+  if (form == 0)  // warp-specialised: producers (records) and consumers (DMMA) in one CTA
+    XB_LAUNCH(c, k_cell_moments_ws, grid, WS_THREADS, smem_ws, c->g, a, c->B, c->stage, zl_off, groups, (unsigned)c->ws_backoff_ns);
+  else            // every warp does everything for its cell
     XB_LAUNCH(c, k_cell_moments<3>, grid, FM_THREADS, smem, c->g, a, c->B, c->stage, zl_off, groups);
   return 0;
 }

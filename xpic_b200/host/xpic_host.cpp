@@ -1,12 +1,18 @@
 // xpic_host.cpp -- see xpic_host.h.
 #include "xpic_host.h"
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <array>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <filesystem>
 #include <format>
 #include <iostream>
 #include <stdexcept>
+#include <thread>
 
 #include <nlohmann/json.hpp>
 
@@ -23,21 +29,32 @@ constexpr double mec2 = 511.0;  // src/constants.h:30
     }                                                                                \
   } while (0)
 
-// ---- Builder::parse_value (src/interfaces/builder.cpp:54-81) -----------------------------------
+// ---- the unit grammar of Builder::parse_value (src/interfaces/builder.cpp:54-81) ------------------
+// a number, one of the geometry names, or "<number> [unit]" with the units of the table below
 static double parse_value(const json& value, const Geometry& g)
 {
   if (!value.is_string()) return value.get<double>();
   const std::string str = value.get<std::string>();
-  if (str == "geom_x" || str == "geom_nx") return g.geom_x;
-  if (str == "geom_y" || str == "geom_ny") return g.geom_y;
-  if (str == "geom_z" || str == "geom_nz") return g.geom_z;
-  auto ends = [&](const char* suffix) { return str.ends_with(suffix); };
-  if (ends(" [dx]")) return std::stod(str.substr(0, str.size() - 5)) * g.dx;
-  if (ends(" [dy]")) return std::stod(str.substr(0, str.size() - 5)) * g.dy;
-  if (ends(" [dz]")) return std::stod(str.substr(0, str.size() - 5)) * g.dz;
-  if (ends(" [dt]")) return std::stod(str.substr(0, str.size() - 5)) * g.dt;
-  if (ends(" [c/w_pe]") || ends(" [1/w_pe]")) return std::stod(str.substr(0, str.size() - 9));
+  const struct { const char* name; double value; } named[] = {
+    {"geom_x", g.geom_x}, {"geom_nx", g.geom_x}, {"geom_y", g.geom_y}, {"geom_ny", g.geom_y}, {"geom_z", g.geom_z}, {"geom_nz", g.geom_z}};
+  for (const auto& n : named)
+    if (str == n.name) return n.value;
+  const struct { const char* unit; double scale; } units[] = {
+    {" [dx]", g.dx}, {" [dy]", g.dy}, {" [dz]", g.dz}, {" [dt]", g.dt}, {" [c/w_pe]", 1.0}, {" [1/w_pe]", 1.0}};
+  for (const auto& u : units) {
+    const std::string unit = u.unit;
+    if (str.size() > unit.size() && str.compare(str.size() - unit.size(), unit.size(), unit) == 0)
+      return std::stod(str.substr(0, str.size() - unit.size())) * u.scale;
+  }
   throw std::runtime_error("Unknown string format to convert: " + str);
+}
+
+// Builder::parse_vector: three values of the grammar above
+static std::array<double, 3> parse_vector(const json& info, const char* key, const Geometry& g)
+{
+  const json& v = info.at(key);
+  if (!v.is_array() || v.size() != 3) throw std::runtime_error(std::string("Vector ") + key + " should have 3 components");
+  return {parse_value(v[0], g), parse_value(v[1], g), parse_value(v[2], g)};
 }
 
 static int round_step(double s, double ds) { return static_cast<int>(std::round(s / ds)); }
@@ -45,6 +62,7 @@ static int round_step(double s, double ds) { return static_cast<int>(std::round(
 // ---- Table -------------------------------------------------------------------------------------
 Table::Table(const std::string& filename, bool append)
 {
+  if (filename.empty()) return;  // ranks other than 0 evaluate the (collective) diagnostics but do not print them
   std::filesystem::create_directories(std::filesystem::path(filename).parent_path());
   file_.open(filename, append ? std::ios::out | std::ios::app : std::ios::out);
 }
@@ -81,7 +99,7 @@ int Particles::add_particle(const Point& point, bool* is_added)
 {
   const Geometry& g = simulation_.geom;
   const int vx = (int)std::floor(point.r[0] / g.dx), vy = (int)std::floor(point.r[1] / g.dy), vz = (int)std::floor(point.r[2] / g.dz);
-  if (vx < 0 || vx >= g.geom_nx || vy < 0 || vy >= g.geom_ny || vz < 0 || vz >= g.geom_nz) return 0;
+  if (vx < 0 || vx >= g.geom_nx || vy < 0 || vy >= g.geom_ny || vz < simulation_.slab_begin() || vz >= simulation_.slab_end()) return 0;
   pending_.push_back(point);
   if (is_added) *is_added = true;
   return 0;
@@ -137,6 +155,10 @@ void Simulation::set_option(const std::string& key, const std::string& value)
   else if (key == "-curl_sign") curl_sign_ = std::stoi(value);
   else if (key == "-device") device_ = std::stoi(value);
   else if (key == "-precond") precond_ = std::stoi(value);
+  else if (key == "-rank") rank_ = std::stoi(value);
+  else if (key == "-nranks") nranks_ = std::stoi(value);
+  else if (key == "-comm_file") comm_file_ = value;
+  else if (key == "-da_processors_z") da_processors_z_ = std::stoi(value);  // PETSc's own option (DMSetFromOptions)
   else throw std::runtime_error("Unknown option " + key);
 }
 
@@ -206,23 +228,68 @@ int Simulation::configure(const std::string& config_path)
           throw std::runtime_error("DistributionMoment: only the density moment is covered by this build");
         density_views_.push_back(info.at("particles").get<std::string>());
       }
+      else if (name == "LogView") {  // diagnostics/builders/log_view_builder.cpp: one of three levels
+        const std::string level = info.at("level").get<std::string>();
+        if (level == "EachTimestep") log_levels_ |= 1;
+        else if (level == "DiagnosePeriodAvg") log_levels_ |= 2;
+        else if (level == "AllTimestepsSummary") log_levels_ |= 4;
+        else throw std::runtime_error("Unknown LogView level " + level);
+      }
       else
         std::cout << "  diagnostic " << name << " is not covered by this build, skipped\n";
     }
-  if (cfg.contains("Presets"))  // commands/builders/command_builder.cpp:42-59
+  if (cfg.contains("Presets"))  // commands/builders/command_builder.cpp:42-59, particles_builder.cpp:9-70
     for (const json& info : cfg.at("Presets")) {
       const std::string command = info.at("command").get<std::string>();
       if (command != "SetParticles") throw std::runtime_error("Preset " + command + " is not covered by this build");
       Preset pr;
       info.at("particles").get_to(pr.particles);
-      pr.coordinate = info.at("coordinate").at("name").get<std::string>();
-      pr.momentum = info.at("momentum").at("name").get<std::string>();
-      if (info.at("momentum").contains("tov")) info.at("momentum").at("tov").get_to(pr.tov);
-      if (pr.coordinate != "CoordinateInBox" || info.at("coordinate").contains("min") || info.at("coordinate").contains("max"))
-        throw std::runtime_error("SetParticles: only the whole-box CoordinateInBox generator is covered by this build");
-      if (pr.momentum != "MaxwellianMomentum") throw std::runtime_error("SetParticles: only MaxwellianMomentum is covered by this build");
+      const json& co = info.at("coordinate");
+      pr.coordinate = co.at("name").get<std::string>();
+      pr.box_min = {0.0, 0.0, 0.0};
+      pr.box_max = {geom.geom_x, geom.geom_y, geom.geom_z};
+      if (pr.coordinate == "CoordinateInBox") {
+        if (co.contains("min")) pr.box_min = parse_vector(co, "min", geom);
+        if (co.contains("max")) pr.box_max = parse_vector(co, "max", geom);
+      }
+      else if (pr.coordinate == "CoordinateInCylinder") {  // builder.cpp:96-111
+        pr.center = {0.5 * geom.geom_x, 0.5 * geom.geom_y, 0.5 * geom.geom_z};
+        pr.radius = 0.5 * std::min(geom.geom_x, geom.geom_y);
+        pr.height = geom.geom_z;
+        if (co.contains("center")) pr.center = parse_vector(co, "center", geom);
+        if (co.contains("radius")) co.at("radius").get_to(pr.radius);
+        if (co.contains("height")) co.at("height").get_to(pr.height);
+      }
+      else if (pr.coordinate == "PreciseCoordinate")
+        pr.center = parse_vector(co, "value", geom);
+      else
+        throw std::runtime_error("Unknown coordinate generator name " + pr.coordinate);
+      const json& mo = info.at("momentum");
+      pr.momentum = mo.at("name").get<std::string>();
+      if (pr.momentum == "MaxwellianMomentum") {
+        if (mo.contains("tov")) mo.at("tov").get_to(pr.tov);
+      }
+      else if (pr.momentum == "PreciseMomentum")
+        pr.value = parse_vector(mo, "value", geom);
+      else if (pr.momentum == "MaxwellCosinePerturbation") {
+        pr.mbox_min = {0.0, 0.0, 0.0};
+        pr.mbox_max = {geom.geom_x, geom.geom_y, geom.geom_z};
+        if (mo.contains("min")) pr.mbox_min = parse_vector(mo, "min", geom);
+        if (mo.contains("max")) pr.mbox_max = parse_vector(mo, "max", geom);
+        pr.amplitude = parse_vector(mo, "amplitude", geom);
+        pr.wave_number = parse_vector(mo, "wave_number", geom);
+      }
+      else
+        throw std::runtime_error("Unknown coordinate generator name " + pr.momentum);  // the reference's message, particles_builder.cpp:67
       presets_.push_back(pr);
     }
+  if (cfg.contains("mpi")) {  // utils/configuration.cpp:111-130: only the z split exists in a slab layout
+    const json& mpi = cfg.at("mpi");
+    for (const char* key : {"da_processors_x", "da_processors_y"})
+      if (mpi.contains(key) && mpi.at(key).get<int>() > 1)
+        throw std::runtime_error(std::string(key) + " > 1: this build decomposes along z only (da_processors_z)");
+    if (mpi.contains("da_processors_z")) da_processors_z_ = mpi.at("da_processors_z").get<int>();
+  }
   return 0;
 }
 
@@ -239,7 +306,7 @@ int Simulation::get_named_vector(const std::string& name, std::vector<double>& o
                                                                  {"currI", XB_CURRI}, {"currJe", XB_CURRJE}};
   for (auto& [n, id] : names)
     if (n == name) {
-      out.resize((size_t)3 * geom.geom_nx * geom.geom_ny * geom.geom_nz);
+      out.resize((size_t)3 * geom.geom_nx * geom.geom_ny * nzl_);  // this rank's z-slab (the whole box on one GPU)
       B200_CALL(xb_field_download(ctx, id, 0, out.data()));
       return 0;
     }
@@ -254,15 +321,56 @@ int Simulation::initialize()
   g.dt = geom.dt;
   g.curl_sign = curl_sign_;
   g.device = device_;
-  g.rank = 0;
-  g.nranks = 1;
+  // one process per GPU (the reference: one MPI rank per DMDA box, -da_processors_z N); the launcher passes
+  // -rank / -nranks or sets RANK / WORLD_SIZE / LOCAL_RANK (torchrun, mpirun wrappers)
+  auto env_int = [](const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : fallback;
+  };
+  if (nranks_ == 1 && rank_ == 0) {
+    nranks_ = env_int("WORLD_SIZE", 1);
+    rank_ = env_int("RANK", 0);
+    if (nranks_ > 1 && device_ == 0) device_ = env_int("LOCAL_RANK", rank_);
+  }
+  if (da_processors_z_ > 0 && da_processors_z_ != nranks_)
+    throw std::runtime_error(std::format("da_processors_z = {} but {} process(es) were started: launch one process per z-slab (-rank r -nranks N)",
+                                         da_processors_z_, nranks_));
+  g.rank = rank_;
+  g.nranks = nranks_;
   g.track_ids = 0;
-  B200_CALL(xb_create(&g, nullptr, &ctx));
+  {  // the library's split (DMDA's: the first nz % N slabs are one plane thicker)
+    const int base = geom.geom_nz / nranks_, rem = geom.geom_nz % nranks_;
+    nzl_ = base + (rank_ < rem ? 1 : 0);
+    z0_ = rank_ * base + std::min(rank_, rem);
+  }
+  unsigned char uid[128];
+  const void* uid_ptr = nullptr;
+  if (nranks_ > 1) {
+    // MPI_Init's role: rank 0 creates the NCCL id and leaves it in a file the other ranks wait for
+    if (comm_file_.empty()) comm_file_ = out_dir + "/.xpic_b200_comm_id";
+    if (rank_ == 0) {
+      B200_CALL(xb_comm_unique_id(uid));
+      std::filesystem::create_directories(std::filesystem::path(comm_file_).parent_path());
+      std::ofstream(comm_file_ + ".tmp", std::ios::binary).write(reinterpret_cast<const char*>(uid), sizeof(uid));
+      std::filesystem::rename(comm_file_ + ".tmp", comm_file_);
+    }
+    else {
+      for (int tries = 0; !std::filesystem::exists(comm_file_) || std::filesystem::file_size(comm_file_) != sizeof(uid); ++tries) {
+        if (tries > 6000) throw std::runtime_error("rank " + std::to_string(rank_) + ": no communicator id in " + comm_file_);
+        std::this_thread::sleep_for(std::chrono::milliseconds(10));
+      }
+      std::ifstream(comm_file_, std::ios::binary).read(reinterpret_cast<char*>(uid), sizeof(uid));
+    }
+    uid_ptr = uid;
+  }
+  if (rank_ != 0) std::cout.setstate(std::ios_base::failbit);  // PetscPrintf(PETSC_COMM_WORLD, ...): rank 0 talks
+  B200_CALL(xb_create(&g, uid_ptr, &ctx));
+  if (nranks_ > 1 && rank_ == 0) std::filesystem::remove(comm_file_);  // every rank has joined the communicator
   for (int w = 0; w < 2; ++w) B200_CALL(xb_solver_set(ctx, w, rtol_[w], atol_[w], maxit_[w], 30, precond_));
   // SNESSetTolerances + the Crank-Nicolson tolerance 0.5 * atol (eccapfim/simulation.cpp:384, particles.cpp:99-101)
   B200_CALL(xb_nonlinear_set(ctx, snes_atol_, snes_rtol_, snes_stol_, snes_maxit_, 10, 12, 0.5 * snes_atol_, 30));
 
-  const int64_t ncells = (int64_t)geom.geom_nx * geom.geom_ny * geom.geom_nz;
+  const int64_t ncells = (int64_t)geom.geom_nx * geom.geom_ny * nzl_;
   for (const auto& p : sorts_) {
     int32_t sid = 0;
     B200_CALL(xb_species_add(ctx, p.q, p.m, p.n, p.Np, (int64_t)(1.5 * ncells * p.Np) + 4096, &sid));
@@ -282,21 +390,50 @@ int Simulation::initialize()
     Particles& sort = get_named_particles(pr.particles);
     const SortParameters& sp = sort.parameters;
     const double frac = sp.Np / (geom.dx * geom.dy * geom.dz);
-    const int64_t count = (int64_t)((geom.geom_x * geom.geom_y * geom.geom_z) * frac);
+    // number_of_particles of ParticlesBuilder::load_coordinate (particles_builder.cpp:16-37), truncated like its PetscInt
+    int64_t count = 0;
+    if (pr.coordinate == "CoordinateInBox")
+      count = (int64_t)(((pr.box_max[0] - pr.box_min[0]) * (pr.box_max[1] - pr.box_min[1]) * (pr.box_max[2] - pr.box_min[2])) * frac);
+    else if (pr.coordinate == "CoordinateInCylinder")
+      count = (int64_t)(M_PI * (pr.radius * pr.radius) * pr.height * frac);
+    else
+      count = sp.Np;
     auto tm = [&](double T) { return std::sqrt(-2.0 * (T * sp.m / mec2) * std::log(r01())); };
+    const double T[3] = {sp.Tx, sp.Ty, sp.Tz}, p0[3] = {sp.px, sp.py, sp.pz};
     for (int64_t i = 0; i < count; ++i) {
       Point pt;
-      pt.r[0] = 0.0 + r01() * (geom.geom_x - 0.0);
-      pt.r[1] = 0.0 + r01() * (geom.geom_y - 0.0);
-      pt.r[2] = 0.0 + r01() * (geom.geom_z - 0.0);
-      const double T[3] = {sp.Tx, sp.Ty, sp.Tz}, p0[3] = {sp.px, sp.py, sp.pz};
-      for (int c = 0; c < 3; ++c) {
-        const double sn = std::sin(2.0 * M_PI * r01());  // the sine factor is drawn first
-        pt.p[c] = p0[c] + sn * tm(T[c]);
+      // src/utils/particles_load.cpp:6-32: every rank draws the whole stream and keeps its own particles
+      if (pr.coordinate == "CoordinateInBox") {
+        for (int c = 0; c < 3; ++c) pt.r[c] = pr.box_min[c] + r01() * (pr.box_max[c] - pr.box_min[c]);
       }
-      if (pr.tov) {
-        const double den = std::sqrt(sp.m * sp.m + (pt.p[0] * pt.p[0] + pt.p[1] * pt.p[1] + pt.p[2] * pt.p[2]));
-        for (double& v : pt.p) v /= den;
+      else if (pr.coordinate == "CoordinateInCylinder") {
+        const double r = pr.radius * std::sqrt(r01());
+        const double phi = 2.0 * M_PI * r01();
+        pt.r[0] = pr.center[0] + r * std::cos(phi);
+        pt.r[1] = pr.center[1] + r * std::sin(phi);
+        pt.r[2] = pr.center[2] + pr.height * (r01() - 0.5);
+      }
+      else {
+        for (int c = 0; c < 3; ++c) pt.r[c] = pr.center[c];
+      }
+      if (pr.momentum == "PreciseMomentum") {
+        for (int c = 0; c < 3; ++c) pt.p[c] = pr.value[c];
+      }
+      else {
+        const bool cosine = pr.momentum == "MaxwellCosinePerturbation";  // particles_load.cpp:78-104
+        for (int c = 0; c < 3; ++c) {
+          const double sn = std::sin(2.0 * M_PI * r01());  // the sine factor is drawn first
+          pt.p[c] = (cosine ? 0.0 : p0[c]) + sn * tm(T[c]);
+        }
+        if (pr.tov || cosine) {
+          const double den = std::sqrt(sp.m * sp.m + (pt.p[0] * pt.p[0] + pt.p[1] * pt.p[1] + pt.p[2] * pt.p[2]));
+          for (double& v : pt.p) v /= den;
+        }
+        if (cosine)
+          for (int c = 0; c < 3; ++c) {
+            const double v0 = pr.amplitude[c] * std::sqrt(T[c] / (sp.m * mec2));
+            pt.p[c] += v0 * std::cos(2.0 * M_PI * pr.wave_number[c] * pt.r[c] / (pr.mbox_max[c] - pr.mbox_min[c]));
+          }
       }
       sort.add_particle(pt);
     }
@@ -304,22 +441,22 @@ int Simulation::initialize()
   }
 
   // after a restart the tables of the backup continue (rows up to `start` are already there)
-  energy_ = std::make_unique<Table>(out_dir + "/temporal/energy.txt", restart);
-  energy_cons_ = std::make_unique<Table>(out_dir + "/temporal/energy_conservation.txt", restart);
+  energy_ = std::make_unique<Table>(rank_ == 0 ? out_dir + "/temporal/energy.txt" : std::string(), restart);
+  energy_cons_ = std::make_unique<Table>(rank_ == 0 ? out_dir + "/temporal/energy_conservation.txt" : std::string(), restart);
   K_.assign(particles_.size(), 0.0);
   K0_ = stdK_ = K_;
   if (scheme == XB_ECCAPFIM) {  // eccapfim/simulation.cpp:28
-    convergence_ = std::make_unique<Table>(out_dir + "/temporal/convergence_history.txt", restart);
+    convergence_ = std::make_unique<Table>(rank_ == 0 ? out_dir + "/temporal/convergence_history.txt" : std::string(), restart);
     if (!restart && diagnose_convergence(start)) return 1;
   }
   if (scheme != XB_ECSIM) {  // ChargeConservation: interfaces/simulation.cpp:32-38 (J), ecsimcorr/simulation.cpp:103-110 (currJe)
-    charge_ = std::make_unique<Table>(out_dir + "/temporal/charge_conservation.txt", restart);
+    charge_ = std::make_unique<Table>(rank_ == 0 ? out_dir + "/temporal/charge_conservation.txt" : std::string(), restart);
     charge_header_ = restart;
     for (size_t i = 0; i < particles_.size(); ++i) B200_CALL(xb_charge_density(ctx, (int32_t)i, nullptr));  // ChargeConservation::initialize
     if (!restart && diagnose_charge(start)) return 1;
   }
   // MomentumConservation (interfaces/simulation.cpp:54-56): initialize() stores P at t = 0
-  momentum_ = std::make_unique<Table>(out_dir + "/temporal/momentum_conservation.txt", restart);
+  momentum_ = std::make_unique<Table>(rank_ == 0 ? out_dir + "/temporal/momentum_conservation.txt" : std::string(), restart);
   P0_.assign(particles_.size(), {0.0, 0.0, 0.0});
   for (size_t i = 0; i < particles_.size(); ++i) {
     double o[6];
@@ -352,24 +489,44 @@ int Simulation::diagnose_fields(int t)
     for (size_t i = 0; i < particles_.size(); ++i)
       if (particles_[i]->parameters.sort_name == sort) sid = (int32_t)i;
     if (sid < 0) throw std::runtime_error("No particles with name " + sort);
-    f.resize((size_t)geom.geom_nx * geom.geom_ny * geom.geom_nz);
+    f.resize((size_t)geom.geom_nx * geom.geom_ny * nzl_);
     B200_CALL(xb_distribution_moment(ctx, sid, XB_MOMENT_DENSITY, f.data()));
     out.assign(f.begin(), f.end());
     const std::string dir = out_dir + "/" + sort + "/density";
     std::filesystem::create_directories(dir);
-    std::ofstream file(dir + "/" + std::format("{:0{}d}", t, width), std::ios::binary);
-    file.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)(out.size() * sizeof(float)));
-    if (!file) throw std::runtime_error("DistributionMoment: cannot write into " + dir);
+    if (write_slab(dir + "/" + std::format("{:0{}d}", t, width), out, 1)) return 1;
   }
   for (const std::string& field : field_views_) {
     if (get_named_vector(field, f)) return 1;
     out.assign(f.begin(), f.end());
     const std::string dir = out_dir + "/" + field;
     std::filesystem::create_directories(dir);
-    std::ofstream file(dir + "/" + std::format("{:0{}d}", t, width), std::ios::binary);
-    file.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)(out.size() * sizeof(float)));
-    if (!file) throw std::runtime_error("FieldView: cannot write into " + dir);
+    if (write_slab(dir + "/" + std::format("{:0{}d}", t, width), out, 3)) return 1;
   }
+  return 0;
+}
+
+// One dump file for all ranks, as MPIBinaryFile writes it through an MPI subarray view (field_view.cpp:59-95):
+// with z-slabs the slab of rank r is a contiguous range of the natural [z][y][x][c] image, written at its offset.
+int Simulation::write_slab(const std::string& path, const std::vector<float>& slab, int components)
+{
+  const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT, 0644);
+  if (fd < 0) throw std::runtime_error("cannot open " + path + " for writing");
+  const off_t offset = (off_t)sizeof(float) * components * geom.geom_nx * geom.geom_ny * (off_t)z0_;
+  const char* data = reinterpret_cast<const char*>(slab.data());
+  size_t left = slab.size() * sizeof(float);
+  off_t at = offset;
+  while (left > 0) {
+    const ssize_t w = ::pwrite(fd, data, left, at);
+    if (w <= 0) {
+      ::close(fd);
+      throw std::runtime_error("short write into " + path);
+    }
+    data += w;
+    at += w;
+    left -= (size_t)w;
+  }
+  ::close(fd);
   return 0;
 }
 
@@ -381,8 +538,9 @@ int Simulation::timestep_implementation(int /* t */)
 
 int Simulation::calculate()
 {
+  wall_start_ = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   for (int t = start + 1; t <= geom.geom_nt; ++t) {
-    std::cout << std::format("Timestep = {:.4f} [1/w_pe] = {} [dt]", t * geom.dt, t) << "\n";
+    if (rank_ == 0) std::cout << std::format("Timestep = {:.4f} [1/w_pe] = {} [dt]", t * geom.dt, t) << "\n";
     if (timestep_implementation(t)) return 1;
     if (scheme == XB_ECCAPFIM) {  // the LOG lines of calc_iteration, eccapfim/simulation.cpp:80-96
       int32_t its = 0, fev = 0, reason = 0;
@@ -403,6 +561,7 @@ int Simulation::calculate()
     if (diagnose_momentum(t)) return 1;
     if (diagnose_fields(t)) return 1;
     if (diagnose_energy(t)) return 1;
+    if (log_levels_ && diagnose_log(t)) return 1;
     if (backup_period_ > 0 && t % backup_period_ == 0 && save_backup(t)) return 1;
   }
   std::cout << "Summary of Stages:\n";  // utils/sync_clock.cpp:85-91
@@ -419,8 +578,85 @@ int Simulation::calculate()
   return 0;
 }
 
+// LogView (src/diagnostics/log_view.cpp): the per-stage clocks of the step.  The reference reads PETSc's log
+// stages; here the stage clocks are CUDA-event times of the library (xb_timing), one "rank" per GPU, so the
+// Comm-Avg column is the stage time itself.  Same files, same columns:
+//   log-EachTimestep.txt       (:33-110)  Timestep  Total_[sec]  <stage>: seconds and % of the step
+//   log-DiagnosePeriodAvg.txt  (:112-235) rewritten every diagnose_period: totals and per-step averages of the period
+//   log-AllTimestepsSummary.txt (:237-247) PetscLogView's role: the totals since the start
+int Simulation::diagnose_log(int t)
+{
+  static const char* names_ec[XB_STAGE_COUNT] = {"Clear sources", "First push", "Advance field", "Second push", "Correct fields", "Final update"};
+  static const char* names_corr[XB_STAGE_COUNT] = {"Clear sources", "First push", "Predict field", "Second push", "Correct fields", "Final update"};
+  static const char* names_cap[XB_STAGE_COUNT] = {"Init iteration", "-", "Calc iteration", "-", "-", "After iteration"};
+  const char* const* names = scheme == XB_ECCAPFIM ? names_cap : (scheme == XB_ECSIMCORR ? names_corr : names_ec);
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  if (log_prev_wall_ == 0) log_prev_wall_ = log_period_wall_ = wall_start_;
+  std::array<double, XB_STAGE_COUNT> now{};
+  for (int st = 0; st < XB_STAGE_COUNT; ++st) {
+    int64_t calls = 0;
+    B200_CALL(xb_timing(ctx, st, &now[st], &calls));
+  }
+  if (rank_ != 0) {
+    log_prev_wall_ = wall;
+    log_prev_stage_ = now;
+    return 0;
+  }
+  auto underscored = [](std::string v) {
+    for (char& ch : v)
+      if (ch == ' ') ch = '_';
+    return v;
+  };
+  if (log_levels_ & 1) {
+    if (!log_each_) {
+      log_each_ = std::make_unique<std::ofstream>(out_dir + "/log-EachTimestep.txt");
+      *log_each_ << "Timestep  Total_[sec]  " << std::format("{:<19s}", "Main_Stage");
+      for (int st = 0; st < XB_STAGE_COUNT; ++st)
+        if (names[st][0] != '-') *log_each_ << std::format("{:<19s}", underscored(names[st]));
+      *log_each_ << "\n";
+    }
+    const double total = wall - log_prev_wall_;
+    double staged = 0.0;
+    for (int st = 0; st < XB_STAGE_COUNT; ++st) staged += now[st] - log_prev_stage_[st];
+    *log_each_ << std::format("{:5d}     {:9.3e}    ", t, total);
+    auto cell = [&](double sec) { *log_each_ << std::format("{:<6.4e} {:5.1f}%  ", sec, total > 0.0 ? 100.0 * sec / total : 0.0); };
+    cell(std::max(0.0, total - staged));  // PETSc's "Main Stage": everything outside the logged stages (diagnostics, I/O)
+    for (int st = 0; st < XB_STAGE_COUNT; ++st)
+      if (names[st][0] != '-') cell(now[st] - log_prev_stage_[st]);
+    *log_each_ << "\n";
+    if (t % geom.diagnose_period == 0) log_each_->flush();
+  }
+  if (t % geom.diagnose_period == 0) {
+    auto summary = [&](const std::string& file, double t0, const std::array<double, XB_STAGE_COUNT>& s0, int steps) {
+      std::ofstream f(file);
+      const double period = wall - t0;
+      f << std::format("Total time (sec):     {:5.3e}\n", period);
+      f << "\nSummary of Stages:    ------------ Time ------------\n";
+      f << "                        Comm-Avg  Period-Avg  %Total\n";
+      double staged = 0.0;
+      for (int st = 0; st < XB_STAGE_COUNT; ++st) staged += now[st] - s0[st];
+      auto line = [&](int idx, const char* name, double sec) {
+        if (period <= 0.0 || 100.0 * sec / period < 0.1) return;
+        f << std::format("{:2d}:  {:>15s}: {:6.4e}  {:6.4e}  {:5.1f}%\n", idx, name, sec, sec / std::max(steps, 1), 100.0 * sec / period);
+      };
+      line(0, "Main Stage", std::max(0.0, period - staged));
+      for (int st = 0, idx = 1; st < XB_STAGE_COUNT; ++st)
+        if (names[st][0] != '-') line(idx++, names[st], now[st] - s0[st]);
+      f << "\n";
+    };
+    if (log_levels_ & 2) summary(out_dir + "/log-DiagnosePeriodAvg.txt", log_period_wall_, log_period_stage_, geom.diagnose_period);
+    if (log_levels_ & 4) summary(out_dir + "/log-AllTimestepsSummary.txt", wall_start_, std::array<double, XB_STAGE_COUNT>{}, t - start);
+    log_period_wall_ = wall;
+    log_period_stage_ = now;
+  }
+  log_prev_wall_ = wall;
+  log_prev_stage_ = now;
+  return 0;
+}
+
 int Simulation::finalize()
 {
+  if (log_each_) log_each_->flush();
   if (energy_) energy_->flush();
   if (energy_cons_) energy_cons_->flush();
   if (convergence_) convergence_->flush();
@@ -472,19 +708,38 @@ int Simulation::save_backup(int t)
   const std::string dir = std::format("{}/simulation_backup/{}", out_dir, t);
   std::filesystem::create_directories(dir);
   std::vector<double> f;
+  const size_t n3 = (size_t)3 * geom.geom_nx * geom.geom_ny * geom.geom_nz;
   for (const char* name : {"E", "B", "B0"}) {  // simulation_backup_builder.cpp:17-21
     if (get_named_vector(name, f)) return 1;
-    std::ofstream file(dir + "/" + name, std::ios::binary);
-    const int32_t header[2] = {byteswap(VEC_FILE_CLASSID), byteswap((int32_t)f.size())};
-    file.write(reinterpret_cast<const char*>(header), sizeof(header));
-    write_be_doubles(file, f.data(), f.size());
-    if (!file) throw std::runtime_error("SimulationBackup: cannot write " + dir + "/" + name);
-    std::ofstream(dir + "/" + name + ".info") << "-vecload_block_size 3\n";
+    const std::string path = dir + "/" + name;
+    const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT, 0644);
+    if (fd < 0) throw std::runtime_error("SimulationBackup: cannot write " + path);
+    bool ok = true;
+    if (rank_ == 0) {
+      const int32_t header[2] = {byteswap(VEC_FILE_CLASSID), byteswap((int32_t)n3)};
+      ok = ::pwrite(fd, header, sizeof(header), 0) == (ssize_t)sizeof(header);
+      std::ofstream(path + ".info") << "-vecload_block_size 3\n";
+    }
+    // the slab of this rank inside the natural-order image (one file for all ranks, as VecView writes it)
+    std::vector<double> be(f);
+    for (double& x : be) x = byteswap(x);
+    const off_t at = 8 + (off_t)sizeof(double) * 3 * geom.geom_nx * geom.geom_ny * (off_t)z0_;
+    const char* data = reinterpret_cast<const char*>(be.data());
+    size_t left = be.size() * sizeof(double), done = 0;
+    while (ok && left > 0) {
+      const ssize_t w = ::pwrite(fd, data + done, left, at + (off_t)done);
+      ok = w > 0;
+      if (ok) { done += (size_t)w; left -= (size_t)w; }
+    }
+    ::close(fd);
+    if (!ok) throw std::runtime_error("SimulationBackup: cannot write " + path);
   }
   std::vector<Point> pts;
   for (auto& sort : particles_) {
     if (sort->download(pts)) return 1;
-    const std::string base = dir + "/" + sort->parameters.sort_name;
+    // one rank: the reference's file names; several ranks: one pair of files per rank (the reference's MPI-IO viewer
+    // concatenates the ranks' particles into one file, which needs the counts of the lower ranks first)
+    const std::string base = dir + "/" + sort->parameters.sort_name + (nranks_ > 1 ? std::format(".rank{}", rank_) : std::string());
     const int32_t n = byteswap((int32_t)pts.size());
     std::ofstream(base + ".numparts", std::ios::binary).write(reinterpret_cast<const char*>(&n), sizeof(n));
     std::ofstream file(base, std::ios::binary);
@@ -494,6 +749,7 @@ int Simulation::save_backup(int t)
   // save_temporal_diagnostics (:98-106): the tables as they are now
   for (Table* tb : {energy_.get(), energy_cons_.get(), convergence_.get(), charge_.get(), momentum_.get()})
     if (tb) tb->flush();
+  if (rank_ != 0) return 0;
   if (std::filesystem::exists(out_dir + "/temporal"))
     std::filesystem::copy(out_dir + "/temporal", dir + "/temporal",
                           std::filesystem::copy_options::overwrite_existing | std::filesystem::copy_options::recursive);
@@ -507,7 +763,8 @@ int Simulation::load_backup(int t)
   const std::string dir = std::format("{}/simulation_backup/{}", out_dir, t);
   if (!std::filesystem::exists(dir)) throw std::runtime_error("Cannot load the timestep, no backup directory " + dir);
   const size_t n3 = (size_t)3 * geom.geom_nx * geom.geom_ny * geom.geom_nz;
-  std::vector<double> f(n3);
+  const size_t nloc = (size_t)3 * geom.geom_nx * geom.geom_ny * nzl_, off = (size_t)3 * geom.geom_nx * geom.geom_ny * z0_;
+  std::vector<double> f(nloc);
   const std::pair<const char*, int> fields[] = {{"E", XB_E}, {"B", XB_B}, {"B0", XB_B0}};
   for (auto& [name, id] : fields) {
     std::ifstream file(dir + "/" + name, std::ios::binary);
@@ -515,30 +772,38 @@ int Simulation::load_backup(int t)
     file.read(reinterpret_cast<char*>(header), sizeof(header));
     if (!file || byteswap(header[0]) != VEC_FILE_CLASSID || (size_t)byteswap(header[1]) != n3)
       throw std::runtime_error(std::string("SimulationBackup: ") + name + " is not a PETSc binary Vec of this geometry");
-    read_be_doubles(file, f.data(), n3);
+    file.seekg((std::streamoff)(8 + off * sizeof(double)));
+    read_be_doubles(file, f.data(), nloc);
     if (!file) throw std::runtime_error(std::string("SimulationBackup: short read of ") + name);
     B200_CALL(xb_field_upload(ctx, id, 0, f.data()));
   }
   for (auto& sort : particles_) {
-    const std::string base = dir + "/" + sort->parameters.sort_name;
-    int32_t n = 0;
-    std::ifstream(base + ".numparts", std::ios::binary).read(reinterpret_cast<char*>(&n), sizeof(n));
-    n = byteswap(n);
-    std::ifstream file(base, std::ios::binary);
-    std::vector<double> raw((size_t)6 * (size_t)std::max(n, 0));
-    read_be_doubles(file, raw.data(), raw.size());
-    if (!file) throw std::runtime_error("SimulationBackup: short read of " + base);
-    for (int32_t i = 0; i < n; ++i) {
-      Point pt;
-      for (int c = 0; c < 3; ++c) {
-        pt.r[c] = raw[6 * (size_t)i + c];
-        pt.p[c] = raw[6 * (size_t)i + 3 + c];
+    // every rank reads every particle file and keeps the particles of its slab (add_particle)
+    std::vector<std::string> bases;
+    const std::string plain = dir + "/" + sort->parameters.sort_name;
+    if (std::filesystem::exists(plain + ".numparts")) bases.push_back(plain);
+    for (int r = 0; std::filesystem::exists(std::format("{}.rank{}.numparts", plain, r)); ++r) bases.push_back(std::format("{}.rank{}", plain, r));
+    if (bases.empty()) throw std::runtime_error("SimulationBackup: no particle file " + plain);
+    for (const std::string& base : bases) {
+      int32_t n = 0;
+      std::ifstream(base + ".numparts", std::ios::binary).read(reinterpret_cast<char*>(&n), sizeof(n));
+      n = byteswap(n);
+      std::ifstream file(base, std::ios::binary);
+      std::vector<double> raw((size_t)6 * (size_t)std::max(n, 0));
+      read_be_doubles(file, raw.data(), raw.size());
+      if (!file) throw std::runtime_error("SimulationBackup: short read of " + base);
+      for (int32_t i = 0; i < n; ++i) {
+        Point pt;
+        for (int c = 0; c < 3; ++c) {
+          pt.r[c] = raw[6 * (size_t)i + c];
+          pt.p[c] = raw[6 * (size_t)i + 3 + c];
+        }
+        sort->add_particle(pt);
       }
-      sort->add_particle(pt);
     }
     if (sort->flush()) return 1;
   }
-  if (std::filesystem::exists(dir + "/temporal"))  // load_temporal_diagnostics (:162-169)
+  if (rank_ == 0 && std::filesystem::exists(dir + "/temporal"))  // load_temporal_diagnostics (:162-169)
     std::filesystem::copy(dir + "/temporal", out_dir + "/temporal",
                           std::filesystem::copy_options::overwrite_existing | std::filesystem::copy_options::recursive);
   std::cout << std::format("  Simulation is successfully loaded from {:.1f} [1/w_pe], {} [dt]", t * geom.dt, t) << "\n";
@@ -634,16 +899,12 @@ int Simulation::prime_energy()
 int Simulation::diagnose_energy(int t)
 {
   auto field = [&](const char* name, double& w, double& sd) {
-    std::vector<double> f;
-    if (get_named_vector(name, f)) return 1;
-    double n2 = 0, mean[3] = {0, 0, 0};
-    for (size_t i = 0; i < f.size(); ++i) {
-      n2 += f[i] * f[i];
-      mean[i % 3] += f[i];
-    }
-    w = 0.5 * n2;  // energy.cpp:46-50 (the norm is squared again there)
+    // VecNorm and VecStrideSumAll of energy.cpp:43-59 on the device, summed over all ranks
+    double sums[4];
+    B200_CALL(xb_field_sums(ctx, std::string(name) == "E" ? XB_E : XB_B, 0, sums));
+    w = 0.5 * sums[3];  // energy.cpp:46-50 (the norm is squared again there)
     const double g3 = (double)geom.geom_nx * geom.geom_ny * geom.geom_nz;
-    sd = std::sqrt((w - 0.5 * (mean[0] * mean[0] + mean[1] * mean[1] + mean[2] * mean[2]) / g3) / g3);
+    sd = std::sqrt((w - 0.5 * (sums[0] * sums[0] + sums[1] * sums[1] + sums[2] * sums[2]) / g3) / g3);
     return 0;
   };
   auto kinetic = [&]() {

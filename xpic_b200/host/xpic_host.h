@@ -82,7 +82,8 @@ public:
   /// reads the reference's config.json schema
   int configure(const std::string& config_path);
   /// options the reference takes from PETSc's database: -ksp_rtol/-ksp_atol/-ksp_max_it (ecsim),
-  /// -predict_ksp_*, -correct_ksp_* (ecsimcorr), plus -curl_sign, -device, -precond
+  /// -predict_ksp_*, -correct_ksp_* (ecsimcorr), plus -curl_sign, -device, -precond, and the launch of one
+  /// process per GPU: -rank r -nranks N [-comm_file path] (defaults: RANK / WORLD_SIZE / LOCAL_RANK of the environment)
   void set_option(const std::string& key, const std::string& value);
 
   int initialize();   // interfaces::Simulation::initialize (src/interfaces/simulation.cpp:16-73)
@@ -95,6 +96,8 @@ public:
   Particles& get_named_particles(const std::string& name);  // throws std::runtime_error if unknown
 
   Geometry geom;
+  int slab_begin() const { return z0_; }  // owned planes [slab_begin, slab_end) of this process
+  int slab_end() const { return z0_ + nzl_; }
   std::string scheme_name = "ecsim";
   std::string out_dir = "results";
   std::vector<std::shared_ptr<Particles>> particles_;
@@ -111,10 +114,25 @@ private:
   int prime_energy();
   int save_backup(int t);           // SimulationBackup::save
   int load_backup(int t);           // SimulationBackup::load
-  struct Preset {
+  struct Preset {  // SetParticles: coordinate and momentum generators (src/utils/particles_load.h)
     std::string particles, coordinate, momentum;
     bool tov = false;
+    std::array<double, 3> box_min{}, box_max{};       // CoordinateInBox
+    std::array<double, 3> center{};                   // CoordinateInCylinder centre / PreciseCoordinate value
+    double radius = 0, height = 0;                    // CoordinateInCylinder
+    std::array<double, 3> value{};                    // PreciseMomentum
+    std::array<double, 3> amplitude{}, wave_number{}, mbox_min{}, mbox_max{};  // MaxwellCosinePerturbation
   };
+  int diagnose_log(int t);          // LogView (src/diagnostics/log_view.cpp)
+  int write_slab(const std::string& path, const std::vector<float>& slab, int components);  // every rank's part of one dump file
+  int log_levels_ = 0;              // bit 0 EachTimestep, bit 1 DiagnosePeriodAvg, bit 2 AllTimestepsSummary
+  double log_prev_wall_ = 0, log_period_wall_ = 0, wall_start_ = 0;
+  std::array<double, XB_STAGE_COUNT> log_prev_stage_{}, log_period_stage_{};
+  std::unique_ptr<std::ofstream> log_each_;
+  int da_processors_z_ = -1;        // "mpi": {"da_processors_z"} (utils/configuration.cpp:111-130)
+  int rank_ = 0, nranks_ = 1;       // z-slab of this process (-rank / -nranks or RANK / WORLD_SIZE)
+  std::string comm_file_;           // where rank 0 leaves the communicator id for the other ranks
+  int z0_ = 0, nzl_ = 0;            // owned planes
   std::vector<SortParameters> sorts_;
   std::vector<Preset> presets_;
   std::vector<std::string> density_views_;  // "Diagnostics": [{"diagnostic": "DistributionMoment", "particles": ..., "moment": "density"}]
