@@ -34,7 +34,14 @@ typedef struct xb_grid {
   int32_t rank;      /* z-slab index */
   int32_t nranks;    /* number of z-slabs (1 = single GPU) */
   int32_t track_ids; /* 1: carry a 64-bit particle id (parity / diagnostics), 0: do not */
+  /* "da_boundary_x/y/z" (src/utils/configuration.cpp:88-108): XB_BOUNDARY_PERIODIC or XB_BOUNDARY_OPEN
+   * (DM_BOUNDARY_NONE / DM_BOUNDARY_GHOSTED: nodes outside the box do not exist -- their matrix entries and
+   * deposits are dropped, gathers read zero there, particles that leave are removed,
+   * src/interfaces/particles.cpp:100-103).  This build: x and y periodic only; open z with scheme XB_ECSIM. */
+  int32_t boundary[3];
 } xb_grid;
+
+enum { XB_BOUNDARY_PERIODIC = 0, XB_BOUNDARY_OPEN = 1 };
 
 enum { XB_ECSIM = 0, XB_ECSIMCORR = 1, XB_ECCAPFIM = 2 }; /* "Simulation" key, src/interfaces/simulation.cpp:169-178 */
 

@@ -59,6 +59,7 @@ def lib():
         L.xo_csr_export.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32), dp]
         L.xo_spmv.argtypes = [C.c_void_p, C.c_int, dp, dp]
         L.xo_curl.argtypes = [C.c_void_p, C.c_int, dp, dp]
+        L.xo_set_open_z.argtypes = [C.c_void_p, C.c_int]
         L.xo_interpolate.argtypes = [C.c_void_p, dp, dp, dp]
         L.xo_boris_update_vEB.argtypes = [C.c_double, C.c_double, dp, dp, dp]
         L.xo_esirkepov.argtypes = [C.c_void_p, dp, dp, C.c_double, dp]
@@ -91,12 +92,14 @@ def _dp(a):
 class Oracle:
     """One simulation box (all axes periodic), mirroring ecsim::Simulation / ecsimcorr::Simulation."""
 
-    def __init__(self, n, d=(0.5, 0.5, 0.5), dt=1.5, curl_sign=+1):
+    def __init__(self, n, d=(0.5, 0.5, 0.5), dt=1.5, curl_sign=+1, open_z=False):
         self.n = tuple(int(v) for v in n)
         self.d = tuple(float(v) for v in d)
         self.dt = float(dt)
         self.n3 = 3 * self.n[0] * self.n[1] * self.n[2]
         self._h = lib().xo_create(*self.n, *self.d, self.dt, int(curl_sign))
+        if open_z:  # da_boundary_z = DM_BOUNDARY_NONE / GHOSTED
+            lib().xo_set_open_z(self._h, 1)
 
     def __del__(self):
         if getattr(self, "_h", None):

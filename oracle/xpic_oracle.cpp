@@ -103,16 +103,27 @@ struct Sim {
   std::vector<double> Ehk, J;  // eccapfim: E^{n+1/2,k} and the total current of the last evaluation
   Ngmres snes;
 
+  // DM_BOUNDARY_NONE / GHOSTED along z (src/utils/configuration.cpp:88-108): nodes outside the box do not exist.
+  // Their matrix entries and deposits are dropped (Operator::remap_stencil gives -1, MatSetValuesCOO ignores it,
+  // src/utils/operators.cpp:12-43), the ghost values the gathers read there are zero, and a particle that leaves
+  // through such a face is removed (src/interfaces/particles.cpp:100-103).
+  bool open_z = false;
   inline int wrap(int i, int a) const
   {
     int n = N[a];
     i %= n;
     return i < 0 ? i + n : i;
   }
-  // src/utils/utils.h:20-24  ((z*Ny + y)*Nx + x)*3 + c, periodic ghosts folded
+  // src/utils/utils.h:20-24  ((z*Ny + y)*Nx + x)*3 + c, periodic ghosts folded; -1: no such node (open boundary)
   inline int64_t vidx(int x, int y, int z, int c) const
   {
+    if (open_z && (z < 0 || z >= N[2])) return -1;
     return (((int64_t)wrap(z, 2) * N[1] + wrap(y, 1)) * N[0] + wrap(x, 0)) * 3 + c;
+  }
+  inline double get(const double* f, int x, int y, int z, int c) const
+  {
+    const int64_t i = vidx(x, y, z, c);
+    return i < 0 ? 0.0 : f[i];
   }
   inline int64_t cell(int x, int y, int z) const { return ((int64_t)z * N[1] + y) * N[0] + x; }
 };
@@ -162,15 +173,15 @@ void curl(const Sim& s, bool positive, const double* f, double* out)
         double cx, cy, cz;
         if (positive) {
           const int xp = x + 1, yp = y + 1, zp = z + 1;
-          cx = (+iy * f[s.vidx(x, yp, z, 2)] - iy * f[s.vidx(x, y, z, 2)]) + (-iz * f[s.vidx(x, y, zp, 1)] + iz * f[s.vidx(x, y, z, 1)]);
-          cy = (-ix * f[s.vidx(xp, y, z, 2)] + ix * f[s.vidx(x, y, z, 2)]) + (+iz * f[s.vidx(x, y, zp, 0)] - iz * f[s.vidx(x, y, z, 0)]);
-          cz = (+ix * f[s.vidx(xp, y, z, 1)] - ix * f[s.vidx(x, y, z, 1)]) + (-iy * f[s.vidx(x, yp, z, 0)] + iy * f[s.vidx(x, y, z, 0)]);
+          cx = (+iy * s.get(f, x, yp, z, 2) - iy * s.get(f, x, y, z, 2)) + (-iz * s.get(f, x, y, zp, 1) + iz * s.get(f, x, y, z, 1));
+          cy = (-ix * s.get(f, xp, y, z, 2) + ix * s.get(f, x, y, z, 2)) + (+iz * s.get(f, x, y, zp, 0) - iz * s.get(f, x, y, z, 0));
+          cz = (+ix * s.get(f, xp, y, z, 1) - ix * s.get(f, x, y, z, 1)) + (-iy * s.get(f, x, yp, z, 0) + iy * s.get(f, x, y, z, 0));
         }
         else {
           const int xm = x - 1, ym = y - 1, zm = z - 1;
-          cx = (+iy * f[s.vidx(x, y, z, 2)] - iy * f[s.vidx(x, ym, z, 2)]) + (-iz * f[s.vidx(x, y, z, 1)] + iz * f[s.vidx(x, y, zm, 1)]);
-          cy = (-ix * f[s.vidx(x, y, z, 2)] + ix * f[s.vidx(xm, y, z, 2)]) + (+iz * f[s.vidx(x, y, z, 0)] - iz * f[s.vidx(x, y, zm, 0)]);
-          cz = (+ix * f[s.vidx(x, y, z, 1)] - ix * f[s.vidx(xm, y, z, 1)]) + (-iy * f[s.vidx(x, y, z, 0)] + iy * f[s.vidx(x, ym, z, 0)]);
+          cx = (+iy * s.get(f, x, y, z, 2) - iy * s.get(f, x, ym, z, 2)) + (-iz * s.get(f, x, y, z, 1) + iz * s.get(f, x, y, zm, 1));
+          cy = (-ix * s.get(f, x, y, z, 2) + ix * s.get(f, xm, y, z, 2)) + (+iz * s.get(f, x, y, z, 0) - iz * s.get(f, x, y, zm, 0));
+          cz = (+ix * s.get(f, x, y, z, 1) - ix * s.get(f, xm, y, z, 1)) + (-iy * s.get(f, x, y, z, 0) + iy * s.get(f, x, ym, z, 0));
         }
         const int64_t o = s.vidx(x, y, z, 0);
         out[o + 0] = sg * cx;
@@ -224,7 +235,10 @@ void build_matM(Sim& s)
           for (auto& a : tm) {
             curl_terms(true, a.c, tp);
             for (auto& b : tp) {
+              // both curls drop their own missing columns: the intermediate B site must exist as well
+              if (s.vidx(x + a.dx, y + a.dy, z + a.dz, a.c) < 0) continue;
               const int32_t col = (int32_t)s.vidx(x + a.dx + b.dx, y + a.dy + b.dy, z + a.dz + b.dz, b.c);
+              if (col < 0) continue;
               r.push_back({col, 0.5 * s.dt * s.dt * a.v * b.v});
             }
           }
@@ -264,12 +278,15 @@ void build_matL_pattern(Sim& s)
             for (int j1 = 0; j1 < sz1[1]; ++j1)
               for (int i1 = 0; i1 < sz1[0]; ++i1) {
                 const int64_t row = s.vidx(x + i1 + lo1[0], y + j1 + lo1[1], z + k1 + lo1[2], c1);
+                if (row < 0) continue;
                 for (int c2 = 0; c2 < 3; ++c2) {
                   window(c2, lo2, sz2);
                   for (int k2 = 0; k2 < sz2[2]; ++k2)
                     for (int j2 = 0; j2 < sz2[1]; ++j2)
-                      for (int i2 = 0; i2 < sz2[0]; ++i2)
-                        cols[row].push_back((int32_t)s.vidx(x + i2 + lo2[0], y + j2 + lo2[1], z + k2 + lo2[2], c2));
+                      for (int i2 = 0; i2 < sz2[0]; ++i2) {
+                        const int64_t col = s.vidx(x + i2 + lo2[0], y + j2 + lo2[1], z + k2 + lo2[2], c2);
+                        if (col >= 0) cols[row].push_back((int32_t)col);
+                      }
                 }
               }
         }
@@ -375,7 +392,8 @@ void update_cells_seq(const Sim& s, Species& sp)
     auto& cellg = sp.storage[g];
     auto it = cellg.begin();
     while (it != cellg.end()) {
-      for (int a = 0; a < 3; ++a) g_bound_periodic(s, *it, a);
+      for (int a = 0; a < 3; ++a)
+        if (!(a == 2 && s.open_z)) g_bound_periodic(s, *it, a);  // Particles::correct_coordinates, interfaces/particles.cpp:329-338
       const int vx = (int)std::floor(it->r[0] / s.d[0]);
       const int vy = (int)std::floor(it->r[1] / s.d[1]);
       const int vz = (int)std::floor(it->r[2] / s.d[2]);
@@ -438,12 +456,13 @@ void decompose_ecsim_current(const Sim& s, const Species& sp, const Point& pt, s
         s1[0] = w.wn[2][k1] * w.wn[1][j1] * w.ws[0][i1];
         s1[1] = w.wn[2][k1] * w.ws[1][j1] * w.wn[0][i1];
         s1[2] = w.ws[2][k1] * w.wn[1][j1] * w.wn[0][i1];
+        const int64_t node[3] = {s.vidx(w.is[0] + i1, w.in[1] + j1, w.in[2] + k1, 0), s.vidx(w.in[0] + i1, w.is[1] + j1, w.in[2] + k1, 1),
+                                 s.vidx(w.in[0] + i1, w.in[1] + j1, w.is[2] + k1, 2)};
+        for (int c = 0; c < 3; ++c) {
+          if (node[c] < 0) continue;  // outside an open boundary: dropped
 #pragma omp atomic update
-        currI[s.vidx(w.is[0] + i1, w.in[1] + j1, w.in[2] + k1, 0)] += s1[0] * I_p[0];
-#pragma omp atomic update
-        currI[s.vidx(w.in[0] + i1, w.is[1] + j1, w.in[2] + k1, 1)] += s1[1] * I_p[1];
-#pragma omp atomic update
-        currI[s.vidx(w.in[0] + i1, w.in[1] + j1, w.is[2] + k1, 2)] += s1[2] * I_p[2];
+          currI[node[c]] += s1[c] * I_p[c];
+        }
 
         i[0] = (k1 * 2 + j1) * 3 + (ox + i1);
         i[1] = (k1 * 3 + (oy + j1)) * 2 + i1;
@@ -475,6 +494,7 @@ void add_block_to_csr(Sim& s, int x, int y, int z, const double* coo_v)
       for (int j1 = 0; j1 < sz1[1]; ++j1)
         for (int i1 = 0; i1 < sz1[0]; ++i1) {
           const int64_t row = s.vidx(x + i1 + lo1[0], y + j1 + lo1[1], z + k1 + lo1[2], c1);
+          if (row < 0) continue;
           const int i = (k1 * sz1[1] + j1) * sz1[0] + i1;
           for (int c2 = 0; c2 < 3; ++c2) {
             window(c2, lo2, sz2);
@@ -482,6 +502,7 @@ void add_block_to_csr(Sim& s, int x, int y, int z, const double* coo_v)
               for (int j2 = 0; j2 < sz2[1]; ++j2)
                 for (int i2 = 0; i2 < sz2[0]; ++i2) {
                   const int32_t col = (int32_t)s.vidx(x + i2 + lo2[0], y + j2 + lo2[1], z + k2 + lo2[2], c2);
+                  if (col < 0) continue;
                   const int j = (k2 * sz2[1] + j2) * sz2[0] + i2;
                   const int ind = (c1 * 3 + c2) * 144 + (i * 12 + j);
                   double& dst = csr_at(s.matL, row, col);
@@ -1401,6 +1422,15 @@ void* xo_create(int nx, int ny, int nz, double dx, double dy, double dz, double 
 }
 
 void xo_destroy(void* h) { delete (Sim*)h; }
+
+// "da_boundary_z": DM_BOUNDARY_NONE / DM_BOUNDARY_GHOSTED instead of PERIODIC; call before particles are added
+void xo_set_open_z(void* h, int open)
+{
+  Sim& s = *(Sim*)h;
+  s.open_z = open != 0;
+  build_matM(s);
+  build_matL_pattern(s);
+}
 
 int xo_add_species(void* h, double q, double m, double n, int Np)
 {

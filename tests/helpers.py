@@ -59,6 +59,27 @@ def csr_to_stencil(o, table):
     return coef
 
 
+def csr_to_stencil_open(o, table):
+    """As csr_to_stencil for a box whose z boundary is open: columns outside the box do not exist (coefficient 0)."""
+    import scipy.sparse as sp
+
+    rp, col, val = o.csr(0)
+    A = sp.csr_matrix((val, col, rp), shape=(o.n3, o.n3))
+    nx, ny, nz = o.n
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    node = ((z * ny + y) * nx + x).reshape(-1)
+    coef = np.zeros((len(table), node.size))
+    for k, (c1, c2, dx, dy, dz) in enumerate(table):
+        rows = node * 3 + c1
+        zc = (z + dz).reshape(-1)
+        inside = (zc >= 0) & (zc < nz)
+        cn = ((np.clip(zc, 0, nz - 1).reshape(z.shape) * ny + ((y + dy) % ny)) * nx + ((x + dx) % nx)).reshape(-1)
+        cols = cn * 3 + c2
+        v = np.asarray(A[rows, cols]).reshape(-1)
+        coef[k] = np.where(inside, v, 0.0)
+    return coef
+
+
 def spline2(s):
     s = np.abs(s)
     return np.where(s <= 0.5, 0.75 - s * s, np.where(s < 1.5, 0.5 * (1.5 - s) ** 2, 0.0))

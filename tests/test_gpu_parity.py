@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from helpers import by_id, csr_to_stencil, make_pair, rel_err
+from helpers import by_id, csr_to_stencil, csr_to_stencil_open, make_pair, rel_err
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -609,4 +609,86 @@ def test_decomposition_independence_on_two_gpus(X):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("-> OK") == 3
+    assert r.stdout.count("-> OK") == 4
+
+
+def test_open_z_boundary_state_parity(X):
+    """da_boundary_z = DM_BOUNDARY_NONE / GHOSTED: no nodes outside the box (matrix entries and deposits dropped,
+    zero ghost values), particles that leave through z are removed (src/interfaces/particles.cpp:100-103,
+    src/utils/operators.cpp:12-43).  Operators, deposit and 10 ECSIM steps against the oracle with the same switch."""
+    n = (9, 8, 10)
+    o = O.Oracle(n, open_z=True)
+    s = X.Simulation(n, scheme=X.ECSIM, track_ids=True, open_z=True)
+    sid = o.add_species(Np=30)
+    o.set_particles_maxwell(sid, T=2.0, tov=True)  # hot enough that particles reach the faces within ten steps
+    s.add_species(Np=30)
+    pts, ids = o.get_particles(sid)
+    assert s.add_particles(0, pts, ids) == len(ids)
+    for which in (0, 1):
+        o.solver_set(which, 1e-12, 1e-50, 1000, 30)
+        s.solver_set(which, 1e-12, 1e-50, 1000, 30, 0)
+    rng = np.random.default_rng(17)
+    for name, amp in (("E", 0.02), ("B", 0.05)):
+        f = amp * rng.standard_normal(o.n3)
+        o.set_field(name, f)
+        s.set_field(name, f)
+    x = rng.standard_normal(o.n3)
+    for positive in (True, False):
+        assert rel_err(s.curl(x, positive), o.curl(x, positive)) < 1e-14
+    assert rel_err(s.spmv(x, op=2), o.spmv(x, L=False, M=True)) < 1e-13
+    o.deposit()
+    s.deposit()
+    ref = csr_to_stencil_open(o, X.coef_table())
+    assert np.max(np.abs(s.operator_download() - ref)) / np.max(np.abs(ref)) < 1e-13
+    assert rel_err(s.get_field("currI"), o.get_field("currI")) < 1e-12
+    assert rel_err(s.spmv(x, op=3), o.spmv(x, L=True, M=True)) < 1e-12
+    n0 = o.particle_count()
+    for _ in range(10):
+        o.step(O.ECSIM)
+        s.step()
+    assert o.particle_count() < n0  # the test does exercise the removal
+    assert s.particle_count() == o.particle_count()
+    _compare_state(o, s, 1e-8)
+
+
+def test_host_program_on_two_gpus(X, tmp_path):
+    """The C++ host program as one process per GPU (`-rank r -nranks 2`, the reference's `mpiexec -n 2 ... -da_processors_z 2`,
+    tests/ecsim/CMakeLists.txt:14-16): the energy tables of the 2-rank run equal the reference's golden tables, the
+    field dump is one file written slab-wise by both ranks."""
+    import json
+    import subprocess
+
+    import torch
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "xpic_b200", "_build", "xpic_b200.out")
+    if torch.cuda.device_count() < 2 or not os.path.exists(exe):
+        pytest.skip("needs two GPUs and the host program")
+    cfg = json.load(open(os.path.join(ROOT, "configs", "ecsim_ex1.json")))
+    cfg["OutputDirectory"] = str(tmp_path / "two")
+    cfg["mpi"] = {"da_processors_z": 2}
+    cfg.setdefault("Diagnostics", []).append({"diagnostic": "LogView", "level": "EachTimestep"})
+    path = tmp_path / "two.json"
+    path.write_text(json.dumps(cfg))
+    opts = ["-curl_sign", "-1", "-ksp_max_it", "500", "-ksp_rtol", "1e-11", "-ksp_atol", "1e-50"]
+    procs = [subprocess.Popen([exe, str(path), "-rank", str(r), "-nranks", "2", "-device", str(r)] + opts, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    for table in ("energy.txt", "energy_conservation.txt"):
+        tg, gold = O.read_table(os.path.join(GOLDEN, "ecsim_ex1", table))
+        to, out = O.read_table(str(tmp_path / "two" / "temporal" / table))
+        assert to == tg and out.shape[0] == 11
+        if table == "energy.txt":
+            np.testing.assert_allclose(out[:, 1:4], gold[:11, 1:4], rtol=2e-6, atol=1e-10)
+        else:
+            assert np.max(np.abs(out[:, -1])) < 1e-11
+    assert os.path.exists(str(tmp_path / "two" / "E" / "10")), os.listdir(str(tmp_path / "two"))
+    dump = np.fromfile(str(tmp_path / "two" / "E" / "10"), dtype=np.float32)
+    gold = np.fromfile(os.path.join(GOLDEN, "ecsim_ex1", "E_010.f32"), dtype=np.float32) if os.path.exists(os.path.join(GOLDEN, "ecsim_ex1", "E_010.f32")) else None
+    assert dump.size == 3 * 10 * 10 * 10
+    if gold is not None:
+        np.testing.assert_allclose(dump, gold, rtol=2e-4, atol=2e-7)
+    log = open(str(tmp_path / "two" / "log-EachTimestep.txt")).read().splitlines()
+    assert log[0].split()[:3] == ["Timestep", "Total_[sec]", "Main_Stage"] and len(log) == 11

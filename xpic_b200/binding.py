@@ -29,7 +29,7 @@ class XpicB200Error(RuntimeError):
 
 class _Grid(C.Structure):
     _fields_ = [("n", C.c_int32 * 3), ("d", C.c_double * 3), ("dt", C.c_double), ("curl_sign", C.c_int32), ("device", C.c_int32),
-                ("rank", C.c_int32), ("nranks", C.c_int32), ("track_ids", C.c_int32)]
+                ("rank", C.c_int32), ("nranks", C.c_int32), ("track_ids", C.c_int32), ("boundary", C.c_int32 * 3)]
 
 
 def slab_range(nz, rank, nranks):
@@ -166,7 +166,7 @@ def coef_table():
 
 class Simulation:
     def __init__(self, n, d=(0.5, 0.5, 0.5), dt=1.5, scheme=ECSIM, curl_sign=+1, device=0, rank=0, nranks=1, comm_id=None,
-                 track_ids=True):
+                 track_ids=True, open_z=False):
         self._L = load_library()
         self.n = tuple(int(v) for v in n)
         self.d = tuple(float(v) for v in d)
@@ -185,6 +185,7 @@ class Simulation:
         g.rank = rank
         g.nranks = nranks
         g.track_ids = 1 if track_ids else 0
+        g.boundary[:] = (0, 0, 1 if open_z else 0)  # da_boundary_z = DM_BOUNDARY_NONE / GHOSTED
         self.track_ids = bool(track_ids)
         h = C.c_void_p()
         uid = C.create_string_buffer(comm_id, 128) if comm_id is not None else None

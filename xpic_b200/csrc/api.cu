@@ -285,6 +285,9 @@ static int create_impl(xb_ctx* c, const xb_grid* gr, const void* uid)
   }
   g.Lx = g.nx * g.dx; g.Ly = g.ny * g.dy; g.Lz = g.nz * g.dz;  // utils/world.cpp:97-100
   g.curl_sign = gr->curl_sign < 0 ? -1 : +1;
+  if (gr->boundary[0] != XB_BOUNDARY_PERIODIC || gr->boundary[1] != XB_BOUNDARY_PERIODIC)
+    XB_FAIL("xb_create: da_boundary_x / da_boundary_y other than DM_BOUNDARY_PERIODIC are not covered by this build (z may be open)");
+  g.open_z = gr->boundary[2] != XB_BOUNDARY_PERIODIC ? 1 : 0;
   g.rank = gr->rank; g.nranks = gr->nranks;
   const int base = g.nz / g.nranks, rem = g.nz % g.nranks;
   g.nzl = base + (g.rank < rem ? 1 : 0);
@@ -517,6 +520,7 @@ int xb_step(xb_ctx* c, int32_t scheme)
 {
   XB_API_BEGIN(c);
   if (scheme != XB_ECSIM && scheme != XB_ECSIMCORR && scheme != XB_ECCAPFIM) XB_FAIL("unknown scheme");
+  if (c->g.open_z && scheme != XB_ECSIM) XB_FAIL("an open z boundary is covered for scheme ecsim only");
   XB_CHECK(ensure_sorted(c));
   for (int st = 0; st < XB_STAGE_COUNT; ++st) XB_CHECK(run_stage(c, scheme, st));
   return 0;

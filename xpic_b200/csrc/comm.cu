@@ -149,7 +149,11 @@ int comm_halo_fill(xb_ctx* c, double* v, int w)
   double* own_hi = v + (int64_t)(GZ + g.nzl - w) * p3;
   double* gh_lo = v + (int64_t)(GZ - w) * p3;
   double* gh_hi = v + (int64_t)(GZ + g.nzl) * p3;
-  return comm_exchange(c, own_lo, bytes, own_hi, bytes, gh_hi, bytes, gh_lo, bytes);
+  // open z: nothing crosses the box ends; the ghost planes there hold zeros (DMDA local vectors)
+  const bool down = !(g.open_z && g.rank == 0), up = !(g.open_z && g.rank == g.nranks - 1);
+  if (!down) XB_CUDA(cudaMemsetAsync(gh_lo, 0, bytes, c->stream));
+  if (!up) XB_CUDA(cudaMemsetAsync(gh_hi, 0, bytes, c->stream));
+  return comm_exchange(c, own_lo, down ? bytes : 0, own_hi, up ? bytes : 0, gh_hi, up ? bytes : 0, gh_lo, down ? bytes : 0);
 }
 
 // owned bottom planes += up-neighbour's view of them (its high ghosts go to up's owners) ...
@@ -164,11 +168,13 @@ int comm_halo_reduce(xb_ctx* c, double* v, int wlo, int whi)
   double* gh_hi = v + (int64_t)(GZ + g.nzl) * p3;
   double* r_from_up = cm->recv_buf;               // up's low ghosts = my top planes [nzl - wlo, nzl)
   double* r_from_down = cm->recv_buf + GZ * p3;   // down's high ghosts = my bottom planes [0, whi)
-  XB_CHECK(comm_exchange(c, gh_lo, sizeof(double) * wlo * p3, gh_hi, sizeof(double) * whi * p3, r_from_up,
-                         sizeof(double) * wlo * p3, r_from_down, sizeof(double) * whi * p3));
+  // open z: what was deposited outside the box ends is dropped
+  const bool down = !(g.open_z && g.rank == 0), up = !(g.open_z && g.rank == g.nranks - 1);
+  XB_CHECK(comm_exchange(c, gh_lo, down ? sizeof(double) * wlo * p3 : 0, gh_hi, up ? sizeof(double) * whi * p3 : 0, r_from_up,
+                         up ? sizeof(double) * wlo * p3 : 0, r_from_down, down ? sizeof(double) * whi * p3 : 0));
   // fixed order: contribution from below first, then from above
-  if (whi) XB_CHECK(add_planes(c, v + (int64_t)GZ * p3, r_from_down, whi * p3));
-  if (wlo) XB_CHECK(add_planes(c, v + (int64_t)(GZ + g.nzl - wlo) * p3, r_from_up, wlo * p3));
+  if (whi && down) XB_CHECK(add_planes(c, v + (int64_t)GZ * p3, r_from_down, whi * p3));
+  if (wlo && up) XB_CHECK(add_planes(c, v + (int64_t)(GZ + g.nzl - wlo) * p3, r_from_up, wlo * p3));
   XB_CUDA(cudaMemsetAsync(gh_lo, 0, sizeof(double) * wlo * p3, c->stream));
   XB_CUDA(cudaMemsetAsync(gh_hi, 0, sizeof(double) * whi * p3, c->stream));
   return 0;

@@ -55,6 +55,7 @@ struct Grid {
   int exact_inv;  // bit a set: d[a] is a power of two, r * inv_d == r / d exactly
   double Lx, Ly, Lz;
   int curl_sign;
+  int open_z;  // da_boundary_z is not periodic: no nodes below plane 0 / above plane nz - 1 (xb_grid.boundary)
   int64_t plane;  // nx * ny
   int64_t ncl;    // owned cells = plane * nzl
   int64_t nown;   // 3 * ncl

@@ -464,14 +464,17 @@ struct GatherArgs {
   int single_rank;  // 1: staging planes = owned planes, z wraps; 0: staging plane = zl + 1
 };
 
+// staging id of cell (x, y, zl), zl in [-1, nzl]; -1: the cell lies outside an open z boundary
 __device__ __forceinline__ int64_t stage_cell(const Grid& g, const GatherArgs& a, int x, int y, int zl)
 {
+  if (g.open_z && (g.z0 + zl < 0 || g.z0 + zl >= g.nz)) return -1;
   const int pz = a.single_rank ? wrapi(zl, g.nzl) : zl + 1;
   return ((int64_t)pz * g.ny + y) * g.nx + x;
 }
 
 __device__ __forceinline__ double stage_read(const double* __restrict__ stage, int64_t cell, int e)
 {
+  if (cell < 0) return 0.0;
   return __ldg(stage + (cell / CELL_GROUP) * (int64_t)(BLOCK_ALL * CELL_GROUP) + (int64_t)e * CELL_GROUP + (cell % CELL_GROUP));
 }
 

@@ -24,7 +24,8 @@ __global__ void k_halo_fill_local(Grid g, double* __restrict__ v, int width)
     const int64_t e = i % p3;
     const int zl = which < width ? -(which + 1) : g.nzl + (which - width);
     const int src = wrapi(zl, g.nzl);
-    v[(int64_t)(zl + GZ) * p3 + e] = v[(int64_t)(src + GZ) * p3 + e];
+    // open z: the ghost planes lie outside the box, where DMDA's local vectors hold zeros
+    v[(int64_t)(zl + GZ) * p3 + e] = g.open_z ? 0.0 : v[(int64_t)(src + GZ) * p3 + e];
   }
 }
 
@@ -35,12 +36,12 @@ __global__ void k_halo_reduce_local(Grid g, double* __restrict__ v, int wlo, int
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < p3; e += (int64_t)gridDim.x * blockDim.x) {
     for (int k = 1; k <= wlo; ++k) {
       const int zl = -k, dst = wrapi(zl, g.nzl);
-      v[(int64_t)(dst + GZ) * p3 + e] += v[(int64_t)(zl + GZ) * p3 + e];
+      if (!g.open_z) v[(int64_t)(dst + GZ) * p3 + e] += v[(int64_t)(zl + GZ) * p3 + e];  // open z: deposits outside the box are dropped
       v[(int64_t)(zl + GZ) * p3 + e] = 0.0;
     }
     for (int k = 0; k < whi; ++k) {
       const int zl = g.nzl + k, dst = wrapi(zl, g.nzl);
-      v[(int64_t)(dst + GZ) * p3 + e] += v[(int64_t)(zl + GZ) * p3 + e];
+      if (!g.open_z) v[(int64_t)(dst + GZ) * p3 + e] += v[(int64_t)(zl + GZ) * p3 + e];
       v[(int64_t)(zl + GZ) * p3 + e] = 0.0;
     }
   }

@@ -209,11 +209,26 @@ __device__ __forceinline__ double moved_coord(double r, double v, double dtm, do
   return wrap_coord(dtm != 0.0 ? __dadd_rn(r, __dmul_rn(v, dtm)) : r, L);
 }
 
+// z after the move: periodic wrap, or none when the z boundary is open (Particles::correct_coordinates wraps the
+// periodic axes only, src/interfaces/particles.cpp:329-338); the same bits in the key pass and in the scatter
+__device__ __forceinline__ double moved_z(const Grid& g, double r, double v, double dtm)
+{
+  if (g.open_z) return dtm != 0.0 ? __dadd_rn(r, __dmul_rn(v, dtm)) : r;
+  return moved_coord(r, v, dtm, g.Lz);
+}
+
+// a particle beyond an open z boundary is removed by the re-binning (src/interfaces/particles.cpp:100-103)
+__device__ __forceinline__ bool left_the_box(const Grid& g, double pz)
+{
+  return g.open_z && ((int)floor(to_cells(pz, g.dz, g.inv_dz, g.exact_inv & 4)) < 0 || (int)floor(to_cells(pz, g.dz, g.inv_dz, g.exact_inv & 4)) >= g.nz);
+}
+
 // bin plane of a (wrapped) z: 1..nzl inside the slab, 0 / nzl + 1 for the neighbour below / above
 __device__ __forceinline__ int slab_plane(const Grid& g, double pz)
 {
   int iz = (int)floor(to_cells(pz, g.dz, g.inv_dz, g.exact_inv & 4));
   iz = min(max(iz, 0), g.nz - 1);
+  if (g.open_z && (iz < g.z0 || iz >= g.z0 + g.nzl)) return iz < g.z0 ? 0 : g.nzl + 1;  // no wrap-around neighbour
   const int rel = iz - g.z0;
   if (rel >= 0 && rel < g.nzl) return rel + 1;
   const int up = (iz - (g.z0 + g.nzl) + 2 * g.nz) % g.nz;  // planes above the slab top (periodic)

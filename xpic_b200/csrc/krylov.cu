@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_cheb_step(Grid g, const double* __restr
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const double zc = f(c, 0, 0, 0);
-    const double Dz = diag * zc + h * curlcurl(c, inv_d, f);
+    const double Dz = diag * zc + h * curlcurl(c, inv_d, f, g.open_z && g.z0 + zl == 0);
     const double zo = z0 ? z0[o + c] : 0.0;
     z2[o + c] = zc + a * (zc - zo) + b * (u[o + c] - Dz);
   }

@@ -32,6 +32,7 @@ namespace xb {
 
 int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBuffers* arrivals, int64_t n_from_down, int64_t n_from_up,
                           double dt_move);  // particles.cu
+int count_after_open_sort(xb_ctx* c, Species& s);
 int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* bin_start, int64_t bin_cell0, int64_t ncells, int64_t stage_cell0,
                   int zshift, double** rec, int64_t rec_stride, int64_t nparticles);  // deposit.cu
 
@@ -103,7 +104,11 @@ __global__ void k_move_key_slab(Grid g, int64_t n, const double* __restrict__ x,
   if (i >= n) return;
   const double px = moved_coord(x[i], dtm != 0.0 ? vx[i] : 0.0, dtm, g.Lx);
   const double py = moved_coord(y[i], dtm != 0.0 ? vy[i] : 0.0, dtm, g.Ly);
-  const double pz = moved_coord(z[i], dtm != 0.0 ? vz[i] : 0.0, dtm, g.Lz);
+  const double pz = moved_z(g, z[i], dtm != 0.0 ? vz[i] : 0.0, dtm);
+  if (left_the_box(g, pz)) {
+    key[i] = -1;  // gone through an open boundary: neither kept nor sent
+    return;
+  }
   const int pl = slab_plane(g, pz);
   if (pl >= 1 && pl <= g.nzl) {
     const int32_t k = particle_key(g, px, py, pz, pl);
@@ -229,6 +234,7 @@ int migrate_and_sort(xb_ctx* c, Species& s, double dt_move)
     XB_LAUNCH(c, k_key_arrivals, (int)((from_up + 255) / 256), 256, 0, g, from_up, m.recv[1][0], m.recv[1][1], m.recv[1][2], m.recv_key[1], c->hist, bad);
   XB_CHECK(sort_scan_and_scatter(c, s, n, &m, from_down, from_up, dt_move));  // the scatter recomputes the moved position of the particles that stay
   s.count = n - to_down - to_up + from_down + from_up;
+  if (g.open_z) XB_CHECK(count_after_open_sort(c, s));  // minus the particles that left the box
   s.sorted = true;
   return 0;
 }
@@ -268,13 +274,16 @@ int ghost_exchange_begin(xb_ctx* c, Species& s)
   for (int r = 0; r < g.nranks; ++r) {
     const unsigned long long* t = row(r);
     if (t[5]) XB_FAIL("a particle crossed more than one slab in a single move (rank " + std::to_string(r) + ")");
-    if (row(r - 1)[1] > t[4] || row(r + 1)[0] > t[4]) XB_FAIL("ghost particle buffer overflow on rank " + std::to_string(r));
+    const bool has_down = !(g.open_z && r == 0), has_up = !(g.open_z && r == g.nranks - 1);
+    if ((has_down && row(r - 1)[1] > t[4]) || (has_up && row(r + 1)[0] > t[4])) XB_FAIL("ghost particle buffer overflow on rank " + std::to_string(r));
   }
   const unsigned long long* me = row(g.rank);
-  const int64_t nlo = (int64_t)me[0], nhi = (int64_t)me[1], lo0 = (int64_t)me[2], hi0 = (int64_t)me[3];
+  // open z: no neighbour across the box ends, their ghost cell planes stay empty (the staging planes keep their zeros)
+  const bool down = !(g.open_z && g.rank == 0), up = !(g.open_z && g.rank == g.nranks - 1);
+  const int64_t nlo = down ? (int64_t)me[0] : 0, nhi = up ? (int64_t)me[1] : 0, lo0 = (int64_t)me[2], hi0 = (int64_t)me[3];
   // from below arrives its top plane (my low ghost plane), from above its bottom plane (my high ghost plane)
-  m.nghost[0] = (int64_t)row(g.rank - 1)[1];
-  m.nghost[1] = (int64_t)row(g.rank + 1)[0];
+  m.nghost[0] = down ? (int64_t)row(g.rank - 1)[1] : -1;
+  m.nghost[1] = up ? (int64_t)row(g.rank + 1)[0] : -1;
   double** p = s.p[s.cur];
   ExchangeList l;
   l.n = 7;
@@ -284,19 +293,21 @@ int ghost_exchange_begin(xb_ctx* c, Species& s)
     l.to_up[k] = p[k] + hi0;
     l.n_to_up[k] = sizeof(double) * nhi;
     l.from_up[k] = m.ghost[1][k];
-    l.n_from_up[k] = sizeof(double) * m.nghost[1];
+    l.n_from_up[k] = up ? sizeof(double) * m.nghost[1] : 0;
     l.from_down[k] = m.ghost[0][k];
-    l.n_from_down[k] = sizeof(double) * m.nghost[0];
+    l.n_from_down[k] = down ? sizeof(double) * m.nghost[0] : 0;
   }
   // bin tables of the two planes (pb + 1 entries each, absolute offsets; rebased after receipt)
   l.to_down[6] = s.bin_start + 1 * pb;
   l.to_up[6] = s.bin_start + (int64_t)g.nzl * pb;
   l.from_up[6] = m.ghost_bins_raw[1];
   l.from_down[6] = m.ghost_bins_raw[0];
-  l.n_to_down[6] = l.n_to_up[6] = l.n_from_up[6] = l.n_from_down[6] = sizeof(int32_t) * (pb + 1);
+  l.n_to_down[6] = l.n_from_down[6] = down ? sizeof(int32_t) * (pb + 1) : 0;
+  l.n_to_up[6] = l.n_from_up[6] = up ? sizeof(int32_t) * (pb + 1) : 0;
   XB_CHECK(comm_exchange_list(c, l, cs));
   const int blocks = (int)((pb + 1 + 255) / 256);
   for (int d = 0; d < 2; ++d) {
+    if (m.nghost[d] < 0) continue;
     k_rebase_bins<<<blocks, 256, 0, cs>>>(m.ghost_bins_raw[d], m.ghost_bins[d], pb + 1);
     c->launches++;
   }
@@ -315,8 +326,9 @@ int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage)
   // low ghost plane: the neighbour below; across the periodic boundary its z is nz planes above mine
   const int zs_lo = g.rank == 0 ? -g.nz : 0;
   const int zs_hi = g.rank == g.nranks - 1 ? +g.nz : 0;
-  XB_CHECK(deposit_cells(c, s, m.ghost[0], m.ghost_bins[0], 0, g.plane, 0, zs_lo, &m.ghost_rec[0], m.ghost_cap, m.nghost[0]));
-  XB_CHECK(deposit_cells(c, s, m.ghost[1], m.ghost_bins[1], 0, g.plane, (int64_t)(g.nzl + 1) * g.plane, zs_hi, &m.ghost_rec[1], m.ghost_cap, m.nghost[1]));
+  if (m.nghost[0] >= 0) XB_CHECK(deposit_cells(c, s, m.ghost[0], m.ghost_bins[0], 0, g.plane, 0, zs_lo, &m.ghost_rec[0], m.ghost_cap, m.nghost[0]));
+  if (m.nghost[1] >= 0)
+    XB_CHECK(deposit_cells(c, s, m.ghost[1], m.ghost_bins[1], 0, g.plane, (int64_t)(g.nzl + 1) * g.plane, zs_hi, &m.ghost_rec[1], m.ghost_cap, m.nghost[1]));
   return 0;
 }
 

@@ -70,7 +70,11 @@ __global__ void k_move_key(Grid g, int64_t n, const double* __restrict__ x, cons
   if (i >= n) return;
   const double px = moved_coord(x[i], dtm != 0.0 ? vx[i] : 0.0, dtm, g.Lx);
   const double py = moved_coord(y[i], dtm != 0.0 ? vy[i] : 0.0, dtm, g.Ly);
-  const double pz = moved_coord(z[i], dtm != 0.0 ? vz[i] : 0.0, dtm, g.Lz);
+  const double pz = moved_z(g, z[i], dtm != 0.0 ? vz[i] : 0.0, dtm);
+  if (left_the_box(g, pz)) {
+    key[i] = -1;  // not scattered: the particle is gone
+    return;
+  }
   const int32_t k = particle_key(g, px, py, pz, slab_plane(g, pz));
   key[i] = k;
   atomicAdd(&hist[k], 1);
@@ -184,8 +188,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(int64_t n, const in
                                                             const double* __restrict__ s4, const double* __restrict__ s5,
                                                             const uint64_t* __restrict__ sid, double* __restrict__ d0, double* __restrict__ d1,
                                                             double* __restrict__ d2, double* __restrict__ d3, double* __restrict__ d4,
-                                                            double* __restrict__ d5, uint64_t* __restrict__ did, double dtm, double Lx, double Ly,
-                                                            double Lz)
+                                                            double* __restrict__ d5, uint64_t* __restrict__ did, double dtm, Grid g)
 {
   const int lane = threadIdx.x & 31;
   const int64_t first = (int64_t)blockIdx.x * (SCATTER_THREADS * SCATTER_ITEMS) + threadIdx.x;
@@ -214,9 +217,9 @@ __global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(int64_t n, const in
     const int32_t b = __shfl_sync(peers[j], base[j], __ffs(peers[j]) - 1);
     const int32_t pos = b + __popc(peers[j] & ((1u << lane) - 1u));
     const double vx = s3[i], vy = s4[i], vz = s5[i];
-    d0[pos] = moved_coord(s0[i], vx, dtm, Lx);  // the same bits the key pass binned (dtm = 0: plain copy + wrap)
-    d1[pos] = moved_coord(s1[i], vy, dtm, Ly);
-    d2[pos] = moved_coord(s2[i], vz, dtm, Lz);
+    d0[pos] = moved_coord(s0[i], vx, dtm, g.Lx);  // the same bits the key pass binned (dtm = 0: plain copy + wrap)
+    d1[pos] = moved_coord(s1[i], vy, dtm, g.Ly);
+    d2[pos] = moved_z(g, s2[i], vz, dtm);
     d3[pos] = vx;
     d4[pos] = vy;
     d5[pos] = vz;
@@ -276,14 +279,14 @@ int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBu
   uint64_t* did = s.id[1 - s.cur];
   if (nlocal > 0)
     XB_LAUNCH(c, k_scatter, grid_for(nlocal, SCATTER_THREADS * SCATTER_ITEMS), SCATTER_THREADS, 0, nlocal, s.key, c->cursor, p[0], p[1], p[2], p[3], p[4], p[5], s.id[s.cur], d[0], d[1], d[2], d[3],
-              d[4], d[5], did, dt_move, g.Lx, g.Ly, g.Lz);
+              d[4], d[5], did, dt_move, g);
   if (arr) {
     const int64_t na[2] = {n_from_down, n_from_up};
     for (int k = 0; k < 2; ++k)
       if (na[k] > 0)
         XB_LAUNCH(c, k_scatter, grid_for(na[k], SCATTER_THREADS * SCATTER_ITEMS), SCATTER_THREADS, 0, na[k], arr->recv_key[k], c->cursor, arr->recv[k][0], arr->recv[k][1], arr->recv[k][2],
                   arr->recv[k][3], arr->recv[k][4], arr->recv[k][5], c->track_ids ? reinterpret_cast<const uint64_t*>(arr->recv[k][6]) : nullptr, d[0],
-                  d[1], d[2], d[3], d[4], d[5], did, 0.0, g.Lx, g.Ly, g.Lz);
+                  d[1], d[2], d[3], d[4], d[5], did, 0.0, g);
   }
   s.cur = 1 - s.cur;
   {
@@ -296,6 +299,16 @@ int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBu
   return 0;
 }
 
+// open z boundary: particles may have left the box; the scan's total is the number that stayed
+int count_after_open_sort(xb_ctx* c, Species& s)
+{
+  int32_t total = 0;
+  XB_CUDA(cudaMemcpyAsync(&total, s.bin_start + c->nbins, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  s.count = total;
+  return 0;
+}
+
 int particles_sort(xb_ctx* c, Species& s, double dt_move)
 {
   const Grid& g = c->g;
@@ -305,6 +318,7 @@ int particles_sort(xb_ctx* c, Species& s, double dt_move)
   double** p = s.p[s.cur];
   if (n > 0) XB_LAUNCH(c, k_move_key, grid_for(n), 256, 0, g, n, p[0], p[1], p[2], p[3], p[4], p[5], dt_move, s.key, c->hist);
   XB_CHECK(sort_scan_and_scatter(c, s, n, nullptr, 0, 0, dt_move));
+  if (g.open_z) XB_CHECK(count_after_open_sort(c, s));
   s.sorted = true;
   return 0;
 }

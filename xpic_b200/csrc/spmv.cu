@@ -84,8 +84,9 @@ __global__ void __launch_bounds__(TX * TY * TZ, 3) k_spmv(Grid g, const double* 
     const double inv_d[3] = {1.0 / g.dx, 1.0 / g.dy, 1.0 / g.dz};
     auto f = [&](int comp, int ox, int oy, int oz) { return xs[comp][tz + HALO + oz][ty + HALO + oy][tx + HALO + ox]; };
     const double h = 0.5 * g.dt * g.dt;
+    const bool cut = g.open_z && g.z0 + zl == 0;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) acc[c] += 2.0 * f(c, 0, 0, 0) + h * curlcurl(c, inv_d, f);
+    for (int c = 0; c < 3; ++c) acc[c] += 2.0 * f(c, 0, 0, 0) + h * curlcurl(c, inv_d, f, cut);
   }
   const int64_t o = g.vidx(gx, gy, zl, 0);
   y[o + 0] = acc[0];
