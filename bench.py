@@ -384,7 +384,11 @@ def main():
                 k["frac"] = k["achieved"] / (peak if k["bound"] == "hbm" else fp64_peak)
         kernels[1]["peak"] = fp64_peak
         kernels[1]["peak_source"] = fp64_src
-        stage_sum = {"first_push": t_sort + t_dep, "advance_fields_spmv_plus_precond": spmv_ms / args.steps + t_pre, "second_push": t_push}
+        stage_sum = {"first_push": t_sort + t_dep, "advance_fields_spmv_plus_precond": spmv_ms / args.steps + t_pre, "second_push": t_push,
+                     "moments_parts": {"cell_blocks_owned_planes": per["moments_cells"][0], "cell_blocks_ghost_planes_incl_wait": per["moments_ghost"][0],
+                                       "row_gather": per["moments_rows"][0]},
+                     "sort_parts": {"move_and_key_pass": per["sort_keys"][0], "migration_counts_payloads_arrivals": per["sort_migrate"][0],
+                                    "scan_and_scatter": per["sort_scatter"][0]}}
         # by time the moment deposition is the dominant kernel family of the step (the SpMV above is the kernel
         # BASELINE.json's metric names); its roof is the fp64 tensor / FMA rate, not HBM
         roofline_dominant = {"kernel": "moment deposition: k_cell_moments (fp64 DMMA m8n8k4, fused field records) + k_gather_rows", "bound": "tensor",

@@ -158,7 +158,12 @@ int xb_spmv_profile_read(xb_ctx* ctx, int64_t* launches, double* total_ms);
  * re-binning (Particles::update_cells, src/interfaces/particles.cpp:79-116, with the move of first_push fused),
  * moments (fill_ecsim_current, src/impls/ecsim/simulation.cpp:336-368), second push (ecsim/particles.cpp:175-192),
  * operator SpMV (MatMult), Chebyshev preconditioner steps (PCApply). */
-enum { XB_FAMILY_SORT = 0, XB_FAMILY_MOMENTS = 1, XB_FAMILY_PUSH2 = 2, XB_FAMILY_SPMV = 3, XB_FAMILY_PRECOND = 4, XB_FAMILY_COUNT = 5 };
+enum { XB_FAMILY_SORT = 0, XB_FAMILY_MOMENTS = 1, XB_FAMILY_PUSH2 = 2, XB_FAMILY_SPMV = 3, XB_FAMILY_PRECOND = 4,
+       /* parts of XB_FAMILY_MOMENTS: cell blocks of the owned planes, of the two ghost planes (multi-rank: includes
+        * the wait for the neighbours' boundary particles), gather of the rows */
+       XB_FAMILY_MOMENTS_CELLS = 5, XB_FAMILY_MOMENTS_GHOST = 6, XB_FAMILY_MOMENTS_ROWS = 7,
+       /* parts of XB_FAMILY_SORT: move + key pass, migration (count table, payloads, keys of the arrivals; multi-rank), scan + scatter */
+       XB_FAMILY_SORT_KEYS = 8, XB_FAMILY_SORT_MIGRATE = 9, XB_FAMILY_SORT_SCATTER = 10, XB_FAMILY_COUNT = 11 };
 int xb_family_profile(xb_ctx* ctx, int32_t enable);
 int xb_family_profile_read(xb_ctx* ctx, int32_t family, int64_t* launches, double* total_ms);
 /* Energy::calculate_energy (src/diagnostics/energy.cpp:43-59): 0.5 * |v|^2 of a named vector, summed over all ranks. */
@@ -228,10 +233,16 @@ int xb_charge_density(xb_ctx* ctx, int32_t sid, double* rho);
 int xb_charge_conservation(xb_ctx* ctx, int32_t which_current, double* norms);
 
 /* DistributionMoment::collect (src/diagnostics/distribution_moment.cpp:157-210) for sort sid: cell-centred
- * moments with the 1st-order form factor, owned slab in natural [z][y][x] order, Nx*Ny*nzl doubles.
- * moment: XB_MOMENT_DENSITY (get_density, :212-216); the velocity / flux moments are not covered. */
-enum { XB_MOMENT_DENSITY = 0 };
+ * moments with the 1st-order form factor on the owned slab, natural [z][y][x][component] order,
+ * Nx*Ny*nzl*components doubles.  moment: get_density (1 component), get_current (3), get_momentum_flux (6: xx xy xz yy yz zz),
+ * get_momentum_flux_cyl (6: rr ra rz aa az zz about the box axis), the two diagonal forms (3) -- :212-313.
+ * The region form takes `start` / `size` in cells ("region" of the diagnostic, field_view_builder.cpp:52-97): only
+ * particles whose cell lies inside contribute (:180-181) and what they deposit outside is dropped unless the region
+ * spans the whole axis; the output is still the whole owned slab (zeros outside the region). */
+enum { XB_MOMENT_DENSITY = 0, XB_MOMENT_CURRENT = 1, XB_MOMENT_MOMENTUM_FLUX = 2, XB_MOMENT_MOMENTUM_FLUX_CYL = 3, XB_MOMENT_MOMENTUM_FLUX_DIAG = 4,
+       XB_MOMENT_MOMENTUM_FLUX_DIAG_CYL = 5 };
 int xb_distribution_moment(xb_ctx* ctx, int32_t sid, int32_t moment, double* out);
+int xb_distribution_moment_region(xb_ctx* ctx, int32_t sid, int32_t moment, const int32_t start[3], const int32_t size[3], double* out);
 
 /* MomentumConservation::calculate (src/diagnostics/momentum_conservation.cpp:71-126) for sort sid with the
  * present E: out = { Px, Py, Pz, QEx, QEy, QEz }, P = m / Np * sum v, QE = q / Np * sum E(x_p) with the global

@@ -60,7 +60,9 @@ def csr_to_stencil(o, table):
 
 
 def csr_to_stencil_open(o, table):
-    """As csr_to_stencil for a box whose z boundary is open: columns outside the box do not exist (coefficient 0)."""
+    """As csr_to_stencil for a box whose z boundary is open.  Returns (coef, exists): exists[k, node] is False where the
+    column of slot k lies outside the box -- the reference has no such matrix entry; the product keeps whatever the
+    particles deposited there, it only ever multiplies the zero ghost values of x."""
     import scipy.sparse as sp
 
     rp, col, val = o.csr(0)
@@ -69,6 +71,7 @@ def csr_to_stencil_open(o, table):
     z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
     node = ((z * ny + y) * nx + x).reshape(-1)
     coef = np.zeros((len(table), node.size))
+    exists = np.zeros((len(table), node.size), dtype=bool)
     for k, (c1, c2, dx, dy, dz) in enumerate(table):
         rows = node * 3 + c1
         zc = (z + dz).reshape(-1)
@@ -77,7 +80,8 @@ def csr_to_stencil_open(o, table):
         cols = cn * 3 + c2
         v = np.asarray(A[rows, cols]).reshape(-1)
         coef[k] = np.where(inside, v, 0.0)
-    return coef
+        exists[k] = inside
+    return coef, exists
 
 
 def spline2(s):
@@ -126,3 +130,54 @@ def cell_density(pts, n, d, n_np):
                 wx = s1(p[:, 0] - (start[:, 0] + i + 0.5))
                 np.add.at(rho, ((start[:, 2] + k) % nz, (start[:, 1] + j) % ny, (start[:, 0] + i) % nx), n_np * wx * wy * wz)
     return rho
+
+
+def cell_moment(pts, n, d, n_np, name, q=-1.0, m=1.0, start=(0, 0, 0), size=None):
+    """DistributionMoment::collect for any moment of src/diagnostics/distribution_moment.cpp:212-313 and a region:
+    (nz, ny, nx, components) array; particles whose cell lies outside the region do not contribute, deposits outside the
+    region are dropped unless the region spans the whole (periodic) axis."""
+    nx, ny, nz = n
+    size = tuple(n) if size is None else tuple(size)
+    v = pts[:, 3:]
+    if name == "density":
+        mv = np.ones((len(pts), 1))
+    elif name == "current":
+        mv = q * v
+    else:
+        w = v.copy()
+        if name.endswith("cyl"):
+            x, y = pts[:, 0] - 0.5 * nx * d[0], pts[:, 1] - 0.5 * ny * d[1]
+            r = np.hypot(x, y)
+            ok = r > 0
+            w[ok, 0] = (x[ok] * v[ok, 0] + y[ok] * v[ok, 1]) / r[ok]
+            w[ok, 1] = (-y[ok] * v[ok, 0] + x[ok] * v[ok, 1]) / r[ok]
+        if "diag" in name:
+            mv = m * w * w
+        else:
+            mv = m * np.stack([w[:, 0] * w[:, 0], w[:, 0] * w[:, 1], w[:, 0] * w[:, 2], w[:, 1] * w[:, 1], w[:, 1] * w[:, 2], w[:, 2] * w[:, 2]], axis=1)
+    out = np.zeros((nz, ny, nx, mv.shape[1]))
+    p = pts[:, :3] / np.array(d)
+    cell = np.floor(p).astype(int)
+    inside = np.ones(len(pts), dtype=bool)
+    for a in range(3):
+        inside &= (cell[:, a] >= start[a]) & (cell[:, a] < start[a] + size[a])
+    st = np.round(p - 1.0).astype(int)
+
+    def s1(s):
+        s = np.abs(s)
+        return np.where(s <= 1.0, 1.0 - s, 0.0)
+
+    for k in range(2):
+        wz = s1(p[:, 2] - (st[:, 2] + k + 0.5))
+        for j in range(2):
+            wy = s1(p[:, 1] - (st[:, 1] + j + 0.5))
+            for i in range(2):
+                wx = s1(p[:, 0] - (st[:, 0] + i + 0.5))
+                c = st + np.array([i, j, k])
+                keep = inside.copy()
+                for a in range(3):
+                    if size[a] != n[a]:
+                        keep &= (c[:, a] >= start[a]) & (c[:, a] < start[a] + size[a])
+                idx = (c[keep, 2] % nz, c[keep, 1] % ny, c[keep, 0] % nx)
+                np.add.at(out, idx, (n_np * wx * wy * wz)[keep, None] * mv[keep])
+    return out

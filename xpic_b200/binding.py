@@ -19,7 +19,7 @@ ECSIM, ECSIMCORR, ECCAPFIM = 0, 1, 2
 FIELDS = {"E": 0, "B": 1, "B0": 2, "Ep": 3, "Ec": 4, "currI": 5, "currJe": 6, "currI_sort": 7, "currJe_sort": 8, "J": 9, "J_sort": 10, "Ehk": 11}
 SCALARS = {"kinetic": 0, "pred_w": 1, "corr_w": 2, "pred_dK": 3, "corr_dK": 4, "lambda_dK": 5, "energy_member": 6, "j_diff_norm": 7}
 STAGES = ["clear_sources", "first_push", "advance_fields", "second_push", "correct_fields", "final_update"]
-FAMILIES = ["sort", "moments", "second_push", "spmv", "precond"]
+FAMILIES = ["sort", "moments", "second_push", "spmv", "precond", "moments_cells", "moments_ghost", "moments_rows", "sort_keys", "sort_migrate", "sort_scatter"]
 OP_L, OP_M, OP_A = 1, 2, 3
 
 
@@ -118,6 +118,7 @@ SYMBOLS = {
     "xb_charge_conservation": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "xb_momentum": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "xb_distribution_moment": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "xb_distribution_moment_region": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _i32p, _i32p, _dp]),
 }
 
 
@@ -301,6 +302,22 @@ class Simulation:
         out = np.zeros(2 * (self.nsorts + 1))
         _check(self._L.xb_charge_conservation(self._h, {"currJe": 0, "J": 1}[current], _as_dp(out)))
         return out.reshape(-1, 2)
+
+    MOMENTS = {"density": (0, 1), "current": (1, 3), "momentum_flux": (2, 6), "momentum_flux_cyl": (3, 6), "momentum_flux_diag": (4, 3),
+               "momentum_flux_diag_cyl": (5, 3)}
+
+    def distribution_moment(self, name, sid=0, start=None, size=None):
+        """DistributionMoment::collect: (ncl, components) array of the named moment on the owned cells; start / size (cells)
+        restrict the particles to a region."""
+        mid, ms = self.MOMENTS[name]
+        out = np.empty((self.ncl, ms), dtype=np.float64)
+        if start is None and size is None:
+            _check(self._L.xb_distribution_moment(self._h, sid, mid, _as_dp(out)))
+        else:
+            st = (C.c_int32 * 3)(*(start if start is not None else (0, 0, 0)))
+            sz = (C.c_int32 * 3)(*(size if size is not None else self.n))
+            _check(self._L.xb_distribution_moment_region(self._h, sid, mid, st, sz, _as_dp(out)))
+        return out
 
     def density(self, sid=0):
         """DistributionMoment "density": cell-centred number density of sort sid on the owned cells."""

@@ -855,18 +855,26 @@ int xb_charge_density(xb_ctx* c, int32_t sid, double* rho)
   return 0;
 }
 
-int xb_distribution_moment(xb_ctx* c, int32_t sid, int32_t moment, double* out)
+int xb_distribution_moment_region(xb_ctx* c, int32_t sid, int32_t moment, const int32_t start[3], const int32_t size[3], double* out)
 {
   XB_API_BEGIN(c);
   if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
   if (!out) XB_FAIL("xb_distribution_moment: null output");
-  XB_CHECK(distribution_moment(c, c->sorts[sid], moment));
-  std::vector<double> tmp((size_t)c->g.nown);
-  XB_CHECK(download_owned(c, c->tmp2, tmp.data()));
+  XB_CHECK(distribution_moment(c, c->sorts[sid], moment, start, size));
+  const int ms = moment_size(moment);
+  std::vector<double> lo((size_t)c->g.nown), hi;
+  XB_CHECK(download_owned(c, c->tmp2, lo.data()));
+  if (ms > 3) {
+    hi.resize((size_t)c->g.nown);
+    XB_CHECK(download_owned(c, c->tmp, hi.data()));
+  }
   XB_CUDA(cudaStreamSynchronize(c->stream));
-  for (int64_t i = 0; i < c->g.ncl; ++i) out[i] = tmp[3 * i];
+  for (int64_t i = 0; i < c->g.ncl; ++i)
+    for (int j = 0; j < ms; ++j) out[(size_t)i * ms + j] = j < 3 ? lo[3 * i + j] : hi[3 * i + j - 3];
   return 0;
 }
+
+int xb_distribution_moment(xb_ctx* c, int32_t sid, int32_t moment, double* out) { return xb_distribution_moment_region(c, sid, moment, nullptr, nullptr, out); }
 
 int xb_momentum(xb_ctx* c, int32_t sid, double out[6])
 {

@@ -270,7 +270,8 @@ int cap_read_counters(xb_ctx* c);                        // averages of the last
 int charge_density(xb_ctx* c, Species& s);                               // ParticlesChargeDensity::collect
 int charge_conservation(xb_ctx* c, int which_current, double* norms);   // ChargeConservation::add_columns
 int momentum(xb_ctx* c, Species& s, double* out6);                      // MomentumConservation::calculate
-int distribution_moment(xb_ctx* c, Species& s, int moment);             // DistributionMoment::collect -> c->tmp2, component 0
+int distribution_moment(xb_ctx* c, Species& s, int moment, const int32_t* start, const int32_t* size);  // DistributionMoment::collect -> c->tmp2 (+ c->tmp)
+int moment_size(int moment);
 
 // ---- api.cu: in-step kernel-family timing ------------------------------------------------------
 int prof_begin(xb_ctx* c, int family);

@@ -643,12 +643,17 @@ int deposit_moments(xb_ctx* c)
     if (!s.sorted) XB_FAIL("deposit: particles are not sorted");
     // bin plane 1 = first owned plane; staging plane 0 is the low ghost plane in multi-rank runs
     if (!single) XB_CHECK(ghost_exchange_mark(c, s));
+    XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_CELLS));
     XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane, g.ncl, single ? 0 : g.plane, 0, &s.rec, s.capacity, s.count));
+    XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_CELLS));
     if (!single) {
       // the boundary-plane particles of the z neighbours travel (copy stream) while the owned planes are computed
       XB_CHECK(ghost_exchange_begin(c, s));
+      XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_GHOST));
       XB_CHECK(deposit_ghost_cells(c, s, c->stage));
+      XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_GHOST));
     }
+    XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_ROWS));
     GatherArgs ga{c->stage, single ? 1 : 0};
     const int acc = first ? 0 : 1;
     XB_CHECK((launch_gather<0, 0>(c, ga, acc)));
@@ -662,6 +667,7 @@ int deposit_moments(xb_ctx* c)
     XB_CHECK((launch_gather<2, 2>(c, ga, acc)));
     const int blocks = (int)((g.ncl + 127) / 128);
     XB_LAUNCH(c, k_gather_current, blocks, 128, 0, g, ga, s.currI, c->currI);
+    XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_ROWS));
     first = false;
   }
   if (c->sorts.empty()) XB_CUDA(cudaMemsetAsync(c->coef, 0, sizeof(double) * c->coef_elems, c->stream));

@@ -163,45 +163,137 @@ int momentum(xb_ctx* c, Species& s, double* out)
   return 0;
 }
 
-// DistributionMoment::collect with the "density" moment (src/diagnostics/distribution_moment.cpp:125-210):
-// cell-centred quantity, 1st-order form factor on the two cells per axis from round(p - 1), weight n / Np
-__global__ void __launch_bounds__(256) k_cell_density(Grid g, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
-                                                     const double* __restrict__ z, double n_Np, double* __restrict__ rho)
+// DistributionMoment::collect (src/diagnostics/distribution_moment.cpp:157-210) with the moments of :212-313:
+// cell-centred quantities, 1st-order form factor on the two cells per axis from round(p - 1), weight n / Np.
+// Only particles whose cell lies in the region contribute (:180-181); a deposit outside the region is dropped
+// unless the region spans the whole (periodic) axis (set_local_da, :59-110: DM_BOUNDARY_GHOSTED otherwise).
+struct MomentArgs {
+  int moment;
+  int start[3], size[3];  // region in cells
+  double q, m, n_Np;
+  double cx, cy;          // box centre for the cylindrical moments
+};
+
+__device__ __forceinline__ int moment_values(const MomentArgs& a, double px, double py, const double* v, double* out)
+{
+  switch (a.moment) {
+    case XB_MOMENT_DENSITY: out[0] = 1.0; return 1;
+    case XB_MOMENT_CURRENT:
+      for (int c = 0; c < 3; ++c) out[c] = a.q * v[c];
+      return 3;
+    case XB_MOMENT_MOMENTUM_FLUX:
+    case XB_MOMENT_MOMENTUM_FLUX_DIAG:
+    case XB_MOMENT_MOMENTUM_FLUX_CYL:
+    case XB_MOMENT_MOMENTUM_FLUX_DIAG_CYL: {
+      double w[3] = {v[0], v[1], v[2]};
+      if (a.moment == XB_MOMENT_MOMENTUM_FLUX_CYL || a.moment == XB_MOMENT_MOMENTUM_FLUX_DIAG_CYL) {  // _get_v_cyl, :257-275
+        const double x = px - a.cx, y = py - a.cy, r = hypot(x, y);
+        if (!isinf(1.0 / r)) {
+          w[0] = (+x * v[0] + y * v[1]) / r;
+          w[1] = (-y * v[0] + x * v[1]) / r;
+        }
+      }
+      if (a.moment == XB_MOMENT_MOMENTUM_FLUX_DIAG || a.moment == XB_MOMENT_MOMENTUM_FLUX_DIAG_CYL) {
+        for (int c = 0; c < 3; ++c) out[c] = a.m * w[c] * w[c];
+        return 3;
+      }
+      out[0] = a.m * w[0] * w[0];
+      out[1] = a.m * w[0] * w[1];
+      out[2] = a.m * w[0] * w[2];
+      out[3] = a.m * w[1] * w[1];
+      out[4] = a.m * w[1] * w[2];
+      out[5] = a.m * w[2] * w[2];
+      return 6;
+    }
+  }
+  return 0;
+}
+
+// lo: components 0..2 of the moment, hi: components 3..5 (grid vectors, owned part valid after the halo reduction)
+__global__ void __launch_bounds__(256) k_cell_moment(Grid g, MomentArgs a, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                                                    const double* __restrict__ z, const double* __restrict__ vx, const double* __restrict__ vy,
+                                                    const double* __restrict__ vz, double* __restrict__ lo, double* __restrict__ hi)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double p[3] = {to_cells(x[i], g.dx, g.inv_dx, g.exact_inv & 1), to_cells(y[i], g.dy, g.inv_dy, g.exact_inv & 2),
                        to_cells(z[i], g.dz, g.inv_dz, g.exact_inv & 4)};
+  const int full[3] = {a.size[0] == g.nx, a.size[1] == g.ny, a.size[2] == g.nz};
   int start[3];
   double w[3][2];
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    start[a] = (int)round(p[a] - 1.0);  // Shape::make_start(p_r, shr = 1)
+  for (int ax = 0; ax < 3; ++ax) {
+    const int cell = (int)floor(p[ax]);
+    if (cell < a.start[ax] || cell >= a.start[ax] + a.size[ax]) return;  // is_point_within_bounds(vg, gstart, gsize)
+    start[ax] = (int)round(p[ax] - 1.0);  // Shape::make_start(p_r, shr = 1)
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const double s = fabs(p[a] - ((double)(start[a] + j) + 0.5));
-      w[a][j] = s <= 1.0 ? 1.0 - s : 0.0;  // spline_of_1st_order
+      const double s = fabs(p[ax] - ((double)(start[ax] + j) + 0.5));
+      w[ax][j] = s <= 1.0 ? 1.0 - s : 0.0;  // spline_of_1st_order
     }
   }
+  const double v[3] = {vx[i], vy[i], vz[i]};
+  double mv[6];
+  const int ms = moment_values(a, x[i], y[i], v, mv);
 #pragma unroll
   for (int kz = 0; kz < 2; ++kz)
 #pragma unroll
     for (int jy = 0; jy < 2; ++jy)
 #pragma unroll
-      for (int ix = 0; ix < 2; ++ix)
-        atomicAdd(&rho[g.vidx(wrapi(start[0] + ix, g.nx), wrapi(start[1] + jy, g.ny), start[2] + kz - g.z0, 0)], (w[0][ix] * w[1][jy] * w[2][kz]) * n_Np);
+      for (int ix = 0; ix < 2; ++ix) {
+        const int c[3] = {start[0] + ix, start[1] + jy, start[2] + kz};
+        bool keep = true;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax)
+          if (!full[ax] && (c[ax] < a.start[ax] || c[ax] >= a.start[ax] + a.size[ax])) keep = false;
+        if (!keep) continue;
+        const double si = (w[0][ix] * w[1][jy] * w[2][kz]) * a.n_Np;
+        const int64_t o = g.vidx(wrapi(c[0], g.nx), wrapi(c[1], g.ny), c[2] - g.z0, 0);
+        for (int j = 0; j < ms; ++j) atomicAdd(j < 3 ? &lo[o + j] : &hi[o + j - 3], mv[j] * si);
+      }
 }
 
-// moment 0 = density into component 0 of c->tmp2 (owned part valid after the halo reduction)
-int distribution_moment(xb_ctx* c, Species& s, int moment)
+int moment_size(int moment)
 {
-  if (moment != 0) XB_FAIL("distribution_moment: only the density moment is covered");
+  switch (moment) {
+    case XB_MOMENT_DENSITY: return 1;
+    case XB_MOMENT_CURRENT:
+    case XB_MOMENT_MOMENTUM_FLUX_DIAG:
+    case XB_MOMENT_MOMENTUM_FLUX_DIAG_CYL: return 3;
+    case XB_MOMENT_MOMENTUM_FLUX:
+    case XB_MOMENT_MOMENTUM_FLUX_CYL: return 6;
+  }
+  return 0;
+}
+
+// components 0..2 into c->tmp2, 3..5 into c->tmp (owned parts valid after the halo reduction)
+int distribution_moment(xb_ctx* c, Species& s, int moment, const int32_t* start, const int32_t* size)
+{
+  const Grid& g = c->g;
+  const int ms = moment_size(moment);
+  if (ms == 0) XB_FAIL("distribution_moment: unknown moment");
+  MomentArgs a;
+  a.moment = moment;
+  const int full[3] = {g.nx, g.ny, g.nz};
+  for (int ax = 0; ax < 3; ++ax) {
+    a.start[ax] = start ? start[ax] : 0;
+    a.size[ax] = size ? size[ax] : full[ax];
+    if (a.start[ax] < 0 || a.size[ax] < 1 || a.start[ax] + a.size[ax] > full[ax]) XB_FAIL("distribution_moment: the region is not inside the box");
+  }
+  a.q = s.q;
+  a.m = s.m;
+  a.n_Np = s.n / (double)s.Np;
+  a.cx = 0.5 * g.Lx;
+  a.cy = 0.5 * g.Ly;
   XB_CHECK(vec_zero(c, c->tmp2));
+  if (ms > 3) XB_CHECK(vec_zero(c, c->tmp));
   if (s.count > 0) {
     double** p = s.p[s.cur];
-    XB_LAUNCH(c, k_cell_density, (int)((s.count + 255) / 256), 256, 0, c->g, s.count, p[0], p[1], p[2], s.n / (double)s.Np, c->tmp2);
+    XB_LAUNCH(c, k_cell_moment, (int)((s.count + 255) / 256), 256, 0, g, a, s.count, p[0], p[1], p[2], p[3], p[4], p[5], c->tmp2, c->tmp);
   }
-  return halo_reduce(c, c->tmp2, GZ, GZ);
+  XB_CHECK(halo_reduce(c, c->tmp2, GZ, GZ));
+  if (ms > 3) XB_CHECK(halo_reduce(c, c->tmp, GZ, GZ));
+  return 0;
 }
 
 static int ensure_rho(xb_ctx* c, Species& s)

@@ -120,13 +120,16 @@ __global__ void k_move_key_slab(Grid g, int64_t n, const double* __restrict__ x,
   const unsigned long long slot = atomicAdd(&send_count[dir], 1ull);
   key[i] = -1;
   if ((int64_t)slot >= cap) return;  // overflow is detected from the count, by every rank (migrate_and_sort)
-  sp.a[dir][0][slot] = px;
-  sp.a[dir][1][slot] = py;
-  sp.a[dir][2][slot] = pz;
-  sp.a[dir][3][slot] = vx[i];
-  sp.a[dir][4][slot] = vy[i];
-  sp.a[dir][5][slot] = vz[i];
-  if (id) reinterpret_cast<uint64_t*>(sp.a[dir][6])[slot] = id[i];
+  // static indices into the parameter struct (a run-time `dir` index would make every thread copy it to its stack)
+#define XB_SEND(k) (dir ? sp.a[1][k] : sp.a[0][k])
+  XB_SEND(0)[slot] = px;
+  XB_SEND(1)[slot] = py;
+  XB_SEND(2)[slot] = pz;
+  XB_SEND(3)[slot] = vx[i];
+  XB_SEND(4)[slot] = vy[i];
+  XB_SEND(5)[slot] = vz[i];
+  if (id) reinterpret_cast<uint64_t*>(XB_SEND(6))[slot] = id[i];
+#undef XB_SEND
 }
 
 __global__ void k_key_arrivals(Grid g, int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
@@ -193,11 +196,14 @@ int migrate_and_sort(xb_ctx* c, Species& s, double dt_move)
   SendPtrs sp;
   for (int d = 0; d < 2; ++d)
     for (int k = 0; k < 7; ++k) sp.a[d][k] = m.send[d][k];
+  XB_CHECK(prof_begin(c, XB_FAMILY_SORT_KEYS));
   if (n > 0) {
     const int blocks = (int)((n + 255) / 256);
     XB_LAUNCH(c, k_move_key_slab, blocks, 256, 0, g, n, p[0], p[1], p[2], p[3], p[4], p[5], s.id[s.cur], dt_move, s.key, c->hist, sp, m.counts_dev,
               m.cap);
   }
+  XB_CHECK(prof_end(c, XB_FAMILY_SORT_KEYS));
+  XB_CHECK(prof_begin(c, XB_FAMILY_SORT_MIGRATE));
   XB_LAUNCH(c, k_fill_slot, 1, 1, 0, m.table_dev + (size_t)g.rank * SLOT, m.counts_dev, (unsigned long long)n, (unsigned long long)s.capacity,
             (unsigned long long)m.cap);
   XB_CHECK(gather_table(c, m, c->stream));
@@ -232,7 +238,10 @@ int migrate_and_sort(xb_ctx* c, Species& s, double dt_move)
     XB_LAUNCH(c, k_key_arrivals, (int)((from_down + 255) / 256), 256, 0, g, from_down, m.recv[0][0], m.recv[0][1], m.recv[0][2], m.recv_key[0], c->hist, bad);
   if (from_up > 0)
     XB_LAUNCH(c, k_key_arrivals, (int)((from_up + 255) / 256), 256, 0, g, from_up, m.recv[1][0], m.recv[1][1], m.recv[1][2], m.recv_key[1], c->hist, bad);
+  XB_CHECK(prof_end(c, XB_FAMILY_SORT_MIGRATE));
+  XB_CHECK(prof_begin(c, XB_FAMILY_SORT_SCATTER));
   XB_CHECK(sort_scan_and_scatter(c, s, n, &m, from_down, from_up, dt_move));  // the scatter recomputes the moved position of the particles that stay
+  XB_CHECK(prof_end(c, XB_FAMILY_SORT_SCATTER));
   s.count = n - to_down - to_up + from_down + from_up;
   if (g.open_z) XB_CHECK(count_after_open_sort(c, s));  // minus the particles that left the box
   s.sorted = true;

@@ -179,7 +179,7 @@ __global__ void k_scan_add(int32_t* __restrict__ out, int64_t n, const int32_t* 
 // run with one atomic.  The kernel is bound by the latency of those returning atomics (ncu: 65 stall
 // cycles per issued instruction on the long scoreboard), so every thread carries SCATTER_ITEMS
 // particles whose reservations are all in flight before the first one is used.
-constexpr int SCATTER_ITEMS = 4;
+constexpr int SCATTER_ITEMS = 8;
 constexpr int SCATTER_THREADS = 256;
 
 __global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(int64_t n, const int32_t* __restrict__ key, int32_t* __restrict__ cursor,
@@ -193,29 +193,34 @@ __global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(int64_t n, const in
   const int lane = threadIdx.x & 31;
   const int64_t first = (int64_t)blockIdx.x * (SCATTER_THREADS * SCATTER_ITEMS) + threadIdx.x;
   int32_t k[SCATTER_ITEMS], base[SCATTER_ITEMS];
-  unsigned peers[SCATTER_ITEMS];
+  int head_lane[SCATTER_ITEMS];
 #pragma unroll
   for (int j = 0; j < SCATTER_ITEMS; ++j) {
     const int64_t i = first + (int64_t)j * SCATTER_THREADS;
-    k[j] = i < n ? key[i] : -1;  // key -1: the particle left the slab (migrate.cu)
+    k[j] = i < n ? key[i] : -1;  // key -1: the particle left the slab (migrate.cu) or the box (open boundary)
   }
+  // The input is nearly sorted: the lanes of a warp form a few runs of equal keys.  The first lane of a run reserves
+  // the whole run with one atomic; runs are found with one shuffle and two ballots (a key that appears in two
+  // separate runs simply reserves twice).
 #pragma unroll
   for (int j = 0; j < SCATTER_ITEMS; ++j) {
     const bool live = k[j] >= 0;
-    const unsigned active = __ballot_sync(0xffffffffu, live);
-    peers[j] = 0u;
+    const int32_t prev = __shfl_up_sync(0xffffffffu, k[j], 1);
+    const bool head = live && (lane == 0 || prev != k[j]);
+    const unsigned heads = __ballot_sync(0xffffffffu, head), lives = __ballot_sync(0xffffffffu, live);
+    const unsigned upto = 0xffffffffu >> (31 - lane);  // bits 0 .. lane
+    head_lane[j] = 31 - __clz(heads & upto);
+    const unsigned stops = (heads | ~lives) & ~upto;   // the next run start or dead lane above this lane
+    const int end = stops ? __ffs(stops) - 1 : 32;
     base[j] = 0;
-    if (live) {
-      peers[j] = __match_any_sync(active, k[j]);
-      if (lane == __ffs(peers[j]) - 1) base[j] = atomicAdd(&cursor[k[j]], __popc(peers[j]));
-    }
+    if (head) base[j] = atomicAdd(&cursor[k[j]], end - lane);
   }
 #pragma unroll
   for (int j = 0; j < SCATTER_ITEMS; ++j) {
+    const int32_t b = __shfl_sync(0xffffffffu, base[j], head_lane[j] & 31);
     if (k[j] < 0) continue;
     const int64_t i = first + (int64_t)j * SCATTER_THREADS;
-    const int32_t b = __shfl_sync(peers[j], base[j], __ffs(peers[j]) - 1);
-    const int32_t pos = b + __popc(peers[j] & ((1u << lane) - 1u));
+    const int32_t pos = b + (lane - head_lane[j]);
     const double vx = s3[i], vy = s4[i], vz = s5[i];
     d0[pos] = moved_coord(s0[i], vx, dtm, g.Lx);  // the same bits the key pass binned (dtm = 0: plain copy + wrap)
     d1[pos] = moved_coord(s1[i], vy, dtm, g.Ly);
@@ -316,8 +321,12 @@ int particles_sort(xb_ctx* c, Species& s, double dt_move)
   if (g.nranks > 1) XB_FAIL("particles_sort: multi-rank runs sort through migrate_and_sort");
   XB_CUDA(cudaMemsetAsync(c->hist, 0, sizeof(int32_t) * c->nbins, c->stream));
   double** p = s.p[s.cur];
+  XB_CHECK(prof_begin(c, XB_FAMILY_SORT_KEYS));
   if (n > 0) XB_LAUNCH(c, k_move_key, grid_for(n), 256, 0, g, n, p[0], p[1], p[2], p[3], p[4], p[5], dt_move, s.key, c->hist);
+  XB_CHECK(prof_end(c, XB_FAMILY_SORT_KEYS));
+  XB_CHECK(prof_begin(c, XB_FAMILY_SORT_SCATTER));
   XB_CHECK(sort_scan_and_scatter(c, s, n, nullptr, 0, 0, dt_move));
+  XB_CHECK(prof_end(c, XB_FAMILY_SORT_SCATTER));
   if (g.open_z) XB_CHECK(count_after_open_sort(c, s));
   s.sorted = true;
   return 0;

@@ -218,15 +218,32 @@ int Simulation::configure(const std::string& config_path)
   if (cfg.contains("Diagnostics"))  // diagnostics/builders/diagnostic_builder.cpp, field_view_builder.cpp:13-52
     for (const json& info : cfg.at("Diagnostics")) {
       const std::string name = info.at("diagnostic").get<std::string>();
-      if (name == "FieldView") {
-        if (info.contains("region")) throw std::runtime_error("FieldView: only the whole-box region is covered by this build");
-        field_views_.push_back(info.at("field").get<std::string>());
+      if (name == "FieldView") {  // diagnostics/builders/field_view_builder.cpp:13-50
+        View v;
+        v.field = info.at("field").get<std::string>();
+        v.dof = 3;
+        parse_region(json_ref{&info}, v);
+        v.dir = out_dir + "/" + v.field + v.suffix;
+        field_views_.push_back(v);
       }
-      else if (name == "DistributionMoment") {  // diagnostics/builders/distribution_moment_builder.cpp:27-75
-        if (info.contains("region")) throw std::runtime_error("DistributionMoment: only the whole-box region is covered by this build");
-        if (info.at("moment").get<std::string>() != "density")
-          throw std::runtime_error("DistributionMoment: only the density moment is covered by this build");
-        density_views_.push_back(info.at("particles").get<std::string>());
+      else if (name == "DistributionMoment") {  // diagnostics/builders/distribution_moment_builder.cpp:13-75
+        static const std::pair<const char*, std::pair<int, int>> moments[] = {
+          {"density", {XB_MOMENT_DENSITY, 1}}, {"current", {XB_MOMENT_CURRENT, 3}}, {"momentum_flux", {XB_MOMENT_MOMENTUM_FLUX, 6}},
+          {"momentum_flux_cyl", {XB_MOMENT_MOMENTUM_FLUX_CYL, 6}}, {"momentum_flux_diag", {XB_MOMENT_MOMENTUM_FLUX_DIAG, 3}},
+          {"momentum_flux_diag_cyl", {XB_MOMENT_MOMENTUM_FLUX_DIAG_CYL, 3}}};
+        View v;
+        v.particles = info.at("particles").get<std::string>();
+        v.field = info.at("moment").get<std::string>();
+        v.moment = -1;
+        for (const auto& m : moments)
+          if (v.field == m.first) {
+            v.moment = m.second.first;
+            v.dof = m.second.second;
+          }
+        if (v.moment < 0) throw std::runtime_error("Unknown moment name " + v.field + " for particles " + v.particles);
+        parse_region(json_ref{&info}, v);
+        v.dir = out_dir + "/" + v.particles + "/" + v.field + v.suffix;
+        moment_views_.push_back(v);
       }
       else if (name == "LogView") {  // diagnostics/builders/log_view_builder.cpp: one of three levels
         const std::string level = info.at("level").get<std::string>();
@@ -291,6 +308,40 @@ int Simulation::configure(const std::string& config_path)
     if (mpi.contains("da_processors_z")) da_processors_z_ = mpi.at("da_processors_z").get<int>();
   }
   return 0;
+}
+
+// "region" of a FieldView / DistributionMoment (field_view_builder.cpp:52-147): a 3D box or a one-cell-thick 2D plane
+void Simulation::parse_region(const json_ref& info_ref, View& v) const
+{
+  const json& info = *static_cast<const json*>(info_ref.p);
+  v.start = {0, 0, 0};
+  v.size = {geom.geom_nx, geom.geom_ny, geom.geom_nz};
+  v.suffix.clear();
+  if (!info.contains("region")) return;
+  const json& r = info.at("region");
+  const std::string type = r.contains("type") ? r.at("type").get<std::string>() : std::string("3D");
+  if (type != "3D" && type != "2D") throw std::runtime_error("Incorrect type is used for " + v.field + " .");
+  std::array<double, 3> start = {0.0, 0.0, 0.0}, size = {geom.geom_x, geom.geom_y, geom.geom_z};
+  if (r.contains("start")) start = parse_vector(r, "start", geom);
+  if (r.contains("size")) size = parse_vector(r, "size", geom);
+  const double d[3] = {geom.dx, geom.dy, geom.dz};
+  if (type == "2D") {
+    const std::string plane = r.at("plane").get<std::string>();
+    const int axis = plane == "X" ? 0 : (plane == "Y" ? 1 : (plane == "Z" ? 2 : -1));
+    if (axis < 0) throw std::runtime_error("Unknown plane " + plane);
+    double position = 0.5 * (axis == 0 ? geom.geom_x : (axis == 1 ? geom.geom_y : geom.geom_z));
+    if (r.contains("position")) r.at("position").get_to(position);
+    start[axis] = position;
+    size[axis] = d[axis];
+    v.suffix = std::format("_plane{}_{:04d}", plane, (int)std::floor(position / d[axis]));
+  }
+  const int n[3] = {geom.geom_nx, geom.geom_ny, geom.geom_nz};
+  for (int a = 0; a < 3; ++a) {
+    v.start[a] = (int)std::floor(start[a] / d[a]);
+    v.size[a] = (int)std::floor(size[a] / d[a]);
+    if (v.start[a] < 0 || v.start[a] + v.size[a] > n[a]) throw std::runtime_error("Region is not in global boundaries for " + v.field + " diagnostic.");
+    if (v.size[a] <= 0) throw std::runtime_error("Sizes are invalid for " + v.field + " diagnostic.");
+  }
 }
 
 Particles& Simulation::get_named_particles(const std::string& name)
@@ -483,50 +534,53 @@ int Simulation::diagnose_fields(int t)
   if (t % geom.diagnose_period != 0) return 0;
   const int width = (int)std::to_string(geom.geom_nt).size();
   std::vector<double> f;
-  std::vector<float> out;
-  for (const std::string& sort : density_views_) {  // DistributionMoment::diagnose (distribution_moment.cpp:112-122)
+  for (const View& v : moment_views_) {  // DistributionMoment::diagnose (distribution_moment.cpp:112-122)
     int32_t sid = -1;
     for (size_t i = 0; i < particles_.size(); ++i)
-      if (particles_[i]->parameters.sort_name == sort) sid = (int32_t)i;
-    if (sid < 0) throw std::runtime_error("No particles with name " + sort);
-    f.resize((size_t)geom.geom_nx * geom.geom_ny * nzl_);
-    B200_CALL(xb_distribution_moment(ctx, sid, XB_MOMENT_DENSITY, f.data()));
-    out.assign(f.begin(), f.end());
-    const std::string dir = out_dir + "/" + sort + "/density";
-    std::filesystem::create_directories(dir);
-    if (write_slab(dir + "/" + std::format("{:0{}d}", t, width), out, 1)) return 1;
+      if (particles_[i]->parameters.sort_name == v.particles) sid = (int32_t)i;
+    if (sid < 0) throw std::runtime_error("No particles with name " + v.particles);
+    f.resize((size_t)v.dof * geom.geom_nx * geom.geom_ny * nzl_);
+    const int32_t st[3] = {v.start[0], v.start[1], v.start[2]}, sz[3] = {v.size[0], v.size[1], v.size[2]};
+    B200_CALL(xb_distribution_moment_region(ctx, sid, v.moment, st, sz, f.data()));
+    std::filesystem::create_directories(v.dir);
+    if (write_region(v.dir + "/" + std::format("{:0{}d}", t, width), f, v)) return 1;
   }
-  for (const std::string& field : field_views_) {
-    if (get_named_vector(field, f)) return 1;
-    out.assign(f.begin(), f.end());
-    const std::string dir = out_dir + "/" + field;
-    std::filesystem::create_directories(dir);
-    if (write_slab(dir + "/" + std::format("{:0{}d}", t, width), out, 3)) return 1;
+  for (const View& v : field_views_) {
+    if (get_named_vector(v.field, f)) return 1;
+    std::filesystem::create_directories(v.dir);
+    if (write_region(v.dir + "/" + std::format("{:0{}d}", t, width), f, v)) return 1;
   }
   return 0;
 }
 
-// One dump file for all ranks, as MPIBinaryFile writes it through an MPI subarray view (field_view.cpp:59-95):
-// with z-slabs the slab of rank r is a contiguous range of the natural [z][y][x][c] image, written at its offset.
-int Simulation::write_slab(const std::string& path, const std::vector<float>& slab, int components)
+// One dump file for all ranks, as MPIBinaryFile writes it through MPI subarray views (field_view.cpp:59-95): the
+// float32 image of the region in natural [z][y][x][component] order.  `slab` is this rank's z-slab of the whole box;
+// the rows of the region that lie in it are written at their offsets (one write per plane when the region spans x and y).
+int Simulation::write_region(const std::string& path, const std::vector<double>& slab, const View& v)
 {
+  const int nx = geom.geom_nx, ny = geom.geom_ny;
+  const int zlo = std::max(v.start[2], z0_), zhi = std::min(v.start[2] + v.size[2], z0_ + nzl_);
   const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT, 0644);
   if (fd < 0) throw std::runtime_error("cannot open " + path + " for writing");
-  const off_t offset = (off_t)sizeof(float) * components * geom.geom_nx * geom.geom_ny * (off_t)z0_;
-  const char* data = reinterpret_cast<const char*>(slab.data());
-  size_t left = slab.size() * sizeof(float);
-  off_t at = offset;
-  while (left > 0) {
-    const ssize_t w = ::pwrite(fd, data, left, at);
-    if (w <= 0) {
-      ::close(fd);
-      throw std::runtime_error("short write into " + path);
+  const size_t row = (size_t)v.size[0] * v.dof;
+  std::vector<float> buf(row * v.size[1]);
+  bool ok = true;
+  for (int z = zlo; z < zhi && ok; ++z) {
+    for (int y = 0; y < v.size[1]; ++y) {
+      const double* src = slab.data() + ((((size_t)(z - z0_) * ny + (v.start[1] + y)) * nx + v.start[0]) * v.dof);
+      for (size_t i = 0; i < row; ++i) buf[(size_t)y * row + i] = (float)src[i];
     }
-    data += w;
-    at += w;
-    left -= (size_t)w;
+    const off_t at = (off_t)sizeof(float) * row * v.size[1] * (off_t)(z - v.start[2]);
+    const char* data = reinterpret_cast<const char*>(buf.data());
+    size_t left = buf.size() * sizeof(float), done = 0;
+    while (ok && left > 0) {
+      const ssize_t w = ::pwrite(fd, data + done, left, at + (off_t)done);
+      ok = w > 0;
+      if (ok) { done += (size_t)w; left -= (size_t)w; }
+    }
   }
   ::close(fd);
+  if (!ok) throw std::runtime_error("short write into " + path);
   return 0;
 }
 

@@ -124,7 +124,14 @@ private:
     std::array<double, 3> amplitude{}, wave_number{}, mbox_min{}, mbox_max{};  // MaxwellCosinePerturbation
   };
   int diagnose_log(int t);          // LogView (src/diagnostics/log_view.cpp)
-  int write_slab(const std::string& path, const std::vector<float>& slab, int components);  // every rank's part of one dump file
+  struct View {  // FieldView / DistributionMoment: what is dumped, which region, where
+    std::string field, particles, dir, suffix;
+    int moment = -1, dof = 3;
+    std::array<int, 3> start{}, size{};
+  };
+  struct json_ref { const void* p; };  // keeps nlohmann/json out of this header
+  void parse_region(const json_ref& info, View& v) const;
+  int write_region(const std::string& path, const std::vector<double>& slab, const View& v);  // every rank's part of one dump file
   int log_levels_ = 0;              // bit 0 EachTimestep, bit 1 DiagnosePeriodAvg, bit 2 AllTimestepsSummary
   double log_prev_wall_ = 0, log_period_wall_ = 0, wall_start_ = 0;
   std::array<double, XB_STAGE_COUNT> log_prev_stage_{}, log_period_stage_{};
@@ -135,8 +142,8 @@ private:
   int z0_ = 0, nzl_ = 0;            // owned planes
   std::vector<SortParameters> sorts_;
   std::vector<Preset> presets_;
-  std::vector<std::string> density_views_;  // "Diagnostics": [{"diagnostic": "DistributionMoment", "particles": ..., "moment": "density"}]
-  std::vector<std::string> field_views_;  // "Diagnostics": [{"diagnostic": "FieldView", "field": ...}]
+  std::vector<View> moment_views_;  // "Diagnostics": [{"diagnostic": "DistributionMoment", "particles": ..., "moment": ..., "region": ...}]
+  std::vector<View> field_views_;   // "Diagnostics": [{"diagnostic": "FieldView", "field": ..., "region": ...}]
   std::unique_ptr<Table> energy_, energy_cons_, convergence_, charge_, momentum_;
   std::vector<std::array<double, 3>> P0_;  // MomentumConservation::P0
   bool charge_header_ = false;
