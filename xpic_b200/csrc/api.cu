@@ -303,7 +303,12 @@ static int create_impl(xb_ctx* c, const xb_grid* gr, const void* uid)
   if (g.ntot >= (int64_t)0x7fffffff) XB_FAIL("xb_create: slab too large for 32-bit field offsets");
 
   XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  XB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  {  // the copy stream carries host copies and, in multi-rank runs, the exchanges that run beside the main stream's
+     // kernels (ghost particles, halo planes): highest priority, so that its kernels get the first SM that frees up
+    int lo = 0, hi = 0;
+    XB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    XB_CUDA(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, hi));
+  }
   XB_CUDA(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
   XB_CUDA(cudaEventCreate(&c->ev0));
   XB_CUDA(cudaEventCreate(&c->ev1));
@@ -382,6 +387,8 @@ int xb_destroy(xb_ctx* c)
   for (auto& v : c->prof_events)
     for (auto e : v) cudaEventDestroy(e);
   if (c->copy_done) cudaEventDestroy(c->copy_done);
+  if (c->halo_ready) cudaEventDestroy(c->halo_ready);
+  if (c->halo_done) cudaEventDestroy(c->halo_done);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;

@@ -1,5 +1,7 @@
 // comm.cu -- see comm.cuh.
 #include <dlfcn.h>
+
+#include <cstdlib>
 #include <nccl.h>
 
 #include "comm.cuh"
@@ -139,8 +141,9 @@ int comm_exchange_list(xb_ctx* c, const ExchangeList& l, cudaStream_t stream)
 }
 
 // ghost planes [-w, 0) <- down's top planes ; [nzl, nzl + w) <- up's bottom planes
-int comm_halo_fill(xb_ctx* c, double* v, int w)
+int comm_halo_fill(xb_ctx* c, double* v, int w, cudaStream_t stream)
 {
+  if (!stream) stream = c->stream;
   const Grid& g = c->g;
   if (g.nzl < w) XB_FAIL("slab thinner than the halo width");
   const int64_t p3 = g.plane * 3;
@@ -151,9 +154,9 @@ int comm_halo_fill(xb_ctx* c, double* v, int w)
   double* gh_hi = v + (int64_t)(GZ + g.nzl) * p3;
   // open z: nothing crosses the box ends; the ghost planes there hold zeros (DMDA local vectors)
   const bool down = !(g.open_z && g.rank == 0), up = !(g.open_z && g.rank == g.nranks - 1);
-  if (!down) XB_CUDA(cudaMemsetAsync(gh_lo, 0, bytes, c->stream));
-  if (!up) XB_CUDA(cudaMemsetAsync(gh_hi, 0, bytes, c->stream));
-  return comm_exchange(c, own_lo, down ? bytes : 0, own_hi, up ? bytes : 0, gh_hi, up ? bytes : 0, gh_lo, down ? bytes : 0);
+  if (!down) XB_CUDA(cudaMemsetAsync(gh_lo, 0, bytes, stream));
+  if (!up) XB_CUDA(cudaMemsetAsync(gh_hi, 0, bytes, stream));
+  return comm_exchange(c, own_lo, down ? bytes : 0, own_hi, up ? bytes : 0, gh_hi, up ? bytes : 0, gh_lo, down ? bytes : 0, stream);
 }
 
 // owned bottom planes += up-neighbour's view of them (its high ghosts go to up's owners) ...

@@ -11,7 +11,7 @@ namespace xb {
 int comm_unique_id(void* out128);
 int comm_init(xb_ctx* c, const void* uid128);
 void comm_free(xb_ctx* c);
-int comm_halo_fill(xb_ctx* c, double* v, int width);
+int comm_halo_fill(xb_ctx* c, double* v, int width, cudaStream_t stream = nullptr);
 int comm_halo_reduce(xb_ctx* c, double* v, int wlo, int whi);
 int comm_allreduce_sum(xb_ctx* c, double* dev, int n);
 // Exchange byte buffers with the z neighbours: `to_down`/`to_up` are sent, `from_up`/`from_down`

@@ -154,6 +154,8 @@ struct xb_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // host<->device copies of xb_step_host that overlap with the particle stages
   cudaEvent_t copy_done = nullptr;
+  cudaEvent_t halo_ready = nullptr, halo_done = nullptr;  // halo_begin / halo_end
+  bool halo_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // CUDA-event pairs (start, stop) recorded around every launch group of a kernel family inside the step
   // (xb_family_profile); family 3 is the operator SpMV (xb_spmv_profile)
@@ -212,6 +214,8 @@ constexpr int RED_MAXV = 32;
 
 // ---- fields.cu -------------------------------------------------------------------------------
 int halo_fill(xb_ctx* c, double* v, int width);                 // DMGlobalToLocal(INSERT)
+int halo_begin(xb_ctx* c, double* v, int width);                // DMGlobalToLocalBegin: the exchange runs beside the main stream
+int halo_end(xb_ctx* c);                                        // DMGlobalToLocalEnd
 int halo_reduce(xb_ctx* c, double* v, int width_lo, int width_hi);  // DMLocalToGlobal(ADD)
 int vec_zero(xb_ctx* c, double* v);                              // whole ghosted vector
 int vec_copy_owned(xb_ctx* c, const double* src, double* dst);

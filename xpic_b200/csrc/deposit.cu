@@ -583,8 +583,10 @@ int ghost_exchange_begin(xb_ctx* c, Species& s);
 int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage);
 
 // cell blocks of `ncells` consecutive cells (bin space) into the staging area
+// zl_first: local plane index of the first cell (the cells of one launch are whole planes: owned planes 0 .. nzl - 1,
+// or one ghost plane, -1 / nzl)
 int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* bin_start, int64_t bin_cell0, int64_t ncells, int64_t stage_cell0,
-                  int zshift, double** rec, int64_t rec_stride, int64_t nparticles)
+                  int zshift, double** rec, int64_t rec_stride, int64_t nparticles, int zl_first)
 {
   // variants (xb_set_option(ctx, 0, v)): 0 fused warp-specialised DMMA kernel, 3 fused kernel without role split,
   // 2 round-1 pipeline (field records in HBM + two-warp DMMA kernel), 1 scalar-FMA cell blocks
@@ -605,9 +607,8 @@ int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* 
   a.rec = nullptr;
   a.rec_stride = rec_stride;
   if ((a.stage_cell0 % CELL_GROUP) != 0) XB_FAIL("deposit: plane size must be a multiple of the staging group in multi-rank runs");
-  // the cells of one launch are whole planes: owned planes (bin plane 1.. -> zl 0..) or one ghost plane
   const Grid& g = c->g;
-  const int zl_off = bin_cell0 == g.plane ? 0 : (stage_cell0 == 0 ? -1 : g.nzl);
+  const int zl_off = zl_first;
   if (variant == 0 || variant == 3) return launch_cell_moments(c, a, zl_off, variant);
 
   const bool use_mma = variant == 2;
@@ -644,7 +645,16 @@ int deposit_moments(xb_ctx* c)
     // bin plane 1 = first owned plane; staging plane 0 is the low ghost plane in multi-rank runs
     if (!single) XB_CHECK(ghost_exchange_mark(c, s));
     XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_CELLS));
-    XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane, g.ncl, single ? 0 : g.plane, 0, &s.rec, s.capacity, s.count));
+    // Several slabs: the owned planes go in two launches, a short one first.  The kernel is persistent (one wave of
+    // CTAs that own their SMs until the launch ends), and NCCL's send / receive kernel of the ghost exchange, which
+    // waits on the high-priority copy stream, can only get SMs where a wave ends: after an eighth of the planes.
+    const int first_chunk = single ? g.nzl : (g.nzl + 7) / 8;
+    for (int p0 = 0; p0 < g.nzl;) {
+      const int np = p0 == 0 ? first_chunk : g.nzl - p0;
+      XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane * (1 + p0), g.plane * np, single ? g.plane * p0 : g.plane * (1 + p0), 0, &s.rec,
+                             s.capacity, s.count, p0));
+      p0 += np;
+    }
     XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_CELLS));
     if (!single) {
       // the boundary-plane particles of the z neighbours travel (copy stream) while the owned planes are computed

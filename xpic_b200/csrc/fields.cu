@@ -73,6 +73,33 @@ int halo_fill(xb_ctx* c, double* v, int width)
   return comm_halo_fill(c, v, width);
 }
 
+// Multi-rank: the exchange of v's ghost planes starts on the copy stream as soon as everything queued so far on the
+// main stream is done (the kernel that produced v's edge planes), halo_end() makes the main stream wait for it.  Work
+// that needs no ghost planes (the interior planes of a stencil sweep) is launched in between and hides the exchange.
+int halo_begin(xb_ctx* c, double* v, int width)
+{
+  if (c->g.nranks == 1) return halo_fill(c, v, width);
+  if (c->halo_pending) XB_FAIL("halo_begin: the previous exchange has not been waited for");
+  if (!c->halo_ready) {
+    XB_CUDA(cudaEventCreateWithFlags(&c->halo_ready, cudaEventDisableTiming));
+    XB_CUDA(cudaEventCreateWithFlags(&c->halo_done, cudaEventDisableTiming));
+  }
+  XB_CUDA(cudaEventRecord(c->halo_ready, c->stream));
+  XB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->halo_ready, 0));
+  XB_CHECK(comm_halo_fill(c, v, width, c->copy_stream));
+  XB_CUDA(cudaEventRecord(c->halo_done, c->copy_stream));
+  c->halo_pending = true;
+  return 0;
+}
+
+int halo_end(xb_ctx* c)
+{
+  if (!c->halo_pending) return 0;
+  XB_CUDA(cudaStreamWaitEvent(c->stream, c->halo_done, 0));
+  c->halo_pending = false;
+  return 0;
+}
+
 int halo_reduce(xb_ctx* c, double* v, int wlo, int whi)
 {
   const Grid& g = c->g;

@@ -22,12 +22,13 @@ int spmv(xb_ctx* c, int op, double* x, double* y);
 // z1 carries valid ghosts (width 1).  96 B of HBM traffic per node (z1, z0, u in, z2 out; the 13-point
 // stencil reads hit L1/L2) against 144 B for the textbook form that carries the residual and the
 // direction along (z += d; r -= D d; d = a d + b r).  z0 == nullptr stands for z0 = 0 (first step).
+// planes [zl0, zl0 + nplanes) of the slab
 __global__ void __launch_bounds__(256) k_cheb_step(Grid g, const double* __restrict__ z1, const double* __restrict__ z0, const double* __restrict__ u,
-                                                  double* __restrict__ z2, double a, double b, double diag)
+                                                  double* __restrict__ z2, double a, double b, double diag, int zl0, int nplanes)
 {
-  const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (node >= g.ncl) return;
-  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = (int)(node / g.plane);
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= g.plane * nplanes) return;
+  const int x = (int)(idx % g.nx), y = (int)((idx / g.nx) % g.ny), zl = zl0 + (int)(idx / g.plane);
   const int xm = x == 0 ? g.nx - 1 : x - 1, xp = x == g.nx - 1 ? 0 : x + 1;
   const int ym = y == 0 ? g.ny - 1 : y - 1, yp = y == g.ny - 1 ? 0 : y + 1;
   auto f = [&](int comp, int ox, int oy, int oz) {
@@ -78,12 +79,29 @@ static int cheb_apply(xb_ctx* c, int deg, const double* u, double* z, double* /*
   const int off = (3 - deg % 3) % 3;  // z_k lives in buf[(k + off) % 3]; z_deg in buf[0] = z
   XB_CHECK(scale_into(c, u, 1.0 / theta, buf[(1 + off) % 3]));  // z_1
   double rho_old = 1.0 / sigma;
-  for (int k = 1; k < deg; ++k) {  // z_{k+1} from z_k, z_{k-1}
-    const double rho = 1.0 / (2.0 * sigma - rho_old);
+  auto step = [&](int k, double rho, int zl0, int nplanes) -> int {
     double* zk = buf[(k + off) % 3];
     const double* zkm = k > 1 ? buf[(k - 1 + off) % 3] : nullptr;
-    XB_CHECK(halo_fill(c, zk, 1));
-    XB_LAUNCH(c, k_cheb_step, (int)((g.ncl + 255) / 256), 256, 0, g, zk, zkm, u, buf[(k + 1 + off) % 3], rho * rho_old, 2.0 * rho / delta, diag);
+    XB_LAUNCH(c, k_cheb_step, (int)((g.plane * nplanes + 255) / 256), 256, 0, g, zk, zkm, u, buf[(k + 1 + off) % 3], rho * rho_old, 2.0 * rho / delta, diag,
+              zl0, nplanes);
+    return 0;
+  };
+  // several slabs: the ghost planes of z_k travel while the planes that need none of them are swept (1 .. nzl - 2)
+  const bool split = g.nranks > 1 && g.nzl >= 4;
+  if (split && deg > 1) XB_CHECK(halo_begin(c, buf[(1 + off) % 3], 1));
+  for (int k = 1; k < deg; ++k) {  // z_{k+1} from z_k, z_{k-1}
+    const double rho = 1.0 / (2.0 * sigma - rho_old);
+    if (split) {
+      XB_CHECK(step(k, rho, 1, g.nzl - 2));
+      XB_CHECK(halo_end(c));
+      XB_CHECK(step(k, rho, 0, 1));
+      XB_CHECK(step(k, rho, g.nzl - 1, 1));
+      if (k + 1 < deg) XB_CHECK(halo_begin(c, buf[(k + 1 + off) % 3], 1));
+    }
+    else {
+      XB_CHECK(halo_fill(c, buf[(k + off) % 3], 1));
+      XB_CHECK(step(k, rho, 0, g.nzl));
+    }
     rho_old = rho;
   }
   return 0;

@@ -34,7 +34,7 @@ int sort_scan_and_scatter(xb_ctx* c, Species& s, int64_t nlocal, const MigrateBu
                           double dt_move);  // particles.cu
 int count_after_open_sort(xb_ctx* c, Species& s);
 int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* bin_start, int64_t bin_cell0, int64_t ncells, int64_t stage_cell0,
-                  int zshift, double** rec, int64_t rec_stride, int64_t nparticles);  // deposit.cu
+                  int zshift, double** rec, int64_t rec_stride, int64_t nparticles, int zl_first);  // deposit.cu
 
 constexpr int SLOT = 8;  // 64-bit words every rank contributes to the all-gathered table
 
@@ -335,9 +335,9 @@ int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage)
   // low ghost plane: the neighbour below; across the periodic boundary its z is nz planes above mine
   const int zs_lo = g.rank == 0 ? -g.nz : 0;
   const int zs_hi = g.rank == g.nranks - 1 ? +g.nz : 0;
-  if (m.nghost[0] >= 0) XB_CHECK(deposit_cells(c, s, m.ghost[0], m.ghost_bins[0], 0, g.plane, 0, zs_lo, &m.ghost_rec[0], m.ghost_cap, m.nghost[0]));
+  if (m.nghost[0] >= 0) XB_CHECK(deposit_cells(c, s, m.ghost[0], m.ghost_bins[0], 0, g.plane, 0, zs_lo, &m.ghost_rec[0], m.ghost_cap, m.nghost[0], -1));
   if (m.nghost[1] >= 0)
-    XB_CHECK(deposit_cells(c, s, m.ghost[1], m.ghost_bins[1], 0, g.plane, (int64_t)(g.nzl + 1) * g.plane, zs_hi, &m.ghost_rec[1], m.ghost_cap, m.nghost[1]));
+    XB_CHECK(deposit_cells(c, s, m.ghost[1], m.ghost_bins[1], 0, g.plane, (int64_t)(g.nzl + 1) * g.plane, zs_hi, &m.ghost_rec[1], m.ghost_cap, m.nghost[1], g.nzl));
   return 0;
 }
 

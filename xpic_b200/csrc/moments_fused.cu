@@ -666,10 +666,7 @@ int launch_cell_moments(xb_ctx* c, const DepositArgs& a, int zl_off, int form)
   }
   const int groups = (int)((a.ncells + FM_CELLS - 1) / FM_CELLS);
   if (c->sm_count == 0) XB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
-  // persistent CTAs: one wave.  In a multi-rank run four SMs stay free: the boundary-plane particles travel through
-  // NCCL's own kernels while this one runs (ghost_exchange_begin), and a CTA of those needs an SM of its own
-  const int sms = c->g.nranks > 1 && c->sm_count > 8 ? c->sm_count - 4 : c->sm_count;
-  const int resident = sms * (form == 0 ? 2 : 3);
+  const int resident = c->sm_count * (form == 0 ? 2 : 3);  // persistent CTAs: one wave
   const int grid = groups < resident ? groups : resident;
   if (grid < 1) return 0;
   if (form == 0)  // warp-specialised: producers (records) and consumers (DMMA) in one CTA
