@@ -372,6 +372,7 @@ int xb_destroy(xb_ctx* c)
                     c->cheb_Md, c->ksp_u, c->red_partial, c->red_out, c->cap_x, c->cap_F, c->cap_g, c->cap_rhs0, c->cap_J})
     cudaFree(v);
   cudaFree(c->cap_counters);
+  cudaFree(c->work_counter);
   for (auto e : c->nl.events)
     if (e) cudaEventDestroy(e);
   for (double* v : c->V) cudaFree(v);

@@ -148,6 +148,7 @@ struct xb_ctx {
   xb::Grid g;
   int device = 0;
   int sm_count = 0;
+  int* work_counter = nullptr;  // k_cell_moments_ws: next group of cells to hand out
   int ws_backoff_ns = 64;  // k_cell_moments_ws: pause of a waiting warp between two polls of its mbarrier (xb_set_option 5)
   bool track_ids = false;
   bool deterministic = false;  // canonical particle order inside every bin even without ids (costs one more pass)

@@ -645,15 +645,15 @@ int deposit_moments(xb_ctx* c)
     // bin plane 1 = first owned plane; staging plane 0 is the low ghost plane in multi-rank runs
     if (!single) XB_CHECK(ghost_exchange_mark(c, s));
     XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_CELLS));
-    // Several slabs: the owned planes go in two launches, a short one first.  The kernel is persistent (one wave of
-    // CTAs that own their SMs until the launch ends), and NCCL's send / receive kernel of the ghost exchange, which
-    // waits on the high-priority copy stream, can only get SMs where a wave ends: after an eighth of the planes.
-    const int first_chunk = single ? g.nzl : (g.nzl + 7) / 8;
-    for (int p0 = 0; p0 < g.nzl;) {
-      const int np = p0 == 0 ? first_chunk : g.nzl - p0;
+    // Several slabs: the owned planes go in eight launches instead of one.  The kernel is persistent (one wave of CTAs
+    // that own their SMs until the launch ends); NCCL's kernels of the ghost exchange, which wait on the high-priority
+    // copy stream, get SMs where a wave ends: the count table after the first launch, the payloads after the second.
+    // The dynamic work distribution of the kernel absorbs the SMs NCCL holds meanwhile.
+    const int chunk = single ? g.nzl : (g.nzl + 7) / 8;
+    for (int p0 = 0; p0 < g.nzl; p0 += chunk) {
+      const int np = chunk < g.nzl - p0 ? chunk : g.nzl - p0;
       XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane * (1 + p0), g.plane * np, single ? g.plane * p0 : g.plane * (1 + p0), 0, &s.rec,
                              s.capacity, s.count, p0));
-      p0 += np;
     }
     XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_CELLS));
     if (!single) {

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(FM_THREADS, MINB) k_cell_moments(Grid g, Depos
 // =====================================================================================================
 constexpr int WS_THREADS = 256;
 constexpr int WS_STAGES = 2;
-constexpr int WS_META = 16;  // ints per stage: [0..8] bin boundaries of the cell (first round only), [9] base, [10] n, [11] 1 = first | 2 = last
+constexpr int WS_META = 16;  // ints per stage: [0..8] bin boundaries of the cell (first round only), [9] base, [10] n, [11] 1 = first | 2 = last | 4 = stop, [12] group
 // per cell: block, WS_STAGES x 32 records, zero record, B tile, meta, 2 x WS_STAGES mbarriers (+ pad to 16 k + 8)
 constexpr int WS_CELL = FM_BLOCK + WS_STAGES * FM_CHUNK * FM_REC + FM_REC + FM_TILE + WS_STAGES * WS_META / 2 + 2 * WS_STAGES + 12;
 static_assert(WS_CELL % 16 == 8, "write-out reads the four blocks of a CTA without bank conflicts");
@@ -429,7 +429,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity, unsigned ba
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage, int zl_off,
-                                                                   int groups, unsigned backoff_ns)
+                                                                   int groups, unsigned backoff_ns, int* __restrict__ next_group)
 {
   extern __shared__ __align__(16) double smem[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -442,6 +442,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
   int* meta = reinterpret_cast<int*>(Bt + FM_TILE);
   uint64_t* full = reinterpret_cast<uint64_t*>(meta + WS_STAGES * WS_META);
   uint64_t* empty = full + WS_STAGES;
+  // Work is handed out dynamically: producer warp 4 takes the next group of four cells from a global counter and
+  // tells the other producers through these two slots (one named barrier per round); the consumers read the group
+  // from the first message of the round.  A CTA that starts late -- another kernel held its SM -- simply takes less.
+  __shared__ int sched[2];
 
   if (!producer) {
     double2* b2 = reinterpret_cast<double2*>(block);
@@ -469,9 +473,29 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
     }
     const double f = a.f_beta;
     int seq = 0;
-    for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    for (int round = 0;; ++round) {
+      if (wid == 4 && lane == 0) sched[round & 1] = atomicAdd(next_group, 1);
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // the four producer warps
+      const int grp = sched[round & 1];
       const int64_t cell_local = (int64_t)grp * FM_CELLS + slot;
-      if (cell_local >= a.ncells) continue;
+      if (grp >= groups || cell_local >= a.ncells) {
+        // nothing to produce for this slot: an empty message keeps the consumer in step (and stops it after the last group)
+        const int st = seq & (WS_STAGES - 1);
+        mbar_wait(empty + st, ((seq / WS_STAGES) & 1) ^ 1, backoff_ns);
+        int* mt = meta + st * WS_META;
+        if (lane == 0) {
+          mt[9] = 0;
+          mt[10] = 0;
+          mt[11] = 1 | 2 | (grp >= groups ? 4 : 0);
+          mt[12] = grp;
+        }
+        if (lane < 9) mt[lane] = 0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + st);
+        ++seq;
+        if (grp >= groups) break;
+        continue;
+      }
       // the cells of one launch are whole planes (deposit_cells): owned planes or one ghost plane
       const int pl = (int)(cell_local / g.plane), rem = (int)(cell_local % g.plane);
       const int cy = rem / g.nx, cx = rem % g.nx, zl = pl + zl_off;
@@ -554,6 +578,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
           mt[9] = base;
           mt[10] = n;
           mt[11] = (first ? 1 : 0) | (base + n >= p1 ? 2 : 0);
+          mt[12] = grp;
         }
         __syncwarp();  // every lane's records are written before lane 0 publishes the stage
         if (lane == 0) mbar_arrive(full + st);
@@ -577,9 +602,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
     L.colpos[c] = block_pos(c, 2 * L.q, 0, 0, 0);
   }
   int seq = 0;
-  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-    const int64_t cell_local = (int64_t)grp * FM_CELLS + slot;
-    if (cell_local < a.ncells) {
+  for (;;) {
+    int grp = 0;
+    bool stop = false;
+    {
       double acc[NMAT][2], cur[NCUR];
 #pragma unroll
       for (int v = 0; v < NMAT; ++v) acc[v][0] = acc[v][1] = 0.0;
@@ -597,6 +623,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
         if (flags & 1) {
           bsc = lane < 9 ? mt[lane] : 0;
           oend = __shfl_sync(0xffffffffu, bsc, 1);
+          grp = mt[12];
+          stop = (flags & 4) != 0;
         }
         const double* rbuf = recs + st * FM_CHUNK * FM_REC;
         int32_t pos = base;
@@ -635,6 +663,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
         fold<false, 0>(block, L, acc, cur);
       }
     }
+    if (stop) break;  // every slot of the CTA receives the stop message in the same round
     consumer_barrier();
     // coalesced write-out of the CTA's four blocks, stage[group][entry][cell % 4]: one consumer thread per entry
     // reads it from the four blocks, stores 32 contiguous bytes and leaves zeros behind for the next round
@@ -669,8 +698,11 @@ int launch_cell_moments(xb_ctx* c, const DepositArgs& a, int zl_off, int form)
   const int resident = c->sm_count * (form == 0 ? 2 : 3);  // persistent CTAs: one wave
   const int grid = groups < resident ? groups : resident;
   if (grid < 1) return 0;
-  if (form == 0)  // warp-specialised: producers (records) and consumers (DMMA) in one CTA
-    XB_LAUNCH(c, k_cell_moments_ws, grid, WS_THREADS, smem_ws, c->g, a, c->B, c->stage, zl_off, groups, (unsigned)c->ws_backoff_ns);
+  if (form == 0) {  // warp-specialised: producers (records) and consumers (DMMA) in one CTA, groups handed out dynamically
+    if (!c->work_counter) XB_CUDA(cudaMalloc(&c->work_counter, sizeof(int)));
+    XB_CUDA(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
+    XB_LAUNCH(c, k_cell_moments_ws, grid, WS_THREADS, smem_ws, c->g, a, c->B, c->stage, zl_off, groups, (unsigned)c->ws_backoff_ns, c->work_counter);
+  }
   else            // every warp does everything for its cell
     XB_LAUNCH(c, k_cell_moments<3>, grid, FM_THREADS, smem, c->g, a, c->B, c->stage, zl_off, groups);
   return 0;
