@@ -28,7 +28,10 @@ def main():
     steps = int(os.environ.get("XPIC_CHECK_STEPS", "6"))
     ok = True
     # the three schemes in a periodic box, then ECSIM with an open z boundary (particles leave through the outer slabs)
-    for scheme, oscheme, open_z in ((X.ECSIM, O.ECSIM, False), (X.ECSIMCORR, O.ECSIMCORR, False), (X.ECCAPFIM, O.ECCAPFIM, False), (X.ECSIM, O.ECSIM, True)):
+    # ... and ECSIM with the slabs depositing in batches of planes (the staging mode of large slabs)
+    cases = ((X.ECSIM, O.ECSIM, False, None), (X.ECSIMCORR, O.ECSIMCORR, False, None), (X.ECCAPFIM, O.ECCAPFIM, False, None), (X.ECSIM, O.ECSIM, True, None),
+             (X.ECSIM, O.ECSIM, False, "5.2e-3"))
+    for scheme, oscheme, open_z, stage_gb in cases:
         ids = [X.comm_unique_id() if rank == 0 else None]  # one communicator id per context
         dist.broadcast_object_list(ids, src=0)
         o = O.Oracle(n)  # only used for the reference's mt19937 initial particles
@@ -37,7 +40,10 @@ def main():
         pts, pid = o.get_particles(sid)
         rng = np.random.default_rng(5)
         B0 = 0.05 * rng.standard_normal(o.n3)
+        if stage_gb:
+            os.environ["XPIC_STAGE_GB"] = stage_gb  # 5 planes of 12 x 8 cells: batches of 3 planes
         slab = X.Simulation(n, scheme=scheme, device=local, rank=rank, nranks=world, comm_id=ids[0], track_ids=True, open_z=open_z)
+        os.environ.pop("XPIC_STAGE_GB", None)
         slab.add_species(Np=20, capacity=len(pid))
         mine = slab.add_particles(0, pts, pid)
         lo, hi = 3 * n[0] * n[1] * slab.z0, 3 * n[0] * n[1] * (slab.z0 + slab.nzl)
@@ -75,7 +81,7 @@ def main():
             eP = np.linalg.norm(P[order] - Ps[so]) / np.linalg.norm(Ps[so])
             left = len(pid) - len(Is)
             good = int(cnt.item()) == len(Is) and (left > 0) == open_z and np.array_equal(I[order], Is[so]) and max(eE, eB, eP) < 1e-9
-            print(f"scheme {scheme}{' open z' if open_z else ''}: ranks {world} particles {int(cnt.item())}/{len(pid)} relerr E {eE:.2e} B {eB:.2e} particles {eP:.2e} -> {'OK' if good else 'FAIL'}",
+            print(f"scheme {scheme}{' open z' if open_z else ''}{' batched staging' if stage_gb else ''}: ranks {world} particles {int(cnt.item())}/{len(pid)} relerr E {eE:.2e} B {eB:.2e} particles {eP:.2e} -> {'OK' if good else 'FAIL'}",
                   flush=True)
             ok = ok and good
             single.close()

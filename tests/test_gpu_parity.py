@@ -609,7 +609,7 @@ def test_decomposition_independence_on_two_gpus(X):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("-> OK") == 4
+    assert r.stdout.count("-> OK") == 5
 
 
 def test_open_z_boundary_state_parity(X):
@@ -708,3 +708,75 @@ def test_distribution_moments_and_regions(X, name):
         ref = cell_moment(pts, n, (0.5, 0.5, 0.5), 1.0 / 12, name, start=start or (0, 0, 0), size=size)
         assert got.shape == ref.shape
         assert np.max(np.abs(got - ref)) < 1e-12 * max(np.max(np.abs(ref)), 1e-30), (name, start)
+
+
+def test_host_program_runs_the_reference_root_configuration(X, tmp_path):
+    """The set-up of the reference's root config.json (eccapfim Langmuir wave: a 2 x 2 x 32 box, 1000 particles per cell,
+    MaxwellCosinePerturbation, three LogView levels), shortened to 20 steps, plus a 2D FieldView plane and a
+    DistributionMoment region: the host program accepts the schema, conserves energy at the solver tolerance and writes the
+    files the reference would."""
+    import json
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "xpic_b200", "_build", "xpic_b200.out")
+    if not os.path.exists(exe):
+        pytest.skip("host program not built")
+    cfg = json.load(open(os.path.join(ROOT, "configs", "langmuir_eccapfim.json")))
+    cfg["OutputDirectory"] = str(tmp_path / "lw")
+    path = tmp_path / "lw.json"
+    path.write_text(json.dumps(cfg))
+    r = subprocess.run([exe, str(path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    out = tmp_path / "lw"
+    titles, en = O.read_table(str(out / "temporal" / "energy_conservation.txt"))
+    assert en.shape[0] == 21
+    _, e = O.read_table(str(out / "temporal" / "energy.txt"))
+    total = e[:, 1] + e[:, 2] + e[:, 3]
+    assert np.max(np.abs(np.diff(total))) < 2e-6 * total[0]  # SNES atol = rtol = 1e-7, Picard tolerance 0.5e-7 per particle
+    assert e[-1, 1] > 10 * e[1, 1] or e[:, 1].max() > 1e-4  # the perturbation drives a field: wE grows from zero
+    for name in ("log-EachTimestep.txt", "log-DiagnosePeriodAvg.txt", "log-AllTimestepsSummary.txt"):
+        assert (out / name).exists()
+    assert len(open(str(out / "log-EachTimestep.txt")).read().splitlines()) == 21
+    plane = np.fromfile(str(out / "E_planeX_0001" / "20"), dtype=np.float32)
+    assert plane.size == 3 * 1 * 2 * 32  # one cell thick in x
+    cur = np.fromfile(str(out / "electrons" / "current" / "20"), dtype=np.float32)
+    assert cur.size == 3 * 2 * 2 * 8 and np.abs(cur).max() > 0
+
+
+@pytest.mark.parametrize("open_z", [False, True])
+def test_batched_staging_equals_whole_slab_staging(X, open_z, monkeypatch):
+    """Large slabs deposit in batches of P planes through a staging area of P + 2 planes (XPIC_STAGE_GB): the operator
+    and the current are bit-identical to the whole-slab staging, for every kernel variant."""
+    n = (12, 8, 10)
+    o, s0 = make_pair(n=n, Np=15, seed_fields=51)
+    pts, ids = o.get_particles(0)
+    f = s0.get_field("B")
+
+    def build(stage_gb):
+        if stage_gb is None:
+            monkeypatch.delenv("XPIC_STAGE_GB", raising=False)
+        else:
+            monkeypatch.setenv("XPIC_STAGE_GB", stage_gb)
+        s = X.Simulation(n, track_ids=True, open_z=open_z)
+        s.add_species(Np=15)
+        assert s.add_particles(0, pts, ids) == len(ids)
+        s.set_field("B", f)
+        return s
+
+    whole, batched = build(None), build("6.2e-3")  # 6 planes of 12 x 8 cells x 10.6 KB: batches of 4, 4, 2 planes
+    for variant in (0, 3, 2):
+        res = []
+        for s in (whole, batched):
+            s.set_option(0, variant)
+            s.deposit()
+            res.append((s.operator_download(), s.get_field("currI")))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]), variant
+    if not open_z:
+        o.deposit()
+        ref = csr_to_stencil(o, X.coef_table())
+        assert np.max(np.abs(res[1][0] - ref)) / np.max(np.abs(ref)) < 1e-13
+    whole.close()
+    batched.close()
+    s0.close()

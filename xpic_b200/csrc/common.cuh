@@ -177,6 +177,7 @@ struct xb_ctx {
   // deposit staging (cell blocks)
   double* stage = nullptr;
   int64_t stage_cells = 0;
+  int batch_planes = 0;  // 0: the staging area holds the whole slab; P > 0: batches of P planes through P + 2 staging planes
   // Krylov workspace
   std::vector<double*> V;  // restart + 1 basis vectors (ghosted)
   double* Z = nullptr;     // preconditioned direction (ghosted)

@@ -461,14 +461,16 @@ __global__ void __launch_bounds__(MMA_WARPS * 32, 2) k_cell_blocks_mma(Grid g, D
 // ---------------------------------------------------------------------------------------------
 struct GatherArgs {
   const double* stage;
-  int single_rank;  // 1: staging planes = owned planes, z wraps; 0: staging plane = zl + 1
+  int wrap;     // 1: the staging area holds exactly the owned planes of a single slab, z wraps
+  int base;     // else: staging plane of cell plane zl = zl - base (whole slab + 2 ghost planes: -1; a batch: first plane - 1)
+  int zl0, nplanes;  // planes whose rows this launch gathers
 };
 
 // staging id of cell (x, y, zl), zl in [-1, nzl]; -1: the cell lies outside an open z boundary
 __device__ __forceinline__ int64_t stage_cell(const Grid& g, const GatherArgs& a, int x, int y, int zl)
 {
   if (g.open_z && (g.z0 + zl < 0 || g.z0 + zl >= g.nz)) return -1;
-  const int pz = a.single_rank ? wrapi(zl, g.nzl) : zl + 1;
+  const int pz = a.wrap ? wrapi(zl, g.nzl) : zl - a.base;
   return ((int64_t)pz * g.ny + y) * g.nx + x;
 }
 
@@ -482,8 +484,8 @@ template <int C1, int C2>
 __global__ void __launch_bounds__(128) k_gather_rows(Grid g, GatherArgs a, double* __restrict__ coef, int accumulate)
 {
   const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (node >= g.ncl) return;
-  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = (int)(node / g.plane);
+  if (node >= g.plane * a.nplanes) return;
+  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = a.zl0 + (int)(node / g.plane);
   constexpr int NS = pair_size(C1, C2);
   double acc[NS];
 #pragma unroll
@@ -524,8 +526,8 @@ __global__ void __launch_bounds__(128) k_gather_rows(Grid g, GatherArgs a, doubl
 __global__ void k_gather_current(Grid g, GatherArgs a, double* __restrict__ sort_currI, double* __restrict__ sim_currI)
 {
   const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (node >= g.ncl) return;
-  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = (int)(node / g.plane);
+  if (node >= g.plane * a.nplanes) return;
+  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = a.zl0 + (int)(node / g.plane);
   double r[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int c = 0; c < 3; ++c)
@@ -572,7 +574,7 @@ int coef_convert(xb_ctx* c, double* plain_dev, bool to_blocked)
 template <int C1, int C2>
 static int launch_gather(xb_ctx* c, const GatherArgs& ga, int accumulate)
 {
-  const int blocks = (int)((c->g.ncl + 127) / 128);
+  const int blocks = (int)((c->g.plane * ga.nplanes + 127) / 128);
   XB_LAUNCH(c, (k_gather_rows<C1, C2>), blocks, 128, 0, c->g, ga, c->coef, accumulate);
   return 0;
 }
@@ -580,7 +582,7 @@ static int launch_gather(xb_ctx* c, const GatherArgs& ga, int accumulate)
 // migrate.cu (multi-rank only)
 int ghost_exchange_mark(xb_ctx* c, Species& s);
 int ghost_exchange_begin(xb_ctx* c, Species& s);
-int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage);
+int deposit_ghost_cells(xb_ctx* c, Species& s, int64_t stage_lo, int64_t stage_hi, bool do_lo, bool do_hi);
 
 // cell blocks of `ncells` consecutive cells (bin space) into the staging area
 // zl_first: local plane index of the first cell (the cells of one launch are whole planes: owned planes 0 .. nzl - 1,
@@ -634,6 +636,22 @@ int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* 
   return 0;
 }
 
+static int gather_rows_of(xb_ctx* c, Species& s, const GatherArgs& ga, int acc)
+{
+  XB_CHECK((launch_gather<0, 0>(c, ga, acc)));
+  XB_CHECK((launch_gather<0, 1>(c, ga, acc)));
+  XB_CHECK((launch_gather<0, 2>(c, ga, acc)));
+  XB_CHECK((launch_gather<1, 0>(c, ga, acc)));
+  XB_CHECK((launch_gather<1, 1>(c, ga, acc)));
+  XB_CHECK((launch_gather<1, 2>(c, ga, acc)));
+  XB_CHECK((launch_gather<2, 0>(c, ga, acc)));
+  XB_CHECK((launch_gather<2, 1>(c, ga, acc)));
+  XB_CHECK((launch_gather<2, 2>(c, ga, acc)));
+  const int blocks = (int)((c->g.plane * ga.nplanes + 127) / 128);
+  XB_LAUNCH(c, k_gather_current, blocks, 128, 0, c->g, ga, s.currI, c->currI);
+  return 0;
+}
+
 int deposit_moments(xb_ctx* c)
 {
   const Grid& g = c->g;
@@ -642,42 +660,63 @@ int deposit_moments(xb_ctx* c)
   bool first = true;
   for (auto& s : c->sorts) {
     if (!s.sorted) XB_FAIL("deposit: particles are not sorted");
-    // bin plane 1 = first owned plane; staging plane 0 is the low ghost plane in multi-rank runs
-    if (!single) XB_CHECK(ghost_exchange_mark(c, s));
-    XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_CELLS));
-    // Several slabs: the owned planes go in eight launches instead of one.  The kernel is persistent (one wave of CTAs
-    // that own their SMs until the launch ends); NCCL's kernels of the ghost exchange, which wait on the high-priority
-    // copy stream, get SMs where a wave ends: the count table after the first launch, the payloads after the second.
-    // The dynamic work distribution of the kernel absorbs the SMs NCCL holds meanwhile.
-    const int chunk = single ? g.nzl : (g.nzl + 7) / 8;
-    for (int p0 = 0; p0 < g.nzl; p0 += chunk) {
-      const int np = chunk < g.nzl - p0 ? chunk : g.nzl - p0;
-      XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane * (1 + p0), g.plane * np, single ? g.plane * p0 : g.plane * (1 + p0), 0, &s.rec,
-                             s.capacity, s.count, p0));
-    }
-    XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_CELLS));
-    if (!single) {
-      // the boundary-plane particles of the z neighbours travel (copy stream) while the owned planes are computed
-      XB_CHECK(ghost_exchange_begin(c, s));
-      XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_GHOST));
-      XB_CHECK(deposit_ghost_cells(c, s, c->stage));
-      XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_GHOST));
-    }
-    XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_ROWS));
-    GatherArgs ga{c->stage, single ? 1 : 0};
     const int acc = first ? 0 : 1;
-    XB_CHECK((launch_gather<0, 0>(c, ga, acc)));
-    XB_CHECK((launch_gather<0, 1>(c, ga, acc)));
-    XB_CHECK((launch_gather<0, 2>(c, ga, acc)));
-    XB_CHECK((launch_gather<1, 0>(c, ga, acc)));
-    XB_CHECK((launch_gather<1, 1>(c, ga, acc)));
-    XB_CHECK((launch_gather<1, 2>(c, ga, acc)));
-    XB_CHECK((launch_gather<2, 0>(c, ga, acc)));
-    XB_CHECK((launch_gather<2, 1>(c, ga, acc)));
-    XB_CHECK((launch_gather<2, 2>(c, ga, acc)));
-    const int blocks = (int)((g.ncl + 127) / 128);
-    XB_LAUNCH(c, k_gather_current, blocks, 128, 0, g, ga, s.currI, c->currI);
-    XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_ROWS));
+    if (!single) XB_CHECK(ghost_exchange_mark(c, s));
+    if (c->batch_planes == 0) {
+      // ---- the staging area holds the cell blocks of the whole slab ---------------------------------------------
+      XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_CELLS));
+      // Several slabs: the owned planes go in eight launches instead of one.  The kernel is persistent (one wave of CTAs
+      // that own their SMs until the launch ends); NCCL's kernels of the ghost exchange, which wait on the high-priority
+      // copy stream, get SMs where a wave ends: the count table after the first launch, the payloads after the second.
+      // The dynamic work distribution of the kernel absorbs the SMs NCCL holds meanwhile.
+      const int chunk = single ? g.nzl : (g.nzl + 7) / 8;
+      for (int p0 = 0; p0 < g.nzl; p0 += chunk) {
+        const int np = chunk < g.nzl - p0 ? chunk : g.nzl - p0;
+        XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane * (1 + p0), g.plane * np, single ? g.plane * p0 : g.plane * (1 + p0), 0, &s.rec,
+                               s.capacity, s.count, p0));
+      }
+      XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_CELLS));
+      if (!single) {
+        // the boundary-plane particles of the z neighbours travel (copy stream) while the owned planes are computed
+        XB_CHECK(ghost_exchange_begin(c, s));
+        XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_GHOST));
+        XB_CHECK(deposit_ghost_cells(c, s, 0, (int64_t)(g.nzl + 1) * g.plane, true, true));
+        XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_GHOST));
+      }
+      XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_ROWS));
+      XB_CHECK(gather_rows_of(c, s, GatherArgs{c->stage, single ? 1 : 0, -1, 0, g.nzl}, acc));
+      XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_ROWS));
+    }
+    else {
+      // ---- large slabs: batches of P planes through a staging area of P + 2 planes (xb_create chose P so that it
+      // fits the budget): staging plane 0 = the plane below the batch, 1 .. np = the batch, np + 1 = the plane above.
+      // The two neighbour planes of a batch are computed again with the next / previous batch (2 / P more cell blocks).
+      if (!single) XB_CHECK(ghost_exchange_begin(c, s));
+      for (int p0 = 0; p0 < g.nzl; p0 += c->batch_planes) {
+        const int np = c->batch_planes < g.nzl - p0 ? c->batch_planes : g.nzl - p0;
+        XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_CELLS));
+        XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane * (1 + p0), g.plane * np, g.plane, 0, &s.rec, s.capacity, s.count, p0));
+        const int64_t hi_stage = (int64_t)(np + 1) * g.plane;
+        const bool open_lo = g.open_z && g.z0 + p0 - 1 < 0, open_hi = g.open_z && g.z0 + p0 + np >= g.nz;
+        if (p0 > 0)  // the plane below is a plane of this slab
+          XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane * p0, g.plane, 0, 0, &s.rec, s.capacity, s.count, p0 - 1));
+        else if (single && !open_lo)  // ... or the top plane, through the periodic boundary
+          XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane * g.nzl, g.plane, 0, -g.nz, &s.rec, s.capacity, s.count, -1));
+        if (p0 + np < g.nzl)
+          XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane * (1 + p0 + np), g.plane, hi_stage, 0, &s.rec, s.capacity, s.count, p0 + np));
+        else if (single && !open_hi)
+          XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane, g.plane, hi_stage, +g.nz, &s.rec, s.capacity, s.count, g.nzl));
+        XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_CELLS));
+        if (!single && (p0 == 0 || p0 + np >= g.nzl)) {  // ... or a plane of the neighbour slab
+          XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_GHOST));
+          XB_CHECK(deposit_ghost_cells(c, s, 0, hi_stage, p0 == 0, p0 + np >= g.nzl));
+          XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_GHOST));
+        }
+        XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_ROWS));
+        XB_CHECK(gather_rows_of(c, s, GatherArgs{c->stage, 0, p0 - 1, p0, np}, acc));
+        XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_ROWS));
+      }
+    }
     first = false;
   }
   if (c->sorts.empty()) XB_CUDA(cudaMemsetAsync(c->coef, 0, sizeof(double) * c->coef_elems, c->stream));

@@ -325,19 +325,20 @@ int ghost_exchange_begin(xb_ctx* c, Species& s)
   return 0;
 }
 
-// Moments of the two ghost cell planes (stage planes 0 and nzl + 1) from the copies ghost_exchange_begin fetched.
-int deposit_ghost_cells(xb_ctx* c, Species& s, double* stage)
+// Moments of the ghost cell planes below / above the slab, from the copies ghost_exchange_begin fetched, into the
+// staging cells stage_lo / stage_hi on.
+int deposit_ghost_cells(xb_ctx* c, Species& s, int64_t stage_lo, int64_t stage_hi, bool do_lo, bool do_hi)
 {
-  (void)stage;
   const Grid& g = c->g;
   MigrateBuffers& m = *s.mig;
   XB_CUDA(cudaStreamWaitEvent(c->stream, m.ghosts_here, 0));
   // low ghost plane: the neighbour below; across the periodic boundary its z is nz planes above mine
   const int zs_lo = g.rank == 0 ? -g.nz : 0;
   const int zs_hi = g.rank == g.nranks - 1 ? +g.nz : 0;
-  if (m.nghost[0] >= 0) XB_CHECK(deposit_cells(c, s, m.ghost[0], m.ghost_bins[0], 0, g.plane, 0, zs_lo, &m.ghost_rec[0], m.ghost_cap, m.nghost[0], -1));
-  if (m.nghost[1] >= 0)
-    XB_CHECK(deposit_cells(c, s, m.ghost[1], m.ghost_bins[1], 0, g.plane, (int64_t)(g.nzl + 1) * g.plane, zs_hi, &m.ghost_rec[1], m.ghost_cap, m.nghost[1], g.nzl));
+  if (do_lo && m.nghost[0] >= 0)
+    XB_CHECK(deposit_cells(c, s, m.ghost[0], m.ghost_bins[0], 0, g.plane, stage_lo, zs_lo, &m.ghost_rec[0], m.ghost_cap, m.nghost[0], -1));
+  if (do_hi && m.nghost[1] >= 0)
+    XB_CHECK(deposit_cells(c, s, m.ghost[1], m.ghost_bins[1], 0, g.plane, stage_hi, zs_hi, &m.ghost_rec[1], m.ghost_cap, m.nghost[1], g.nzl));
   return 0;
 }
 
