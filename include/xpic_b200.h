@@ -250,6 +250,19 @@ int xb_distribution_moment_region(xb_ctx* ctx, int32_t sid, int32_t moment, cons
  * (P1 - P0) / dt - QE residual of add_columns (:29-68). */
 int xb_momentum(xb_ctx* ctx, int32_t sid, double out[6]);
 
+/* --- StepPresets commands on the device (src/commands) ---------------------------------------------------------
+ * Geometry of a command: XB_GEOMETRY_BOX with p = { min[3], max[3] } (BoxGeometry, WithinBox, src/utils/geometries.cpp:3-9)
+ * or XB_GEOMETRY_CYLINDER with p = { center[3], radius, height, 0 } (WithinCylinder, :12-19). */
+enum { XB_GEOMETRY_BOX = 0, XB_GEOMETRY_CYLINDER = 1 };
+/* FieldsDamping::execute (src/commands/fields_damping.cpp:16-112): E and B - B0 at the nodes whose cell centre lies
+ * outside the geometry are multiplied by DampForBox / DampForCylinder's factor (:66-112); *damped_energy receives
+ * the energy taken out, 0.5 f^2 (1 - damping^2) summed over all ranks (may be NULL). */
+int xb_fields_damping(xb_ctx* ctx, int32_t geometry, const double p[6], double coefficient, double* damped_energy);
+/* RemoveParticles::execute (src/commands/remove_particles.cpp:11-45): every particle of sort sid whose CELL corner
+ * (x dx, y dy, z dz) lies outside the geometry is removed; out = { removed particles, removed kinetic energy
+ * 0.5 m v^2 n / Np } over all ranks (may be NULL).  Collective in a multi-rank run. */
+int xb_particles_remove(xb_ctx* ctx, int32_t sid, int32_t geometry, const double p[6], double out[2]);
+
 /* Moments only at the present particle positions: fill_ecsim_current (ecsim/simulation.cpp:336-368). */
 int xb_deposit(xb_ctx* ctx);
 /* Solve (L? + M) x = b for host vectors with the given solver slot (KSPSolve). */

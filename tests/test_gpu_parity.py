@@ -780,3 +780,97 @@ def test_batched_staging_equals_whole_slab_staging(X, open_z, monkeypatch):
     whole.close()
     batched.close()
     s0.close()
+
+
+def _within(geometry, p, r):
+    if geometry == "box":
+        return np.all((np.array(p[:3]) <= r) & (r < np.array(p[3:6])), axis=-1)
+    d = r - np.array(p[:3])
+    return (np.abs(d[..., 2]) < 0.5 * p[4]) & (d[..., 0] ** 2 + d[..., 1] ** 2 <= p[3] ** 2)
+
+
+@pytest.mark.parametrize("geometry,params", [("box", (1.0, 1.0, 0.5, 4.0, 3.5, 3.0)), ("cylinder", (2.5, 2.25, 2.0, 1.5, 3.0))])
+def test_fields_damping_matches_the_reference_formulas(X, geometry, params):
+    """FieldsDamping::execute with DampForBox / DampForCylinder (src/commands/fields_damping.cpp:16-112), evaluated with numpy."""
+    n, d, coef = (10, 9, 8), (0.5, 0.5, 0.5), 0.8
+    s = X.Simulation(n, d=d)
+    rng = np.random.default_rng(23)
+    E, B, B0 = (rng.standard_normal(s.nown) for _ in range(3))
+    for name, f in (("E", E), ("B", B), ("B0", B0)):
+        s.set_field(name, f)
+    taken = s.fields_damping(geometry, params, coef)
+    z, y, x = np.meshgrid(np.arange(n[2]), np.arange(n[1]), np.arange(n[0]), indexing="ij")
+    r = np.stack([(x + 0.5) * d[0], (y + 0.5) * d[1], (z + 0.5) * d[2]], axis=-1)
+    L = np.array(n) * np.array(d)
+    if geometry == "box":
+        damp = np.ones(r.shape[:-1])
+        for i in range(3):
+            hi, lo = r[..., i] > params[3 + i], r[..., i] < params[i]
+            t_hi = (r[..., i] - params[3 + i]) / (L[i] - params[3 + i]) - 1.0
+            t_lo = r[..., i] / params[i] - 1.0 if params[i] > 0 else np.zeros_like(damp)
+            damp = damp * np.where(hi, 1.0 - coef * t_hi ** 2, np.where(lo, 1.0 - coef * t_lo ** 2, 1.0))
+    else:
+        rr = np.hypot(r[..., 0] - params[0], r[..., 1] - params[1])
+        width, delta = params[0] - params[3], rr - params[3]
+        delta0 = width * (1.0 + 1.0 / np.sqrt(coef))
+        damp = np.where(rr < params[3], 1.0, np.where(delta < delta0, 1.0 - coef * (delta / width - 1.0) ** 2, 0.0))
+    damp = np.where(_within(geometry, params, r), 1.0, damp)[..., None]
+    Eg, Bg, B0g = (f.reshape(n[2], n[1], n[0], 3) for f in (E, B, B0))
+    ref_taken = np.sum(0.5 * Eg ** 2 * (1 - damp ** 2)) + np.sum(0.5 * (Bg - B0g) ** 2 * (1 - damp ** 2))
+    assert np.any(damp != 1.0)
+    np.testing.assert_allclose(s.get_field("E").reshape(Eg.shape), Eg * damp, rtol=1e-14, atol=1e-15)
+    np.testing.assert_allclose(s.get_field("B").reshape(Eg.shape), (Bg - B0g) * damp + B0g, rtol=1e-14, atol=1e-15)
+    assert abs(taken - ref_taken) < 1e-11 * ref_taken
+    s.close()
+
+
+@pytest.mark.parametrize("geometry,params", [("box", (1.0, 0.5, 1.0, 4.0, 3.5, 3.5)), ("cylinder", (2.5, 2.5, 2.5, 1.6, 3.0))])
+def test_remove_particles_matches_the_reference_rule(X, geometry, params):
+    """RemoveParticles::execute (src/commands/remove_particles.cpp:11-45): cells whose corner lies outside the geometry are emptied."""
+    o, s = make_pair(n=(10, 10, 10), Np=8)
+    pts, ids = o.get_particles(0)
+    corner = np.floor(pts[:, :3] / 0.5) * 0.5
+    keep = _within(geometry, params, corner)
+    removed, energy = s.remove_particles(geometry, params)
+    assert removed == int((~keep).sum()) and 0 < removed < len(ids)
+    ref_energy = np.sum(0.5 * 1.0 * np.sum(pts[~keep, 3:] ** 2, axis=1) * (1.0 / 8))
+    assert abs(energy - ref_energy) < 1e-11 * ref_energy
+    assert s.particle_count() == int(keep.sum())
+    got = np.sort(s.get_particles(0)[1])
+    assert np.array_equal(got, np.sort(ids[keep]))
+    s.step()  # the store is consistent: a step runs on what is left
+    assert s.particle_count() == int(keep.sum())
+    s.close()
+
+
+def test_host_program_open_trap_with_step_presets(X, tmp_path):
+    """An open-trap set-up in the reference's schema: open z boundary, SetMagneticField with coils, particles in a
+    cylinder, and the StepPresets InjectParticles / RemoveParticles / FieldsDamping before every step
+    (src/interfaces/simulation.cpp:82-84).  The host program runs it; B0 is the analytic two-coil field (spot-checked on
+    the axis against the closed form of a current loop), the tables are complete."""
+    import json
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "xpic_b200", "_build", "xpic_b200.out")
+    if not os.path.exists(exe):
+        pytest.skip("host program not built")
+    cfg = json.load(open(os.path.join(ROOT, "configs", "open_trap_ecsim.json")))
+    cfg["OutputDirectory"] = str(tmp_path / "trap")
+    path = tmp_path / "trap.json"
+    path.write_text(json.dumps(cfg))
+    r = subprocess.run([exe, str(path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = tmp_path / "trap"
+    _, e = O.read_table(str(out / "temporal" / "energy.txt"))
+    assert e.shape[0] == 13 and np.all(np.isfinite(e))
+    assert r.stdout.count("Particles have been removed from") == 24 and r.stdout.count("Fields are damped") == 12
+    B0 = np.fromfile(str(out / "B0" / "00"), dtype=np.float32).reshape(24, 12, 12, 3)
+    # B_z of two loops on the axis: I R^2 ... the reference's quadrature of I R (R - r cos) / d^3 at r -> 0 gives 2 pi I R^2 / (z^2 + R^2)^1.5
+    z = np.arange(24) * 0.5
+    on_axis = sum(2 * np.pi * 4.0 * 3.0 ** 2 / ((z - z0) ** 2 + 3.0 ** 2) ** 1.5 for z0 in (-2.0, 14.0))
+    # B_z sits at (x + 1/2, y + 1/2, z): the node next to the axis is a quarter cell diagonal away from it
+    np.testing.assert_allclose(B0[:, 5, 5, 2], on_axis, rtol=2e-2)
+    dens = np.fromfile(str(out / "electrons" / "density" / "12"), dtype=np.float32)
+    assert dens.size == 24 * 12 * 12 and dens.max() > 0

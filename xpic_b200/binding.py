@@ -95,6 +95,8 @@ SYMBOLS = {
     "xb_family_profile_read": (C.c_int, [C.c_void_p, C.c_int32, _i64p, _dp]),
     "xb_field_energy": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "xb_field_sums": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "xb_fields_damping": (C.c_int, [C.c_void_p, C.c_int32, _dp, C.c_double, _dp]),
+    "xb_particles_remove": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp]),
     "xb_scalar": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "xb_particle_moments": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "xb_timing": (C.c_int, [C.c_void_p, C.c_int32, _dp, _i64p]),
@@ -381,6 +383,22 @@ class Simulation:
         out = C.c_double()
         _check(self._L.xb_field_energy(self._h, FIELDS[name], sid, C.byref(out)))
         return out.value
+
+    def fields_damping(self, geometry, params, coefficient):
+        """FieldsDamping::execute; geometry "box" (min[3], max[3]) or "cylinder" (center[3], radius, height); returns the damped energy."""
+        p = np.zeros(6)
+        p[: len(params)] = params
+        out = C.c_double()
+        _check(self._L.xb_fields_damping(self._h, {"box": 0, "cylinder": 1}[geometry], _as_dp(p), float(coefficient), C.byref(out)))
+        return out.value
+
+    def remove_particles(self, geometry, params, sid=0):
+        """RemoveParticles::execute; returns (removed particles, removed kinetic energy) over all ranks."""
+        p = np.zeros(6)
+        p[: len(params)] = params
+        out = np.zeros(2)
+        _check(self._L.xb_particles_remove(self._h, sid, {"box": 0, "cylinder": 1}[geometry], _as_dp(p), _as_dp(out)))
+        return int(out[0]), float(out[1])
 
     def scalar(self, name, sid=0):
         out = C.c_double()

@@ -388,6 +388,7 @@ int xb_destroy(xb_ctx* c)
     cudaFree(v);
   cudaFree(c->cap_counters);
   cudaFree(c->work_counter);
+  cudaFree(c->removed_dev);
   for (auto e : c->nl.events)
     if (e) cudaEventDestroy(e);
   for (double* v : c->V) cudaFree(v);
@@ -913,6 +914,52 @@ int xb_charge_conservation(xb_ctx* c, int32_t which_current, double* norms)
   if (which_current != 0 && which_current != 1) XB_FAIL("xb_charge_conservation: which_current must be 0 (currJe) or 1 (J)");
   if (!norms) XB_FAIL("xb_charge_conservation: null output");
   return charge_conservation(c, which_current, norms);
+}
+
+int xb_fields_damping(xb_ctx* c, int32_t geometry, const double p[6], double coefficient, double* damped_energy)
+{
+  XB_API_BEGIN(c);
+  if ((geometry != XB_GEOMETRY_BOX && geometry != XB_GEOMETRY_CYLINDER) || !p) XB_FAIL("xb_fields_damping: unknown geometry");
+  Geometry ge;
+  ge.kind = geometry;
+  for (int k = 0; k < 6; ++k) ge.p[k] = p[k];
+  return fields_damping(c, ge, coefficient, damped_energy);
+}
+
+int xb_particles_remove(xb_ctx* c, int32_t sid, int32_t geometry, const double p[6], double out[2])
+{
+  XB_API_BEGIN(c);
+  if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
+  if ((geometry != XB_GEOMETRY_BOX && geometry != XB_GEOMETRY_CYLINDER) || !p) XB_FAIL("xb_particles_remove: unknown geometry");
+  // the removal rides on a re-binning without a move: the key pass tests the cell of every particle, the scatter drops the marked ones
+  if (!c->removed_dev) XB_CUDA(cudaMalloc(&c->removed_dev, 2 * sizeof(unsigned long long)));
+  XB_CUDA(cudaMemsetAsync(c->removed_dev, 0, 2 * sizeof(unsigned long long), c->stream));
+  c->remove.kind = geometry;
+  for (int k = 0; k < 6; ++k) c->remove.p[k] = p[k];
+  const int rc = sort_species(c, c->sorts[sid], 0.0);
+  c->remove.kind = -1;
+  if (rc) return rc;
+  unsigned long long h[2];
+  XB_CUDA(cudaMemcpyAsync(h, c->removed_dev, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  XB_CUDA(cudaStreamSynchronize(c->stream));
+  double res[2];
+  res[0] = (double)h[0];
+  memcpy(&res[1], &h[1], sizeof(double));
+  if (c->g.nranks > 1) {
+    c->red_host[0] = res[0];
+    c->red_host[1] = res[1];
+    XB_CUDA(cudaMemcpyAsync(c->red_out, c->red_host, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    XB_CHECK(comm_allreduce_sum(c, c->red_out, 2));
+    XB_CUDA(cudaMemcpyAsync(c->red_host, c->red_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    XB_CUDA(cudaStreamSynchronize(c->stream));
+    res[0] = c->red_host[0];
+    res[1] = c->red_host[1];
+  }
+  if (out) {
+    out[0] = res[0];
+    out[1] = res[1];
+  }
+  return 0;
 }
 
 int xb_deposit(xb_ctx* c)

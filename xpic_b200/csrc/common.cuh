@@ -68,6 +68,20 @@ struct Grid {
   }
 };
 
+// geometry of a StepPresets command (src/utils/geometries.h): kind < 0: none
+struct Geometry {
+  int kind = -1;
+  double p[6] = {0, 0, 0, 0, 0, 0};  // box: min[3], max[3]; cylinder: center[3], radius, height
+};
+
+__host__ __device__ inline bool within_geometry(const Geometry& ge, double x, double y, double z)
+{
+  if (ge.kind == XB_GEOMETRY_BOX)  // WithinBox, src/utils/geometries.cpp:3-9
+    return (ge.p[0] <= x && x < ge.p[3]) && (ge.p[1] <= y && y < ge.p[4]) && (ge.p[2] <= z && z < ge.p[5]);
+  const double dx = x - ge.p[0], dy = y - ge.p[1], dz = z - ge.p[2];  // WithinCylinder, :12-19
+  return (fabs(dz) < 0.5 * ge.p[4]) && ((dx * dx + dy * dy) <= ge.p[3] * ge.p[3]);
+}
+
 struct Solver {
   double rtol = 1e-7, atol = 1e-7;  // src/impls/ecsim/simulation.h:15-16
   int maxit = 100, restart = 30;    // :18, PETSc GMRES default restart
@@ -196,6 +210,8 @@ struct xb_ctx {
   double* pinned = nullptr;
   size_t pinned_bytes = 0;
 
+  xb::Geometry remove;  // RemoveParticles: applied by the next re-binning of the sort it was set for (kind >= 0)
+  unsigned long long* removed_dev = nullptr;  // { particles, kinetic energy as double bits } of that re-binning
   std::vector<xb::Species> sorts;
   xb::Solver solver[2];
   xb::StageClock clock;
@@ -245,6 +261,7 @@ int species_alloc(xb_ctx* c, Species& s, int64_t capacity);
 void species_free(Species& s);
 void migrate_free(Species& s);  // migrate.cu
 int particles_sort(xb_ctx* c, Species& s, double dt_move);   // r += v dt_move, wrap, re-bin
+int fields_damping(xb_ctx* c, const Geometry& ge, double coefficient, double* damped_energy);  // fields.cu
 int push_second(xb_ctx* c, Species& s, const double* Eh, const double* B);
 int push_second_work(xb_ctx* c, Species& s, const double* Eh, const double* B, double* pred_w);
 int kinetic_energy(xb_ctx* c, Species& s, double* sum_v2, double* K);

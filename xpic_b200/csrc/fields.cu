@@ -254,6 +254,86 @@ int final_update(xb_ctx* c, const double* Ehalf)
 }
 
 // ---------------------------------------------------------------------------------------------
+// FieldsDamping (src/commands/fields_damping.cpp:16-112): a node whose cell centre lies outside the geometry has E and
+// B - B0 multiplied by the damping factor of DampForBox (:66-89) / DampForCylinder (:91-112)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double damping_factor(const Grid& g, const Geometry& ge, double coef, const double* r)
+{
+  if (ge.kind == XB_GEOMETRY_BOX) {
+    const double L[3] = {g.Lx, g.Ly, g.Lz};
+    double damping = 1.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double width, delta;
+      if (r[i] > ge.p[3 + i]) {
+        width = L[i] - ge.p[3 + i];
+        delta = r[i] - ge.p[3 + i];
+      }
+      else if (r[i] < ge.p[i]) {
+        width = ge.p[i] - 0;
+        delta = r[i] - 0;
+      }
+      else
+        continue;
+      const double t = delta / width - 1.0;
+      damping *= 1.0 - coef * (t * t);
+    }
+    return damping;
+  }
+  const double rr = hypot(r[0] - ge.p[0], r[1] - ge.p[1]);
+  if (rr < ge.p[3]) return 1.0;
+  const double width = ge.p[0] - ge.p[3], delta = rr - ge.p[3];
+  const double delta0 = width * (1.0 + 1.0 / sqrt(coef));
+  if (!(delta < delta0)) return 0.0;  // avoids negative factors (:104-109)
+  const double t = delta / width - 1.0;
+  return 1.0 - coef * (t * t);
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_fields_damping(Grid g, Geometry ge, double coef, double* __restrict__ E, double* __restrict__ B,
+                                                               const double* __restrict__ B0, double* __restrict__ partial)
+{
+  double taken = 0.0;
+  XB_NODE_LOOP(g, node, x, y, zl)
+  {
+    const double r[3] = {(x + 0.5) * g.dx, (y + 0.5) * g.dy, (g.z0 + zl + 0.5) * g.dz};
+    if (within_geometry(ge, r[0], r[1], r[2])) continue;
+    const double d = damping_factor(g, ge, coef, r);
+    const int64_t o = g.vidx(x, y, zl, 0);
+    double e2 = 0.0, b2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double e = E[o + c], b = B[o + c] - B0[o + c];
+      e2 += e * e;
+      b2 += b * b;
+      E[o + c] = e * d;
+      B[o + c] = b * d + B0[o + c];
+    }
+    taken += (0.5 * e2) * (1.0 - d * d) + (0.5 * b2) * (1.0 - d * d);  // Energy::get_field(f) * (1 - damping^2)
+  }
+  __shared__ double sh[RED_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  taken = warp_sum(taken);
+  if (lane == 0) sh[wid] = taken;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < RED_THREADS / 32; ++q) t += sh[q];
+    partial[(int64_t)blockIdx.x * RED_MAXV] = t;
+  }
+}
+
+int reduce_finish(xb_ctx* c, int nv, double* host_out);
+
+int fields_damping(xb_ctx* c, const Geometry& ge, double coefficient, double* damped_energy)
+{
+  XB_LAUNCH(c, k_fields_damping, RED_BLOCKS, RED_THREADS, 0, c->g, ge, coefficient, c->E, c->B, c->B0, c->red_partial);
+  double e = 0.0;
+  XB_CHECK(reduce_finish(c, 1, &e));
+  if (damped_energy) *damped_energy = e;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Reductions: fixed grid, fixed tree => bit-reproducible run to run.
 // ---------------------------------------------------------------------------------------------
 struct VecPtrs {

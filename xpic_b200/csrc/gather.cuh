@@ -245,6 +245,21 @@ __device__ __forceinline__ void clamped_cell_and_octant(double xn, int n, int& i
   o = min(max((int)floor(xn - 0.5) - i + 1, 0), 1);
 }
 
+// RemoveParticles::execute (src/commands/remove_particles.cpp:22-39): the particle goes when the corner of its cell lies
+// outside the geometry; tallies { particles, kinetic energy 0.5 m v^2 n / Np } (Energy::get_kinetic)
+__device__ __forceinline__ bool removed_by_command(const Grid& g, const Geometry& rm, double px, double py, double pz, double vx, double vy, double vz,
+                                                   double m_mpw, unsigned long long* __restrict__ tally)
+{
+  if (rm.kind < 0) return false;
+  const int ix = min(max((int)floor(to_cells(px, g.dx, g.inv_dx, g.exact_inv & 1)), 0), g.nx - 1);
+  const int iy = min(max((int)floor(to_cells(py, g.dy, g.inv_dy, g.exact_inv & 2)), 0), g.ny - 1);
+  const int iz = min(max((int)floor(to_cells(pz, g.dz, g.inv_dz, g.exact_inv & 4)), 0), g.nz - 1);
+  if (within_geometry(rm, ix * g.dx, iy * g.dy, iz * g.dz)) return false;
+  atomicAdd(&tally[0], 1ull);
+  atomicAdd(reinterpret_cast<double*>(&tally[1]), 0.5 * (m_mpw * ((vx * vx + vy * vy) + vz * vz)));
+  return true;
+}
+
 __device__ __forceinline__ int32_t particle_key(const Grid& g, double px, double py, double pz, int pl)
 {
   int ix, iy, iz, ox, oy, oz;

@@ -98,15 +98,15 @@ struct SendPtrs {
 __global__ void k_move_key_slab(Grid g, int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                                 const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
                                 const uint64_t* __restrict__ id, double dtm, int32_t* __restrict__ key, int32_t* __restrict__ hist, SendPtrs sp,
-                                unsigned long long* __restrict__ send_count, int64_t cap)
+                                unsigned long long* __restrict__ send_count, int64_t cap, Geometry rm, double m_mpw, unsigned long long* __restrict__ tally)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double px = moved_coord(x[i], dtm != 0.0 ? vx[i] : 0.0, dtm, g.Lx);
   const double py = moved_coord(y[i], dtm != 0.0 ? vy[i] : 0.0, dtm, g.Ly);
   const double pz = moved_z(g, z[i], dtm != 0.0 ? vz[i] : 0.0, dtm);
-  if (left_the_box(g, pz)) {
-    key[i] = -1;  // gone through an open boundary: neither kept nor sent
+  if (left_the_box(g, pz) || removed_by_command(g, rm, px, py, pz, vx[i], vy[i], vz[i], m_mpw, tally)) {
+    key[i] = -1;  // gone through an open boundary or taken out by RemoveParticles: neither kept nor sent
     return;
   }
   const int pl = slab_plane(g, pz);
@@ -200,7 +200,7 @@ int migrate_and_sort(xb_ctx* c, Species& s, double dt_move)
   if (n > 0) {
     const int blocks = (int)((n + 255) / 256);
     XB_LAUNCH(c, k_move_key_slab, blocks, 256, 0, g, n, p[0], p[1], p[2], p[3], p[4], p[5], s.id[s.cur], dt_move, s.key, c->hist, sp, m.counts_dev,
-              m.cap);
+              m.cap, c->remove, s.m * (s.n / (double)s.Np), c->removed_dev);
   }
   XB_CHECK(prof_end(c, XB_FAMILY_SORT_KEYS));
   XB_CHECK(prof_begin(c, XB_FAMILY_SORT_MIGRATE));
@@ -243,7 +243,7 @@ int migrate_and_sort(xb_ctx* c, Species& s, double dt_move)
   XB_CHECK(sort_scan_and_scatter(c, s, n, &m, from_down, from_up, dt_move));  // the scatter recomputes the moved position of the particles that stay
   XB_CHECK(prof_end(c, XB_FAMILY_SORT_SCATTER));
   s.count = n - to_down - to_up + from_down + from_up;
-  if (g.open_z) XB_CHECK(count_after_open_sort(c, s));  // minus the particles that left the box
+  if (g.open_z || c->remove.kind >= 0) XB_CHECK(count_after_open_sort(c, s));  // minus the particles that left the box / were removed
   s.sorted = true;
   return 0;
 }

@@ -64,14 +64,14 @@ void species_free(Species& s)
 // same moved_coord() while it copies the particle (saves 24 B / particle of HBM writes)
 __global__ void k_move_key(Grid g, int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                            const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz, double dtm,
-                           int32_t* __restrict__ key, int32_t* __restrict__ hist)
+                           int32_t* __restrict__ key, int32_t* __restrict__ hist, Geometry rm, double m_mpw, unsigned long long* __restrict__ tally)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double px = moved_coord(x[i], dtm != 0.0 ? vx[i] : 0.0, dtm, g.Lx);
   const double py = moved_coord(y[i], dtm != 0.0 ? vy[i] : 0.0, dtm, g.Ly);
   const double pz = moved_z(g, z[i], dtm != 0.0 ? vz[i] : 0.0, dtm);
-  if (left_the_box(g, pz)) {
+  if (left_the_box(g, pz) || removed_by_command(g, rm, px, py, pz, vx[i], vy[i], vz[i], m_mpw, tally)) {
     key[i] = -1;  // not scattered: the particle is gone
     return;
   }
@@ -322,12 +322,14 @@ int particles_sort(xb_ctx* c, Species& s, double dt_move)
   XB_CUDA(cudaMemsetAsync(c->hist, 0, sizeof(int32_t) * c->nbins, c->stream));
   double** p = s.p[s.cur];
   XB_CHECK(prof_begin(c, XB_FAMILY_SORT_KEYS));
-  if (n > 0) XB_LAUNCH(c, k_move_key, grid_for(n), 256, 0, g, n, p[0], p[1], p[2], p[3], p[4], p[5], dt_move, s.key, c->hist);
+  if (n > 0)
+    XB_LAUNCH(c, k_move_key, grid_for(n), 256, 0, g, n, p[0], p[1], p[2], p[3], p[4], p[5], dt_move, s.key, c->hist, c->remove, s.m * (s.n / (double)s.Np),
+              c->removed_dev);
   XB_CHECK(prof_end(c, XB_FAMILY_SORT_KEYS));
   XB_CHECK(prof_begin(c, XB_FAMILY_SORT_SCATTER));
   XB_CHECK(sort_scan_and_scatter(c, s, n, nullptr, 0, 0, dt_move));
   XB_CHECK(prof_end(c, XB_FAMILY_SORT_SCATTER));
-  if (g.open_z) XB_CHECK(count_after_open_sort(c, s));
+  if (g.open_z || c->remove.kind >= 0) XB_CHECK(count_after_open_sort(c, s));
   s.sorted = true;
   return 0;
 }

@@ -188,9 +188,11 @@ int Simulation::configure(const std::string& config_path)
   geom.geom_nz = round_step(geom.geom_z, geom.dz);
   geom.geom_nt = round_step(geom.geom_t, geom.dt);
   geom.diagnose_period = std::max(1, round_step(parse_value(ge.at("diagnose_period"), geom), geom.dt));
-  for (const char* key : {"da_boundary_x", "da_boundary_y", "da_boundary_z"})
+  for (const char* key : {"da_boundary_x", "da_boundary_y"})
     if (ge.contains(key) && ge.at(key).get<std::string>() != "DM_BOUNDARY_PERIODIC")
-      throw std::runtime_error(std::string(key) + ": only DM_BOUNDARY_PERIODIC is covered by this build");
+      throw std::runtime_error(std::string(key) + ": only DM_BOUNDARY_PERIODIC is covered by this build (z may be DM_BOUNDARY_NONE / GHOSTED)");
+  // utils/configuration.cpp:96-104: anything but PERIODIC / GHOSTED means NONE; both have no nodes outside the box
+  open_z_ = ge.contains("da_boundary_z") && ge.at("da_boundary_z").get<std::string>() != "DM_BOUNDARY_PERIODIC";
 
   if (cfg.contains("Particles"))  // src/interfaces/simulation.tpp:12-45
     for (const json& info : cfg.at("Particles")) {
@@ -255,51 +257,126 @@ int Simulation::configure(const std::string& config_path)
       else
         std::cout << "  diagnostic " << name << " is not covered by this build, skipped\n";
     }
-  if (cfg.contains("Presets"))  // commands/builders/command_builder.cpp:42-59, particles_builder.cpp:9-70
-    for (const json& info : cfg.at("Presets")) {
-      const std::string command = info.at("command").get<std::string>();
-      if (command != "SetParticles") throw std::runtime_error("Preset " + command + " is not covered by this build");
-      Preset pr;
-      info.at("particles").get_to(pr.particles);
-      const json& co = info.at("coordinate");
-      pr.coordinate = co.at("name").get<std::string>();
-      pr.box_min = {0.0, 0.0, 0.0};
-      pr.box_max = {geom.geom_x, geom.geom_y, geom.geom_z};
-      if (pr.coordinate == "CoordinateInBox") {
-        if (co.contains("min")) pr.box_min = parse_vector(co, "min", geom);
-        if (co.contains("max")) pr.box_max = parse_vector(co, "max", geom);
-      }
-      else if (pr.coordinate == "CoordinateInCylinder") {  // builder.cpp:96-111
-        pr.center = {0.5 * geom.geom_x, 0.5 * geom.geom_y, 0.5 * geom.geom_z};
-        pr.radius = 0.5 * std::min(geom.geom_x, geom.geom_y);
-        pr.height = geom.geom_z;
-        if (co.contains("center")) pr.center = parse_vector(co, "center", geom);
-        if (co.contains("radius")) co.at("radius").get_to(pr.radius);
-        if (co.contains("height")) co.at("height").get_to(pr.height);
-      }
-      else if (pr.coordinate == "PreciseCoordinate")
-        pr.center = parse_vector(co, "value", geom);
-      else
-        throw std::runtime_error("Unknown coordinate generator name " + pr.coordinate);
-      const json& mo = info.at("momentum");
-      pr.momentum = mo.at("name").get<std::string>();
-      if (pr.momentum == "MaxwellianMomentum") {
-        if (mo.contains("tov")) mo.at("tov").get_to(pr.tov);
-      }
-      else if (pr.momentum == "PreciseMomentum")
-        pr.value = parse_vector(mo, "value", geom);
-      else if (pr.momentum == "MaxwellCosinePerturbation") {
-        pr.mbox_min = {0.0, 0.0, 0.0};
-        pr.mbox_max = {geom.geom_x, geom.geom_y, geom.geom_z};
-        if (mo.contains("min")) pr.mbox_min = parse_vector(mo, "min", geom);
-        if (mo.contains("max")) pr.mbox_max = parse_vector(mo, "max", geom);
-        pr.amplitude = parse_vector(mo, "amplitude", geom);
-        pr.wave_number = parse_vector(mo, "wave_number", geom);
-      }
-      else
-        throw std::runtime_error("Unknown coordinate generator name " + pr.momentum);  // the reference's message, particles_builder.cpp:67
-      presets_.push_back(pr);
+  // ParticlesBuilder::load_coordinate / load_momentum (commands/builders/particles_builder.cpp:9-70)
+  auto load_coordinate = [&](const json& co, Preset& pr) {
+    pr.coordinate = co.at("name").get<std::string>();
+    pr.box_min = {0.0, 0.0, 0.0};
+    pr.box_max = {geom.geom_x, geom.geom_y, geom.geom_z};
+    if (pr.coordinate == "CoordinateInBox") {
+      if (co.contains("min")) pr.box_min = parse_vector(co, "min", geom);
+      if (co.contains("max")) pr.box_max = parse_vector(co, "max", geom);
     }
+    else if (pr.coordinate == "CoordinateInCylinder") {  // builder.cpp:96-111
+      pr.center = {0.5 * geom.geom_x, 0.5 * geom.geom_y, 0.5 * geom.geom_z};
+      pr.radius = 0.5 * std::min(geom.geom_x, geom.geom_y);
+      pr.height = geom.geom_z;
+      if (co.contains("center")) pr.center = parse_vector(co, "center", geom);
+      if (co.contains("radius")) co.at("radius").get_to(pr.radius);
+      if (co.contains("height")) co.at("height").get_to(pr.height);
+    }
+    else if (pr.coordinate == "PreciseCoordinate")
+      pr.center = parse_vector(co, "value", geom);
+    else
+      throw std::runtime_error("Unknown coordinate generator name " + pr.coordinate);
+  };
+  auto load_momentum = [&](const json& mo, Momentum& m) {
+    m.name = mo.at("name").get<std::string>();
+    if (m.name == "MaxwellianMomentum") {
+      if (mo.contains("tov")) mo.at("tov").get_to(m.tov);
+    }
+    else if (m.name == "PreciseMomentum")
+      m.value = parse_vector(mo, "value", geom);
+    else if (m.name == "MaxwellCosinePerturbation") {
+      m.box_min = {0.0, 0.0, 0.0};
+      m.box_max = {geom.geom_x, geom.geom_y, geom.geom_z};
+      if (mo.contains("min")) m.box_min = parse_vector(mo, "min", geom);
+      if (mo.contains("max")) m.box_max = parse_vector(mo, "max", geom);
+      m.amplitude = parse_vector(mo, "amplitude", geom);
+      m.wave_number = parse_vector(mo, "wave_number", geom);
+    }
+    else
+      throw std::runtime_error("Unknown coordinate generator name " + m.name);  // the reference's message, particles_builder.cpp:67
+  };
+  // Builder::load_geometry (interfaces/builder.cpp:83-111) into the C ABI's six numbers
+  auto load_geometry = [&](const json& ge, Command& cmd) {
+    const std::string name = ge.at("name").get<std::string>();
+    if (name == "BoxGeometry") {
+      std::array<double, 3> lo = {0.0, 0.0, 0.0}, hi = {geom.geom_x, geom.geom_y, geom.geom_z};
+      if (ge.contains("min")) lo = parse_vector(ge, "min", geom);
+      if (ge.contains("max")) hi = parse_vector(ge, "max", geom);
+      cmd.geometry = XB_GEOMETRY_BOX;
+      cmd.p = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+    }
+    else if (name == "CylinderGeometry") {
+      std::array<double, 3> center = {0.5 * geom.geom_x, 0.5 * geom.geom_y, 0.5 * geom.geom_z};
+      double radius = 0.5 * std::min(geom.geom_x, geom.geom_y), height = geom.geom_z;
+      if (ge.contains("center")) center = parse_vector(ge, "center", geom);
+      if (ge.contains("radius")) ge.at("radius").get_to(radius);
+      if (ge.contains("height")) ge.at("height").get_to(height);
+      cmd.geometry = XB_GEOMETRY_CYLINDER;
+      cmd.p = {center[0], center[1], center[2], radius, height, 0.0};
+    }
+    else
+      throw std::runtime_error("Unknown geometry name " + name);
+  };
+  // commands/builders/command_builder.cpp:42-59: "Presets" run once before the first step, "StepPresets" before every step
+  for (const char* list : {"Presets", "StepPresets"}) {
+    if (!cfg.contains(list)) continue;
+    const bool every_step = std::string(list) == "StepPresets";
+    for (const json& info : cfg.at(list)) {
+      const std::string command = info.at("command").get<std::string>();
+      Command cmd;
+      cmd.name = command;
+      if (command == "SetParticles") {
+        info.at("particles").get_to(cmd.preset.particles);
+        load_coordinate(info.at("coordinate"), cmd.preset);
+        load_momentum(info.at("momentum"), cmd.preset.momentum);
+      }
+      else if (command == "InjectParticles") {  // commands/builders/inject_particles_builder.cpp:9-68
+        info.at("ionized").get_to(cmd.preset.particles);
+        info.at("ejected").get_to(cmd.ejected);
+        if (info.contains("injection_start")) cmd.injection_start = round_step(info.at("injection_start").get<double>(), geom.dt);
+        if (info.contains("injection_end")) {
+          const json& v = info.at("injection_end");
+          if (v.is_string()) {
+            if (v.get<std::string>() == "geom_t") cmd.injection_end = geom.geom_nt;
+          }
+          else
+            cmd.injection_end = round_step(v.get<double>(), geom.dt);
+        }
+        load_coordinate(info.at("coordinate"), cmd.preset);
+        load_momentum(info.at("momentum_i"), cmd.preset.momentum);
+        load_momentum(info.at("momentum_e"), cmd.momentum_e);
+        if (info.contains("tau")) cmd.tau = round_step(info.at("tau").get<double>(), geom.dt);
+        if (info.contains("per_step_particles_num")) cmd.per_step = info.at("per_step_particles_num").get<int64_t>();
+      }
+      else if (command == "RemoveParticles") {  // commands/builders/remove_particles_builder.cpp
+        info.at("particles").get_to(cmd.preset.particles);
+        load_geometry(info.at("geometry"), cmd);
+      }
+      else if (command == "FieldsDamping") {  // commands/builders/fields_damping_builder.cpp
+        for (const char* key : {"E", "B", "B0"})
+          if (info.at(key).get<std::string>() != key) throw std::runtime_error("FieldsDamping: the vectors must be E, B, B0");
+        info.at("damping_coefficient").get_to(cmd.coefficient);
+        load_geometry(info.at("geometry"), cmd);
+      }
+      else if (command == "SetMagneticField") {  // commands/builders/set_magnetic_field_builder.cpp
+        info.at("field").get_to(cmd.field);
+        if (info.contains("field_axpy")) info.at("field_axpy").get_to(cmd.field_axpy);
+        const json& setter = info.at("setter");
+        cmd.setter = setter.at("name").get<std::string>();
+        if (cmd.setter == "SetUniformField")
+          cmd.value = parse_vector(setter, "value", geom);
+        else if (cmd.setter == "SetCoilsField")
+          for (const json& coil : setter.at("coils")) cmd.coils.push_back({coil.at("z0").get<double>(), coil.at("R").get<double>(), coil.at("I").get<double>()});
+        else
+          throw std::runtime_error("Unknown setter name " + cmd.setter);
+      }
+      else
+        throw std::runtime_error("Preset " + command + " is not covered by this build");
+      (every_step ? step_presets_ : presets_).push_back(cmd);
+    }
+  }
   if (cfg.contains("mpi")) {  // utils/configuration.cpp:111-130: only the z split exists in a slab layout
     const json& mpi = cfg.at("mpi");
     for (const char* key : {"da_processors_x", "da_processors_y"})
@@ -389,6 +466,7 @@ int Simulation::initialize()
   g.rank = rank_;
   g.nranks = nranks_;
   g.track_ids = 0;
+  g.boundary[2] = open_z_ ? XB_BOUNDARY_OPEN : XB_BOUNDARY_PERIODIC;
   {  // the library's split (DMDA's: the first nz % N slabs are one plane thicker)
     const int base = geom.geom_nz / nranks_, rem = geom.geom_nz % nranks_;
     nzl_ = base + (rank_ < rem ? 1 : 0);
@@ -435,61 +513,9 @@ int Simulation::initialize()
     if (load_backup(load_from_)) return 1;
     start = load_from_;
   }
-  auto r01 = [&]() { return uni_(gen_); };
-  for (const auto& pr : presets_) {
-    if (restart) break;
-    Particles& sort = get_named_particles(pr.particles);
-    const SortParameters& sp = sort.parameters;
-    const double frac = sp.Np / (geom.dx * geom.dy * geom.dz);
-    // number_of_particles of ParticlesBuilder::load_coordinate (particles_builder.cpp:16-37), truncated like its PetscInt
-    int64_t count = 0;
-    if (pr.coordinate == "CoordinateInBox")
-      count = (int64_t)(((pr.box_max[0] - pr.box_min[0]) * (pr.box_max[1] - pr.box_min[1]) * (pr.box_max[2] - pr.box_min[2])) * frac);
-    else if (pr.coordinate == "CoordinateInCylinder")
-      count = (int64_t)(M_PI * (pr.radius * pr.radius) * pr.height * frac);
-    else
-      count = sp.Np;
-    auto tm = [&](double T) { return std::sqrt(-2.0 * (T * sp.m / mec2) * std::log(r01())); };
-    const double T[3] = {sp.Tx, sp.Ty, sp.Tz}, p0[3] = {sp.px, sp.py, sp.pz};
-    for (int64_t i = 0; i < count; ++i) {
-      Point pt;
-      // src/utils/particles_load.cpp:6-32: every rank draws the whole stream and keeps its own particles
-      if (pr.coordinate == "CoordinateInBox") {
-        for (int c = 0; c < 3; ++c) pt.r[c] = pr.box_min[c] + r01() * (pr.box_max[c] - pr.box_min[c]);
-      }
-      else if (pr.coordinate == "CoordinateInCylinder") {
-        const double r = pr.radius * std::sqrt(r01());
-        const double phi = 2.0 * M_PI * r01();
-        pt.r[0] = pr.center[0] + r * std::cos(phi);
-        pt.r[1] = pr.center[1] + r * std::sin(phi);
-        pt.r[2] = pr.center[2] + pr.height * (r01() - 0.5);
-      }
-      else {
-        for (int c = 0; c < 3; ++c) pt.r[c] = pr.center[c];
-      }
-      if (pr.momentum == "PreciseMomentum") {
-        for (int c = 0; c < 3; ++c) pt.p[c] = pr.value[c];
-      }
-      else {
-        const bool cosine = pr.momentum == "MaxwellCosinePerturbation";  // particles_load.cpp:78-104
-        for (int c = 0; c < 3; ++c) {
-          const double sn = std::sin(2.0 * M_PI * r01());  // the sine factor is drawn first
-          pt.p[c] = (cosine ? 0.0 : p0[c]) + sn * tm(T[c]);
-        }
-        if (pr.tov || cosine) {
-          const double den = std::sqrt(sp.m * sp.m + (pt.p[0] * pt.p[0] + pt.p[1] * pt.p[1] + pt.p[2] * pt.p[2]));
-          for (double& v : pt.p) v /= den;
-        }
-        if (cosine)
-          for (int c = 0; c < 3; ++c) {
-            const double v0 = pr.amplitude[c] * std::sqrt(T[c] / (sp.m * mec2));
-            pt.p[c] += v0 * std::cos(2.0 * M_PI * pr.wave_number[c] * pt.r[c] / (pr.mbox_max[c] - pr.mbox_min[c]));
-          }
-      }
-      sort.add_particle(pt);
-    }
-    if (sort.flush()) return 1;
-  }
+  if (!restart)
+    for (const Command& cmd : presets_)
+      if (execute_command(cmd, start)) return 1;
 
   // after a restart the tables of the backup continue (rows up to `start` are already there)
   energy_ = std::make_unique<Table>(rank_ == 0 ? out_dir + "/temporal/energy.txt" : std::string(), restart);
@@ -524,6 +550,179 @@ int Simulation::initialize()
   if (diagnose_energy(start)) return 1;
   if (backup_period_ > 0 && save_backup(start)) return 1;
   return 0;
+}
+
+// ---- commands (src/commands) ------------------------------------------------------------------------------
+// Coordinates and momenta come from the reference's default-seeded mt19937 stream in its draw order
+// (src/utils/particles_load.cpp); every rank draws the whole stream and keeps its own particles.
+void Simulation::draw_coordinate(const Preset& pr, Point& pt)
+{
+  auto r01 = [&]() { return uni_(gen_); };
+  if (pr.coordinate == "CoordinateInBox") {
+    for (int c = 0; c < 3; ++c) pt.r[c] = pr.box_min[c] + r01() * (pr.box_max[c] - pr.box_min[c]);
+  }
+  else if (pr.coordinate == "CoordinateInCylinder") {
+    const double r = pr.radius * std::sqrt(r01());
+    const double phi = 2.0 * M_PI * r01();
+    pt.r[0] = pr.center[0] + r * std::cos(phi);
+    pt.r[1] = pr.center[1] + r * std::sin(phi);
+    pt.r[2] = pr.center[2] + pr.height * (r01() - 0.5);
+  }
+  else {
+    for (int c = 0; c < 3; ++c) pt.r[c] = pr.center[c];
+  }
+}
+
+void Simulation::draw_momentum(const Momentum& m, const SortParameters& sp, Point& pt)
+{
+  auto r01 = [&]() { return uni_(gen_); };
+  if (m.name == "PreciseMomentum") {
+    for (int c = 0; c < 3; ++c) pt.p[c] = m.value[c];
+    return;
+  }
+  auto tm = [&](double T) { return std::sqrt(-2.0 * (T * sp.m / mec2) * std::log(r01())); };
+  const double T[3] = {sp.Tx, sp.Ty, sp.Tz}, p0[3] = {sp.px, sp.py, sp.pz};
+  const bool cosine = m.name == "MaxwellCosinePerturbation";  // particles_load.cpp:78-104
+  for (int c = 0; c < 3; ++c) {
+    const double sn = std::sin(2.0 * M_PI * r01());  // the sine factor is drawn first
+    pt.p[c] = (cosine ? 0.0 : p0[c]) + sn * tm(T[c]);
+  }
+  if (m.tov || cosine) {
+    const double den = std::sqrt(sp.m * sp.m + (pt.p[0] * pt.p[0] + pt.p[1] * pt.p[1] + pt.p[2] * pt.p[2]));
+    for (double& v : pt.p) v /= den;
+  }
+  if (cosine)
+    for (int c = 0; c < 3; ++c) {
+      const double v0 = m.amplitude[c] * std::sqrt(T[c] / (sp.m * mec2));
+      pt.p[c] += v0 * std::cos(2.0 * M_PI * m.wave_number[c] * pt.r[c] / (m.box_max[c] - m.box_min[c]));
+    }
+}
+
+// number_of_particles of ParticlesBuilder::load_coordinate (particles_builder.cpp:16-37), truncated like its PetscInt
+int64_t Simulation::preset_count(const Preset& pr, const SortParameters& sp) const
+{
+  const double frac = sp.Np / (geom.dx * geom.dy * geom.dz);
+  if (pr.coordinate == "CoordinateInBox")
+    return (int64_t)(((pr.box_max[0] - pr.box_min[0]) * (pr.box_max[1] - pr.box_min[1]) * (pr.box_max[2] - pr.box_min[2])) * frac);
+  if (pr.coordinate == "CoordinateInCylinder") return (int64_t)(M_PI * (pr.radius * pr.radius) * pr.height * frac);
+  return sp.Np;
+}
+
+int Simulation::execute_command(const Command& cmd, int t)
+{
+  if (cmd.name == "SetParticles") {  // SetParticles::execute (src/commands/set_particles.cpp:19-43)
+    Particles& sort = get_named_particles(cmd.preset.particles);
+    const int64_t count = preset_count(cmd.preset, sort.parameters);
+    for (int64_t i = 0; i < count; ++i) {
+      Point pt;
+      draw_coordinate(cmd.preset, pt);
+      draw_momentum(cmd.preset.momentum, sort.parameters, pt);
+      sort.add_particle(pt);
+    }
+    return sort.flush();
+  }
+  if (cmd.name == "InjectParticles") {  // InjectParticles::execute (src/commands/inject_particles.cpp:27-67)
+    if (t < cmd.injection_start || t > cmd.injection_end) return 0;
+    Particles& ionized = get_named_particles(cmd.preset.particles);
+    Particles& ejected = get_named_particles(cmd.ejected);
+    int64_t per_step = cmd.per_step;
+    if (per_step < 0) {
+      const int tau = cmd.tau > 0 ? cmd.tau : cmd.injection_end - cmd.injection_start;
+      per_step = preset_count(cmd.preset, ionized.parameters) / std::max(tau, 1);
+    }
+    for (int64_t i = 0; i < per_step; ++i) {
+      Point pi, pe;
+      draw_coordinate(cmd.preset, pi);
+      for (int c = 0; c < 3; ++c) pe.r[c] = pi.r[c];
+      draw_momentum(cmd.preset.momentum, ionized.parameters, pi);
+      draw_momentum(cmd.momentum_e, ejected.parameters, pe);
+      ionized.add_particle(pi);
+      ejected.add_particle(pe);
+    }
+    if (ionized.flush()) return 1;
+    return ejected.flush();
+  }
+  if (cmd.name == "RemoveParticles") {  // RemoveParticles::execute (src/commands/remove_particles.cpp:11-45) on the device
+    int32_t sid = -1;
+    for (size_t i = 0; i < particles_.size(); ++i)
+      if (particles_[i]->parameters.sort_name == cmd.preset.particles) sid = (int32_t)i;
+    if (sid < 0) throw std::runtime_error("No particles with name " + cmd.preset.particles);
+    double out[2] = {0.0, 0.0};
+    B200_CALL(xb_particles_remove(ctx, sid, cmd.geometry, cmd.p.data(), out));
+    std::cout << std::format("  Particles have been removed from \"{}\": {} particles, energy: {:6.4e}", cmd.preset.particles, (int64_t)out[0], out[1]) << "\n";
+    return 0;
+  }
+  if (cmd.name == "FieldsDamping") {  // FieldsDamping::execute (src/commands/fields_damping.cpp:16-31) on the device
+    double taken = 0.0;
+    B200_CALL(xb_fields_damping(ctx, cmd.geometry, cmd.p.data(), cmd.coefficient, &taken));
+    std::cout << std::format("  Fields are damped, additional energy runoff: {:6.4e}", taken) << "\n";
+    return 0;
+  }
+  if (cmd.name == "SetMagneticField") {  // SetMagneticField::execute (src/commands/set_magnetic_field.cpp:12-19)
+    const size_t nloc = (size_t)3 * geom.geom_nx * geom.geom_ny * nzl_;
+    std::vector<double> f;
+    if (get_named_vector(cmd.field, f)) return 1;
+    if (cmd.setter == "SetUniformField") {  // VecStrideSet: the value replaces what was there (:27-35)
+      for (size_t i = 0; i < nloc; ++i) f[i] = cmd.value[i % 3];
+    }
+    else {  // SetCoilsField::operator() (:47-91): a sum of current loops on the axis of the box, N = 2000 point quadrature
+      constexpr int N = 2000;
+      constexpr double hp = 2 * M_PI / N, tol = 1e-10;
+      std::vector<double> cosv(N);
+      for (int i = 0; i < N; ++i) cosv[i] = std::cos(i * hp);
+      auto integ = [&](double z, double r, double R, bool radial) {
+        double integral = 0.0;
+        for (int i = 0; i < N; ++i) {
+          double den = z * z + R * R + r * r - 2.0 * R * r * cosv[i];
+          if (std::abs(den) < tol) den = tol;
+          integral += (radial ? cosv[i] : (R - r * cosv[i])) / (den * std::sqrt(den));
+        }
+        return hp * integral;
+      };
+      auto Br = [&](double z, double r) {
+        double v = 0.0;
+        for (auto& co : cmd.coils) v += co[2] * co[1] * (z - co[0]) * integ(z - co[0], r, co[1], true);
+        return v;
+      };
+      auto Bz = [&](double z, double r) {
+        double v = 0.0;
+        for (auto& co : cmd.coils) v += co[2] * co[1] * integ(z - co[0], r, co[1], false);
+        return v;
+      };
+      const double cx = 0.5 * geom.geom_x, cy = 0.5 * geom.geom_y;
+      for (int zl = 0; zl < nzl_; ++zl)
+        for (int y = 0; y < geom.geom_ny; ++y)
+          for (int x = 0; x < geom.geom_nx; ++x) {
+            const int z = z0_ + zl;
+            double* a = &f[(((size_t)zl * geom.geom_ny + y) * geom.geom_nx + x) * 3];
+            double sx = x * geom.dx - cx, sy = (y + 0.5) * geom.dy - cy, sz = (z + 0.5) * geom.dz, r = std::hypot(sx, sy);
+            a[0] += Br(sz, r) * sx / r;
+            sy = y * geom.dy - cy;
+            sx = (x + 0.5) * geom.dx - cx;
+            r = std::hypot(sx, sy);
+            a[1] += Br(sz, r) * sy / r;
+            sz = z * geom.dz;
+            sy = (y + 0.5) * geom.dy - cy;
+            r = std::hypot(sx, sy);
+            a[2] += Bz(sz, r);
+          }
+    }
+    static const std::vector<std::pair<std::string, int>> names = {{"E", XB_E}, {"B", XB_B}, {"B0", XB_B0}};
+    auto id_of = [&](const std::string& n) {
+      for (auto& [name, id] : names)
+        if (name == n) return id;
+      throw std::runtime_error("Unknown vector name " + n);
+    };
+    B200_CALL(xb_field_upload(ctx, id_of(cmd.field), 0, f.data()));
+    if (!cmd.field_axpy.empty()) {  // VecAXPY(B, 1.0, B0)
+      std::vector<double> b;
+      if (get_named_vector(cmd.field_axpy, b)) return 1;
+      for (size_t i = 0; i < nloc; ++i) b[i] += f[i];
+      B200_CALL(xb_field_upload(ctx, id_of(cmd.field_axpy), 0, b.data()));
+    }
+    return 0;
+  }
+  throw std::runtime_error("Preset " + cmd.name + " is not covered by this build");
 }
 
 // FieldView::diagnose (src/diagnostics/field_view.cpp:98-118): float32 image of the whole vector in
@@ -595,6 +794,8 @@ int Simulation::calculate()
   wall_start_ = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   for (int t = start + 1; t <= geom.geom_nt; ++t) {
     if (rank_ == 0) std::cout << std::format("Timestep = {:.4f} [1/w_pe] = {} [dt]", t * geom.dt, t) << "\n";
+    for (const Command& cmd : step_presets_)  // interfaces/simulation.cpp:82-84
+      if (execute_command(cmd, t)) return 1;
     if (timestep_implementation(t)) return 1;
     if (scheme == XB_ECCAPFIM) {  // the LOG lines of calc_iteration, eccapfim/simulation.cpp:80-96
       int32_t its = 0, fev = 0, reason = 0;

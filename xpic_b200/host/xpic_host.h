@@ -114,15 +114,37 @@ private:
   int prime_energy();
   int save_backup(int t);           // SimulationBackup::save
   int load_backup(int t);           // SimulationBackup::load
-  struct Preset {  // SetParticles: coordinate and momentum generators (src/utils/particles_load.h)
-    std::string particles, coordinate, momentum;
+  struct Momentum {  // MomentumGenerator (src/utils/particles_load.h)
+    std::string name;
     bool tov = false;
+    std::array<double, 3> value{};                                           // PreciseMomentum
+    std::array<double, 3> amplitude{}, wave_number{}, box_min{}, box_max{};  // MaxwellCosinePerturbation
+  };
+  struct Preset {  // a sort with its coordinate and momentum generators
+    std::string particles, coordinate;
+    Momentum momentum;
     std::array<double, 3> box_min{}, box_max{};       // CoordinateInBox
     std::array<double, 3> center{};                   // CoordinateInCylinder centre / PreciseCoordinate value
     double radius = 0, height = 0;                    // CoordinateInCylinder
-    std::array<double, 3> value{};                    // PreciseMomentum
-    std::array<double, 3> amplitude{}, wave_number{}, mbox_min{}, mbox_max{};  // MaxwellCosinePerturbation
   };
+  struct Command {  // one entry of "Presets" / "StepPresets" (src/commands)
+    std::string name;
+    Preset preset;                        // SetParticles, InjectParticles (ionized sort), RemoveParticles (sort name)
+    std::string ejected;                  // InjectParticles
+    Momentum momentum_e;
+    int injection_start = 0, injection_end = 1, tau = 0;
+    int64_t per_step = -1;
+    int32_t geometry = XB_GEOMETRY_BOX;   // RemoveParticles, FieldsDamping
+    std::array<double, 6> p{};
+    double coefficient = 0;               // FieldsDamping
+    std::string field, field_axpy, setter;  // SetMagneticField
+    std::array<double, 3> value{};
+    std::vector<std::array<double, 3>> coils;  // {z0, R, I}
+  };
+  int execute_command(const Command& cmd, int t);
+  void draw_coordinate(const Preset& pr, Point& pt);
+  void draw_momentum(const Momentum& m, const SortParameters& sp, Point& pt);
+  int64_t preset_count(const Preset& pr, const SortParameters& sp) const;
   int diagnose_log(int t);          // LogView (src/diagnostics/log_view.cpp)
   struct View {  // FieldView / DistributionMoment: what is dumped, which region, where
     std::string field, particles, dir, suffix;
@@ -136,12 +158,13 @@ private:
   double log_prev_wall_ = 0, log_period_wall_ = 0, wall_start_ = 0;
   std::array<double, XB_STAGE_COUNT> log_prev_stage_{}, log_period_stage_{};
   std::unique_ptr<std::ofstream> log_each_;
+  bool open_z_ = false;             // "da_boundary_z" is not DM_BOUNDARY_PERIODIC
   int da_processors_z_ = -1;        // "mpi": {"da_processors_z"} (utils/configuration.cpp:111-130)
   int rank_ = 0, nranks_ = 1;       // z-slab of this process (-rank / -nranks or RANK / WORLD_SIZE)
   std::string comm_file_;           // where rank 0 leaves the communicator id for the other ranks
   int z0_ = 0, nzl_ = 0;            // owned planes
   std::vector<SortParameters> sorts_;
-  std::vector<Preset> presets_;
+  std::vector<Command> presets_, step_presets_;
   std::vector<View> moment_views_;  // "Diagnostics": [{"diagnostic": "DistributionMoment", "particles": ..., "moment": ..., "region": ...}]
   std::vector<View> field_views_;   // "Diagnostics": [{"diagnostic": "FieldView", "field": ..., "region": ...}]
   std::unique_ptr<Table> energy_, energy_cons_, convergence_, charge_, momentum_;
