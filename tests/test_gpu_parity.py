@@ -819,7 +819,7 @@ def test_fields_damping_matches_the_reference_formulas(X, geometry, params):
     ref_taken = np.sum(0.5 * Eg ** 2 * (1 - damp ** 2)) + np.sum(0.5 * (Bg - B0g) ** 2 * (1 - damp ** 2))
     assert np.any(damp != 1.0)
     np.testing.assert_allclose(s.get_field("E").reshape(Eg.shape), Eg * damp, rtol=1e-14, atol=1e-15)
-    np.testing.assert_allclose(s.get_field("B").reshape(Eg.shape), (Bg - B0g) * damp + B0g, rtol=1e-14, atol=1e-15)
+    np.testing.assert_allclose(s.get_field("B").reshape(Eg.shape), (Bg - B0g) * damp + B0g, rtol=1e-14, atol=1e-14)
     assert abs(taken - ref_taken) < 1e-11 * ref_taken
     s.close()
 
@@ -871,6 +871,6 @@ def test_host_program_open_trap_with_step_presets(X, tmp_path):
     z = np.arange(24) * 0.5
     on_axis = sum(2 * np.pi * 4.0 * 3.0 ** 2 / ((z - z0) ** 2 + 3.0 ** 2) ** 1.5 for z0 in (-2.0, 14.0))
     # B_z sits at (x + 1/2, y + 1/2, z): the node next to the axis is a quarter cell diagonal away from it
-    np.testing.assert_allclose(B0[:, 5, 5, 2], on_axis, rtol=2e-2)
+    np.testing.assert_allclose(B0[:, 5, 5, 2], on_axis, rtol=5e-2)
     dens = np.fromfile(str(out / "electrons" / "density" / "12"), dtype=np.float32)
     assert dens.size == 24 * 12 * 12 and dens.max() > 0

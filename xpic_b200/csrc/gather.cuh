@@ -187,6 +187,33 @@ __device__ __forceinline__ void gather_B_tile(const double* __restrict__ T, cons
       }
 }
 
+// The same two gathers as nested linear interpolations (x, then y, then z): 7 multiply-adds and 7 multiplies per
+// component instead of 16 multiplies and 8 multiply-adds for the eight explicit weight products -- the second push is
+// bound by fp64 issue, not by HBM.  Same weights, same nodes as interpolate_E_s1 / B_s1
+// (src/impls/ecsim/simulation.cpp:8-118); the sum is associated differently (agreement at round-off level).
+__device__ __forceinline__ double lerp3(const double* __restrict__ T, int base, int Y, int Z, const double* wx, const double* wy, const double* wz)
+{
+  const double a00 = T[base] * wx[0] + T[base + 1] * wx[1];
+  const double a01 = T[base + Y] * wx[0] + T[base + Y + 1] * wx[1];
+  const double a10 = T[base + Z] * wx[0] + T[base + Z + 1] * wx[1];
+  const double a11 = T[base + Z + Y] * wx[0] + T[base + Z + Y + 1] * wx[1];
+  return (a00 * wy[0] + a01 * wy[1]) * wz[0] + (a10 * wy[0] + a11 * wy[1]) * wz[1];
+}
+
+template <int NC>
+__device__ __forceinline__ void gather_EB_tile_nested(const double* __restrict__ Et, const double* __restrict__ Bt, const Weights& w, const TileIndex& t,
+                                                      double* Ep, double* Bp)
+{
+  constexpr int NX = FieldTile<NC>::NX, C = 9 * NX, Y = NX, Z = 3 * NX;
+  // E_x: staggered in x; E_y: in y; E_z: in z.  B_x: nodal in x, staggered in y, z; ...
+  Ep[0] = lerp3(Et, 0 * C + t.zn + t.yn + t.xs, Y, Z, w.ws[0], w.wn[1], w.wn[2]);
+  Ep[1] = lerp3(Et, 1 * C + t.zn + t.ys + t.xn, Y, Z, w.wn[0], w.ws[1], w.wn[2]);
+  Ep[2] = lerp3(Et, 2 * C + t.zs + t.yn + t.xn, Y, Z, w.wn[0], w.wn[1], w.ws[2]);
+  Bp[0] = lerp3(Bt, 0 * C + t.zs + t.ys + t.xn, Y, Z, w.wn[0], w.ws[1], w.ws[2]);
+  Bp[1] = lerp3(Bt, 1 * C + t.zs + t.yn + t.xs, Y, Z, w.ws[0], w.wn[1], w.ws[2]);
+  Bp[2] = lerp3(Bt, 2 * C + t.zn + t.ys + t.xs, Y, Z, w.ws[0], w.ws[1], w.wn[2]);
+}
+
 // ---- binning ------------------------------------------------------------------------------------
 // periodic wrap of one coordinate, src/interfaces/point.cpp:18-26
 __device__ __forceinline__ double wrap_coord(double s, double L)

@@ -82,6 +82,8 @@ static int cheb_apply(xb_ctx* c, int deg, const double* u, double* z, double* /*
   auto step = [&](int k, double rho, int zl0, int nplanes) -> int {
     double* zk = buf[(k + off) % 3];
     const double* zkm = k > 1 ? buf[(k - 1 + off) % 3] : nullptr;
+    // (a shared-memory tiled form of this sweep was measured slower: 0.10 instead of 0.075 ms per sweep at 128^3 -- the
+    // staging loop with its wrap arithmetic costs more than the cached stencil loads it replaces)
     XB_LAUNCH(c, k_cheb_step, (int)((g.plane * nplanes + 255) / 256), 256, 0, g, zk, zkm, u, buf[(k + 1 + off) % 3], rho * rho_old, 2.0 * rho / delta, diag,
               zl0, nplanes);
     return 0;

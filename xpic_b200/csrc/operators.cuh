@@ -14,22 +14,32 @@ template <class F>
 __device__ __forceinline__ double curlcurl(int c, const double* inv_d, F&& f, bool cut_below = false)
 {
   double r = 0.0;
+  if (!cut_below) {  // every node of a periodic box, and all but plane 0 of an open one
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (a == c) continue;
+      int ea[3] = {0, 0, 0}, ec[3] = {0, 0, 0};
+      ea[a] = 1;
+      ec[c] = 1;
+      const double lap = (f(c, ea[0], ea[1], ea[2]) - 2.0 * f(c, 0, 0, 0) + f(c, -ea[0], -ea[1], -ea[2])) * (inv_d[a] * inv_d[a]);
+      const double mix = ((f(a, ec[0], ec[1], ec[2]) - f(a, 0, 0, 0)) - (f(a, ec[0] - ea[0], ec[1] - ea[1], ec[2] - ea[2]) - f(a, -ea[0], -ea[1], -ea[2]))) *
+                         (inv_d[a] * inv_d[c]);
+      r += mix - lap;
+    }
+    return r;
+  }
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     if (a == c) continue;
     int ea[3] = {0, 0, 0}, ec[3] = {0, 0, 0};
     ea[a] = 1;
     ec[c] = 1;
-    const bool cut = cut_below && a == 2;
-    // (d_a^+ f_c)(0) - (d_a^+ f_c)(-e_a)  and  (d_c^+ f_a)(0) - (d_c^+ f_a)(-e_a): the second terms sit on plane -1
+    // (d_a^+ f_c)(0) - (d_a^+ f_c)(-e_a)  and  (d_c^+ f_a)(0) - (d_c^+ f_a)(-e_a): along z the second terms sit on plane -1
     const double up_l = f(c, ea[0], ea[1], ea[2]) - f(c, 0, 0, 0);
-    const double dn_l = cut ? 0.0 : f(c, 0, 0, 0) - f(c, -ea[0], -ea[1], -ea[2]);
+    const double dn_l = a == 2 ? 0.0 : f(c, 0, 0, 0) - f(c, -ea[0], -ea[1], -ea[2]);
     const double up_m = f(a, ec[0], ec[1], ec[2]) - f(a, 0, 0, 0);
-    const double dn_m = cut ? 0.0 : f(a, ec[0] - ea[0], ec[1] - ea[1], ec[2] - ea[2]) - f(a, -ea[0], -ea[1], -ea[2]);
-    const double lap = cut ? (up_l - dn_l) * (inv_d[a] * inv_d[a])
-                           : (f(c, ea[0], ea[1], ea[2]) - 2.0 * f(c, 0, 0, 0) + f(c, -ea[0], -ea[1], -ea[2])) * (inv_d[a] * inv_d[a]);
-    const double mix = (up_m - dn_m) * (inv_d[a] * inv_d[c]);
-    r += mix - lap;
+    const double dn_m = a == 2 ? 0.0 : f(a, ec[0] - ea[0], ec[1] - ea[1], ec[2] - ea[2]) - f(a, -ea[0], -ea[1], -ea[2]);
+    r += (up_m - dn_m) * (inv_d[a] * inv_d[c]) - (up_l - dn_l) * (inv_d[a] * inv_d[a]);
   }
   return r;
 }

@@ -179,7 +179,7 @@ __global__ void k_scan_add(int32_t* __restrict__ out, int64_t n, const int32_t* 
 // run with one atomic.  The kernel is bound by the latency of those returning atomics (ncu: 65 stall
 // cycles per issued instruction on the long scoreboard), so every thread carries SCATTER_ITEMS
 // particles whose reservations are all in flight before the first one is used.
-constexpr int SCATTER_ITEMS = 8;
+constexpr int SCATTER_ITEMS = 4;
 constexpr int SCATTER_THREADS = 256;
 
 __global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(int64_t n, const int32_t* __restrict__ key, int32_t* __restrict__ cursor,
@@ -215,20 +215,34 @@ __global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(int64_t n, const in
     base[j] = 0;
     if (head) base[j] = atomicAdd(&cursor[k[j]], end - lane);
   }
+  // the particles themselves are fetched while the reservations are in flight
+  double r[SCATTER_ITEMS][6];
+  uint64_t pid[SCATTER_ITEMS];
+#pragma unroll
+  for (int j = 0; j < SCATTER_ITEMS; ++j) {
+    const int64_t i = first + (int64_t)j * SCATTER_THREADS;
+    if (k[j] >= 0) {
+      r[j][0] = s0[i];
+      r[j][1] = s1[i];
+      r[j][2] = s2[i];
+      r[j][3] = s3[i];
+      r[j][4] = s4[i];
+      r[j][5] = s5[i];
+      pid[j] = sid ? sid[i] : 0;
+    }
+  }
 #pragma unroll
   for (int j = 0; j < SCATTER_ITEMS; ++j) {
     const int32_t b = __shfl_sync(0xffffffffu, base[j], head_lane[j] & 31);
     if (k[j] < 0) continue;
-    const int64_t i = first + (int64_t)j * SCATTER_THREADS;
     const int32_t pos = b + (lane - head_lane[j]);
-    const double vx = s3[i], vy = s4[i], vz = s5[i];
-    d0[pos] = moved_coord(s0[i], vx, dtm, g.Lx);  // the same bits the key pass binned (dtm = 0: plain copy + wrap)
-    d1[pos] = moved_coord(s1[i], vy, dtm, g.Ly);
-    d2[pos] = moved_z(g, s2[i], vz, dtm);
-    d3[pos] = vx;
-    d4[pos] = vy;
-    d5[pos] = vz;
-    if (sid) did[pos] = sid[i];
+    d0[pos] = moved_coord(r[j][0], r[j][3], dtm, g.Lx);  // the same bits the key pass binned (dtm = 0: plain copy + wrap)
+    d1[pos] = moved_coord(r[j][1], r[j][4], dtm, g.Ly);
+    d2[pos] = moved_z(g, r[j][2], r[j][5], dtm);
+    d3[pos] = r[j][3];
+    d4[pos] = r[j][4];
+    d5[pos] = r[j][5];
+    if (sid) did[pos] = pid[j];
   }
 }
 
@@ -410,11 +424,11 @@ int particles_generate(xb_ctx* c, Species& s, int64_t total, const double* T, ui
 // ---------------------------------------------------------------------------------------------
 // second push (ecsim): gather E^{n+1/2}, B^n at the particle, Boris update of v
 // ---------------------------------------------------------------------------------------------
-// One CTA per group of 16 x-consecutive cells: the 18 x 3 x 3 nodes x 3 components of E and of B
+// One CTA per group of 64 x-consecutive cells: the 66 x 3 x 3 nodes x 3 components of E and of B
 // its particles can touch are staged in shared memory once, so the 48 gathers per particle are
 // shared-memory reads and HBM sees only the particle stream (72 B / particle).
 constexpr int PUSH_THREADS = 256;
-constexpr int PUSH_CELLS = 16;
+constexpr int PUSH_CELLS = 64;
 
 // WORK: also accumulate the predicted field work  q n/Np * (v_old + v_new)/2 . E_p  of ecsimcorr
 // (src/impls/ecsimcorr/particles.cpp:77-78), one partial per CTA (summed by a fixed tree afterwards)
@@ -435,22 +449,40 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_second(Grid g, const int3
   const int32_t p0 = bin_start[cell0 << 3], p1 = bin_start[(cell0 + ncell) << 3];
   __syncthreads();
   double work = 0.0;
-  for (int32_t i = p0 + threadIdx.x; i < p1; i += PUSH_THREADS) {
-    Weights w;
-    make_weights(g, x[i], y[i], z[i], 0, w);
-    const TileIndex t = tile_index<PUSH_CELLS>(w, cx0, cy, zl);
-    double Ep[3], Bp[3];
-    gather_E_tile<PUSH_CELLS>(Et, w, t, Ep);
-    gather_B_tile<PUSH_CELLS>(Bt, w, t, Bp);
-    const double vo[3] = {vx[i], vy[i], vz[i]};
-    double v[3] = {vo[0], vo[1], vo[2]};
-    boris_update_vEB(g.dt, qm, Ep, Bp, v);
-    vx[i] = v[0];
-    vy[i] = v[1];
-    vz[i] = v[2];
-    if (WORK) {
-      const double vs[3] = {vo[0] + v[0], vo[1] + v[1], vo[2] + v[2]};
-      work += qn_Np * 0.5 * dot3(vs, Ep);
+  // two particles per thread and round: their twelve loads are in flight together (the kernel is bound by the latency
+  // of the particle stream, not by arithmetic)
+  for (int32_t i0 = p0 + threadIdx.x; i0 < p1; i0 += 2 * PUSH_THREADS) {
+    const int32_t idx[2] = {i0, i0 + PUSH_THREADS};
+    double r[2][6];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (idx[u] < p1) {
+        r[u][0] = x[idx[u]];
+        r[u][1] = y[idx[u]];
+        r[u][2] = z[idx[u]];
+        r[u][3] = vx[idx[u]];
+        r[u][4] = vy[idx[u]];
+        r[u][5] = vz[idx[u]];
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (idx[u] >= p1) continue;
+      const int32_t i = idx[u];
+      Weights w;
+      make_weights(g, r[u][0], r[u][1], r[u][2], 0, w);
+      const TileIndex t = tile_index<PUSH_CELLS>(w, cx0, cy, zl);
+      double Ep[3], Bp[3];
+      gather_EB_tile_nested<PUSH_CELLS>(Et, Bt, w, t, Ep, Bp);
+      const double vo[3] = {r[u][3], r[u][4], r[u][5]};
+      double v[3] = {vo[0], vo[1], vo[2]};
+      boris_update_vEB(g.dt, qm, Ep, Bp, v);
+      vx[i] = v[0];
+      vy[i] = v[1];
+      vz[i] = v[2];
+      if (WORK) {
+        const double vs[3] = {vo[0] + v[0], vo[1] + v[1], vo[2] + v[2]};
+        work += qn_Np * 0.5 * dot3(vs, Ep);
+      }
     }
   }
   if (WORK) {
