@@ -244,6 +244,17 @@ enum { XB_MOMENT_DENSITY = 0, XB_MOMENT_CURRENT = 1, XB_MOMENT_MOMENTUM_FLUX = 2
 int xb_distribution_moment(xb_ctx* ctx, int32_t sid, int32_t moment, double* out);
 int xb_distribution_moment_region(xb_ctx* ctx, int32_t sid, int32_t moment, const int32_t start[3], const int32_t size[3], double* out);
 
+/* VelocityDistribution::collect (src/diagnostics/velocity_distribution.cpp:116-166) for sort sid: the number density
+ * n / Np of the particles whose cell centre lies inside the geometry (same six numbers as the commands below), binned
+ * over two projections of the velocity -- get_vx_vy, get_vz_vxy, get_vr_vphi (:169-194) -- with ROUND_STEP(v, dv).
+ * As in set_regions (:53-63) both axes start at ROUND_STEP(vmin[0], dv[0]) and hold ROUND_STEP(vmax[0] - vmin[0], dv[0])
+ * bins; xb_velocity_distribution_size returns those two numbers.  out receives size * size doubles,
+ * [second projection][first projection], summed over all ranks (the reference's VecScatter ADD, :163-164). */
+enum { XB_PROJECTOR_VX_VY = 0, XB_PROJECTOR_VZ_VXY = 1, XB_PROJECTOR_VR_VPHI = 2 };
+int xb_velocity_distribution_size(const double dv[2], const double vmin[2], const double vmax[2], int32_t* start, int32_t* size);
+int xb_velocity_distribution(xb_ctx* ctx, int32_t sid, int32_t projector, int32_t geometry, const double p[6], const double dv[2],
+                             const double vmin[2], const double vmax[2], double* out);
+
 /* MomentumConservation::calculate (src/diagnostics/momentum_conservation.cpp:71-126) for sort sid with the
  * present E: out = { Px, Py, Pz, QEx, QEy, QEz }, P = m / Np * sum v, QE = q / Np * sum E(x_p) with the global
  * 2nd-order form factor, summed over all ranks.  The caller keeps P of the previous call for the

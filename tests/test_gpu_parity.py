@@ -710,6 +710,51 @@ def test_distribution_moments_and_regions(X, name):
         assert np.max(np.abs(got - ref)) < 1e-12 * max(np.max(np.abs(ref)), 1e-30), (name, start)
 
 
+@pytest.mark.parametrize("projector", ["vx_vy", "vz_vxy", "vr_vphi"])
+def test_velocity_distribution(X, projector):
+    """VelocityDistribution::collect (src/diagnostics/velocity_distribution.cpp:116-166) on the device, for a box and a
+    cylinder, against the same rule evaluated with numpy: a particle counts when the centre of its cell is inside the
+    geometry, its projected velocity is binned with ROUND_STEP, both axes use the x range."""
+    n = (9, 8, 7)
+    d = 0.5
+    o, s = make_pair(n=n, Np=12, T=40.0)
+    pts, _ = o.get_particles(0)
+    r, v = pts[:, :3], pts[:, 3:]
+    dv, vmin, vmax = (0.05, 0.04), (-0.6, -0.2), (0.7, 0.9)
+    start, size = int(np.round(vmin[0] / dv[0])), int(np.round((vmax[0] - vmin[0]) / dv[0]))
+    for geometry, p in (("box", (0.6, 0.0, 1.1, 3.9, 3.2, 3.0)), ("cylinder", (2.25, 2.0, 1.75, 1.6, 2.2, 0.0))):
+        cell = np.floor(r / d).astype(int)
+        centre = (cell + 0.5) * d
+        if geometry == "box":
+            lo, hi = np.array(p[:3]), np.array(p[3:])
+            a0, a1 = np.floor(lo / d).astype(int), np.floor(hi / d).astype(int)
+            inside = np.all((lo <= centre) & (centre < hi), axis=1)
+        else:
+            c, rad, h = np.array(p[:3]), p[3], p[4]
+            lo, hi = c - np.array([rad, rad, 0.5 * h]), c + np.array([rad, rad, 0.5 * h])
+            a0, a1 = np.floor(lo / d).astype(int), np.floor(hi / d).astype(int)
+            inside = (np.abs(centre[:, 2] - c[2]) < 0.5 * h) & ((centre[:, 0] - c[0]) ** 2 + (centre[:, 1] - c[1]) ** 2 <= rad * rad)
+        inside &= np.all((cell >= a0) & (cell < a1), axis=1)
+        if projector == "vx_vy":
+            pa, pb = v[:, 0], v[:, 1]
+        elif projector == "vz_vxy":
+            pa, pb = v[:, 2], np.hypot(v[:, 0], v[:, 1])
+        else:
+            x, y = r[:, 0] - 0.5 * n[0] * d, r[:, 1] - 0.5 * n[1] * d
+            rr = np.hypot(x, y)
+            pa, pb = (x * v[:, 0] + y * v[:, 1]) / rr, (-y * v[:, 0] + x * v[:, 1]) / rr
+        ia = np.round(pa / dv[0]).astype(int) - start  # np.round is half-to-even; an exact tie of a random velocity does not occur
+        ib = np.round(pb / dv[1]).astype(int) - start
+        keep = inside & (ia >= 0) & (ia < size) & (ib >= 0) & (ib < size)
+        ref = np.zeros((size, size))
+        np.add.at(ref, (ib[keep], ia[keep]), 1.0 / 12)
+        got_start, got = s.velocity_distribution(projector, geometry, p, dv, vmin, vmax)
+        assert got_start == start and got.shape == ref.shape
+        assert keep.sum() > 100
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12 * ref.max())
+    s.close()
+
+
 def test_host_program_runs_the_reference_root_configuration(X, tmp_path):
     """The set-up of the reference's root config.json (eccapfim Langmuir wave: a 2 x 2 x 32 box, 1000 particles per cell,
     MaxwellCosinePerturbation, three LogView levels), shortened to 20 steps, plus a 2D FieldView plane and a
@@ -874,3 +919,6 @@ def test_host_program_open_trap_with_step_presets(X, tmp_path):
     np.testing.assert_allclose(B0[:, 5, 5, 2], on_axis, rtol=5e-2)
     dens = np.fromfile(str(out / "electrons" / "density" / "12"), dtype=np.float32)
     assert dens.size == 24 * 12 * 12 and dens.max() > 0
+    # VelocityDistribution "vz_vxy": 60 x 60 bins from -30 (both axes, as the reference sizes them); |v_perp| >= 0 fills rows >= 30 only
+    fv = np.fromfile(str(out / "electrons" / "vz_vxy" / "12"), dtype=np.float32).reshape(60, 60)
+    assert fv.sum() > 0 and fv[:29].sum() == 0

@@ -121,6 +121,8 @@ SYMBOLS = {
     "xb_momentum": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "xb_distribution_moment": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "xb_distribution_moment_region": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _i32p, _i32p, _dp]),
+    "xb_velocity_distribution_size": (C.c_int, [_dp, _dp, _dp, _i32p, _i32p]),
+    "xb_velocity_distribution": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp]),
 }
 
 
@@ -320,6 +322,20 @@ class Simulation:
             sz = (C.c_int32 * 3)(*(size if size is not None else self.n))
             _check(self._L.xb_distribution_moment_region(self._h, sid, mid, st, sz, _as_dp(out)))
         return out
+
+    PROJECTORS = {"vx_vy": 0, "vz_vxy": 1, "vr_vphi": 2}
+
+    def velocity_distribution(self, projector, geometry, p, dv, vmin=(-1.0, -1.0), vmax=(1.0, 1.0), sid=0):
+        """VelocityDistribution::collect: (start, f) with f[second projection bin][first projection bin] summed over all
+        ranks; bins start..start+len(f) on both axes (the reference sizes both from vmin[0], vmax[0], dv[0])."""
+        p = np.ascontiguousarray(np.resize(np.asarray(p, dtype=np.float64), 6))
+        dv, vmin, vmax = (np.ascontiguousarray(v, dtype=np.float64) for v in (dv, vmin, vmax))
+        start, size = C.c_int32(0), C.c_int32(0)
+        _check(self._L.xb_velocity_distribution_size(_as_dp(dv), _as_dp(vmin), _as_dp(vmax), C.byref(start), C.byref(size)))
+        out = np.zeros((size.value, size.value), dtype=np.float64)
+        _check(self._L.xb_velocity_distribution(self._h, sid, self.PROJECTORS[projector], {"box": 0, "cylinder": 1}[geometry], _as_dp(p), _as_dp(dv),
+                                                _as_dp(vmin), _as_dp(vmax), _as_dp(out)))
+        return start.value, out
 
     def density(self, sid=0):
         """DistributionMoment "density": cell-centred number density of sort sid on the owned cells."""

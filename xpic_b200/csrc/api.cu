@@ -900,6 +900,29 @@ int xb_distribution_moment_region(xb_ctx* c, int32_t sid, int32_t moment, const 
 
 int xb_distribution_moment(xb_ctx* c, int32_t sid, int32_t moment, double* out) { return xb_distribution_moment_region(c, sid, moment, nullptr, nullptr, out); }
 
+int xb_velocity_distribution_size(const double dv[2], const double vmin[2], const double vmax[2], int32_t* start, int32_t* size)
+{
+  if (!dv || !vmin || !vmax || !start || !size) XB_FAIL("xb_velocity_distribution_size: null argument");
+  if (!(dv[0] > 0.0) || !(dv[1] > 0.0)) XB_FAIL("xb_velocity_distribution_size: dv must be positive");
+  velocity_region(dv, vmin, vmax, start, size);
+  return 0;
+}
+
+int xb_velocity_distribution(xb_ctx* c, int32_t sid, int32_t projector, int32_t geometry, const double p[6], const double dv[2], const double vmin[2],
+                             const double vmax[2], double* out)
+{
+  XB_API_BEGIN(c);
+  if (sid < 0 || sid >= (int)c->sorts.size()) XB_FAIL("bad species id");
+  if (projector < XB_PROJECTOR_VX_VY || projector > XB_PROJECTOR_VR_VPHI) XB_FAIL("xb_velocity_distribution: unknown projector");
+  if ((geometry != XB_GEOMETRY_BOX && geometry != XB_GEOMETRY_CYLINDER) || !p) XB_FAIL("xb_velocity_distribution: unknown geometry");
+  if (!dv || !vmin || !vmax || !out) XB_FAIL("xb_velocity_distribution: null argument");
+  if (!(dv[0] > 0.0) || !(dv[1] > 0.0)) XB_FAIL("xb_velocity_distribution: dv must be positive");
+  Geometry ge;
+  ge.kind = geometry;
+  for (int k = 0; k < 6; ++k) ge.p[k] = p[k];
+  return velocity_distribution(c, c->sorts[sid], projector, ge, dv, vmin, vmax, out);
+}
+
 int xb_momentum(xb_ctx* c, int32_t sid, double out[6])
 {
   XB_API_BEGIN(c);

@@ -295,6 +295,9 @@ int charge_conservation(xb_ctx* c, int which_current, double* norms);   // Charg
 int momentum(xb_ctx* c, Species& s, double* out6);                      // MomentumConservation::calculate
 int distribution_moment(xb_ctx* c, Species& s, int moment, const int32_t* start, const int32_t* size);  // DistributionMoment::collect -> c->tmp2 (+ c->tmp)
 int moment_size(int moment);
+void velocity_region(const double dv[2], const double vmin[2], const double vmax[2], int32_t* vstart, int32_t* vsize);
+int velocity_distribution(xb_ctx* c, Species& s, int projector, const Geometry& ge, const double dv[2], const double vmin[2], const double vmax[2],
+                          double* host_out);
 
 // ---- api.cu: in-step kernel-family timing ------------------------------------------------------
 int prof_begin(xb_ctx* c, int family);

@@ -7,6 +7,7 @@
 //   Divergence (negative Yee shift)                  src/utils/operators.cpp:275-323
 // The charge density is a scalar field kept in component 0 of a ghosted grid vector, so the halo
 // reduction and the slab layout of the field kernels apply unchanged.
+#include "comm.cuh"
 #include "common.cuh"
 #include "gather.cuh"
 
@@ -293,6 +294,121 @@ int distribution_moment(xb_ctx* c, Species& s, int moment, const int32_t* start,
   }
   XB_CHECK(halo_reduce(c, c->tmp2, GZ, GZ));
   if (ms > 3) XB_CHECK(halo_reduce(c, c->tmp, GZ, GZ));
+  return 0;
+}
+
+// ---- VelocityDistribution (src/diagnostics/velocity_distribution.cpp) ------------------------------
+struct VelocityArgs {
+  int projector;
+  Geometry ge;
+  int xstart[3], xsize[3];  // axis-aligned box of the geometry in cells (velocity_distribution_builder.cpp:35-69)
+  int vstart, vsize;        // the same for both velocity axes, as in set_regions (:53-63)
+  double dvx, dvy;
+  double cx, cy;            // 0.5 * geom_x, 0.5 * geom_y (get_vr_vphi, :178-194)
+};
+
+// one thread per particle: the cell it sits in selects it (centre inside the geometry, :133-145), its projected
+// velocity picks the bin (:147-156); counts are integers, the weight n / Np is applied afterwards
+__global__ void __launch_bounds__(256) k_velocity_histogram(Grid g, VelocityArgs a, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                                                           const double* __restrict__ z, const double* __restrict__ vx, const double* __restrict__ vy,
+                                                           const double* __restrict__ vz, unsigned long long* __restrict__ hist)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r[3] = {x[i], y[i], z[i]};
+  const int cell[3] = {(int)floor(to_cells(r[0], g.dx, g.inv_dx, g.exact_inv & 1)), (int)floor(to_cells(r[1], g.dy, g.inv_dy, g.exact_inv & 2)),
+                       (int)floor(to_cells(r[2], g.dz, g.inv_dz, g.exact_inv & 4))};
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax)
+    if (cell[ax] < a.xstart[ax] || cell[ax] >= a.xstart[ax] + a.xsize[ax]) return;
+  if (!within_geometry(a.ge, (cell[0] + 0.5) * g.dx, (cell[1] + 0.5) * g.dy, (cell[2] + 0.5) * g.dz)) return;
+  const double v[3] = {vx[i], vy[i], vz[i]};
+  double pa, pb;
+  if (a.projector == XB_PROJECTOR_VX_VY) {
+    pa = v[0];
+    pb = v[1];
+  }
+  else if (a.projector == XB_PROJECTOR_VZ_VXY) {
+    pa = v[2];
+    pb = sqrt(v[0] * v[0] + v[1] * v[1] + 0.0);  // Vector3R(px, py, 0).length()
+  }
+  else {
+    const double X = r[0] - a.cx, Y = r[1] - a.cy;
+    const double rr = hypot(X, Y);
+    if (isinf(1.0 / rr)) {  // particles on the axis keep (vx, vy)
+      pa = v[0];
+      pb = v[1];
+    }
+    else {
+      pa = (+X * v[0] + Y * v[1]) / rr;
+      pb = (-Y * v[0] + X * v[1]) / rr;
+    }
+  }
+  const long long ia = (long long)round(pa / a.dvx), ib = (long long)round(pb / a.dvy);  // ROUND_STEP
+  if (ia < a.vstart || ia >= (long long)a.vstart + a.vsize || ib < a.vstart || ib >= (long long)a.vstart + a.vsize) return;
+  atomicAdd(&hist[(ib - a.vstart) * (long long)a.vsize + (ia - a.vstart)], 1ull);
+}
+
+__global__ void __launch_bounds__(256) k_histogram_counts(int64_t n, const unsigned long long* __restrict__ hist, double* __restrict__ out)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)hist[i];  // exact; the weight is applied after the sum over the ranks
+}
+
+void velocity_region(const double dv[2], const double vmin[2], const double vmax[2], int32_t* vstart, int32_t* vsize)
+{
+  // set_regions (velocity_distribution.cpp:53-63) uses vx_min, vx_max and dvx for both axes
+  *vstart = (int32_t)std::round(vmin[0] / dv[0]);
+  *vsize = (int32_t)std::round((vmax[0] - vmin[0]) / dv[0]);
+}
+
+// out: vsize * vsize doubles, [index of the second projection][index of the first], summed over all ranks
+int velocity_distribution(xb_ctx* c, Species& s, int projector, const Geometry& ge, const double dv[2], const double vmin[2], const double vmax[2],
+                          double* host_out)
+{
+  const Grid& g = c->g;
+  VelocityArgs a;
+  a.projector = projector;
+  a.ge = ge;
+  const double d[3] = {g.dx, g.dy, g.dz};
+  for (int ax = 0; ax < 3; ++ax) {  // FLOOR_STEP of the bounding box
+    const double lo = ge.kind == XB_GEOMETRY_BOX ? ge.p[ax] : (ax < 2 ? ge.p[ax] - ge.p[3] : ge.p[2] - 0.5 * ge.p[4]);
+    const double hi = ge.kind == XB_GEOMETRY_BOX ? ge.p[3 + ax] : (ax < 2 ? ge.p[ax] + ge.p[3] : ge.p[2] + 0.5 * ge.p[4]);
+    a.xstart[ax] = (int)std::floor(lo / d[ax]);
+    a.xsize[ax] = (int)std::floor(hi / d[ax]) - a.xstart[ax];
+  }
+  int32_t vstart, vsize;
+  velocity_region(dv, vmin, vmax, &vstart, &vsize);
+  if (vsize <= 0) XB_FAIL("velocity distribution: empty velocity region");
+  a.vstart = vstart;
+  a.vsize = vsize;
+  a.dvx = dv[0];
+  a.dvy = dv[1];
+  a.cx = 0.5 * g.Lx;
+  a.cy = 0.5 * g.Ly;
+  const int64_t bins = (int64_t)vsize * vsize;
+  unsigned long long* hist = nullptr;
+  double* sum = nullptr;
+  XB_CUDA(cudaMalloc(&hist, sizeof(unsigned long long) * bins));
+  XB_CUDA(cudaMalloc(&sum, sizeof(double) * bins));
+  int rc = 0;
+  do {
+    if ((rc = cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * bins, c->stream) != cudaSuccess)) break;
+    if (s.count > 0) {
+      double** p = s.p[s.cur];
+      k_velocity_histogram<<<(int)((s.count + 255) / 256), 256, 0, c->stream>>>(g, a, s.count, p[0], p[1], p[2], p[3], p[4], p[5], hist);
+    }
+    k_histogram_counts<<<(int)((bins + 255) / 256), 256, 0, c->stream>>>(bins, hist, sum);
+    if ((rc = cudaGetLastError() != cudaSuccess)) break;
+    if (g.nranks > 1 && (rc = comm_allreduce_sum(c, sum, (int)bins))) break;  // VecScatter ADD_VALUES over the ranks (:163-164)
+    if ((rc = cudaMemcpyAsync(host_out, sum, sizeof(double) * bins, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)) break;
+    rc = cudaStreamSynchronize(c->stream) != cudaSuccess;
+  } while (false);
+  cudaFree(hist);
+  cudaFree(sum);
+  if (rc) XB_FAIL("velocity distribution: device error");
+  const double w = s.n / (double)s.Np;  // n_Np(point)
+  for (int64_t i = 0; i < bins; ++i) host_out[i] *= w;
   return 0;
 }
 

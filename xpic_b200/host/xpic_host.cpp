@@ -247,6 +247,42 @@ int Simulation::configure(const std::string& config_path)
         v.dir = out_dir + "/" + v.particles + "/" + v.field + v.suffix;
         moment_views_.push_back(v);
       }
+      else if (name == "VelocityDistribution") {  // diagnostics/builders/velocity_distribution_builder.cpp:13-112
+        static const std::pair<const char*, int> projectors[] = {{"vx_vy", XB_PROJECTOR_VX_VY}, {"vz_vxy", XB_PROJECTOR_VZ_VXY}, {"vr_vphi", XB_PROJECTOR_VR_VPHI}};
+        VelocityView v;
+        info.at("particles").get_to(v.particles);
+        info.at("projector").get_to(v.projector);
+        v.projector_id = -1;
+        for (const auto& pr : projectors)
+          if (v.projector == pr.first) v.projector_id = pr.second;
+        if (v.projector_id < 0) throw std::runtime_error("Unkown projector name " + v.projector);  // the reference's message, velocity_distribution.cpp:204
+        const json& ge = info.at("geometry");
+        const std::string gname = ge.at("name").get<std::string>();
+        if (gname == "BoxGeometry") {  // Builder::load_geometry, interfaces/builder.cpp:83-94
+          std::array<double, 3> lo = {0.0, 0.0, 0.0}, hi = {geom.geom_x, geom.geom_y, geom.geom_z};
+          if (ge.contains("min")) lo = parse_vector(ge, "min", geom);
+          if (ge.contains("max")) hi = parse_vector(ge, "max", geom);
+          v.geometry = XB_GEOMETRY_BOX;
+          v.p = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+        }
+        else if (gname == "CylinderGeometry") {  // :96-111
+          std::array<double, 3> center = {0.5 * geom.geom_x, 0.5 * geom.geom_y, 0.5 * geom.geom_z};
+          double radius = 0.5 * std::min(geom.geom_x, geom.geom_y), height = geom.geom_z;
+          if (ge.contains("center")) center = parse_vector(ge, "center", geom);
+          if (ge.contains("radius")) ge.at("radius").get_to(radius);
+          if (ge.contains("height")) ge.at("height").get_to(height);
+          v.geometry = XB_GEOMETRY_CYLINDER;
+          v.p = {center[0], center[1], center[2], radius, height, 0.0};
+        }
+        else
+          throw std::runtime_error("Unknown geometry name " + gname);
+        info.at("dv").at(0).get_to(v.dv[0]);
+        info.at("dv").at(1).get_to(v.dv[1]);
+        if (info.contains("vmax")) v.vmax = {info.at("vmax").at(0).get<double>(), info.at("vmax").at(1).get<double>()};
+        if (info.contains("vmin")) v.vmin = {info.at("vmin").at(0).get<double>(), info.at("vmin").at(1).get<double>()};
+        v.dir = out_dir + "/" + v.particles + "/" + v.projector;
+        velocity_views_.push_back(v);
+      }
       else if (name == "LogView") {  // diagnostics/builders/log_view_builder.cpp: one of three levels
         const std::string level = info.at("level").get<std::string>();
         if (level == "EachTimestep") log_levels_ |= 1;
@@ -743,6 +779,23 @@ int Simulation::diagnose_fields(int t)
     B200_CALL(xb_distribution_moment_region(ctx, sid, v.moment, st, sz, f.data()));
     std::filesystem::create_directories(v.dir);
     if (write_region(v.dir + "/" + std::format("{:0{}d}", t, width), f, v)) return 1;
+  }
+  for (const VelocityView& v : velocity_views_) {  // VelocityDistribution::collect + FieldView::diagnose: one float32 [vy][vx] image
+    int32_t sid = -1;
+    for (size_t i = 0; i < particles_.size(); ++i)
+      if (particles_[i]->parameters.sort_name == v.particles) sid = (int32_t)i;
+    if (sid < 0) throw std::runtime_error("No particles with name " + v.particles);
+    int32_t vstart = 0, vsize = 0;
+    B200_CALL(xb_velocity_distribution_size(v.dv.data(), v.vmin.data(), v.vmax.data(), &vstart, &vsize));
+    f.assign((size_t)vsize * vsize, 0.0);
+    B200_CALL(xb_velocity_distribution(ctx, sid, v.projector_id, v.geometry, v.p.data(), v.dv.data(), v.vmin.data(), v.vmax.data(), f.data()));
+    if (rank_ == 0) {  // every rank holds the sum
+      std::filesystem::create_directories(v.dir);
+      std::vector<float> img(f.begin(), f.end());
+      std::ofstream out(v.dir + "/" + std::format("{:0{}d}", t, width), std::ios::binary | std::ios::trunc);
+      out.write(reinterpret_cast<const char*>(img.data()), (std::streamsize)(img.size() * sizeof(float)));
+      if (!out) throw std::runtime_error("short write into " + v.dir);
+    }
   }
   for (const View& v : field_views_) {
     if (get_named_vector(v.field, f)) return 1;

@@ -151,6 +151,13 @@ private:
     int moment = -1, dof = 3;
     std::array<int, 3> start{}, size{};
   };
+  struct VelocityView {  // "Diagnostics": [{"diagnostic": "VelocityDistribution", ...}] (builders/velocity_distribution_builder.cpp)
+    std::string particles, projector, dir;
+    int32_t projector_id = 0, geometry = XB_GEOMETRY_BOX;
+    std::array<double, 6> p{};
+    std::array<double, 2> dv{}, vmin{-1.0, -1.0}, vmax{1.0, 1.0};
+  };
+  std::vector<VelocityView> velocity_views_;
   struct json_ref { const void* p; };  // keeps nlohmann/json out of this header
   void parse_region(const json_ref& info, View& v) const;
   int write_region(const std::string& path, const std::vector<double>& slab, const View& v);  // every rank's part of one dump file
