@@ -170,6 +170,30 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def bind_near_gpu(local_rank):
+    """Moves this process onto the CPUs NVML lists as local to its GPU; returns the previous affinity (None when NVML
+    is not available: the run is then simply not bound)."""
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)).encode())
+        except Exception:  # noqa: BLE001
+            handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        before = os.sched_getaffinity(0)
+        cpus &= before
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return before
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -308,6 +332,8 @@ def main():
     value = nparticles * args.steps / (ms * 1e-3)
 
     # ---- end-to-end arm: the same K steps through xb_step_host with pinned HOST buffers ------------
+    # (allocated while the process sits on the CPUs next to its GPU, so that the copies do not cross sockets)
+    affinity = bind_near_gpu(local_rank)
     E = torch.zeros(sim.nown, dtype=torch.float64).pin_memory()
     B = torch.zeros(sim.nown, dtype=torch.float64).pin_memory()
     B0 = torch.zeros(sim.nown, dtype=torch.float64).pin_memory()
@@ -322,6 +348,8 @@ def main():
     h2d = 3 * sim.nown * 8 * world
     d2h = (2 * sim.nown * 8 + 8) * world
     del E, B, B0
+    if affinity:
+        os.sched_setaffinity(0, affinity)  # the CPU baseline below uses every host thread again
 
     checks = conservation_checks(sim, nparticles)
 
@@ -446,7 +474,7 @@ def main():
                                          "reference_residual_evaluations_per_step": 105}} if cap else {})},
             "roofline": roofline, "roofline_dominant": roofline_dominant, "kernels": kernels, "fp64_peak": fp64, "checks": checks, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                    "boundary": "xb_step_host: E, B, B0 uploaded from pinned host buffers, E, B and kinetic energy downloaded every step; particles resident"},
+                    "boundary": "xb_step_host: E, B, B0 uploaded from pinned host buffers (B under the re-binning, E and B0 under the particle stages), E, B and kinetic energy downloaded every step; particles resident"},
             "other_configs": extra,
             "gpu_launches": launches, "clocks": clocks,
         }

@@ -402,13 +402,10 @@ def test_step_host_equals_resident_step(X, scheme):
     pa, ia = by_id(*a.get_particles())
     pb, ib = by_id(*b.get_particles())
     assert np.array_equal(ia, ib) and np.array_equal(b.get_field("E"), E)
-    if scheme == 2:
-        # eccapfim's current is summed with shared-memory fp64 additions whose order varies run to run
-        assert rel_err(a.get_field("E"), E) < 1e-11 and rel_err(a.get_field("B"), B) < 1e-11
-        assert abs(K[0] / a.scalar("kinetic") - 1) < 1e-12 and rel_err(pa, pb) < 1e-12
-    else:
-        assert np.array_equal(a.get_field("E"), E) and np.array_equal(a.get_field("B"), B)
-        assert K[0] == a.scalar("kinetic") and np.array_equal(pa, pb)
+    # bit-identical for all three schemes: eccapfim's current is accumulated in fixed point (integer additions commute),
+    # the other deposits are atomic-free
+    assert np.array_equal(a.get_field("E"), E) and np.array_equal(a.get_field("B"), B)
+    assert K[0] == a.scalar("kinetic") and np.array_equal(pa, pb)
 
 
 def test_device_charge_density_matches_host_restatement(X):

@@ -104,6 +104,10 @@ static int stage_first_push(xb_ctx* c, int scheme)
       XB_CHECK(sort_species(c, s, 0.0));
     }
   }
+  if (c->b_pending) {  // xb_step_host: B^n travelled underneath the re-binning
+    XB_CUDA(cudaStreamWaitEvent(c->stream, c->b_ready, 0));
+    c->b_pending = false;
+  }
   XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS));
   XB_CHECK(deposit_moments(c));
   return prof_end(c, XB_FAMILY_MOMENTS);
@@ -310,7 +314,9 @@ static int create_impl(xb_ctx* c, const xb_grid* gr, const void* uid)
     XB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     XB_CUDA(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, hi));
   }
+  XB_CUDA(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
   XB_CUDA(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
+  XB_CUDA(cudaEventCreateWithFlags(&c->b_ready, cudaEventDisableTiming));
   XB_CUDA(cudaEventCreate(&c->ev0));
   XB_CUDA(cudaEventCreate(&c->ev1));
   XB_CUDA(cudaEventCreate(&c->ev2));
@@ -404,6 +410,8 @@ int xb_destroy(xb_ctx* c)
   for (auto& v : c->prof_events)
     for (auto e : v) cudaEventDestroy(e);
   if (c->copy_done) cudaEventDestroy(c->copy_done);
+  if (c->b_ready) cudaEventDestroy(c->b_ready);
+  if (c->host_stream) cudaStreamDestroy(c->host_stream);
   if (c->halo_ready) cudaEventDestroy(c->halo_ready);
   if (c->halo_done) cudaEventDestroy(c->halo_done);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -555,34 +563,42 @@ int xb_step_host(xb_ctx* c, int32_t scheme, double* E, double* B, const double* 
   XB_API_BEGIN(c);
   if (scheme != XB_ECSIM && scheme != XB_ECSIMCORR && scheme != XB_ECCAPFIM) XB_FAIL("unknown scheme");
   const Grid& g = c->g;
-  // B^n is needed by the first particle stage (moments); E^n and B0 only by the field solve, so for ecsim /
-  // ecsimcorr their upload travels on a second stream underneath the push, re-binning and moment kernels
+  // B^n is needed from the moment deposition on (after the re-binning), E^n and B0 only by the field solve: for
+  // ecsim / ecsimcorr the uploads travel on their own stream underneath the push, re-binning and moment kernels
   const bool overlap = scheme != XB_ECCAPFIM;
-  XB_CHECK(upload_owned(c, B, c->B));
   if (overlap) {
-    XB_CUDA(cudaEventRecord(c->copy_done, c->stream));  // the previous step's readers of E, B0 are done
-    XB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_done, 0));
-    XB_CUDA(cudaMemcpyAsync(c->E + g.own0, E, sizeof(double) * g.nown, cudaMemcpyHostToDevice, c->copy_stream));
-    if (B0) XB_CUDA(cudaMemcpyAsync(c->B0 + g.own0, B0, sizeof(double) * g.nown, cudaMemcpyHostToDevice, c->copy_stream));
-    XB_CUDA(cudaEventRecord(c->copy_done, c->copy_stream));
+    XB_CUDA(cudaEventRecord(c->copy_done, c->stream));  // the previous step's readers of E, B, B0 are done
+    XB_CUDA(cudaStreamWaitEvent(c->host_stream, c->copy_done, 0));
+    XB_CUDA(cudaMemcpyAsync(c->B + g.own0, B, sizeof(double) * g.nown, cudaMemcpyHostToDevice, c->host_stream));
+    XB_CUDA(cudaEventRecord(c->b_ready, c->host_stream));
+    c->b_pending = true;
+    XB_CUDA(cudaMemcpyAsync(c->E + g.own0, E, sizeof(double) * g.nown, cudaMemcpyHostToDevice, c->host_stream));
+    if (B0) XB_CUDA(cudaMemcpyAsync(c->B0 + g.own0, B0, sizeof(double) * g.nown, cudaMemcpyHostToDevice, c->host_stream));
+    XB_CUDA(cudaEventRecord(c->copy_done, c->host_stream));
   }
   else {
+    XB_CHECK(upload_owned(c, B, c->B));
     XB_CHECK(upload_owned(c, E, c->E));
     if (B0) XB_CHECK(upload_owned(c, B0, c->B0));
   }
-  XB_CHECK(ensure_sorted(c));
-  for (int st = 0; st < XB_STAGE_COUNT; ++st) {
+  int rc = ensure_sorted(c);
+  for (int st = 0; st < XB_STAGE_COUNT && !rc; ++st) {
     if (overlap && st == XB_STAGE_ADVANCE_FIELDS) XB_CUDA(cudaStreamWaitEvent(c->stream, c->copy_done, 0));
-    XB_CHECK(run_stage(c, scheme, st));
+    rc = run_stage(c, scheme, st);
   }
+  if (c->b_pending) {  // an error before the deposition: nothing may be left waiting for the next call
+    c->b_pending = false;
+    cudaStreamSynchronize(c->host_stream);
+  }
+  if (rc) return rc;
   // E goes home on the second stream while the kinetic energies are reduced and B follows on the first
   XB_CUDA(cudaEventRecord(c->copy_done, c->stream));
-  XB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_done, 0));
-  XB_CUDA(cudaMemcpyAsync(E, c->E + g.own0, sizeof(double) * g.nown, cudaMemcpyDeviceToHost, c->copy_stream));
+  XB_CUDA(cudaStreamWaitEvent(c->host_stream, c->copy_done, 0));
+  XB_CUDA(cudaMemcpyAsync(E, c->E + g.own0, sizeof(double) * g.nown, cudaMemcpyDeviceToHost, c->host_stream));
   if (kinetic)
     for (size_t i = 0; i < c->sorts.size(); ++i) XB_CHECK(kinetic_energy(c, c->sorts[i], nullptr, &kinetic[i]));
   XB_CHECK(download_owned(c, c->B, B));
-  XB_CUDA(cudaStreamSynchronize(c->copy_stream));
+  XB_CUDA(cudaStreamSynchronize(c->host_stream));
   XB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }

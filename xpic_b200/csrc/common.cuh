@@ -147,6 +147,7 @@ struct Species {
   MigrateBuffers* mig = nullptr;
   // ecsimcorr::Particles scalars (src/impls/ecsimcorr/particles.h:33-38)
   double energy = 0, pred_w = 0, corr_w = 0, pred_dK = 0, corr_dK = 0, lambda_dK = 0;
+  double cap_unit = 1.0;  // eccapfim: unit of the fixed-point current accumulators of this step (a power of two)
 };
 
 struct Comm;  // comm.cu (NCCL over NVLink, loaded lazily)
@@ -167,8 +168,11 @@ struct xb_ctx {
   bool track_ids = false;
   bool deterministic = false;  // canonical particle order inside every bin even without ids (costs one more pass)
   cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;  // host<->device copies of xb_step_host that overlap with the particle stages
+  cudaStream_t copy_stream = nullptr;  // exchanges that run beside the main stream's kernels (ghost particles, halo planes)
+  cudaStream_t host_stream = nullptr;  // host<->device copies of xb_step_host that overlap with the particle stages
   cudaEvent_t copy_done = nullptr;
+  cudaEvent_t b_ready = nullptr;       // xb_step_host: B^n has arrived (awaited before the moment deposition)
+  bool b_pending = false;
   cudaEvent_t halo_ready = nullptr, halo_done = nullptr;  // halo_begin / halo_end
   bool halo_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;

@@ -30,6 +30,7 @@
 // The Picard iteration of evaluation k + 1 starts from the velocity evaluation k converged to (option 4).
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "comm.cuh"
 #include "common.cuh"
@@ -62,7 +63,8 @@ struct CapArgs {
   const int32_t* bin_start;
   const double* E;  // E^{n+1/2,k}, ghosts valid (width GZ)
   const double* B;  // B^n, ghosts valid
-  double* J;        // this sort's current (ghosted, zeroed by the caller)
+  double* J;        // this sort's current (ghosted, zeroed by the caller): 64-bit fixed-point accumulators during the pass
+  double inv_unit;  // 1 / unit of those accumulators (a power of two)
   double q, m, mpw;
   double cn_tol;
   int cn_maxit;
@@ -169,12 +171,23 @@ __device__ __forceinline__ void cap_weights(const Grid& g, const double* rn, con
 
 // E gather (FAST: from the tile) -- implicit_esirkepov.cpp:71-90; DEPOSIT: the same loop adds
 // alpha * v[c] * weight into J (:97-116)
-// fp64 addition into the shared-memory current tile.  sm_100a has no native 64-bit shared atomic add: the
-// instruction is a load / add / compare-and-swap spin either way, but naming the state space saves the
-// generic-address test the plain atomicAdd() carries
-__device__ __forceinline__ void shared_add_f64(unsigned addr, double v)
+// The current is accumulated in 64-bit FIXED POINT (unit = a power of two 2^-46 below q n / Np, CapArgs::inv_unit
+// is folded into alpha): integer additions commute, so the result does not depend on the order in which
+// threads, warps and CTAs arrive -- two runs are bit-identical -- and the additions need no compare-and-swap spin
+// (sm_100a has no native 64-bit shared atomic, fp64 or integer).  One entry of the shared tile is two 32-bit
+// words updated with native 32-bit atomics: the low word reports its carry through the value it returns.
+__device__ __forceinline__ void shared_add_fixed(unsigned addr, long long x)
 {
-  asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+  const unsigned lo = (unsigned)x;
+  unsigned old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(lo) : "memory");
+  const int hi = (int)(x >> 32) + ((old + lo) < old ? 1 : 0);
+  if (hi != 0) asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr + 4u), "r"(hi) : "memory");
+}
+
+__device__ __forceinline__ void global_add_fixed(double* entry, long long x)
+{
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(entry)), "l"(x) : "memory");
 }
 
 template <bool FAST, bool DEPOSIT, class K>
@@ -206,14 +219,14 @@ __device__ __forceinline__ void cap_apply(const K& k, const CapW& w, double* Ep,
           if (FAST) {
             const int e = cx * K::VOL + base + (d[2] * K::NY + d[1]) * K::NX + d[0];
             if (DEPOSIT)
-              shared_add_f64(jaddr + 8u * (unsigned)(e - base), av * wt);
+              shared_add_fixed(jaddr + 8u * (unsigned)(e - base), __double2ll_rn(av * wt));
             else
               acc += k.Et[e] * wt;
           }
           else {
             const int64_t e = k.gidx(w.start[0] + d[0], w.start[1] + d[1], w.start[2] + d[2], cx);
             if (DEPOSIT)
-              atomicAdd(&k.J[e], av * wt);
+              global_add_fixed(&k.J[e], __double2ll_rn(av * wt));
             else
               acc += __ldg(&k.E[e]) * wt;
           }
@@ -414,7 +427,7 @@ __device__ __forceinline__ void cap_push_particle(const CapCtx& k, const CapArgs
         tb = (lo[c] - r0[c]) / vh[c];
       dtau = fmin(dtau, tb);
     }
-    const double a0 = q * a.mpw;
+    const double a0 = q * a.mpw * a.inv_unit;  // the current in accumulator units (exact scaling)
     const double alpha = 0.5 * dtau * (q / m);
     double Ep[3], Bp[3];
     int nseg = 0;
@@ -548,10 +561,11 @@ __global__ void __launch_bounds__(CAP_THREADS) k_cap_push(Grid g, CapArgs a)
   if (threadIdx.x < 2 && cnt[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], cnt[threadIdx.x]);
   // flush the current tile: one reduction per touched node instead of 54 per particle segment
   for (int e = threadIdx.x; e < 3 * CAP_VOL; e += CAP_THREADS) {
-    const double val = Jt[e];
-    if (val == 0.0) continue;
+    const long long val = reinterpret_cast<const long long*>(Jt)[e];
+    if (val == 0) continue;
+    if (llabs(val) >> 61) *a.error = 5;  // within a factor 4 of the accumulator range
     const int x = e % CAP_NX, y = (e / CAP_NX) % CAP_NY, z = (e / (CAP_NX * CAP_NY)) % CAP_NZ, c = e / CAP_VOL;
-    atomicAdd(&a.J[g.vidx(wrap_near(cx0 - CAP_LO + x, g.nx), wrap_near(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c)], val);
+    global_add_fixed(&a.J[g.vidx(wrap_near(cx0 - CAP_LO + x, g.nx), wrap_near(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c)], val);
   }
 }
 
@@ -624,7 +638,7 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
   __syncthreads();
   const CapCtx2 k{g, Et, Bt, Jt, cx0 - CAP_LO, cy - CAP_LO, g.z0 + zl - CAP_LO, a.E, a.B, a.J, a.error};
 
-  const double dt = g.dt, qm = a.q / a.m, a0 = a.q * a.mpw;
+  const double dt = g.dt, qm = a.q / a.m, a0 = a.q * a.mpw * a.inv_unit;  // currents in accumulator units
 
   // the particle this thread owns: start state (r0, v0), mean velocity vh of the present Picard iterate,
   // from which r = r0 + dtau vh, v = 2 vh - v0 once the particle has been moved (particles.cpp:143-144)
@@ -899,11 +913,34 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
   __syncthreads();
   if (tid < 2 && cnt[tid]) atomicAdd(&a.counters[tid], cnt[tid]);
   for (int e = tid; e < VOL3; e += CAP2_THREADS) {
-    const double val = Jt[e];
-    if (val == 0.0) continue;
+    const long long val = reinterpret_cast<const long long*>(Jt)[e];
+    if (val == 0) continue;
+    if (llabs(val) >> 61) *a.error = 5;  // within a factor 4 of the accumulator range
     const int x = e % CapCtx2::NX, y = (e / CapCtx2::NX) % CapCtx2::NY, z = (e / (CapCtx2::NX * CapCtx2::NY)) % CapCtx2::NZ, c = e / CapCtx2::VOL;
-    atomicAdd(&a.J[g.vidx(wrap_near(cx0 - CAP_LO + x, g.nx), wrap_near(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c)], val);
+    global_add_fixed(&a.J[g.vidx(wrap_near(cx0 - CAP_LO + x, g.nx), wrap_near(cy - CAP_LO + y, g.ny), zl - CAP_LO + z, c)], val);
   }
+}
+
+// max over the particles of |v_c| as the bit pattern of a non-negative double (integer order == numeric order)
+__global__ void __launch_bounds__(256) k_cap_max_speed(int64_t n, const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
+                                                      unsigned long long* __restrict__ out)
+{
+  double m = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmax(m, fmax(fabs(vx[i]), fmax(fabs(vy[i]), fabs(vz[i]))));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// fixed-point accumulators -> the current, in place (one rounding per entry)
+__global__ void __launch_bounds__(256) k_cap_current_from_fixed(double* __restrict__ J, int64_t n, double unit, int* __restrict__ error)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long acc = reinterpret_cast<const long long*>(J)[i];
+  if (llabs(acc) >> 62) *error = 5;
+  J[i] = (double)acc * unit;
 }
 
 // F = x + dt^2/4 curl^- curl^+ x - rhs0 + dt/2 J        (form_function, simulation.cpp:228-236;
@@ -990,6 +1027,8 @@ int cap_form_function(xb_ctx* c, double* x, double* F)
     a.counters = c->cap_counters;
     a.error = reinterpret_cast<int*>(c->cap_counters + 2);
     a.warm = (nl.warm_start && nl.pn_valid) ? 1 : 0;
+    const double unit = s.cap_unit;  // set once per step by cap_prepare
+    a.inv_unit = 1.0 / unit;
     if (!have_particles) {
     }
     else if (c->cap_variant == 1) {  // thread-per-particle kernel, kept as a cross-check
@@ -1007,6 +1046,7 @@ int cap_form_function(xb_ctx* c, double* x, double* F)
       const int64_t blocks = (int64_t)a.groups_x * g.ny * g.nzl;
       XB_LAUNCH(c, k_cap_push_tasks, (int)blocks, CAP2_THREADS, smem, g, a);
     }
+    if (have_particles) XB_LAUNCH(c, k_cap_current_from_fixed, grid_for(g.ntot), 256, 0, s.currI, g.ntot, unit, a.error);
     XB_CHECK(halo_reduce(c, s.currI, GZ, GZ));  // DMLocalToGlobal(ADD), particles.cpp:179
     const double one = 1.0;
     const double* vs[1] = {s.currI};
@@ -1030,6 +1070,7 @@ int cap_read_counters(xb_ctx* c)
   if (err == 2) XB_FAIL("eccapfim: a particle moved beyond the ghost planes of its slab within one step");
   if (err == 3) XB_FAIL("eccapfim: a particle crossed more cell faces in one step than the path splitter holds (CAP2_MAXSEG)");
   if (err == 4) XB_FAIL("eccapfim: a time-split sub-step ended inside the box (only the split at the box edge is supported)");
+  if (err == 5) XB_FAIL("eccapfim: the fixed-point current accumulators are close to their range (thousands of particles per node at twice the largest start-of-step speed)");
   if (err) XB_FAIL("eccapfim: particle pass failed with device error code " + std::to_string(err));
   double sums[2] = {(double)h[0], (double)h[1]};
   double n = (double)nl.particles_per_eval;
@@ -1059,6 +1100,30 @@ int cap_prepare(xb_ctx* c)
       if (c->g.nranks > 1) XB_CHECK(migrate_and_sort(c, s, 0.0));
       else XB_CHECK(particles_sort(c, s, 0.0));
     }
+  // Unit of the fixed-point current accumulators of every sort for this step: 2^-49 of (the power of two below
+  // |q n / Np|) x (the power of two above twice the largest velocity component at the start of the step).  An
+  // accumulator holds 2^12 such products before the range check where the tiles are flushed fires -- in units of
+  // particles per node: more than 8000 at the largest speed, typically ten times that.
+  {
+    unsigned long long* slot = reinterpret_cast<unsigned long long*>(c->red_out);
+    const size_t ns = c->sorts.size();
+    if (ns > (size_t)RED_MAXV) XB_FAIL("eccapfim: too many sorts");
+    XB_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned long long) * ns, c->stream));
+    for (size_t i = 0; i < ns; ++i) {
+      Species& s = c->sorts[i];
+      if (s.count > 0) XB_LAUNCH(c, k_cap_max_speed, RED_BLOCKS, 256, 0, s.count, s.p[s.cur][3], s.p[s.cur][4], s.p[s.cur][5], slot + i);
+    }
+    XB_CUDA(cudaMemcpyAsync(c->red_host, slot, sizeof(unsigned long long) * ns, cudaMemcpyDeviceToHost, c->stream));
+    XB_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < ns; ++i) {
+      Species& s = c->sorts[i];
+      double vmax;
+      std::memcpy(&vmax, reinterpret_cast<const char*>(c->red_host) + sizeof(double) * i, sizeof(double));
+      const double flux = std::fabs(s.q * (s.n / (double)s.Np));
+      const int ev = vmax > 0.0 ? std::ilogb(vmax) + 2 : 0;  // 2^ev > 2 vmax
+      s.cap_unit = flux > 0.0 ? std::ldexp(1.0, std::ilogb(flux) + ev - 49) : 1.0;
+    }
+  }
   c->nl.pn_valid = false;  // the first evaluation of a step starts every particle from (r0, v0)
   XB_CHECK(halo_fill(c, c->B, GZ));  // DMGlobalToLocal(B), simulation.cpp:64
   XB_CHECK(vec_copy_owned(c, c->E, c->cap_rhs0));
