@@ -10,6 +10,7 @@
 #include <cmath>
 #include <utility>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "operators.cuh"
 
@@ -79,30 +80,50 @@ static int cheb_apply(xb_ctx* c, int deg, const double* u, double* z, double* /*
   const int off = (3 - deg % 3) % 3;  // z_k lives in buf[(k + off) % 3]; z_deg in buf[0] = z
   XB_CHECK(scale_into(c, u, 1.0 / theta, buf[(1 + off) % 3]));  // z_1
   double rho_old = 1.0 / sigma;
-  auto step = [&](int k, double rho, int zl0, int nplanes) -> int {
+  auto step = [&](int k, double rho, int zl0, int nplanes, cudaStream_t st) -> int {
     double* zk = buf[(k + off) % 3];
     const double* zkm = k > 1 ? buf[(k - 1 + off) % 3] : nullptr;
     // (a shared-memory tiled form of this sweep was measured slower: 0.10 instead of 0.075 ms per sweep at 128^3 -- the
     // staging loop with its wrap arithmetic costs more than the cached stencil loads it replaces)
-    XB_LAUNCH(c, k_cheb_step, (int)((g.plane * nplanes + 255) / 256), 256, 0, g, zk, zkm, u, buf[(k + 1 + off) % 3], rho * rho_old, 2.0 * rho / delta, diag,
-              zl0, nplanes);
+    k_cheb_step<<<(int)((g.plane * nplanes + 255) / 256), 256, 0, st>>>(g, zk, zkm, u, buf[(k + 1 + off) % 3], rho * rho_old, 2.0 * rho / delta, diag, zl0,
+                                                                        nplanes);
+    c->launches++;
+    XB_CUDA(cudaGetLastError());
     return 0;
   };
-  // several slabs: the ghost planes of z_k travel while the planes that need none of them are swept (1 .. nzl - 2)
-  const bool split = g.nranks > 1 && g.nzl >= 4;
-  if (split && deg > 1) XB_CHECK(halo_begin(c, buf[(1 + off) % 3], 1));
+  // Several slabs: the two boundary planes of every sweep live on the exchange stream.  There the chain is
+  //   exchange ghosts of z_k -> sweep planes 0 and nzl - 1 of z_{k+1} -> exchange ghosts of z_{k+1} -> ...
+  // while the main stream sweeps the planes 1 .. nzl - 2, which read no ghost plane.  Two events per sweep tie the
+  // streams: the inner sweep k + 1 reads the boundary planes of z_{k+1} (halo_done), the boundary sweep k + 1 reads
+  // planes 1 and nzl - 2 of z_{k+1} (halo_ready).  Nothing of the exchange is left on the main stream.
+  const bool split = g.nranks > 1 && g.nzl >= 4 && deg > 1;
+  if (split) {
+    if (c->halo_pending) XB_FAIL("cheb_apply: an exchange is still pending");
+    if (!c->halo_ready) {
+      XB_CUDA(cudaEventCreateWithFlags(&c->halo_ready, cudaEventDisableTiming));
+      XB_CUDA(cudaEventCreateWithFlags(&c->halo_done, cudaEventDisableTiming));
+    }
+    XB_CUDA(cudaEventRecord(c->halo_ready, c->stream));  // z_1 is complete
+    XB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->halo_ready, 0));
+    XB_CHECK(comm_halo_fill(c, buf[(1 + off) % 3], 1, c->copy_stream));
+  }
   for (int k = 1; k < deg; ++k) {  // z_{k+1} from z_k, z_{k-1}
     const double rho = 1.0 / (2.0 * sigma - rho_old);
     if (split) {
-      XB_CHECK(step(k, rho, 1, g.nzl - 2));
-      XB_CHECK(halo_end(c));
-      XB_CHECK(step(k, rho, 0, 1));
-      XB_CHECK(step(k, rho, g.nzl - 1, 1));
-      if (k + 1 < deg) XB_CHECK(halo_begin(c, buf[(k + 1 + off) % 3], 1));
+      XB_CHECK(step(k, rho, 1, g.nzl - 2, c->stream));
+      XB_CUDA(cudaEventRecord(c->halo_ready, c->stream));
+      XB_CHECK(step(k, rho, 0, 1, c->copy_stream));
+      XB_CHECK(step(k, rho, g.nzl - 1, 1, c->copy_stream));
+      XB_CUDA(cudaEventRecord(c->halo_done, c->copy_stream));
+      XB_CUDA(cudaStreamWaitEvent(c->stream, c->halo_done, 0));  // the next inner sweep reads (and later overwrites) these planes
+      if (k + 1 < deg) {
+        XB_CHECK(comm_halo_fill(c, buf[(k + 1 + off) % 3], 1, c->copy_stream));  // its boundary planes were just written on this stream
+        XB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->halo_ready, 0));         // the next boundary sweep reads planes 1, nzl - 2 of z_{k+1}
+      }
     }
     else {
       XB_CHECK(halo_fill(c, buf[(k + off) % 3], 1));
-      XB_CHECK(step(k, rho, 0, g.nzl));
+      XB_CHECK(step(k, rho, 0, g.nzl, c->stream));
     }
     rho_old = rho;
   }
