@@ -91,6 +91,21 @@ struct Lane {
 
 __device__ __forceinline__ const double2& ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
+// Row order of the 12 x 12 slots inside the shared-memory cell block.  A quarter warp of a 128-bit fold holds the two
+// rows p, p + 1 (corner bit i) of four column chunks: with the rows in natural order they are 96 bytes apart and hit
+// eight banks twice.  The order p -> 2 p (p < 6), 2 (p - 6) + 1 puts
+// p and p + 1 two rows = 192 bytes apart (p = 5, 6 never form a pair: block_pos), i.e. on disjoint halves of the banks.
+// The write-out walks the block in this physical order and un-permutes the staging address.
+__device__ __forceinline__ constexpr int smem_row(int p) { return p < 6 ? 2 * p : 2 * (p - 6) + 1; }
+__device__ __forceinline__ constexpr int slot_row(int r) { return (r & 1) ? 6 + (r >> 1) : (r >> 1); }
+// staging entry of the element at physical index f of a cell block
+__device__ __forceinline__ int staged_entry(int f)
+{
+  if (f >= BLOCK_MAT) return f;  // the 36 current partials are not permuted
+  const int sl = f / 144, rem = f - sl * 144, r = rem / 12, p2 = rem - r * 12;
+  return sl * 144 + slot_row(r) * 12 + p2;
+}
+
 // all groups of four particles of one octant segment: cnt particles whose records start at r0
 template <int OXY>
 __device__ __forceinline__ void octant_segment(const double* __restrict__ r0, const double* __restrict__ zero_rec, int cnt, const Lane& L,
@@ -140,7 +155,7 @@ __device__ __forceinline__ void fold(double* __restrict__ block, const Lane& L, 
       if (dep(sl, 2) != ZDEP || v >= nvar(sl)) continue;
       const int c1 = sl / 3, c2 = sl % 3;
       const int o1 = vbit(sl, v, c1, OZ), o2 = vbit(sl, v, c2, OZ);
-      double* e = block + sl * 144 + (L.rowpos[c1] + o1 * st[c1]) * 12 + L.colpos[c2] + o2 * st[c2];
+      double* e = block + sl * 144 + smem_row(L.rowpos[c1] + o1 * st[c1]) * 12 + L.colpos[c2] + o2 * st[c2];
       const int k = vbase(sl) + v;
       if (c2 == 0) {  // columns 2 q, 2 q + 1 are adjacent but not 16-byte aligned when ox = 1
         e[0] += acc[k][0];
@@ -381,7 +396,7 @@ __global__ void __launch_bounds__(FM_THREADS, MINB) k_cell_moments(Grid g, Depos
         v[w] = smem[(size_t)w * FM_CELL + e];
         smem[(size_t)w * FM_CELL + e] = 0.0;
       }
-      double2* o2 = reinterpret_cast<double2*>(out + (size_t)e * CELL_GROUP);
+      double2* o2 = reinterpret_cast<double2*>(out + (size_t)staged_entry(e) * CELL_GROUP);
       o2[0] = make_double2(v[0], v[1]);
       o2[1] = make_double2(v[2], v[3]);
     }
@@ -675,7 +690,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
         v[w] = smem[(size_t)w * WS_CELL + e];
         smem[(size_t)w * WS_CELL + e] = 0.0;
       }
-      double2* o2 = reinterpret_cast<double2*>(out + (size_t)e * CELL_GROUP);
+      double2* o2 = reinterpret_cast<double2*>(out + (size_t)staged_entry(e) * CELL_GROUP);
       o2[0] = make_double2(v[0], v[1]);
       o2[1] = make_double2(v[2], v[3]);
     }
