@@ -412,6 +412,8 @@ int xb_destroy(xb_ctx* c)
   if (c->copy_done) cudaEventDestroy(c->copy_done);
   if (c->b_ready) cudaEventDestroy(c->b_ready);
   if (c->host_stream) cudaStreamDestroy(c->host_stream);
+  if (c->blocks_ready) cudaEventDestroy(c->blocks_ready);
+  if (c->blocks_here) cudaEventDestroy(c->blocks_here);
   if (c->halo_ready) cudaEventDestroy(c->halo_ready);
   if (c->halo_done) cudaEventDestroy(c->halo_done);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -582,22 +584,38 @@ int xb_step_host(xb_ctx* c, int32_t scheme, double* E, double* B, const double* 
     if (B0) XB_CHECK(upload_owned(c, B0, c->B0));
   }
   int rc = ensure_sorted(c);
+  bool sent_early = false;
   for (int st = 0; st < XB_STAGE_COUNT && !rc; ++st) {
     if (overlap && st == XB_STAGE_ADVANCE_FIELDS) XB_CUDA(cudaStreamWaitEvent(c->stream, c->copy_done, 0));
     rc = run_stage(c, scheme, st);
+    if (!rc && scheme == XB_ECSIM && st == XB_STAGE_ADVANCE_FIELDS) {
+      // ecsim: E^{n+1} and B^{n+1} follow from E^{n+1/2} alone (ecsim/simulation.cpp:247-248).  They are formed in scratch
+      // vectors right after the solve and go home underneath the second push, which still reads B^n; the final stage
+      // forms them again in place (same kernel, same bits).
+      rc = final_update_into(c, c->Ep, c->tmp, c->tmp2);
+      if (!rc) {
+        XB_CUDA(cudaEventRecord(c->copy_done, c->stream));
+        XB_CUDA(cudaStreamWaitEvent(c->host_stream, c->copy_done, 0));
+        XB_CUDA(cudaMemcpyAsync(E, c->tmp + g.own0, sizeof(double) * g.nown, cudaMemcpyDeviceToHost, c->host_stream));
+        XB_CUDA(cudaMemcpyAsync(B, c->tmp2 + g.own0, sizeof(double) * g.nown, cudaMemcpyDeviceToHost, c->host_stream));
+        sent_early = true;
+      }
+    }
   }
   if (c->b_pending) {  // an error before the deposition: nothing may be left waiting for the next call
     c->b_pending = false;
     cudaStreamSynchronize(c->host_stream);
   }
   if (rc) return rc;
-  // E goes home on the second stream while the kinetic energies are reduced and B follows on the first
-  XB_CUDA(cudaEventRecord(c->copy_done, c->stream));
-  XB_CUDA(cudaStreamWaitEvent(c->host_stream, c->copy_done, 0));
-  XB_CUDA(cudaMemcpyAsync(E, c->E + g.own0, sizeof(double) * g.nown, cudaMemcpyDeviceToHost, c->host_stream));
+  // (other schemes) E goes home on the second stream while the kinetic energies are reduced and B follows on the first
+  if (!sent_early) {
+    XB_CUDA(cudaEventRecord(c->copy_done, c->stream));
+    XB_CUDA(cudaStreamWaitEvent(c->host_stream, c->copy_done, 0));
+    XB_CUDA(cudaMemcpyAsync(E, c->E + g.own0, sizeof(double) * g.nown, cudaMemcpyDeviceToHost, c->host_stream));
+  }
   if (kinetic)
     for (size_t i = 0; i < c->sorts.size(); ++i) XB_CHECK(kinetic_energy(c, c->sorts[i], nullptr, &kinetic[i]));
-  XB_CHECK(download_owned(c, c->B, B));
+  if (!sent_early) XB_CHECK(download_owned(c, c->B, B));
   XB_CUDA(cudaStreamSynchronize(c->host_stream));
   XB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

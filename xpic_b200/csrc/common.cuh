@@ -174,6 +174,7 @@ struct xb_ctx {
   cudaEvent_t b_ready = nullptr;       // xb_step_host: B^n has arrived (awaited before the moment deposition)
   bool b_pending = false;
   cudaEvent_t halo_ready = nullptr, halo_done = nullptr;  // halo_begin / halo_end
+  cudaEvent_t blocks_ready = nullptr, blocks_here = nullptr;  // exchange of the boundary planes' cell blocks (deposit.cu)
   bool halo_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // CUDA-event pairs (start, stop) recorded around every launch group of a kernel family inside the step
@@ -244,6 +245,7 @@ int vec_copy_owned(xb_ctx* c, const double* src, double* dst);
 int curl_apply(xb_ctx* c, bool positive, const double* f, double* out, double scale, bool accumulate);
 int build_rhs(xb_ctx* c, const double* curr, double* rhs);       // 2E - dt curr + dt curl^-(B - B0)
 int final_update(xb_ctx* c, const double* Ehalf);                // E = 2 Eh - E ; B -= dt curl^+ Eh
+int final_update_into(xb_ctx* c, const double* Ehalf, double* Eout, double* Bout);
 int dots(xb_ctx* c, int nv, const double* const* vs, const double* w, double* host_out);  // host_out[i] = vs[i].w
 int field_sums(xb_ctx* c, const double* v, double* out4);  // component sums and sum of squares, all ranks
 int axpy_multi(xb_ctx* c, int nv, const double* const* vs, const double* coef_host, double* w);  // w += sum coef_i vs_i

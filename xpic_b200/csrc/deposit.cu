@@ -19,6 +19,7 @@
 //
 // Roofline: pass 1 is FP64-FMA bound (576 FMA per particle), pass 2 HBM bound
 // (1332 * 8 B read + 369 * 8 B written per cell).
+#include "comm.cuh"
 #include "common.cuh"
 #include "deposit.cuh"
 #include "gather.cuh"
@@ -652,6 +653,27 @@ static int gather_rows_of(xb_ctx* c, Species& s, const GatherArgs& ga, int acc)
   return 0;
 }
 
+// My boundary planes' cell blocks -> the ghost planes of the z neighbours' staging areas (staging plane = zl + 1), on the
+// exchange stream; no neighbour across an open box end (those staging planes are never read: stage_cell).
+static int boundary_blocks_begin(xb_ctx* c)
+{
+  const Grid& g = c->g;
+  if (!c->blocks_ready) {
+    XB_CUDA(cudaEventCreateWithFlags(&c->blocks_ready, cudaEventDisableTiming));
+    XB_CUDA(cudaEventCreateWithFlags(&c->blocks_here, cudaEventDisableTiming));
+  }
+  XB_CUDA(cudaEventRecord(c->blocks_ready, c->stream));
+  XB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->blocks_ready, 0));
+  const size_t per_plane = (size_t)g.plane * BLOCK_ALL;  // doubles; g.plane is a multiple of CELL_GROUP (deposit_cells checks)
+  auto plane = [&](int sp) { return c->stage + (size_t)sp * per_plane; };
+  const bool down = !(g.open_z && g.rank == 0), up = !(g.open_z && g.rank == g.nranks - 1);
+  const size_t bytes = sizeof(double) * per_plane;
+  XB_CHECK(comm_exchange(c, plane(1), down ? bytes : 0, plane(g.nzl), up ? bytes : 0, plane(g.nzl + 1), up ? bytes : 0, plane(0), down ? bytes : 0,
+                         c->copy_stream));
+  XB_CUDA(cudaEventRecord(c->blocks_here, c->copy_stream));
+  return 0;
+}
+
 int deposit_moments(xb_ctx* c)
 {
   const Grid& g = c->g;
@@ -661,37 +683,49 @@ int deposit_moments(xb_ctx* c)
   for (auto& s : c->sorts) {
     if (!s.sorted) XB_FAIL("deposit: particles are not sorted");
     const int acc = first ? 0 : 1;
-    if (!single) XB_CHECK(ghost_exchange_mark(c, s));
-    if (c->batch_planes == 0) {
-      // ---- the staging area holds the cell blocks of the whole slab ---------------------------------------------
+    if (c->batch_planes == 0 && single) {
+      // ---- one GPU, the staging area holds the cell blocks of the whole box: one launch, the gather wraps in z ------
       XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_CELLS));
-      // Several slabs: the owned planes go in eight launches instead of one.  The kernel is persistent (one wave of CTAs
-      // that own their SMs until the launch ends); NCCL's kernels of the ghost exchange, which wait on the high-priority
-      // copy stream, get SMs where a wave ends: the count table after the first launch, the payloads after the second.
-      // The dynamic work distribution of the kernel absorbs the SMs NCCL holds meanwhile.
-      const int chunk = single ? g.nzl : (g.nzl + 7) / 8;
-      for (int p0 = 0; p0 < g.nzl; p0 += chunk) {
-        const int np = chunk < g.nzl - p0 ? chunk : g.nzl - p0;
-        XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane * (1 + p0), g.plane * np, single ? g.plane * p0 : g.plane * (1 + p0), 0, &s.rec,
-                               s.capacity, s.count, p0));
-      }
+      XB_CHECK(deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane, g.ncl, 0, 0, &s.rec, s.capacity, s.count, 0));
       XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_CELLS));
-      if (!single) {
-        // the boundary-plane particles of the z neighbours travel (copy stream) while the owned planes are computed
-        XB_CHECK(ghost_exchange_begin(c, s));
-        XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_GHOST));
-        XB_CHECK(deposit_ghost_cells(c, s, 0, (int64_t)(g.nzl + 1) * g.plane, true, true));
-        XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_GHOST));
-      }
       XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_ROWS));
-      XB_CHECK(gather_rows_of(c, s, GatherArgs{c->stage, single ? 1 : 0, -1, 0, g.nzl}, acc));
+      XB_CHECK(gather_rows_of(c, s, GatherArgs{c->stage, 1, -1, 0, g.nzl}, acc));
+      XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_ROWS));
+    }
+    else if (c->batch_planes == 0) {
+      // ---- several slabs, the staging area holds the slab's planes plus one ghost plane on either side.  Every cell
+      // block is computed once, by its owner: the two boundary planes go first and their blocks (10.6 KB per cell, 0.7 GB
+      // per plane of 256 x 256 cells) travel to the z neighbours on the exchange stream while the other planes are
+      // computed.  (Round 1 and the batched mode below fetch the neighbours' boundary PARTICLES instead and compute the
+      // ghost planes again: 2 / nzl more cell blocks and last-bit differences across the periodic boundary.)
+      // The kernel is persistent (one wave of CTAs that own their SMs until the launch ends): the inner planes go in
+      // four launches so that NCCL's kernels, waiting on the high-priority stream, get their SMs at the latest where the
+      // first of them ends; the dynamic work distribution of the kernel absorbs the SMs NCCL holds meanwhile.
+      auto planes = [&](int p0, int np) -> int {
+        return deposit_cells(c, s, s.p[s.cur], s.bin_start, g.plane * (1 + p0), g.plane * np, g.plane * (1 + p0), 0, &s.rec, s.capacity, s.count, p0);
+      };
+      XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_CELLS));
+      XB_CHECK(planes(0, 1));
+      if (g.nzl > 1) XB_CHECK(planes(g.nzl - 1, 1));
+      XB_CHECK(boundary_blocks_begin(c));
+      const int inner = g.nzl - 2, chunk = (inner + 3) / 4;
+      for (int p0 = 1; p0 < g.nzl - 1; p0 += chunk) XB_CHECK(planes(p0, chunk < g.nzl - 1 - p0 ? chunk : g.nzl - 1 - p0));
+      XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_CELLS));
+      XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_GHOST));  // what is left of the exchange after the inner planes
+      XB_CUDA(cudaStreamWaitEvent(c->stream, c->blocks_here, 0));
+      XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_GHOST));
+      XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_ROWS));
+      XB_CHECK(gather_rows_of(c, s, GatherArgs{c->stage, 0, -1, 0, g.nzl}, acc));
       XB_CHECK(prof_end(c, XB_FAMILY_MOMENTS_ROWS));
     }
     else {
       // ---- large slabs: batches of P planes through a staging area of P + 2 planes (xb_create chose P so that it
       // fits the budget): staging plane 0 = the plane below the batch, 1 .. np = the batch, np + 1 = the plane above.
       // The two neighbour planes of a batch are computed again with the next / previous batch (2 / P more cell blocks).
-      if (!single) XB_CHECK(ghost_exchange_begin(c, s));
+      if (!single) {
+        XB_CHECK(ghost_exchange_mark(c, s));
+        XB_CHECK(ghost_exchange_begin(c, s));
+      }
       for (int p0 = 0; p0 < g.nzl; p0 += c->batch_planes) {
         const int np = c->batch_planes < g.nzl - p0 ? c->batch_planes : g.nzl - p0;
         XB_CHECK(prof_begin(c, XB_FAMILY_MOMENTS_CELLS));

@@ -227,7 +227,7 @@ int build_rhs(xb_ctx* c, const double* curr, double* rhs)
 }
 
 // E^{n+1} = 2 E^{n+1/2} - E^n ;  B^{n+1} = B^n - dt curl^+ E^{n+1/2}   (ecsim/simulation.cpp:247-248)
-__global__ void k_final_update(Grid g, const double* __restrict__ Eh, double* __restrict__ E, double* __restrict__ B)
+__global__ void k_final_update(Grid g, const double* __restrict__ Eh, const double* E, const double* B, double* Eout, double* Bout)
 {
   XB_NODE_LOOP(g, node, x, y, zl)
   {
@@ -237,21 +237,25 @@ __global__ void k_final_update(Grid g, const double* __restrict__ Eh, double* __
     double cx, cy, cz;
     curl_node(g, true, fetch, cx, cy, cz);
     const int64_t o = g.vidx(x, y, zl, 0);
-    E[o + 0] = 2.0 * Eh[o + 0] + (-1.0) * E[o + 0];
-    E[o + 1] = 2.0 * Eh[o + 1] + (-1.0) * E[o + 1];
-    E[o + 2] = 2.0 * Eh[o + 2] + (-1.0) * E[o + 2];
-    B[o + 0] += (-g.dt) * cx;
-    B[o + 1] += (-g.dt) * cy;
-    B[o + 2] += (-g.dt) * cz;
+    Eout[o + 0] = 2.0 * Eh[o + 0] + (-1.0) * E[o + 0];
+    Eout[o + 1] = 2.0 * Eh[o + 1] + (-1.0) * E[o + 1];
+    Eout[o + 2] = 2.0 * Eh[o + 2] + (-1.0) * E[o + 2];
+    Bout[o + 0] = B[o + 0] + (-g.dt) * cx;
+    Bout[o + 1] = B[o + 1] + (-g.dt) * cy;
+    Bout[o + 2] = B[o + 2] + (-g.dt) * cz;
   }
 }
 
-int final_update(xb_ctx* c, const double* Ehalf)
+// E^{n+1}, B^{n+1} into other vectors (E and B themselves stay as they are): xb_step_host sends the new fields home
+// while the second push still reads B^n
+int final_update_into(xb_ctx* c, const double* Ehalf, double* Eout, double* Bout)
 {
   XB_CHECK(halo_fill(c, const_cast<double*>(Ehalf), 1));
-  XB_LAUNCH(c, k_final_update, grid_for(c->g.ncl), 256, 0, c->g, Ehalf, c->E, c->B);
+  XB_LAUNCH(c, k_final_update, grid_for(c->g.ncl), 256, 0, c->g, Ehalf, c->E, c->B, Eout, Bout);
   return 0;
 }
+
+int final_update(xb_ctx* c, const double* Ehalf) { return final_update_into(c, Ehalf, c->E, c->B); }
 
 // ---------------------------------------------------------------------------------------------
 // FieldsDamping (src/commands/fields_damping.cpp:16-112): a node whose cell centre lies outside the geometry has E and
