@@ -1,9 +1,8 @@
 set -x
-python bench.py --scheme eccapfim --steps 3 --warmup 3 --no-extra > gpurun_out/r02_bench_eccapfim_n1.json 2> gpurun_out/r02_bench_eccapfim_n1.err; python - <<'P'
+python -m pytest tests/test_gpu_eccapfim.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -4
+python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_n1j.json 2> gpurun_out/r02_bench_n1j.err; python - <<'P'
 import json
-d=json.loads([l for l in open('gpurun_out/r02_bench_eccapfim_n1.json') if l.startswith('{')][0])
-print(d['ms_per_step'], d.get('e2e',{}).get('ms_per_step'))
-print(d.get('roofline')); print(d.get('kernels')); print(d['config'])
+d=json.loads([l for l in open('gpurun_out/r02_bench_n1j.json') if l.startswith('{')][0])
+print(d['ms_per_step'], d['e2e']['ms_per_step'], {k:v['ms_per_step'] for k,v in d['other_configs'].items()})
+for k in d['kernels']: print(k['name'][:50], round(k['ms'],2), round(k.get('frac',0),3))
 P
-XPIC_SCHEME=eccapfim XPIC_BENCH_GRID=192,192,24 XPIC_BENCH_PPC=32 XPIC_PROFILE_RANGE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'k_cap_push_tasks' -c 2 -f -o gpurun_out/r02_cap_push python tools/profile_step.py 1 > gpurun_out/r02_ncu4.log 2>&1
-tail -3 gpurun_out/r02_ncu4.log

@@ -176,13 +176,22 @@ __device__ __forceinline__ void cap_weights(const Grid& g, const double* rn, con
 // threads, warps and CTAs arrive -- two runs are bit-identical -- and the additions need no compare-and-swap spin
 // (sm_100a has no native 64-bit shared atomic, fp64 or integer).  One entry of the shared tile is two 32-bit
 // words updated with native 32-bit atomics: the low word reports its carry through the value it returns.
-__device__ __forceinline__ void shared_add_fixed(unsigned addr, long long x)
+// lo / hi: shared-memory byte addresses of the entry's two words.  The low words of a tile are one array, the high
+// words another one behind it (HI_OFFSET bytes): consecutive entries are consecutive banks for both.
+__device__ __forceinline__ void shared_add_fixed(unsigned lo_addr, unsigned hi_addr, long long x)
 {
   const unsigned lo = (unsigned)x;
   unsigned old;
-  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(lo) : "memory");
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(lo_addr), "r"(lo) : "memory");
   const int hi = (int)(x >> 32) + ((old + lo) < old ? 1 : 0);
-  if (hi != 0) asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr + 4u), "r"(hi) : "memory");
+  if (hi != 0) asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(hi_addr), "r"(hi) : "memory");
+}
+
+// entry e of a tile of n entries kept as n low words followed by n high words
+__device__ __forceinline__ long long tile_entry_fixed(const double* tile, int n, int e)
+{
+  const unsigned* w = reinterpret_cast<const unsigned*>(tile);
+  return (long long)(((unsigned long long)w[n + e] << 32) | (unsigned long long)w[e]);
 }
 
 __device__ __forceinline__ void global_add_fixed(double* entry, long long x)
@@ -194,7 +203,7 @@ template <bool FAST, bool DEPOSIT, class K>
 __device__ __forceinline__ void cap_apply(const K& k, const CapW& w, double* Ep, double alpha, const double* v)
 {
   const int base = FAST ? k.tile_base(w.start) : 0;
-  const unsigned jaddr = (FAST && DEPOSIT) ? (unsigned)__cvta_generic_to_shared(k.Jt) + 8u * (unsigned)base : 0u;
+  const unsigned jaddr = (FAST && DEPOSIT) ? (unsigned)__cvta_generic_to_shared(k.Jt) + 4u * (unsigned)base : 0u;
 #pragma unroll
   for (int cx = 0; cx < 3; ++cx) {
     const int cy = (cx + 1) % 3, cz = (cx + 2) % 3;
@@ -219,7 +228,7 @@ __device__ __forceinline__ void cap_apply(const K& k, const CapW& w, double* Ep,
           if (FAST) {
             const int e = cx * K::VOL + base + (d[2] * K::NY + d[1]) * K::NX + d[0];
             if (DEPOSIT)
-              shared_add_fixed(jaddr + 8u * (unsigned)(e - base), __double2ll_rn(av * wt));
+              shared_add_fixed(jaddr + 4u * (unsigned)(e - base), jaddr + 4u * (unsigned)(e - base + 3 * K::VOL), __double2ll_rn(av * wt));
             else
               acc += k.Et[e] * wt;
           }
@@ -561,7 +570,7 @@ __global__ void __launch_bounds__(CAP_THREADS) k_cap_push(Grid g, CapArgs a)
   if (threadIdx.x < 2 && cnt[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], cnt[threadIdx.x]);
   // flush the current tile: one reduction per touched node instead of 54 per particle segment
   for (int e = threadIdx.x; e < 3 * CAP_VOL; e += CAP_THREADS) {
-    const long long val = reinterpret_cast<const long long*>(Jt)[e];
+    const long long val = tile_entry_fixed(Jt, 3 * CAP_VOL, e);
     if (val == 0) continue;
     if (llabs(val) >> 61) *a.error = 5;  // within a factor 4 of the accumulator range
     const int x = e % CAP_NX, y = (e / CAP_NX) % CAP_NY, z = (e / (CAP_NX * CAP_NY)) % CAP_NZ, c = e / CAP_VOL;
@@ -913,7 +922,7 @@ __global__ void __launch_bounds__(CAP2_THREADS, 2) k_cap_push_tasks(Grid g, CapA
   __syncthreads();
   if (tid < 2 && cnt[tid]) atomicAdd(&a.counters[tid], cnt[tid]);
   for (int e = tid; e < VOL3; e += CAP2_THREADS) {
-    const long long val = reinterpret_cast<const long long*>(Jt)[e];
+    const long long val = tile_entry_fixed(Jt, VOL3, e);
     if (val == 0) continue;
     if (llabs(val) >> 61) *a.error = 5;  // within a factor 4 of the accumulator range
     const int x = e % CapCtx2::NX, y = (e / CapCtx2::NX) % CapCtx2::NY, z = (e / (CapCtx2::NX * CapCtx2::NY)) % CapCtx2::NZ, c = e / CapCtx2::VOL;
