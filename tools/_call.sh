@@ -1,8 +1,6 @@
 set -x
-python -m pytest tests/test_gpu_eccapfim.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -4
-python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_n1j.json 2> gpurun_out/r02_bench_n1j.err; python - <<'P'
-import json
-d=json.loads([l for l in open('gpurun_out/r02_bench_n1j.json') if l.startswith('{')][0])
-print(d['ms_per_step'], d['e2e']['ms_per_step'], {k:v['ms_per_step'] for k,v in d['other_configs'].items()})
-for k in d['kernels']: print(k['name'][:50], round(k['ms'],2), round(k.get('frac',0),3))
-P
+XPIC_PROFILE_RANGE=1 python tools/profile_step.py 2 > gpurun_out/r02_plain5.log 2>&1 || exit 1
+tail -1 gpurun_out/r02_plain5.log
+XPIC_PROFILE_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_128x64.csv python tools/profile_step.py 2 > gpurun_out/r02_ncu5.log 2>&1
+tail -2 gpurun_out/r02_ncu5.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
