@@ -1,6 +1,11 @@
 set -x
-XPIC_PROFILE_RANGE=1 python tools/profile_step.py 2 > gpurun_out/r02_plain5.log 2>&1 || exit 1
-tail -1 gpurun_out/r02_plain5.log
-XPIC_PROFILE_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_128x64.csv python tools/profile_step.py 2 > gpurun_out/r02_ncu5.log 2>&1
-tail -2 gpurun_out/r02_ncu5.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench_ecsim_n8.json 2> gpurun_out/r02_bench_n8.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 4 --steps 10 --warmup 3 --no-extra > gpurun_out/r02_bench_ecsim_n4.json 2> gpurun_out/r02_bench_n4.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29543 tests/multi_gpu_check.py > gpurun_out/r02_multi_gpu_check_n8.log 2>&1
+tail -6 gpurun_out/r02_multi_gpu_check_n8.log
+python - <<'P'
+import json
+for f in ('gpurun_out/r02_bench_ecsim_n8.json','gpurun_out/r02_bench_ecsim_n4.json'):
+    d=json.loads([l for l in open(f) if l.startswith('{')][0])
+    print(d['n_gpus'], d['ms_per_step'], d['e2e']['ms_per_step'], {k:v['ms_per_step'] for k,v in (d.get('other_configs') or {}).items()})
+P

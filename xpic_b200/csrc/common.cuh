@@ -134,6 +134,7 @@ struct Species {
   int64_t count = 0, capacity = 0;
   int cur = 0;                    // which of the two SoA buffers is live
   double* p[2][6] = {{nullptr}};  // x,y,z,vx,vy,vz
+  double* p_alloc[2][6] = {{nullptr}};  // what cudaMalloc returned (p is skewed, species_alloc)
   uint64_t* id[2] = {nullptr, nullptr};
   int32_t* key = nullptr;        // bin of every particle (capacity)
   double* rec = nullptr;         // field record of every particle, SoA [12][capacity]: cross-check pipeline only, allocated on first use (deposit.cu)

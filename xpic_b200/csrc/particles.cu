@@ -24,11 +24,20 @@ static inline int grid_for(int64_t n, int threads = 256)
   return (int)b;
 }
 
+constexpr int64_t PARTICLE_SKEW = 33 * 32;  // doubles: 33 x 256 bytes
+
 int species_alloc(xb_ctx* c, Species& s, int64_t capacity)
 {
   s.capacity = capacity;
   for (int b = 0; b < 2; ++b) {
-    for (int k = 0; k < 6; ++k) XB_CUDA(cudaMalloc(&s.p[b][k], sizeof(double) * capacity));
+    for (int k = 0; k < 6; ++k) {
+      // The kernels stream the same index of up to thirteen arrays at once.  cudaMalloc hands out bases that are equal
+      // modulo 2 MB: every array gets its own offset (an odd multiple of 256 B per array) so that the streams do not
+      // walk the DRAM channels in lockstep.
+      const int64_t skew = (int64_t)(b * 6 + k) * PARTICLE_SKEW;
+      XB_CUDA(cudaMalloc(&s.p_alloc[b][k], sizeof(double) * (capacity + 12 * PARTICLE_SKEW)));
+      s.p[b][k] = s.p_alloc[b][k] + skew;
+    }
     if (c->track_ids) XB_CUDA(cudaMalloc(&s.id[b], sizeof(uint64_t) * capacity));
   }
   XB_CUDA(cudaMalloc(&s.key, sizeof(int32_t) * capacity));
@@ -44,7 +53,7 @@ int species_alloc(xb_ctx* c, Species& s, int64_t capacity)
 void species_free(Species& s)
 {
   for (int b = 0; b < 2; ++b) {
-    for (int k = 0; k < 6; ++k) cudaFree(s.p[b][k]);
+    for (int k = 0; k < 6; ++k) cudaFree(s.p_alloc[b][k]);
     cudaFree(s.id[b]);
   }
   cudaFree(s.key);
