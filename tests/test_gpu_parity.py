@@ -71,7 +71,7 @@ def test_deposit_scalar_and_tensor_core_kernels_agree(X):
     o, s = make_pair(n=(9, 8, 7), Np=37, seed_fields=15)
     o.deposit()
     ref = csr_to_stencil(o, X.coef_table())
-    for variant in (0, 1):  # 0: DMMA cell blocks, 1: scalar FMA cell blocks
+    for variant in (0, 4, 1):  # 0: DMMA variant tiles, 4: DMMA cell blocks folded in shared memory, 1: scalar FMA cell blocks
         s.set_option(0, variant)
         s.deposit()
         assert np.max(np.abs(s.operator_download() - ref)) / np.max(np.abs(ref)) < 1e-13, variant
@@ -490,7 +490,7 @@ def _sorted_rows(pts):
     return pts[np.lexsort(pts.T[::-1])]
 
 
-@pytest.mark.parametrize("variant", [0, 3, 2])
+@pytest.mark.parametrize("variant", [0, 4, 3, 2])
 def test_deposit_variants_at_tiling_size(X, variant):
     """40 x 20 x 12 cells: wider than the SpMV tile (32), the push tiles (16) and not a multiple of either, so
     CTAs own full tiles and partial ones, x-neighbour tiles exist.  Every moment kernel against the oracle's CSR."""
@@ -553,7 +553,7 @@ def test_deposit_with_cell_sizes_that_are_not_powers_of_two(X):
     o, s = make_pair(n=(11, 9, 7), Np=30, seed_fields=41, d=(0.3, 0.45, 0.7), dt=0.8)
     o.deposit()
     ref = csr_to_stencil(o, X.coef_table())
-    for variant in (0, 2, 1):
+    for variant in (0, 4, 2, 1):
         s.set_option(0, variant)
         s.deposit()
         assert np.max(np.abs(s.operator_download() - ref)) / np.max(np.abs(ref)) < 1e-13, variant
@@ -583,7 +583,7 @@ def test_deposit_many_particles_per_cell_and_empty_cells(X):
     s.set_field("B", f)
     o.deposit()
     ref = csr_to_stencil(o, X.coef_table())
-    for variant in (0, 3, 2):
+    for variant in (0, 4, 3, 2):
         s.set_option(0, variant)
         s.deposit()
         assert np.max(np.abs(s.operator_download() - ref)) / np.max(np.abs(ref)) < 1e-13, variant
@@ -808,7 +808,7 @@ def test_batched_staging_equals_whole_slab_staging(X, open_z, monkeypatch):
         return s
 
     whole, batched = build(None), build("6.2e-3")  # 6 planes of 12 x 8 cells x 10.6 KB: batches of 4, 4, 2 planes
-    for variant in (0, 3, 2):
+    for variant in (0, 4, 3, 2):
         res = []
         for s in (whole, batched):
             s.set_option(0, variant)

@@ -1,11 +1,6 @@
 set -x
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench_ecsim_n8.json 2> gpurun_out/r02_bench_n8.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 4 --steps 10 --warmup 3 --no-extra > gpurun_out/r02_bench_ecsim_n4.json 2> gpurun_out/r02_bench_n4.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29543 tests/multi_gpu_check.py > gpurun_out/r02_multi_gpu_check_n8.log 2>&1
-tail -6 gpurun_out/r02_multi_gpu_check_n8.log
-python - <<'P'
-import json
-for f in ('gpurun_out/r02_bench_ecsim_n8.json','gpurun_out/r02_bench_ecsim_n4.json'):
-    d=json.loads([l for l in open(f) if l.startswith('{')][0])
-    print(d['n_gpus'], d['ms_per_step'], d['e2e']['ms_per_step'], {k:v['ms_per_step'] for k,v in (d.get('other_configs') or {}).items()})
-P
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "deposit or batched or staging" 2>&1 | tail -15
+XPIC_DEPOSIT_VARIANTS=0,4 python tools/profile_deposit.py > gpurun_out/prof_tiles.json 2> gpurun_out/prof_tiles.err
+cat gpurun_out/prof_tiles.json
+XPIC_WS_PROF=1 XPIC_DEPOSIT_VARIANTS=0 python tools/profile_deposit.py > gpurun_out/prof_ws.json 2> gpurun_out/prof_ws.err
+tail -3 gpurun_out/prof_ws.err

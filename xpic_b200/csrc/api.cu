@@ -330,12 +330,12 @@ static int create_impl(xb_ctx* c, const xb_grid* gr, const void* uid)
   XB_CUDA(cudaMemset(c->coef, 0, sizeof(double) * c->coef_elems));
   c->stage_cells = g.nranks == 1 ? g.ncl : (g.nzl + 2) * g.plane;
   {
-    // 10.6 KB of cell-block staging per cell: the whole slab when that stays inside the budget (72 GB of the 180 GB,
+    // 15.9 KB of variant-tile staging per cell (the folded cell blocks of the cross-check variants need 10.6 KB): the whole slab when that stays inside the budget (72 GB of the 180 GB,
     // XPIC_STAGE_GB overrides), else batches of P planes through P + 2 staging planes (deposit_moments)
     const char* env = std::getenv("XPIC_STAGE_GB");
     const double budget = (env && *env ? std::atof(env) : 72.0) * 1e9;
-    const double per_plane = (double)g.plane * BLOCK_ALL * sizeof(double);
-    if ((double)c->stage_cells * BLOCK_ALL * sizeof(double) > budget) {
+    const double per_plane = (double)g.plane * STAGE_CELL * sizeof(double);
+    if ((double)c->stage_cells * STAGE_CELL * sizeof(double) > budget) {
       const int P = (int)(budget / per_plane) - 2;
       if (P < 1) XB_FAIL("xb_create: one plane of cell blocks does not fit the staging budget (XPIC_STAGE_GB)");
       if ((g.plane % CELL_GROUP) != 0) XB_FAIL("xb_create: batched staging needs nx * ny to be a multiple of 4");
@@ -344,8 +344,8 @@ static int create_impl(xb_ctx* c, const xb_grid* gr, const void* uid)
     }
   }
   const int64_t groups = (c->stage_cells + CELL_GROUP - 1) / CELL_GROUP;
-  XB_CUDA(cudaMalloc(&c->stage, sizeof(double) * groups * CELL_GROUP * BLOCK_ALL));
-  XB_CUDA(cudaMemset(c->stage, 0, sizeof(double) * groups * CELL_GROUP * BLOCK_ALL));
+  XB_CUDA(cudaMalloc(&c->stage, sizeof(double) * groups * CELL_GROUP * STAGE_CELL));
+  XB_CUDA(cudaMemset(c->stage, 0, sizeof(double) * groups * CELL_GROUP * STAGE_CELL));
   c->nbins = (int64_t)(g.nzl + 2) * g.plane * 8;
   XB_CUDA(cudaMalloc(&c->hist, sizeof(int32_t) * c->nbins));
   XB_CUDA(cudaMalloc(&c->cursor, sizeof(int32_t) * c->nbins));

@@ -190,13 +190,14 @@ struct xb_ctx {
   double* coef = nullptr;   // blocked [tile][k][t], see stencil.cuh
   int64_t coef_elems = 0;
   bool coef_valid = false;
-  int deposit_variant = 0;  // 0: fused DMMA kernel (default), 3: same at 2 CTAs / SM, 2: round-1 DMMA pipeline, 1: scalar FMA (cross-checks)
+  int deposit_variant = 0;  // 0: fused DMMA kernel, variant tiles (default); cross-checks: 4 same with the fold in shared memory, 3 no role split, 2 round-1 DMMA pipeline, 1 scalar FMA
   bool fused_attr_set = false, deposit_attr_set = false, esirkepov_attr_set = false, cap_attr_set = false;  // per context = per device
   int cap_variant = 0;  // eccapfim particle pass: 0 CTA task machine (default), 1 thread per particle (cross-check)
   int esirkepov_variant = 0;  // 0: DMMA cell blocks + gather (default), 1: per-particle global reductions (cross-check)
   // deposit staging (cell blocks)
   double* stage = nullptr;
   int64_t stage_cells = 0;
+  bool stage_tiles = false;  // what the last deposit_cells left there: variant tiles (STAGE_CELL doubles per cell) or folded cell blocks (BLOCK_ALL)
   int batch_planes = 0;  // 0: the staging area holds the whole slab; P > 0: batches of P planes through P + 2 staging planes
   // Krylov workspace
   std::vector<double*> V;  // restart + 1 basis vectors (ghosted)

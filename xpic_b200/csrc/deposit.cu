@@ -523,6 +523,115 @@ __global__ void __launch_bounds__(128) k_gather_rows(Grid g, GatherArgs a, doubl
   }
 }
 
+// ---- the same from variant tiles (deposit.cuh): the production path ----------------------------------------------
+// row gq of a tile: 64 contiguous bytes, two 256-bit loads (whole sectors although the threads of a warp read different cells)
+// The cells around a node in the staging area stage[plane][tile][cell of the plane][64]: offset d - 1 in {-1, 0, 1} per axis
+struct Around {
+  int xs[3], ys[3], ps[3];
+  bool zok[3];  // false: the plane lies outside an open z boundary and contributes nothing
+};
+
+template <bool OPENZ>
+__device__ __forceinline__ Around cells_around(const Grid& g, const GatherArgs& a, int x, int y, int zl)
+{
+  Around r;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int o = d - 1, zz = zl - o;
+    r.xs[d] = wrapi(x - o, g.nx);
+    r.ys[d] = wrapi(y - o, g.ny);
+    r.ps[d] = a.wrap ? wrapi(zz, g.nzl) : zz - a.base;
+    r.zok[d] = !OPENZ || !(g.z0 + zz < 0 || g.z0 + zz >= g.nz);
+  }
+  return r;
+}
+
+// row gq of a tile: 64 contiguous bytes, two 256-bit loads (whole sectors although the threads of a warp read different cells)
+__device__ __forceinline__ void tile_row(const double* __restrict__ p, double (&r)[8])
+{
+  asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3]) : "l"(p));
+  asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r[4]), "=d"(r[5]), "=d"(r[6]), "=d"(r[7]) : "l"(p + 4));
+}
+
+// window coordinates (i, j, k) of position p of component c
+__host__ __device__ constexpr int pos_i(int c, int p) { return p % win_n(c, 0); }
+__host__ __device__ constexpr int pos_j(int c, int p) { return (p / win_n(c, 0)) % win_n(c, 1); }
+__host__ __device__ constexpr int pos_k(int c, int p) { return p / (win_n(c, 0) * win_n(c, 1)); }
+
+// One thread per node and component pair, as k_gather_rows; the contributions of a cell arrive as the 8 x 8 tiles of
+// the pair's (ox, oy, oz) variants: tile row gq sits at window position corner_pos(C1, gq, bit of C1), column t2 at
+// corner_pos(C2, t2, bit of C2).  Every index below is a compile-time constant; the sum runs in a fixed
+// order (variant, tile row, column), so the result does not depend on the decomposition.
+template <int C1, int C2, bool OPENZ>
+__global__ void __launch_bounds__(128, 3) k_gather_tiles(Grid g, GatherArgs a, double* __restrict__ coef, int accumulate)
+{
+  const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (node >= g.plane * a.nplanes) return;
+  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = a.zl0 + (int)(node / g.plane);
+  constexpr int SL = C1 * 3 + C2, NS = pair_size(C1, C2), NZ = dep(SL, 2) ? 2 : 1;
+  const Around ar = cells_around<OPENZ>(g, a, x, y, zl);
+  double acc[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+#pragma unroll
+  for (int oz = 0; oz < NZ; ++oz)
+#pragma unroll
+    for (int v = 0; v < nvar(SL); ++v) {
+      const int tile = tile_id(SL, v, oz);
+#pragma unroll
+      for (int gq = 0; gq < 8; ++gq) {
+        // the cell whose window point p1 (tile row gq of this variant) is this node
+        const int p1 = corner_pos(C1, gq, vbit(SL, v, C1, oz));
+        const int o1x = win_lo(C1, 0) + pos_i(C1, p1), o1y = win_lo(C1, 1) + pos_j(C1, p1), o1z = win_lo(C1, 2) + pos_k(C1, p1);
+        const double* p = a.stage + (((int64_t)ar.ps[o1z + 1] * NTILE + tile) * g.plane + (ar.ys[o1y + 1] * g.nx + ar.xs[o1x + 1])) * 64 + gq * 8;
+        double r[8];
+        tile_row(p, r);
+#pragma unroll
+        for (int t2 = 0; t2 < 8; ++t2) {
+          const int p2 = corner_pos(C2, t2, vbit(SL, v, C2, oz));
+          const double val = (OPENZ && !ar.zok[o1z + 1]) ? 0.0 : r[t2];
+          acc[coef_slot(C1, C2, win_lo(C2, 0) + pos_i(C2, p2) - o1x, win_lo(C2, 1) + pos_j(C2, p2) - o1y, win_lo(C2, 2) + pos_k(C2, p2) - o1z) - pair_base(C1, C2)] += val;
+        }
+      }
+    }
+  const TileMap tm = make_tilemap(g.nx, g.ny, g.nzl);
+  double* out = coef + tm.node_offset(x, y, zl) + (int64_t)pair_base(C1, C2) * TILE_NODES;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    if (accumulate)
+      out[s * TILE_NODES] += acc[s];
+    else
+      out[s * TILE_NODES] = acc[s];
+  }
+}
+
+__global__ void k_gather_current_tiles(Grid g, GatherArgs a, double* __restrict__ sort_currI, double* __restrict__ sim_currI)
+{
+  const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (node >= g.plane * a.nplanes) return;
+  const int x = (int)(node % g.nx), y = (int)((node / g.nx) % g.ny), zl = a.zl0 + (int)(node / g.plane);
+  const Around ar = cells_around<true>(g, a, x, y, zl);
+  double r[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+      for (int gq = 0; gq < 8; ++gq) {
+        const int p = corner_pos(c, gq, o);
+        const int ox = win_lo(c, 0) + pos_i(c, p), oy = win_lo(c, 1) + pos_j(c, p), oz = win_lo(c, 2) + pos_k(c, p);
+        const double* t = a.stage + (((int64_t)ar.ps[oz + 1] * NTILE + TILE_CUR) * g.plane + (ar.ys[oy + 1] * g.nx + ar.xs[ox + 1])) * 64;
+        const double val = __ldg(t + (gq * 4 + c) * 2 + o);
+        r[c] += (g.open_z && !ar.zok[oz + 1]) ? 0.0 : val;
+      }
+  const int64_t o = g.vidx(x, y, zl, 0);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    sort_currI[o + c] = r[c];
+    sim_currI[o + c] += r[c];
+  }
+}
+
 // currI of one sort at the owned nodes; also accumulated into the simulation's total current
 __global__ void k_gather_current(Grid g, GatherArgs a, double* __restrict__ sort_currI, double* __restrict__ sim_currI)
 {
@@ -576,7 +685,12 @@ template <int C1, int C2>
 static int launch_gather(xb_ctx* c, const GatherArgs& ga, int accumulate)
 {
   const int blocks = (int)((c->g.plane * ga.nplanes + 127) / 128);
-  XB_LAUNCH(c, (k_gather_rows<C1, C2>), blocks, 128, 0, c->g, ga, c->coef, accumulate);
+  if (c->stage_tiles && c->g.open_z)
+    XB_LAUNCH(c, (k_gather_tiles<C1, C2, true>), blocks, 128, 0, c->g, ga, c->coef, accumulate);
+  else if (c->stage_tiles)
+    XB_LAUNCH(c, (k_gather_tiles<C1, C2, false>), blocks, 128, 0, c->g, ga, c->coef, accumulate);
+  else
+    XB_LAUNCH(c, (k_gather_rows<C1, C2>), blocks, 128, 0, c->g, ga, c->coef, accumulate);
   return 0;
 }
 
@@ -591,9 +705,12 @@ int deposit_ghost_cells(xb_ctx* c, Species& s, int64_t stage_lo, int64_t stage_h
 int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* bin_start, int64_t bin_cell0, int64_t ncells, int64_t stage_cell0,
                   int zshift, double** rec, int64_t rec_stride, int64_t nparticles, int zl_first)
 {
-  // variants (xb_set_option(ctx, 0, v)): 0 fused warp-specialised DMMA kernel, 3 fused kernel without role split,
-  // 2 round-1 pipeline (field records in HBM + two-warp DMMA kernel), 1 scalar-FMA cell blocks
+  // variants (xb_set_option(ctx, 0, v)): 0 fused warp-specialised DMMA kernel, variant tiles in the staging area (the
+  // production path); cross-checks, all with folded cell blocks in the staging area: 4 the same kernel with the fold in
+  // shared memory, 3 fused kernel without role split, 2 round-1 pipeline (field records in HBM + two-warp DMMA kernel),
+  // 1 scalar-FMA cell blocks
   const int variant = c->deposit_variant;
+  c->stage_tiles = variant == 0;
   DepositArgs a;
   for (int k = 0; k < 6; ++k) a.p[k] = p[k];
   a.bin_start = bin_start;
@@ -612,7 +729,7 @@ int deposit_cells(xb_ctx* c, Species& s, const double* const* p, const int32_t* 
   if ((a.stage_cell0 % CELL_GROUP) != 0) XB_FAIL("deposit: plane size must be a multiple of the staging group in multi-rank runs");
   const Grid& g = c->g;
   const int zl_off = zl_first;
-  if (variant == 0 || variant == 3) return launch_cell_moments(c, a, zl_off, variant);
+  if (variant == 0 || variant == 3 || variant == 4) return launch_cell_moments(c, a, zl_off, variant);
 
   const bool use_mma = variant == 2;
   const size_t smem = sizeof(double) * (use_mma ? MMA_SMEM_PER_CELL : DEP_SMEM_PER_WARP) * CELL_GROUP;
@@ -649,7 +766,10 @@ static int gather_rows_of(xb_ctx* c, Species& s, const GatherArgs& ga, int acc)
   XB_CHECK((launch_gather<2, 1>(c, ga, acc)));
   XB_CHECK((launch_gather<2, 2>(c, ga, acc)));
   const int blocks = (int)((c->g.plane * ga.nplanes + 127) / 128);
-  XB_LAUNCH(c, k_gather_current, blocks, 128, 0, c->g, ga, s.currI, c->currI);
+  if (c->stage_tiles)
+    XB_LAUNCH(c, k_gather_current_tiles, blocks, 128, 0, c->g, ga, s.currI, c->currI);
+  else
+    XB_LAUNCH(c, k_gather_current, blocks, 128, 0, c->g, ga, s.currI, c->currI);
   return 0;
 }
 
@@ -664,7 +784,7 @@ static int boundary_blocks_begin(xb_ctx* c)
   }
   XB_CUDA(cudaEventRecord(c->blocks_ready, c->stream));
   XB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->blocks_ready, 0));
-  const size_t per_plane = (size_t)g.plane * BLOCK_ALL;  // doubles; g.plane is a multiple of CELL_GROUP (deposit_cells checks)
+  const size_t per_plane = (size_t)g.plane * (c->stage_tiles ? STAGE_CELL : BLOCK_ALL);  // doubles; g.plane is a multiple of CELL_GROUP (deposit_cells checks)
   auto plane = [&](int sp) { return c->stage + (size_t)sp * per_plane; };
   const bool down = !(g.open_z && g.rank == 0), up = !(g.open_z && g.rank == g.nranks - 1);
   const size_t bytes = sizeof(double) * per_plane;

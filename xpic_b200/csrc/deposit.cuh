@@ -15,6 +15,68 @@ __device__ __forceinline__ int block_pos(int c, int t, int ox, int oy, int oz)
   return ((oz + k) * 2 + j) * 2 + i;
 }
 
+// ---- accumulator bookkeeping (compile time) -----------------------------------------------------
+// slot sl = c1 * 3 + c2.  A slot's 8 x 8 tile moves inside the cell's 12 x 12 block with the octant bit of
+// its row component (along that component's staggered axis) and of its column component.  Variants over
+// (ox, oy) live in registers; oz is sequenced (see the header comment).
+__host__ __device__ constexpr bool dep(int sl, int a) { return sl / 3 == a || sl % 3 == a; }
+__host__ __device__ constexpr int nvar(int sl) { return (dep(sl, 0) ? 2 : 1) * (dep(sl, 1) ? 2 : 1); }
+__host__ __device__ constexpr int vbase(int sl)
+{
+  int b = 0;
+  for (int i = 0; i < sl; ++i) b += nvar(i);
+  return b;
+}
+// register variant of slot sl for a particle of (ox, oy) = (oxy & 1, oxy >> 1)
+__host__ __device__ constexpr int vidx(int sl, int oxy)
+{
+  return vbase(sl) + (dep(sl, 0) ? (oxy & 1) : 0) + (dep(sl, 1) ? (oxy >> 1) * (dep(sl, 0) ? 2 : 1) : 0);
+}
+// octant bit of axis a that register variant v of slot sl stands for (oz: the sequenced bit)
+__host__ __device__ constexpr int vbit(int sl, int v, int a, int oz)
+{
+  if (a == 2) return oz;
+  if (!dep(sl, a)) return 0;
+  if (a == 0) return v & 1;
+  return dep(sl, 0) ? (v >> 1) : (v & 1);
+}
+constexpr int NMAT = vbase(8) + nvar(8);  // 21 accumulator pairs
+static_assert(NMAT == 21, "21 (slot, ox, oy) variants");
+// currents: component c moves with its own octant bit only: X 2 variants, Y 2, Z 1 (sequenced)
+__host__ __device__ constexpr int cbase(int c) { return c == 0 ? 0 : (c == 1 ? 2 : 4); }
+__host__ __device__ constexpr int cidx(int c, int oxy) { return cbase(c) + (c == 0 ? (oxy & 1) : (c == 1 ? (oxy >> 1) : 0)); }
+constexpr int NCUR = 5;
+
+
+// ---- variant tiles: the staging layout of the production kernel (moments_fused.cu, k_cell_moments_ws<.., true>) ----
+// The accumulator pairs leave the registers as they are: one 8 x 8 tile per (slot, ox, oy, oz) variant, element
+// (row corner gq, column corners 2 q, 2 q + 1) in lane 4 gq + q as a double2.  Tiles 0..20: the 21 register variants at
+// oz = 0 (for a slot without a Z component: its only tile); 21..29: the nine z-dependent variants at oz = 1; 30: the
+// currents, lane (gq, q = c) = (sum at octant bit 0, at octant bit 1) of component c at corner gq.  Overlapping
+// variants are summed by the row gather (k_gather_tiles), not in shared memory.
+// stage[plane][tile][cell of the plane][lane] in double2 units: a consumer warp stores 512 contiguous bytes per tile (whole
+// sectors; 16-byte pieces interleaved over the four cells of a group were measured at 0.2 TB/s), the gather threads of a
+// warp read 64-byte rows of x-consecutive cells, 512 bytes apart.  A plane is contiguous (the exchange of boundary planes).
+__host__ __device__ constexpr int zbase(int sl)  // z-dependent variants below slot sl
+{
+  int b = 0;
+  for (int i = 0; i < sl; ++i) b += dep(i, 2) ? nvar(i) : 0;
+  return b;
+}
+// tile of variant v of slot sl at octant bit oz
+__host__ __device__ constexpr int tile_id(int sl, int v, int oz) { return (oz && dep(sl, 2)) ? NMAT + zbase(sl) + v : vbase(sl) + v; }
+constexpr int TILE_CUR = NMAT + zbase(9);
+constexpr int NTILE = TILE_CUR + 1;
+static_assert(NTILE == 31 && NTILE * 64 == STAGE_CELL, "31 tiles of 64 doubles per cell");
+// window position of corner t of component c at octant bit o of the component's staggered axis (block_pos, compile time)
+__host__ __device__ constexpr int corner_pos(int c, int t, int o)
+{
+  const int i = t & 1, j = (t >> 1) & 1, k = t >> 2;
+  if (c == 0) return (k * 2 + j) * 3 + (o + i);
+  if (c == 1) return (k * 3 + (o + j)) * 2 + i;
+  return ((o + k) * 2 + j) * 2 + i;
+}
+
 struct DepositArgs {
   const double* p[6];
   const int32_t* bin_start;
@@ -32,6 +94,6 @@ struct DepositArgs {
 
 
 // moments_fused.cu: the production pass 1 (field records, DMMA cell blocks, staging write in one kernel)
-int launch_cell_moments(xb_ctx* c, const DepositArgs& a, int zl_off, int occupancy);
+int launch_cell_moments(xb_ctx* c, const DepositArgs& a, int zl_off, int form);
 
 }  // namespace xb

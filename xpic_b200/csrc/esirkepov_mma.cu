@@ -245,7 +245,7 @@ static int run_cells(xb_ctx* c, Species& s)
   }
   const int groups_x = (g.nx + TILE_CELLS - 1) / TILE_CELLS;
   const int64_t groups = (int64_t)groups_x * g.ny * g.nzl;
-  if (groups * EBLOCK * ECELLS > ((c->stage_cells + CELL_GROUP - 1) / CELL_GROUP) * (int64_t)CELL_GROUP * BLOCK_ALL)
+  if (groups * EBLOCK * ECELLS > ((c->stage_cells + CELL_GROUP - 1) / CELL_GROUP) * (int64_t)CELL_GROUP * STAGE_CELL)
     XB_FAIL("esirkepov: staging area too small");
   EsirkepovArgs a;
   double** p = s.p[s.cur];

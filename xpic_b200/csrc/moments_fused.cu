@@ -50,38 +50,6 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// ---- accumulator bookkeeping (compile time) -----------------------------------------------------
-// slot sl = c1 * 3 + c2.  A slot's 8 x 8 tile moves inside the cell's 12 x 12 block with the octant bit of
-// its row component (along that component's staggered axis) and of its column component.  Variants over
-// (ox, oy) live in registers; oz is sequenced (see the header comment).
-__host__ __device__ constexpr bool dep(int sl, int a) { return sl / 3 == a || sl % 3 == a; }
-__host__ __device__ constexpr int nvar(int sl) { return (dep(sl, 0) ? 2 : 1) * (dep(sl, 1) ? 2 : 1); }
-__host__ __device__ constexpr int vbase(int sl)
-{
-  int b = 0;
-  for (int i = 0; i < sl; ++i) b += nvar(i);
-  return b;
-}
-// register variant of slot sl for a particle of (ox, oy) = (oxy & 1, oxy >> 1)
-__host__ __device__ constexpr int vidx(int sl, int oxy)
-{
-  return vbase(sl) + (dep(sl, 0) ? (oxy & 1) : 0) + (dep(sl, 1) ? (oxy >> 1) * (dep(sl, 0) ? 2 : 1) : 0);
-}
-// octant bit of axis a that register variant v of slot sl stands for (oz: the sequenced bit)
-__host__ __device__ constexpr int vbit(int sl, int v, int a, int oz)
-{
-  if (a == 2) return oz;
-  if (!dep(sl, a)) return 0;
-  if (a == 0) return v & 1;
-  return dep(sl, 0) ? (v >> 1) : (v & 1);
-}
-constexpr int NMAT = vbase(8) + nvar(8);  // 21 accumulator pairs
-static_assert(NMAT == 21, "21 (slot, ox, oy) variants");
-// currents: component c moves with its own octant bit only: X 2 variants, Y 2, Z 1 (sequenced)
-__host__ __device__ constexpr int cbase(int c) { return c == 0 ? 0 : (c == 1 ? 2 : 4); }
-__host__ __device__ constexpr int cidx(int c, int oxy) { return cbase(c) + (c == 0 ? (oxy & 1) : (c == 1 ? (oxy >> 1) : 0)); }
-constexpr int NCUR = 5;
-
 struct Lane {
   int gq, q;
   int wofs[3];     // offset (doubles) of this lane's (wn, ws) chunk of axis a inside a record
@@ -420,6 +388,10 @@ constexpr int WS_META = 16;  // ints per stage: [0..8] bin boundaries of the cel
 // per cell: block, WS_STAGES x 32 records, zero record, B tile, meta, 2 x WS_STAGES mbarriers (+ pad to 16 k + 8)
 constexpr int WS_CELL = FM_BLOCK + WS_STAGES * FM_CHUNK * FM_REC + FM_REC + FM_TILE + WS_STAGES * WS_META / 2 + 2 * WS_STAGES + 12;
 static_assert(WS_CELL % 16 == 8, "write-out reads the four blocks of a CTA without bank conflicts");
+// TILES form: no cell block in shared memory (the accumulators go to the staging area as variant tiles, deposit.cuh)
+constexpr int WT_CELL = WS_CELL - FM_BLOCK;
+template <bool TILES>
+__host__ __device__ constexpr int ws_cell() { return TILES ? WT_CELL : WS_CELL; }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
@@ -443,15 +415,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity, unsigned ba
 }
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// PROF: per-role phase clocks (clock64 deltas summed over the warps of a role) into prof[16]; XPIC_WS_PROF=1 selects it.
+//   consumer: 0 wait for a stage, 1 rank-1 updates, 2 folds, 3 barriers, 4 write-out, 5 total
+//   producer: 8 hand-out + barrier, 9 cell header (bins, B tile), 10 particle loads -> stage free, 11 records, 12 total
+template <bool PROF, bool TILES>
 __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, DepositArgs a, const double* __restrict__ B, double* __restrict__ stage, int zl_off,
-                                                                   int groups, unsigned backoff_ns, int* __restrict__ next_group)
+                                                                   int groups, unsigned backoff_ns, int* __restrict__ next_group, unsigned long long* __restrict__ prof)
 {
+  long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = 0, pt0 = 0;
+  auto tick = [&](int k) {
+    if (PROF) {
+      const long long t = clock64();
+      pc[k] += t - pt;
+      pt = t;
+    }
+  };
+  if (PROF) pt = pt0 = clock64();
   extern __shared__ __align__(16) double smem[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = wid & 3;
   const bool producer = wid >= 4;
-  double* block = smem + (size_t)slot * WS_CELL;
-  double* recs = block + FM_BLOCK;
+  double* block = smem + (size_t)slot * ws_cell<TILES>();
+  double* recs = block + (TILES ? 0 : FM_BLOCK);
   double* zero_rec = recs + WS_STAGES * FM_CHUNK * FM_REC;
   double* Bt = zero_rec + FM_REC;
   int* meta = reinterpret_cast<int*>(Bt + FM_TILE);
@@ -463,9 +448,11 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
   __shared__ int sched[2];
 
   if (!producer) {
-    double2* b2 = reinterpret_cast<double2*>(block);
+    if (!TILES) {
+      double2* b2 = reinterpret_cast<double2*>(block);
 #pragma unroll
-    for (int k = 0; k < FM_BLOCK / 64; ++k) b2[k * 32 + lane] = make_double2(0.0, 0.0);
+      for (int k = 0; k < FM_BLOCK / 64; ++k) b2[k * 32 + lane] = make_double2(0.0, 0.0);
+    }
     if (lane < FM_REC) zero_rec[lane] = 0.0;
     if (lane == 0) {
 #pragma unroll
@@ -491,6 +478,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
     for (int round = 0;; ++round) {
       if (wid == 4 && lane == 0) sched[round & 1] = atomicAdd(next_group, 1);
       asm volatile("bar.sync 2, 128;" ::: "memory");  // the four producer warps
+      tick(0);
       const int grp = sched[round & 1];
       const int64_t cell_local = (int64_t)grp * FM_CELLS + slot;
       if (grp >= groups || cell_local >= a.ncells) {
@@ -501,7 +489,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
         if (lane == 0) {
           mt[9] = 0;
           mt[10] = 0;
-          mt[11] = 1 | 2 | (grp >= groups ? 4 : 0);
+          mt[11] = 1 | 2 | 8 | (grp >= groups ? 4 : 0);  // 8: no cell behind this slot (nothing is stored)
           mt[12] = grp;
         }
         if (lane < 9) mt[lane] = 0;
@@ -528,6 +516,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
       for (int j = 0; j < 3; ++j)
         if (te[j] >= 0) Bt[lane + 32 * j] = tl[j];
       __syncwarp();
+      tick(1);
       // the lower node of the cell as the reference's floor() gives it for every particle binned here
       const double cd[3] = {(double)cx, (double)cy, (double)(zl + g.z0 - a.zshift)};
       const int ci[3] = {cx, cy, zl};
@@ -543,6 +532,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
         }
         const int st = seq & (WS_STAGES - 1);
         mbar_wait(empty + st, ((seq / WS_STAGES) & 1) ^ 1, backoff_ns);  // the consumer has released this stage
+        tick(2);
         if (lane < n) {
           Weights w;
           const double xn[3] = {to_cells(pin[0], g.dx, g.inv_dx, g.exact_inv & 1), to_cells(pin[1], g.dy, g.inv_dy, g.exact_inv & 2),
@@ -597,16 +587,140 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
         }
         __syncwarp();  // every lane's records are written before lane 0 publishes the stage
         if (lane == 0) mbar_arrive(full + st);
+        tick(3);
         base += n;
         first = false;
         ++seq;
       } while (base < p1);
+    }
+    if (PROF && lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(prof + 8 + k, (unsigned long long)pc[k]);
+      atomicAdd(prof + 12, (unsigned long long)(clock64() - pt0));
     }
     return;
   }
 
   // ================================== consumer: rank-1 updates, folds, write-out =====================
   asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+  if constexpr (TILES) {
+    // ---- variant tiles: the accumulators are stored as they stand; no cell block, no fold, no barrier between consumers ----
+    Lane L;
+    L.gq = lane >> 2;
+    L.q = lane & 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      L.wofs[c] = 2 * (c + 4 * ((L.gq >> c) & 1));
+      L.rowpos[c] = L.colpos[c] = 0;
+    }
+    double2* const stage2 = reinterpret_cast<double2*>(stage) + lane;
+    const int64_t tstride = g.plane * 32;  // double2 units between two tiles of a staging plane
+    int seq = 0;
+    for (;;) {
+      double acc[NMAT][2], cur[NCUR], curz0 = 0.0;
+#pragma unroll
+      for (int v = 0; v < NMAT; ++v) acc[v][0] = acc[v][1] = 0.0;
+#pragma unroll
+      for (int v = 0; v < NCUR; ++v) cur[v] = 0.0;
+      int oct = 0, grp = 0;
+      int32_t bsc = 0, oend = 0;
+      bool zdone = false, stop = false, nocell = false;
+      double2* out2 = stage2;
+      // the z-dependent variants (and the Z current) of the lower half of the cell leave; the registers restart at zero
+      auto flush_z = [&]() {
+#pragma unroll
+        for (int sl = 0; sl < 9; ++sl) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            if (!dep(sl, 2) || v >= nvar(sl)) continue;
+            const int k = vbase(sl) + v;
+            out2[tile_id(sl, v, 0) * tstride] = make_double2(acc[k][0], acc[k][1]);
+            acc[k][0] = acc[k][1] = 0.0;
+          }
+        }
+        curz0 = cur[cbase(2)];
+        cur[cbase(2)] = 0.0;
+      };
+      while (true) {
+        const int st = seq & (WS_STAGES - 1);
+        mbar_wait(full + st, (seq / WS_STAGES) & 1, backoff_ns);  // the producer has published this stage
+        tick(0);
+        const int* mt = meta + st * WS_META;
+        const int32_t base = mt[9];
+        const int n = mt[10], flags = mt[11];
+        if (flags & 1) {
+          bsc = lane < 9 ? mt[lane] : 0;
+          oend = __shfl_sync(0xffffffffu, bsc, 1);
+          grp = mt[12];
+          stop = (flags & 4) != 0;
+          nocell = (flags & 8) != 0;
+          // staging cell -> [plane][tile][cell of the plane][lane]
+          const int64_t sc = a.stage_cell0 + (int64_t)grp * CELL_GROUP + slot, pz = sc / g.plane;
+          out2 = stage2 + (pz * (NTILE - 1) * g.plane + sc) * 32;
+        }
+        const double* rbuf = recs + st * FM_CHUNK * FM_REC;
+        int32_t pos = base;
+        const int32_t cend = base + n;
+        while (pos < cend) {
+          while (oend <= pos) {  // the octant's particles are exhausted (warp-uniform)
+            ++oct;
+            oend = __shfl_sync(0xffffffffu, bsc, oct + 1);
+          }
+          if (oct >= 4 && !zdone) {  // first particle with oz = 1
+            tick(1);
+            flush_z();
+            zdone = true;
+            tick(2);
+          }
+          const int32_t seg_end = min(oend, cend);
+          const double* r0 = rbuf + (pos - base) * FM_REC;
+          const int cnt = seg_end - pos;
+          switch (oct & 3) {
+            case 0: octant_segment<0>(r0, zero_rec, cnt, L, acc, cur); break;
+            case 1: octant_segment<1>(r0, zero_rec, cnt, L, acc, cur); break;
+            case 2: octant_segment<2>(r0, zero_rec, cnt, L, acc, cur); break;
+            default: octant_segment<3>(r0, zero_rec, cnt, L, acc, cur); break;
+          }
+          pos = seg_end;
+        }
+        __syncwarp();  // every lane is done with the stage before lane 0 releases it
+        if (lane == 0) mbar_arrive(empty + st);
+        tick(1);
+        ++seq;
+        if (flags & 2) break;
+      }
+      if (stop) break;
+      if (nocell) continue;
+      if (!zdone) flush_z();  // no particle in the upper half (or none at all): the oz = 1 tiles below are zeros
+#pragma unroll
+      for (int sl = 0; sl < 9; ++sl) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if (v >= nvar(sl)) continue;
+          const int k = vbase(sl) + v;
+          out2[tile_id(sl, v, 1) * tstride] = make_double2(acc[k][0], acc[k][1]);
+        }
+      }
+      {
+        // currents: the four particles of a row are summed; lane (gq, q = c) keeps component c at octant bits 0 and 1
+        double v[6] = {cur[0], cur[1], cur[2], cur[3], curz0, cur[4]};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          v[k] += __shfl_xor_sync(0xffffffffu, v[k], 1);
+          v[k] += __shfl_xor_sync(0xffffffffu, v[k], 2);
+        }
+        const double2 o = L.q == 0 ? make_double2(v[0], v[1]) : (L.q == 1 ? make_double2(v[2], v[3]) : (L.q == 2 ? make_double2(v[4], v[5]) : make_double2(0.0, 0.0)));
+        out2[TILE_CUR * tstride] = o;
+      }
+      tick(2);
+    }
+    if (PROF && lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) atomicAdd(prof + k, (unsigned long long)pc[k]);
+      atomicAdd(prof + 5, (unsigned long long)(clock64() - pt0));
+    }
+    return;
+  }
   Lane L;
   L.gq = lane >> 2;
   L.q = lane & 3;
@@ -632,6 +746,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
       while (true) {
         const int st = seq & (WS_STAGES - 1);
         mbar_wait(full + st, (seq / WS_STAGES) & 1, backoff_ns);  // the producer has published this stage
+        tick(0);
         const int* mt = meta + st * WS_META;
         const int32_t base = mt[9];
         const int n = mt[10], flags = mt[11];
@@ -651,8 +766,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
             oend = __shfl_sync(0xffffffffu, bsc, oct + 1);
           }
           if (oct >= 4 && !zdone) {  // first particle with oz = 1: the z-dependent slots change their place
+            tick(1);
             fold<true, 0>(block, L, acc, cur);
             zdone = true;
+            tick(2);
           }
           const int32_t seg_end = min(oend, cend);
           const double* r0 = rbuf + (pos - base) * FM_REC;
@@ -667,6 +784,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
         }
         __syncwarp();  // every lane is done with the stage before lane 0 releases it
         if (lane == 0) mbar_arrive(empty + st);
+        tick(1);
         ++seq;
         if (flags & 2) break;
       }
@@ -677,9 +795,11 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
           fold<true, 0>(block, L, acc, cur);
         fold<false, 0>(block, L, acc, cur);
       }
+      tick(2);
     }
     if (stop) break;  // every slot of the CTA receives the stop message in the same round
     consumer_barrier();
+    tick(3);
     // coalesced write-out of the CTA's four blocks, stage[group][entry][cell % 4]: one consumer thread per entry
     // reads it from the four blocks, stores 32 contiguous bytes and leaves zeros behind for the next round
     double* out = stage + ((a.stage_cell0 / CELL_GROUP) + grp) * (int64_t)(BLOCK_ALL * CELL_GROUP);
@@ -694,7 +814,14 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
       o2[0] = make_double2(v[0], v[1]);
       o2[1] = make_double2(v[2], v[3]);
     }
+    tick(4);
     consumer_barrier();
+    tick(3);
+  }
+  if (PROF && lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) atomicAdd(prof + k, (unsigned long long)pc[k]);
+    atomicAdd(prof + 5, (unsigned long long)(clock64() - pt0));
   }
 }
 
@@ -702,24 +829,55 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
 
 int launch_cell_moments(xb_ctx* c, const DepositArgs& a, int zl_off, int form)
 {
-  const size_t smem = sizeof(double) * FM_CELL * FM_CELLS, smem_ws = sizeof(double) * WS_CELL * FM_CELLS;
+  // form 0: warp-specialised, variant tiles (the default); 4: warp-specialised, cell blocks folded in shared memory;
+  // 3: every warp does everything for its cell (cell blocks)
+  const size_t smem = sizeof(double) * FM_CELL * FM_CELLS, smem_ws = sizeof(double) * WS_CELL * FM_CELLS, smem_wt = sizeof(double) * WT_CELL * FM_CELLS;
   if (!c->fused_attr_set) {
     XB_CUDA(cudaFuncSetAttribute(k_cell_moments<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    XB_CUDA(cudaFuncSetAttribute(k_cell_moments_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+    XB_CUDA(cudaFuncSetAttribute((k_cell_moments_ws<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+    XB_CUDA(cudaFuncSetAttribute((k_cell_moments_ws<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+    XB_CUDA(cudaFuncSetAttribute((k_cell_moments_ws<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt));
+    XB_CUDA(cudaFuncSetAttribute((k_cell_moments_ws<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt));
     c->fused_attr_set = true;
   }
   const int groups = (int)((a.ncells + FM_CELLS - 1) / FM_CELLS);
   if (c->sm_count == 0) XB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
-  const int resident = c->sm_count * (form == 0 ? 2 : 3);  // persistent CTAs: one wave
+  const int resident = c->sm_count * (form == 3 ? 3 : 2);  // persistent CTAs: one wave
   const int grid = groups < resident ? groups : resident;
   if (grid < 1) return 0;
-  if (form == 0) {  // warp-specialised: producers (records) and consumers (DMMA) in one CTA, groups handed out dynamically
-    if (!c->work_counter) XB_CUDA(cudaMalloc(&c->work_counter, sizeof(int)));
-    XB_CUDA(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
-    XB_LAUNCH(c, k_cell_moments_ws, grid, WS_THREADS, smem_ws, c->g, a, c->B, c->stage, zl_off, groups, (unsigned)c->ws_backoff_ns, c->work_counter);
-  }
-  else            // every warp does everything for its cell
+  if (form == 3) {
     XB_LAUNCH(c, k_cell_moments<3>, grid, FM_THREADS, smem, c->g, a, c->B, c->stage, zl_off, groups);
+    return 0;
+  }
+  // producers (records) and consumers (DMMA) in one CTA, groups handed out dynamically
+  const bool tiles = form == 0;
+  if (!c->work_counter) XB_CUDA(cudaMalloc(&c->work_counter, sizeof(int)));
+  XB_CUDA(cudaMemsetAsync(c->work_counter, 0, sizeof(int), c->stream));
+  static const bool prof = getenv("XPIC_WS_PROF") != nullptr;  // debugging aid: phase clocks of the two roles on stderr
+  unsigned long long* d = nullptr;
+  if (prof) {
+    XB_CUDA(cudaMalloc(&d, 16 * sizeof(unsigned long long)));
+    XB_CUDA(cudaMemsetAsync(d, 0, 16 * sizeof(unsigned long long), c->stream));
+  }
+  const unsigned backoff = (unsigned)c->ws_backoff_ns;
+  if (tiles && prof)
+    XB_LAUNCH(c, (k_cell_moments_ws<true, true>), grid, WS_THREADS, smem_wt, c->g, a, c->B, c->stage, zl_off, groups, backoff, c->work_counter, d);
+  else if (tiles)
+    XB_LAUNCH(c, (k_cell_moments_ws<false, true>), grid, WS_THREADS, smem_wt, c->g, a, c->B, c->stage, zl_off, groups, backoff, c->work_counter, d);
+  else if (prof)
+    XB_LAUNCH(c, (k_cell_moments_ws<true, false>), grid, WS_THREADS, smem_ws, c->g, a, c->B, c->stage, zl_off, groups, backoff, c->work_counter, d);
+  else
+    XB_LAUNCH(c, (k_cell_moments_ws<false, false>), grid, WS_THREADS, smem_ws, c->g, a, c->B, c->stage, zl_off, groups, backoff, c->work_counter, d);
+  if (prof) {
+    unsigned long long h[16];
+    XB_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    XB_CUDA(cudaStreamSynchronize(c->stream));
+    XB_CUDA(cudaFree(d));
+    const double nc = 4.0 * grid, cells = (double)a.ncells;
+    fprintf(stderr, "k_cell_moments_ws<tiles = %d> phase clocks, cycles per consumer warp (%d CTAs, %.0f cells, %.1f cells per warp):\n", (int)tiles, grid, cells, cells / nc);
+    fprintf(stderr, "  consumer: wait %.0f  mma %.0f  fold / store %.0f  barrier %.0f  write-out %.0f  total %.0f\n", h[0] / nc, h[1] / nc, h[2] / nc, h[3] / nc, h[4] / nc, h[5] / nc);
+    fprintf(stderr, "  producer: hand-out %.0f  header %.0f  loads+wait %.0f  records %.0f  total %.0f\n", h[8] / nc, h[9] / nc, h[10] / nc, h[11] / nc, h[12] / nc);
+  }
   return 0;
 }
 

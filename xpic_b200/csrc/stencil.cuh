@@ -91,6 +91,7 @@ __host__ __device__ inline TileMap make_tilemap(int nx, int ny, int nzl)
 constexpr int BLOCK_MAT = 9 * 144;  // 1296 mass-matrix entries of one cell (ecsim/simulation.cpp:488)
 constexpr int BLOCK_CUR = 36;       // 3 x 12 current partials of one cell
 constexpr int BLOCK_ALL = BLOCK_MAT + BLOCK_CUR;
+constexpr int STAGE_CELL = 31 * 64;  // doubles of staging per cell in the variant-tile layout (deposit.cuh); the staging area is sized for it
 constexpr int CELL_GROUP = 4;       // cells per CTA and per staging group: stage[group][entry][cell % 4] (32-byte runs)
 
 }  // namespace xb
