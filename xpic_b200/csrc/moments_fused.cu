@@ -107,6 +107,50 @@ __device__ __forceinline__ void octant_segment(const double* __restrict__ r0, co
   }
 }
 
+// ---- the same for the variant-tile consumer, software-pipelined across groups AND octant segments: the raw operands of
+// the next group of the round (the next four records, whichever octant they belong to) are requested as soon as the
+// products of this group are formed, and arrive underneath its nine DMMAs.
+struct Raw {
+  double2 w[3], f[6];
+};
+__device__ __forceinline__ void load_raw(Raw& r, const double* __restrict__ rec, const Lane& L)
+{
+#pragma unroll
+  for (int a = 0; a < 3; ++a) r.w[a] = ld2(rec + L.wofs[a]);
+  r.f[0] = ld2(rec + 6);
+#pragma unroll
+  for (int k = 1; k < 6; ++k) r.f[k] = ld2(rec + 12 + 2 * k);
+}
+// live: this lane's particle belongs to the group (a padded lane holds some other record of the round: its weights are
+// replaced by zeros, so it adds exact zeros as the all-zero record of octant_segment does)
+template <int OXY>
+__device__ __forceinline__ void group_update(Raw& raw, bool live, const double* __restrict__ next_rec, const Lane& L, double (&acc)[NMAT][2],
+                                             double (&cur)[NCUR])
+{
+  double s[3];
+  s[0] = (raw.w[2].x * raw.w[1].x) * raw.w[0].y;
+  s[1] = (raw.w[2].x * raw.w[1].y) * raw.w[0].x;
+  s[2] = (raw.w[2].y * raw.w[1].x) * raw.w[0].x;
+  if (!live) s[0] = s[1] = s[2] = 0.0;
+  const double al[9] = {raw.f[0].x, raw.f[0].y, raw.f[1].x, raw.f[1].y, raw.f[2].x, raw.f[2].y, raw.f[3].x, raw.f[3].y, raw.f[4].x};
+  const double ip[3] = {raw.f[4].y, raw.f[5].x, raw.f[5].y};
+  double p[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) p[k] = al[k] * s[k % 3];
+  // the current is a matrix-vector product (see octant_segment); done first: the raw record is dead from here on
+#pragma unroll
+  for (int c1 = 0; c1 < 3; ++c1) cur[cidx(c1, OXY)] += s[c1] * ip[c1];
+  load_raw(raw, next_rec, L);
+#pragma unroll
+  for (int c1 = 0; c1 < 3; ++c1) {
+#pragma unroll
+    for (int c2 = 0; c2 < 3; ++c2) {
+      const int v = vidx(c1 * 3 + c2, OXY);
+      dmma(acc[v][0], acc[v][1], s[c1], p[c1 * 3 + c2]);
+    }
+  }
+}
+
 // fold register variants into the cell block.  ZDEP: the z-dependent slots (row or column component Z) and
 // the Z current, at octant bit OZ, and clear them; else the five z-independent slots and the X, Y currents.
 template <bool ZDEP, int OZ>
@@ -383,13 +427,16 @@ __global__ void __launch_bounds__(FM_THREADS, MINB) k_cell_moments(Grid g, Depos
 // also across cells, so the consumer never sees HBM latency.  Two CTAs per SM: 8 + 8 warps.
 // =====================================================================================================
 constexpr int WS_THREADS = 256;
-constexpr int WS_STAGES = 2;
+constexpr int WS_STAGES = 2;   // ring depth with the cell block in shared memory
+constexpr int WT_STAGES = 2;   // ... of the variant-tile form
+constexpr int WT_PBUF = 2 * 6 * FM_CHUNK;  // two rounds of particles (SoA) requested ahead with cp.async (and a second B tile)
 constexpr int WS_META = 16;  // ints per stage: [0..8] bin boundaries of the cell (first round only), [9] base, [10] n, [11] 1 = first | 2 = last | 4 = stop, [12] group
 // per cell: block, WS_STAGES x 32 records, zero record, B tile, meta, 2 x WS_STAGES mbarriers (+ pad to 16 k + 8)
 constexpr int WS_CELL = FM_BLOCK + WS_STAGES * FM_CHUNK * FM_REC + FM_REC + FM_TILE + WS_STAGES * WS_META / 2 + 2 * WS_STAGES + 12;
 static_assert(WS_CELL % 16 == 8, "write-out reads the four blocks of a CTA without bank conflicts");
 // TILES form: no cell block in shared memory (the accumulators go to the staging area as variant tiles, deposit.cuh)
-constexpr int WT_CELL = WS_CELL - FM_BLOCK;
+constexpr int WT_CELL = WT_STAGES * FM_CHUNK * FM_REC + FM_REC + 2 * FM_TILE + WT_PBUF + WT_STAGES * WS_META / 2 + 2 * WT_STAGES + 12;
+static_assert(WT_CELL % 2 == 0, "16-byte alignment of the records");
 template <bool TILES>
 __host__ __device__ constexpr int ws_cell() { return TILES ? WT_CELL : WS_CELL; }
 
@@ -435,13 +482,15 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = wid & 3;
   const bool producer = wid >= 4;
+  constexpr int NST = TILES ? WT_STAGES : WS_STAGES;
   double* block = smem + (size_t)slot * ws_cell<TILES>();
   double* recs = block + (TILES ? 0 : FM_BLOCK);
-  double* zero_rec = recs + WS_STAGES * FM_CHUNK * FM_REC;
+  double* zero_rec = recs + NST * FM_CHUNK * FM_REC;
   double* Bt = zero_rec + FM_REC;
-  int* meta = reinterpret_cast<int*>(Bt + FM_TILE);
-  uint64_t* full = reinterpret_cast<uint64_t*>(meta + WS_STAGES * WS_META);
-  uint64_t* empty = full + WS_STAGES;
+  double* pbuf = Bt + 2 * FM_TILE;  // TILES only
+  int* meta = reinterpret_cast<int*>(TILES ? pbuf + WT_PBUF : Bt + FM_TILE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(meta + NST * WS_META);
+  uint64_t* empty = full + NST;
   // Work is handed out dynamically: producer warp 4 takes the next group of four cells from a global counter and
   // tells the other producers through these two slots (one named barrier per round); the consumers read the group
   // from the first message of the round.  A CTA that starts late -- another kernel held its SM -- simply takes less.
@@ -456,7 +505,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
     if (lane < FM_REC) zero_rec[lane] = 0.0;
     if (lane == 0) {
 #pragma unroll
-      for (int st = 0; st < WS_STAGES; ++st) {
+      for (int st = 0; st < NST; ++st) {
         mbar_init(full + st, 1);
         mbar_init(empty + st, 1);
       }
@@ -466,7 +515,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
 
   if (producer) {
     // ================================ producer: records =============================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    if (TILES)
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    else
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
     int te[3];  // the three B-tile elements this lane fetches per cell: e = lane + 32 j -> (x, y, z, c)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -475,6 +527,182 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
     }
     const double f = a.f_beta;
     int seq = 0;
+    if constexpr (TILES) {
+      // ---- producer of the variant-tile form: everything it needs from HBM is requested one step ahead with cp.async
+      // (no registers are tied up while the data travels).  The bin table and the B tile of the NEXT cell travel while the
+      // records of this cell are formed, the particles of the NEXT round (of this cell, or the first of the next cell) while
+      // the records of this round are formed.  One commit group per round; wait_group 1 = everything but the newest.
+      auto cp8 = [&](double* dst, const double* src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+      };
+      auto round_size = [&](int32_t base, int32_t b4, int32_t p1) {
+        // a round ends at the oz = 0 / oz = 1 boundary when that keeps it within 32 particles: no octant is split
+        return (base < b4 && b4 - base <= FM_CHUNK) ? b4 - base : min(FM_CHUNK, p1 - base);
+      };
+      const int ncells = (int)a.ncells, plane = (int)g.plane;  // launch_cell_moments checks the range
+      // bin boundaries of the 8 octants (register) and the B tile (into tile buffer tb)
+      auto request_header = [&](int cell_local, int tb) {
+        const int pl = cell_local / plane, rem = cell_local - pl * plane;
+        const int cy = rem / g.nx, cx = rem - cy * g.nx, zl = pl + zl_off;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (te[j] < 0) continue;
+          const int x = wrap1(cx - 1 + (te[j] & 3), g.nx), y = wrap1(cy - 1 + ((te[j] >> 2) & 3), g.ny), z = zl - 1 + ((te[j] >> 4) & 3);
+          cp8(Bt + tb * FM_TILE + lane + 32 * j, &B[g.vidx(x, y, z, te[j] >> 6)]);
+        }
+        return lane < 9 ? __ldg(a.bin_start + ((a.bin_cell0 + (int64_t)cell_local) << 3) + lane) : 0;
+      };
+      // Work is handed out cell by cell from a global counter, to every producer warp on its own (the variant tiles of a
+      // cell are stored by its consumer alone: nothing ties the four cells of a CTA together any more).  The counter is
+      // read two cells ahead, so that its latency is never waited for.
+      auto take = [&]() { return lane == 0 ? atomicAdd(next_group, 1) : 0; };
+      auto request_particles = [&](int32_t base, int n, int pb) {
+        if (lane < n) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) cp8(pbuf + (pb * 6 + k) * FM_CHUNK + lane, a.p[k] + base + lane);
+        }
+      };
+      // first round of the cell with bin table bs: its size; its particles are requested into particle buffer pb
+      auto request_first_round = [&](int32_t bs, int pb) {
+        const int32_t p0 = __shfl_sync(0xffffffffu, bs, 0), p1 = __shfl_sync(0xffffffffu, bs, 8), b4 = __shfl_sync(0xffffffffu, bs, 4);
+        const int n = round_size(p0, b4, p1);
+        request_particles(p0, n, pb);
+        return n;
+      };
+      auto commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
+      int cell = __shfl_sync(0xffffffffu, take(), 0), cell_n = __shfl_sync(0xffffffffu, take(), 0), taken = take();
+      int32_t bs = 0, bs_n = 0;
+      int n = 0, pb = 0, tb = 0;  // size of the round whose particles are in buffer pb; tile buffer of the current cell
+      if (cell < ncells) {
+        bs = request_header(cell, tb);
+        n = request_first_round(bs, pb);
+      }
+      commit();
+      for (;;) {
+        tick(0);
+        const bool valid_n = cell_n < ncells;
+        if (valid_n) bs_n = request_header(cell_n, tb ^ 1);  // joins the commit group of the next request of particles
+        if (cell >= ncells) {
+          // no cell left: the stop message
+          const int st = seq & (NST - 1);
+          mbar_wait(empty + st, ((seq / NST) & 1) ^ 1, backoff_ns);
+          int* mt = meta + st * WS_META;
+          if (lane == 0) {
+            mt[9] = 0;
+            mt[10] = 0;
+            mt[11] = 1 | 2 | 4;
+            mt[12] = cell;
+          }
+          if (lane < 9) mt[lane] = 0;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full + st);
+          break;
+        }
+        {
+          const int pl = cell / plane, rem = cell - pl * plane;
+          const int cy = rem / g.nx, cx = rem - cy * g.nx, zl = pl + zl_off;
+          const int32_t p0 = __shfl_sync(0xffffffffu, bs, 0), p1 = __shfl_sync(0xffffffffu, bs, 8), b4 = __shfl_sync(0xffffffffu, bs, 4);
+          const double* Btc = Bt + tb * FM_TILE;
+          tick(1);
+          // the lower node of the cell as the reference's floor() gives it for every particle binned here
+          const double cd[3] = {(double)cx, (double)cy, (double)(zl + g.z0 - a.zshift)};
+          const int ci[3] = {cx, cy, zl};
+          int32_t base = p0;
+          bool first = true;
+          do {
+            // the particles of the next round: of this cell, or the first round of the next cell
+            const int32_t nb = base + n;
+            int n_next = 0;
+            if (nb < p1) {
+              n_next = round_size(nb, b4, p1);
+              request_particles(nb, n_next, pb ^ 1);
+            }
+            else if (valid_n)
+              n_next = request_first_round(bs_n, pb ^ 1);
+            commit();
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this round's particles (and this cell's B tile) have arrived
+            __syncwarp();                                         // ... those of the other lanes as well (the tile)
+            const int st = seq & (NST - 1);
+            mbar_wait(empty + st, ((seq / NST) & 1) ^ 1, backoff_ns);  // the consumer has released this stage
+            tick(2);
+            if (lane < n) {
+              double pin[6];
+#pragma unroll
+              for (int k = 0; k < 6; ++k) pin[k] = pbuf[(pb * 6 + k) * FM_CHUNK + lane];
+              Weights w;
+              const double xn[3] = {to_cells(pin[0], g.dx, g.inv_dx, g.exact_inv & 1), to_cells(pin[1], g.dy, g.inv_dy, g.exact_inv & 2),
+                                    to_cells(pin[2], g.dz, g.inv_dz, g.exact_inv & 4)};
+#pragma unroll
+              for (int ax = 0; ax < 3; ++ax) {
+                // src/impls/ecsim/particles.cpp:76-105 with floor(xn) = cell and floor(xn - 0.5) = cell - 1 + octant bit;
+                // xn - cell and xn - 0.5 are exact, so the bit is (xn - cell >= 0.5), the one the key pass binned by
+                const double fx = xn[ax] - cd[ax];
+                const int o = fx >= 0.5 ? 1 : 0;
+                w.in[ax] = ci[ax];
+                w.is[ax] = ci[ax] - 1 + o;
+                w.wn[ax][1] = fx;
+                w.wn[ax][0] = 1 - w.wn[ax][1];
+                w.ws[ax][1] = (xn[ax] - 0.5) - (cd[ax] - 1.0 + (double)o);
+                w.ws[ax][0] = 1 - w.ws[ax][1];
+              }
+              const TileIndex t = tile_index<1>(w, cx, cy, zl);
+              double Bp[3], b[3];
+              gather_B_tile<1>(Btc, w, t, Bp);
+              const double v[3] = {pin[3], pin[4], pin[5]};
+#pragma unroll
+              for (int c = 0; c < 3; ++c) b[c] = Bp[c] * f;
+              double vxb[3];
+              cross3(v, b, vxb);
+              const double vb = dot3(v, b), b2 = dot3(b, b);
+              const double cI = a.num_I / (1. + b2);  // q mpw / (1 + b^2)
+              double ip[3];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) ip[c] = cI * (v[c] + vxb[c] + vb * b[c]);
+              const double Ap = a.num_A / (1 + b2);   // dt^2/2 mpw q^2 / m / (1 + b^2)
+              double2* r = reinterpret_cast<double2*>(recs + (st * FM_CHUNK + lane) * FM_REC);
+#pragma unroll
+              for (int ax = 0; ax < 3; ++ax) {
+                r[ax] = make_double2(w.wn[ax][0], w.ws[ax][0]);
+                r[4 + ax] = make_double2(w.wn[ax][1], w.ws[ax][1]);
+              }
+              r[3] = make_double2(Ap * (1.0 + b[0] * b[0]), Ap * (+b[2] + b[0] * b[1]));
+              r[7] = make_double2(Ap * (-b[1] + b[0] * b[2]), Ap * (-b[2] + b[1] * b[0]));
+              r[8] = make_double2(Ap * (1.0 + b[1] * b[1]), Ap * (+b[0] + b[1] * b[2]));
+              r[9] = make_double2(Ap * (+b[1] + b[2] * b[0]), Ap * (-b[0] + b[2] * b[1]));
+              r[10] = make_double2(Ap * (1.0 + b[2] * b[2]), ip[0]);
+              r[11] = make_double2(ip[1], ip[2]);
+            }
+            int* mt = meta + st * WS_META;
+            if (first && lane < 9) mt[lane] = bs;
+            if (lane == 0) {
+              mt[9] = base;
+              mt[10] = n;
+              mt[11] = (first ? 1 : 0) | (nb >= p1 ? 2 : 0);
+              mt[12] = cell;
+            }
+            __syncwarp();  // every lane's records are written (and its tile gathers done) before lane 0 publishes the stage
+            if (lane == 0) mbar_arrive(full + st);
+            tick(3);
+            base = nb;
+            first = false;
+            ++seq;
+            n = n_next;
+            pb ^= 1;
+          } while (base < p1);
+          tb ^= 1;
+        }
+        cell = cell_n;
+        bs = bs_n;
+        cell_n = __shfl_sync(0xffffffffu, taken, 0);
+        taken = take();
+      }
+      if (PROF && lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(prof + 8 + k, (unsigned long long)pc[k]);
+        atomicAdd(prof + 12, (unsigned long long)(clock64() - pt0));
+      }
+      return;
+    }
     for (int round = 0;; ++round) {
       if (wid == 4 && lane == 0) sched[round & 1] = atomicAdd(next_group, 1);
       asm volatile("bar.sync 2, 128;" ::: "memory");  // the four producer warps
@@ -483,8 +711,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
       const int64_t cell_local = (int64_t)grp * FM_CELLS + slot;
       if (grp >= groups || cell_local >= a.ncells) {
         // nothing to produce for this slot: an empty message keeps the consumer in step (and stops it after the last group)
-        const int st = seq & (WS_STAGES - 1);
-        mbar_wait(empty + st, ((seq / WS_STAGES) & 1) ^ 1, backoff_ns);
+        const int st = seq & (NST - 1);
+        mbar_wait(empty + st, ((seq / NST) & 1) ^ 1, backoff_ns);
         int* mt = meta + st * WS_META;
         if (lane == 0) {
           mt[9] = 0;
@@ -530,8 +758,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
 #pragma unroll
           for (int k = 0; k < 6; ++k) pin[k] = __ldg(a.p[k] + base + lane);
         }
-        const int st = seq & (WS_STAGES - 1);
-        mbar_wait(empty + st, ((seq / WS_STAGES) & 1) ^ 1, backoff_ns);  // the consumer has released this stage
+        const int st = seq & (NST - 1);
+        mbar_wait(empty + st, ((seq / NST) & 1) ^ 1, backoff_ns);  // the consumer has released this stage
         tick(2);
         if (lane < n) {
           Weights w;
@@ -602,7 +830,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
   }
 
   // ================================== consumer: rank-1 updates, folds, write-out =====================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+  if (TILES)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+  else
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
   if constexpr (TILES) {
     // ---- variant tiles: the accumulators are stored as they stand; no cell block, no fold, no barrier between consumers ----
     Lane L;
@@ -613,8 +844,6 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
       L.wofs[c] = 2 * (c + 4 * ((L.gq >> c) & 1));
       L.rowpos[c] = L.colpos[c] = 0;
     }
-    double2* const stage2 = reinterpret_cast<double2*>(stage) + lane;
-    const int64_t tstride = g.plane * 32;  // double2 units between two tiles of a staging plane
     int seq = 0;
     for (;;) {
       double acc[NMAT][2], cur[NCUR], curz0 = 0.0;
@@ -622,12 +851,18 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
       for (int v = 0; v < NMAT; ++v) acc[v][0] = acc[v][1] = 0.0;
 #pragma unroll
       for (int v = 0; v < NCUR; ++v) cur[v] = 0.0;
-      int oct = 0, grp = 0;
-      int32_t bsc = 0, oend = 0;
-      bool zdone = false, stop = false, nocell = false;
-      double2* out2 = stage2;
+      int grp = 0;
+      int32_t bsc = 0;
+      bool zdone = false;
+      int flags = 0;  // of the last message: a stop / no-cell message is the first and the last of its "cell"
       // the z-dependent variants (and the Z current) of the lower half of the cell leave; the registers restart at zero
+      auto tile0 = [&]() -> double2* {  // staging cell -> [plane][tile][cell of the plane][lane]
+        const int sc = (int)a.stage_cell0 + grp, pz = sc / (int)g.plane;  // grp: the cell of the launch; launch_cell_moments checks the range
+        return reinterpret_cast<double2*>(stage) + ((int64_t)pz * (NTILE - 1) * g.plane + sc) * 32 + lane;
+      };
       auto flush_z = [&]() {
+        double2* out2 = tile0();
+        const int64_t tstride = g.plane * 32;  // double2 units between two tiles of a staging plane
 #pragma unroll
         for (int sl = 0; sl < 9; ++sl) {
 #pragma unroll
@@ -642,46 +877,50 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
         cur[cbase(2)] = 0.0;
       };
       while (true) {
-        const int st = seq & (WS_STAGES - 1);
-        mbar_wait(full + st, (seq / WS_STAGES) & 1, backoff_ns);  // the producer has published this stage
+        const int st = seq & (NST - 1);
+        mbar_wait(full + st, (seq / NST) & 1, backoff_ns);  // the producer has published this stage
         tick(0);
         const int* mt = meta + st * WS_META;
         const int32_t base = mt[9];
-        const int n = mt[10], flags = mt[11];
+        const int n = mt[10];
+        flags = mt[11];
         if (flags & 1) {
-          bsc = lane < 9 ? mt[lane] : 0;
-          oend = __shfl_sync(0xffffffffu, bsc, 1);
+          bsc = lane < 9 ? mt[lane] : 0;  // bin boundaries of the cell's octants
           grp = mt[12];
-          stop = (flags & 4) != 0;
-          nocell = (flags & 8) != 0;
-          // staging cell -> [plane][tile][cell of the plane][lane]
-          const int64_t sc = a.stage_cell0 + (int64_t)grp * CELL_GROUP + slot, pz = sc / g.plane;
-          out2 = stage2 + (pz * (NTILE - 1) * g.plane + sc) * 32;
         }
         const double* rbuf = recs + st * FM_CHUNK * FM_REC;
-        int32_t pos = base;
-        const int32_t cend = base + n;
-        while (pos < cend) {
-          while (oend <= pos) {  // the octant's particles are exhausted (warp-uniform)
-            ++oct;
-            oend = __shfl_sync(0xffffffffu, bsc, oct + 1);
+        if (n > 0) {
+          Raw raw;
+          load_raw(raw, rbuf + min(L.q, n - 1) * FM_REC, L);
+          int e0 = 0;  // the groups of octant o cover the records [e0, e1) of the round
+          for (int oz = 0; oz < 2; ++oz) {
+            if (oz == 1) {
+              if (e0 >= n) break;
+              if (!zdone) {  // first particle with oz = 1
+                tick(1);
+                flush_z();
+                zdone = true;
+                tick(2);
+              }
+            }
+            int32_t ev[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ev[k] = __shfl_sync(0xffffffffu, bsc, oz * 4 + k + 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e1 = min(max(ev[k] - base, 0), n);
+              for (int pos = e0; pos < e1; pos += 4) {
+                const int nxt = min(pos + 4, e1) + L.q;  // the next group: of this octant, or the first of the next non-empty one
+                const double* next_rec = rbuf + min(nxt, n - 1) * FM_REC;
+                const bool live = L.q < e1 - pos;
+                if (k == 0) group_update<0>(raw, live, next_rec, L, acc, cur);
+                if (k == 1) group_update<1>(raw, live, next_rec, L, acc, cur);
+                if (k == 2) group_update<2>(raw, live, next_rec, L, acc, cur);
+                if (k == 3) group_update<3>(raw, live, next_rec, L, acc, cur);
+              }
+              e0 = e1;
+            }
           }
-          if (oct >= 4 && !zdone) {  // first particle with oz = 1
-            tick(1);
-            flush_z();
-            zdone = true;
-            tick(2);
-          }
-          const int32_t seg_end = min(oend, cend);
-          const double* r0 = rbuf + (pos - base) * FM_REC;
-          const int cnt = seg_end - pos;
-          switch (oct & 3) {
-            case 0: octant_segment<0>(r0, zero_rec, cnt, L, acc, cur); break;
-            case 1: octant_segment<1>(r0, zero_rec, cnt, L, acc, cur); break;
-            case 2: octant_segment<2>(r0, zero_rec, cnt, L, acc, cur); break;
-            default: octant_segment<3>(r0, zero_rec, cnt, L, acc, cur); break;
-          }
-          pos = seg_end;
         }
         __syncwarp();  // every lane is done with the stage before lane 0 releases it
         if (lane == 0) mbar_arrive(empty + st);
@@ -689,9 +928,11 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
         ++seq;
         if (flags & 2) break;
       }
-      if (stop) break;
-      if (nocell) continue;
+      if (flags & 4) break;     // stop
+      if (flags & 8) continue;  // no cell behind this slot: nothing is stored
       if (!zdone) flush_z();  // no particle in the upper half (or none at all): the oz = 1 tiles below are zeros
+      double2* out2 = tile0();
+      const int64_t tstride = g.plane * 32;
 #pragma unroll
       for (int sl = 0; sl < 9; ++sl) {
 #pragma unroll
@@ -744,8 +985,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_cell_moments_ws(Grid g, Depos
       int32_t bsc = 0, oend = 0;
       bool zdone = false, any = false;
       while (true) {
-        const int st = seq & (WS_STAGES - 1);
-        mbar_wait(full + st, (seq / WS_STAGES) & 1, backoff_ns);  // the producer has published this stage
+        const int st = seq & (NST - 1);
+        mbar_wait(full + st, (seq / NST) & 1, backoff_ns);  // the producer has published this stage
         tick(0);
         const int* mt = meta + st * WS_META;
         const int32_t base = mt[9];
@@ -841,6 +1082,7 @@ int launch_cell_moments(xb_ctx* c, const DepositArgs& a, int zl_off, int form)
     c->fused_attr_set = true;
   }
   const int groups = (int)((a.ncells + FM_CELLS - 1) / FM_CELLS);
+  if (a.stage_cell0 + a.ncells + FM_CELLS >= (int64_t)1 << 31) XB_FAIL("deposit: more than 2^31 staging cells");
   if (c->sm_count == 0) XB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
   const int resident = c->sm_count * (form == 3 ? 3 : 2);  // persistent CTAs: one wave
   const int grid = groups < resident ? groups : resident;
