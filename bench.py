@@ -259,7 +259,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_source = "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    precond = env_int("XPIC_BENCH_PRECOND", 6)
+    precond = env_int("XPIC_BENCH_PRECOND", 8)
     codes = {"ecsim": X.ECSIM, "ecsimcorr": X.ECSIMCORR, "eccapfim": X.ECCAPFIM}
 
     def make_sim(scheme_name):
@@ -397,8 +397,8 @@ def main():
         kernels = [
             {"name": "re-binning inside the step (move + key pass, scan, scatter" + (", migration" if world > 1 else "") + ")", "ms": t_sort, "bound": "hbm",
              "achieved": 152.0 * npart_rank / t_sort / 1e6, "unit": "GB/s", "algorithmic": "152 B/particle: read r,v + key, write r,v"},
-            {"name": "moments (fused field records + DMMA cell blocks, row gather)", "ms": t_dep, "bound": "fp64", "achieved": 1200.0 * npart_rank / t_dep / 1e9,
-             "unit": "TFLOP/s", "algorithmic": "1200 flop/particle (576 + 24 FMA); HBM: 48 B/particle in, 10.6 KB/cell staged out and in, 3 KB/cell rows out"},
+            {"name": "moments (k_cell_moments_ws: field records + DMMA accumulator tiles; k_gather_tiles: rows)", "ms": t_dep, "bound": "fp64", "achieved": 1200.0 * npart_rank / t_dep / 1e9,
+             "unit": "TFLOP/s", "algorithmic": "1200 flop/particle (576 + 24 FMA); HBM: 48 B/particle in, 15.9 KB/cell of accumulator tiles staged out and in, 3 KB/cell rows out"},
             {"name": "second push (tile-staged gather + Boris)", "ms": t_push, "bound": "hbm", "achieved": 72.0 * npart_rank / t_push / 1e6, "unit": "GB/s",
              "algorithmic": "72 B/particle: read r,v, write v"},
             {"name": "operator SpMV (all launches of a step)", "ms": spmv_ms / args.steps, "bound": "hbm", "achieved": achieved, "unit": "GB/s",
@@ -413,13 +413,13 @@ def main():
         kernels[1]["peak"] = fp64_peak
         kernels[1]["peak_source"] = fp64_src
         stage_sum = {"first_push": t_sort + t_dep, "advance_fields_spmv_plus_precond": spmv_ms / args.steps + t_pre, "second_push": t_push,
-                     "moments_parts": {"cell_blocks_owned_planes": per["moments_cells"][0], "cell_blocks_ghost_planes_incl_wait": per["moments_ghost"][0],
+                     "moments_parts": {"accumulator_tiles_owned_planes": per["moments_cells"][0], "boundary_plane_exchange_left_over": per["moments_ghost"][0],
                                        "row_gather": per["moments_rows"][0]},
                      "sort_parts": {"move_and_key_pass": per["sort_keys"][0], "migration_counts_payloads_arrivals": per["sort_migrate"][0],
                                     "scan_and_scatter": per["sort_scatter"][0]}}
         # by time the moment deposition is the dominant kernel family of the step (the SpMV above is the kernel
         # BASELINE.json's metric names); its roof is the fp64 tensor / FMA rate, not HBM
-        roofline_dominant = {"kernel": "moment deposition: k_cell_moments (fp64 DMMA m8n8k4, fused field records) + k_gather_rows", "bound": "tensor",
+        roofline_dominant = {"kernel": "moment deposition: k_cell_moments_ws (fp64 DMMA m8n8k4, fused field records, accumulator tiles) + k_gather_tiles", "bound": "tensor",
                              "achieved": kernels[1]["achieved"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": kernels[1]["achieved"] / fp64_peak,
                              "traffic": None, "peak_source": fp64_src, "avg_launch_ms": t_dep,
                              "algorithmic_flops_per_launch": 1200.0 * npart_rank, "share_of_step": t_dep / (ms / args.steps) if ms else None,

@@ -1,6 +1,7 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "deposit or batched or staging" 2>&1 | tail -3
-XPIC_DEPOSIT_VARIANTS=0,4 python tools/profile_deposit.py > gpurun_out/prof_tiles.json 2> gpurun_out/prof_tiles.err
-cat gpurun_out/prof_tiles.json
-XPIC_WS_PROF=1 XPIC_DEPOSIT_VARIANTS=0 python tools/profile_deposit.py > gpurun_out/prof_ws.json 2> gpurun_out/prof_ws.err
-tail -3 gpurun_out/prof_ws.err
+python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/r02_final_bench_n1.json 2> gpurun_out/r02_final_bench_n1.err
+tail -c 600 gpurun_out/r02_final_bench_n1.json
+XPIC_PROFILE_RANGE=1 XPIC_BENCH_PRECOND=8 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r02_final_launches.csv python tools/profile_step.py 2 > gpurun_out/ncu_launches.log 2>&1
+tail -2 gpurun_out/ncu_launches.log
+XPIC_DEPOSIT_VARIANTS=0 ncu --set full --clock-control none --import-source on -k regex:"k_cell_moments_ws|k_gather_tiles" -s 30 -c 3 -o gpurun_out/r02_final_moments python tools/profile_deposit.py > gpurun_out/ncu_tiles.log 2>&1
+tail -3 gpurun_out/ncu_tiles.log
