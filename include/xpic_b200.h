@@ -182,9 +182,11 @@ int xb_spmv_bench(xb_ctx* ctx, int32_t op, int32_t reps, double* ms_per_spmv);
  * MatSetValuesCOO sums into matL (src/impls/ecsim/simulation.cpp:359,366). */
 int xb_operator_download(xb_ctx* ctx, double* coef);
 int xb_operator_upload(xb_ctx* ctx, const double* coef);
-/* Kernel variant switches for cross-checks: what = 0 selects the cell-block kernel of the moment
- * deposition (value 0: fused warp-specialised fp64 tensor-core kernel, default; 3: fused kernel without role split;
- * 2: round-1 pipeline with field records in HBM; 1: scalar FMA); what = 1 the Esirkepov deposit
+/* Kernel variant switches for cross-checks: what = 0 selects the first pass of the moment
+ * deposition (value 0: fused warp-specialised fp64 tensor-core kernel whose accumulator tiles are summed by the row
+ * gather, default; the others stage the reference's 9 x 12 x 12 cell blocks: 4 the same kernel with the fold in shared
+ * memory, 3: fused kernel without role split; 2: round-1 pipeline with field records in HBM; 1: scalar FMA);
+ * what = 1 the Esirkepov deposit
  * of ecsimcorr (0: atomic-free DMMA cell blocks, default; 1: per-particle global fp64 reductions);
  * what = 2: canonical particle order inside every bin after a sort when ids are not tracked
  * (1: runs are bit-reproducible, costs one more pass over the particles; 0, default: keep the order
