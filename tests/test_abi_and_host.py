@@ -90,3 +90,17 @@ def test_slab_ranges_tile_the_box():
                     assert X.owner_rank(k, nz, nranks) == r
                 z += nzl
             assert z == nz
+
+
+def test_accumulator_tile_map_matches_particle_footprint():
+    """The compile-time map of the moment deposition's accumulator tiles (csrc/deposit.cuh: tile element -> node and
+    stencil slot, used by k_gather_tiles) against the footprint of a particle as the reference deposits it
+    (src/impls/ecsim/particles.cpp:119-171), for every component pair, octant, tile row and column.  Host code only."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "xpic_b200", "_build", "tile_map_check")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "xpic_b200", "csrc"), "../_build/tile_map_check"], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "OK" in out.stdout

@@ -553,11 +553,6 @@ __device__ __forceinline__ void tile_row(const double* __restrict__ p, double (&
   asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r[4]), "=d"(r[5]), "=d"(r[6]), "=d"(r[7]) : "l"(p + 4));
 }
 
-// window coordinates (i, j, k) of position p of component c
-__host__ __device__ constexpr int pos_i(int c, int p) { return p % win_n(c, 0); }
-__host__ __device__ constexpr int pos_j(int c, int p) { return (p / win_n(c, 0)) % win_n(c, 1); }
-__host__ __device__ constexpr int pos_k(int c, int p) { return p / (win_n(c, 0) * win_n(c, 1)); }
-
 // One thread per node and component pair, as k_gather_rows; the contributions of a cell arrive as the 8 x 8 tiles of
 // the pair's (ox, oy, oz) variants: tile row gq sits at window position corner_pos(C1, gq, bit of C1), column t2 at
 // corner_pos(C2, t2, bit of C2).  Every index below is a compile-time constant; the sum runs in a fixed
@@ -580,17 +575,15 @@ __global__ void __launch_bounds__(128, 3) k_gather_tiles(Grid g, GatherArgs a, d
       const int tile = tile_id(SL, v, oz);
 #pragma unroll
       for (int gq = 0; gq < 8; ++gq) {
-        // the cell whose window point p1 (tile row gq of this variant) is this node
-        const int p1 = corner_pos(C1, gq, vbit(SL, v, C1, oz));
-        const int o1x = win_lo(C1, 0) + pos_i(C1, p1), o1y = win_lo(C1, 1) + pos_j(C1, p1), o1z = win_lo(C1, 2) + pos_k(C1, p1);
-        const double* p = a.stage + (((int64_t)ar.ps[o1z + 1] * NTILE + tile) * g.plane + (ar.ys[o1y + 1] * g.nx + ar.xs[o1x + 1])) * 64 + gq * 8;
+        // the cell whose window point (tile row gq of this variant) is this node
+        const TileTarget row = tile_target(C1, C2, v, oz, gq, 0);
+        const double* p = a.stage + (((int64_t)ar.ps[row.oz + 1] * NTILE + tile) * g.plane + (ar.ys[row.oy + 1] * g.nx + ar.xs[row.ox + 1])) * 64 + gq * 8;
         double r[8];
         tile_row(p, r);
 #pragma unroll
         for (int t2 = 0; t2 < 8; ++t2) {
-          const int p2 = corner_pos(C2, t2, vbit(SL, v, C2, oz));
-          const double val = (OPENZ && !ar.zok[o1z + 1]) ? 0.0 : r[t2];
-          acc[coef_slot(C1, C2, win_lo(C2, 0) + pos_i(C2, p2) - o1x, win_lo(C2, 1) + pos_j(C2, p2) - o1y, win_lo(C2, 2) + pos_k(C2, p2) - o1z) - pair_base(C1, C2)] += val;
+          const double val = (OPENZ && !ar.zok[row.oz + 1]) ? 0.0 : r[t2];
+          acc[tile_target(C1, C2, v, oz, gq, t2).slot - pair_base(C1, C2)] += val;
         }
       }
     }

@@ -77,6 +77,26 @@ __host__ __device__ constexpr int corner_pos(int c, int t, int o)
   return ((o + k) * 2 + j) * 2 + i;
 }
 
+// window coordinates (i, j, k) of position p of component c
+__host__ __device__ constexpr int pos_i(int c, int p) { return p % win_n(c, 0); }
+__host__ __device__ constexpr int pos_j(int c, int p) { return (p / win_n(c, 0)) % win_n(c, 1); }
+__host__ __device__ constexpr int pos_k(int c, int p) { return p / (win_n(c, 0) * win_n(c, 1)); }
+
+// Where element (row gq, column t2) of the tile of variant v, octant bit oz, of the component pair (c1, c2) belongs: the
+// row's node is the cell + (ox, oy, oz), the coefficient is stencil slot `slot` of that node (k_gather_tiles;
+// tests/host/tile_map_check.cu derives the same from the particle's footprint, src/impls/ecsim/particles.cpp:119-171)
+struct TileTarget {
+  int ox, oy, oz, slot;
+};
+__host__ __device__ constexpr TileTarget tile_target(int c1, int c2, int v, int oz, int gq, int t2)
+{
+  const int sl = c1 * 3 + c2;
+  const int p1 = corner_pos(c1, gq, vbit(sl, v, c1, oz)), p2 = corner_pos(c2, t2, vbit(sl, v, c2, oz));
+  const int o1x = win_lo(c1, 0) + pos_i(c1, p1), o1y = win_lo(c1, 1) + pos_j(c1, p1), o1z = win_lo(c1, 2) + pos_k(c1, p1);
+  return TileTarget{o1x, o1y, o1z,
+                    coef_slot(c1, c2, win_lo(c2, 0) + pos_i(c2, p2) - o1x, win_lo(c2, 1) + pos_j(c2, p2) - o1y, win_lo(c2, 2) + pos_k(c2, p2) - o1z)};
+}
+
 struct DepositArgs {
   const double* p[6];
   const int32_t* bin_start;
