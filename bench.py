@@ -417,11 +417,21 @@ def main():
                                        "row_gather": per["moments_rows"][0]},
                      "sort_parts": {"move_and_key_pass": per["sort_keys"][0], "migration_counts_payloads_arrivals": per["sort_migrate"][0],
                                     "scan_and_scatter": per["sort_scatter"][0]}}
+        moments_traffic = None  # DRAM bytes of the family from the committed ncu capture (same grid, one GPU), else null
+        mpath = os.path.join(ROOT, "profiles", "moments_traffic.json")
+        if os.path.exists(mpath) and world == 1:
+            try:
+                with open(mpath) as f:
+                    mj = json.load(f)
+                if tuple(mj.get("grid", [])) == tuple(n) and mj.get("ppc") == ppc:
+                    moments_traffic = mj.get("dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                pass
         # by time the moment deposition is the dominant kernel family of the step (the SpMV above is the kernel
         # BASELINE.json's metric names); its roof is the fp64 tensor / FMA rate, not HBM
         roofline_dominant = {"kernel": "moment deposition: k_cell_moments_ws (fp64 DMMA m8n8k4, fused field records, accumulator tiles) + k_gather_tiles", "bound": "tensor",
                              "achieved": kernels[1]["achieved"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": kernels[1]["achieved"] / fp64_peak,
-                             "traffic": None, "peak_source": fp64_src, "avg_launch_ms": t_dep,
+                             "traffic": moments_traffic, "peak_source": fp64_src, "avg_launch_ms": t_dep,
                              "algorithmic_flops_per_launch": 1200.0 * npart_rank, "share_of_step": t_dep / (ms / args.steps) if ms else None,
                              "hbm_view": {"algorithmic_bytes": 48.0 * npart_rank + 2976.0 * sim.ncl, "achieved_GBs": (48.0 * npart_rank + 2976.0 * sim.ncl) / t_dep / 1e6,
                                           "frac_of_hbm_peak": (48.0 * npart_rank + 2976.0 * sim.ncl) / t_dep / 1e6 / peak},
